@@ -1,0 +1,185 @@
+/*
+ * htool_b200.h — C ABI of the B200-native H-matrix product.
+ *
+ * This is the drop-in boundary. The reference (htool-ddm/htool, header-only C++) has no FFI of its
+ * own: its plugin API is the pair of abstract classes
+ *     htool::VirtualLocalToLocalOperator<T>   include/htool/distributed_operator/interfaces/virtual_local_to_local_operator.hpp:8-35
+ *     htool::VirtualGlobalToLocalOperator<T>  include/htool/distributed_operator/interfaces/virtual_global_to_local_operator.hpp:8-35
+ * (three virtuals each: add_vector_product :16, add_matrix_product_row_major :25,
+ * add_sub_matrix_product_to_local :33). The header-only shim in
+ * htool_b200/cpp/htool_b200/*.hpp subclasses them and forwards every call to the entry points
+ * below, so this file declares exactly what those virtuals (and the free functions
+ * add_hmatrix_vector_product / add_hmatrix_matrix_product,
+ * include/htool/hmatrix/linalg/add_hmatrix_vector_product.hpp:173,
+ * include/htool/hmatrix/linalg/add_hmatrix_matrix_product.hpp:176) need.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; scalars are passed by pointer so one ABI serves double (8 B)
+ *     and complex<double> (16 B, re/im interleaved like std::complex<double>);
+ *   - every function returns an int status (HTB_OK == 0); htb_last_error() gives the message of the
+ *     last failure on the calling thread. The reference itself never throws or returns codes — it logs
+ *     through htool::Logger and goes on (add_hmatrix_vector_product.hpp:112-115) — so the shim logs
+ *     the message through htool::Logger and returns;
+ *   - vectors are in CLUSTER numbering, relative to the root block's target/source offsets, exactly
+ *     like openmp_internal_add_hmatrix_vector_product (add_hmatrix_vector_product.hpp:107-170);
+ *   - a handle owns one CUDA stream + workspaces: one product in flight per handle (same contract as
+ *     every caller in the reference: one thread per MPI rank);
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     HTB_ERR_CUDA.
+ */
+#ifndef HTOOL_B200_H
+#define HTOOL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HTB_VERSION_MAJOR 0
+#define HTB_VERSION_MINOR 1
+
+/* status codes */
+enum {
+    HTB_OK              = 0,
+    HTB_ERR_INVALID     = 1, /* bad argument (null pointer, negative size, unknown trans, ...) */
+    HTB_ERR_UNSUPPORTED = 2, /* trans='T' with 'H' storage or trans='C' with 'S' storage: the reference logs
+                                "Operation is not supported" (add_hmatrix_vector_product.hpp:112-115) */
+    HTB_ERR_CUDA        = 3, /* CUDA runtime / driver failure, or no device */
+    HTB_ERR_NCCL        = 4,
+    HTB_ERR_ALLOC       = 5
+};
+
+/* coefficient type */
+enum { HTB_DOUBLE = 0,
+       HTB_COMPLEX_DOUBLE = 1 };
+
+/* where the in/out vectors of a product live */
+enum { HTB_MEM_HOST = 0,   /* pageable or pinned host memory: the library stages through pinned buffers */
+       HTB_MEM_DEVICE = 1 /* device pointers on the handle's device: no copies */ };
+
+/* htb_leaf.flags */
+#define HTB_LEAF_APPLY_TRANSPOSED_TOO 0x1 /* leaf is in get_leaves_from(...).second (hmatrix.hpp:264-266) */
+#define HTB_LEAF_DIAG_SYMMETRIC 0x2       /* dense leaf with get_symmetry()=='S' -> symv (add_hmatrix_vector_product.hpp:22-24) */
+#define HTB_LEAF_DIAG_HERMITIAN 0x4       /* dense leaf with get_symmetry()=='H' -> hemv (:43-45) */
+#define HTB_LEAF_UPLO_UPPER 0x8           /* get_UPLO()=='U' (else 'L') for the two flags above */
+
+/* One leaf of the block tree (hmatrix.hpp:29-50). Offsets are in cluster numbering and RELATIVE to the
+ * root block (target offset - root target offset), the same subtraction the reference does at
+ * add_hmatrix_vector_product.hpp:148-150. */
+typedef struct htb_leaf {
+    int32_t row_offset;
+    int32_t col_offset;
+    int32_t nb_rows; /* m */
+    int32_t nb_cols; /* n */
+    int32_t rank;    /* -1: dense leaf; r >= 0: low-rank leaf (r == 0 contributes nothing, add_lrmat_vector_product.hpp:11) */
+    int32_t flags;
+    const void *data0; /* dense: A, m x n column-major, lda = m (matrix.hpp:20-26). low rank: U, m x r column-major (lrmat.hpp:19) */
+    const void *data1; /* low rank: V, r x n column-major. dense: NULL */
+} htb_leaf;
+
+/* Everything htb_create needs; filled by htool_b200::flatten() from an htool::HMatrix. Host pointers
+ * only need to stay valid during htb_create: all coefficients are copied to the device once. */
+typedef struct htb_hmatrix_desc {
+    int32_t dtype;    /* HTB_DOUBLE | HTB_COMPLEX_DOUBLE */
+    int32_t nb_rows;  /* root target cluster size */
+    int32_t nb_cols;  /* root source cluster size */
+    int32_t row_offset; /* root target cluster offset (informational; used by the distributed entry points) */
+    int32_t col_offset; /* root source cluster offset */
+    char symmetry_for_leaves; /* root get_symmetry_for_leaves(): 'N' | 'S' | 'H' (hmatrix.hpp:217) */
+    char uplo_for_leaves;     /* 'N' | 'L' | 'U' */
+    char reserved[2];
+    int32_t device; /* CUDA device ordinal; -1 = the calling thread's current device */
+    int64_t nb_leaves;
+    const htb_leaf *leaves;
+} htb_hmatrix_desc;
+
+typedef struct htb_operator *htb_handle;
+
+/* Numbers describing the device-resident leaf store of a handle. */
+typedef struct htb_info {
+    int64_t nb_leaves, nb_dense_leaves, nb_low_rank_leaves, nb_leaves_applied_twice;
+    int64_t coefficients;         /* C  = sum_dense m*n + sum_lowrank r*(m+n)   */
+    int64_t coefficients_twice;   /* C_sym: coefficients of leaves applied twice */
+    int64_t store_bytes;          /* device bytes of packed coefficients (== sizeof(T)*C + padding) */
+    int64_t descriptor_bytes;     /* device bytes of work-item descriptors */
+    int64_t workspace_bytes;      /* device bytes of scratch (t vectors, staging) */
+    int32_t rank_min, rank_max;
+    int32_t dtype, device;
+    int32_t nb_rows, nb_cols;
+    int32_t nb_target_blocks, nb_source_blocks;
+    int32_t sm_count, reserved;
+} htb_info;
+
+/* ---- life cycle ---------------------------------------------------------------------------------- */
+
+/* Packs the leaves into the device-resident store (uploaded once per assembly). */
+int htb_create(const htb_hmatrix_desc *desc, htb_handle *out);
+int htb_destroy(htb_handle h);
+int htb_get_info(htb_handle h, htb_info *info);
+
+/* Launch on a caller-owned stream (a cudaStream_t passed as void*); NULL restores the handle's own
+ * stream. Lets a caller time with its own events / order against its own work. */
+int htb_set_stream(htb_handle h, void *cuda_stream);
+/* Blocks until every product enqueued on the handle has finished. */
+int htb_synchronize(htb_handle h);
+
+/* ---- products ------------------------------------------------------------------------------------- */
+
+/* out <- beta*out + alpha*op(H)*in, op = N | T | C. Replaces openmp_internal_add_hmatrix_vector_product
+ * (add_hmatrix_vector_product.hpp:107-170) as called from LocalToLocalHMatrix::add_vector_product
+ * (local_to_local_operators/hmatrix.hpp:27-29) and RestrictedGlobalToLocalHMatrix::local_add_vector_product
+ * (global_to_local_operators/hmatrix.hpp:27-29).
+ * trans == 'N': in has nb_cols entries, out nb_rows; otherwise swapped.
+ * HTB_MEM_HOST: returns after out is complete. HTB_MEM_DEVICE: asynchronous on the handle's stream. */
+int htb_add_vector_product(htb_handle h, char trans, const void *alpha, const void *in, const void *beta, void *out, int mem_kind);
+
+/* out <- beta*out + alpha*op(H)*in for mu right-hand sides stored ROW-MAJOR (mu contiguous). Replaces
+ * openmp_internal_add_hmatrix_matrix_product_row_major(trans,'N',...)
+ * (add_hmatrix_matrix_product_row_major.hpp:112-178). */
+int htb_add_matrix_product_row_major(htb_handle h, char trans, const void *alpha, const void *in, const void *beta, void *out, int mu, int mem_kind);
+
+/* User-numbering front ends, add_hmatrix_vector_product (add_hmatrix_vector_product.hpp:173-197) and
+ * add_hmatrix_matrix_product with column-major B and C (add_hmatrix_matrix_product.hpp:176-205): the
+ * permutation gathers/scatters of cluster_node.hpp:150-175 run on the device.
+ * target_permutation / source_permutation: the cluster permutations restricted to the root block,
+ * already shifted so that entries are in [0, nb_rows) / [0, nb_cols) (perm[offset+i]-offset). */
+int htb_set_permutations(htb_handle h, const int32_t *target_permutation, const int32_t *source_permutation);
+int htb_add_vector_product_user_numbering(htb_handle h, char trans, const void *alpha, const void *in, const void *beta, void *out, int mem_kind);
+int htb_add_matrix_product_user_numbering(htb_handle h, char trans, const void *alpha, const void *in, const void *beta, void *out, int mu, int mem_kind);
+
+/* ---- distributed (one process per GPU, NCCL) ------------------------------------------------------- */
+
+#define HTB_NCCL_UNIQUE_ID_BYTES 128
+/* Rank 0 calls this and broadcasts the 128 bytes to the other ranks by any means (MPI_Bcast, torch.distributed). */
+int htb_nccl_get_unique_id(void *id128);
+/* Attaches an NCCL communicator to the handle. partition_offsets has world_size+1 entries: rank r owns
+ * rows/cols [partition_offsets[r], partition_offsets[r+1]) of the global cluster numbering
+ * (PartitionFromCluster::get_offset_of_partition, partition_from_cluster.hpp:22-23). The handle's
+ * H-matrix must be that rank's row strip (built with target_partition_number = rank,
+ * distributed_operator/utility.hpp:56). */
+int htb_comm_init(htb_handle h, const void *id128, int world_size, int rank, const int32_t *partition_offsets);
+int htb_comm_destroy(htb_handle h);
+/* out_local <- beta*out_local + alpha*H_strip*allgather(in_local) (trans == 'N' only), mu >= 1 row-major.
+ * Replaces internal_add_distributed_operator_vector_product_local_to_local
+ * (add_distributed_operator_vector_product_local_to_local.hpp:19-59: MPI_Allgatherv of x at
+ * linalg/utility.hpp:27, then the global-to-local product) and its row-major matrix twin
+ * (add_distributed_operator_matrix_product_row_major_local_to_local.hpp:25-66). The allgather runs on a
+ * second stream and overlaps with the leaves whose source range lies inside the rank's own partition. */
+int htb_dist_add_product_local_to_local(htb_handle h, const void *alpha, const void *in_local, const void *beta, void *out_local, int mu, int mem_kind);
+
+/* ---- misc ------------------------------------------------------------------------------------------ */
+
+const char *htb_last_error(void);
+int htb_device_count(int *count);
+/* Number of kernel launches issued by the handle since creation (bench.py reports it). */
+int htb_launch_count(htb_handle h, int64_t *count);
+/* Tunables (stage bytes, block rows, ...) for experiments; unknown keys return HTB_ERR_INVALID. Must be
+ * set before htb_create, they are read when the store is packed. */
+int htb_set_option(const char *key, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HTOOL_B200_H */
