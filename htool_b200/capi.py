@@ -82,6 +82,23 @@ class htb_info(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
 
+class htb_packed_side(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32),
+        ("n_blocks", C.c_int32),
+        ("n_stages", C.c_int64),
+        ("n_combine", C.c_int64),
+        ("stream_bytes", C.c_int64),
+        ("scratch_elems", C.c_int64),
+        ("blocks", C.c_void_p),
+        ("stages", C.c_void_p),
+        ("order", C.c_void_p),
+        ("combine", C.c_void_p),
+        ("stream", C.c_void_p),
+        ("owner", C.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes): every symbol include/htool_b200.h declares
 SYMBOLS = {
     "htb_create": (C.c_int, [C.POINTER(htb_hmatrix_desc), C.POINTER(C.c_void_p)]),
@@ -102,6 +119,8 @@ SYMBOLS = {
     "htb_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "htb_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "htb_set_option": (C.c_int, [C.c_char_p, C.c_int64]),
+    "htb_pack_host": (C.c_int, [C.POINTER(htb_hmatrix_desc), C.c_int, C.POINTER(htb_packed_side)]),
+    "htb_pack_free": (C.c_int, [C.POINTER(htb_packed_side)]),
 }
 
 _lib = None

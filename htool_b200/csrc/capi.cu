@@ -1,0 +1,666 @@
+// htool_b200/csrc/capi.cu — implementation of the C ABI declared in include/htool_b200.h.
+//
+// A handle owns: the device-resident leaf store (two stream-ordered slabs, store.hpp), the scratch for
+// the t / z vectors, a CUDA stream, pinned staging buffers for the host-pointer entry points and,
+// optionally, an NCCL communicator (dist.cu). There is no CPU path: every compute entry point needs a
+// CUDA device and fails with HTB_ERR_CUDA otherwise.
+#include "handle.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <stdexcept>
+
+namespace htb {
+
+thread_local std::string g_last_error;
+
+int fail(int status, const std::string &msg) {
+    g_last_error = msg;
+    return status;
+}
+int cuda_fail(cudaError_t e, const char *what) {
+    return fail(HTB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+namespace {
+std::mutex g_option_mutex;
+std::map<std::string, int64_t> g_options = {
+    {"block_rows", 64}, {"unit_elems", 512}, {"stage_bytes", 16384}, {"ring_stages", 4}, {"evict_first", 1}, {"upload_chunk_mb", 256}};
+
+int64_t option(const char *key) {
+    std::lock_guard<std::mutex> lock(g_option_mutex);
+    return g_options.at(key);
+}
+} // namespace
+
+#define HTB_CUDA(call)                       \
+    do {                                     \
+        cudaError_t e__ = (call);            \
+        if (e__ != cudaSuccess)              \
+            return cuda_fail(e__, #call);    \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok  = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess)
+            ok = true;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0)
+            cudaSetDevice(prev);
+    }
+};
+
+template <typename V>
+static int upload_vector(const std::vector<V> &v, const V **dptr, std::vector<void *> &owned) {
+    *dptr = nullptr;
+    if (v.empty())
+        return HTB_OK;
+    void *p = nullptr;
+    HTB_CUDA(cudaMalloc(&p, v.size() * sizeof(V)));
+    owned.push_back(p);
+    HTB_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(V), cudaMemcpyHostToDevice));
+    *dptr = static_cast<const V *>(p);
+    return HTB_OK;
+}
+
+static int upload_store(htb_operator *h, const Packer &pk) {
+    const size_t chunk = static_cast<size_t>(std::max<int64_t>(1, option("upload_chunk_mb"))) << 20;
+    // two pinned buffers: the CPU packs block streams into one while the other is in flight to the device
+    size_t need = 0;
+    for (int s = 0; s < 2; s++)
+        need = std::max<size_t>(need, pk.side[s].stream_bytes);
+    const size_t buf_bytes = std::min(need, chunk);
+    char *pinned[2]        = {nullptr, nullptr};
+    cudaEvent_t done[2]    = {nullptr, nullptr};
+    int status             = HTB_OK;
+    auto cleanup           = [&]() {
+        for (int i = 0; i < 2; i++) {
+            if (pinned[i])
+                cudaFreeHost(pinned[i]);
+            if (done[i])
+                cudaEventDestroy(done[i]);
+        }
+    };
+    if (buf_bytes) {
+        for (int i = 0; i < 2; i++) {
+            cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&pinned[i]), buf_bytes);
+            if (e == cudaSuccess)
+                e = cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);
+            if (e != cudaSuccess) {
+                cleanup();
+                return cuda_fail(e, "pinned upload buffers");
+            }
+        }
+    }
+    for (int s = 0; s < 2 && status == HTB_OK; s++) {
+        const SideLayout &sl = pk.side[s];
+        SideDevice &sd       = h->side[s];
+        sd.n                 = sl.n;
+        sd.n_blocks          = static_cast<int>(sl.blocks.size());
+        sd.n_combine         = static_cast<int>(sl.combine.size());
+        sd.any_twice         = sl.any_twice;
+        h->host_blocks[s]    = sl.blocks;
+        h->host_order[s]     = sl.order;
+        if ((status = upload_vector(sl.blocks, &sd.blocks, h->owned)) != HTB_OK)
+            break;
+        if ((status = upload_vector(sl.stages, &sd.stages, h->owned)) != HTB_OK)
+            break;
+        if ((status = upload_vector(sl.order, &sd.order, h->owned)) != HTB_OK)
+            break;
+        if ((status = upload_vector(sl.combine, &sd.combine, h->owned)) != HTB_OK)
+            break;
+        h->descriptor_bytes += sl.blocks.size() * sizeof(BlockDesc) + sl.stages.size() * sizeof(StageDesc) + sl.order.size() * 4 + sl.combine.size() * sizeof(CombineEntry);
+        if (sl.stream_bytes == 0)
+            continue;
+        void *dstream = nullptr;
+        cudaError_t e = cudaMalloc(&dstream, sl.stream_bytes);
+        if (e != cudaSuccess) {
+            status = cuda_fail(e, "cudaMalloc(leaf store)");
+            break;
+        }
+        h->owned.push_back(dstream);
+        sd.stream = static_cast<const unsigned char *>(dstream);
+        h->store_bytes += sl.stream_bytes;
+        // batches of consecutive blocks whose streams fit one pinned buffer
+        const int nb = sd.n_blocks;
+        int b0 = 0, turn = 0;
+        while (b0 < nb) {
+            int b1 = b0 + 1;
+            while (b1 < nb && pk.block_offset(s, b1 + 1) - pk.block_offset(s, b0) <= buf_bytes)
+                b1++;
+            const uint64_t off = pk.block_offset(s, b0), bytes = pk.block_offset(s, b1) - off;
+            if (bytes > buf_bytes) { // cannot happen: a block stream is bounded by the chunk size check below
+                status = fail(HTB_ERR_ALLOC, "block stream larger than the upload buffer");
+                break;
+            }
+            if (bytes) {
+                cudaEventSynchronize(done[turn]);
+                pk.fill(s, b0, b1, pinned[turn]);
+                e = cudaMemcpyAsync(static_cast<char *>(dstream) + off, pinned[turn], bytes, cudaMemcpyHostToDevice, h->own_stream);
+                if (e == cudaSuccess)
+                    e = cudaEventRecord(done[turn], h->own_stream);
+                if (e != cudaSuccess) {
+                    status = cuda_fail(e, "upload of the leaf store");
+                    break;
+                }
+                turn ^= 1;
+            }
+            b0 = b1;
+        }
+    }
+    cudaError_t e = cudaStreamSynchronize(h->own_stream);
+    cleanup();
+    if (status == HTB_OK && e != cudaSuccess)
+        status = cuda_fail(e, "upload of the leaf store");
+    return status;
+}
+
+// ---- products ---------------------------------------------------------------------------------------
+
+template <typename T>
+static int run_product(htb_operator *h, char trans, T alpha, const T *in, T beta, T *out, int stride, const DistSplit *split) {
+    const char sym = h->symmetry;
+    const bool twice = sym != 'N' && (h->side[0].any_twice || h->side[1].any_twice);
+    const int D      = h->row_offset - h->col_offset;
+    T *T1 = static_cast<T *>(h->d_scratch);
+    T *T2 = T1 + h->scratch_elems;
+    cudaStream_t st = h->stream;
+    const bool is_complex = h->dtype == HTB_COMPLEX_DOUBLE;
+    T one;
+    std::memset(&one, 0, sizeof(T));
+    *reinterpret_cast<double *>(&one) = 1.0;
+
+    auto count = [&](cudaError_t e, const char *what) -> int {
+        if (e != cudaSuccess)
+            return cuda_fail(e, what);
+        h->launches++;
+        return HTB_OK;
+    };
+    int rc;
+    if (trans == 'N') {
+        // t = V x for every low-rank leaf (side 1 holds the V^T panels)
+        PassArgs<T> r1;
+        r1.in = in, r1.in_len = h->nb_cols, r1.scratch = T1, r1.stride = stride;
+        if (h->side[1].stream && !split) {
+            if ((rc = count(launch_reduce<T>(h->side[1], h->launch_cfg, r1, st), "reduce(V)")) != HTB_OK)
+                return rc;
+        } else if (h->side[1].stream) {
+            // distributed: source blocks inside the rank's own partition first, they overlap the allgather of x
+            SideDevice part = h->side[1];
+            part.order = split->order_local, part.n_blocks = split->n_local;
+            if (part.n_blocks && (rc = count(launch_reduce<T>(part, h->launch_cfg, r1, st), "reduce(V, local)")) != HTB_OK)
+                return rc;
+        }
+        if (twice) {
+            // second application of the leaves stored once under symmetry (add_hmatrix_vector_product.hpp:154-163):
+            // t' = op(U)^T x[target], z = op(A)^T x[target], op = conj for 'H'
+            PassArgs<T> r0;
+            r0.in = in, r0.in_len = h->nb_cols, r0.in_shift = D, r0.scratch = T2, r0.twice_only = 1, r0.conj = (sym == 'H' && is_complex), r0.stride = stride;
+            if ((rc = count(launch_reduce<T>(h->side[0], h->launch_cfg, r0, st), "reduce(U, twice)")) != HTB_OK)
+                return rc;
+            if (h->side[0].n_combine && (rc = count(launch_combine<T>(h->side[0], T2, 1, st), "combine(U, twice)")) != HTB_OK)
+                return rc;
+        }
+        if (h->side[1].stream && split) {
+            cudaError_t we = cudaStreamWaitEvent(st, split->gather_done, 0);
+            if (we != cudaSuccess)
+                return cuda_fail(we, "cudaStreamWaitEvent(allgather)");
+            SideDevice part = h->side[1];
+            part.order = split->order_remote, part.n_blocks = split->n_remote;
+            if (part.n_blocks && (rc = count(launch_reduce<T>(part, h->launch_cfg, r1, st), "reduce(V, remote)")) != HTB_OK)
+                return rc;
+        }
+        if (h->side[1].stream && h->side[1].n_combine && (rc = count(launch_combine<T>(h->side[1], T1, 0, st), "combine(V)")) != HTB_OK)
+            return rc;
+        // y = beta y + alpha (U t + A x), rows owned by one CTA each
+        PassArgs<T> a0;
+        a0.in = in, a0.in_len = h->nb_cols, a0.out = out, a0.out_len = h->nb_rows, a0.scratch = T1, a0.alpha = alpha, a0.beta = beta, a0.stride = stride;
+        if ((rc = count(launch_apply<T>(h->side[0], h->launch_cfg, a0, st), "apply(U, A)")) != HTB_OK)
+            return rc;
+        if (twice) {
+            PassArgs<T> a1;
+            a1.out = out, a1.out_len = h->nb_rows, a1.out_shift = -D, a1.scratch = T2, a1.alpha = alpha, a1.beta = one, a1.twice_only = 1, a1.conj = (sym == 'H' && is_complex), a1.stride = stride;
+            if ((rc = count(launch_apply<T>(h->side[1], h->launch_cfg, a1, st), "apply(V^T, twice)")) != HTB_OK)
+                return rc;
+        }
+    } else {
+        const int conj = (trans == 'C' && is_complex) ? 1 : 0;
+        PassArgs<T> r0;
+        r0.in = in, r0.in_len = h->nb_rows, r0.scratch = T1, r0.conj = conj, r0.stride = stride;
+        if (h->side[0].stream) {
+            if ((rc = count(launch_reduce<T>(h->side[0], h->launch_cfg, r0, st), "reduce(U, A)")) != HTB_OK)
+                return rc;
+            if (h->side[0].n_combine && (rc = count(launch_combine<T>(h->side[0], T1, 0, st), "combine(U)")) != HTB_OK)
+                return rc;
+        }
+        if (twice) {
+            PassArgs<T> r1;
+            r1.in = in, r1.in_len = h->nb_rows, r1.in_shift = -D, r1.scratch = T2, r1.twice_only = 1, r1.stride = stride;
+            if ((rc = count(launch_reduce<T>(h->side[1], h->launch_cfg, r1, st), "reduce(V, twice)")) != HTB_OK)
+                return rc;
+            if (h->side[1].n_combine && (rc = count(launch_combine<T>(h->side[1], T2, 1, st), "combine(V, twice)")) != HTB_OK)
+                return rc;
+        }
+        PassArgs<T> a1;
+        a1.out = out, a1.out_len = h->nb_cols, a1.scratch = T1, a1.alpha = alpha, a1.beta = beta, a1.conj = conj, a1.stride = stride;
+        if ((rc = count(launch_apply<T>(h->side[1], h->launch_cfg, a1, st), "apply(V^T)")) != HTB_OK)
+            return rc;
+        if (twice) {
+            PassArgs<T> a0;
+            a0.in = in, a0.in_len = h->nb_rows, a0.in_shift = -D, a0.out = out, a0.out_len = h->nb_cols, a0.out_shift = D, a0.scratch = T2, a0.alpha = alpha, a0.beta = one, a0.twice_only = 1, a0.stride = stride;
+            if ((rc = count(launch_apply<T>(h->side[0], h->launch_cfg, a0, st), "apply(U, A, twice)")) != HTB_OK)
+                return rc;
+        }
+    }
+    return HTB_OK;
+}
+
+static int check_trans(const htb_operator *h, char trans) {
+    if (trans != 'N' && trans != 'T' && trans != 'C')
+        return fail(HTB_ERR_INVALID, std::string("unknown trans '") + trans + "'");
+    // same condition and wording as add_hmatrix_vector_product.hpp:112-115
+    if ((trans == 'T' && h->symmetry == 'H') || (trans == 'C' && h->symmetry == 'S'))
+        return fail(HTB_ERR_UNSUPPORTED, std::string("Operation is not supported (trans=") + trans + " with " + h->symmetry + ")");
+    return HTB_OK;
+}
+
+// device pointers, mu right-hand sides row-major
+int product_device(htb_operator *h, char trans, const void *alpha, const void *in, const void *beta, void *out, int mu, const DistSplit *split) {
+    int rc = check_trans(h, trans);
+    if (rc != HTB_OK)
+        return rc;
+    for (int c = 0; c < mu; c++) {
+        if (h->dtype == HTB_DOUBLE)
+            rc = run_product<double>(h, trans, *static_cast<const double *>(alpha), static_cast<const double *>(in) + c, *static_cast<const double *>(beta), static_cast<double *>(out) + c, mu, c == 0 ? split : nullptr);
+        else
+            rc = run_product<cplx>(h, trans, *static_cast<const cplx *>(alpha), static_cast<const cplx *>(in) + c, *static_cast<const cplx *>(beta), static_cast<cplx *>(out) + c, mu, c == 0 ? split : nullptr);
+        if (rc != HTB_OK)
+            return rc;
+    }
+    return HTB_OK;
+}
+
+int ensure_staging(htb_operator *h, size_t in_bytes, size_t out_bytes) {
+    auto grow = [&](void **dev, void **host, size_t *cap, size_t need) -> int {
+        if (need <= *cap)
+            return HTB_OK;
+        if (*dev)
+            cudaFree(*dev);
+        if (*host)
+            cudaFreeHost(*host);
+        *dev = *host = nullptr;
+        *cap         = 0;
+        HTB_CUDA(cudaMalloc(dev, need));
+        HTB_CUDA(cudaMallocHost(host, need));
+        *cap = need;
+        return HTB_OK;
+    };
+    int rc = grow(&h->d_in, &h->h_in, &h->in_cap, in_bytes);
+    if (rc != HTB_OK)
+        return rc;
+    return grow(&h->d_out, &h->h_out, &h->out_cap, out_bytes);
+}
+
+static bool beta_is_zero(const htb_operator *h, const void *beta) {
+    const double *b = static_cast<const double *>(beta);
+    return b[0] == 0. && (h->dtype == HTB_DOUBLE || b[1] == 0.);
+}
+
+// host pointers: stage through pinned buffers, H2D, product, D2H, synchronise
+static int product_host(htb_operator *h, char trans, const void *alpha, const void *in, const void *beta, void *out, int mu) {
+    int rc = check_trans(h, trans);
+    if (rc != HTB_OK)
+        return rc;
+    const size_t ni = trans == 'N' ? h->nb_cols : h->nb_rows, no = trans == 'N' ? h->nb_rows : h->nb_cols;
+    const size_t in_bytes = ni * mu * h->esize, out_bytes = no * mu * h->esize;
+    if ((rc = ensure_staging(h, in_bytes, out_bytes)) != HTB_OK)
+        return rc;
+    cudaStream_t st = h->stream;
+    std::memcpy(h->h_in, in, in_bytes);
+    HTB_CUDA(cudaMemcpyAsync(h->d_in, h->h_in, in_bytes, cudaMemcpyHostToDevice, st));
+    if (!beta_is_zero(h, beta)) {
+        std::memcpy(h->h_out, out, out_bytes);
+        HTB_CUDA(cudaMemcpyAsync(h->d_out, h->h_out, out_bytes, cudaMemcpyHostToDevice, st));
+    }
+    if ((rc = product_device(h, trans, alpha, h->d_in, beta, h->d_out, mu)) != HTB_OK)
+        return rc;
+    HTB_CUDA(cudaMemcpyAsync(h->h_out, h->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    HTB_CUDA(cudaStreamSynchronize(st));
+    std::memcpy(out, h->h_out, out_bytes);
+    return HTB_OK;
+}
+
+} // namespace htb
+
+using namespace htb;
+
+extern "C" {
+
+const char *htb_last_error(void) { return g_last_error.c_str(); }
+
+int htb_device_count(int *count) {
+    if (!count)
+        return fail(HTB_ERR_INVALID, "null argument");
+    *count = 0;
+    HTB_CUDA(cudaGetDeviceCount(count));
+    return HTB_OK;
+}
+
+int htb_set_option(const char *key, int64_t value) {
+    if (!key)
+        return fail(HTB_ERR_INVALID, "null key");
+    std::lock_guard<std::mutex> lock(g_option_mutex);
+    auto it = g_options.find(key);
+    if (it == g_options.end())
+        return fail(HTB_ERR_INVALID, std::string("unknown option ") + key);
+    it->second = value;
+    return HTB_OK;
+}
+
+int htb_create(const htb_hmatrix_desc *desc, htb_handle *out) {
+    if (!desc || !out)
+        return fail(HTB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(HTB_ERR_CUDA, std::string("no CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") + "): htool_b200 has no CPU fallback");
+    int device = desc->device;
+    if (device < 0)
+        HTB_CUDA(cudaGetDevice(&device));
+    if (device >= ndev)
+        return fail(HTB_ERR_INVALID, "device ordinal out of range");
+
+    PackOptions popt;
+    popt.block_rows  = static_cast<int>(option("block_rows"));
+    popt.unit_elems  = static_cast<int>(option("unit_elems"));
+    popt.stage_bytes = static_cast<int>(option("stage_bytes"));
+    std::unique_ptr<Packer> pk;
+    try {
+        pk = std::make_unique<Packer>(*desc, popt);
+    } catch (const std::exception &ex) {
+        return fail(HTB_ERR_INVALID, ex.what());
+    }
+
+    DeviceGuard guard(device);
+    if (!guard.ok)
+        return fail(HTB_ERR_CUDA, "cudaSetDevice failed");
+    auto h            = std::make_unique<htb_operator>();
+    h->device         = device;
+    h->dtype          = desc->dtype;
+    h->esize          = pk->esize;
+    h->nb_rows        = desc->nb_rows;
+    h->nb_cols        = desc->nb_cols;
+    h->row_offset     = desc->row_offset;
+    h->col_offset     = desc->col_offset;
+    h->symmetry       = desc->symmetry_for_leaves ? desc->symmetry_for_leaves : 'N';
+    h->uplo           = desc->uplo_for_leaves ? desc->uplo_for_leaves : 'N';
+    h->scratch_elems  = pk->scratch_elems;
+    h->launch_cfg.block_rows  = popt.block_rows;
+    h->launch_cfg.stage_bytes = popt.stage_bytes;
+    h->launch_cfg.ring_stages = static_cast<int>(option("ring_stages"));
+    h->launch_cfg.evict_first = static_cast<int>(option("evict_first"));
+    if (h->launch_cfg.ring_stages < 2 || h->launch_cfg.ring_stages > 16)
+        return fail(HTB_ERR_INVALID, "ring_stages must be in [2, 16]");
+    cudaDeviceProp prop{};
+    HTB_CUDA(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    if (apply_smem_bytes(h->launch_cfg, 16) > static_cast<size_t>(prop.sharedMemPerBlockOptin))
+        return fail(HTB_ERR_INVALID, "ring_stages * stage_bytes exceeds the shared memory of an SM");
+    HTB_CUDA(configure_kernels(h->launch_cfg));
+    HTB_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+
+    int rc = upload_store(h.get(), *pk);
+    if (rc != HTB_OK) {
+        htb_destroy(h.release());
+        return rc;
+    }
+    // two scratch copies: first application, and the transposed second application under symmetric storage
+    const size_t scratch_bytes = std::max<size_t>(1, h->scratch_elems) * h->esize * 2;
+    e                          = cudaMalloc(&h->d_scratch, scratch_bytes);
+    if (e != cudaSuccess) {
+        htb_destroy(h.release());
+        return cuda_fail(e, "cudaMalloc(scratch)");
+    }
+    cudaMemsetAsync(h->d_scratch, 0, scratch_bytes, h->own_stream);
+    cudaStreamSynchronize(h->own_stream);
+    h->workspace_bytes = scratch_bytes;
+
+    htb_info &i             = h->info;
+    i.nb_leaves             = pk->n_leaves;
+    i.nb_dense_leaves       = pk->n_dense;
+    i.nb_low_rank_leaves    = pk->n_lowrank;
+    i.nb_leaves_applied_twice = pk->n_twice;
+    i.coefficients          = pk->coefficients;
+    i.coefficients_twice    = pk->coefficients_twice;
+    i.rank_min              = pk->rank_min;
+    i.rank_max              = pk->rank_max;
+    i.dtype                 = h->dtype;
+    i.device                = device;
+    i.nb_rows               = h->nb_rows;
+    i.nb_cols               = h->nb_cols;
+    i.nb_target_blocks      = h->side[0].n_blocks;
+    i.nb_source_blocks      = h->side[1].n_blocks;
+    i.sm_count              = h->sm_count;
+    *out                    = h.release();
+    return HTB_OK;
+}
+
+int htb_destroy(htb_handle h) {
+    if (!h)
+        return HTB_OK;
+    DeviceGuard guard(h->device);
+    dist_destroy(h);
+    if (h->own_stream)
+        cudaStreamSynchronize(h->own_stream);
+    for (void *p : h->owned)
+        cudaFree(p);
+    for (void *p : {h->d_scratch, h->d_in, h->d_out, h->d_perm[0], h->d_perm[1], h->d_work_in, h->d_work_out})
+        if (p)
+            cudaFree(p);
+    for (void *p : {h->h_in, h->h_out})
+        if (p)
+            cudaFreeHost(p);
+    if (h->own_stream)
+        cudaStreamDestroy(h->own_stream);
+    delete h;
+    return HTB_OK;
+}
+
+int htb_get_info(htb_handle h, htb_info *info) {
+    if (!h || !info)
+        return fail(HTB_ERR_INVALID, "null argument");
+    *info                  = h->info;
+    info->store_bytes      = static_cast<int64_t>(h->store_bytes);
+    info->descriptor_bytes = static_cast<int64_t>(h->descriptor_bytes);
+    info->workspace_bytes  = static_cast<int64_t>(h->workspace_bytes + h->in_cap + h->out_cap + h->work_cap * 2);
+    return HTB_OK;
+}
+
+int htb_set_stream(htb_handle h, void *cuda_stream) {
+    if (!h)
+        return fail(HTB_ERR_INVALID, "null handle");
+    h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+    return HTB_OK;
+}
+
+int htb_synchronize(htb_handle h) {
+    if (!h)
+        return fail(HTB_ERR_INVALID, "null handle");
+    DeviceGuard guard(h->device);
+    HTB_CUDA(cudaStreamSynchronize(h->stream));
+    return HTB_OK;
+}
+
+int htb_launch_count(htb_handle h, int64_t *count) {
+    if (!h || !count)
+        return fail(HTB_ERR_INVALID, "null argument");
+    *count = h->launches;
+    return HTB_OK;
+}
+
+int htb_add_vector_product(htb_handle h, char trans, const void *alpha, const void *in, const void *beta, void *out, int mem_kind) {
+    return htb_add_matrix_product_row_major(h, trans, alpha, in, beta, out, 1, mem_kind);
+}
+
+int htb_add_matrix_product_row_major(htb_handle h, char trans, const void *alpha, const void *in, const void *beta, void *out, int mu, int mem_kind) {
+    if (!h || !alpha || !beta || mu < 0 || (mem_kind != HTB_MEM_HOST && mem_kind != HTB_MEM_DEVICE))
+        return fail(HTB_ERR_INVALID, "invalid argument");
+    if (mu == 0)
+        return HTB_OK;
+    if (!in || !out)
+        return fail(HTB_ERR_INVALID, "null vector");
+    DeviceGuard guard(h->device);
+    if (mem_kind == HTB_MEM_DEVICE)
+        return product_device(h, trans, alpha, in, beta, out, mu);
+    return product_host(h, trans, alpha, in, beta, out, mu);
+}
+
+int htb_set_permutations(htb_handle h, const int32_t *target_permutation, const int32_t *source_permutation) {
+    if (!h || !target_permutation || !source_permutation)
+        return fail(HTB_ERR_INVALID, "null argument");
+    DeviceGuard guard(h->device);
+    const int32_t *src[2] = {target_permutation, source_permutation};
+    const int n[2]        = {h->nb_rows, h->nb_cols};
+    for (int s = 0; s < 2; s++) {
+        for (int i = 0; i < n[s]; i++)
+            if (src[s][i] < 0 || src[s][i] >= n[s])
+                return fail(HTB_ERR_INVALID, "permutation entry out of range");
+        if (h->d_perm[s])
+            cudaFree(h->d_perm[s]);
+        h->d_perm[s] = nullptr;
+        HTB_CUDA(cudaMalloc(&h->d_perm[s], std::max<size_t>(1, n[s]) * sizeof(int32_t)));
+        HTB_CUDA(cudaMemcpy(h->d_perm[s], src[s], n[s] * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    return HTB_OK;
+}
+
+// add_hmatrix_vector_product / add_hmatrix_matrix_product in user numbering: gather in (and out when beta != 0)
+// into cluster numbering, product, scatter out (add_hmatrix_vector_product.hpp:173-197, add_hmatrix_matrix_product.hpp:176-205)
+static int product_user(htb_handle h, char trans, const void *alpha, const void *in, const void *beta, void *out, int mu, int mem_kind, bool colmajor) {
+    if (!h || !alpha || !beta || !in || !out || mu < 1)
+        return fail(HTB_ERR_INVALID, "invalid argument");
+    if (!h->d_perm[0] || !h->d_perm[1])
+        return fail(HTB_ERR_INVALID, "htb_set_permutations has not been called");
+    int rc = check_trans(h, trans);
+    if (rc != HTB_OK)
+        return rc;
+    DeviceGuard guard(h->device);
+    const int ni = trans == 'N' ? h->nb_cols : h->nb_rows, no = trans == 'N' ? h->nb_rows : h->nb_cols;
+    const int32_t *pin  = static_cast<const int32_t *>(trans == 'N' ? h->d_perm[1] : h->d_perm[0]);
+    const int32_t *pout = static_cast<const int32_t *>(trans == 'N' ? h->d_perm[0] : h->d_perm[1]);
+    const size_t in_bytes = size_t(ni) * mu * h->esize, out_bytes = size_t(no) * mu * h->esize;
+    const size_t need = std::max(in_bytes, out_bytes);
+    if (need > h->work_cap) {
+        for (void **p : {&h->d_work_in, &h->d_work_out}) {
+            if (*p)
+                cudaFree(*p);
+            *p = nullptr;
+        }
+        h->work_cap = 0;
+        HTB_CUDA(cudaMalloc(&h->d_work_in, need));
+        HTB_CUDA(cudaMalloc(&h->d_work_out, need));
+        h->work_cap = need;
+    }
+    cudaStream_t st = h->stream;
+    const void *din = in;
+    void *dout      = out;
+    if (mem_kind == HTB_MEM_HOST) {
+        if ((rc = ensure_staging(h, in_bytes, out_bytes)) != HTB_OK)
+            return rc;
+        std::memcpy(h->h_in, in, in_bytes);
+        HTB_CUDA(cudaMemcpyAsync(h->d_in, h->h_in, in_bytes, cudaMemcpyHostToDevice, st));
+        if (!beta_is_zero(h, beta)) {
+            std::memcpy(h->h_out, out, out_bytes);
+            HTB_CUDA(cudaMemcpyAsync(h->d_out, h->h_out, out_bytes, cudaMemcpyHostToDevice, st));
+        }
+        din  = h->d_in;
+        dout = h->d_out;
+    }
+    const bool b0 = beta_is_zero(h, beta);
+    if (h->dtype == HTB_DOUBLE) {
+        HTB_CUDA(launch_permute<double>(static_cast<const double *>(din), static_cast<double *>(h->d_work_in), pin, ni, mu, true, colmajor, st));
+        if (!b0)
+            HTB_CUDA(launch_permute<double>(static_cast<const double *>(dout), static_cast<double *>(h->d_work_out), pout, no, mu, true, colmajor, st));
+    } else {
+        HTB_CUDA(launch_permute<cplx>(static_cast<const cplx *>(din), static_cast<cplx *>(h->d_work_in), pin, ni, mu, true, colmajor, st));
+        if (!b0)
+            HTB_CUDA(launch_permute<cplx>(static_cast<const cplx *>(dout), static_cast<cplx *>(h->d_work_out), pout, no, mu, true, colmajor, st));
+    }
+    h->launches += b0 ? 1 : 2;
+    if ((rc = product_device(h, trans, alpha, h->d_work_in, beta, h->d_work_out, mu)) != HTB_OK)
+        return rc;
+    if (h->dtype == HTB_DOUBLE)
+        HTB_CUDA(launch_permute<double>(static_cast<const double *>(h->d_work_out), static_cast<double *>(dout), pout, no, mu, false, colmajor, st));
+    else
+        HTB_CUDA(launch_permute<cplx>(static_cast<const cplx *>(h->d_work_out), static_cast<cplx *>(dout), pout, no, mu, false, colmajor, st));
+    h->launches++;
+    if (mem_kind == HTB_MEM_HOST) {
+        HTB_CUDA(cudaMemcpyAsync(h->h_out, h->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+        HTB_CUDA(cudaStreamSynchronize(st));
+        std::memcpy(out, h->h_out, out_bytes);
+    }
+    return HTB_OK;
+}
+
+struct PackedOwner {
+    SideLayout layout;
+    std::vector<char> stream;
+};
+
+int htb_pack_host(const htb_hmatrix_desc *desc, int side, htb_packed_side *out) {
+    if (!desc || !out || (side != 0 && side != 1))
+        return fail(HTB_ERR_INVALID, "invalid argument");
+    PackOptions popt;
+    popt.block_rows  = static_cast<int>(option("block_rows"));
+    popt.unit_elems  = static_cast<int>(option("unit_elems"));
+    popt.stage_bytes = static_cast<int>(option("stage_bytes"));
+    try {
+        Packer pk(*desc, popt);
+        auto *own   = new PackedOwner();
+        own->layout = pk.side[side];
+        own->stream.resize(pk.side[side].stream_bytes);
+        if (!own->layout.blocks.empty())
+            pk.fill(side, 0, static_cast<int>(own->layout.blocks.size()), own->stream.data());
+        out->n             = own->layout.n;
+        out->n_blocks      = static_cast<int32_t>(own->layout.blocks.size());
+        out->n_stages      = static_cast<int64_t>(own->layout.stages.size());
+        out->n_combine     = static_cast<int64_t>(own->layout.combine.size());
+        out->stream_bytes  = static_cast<int64_t>(own->stream.size());
+        out->scratch_elems = static_cast<int64_t>(pk.scratch_elems);
+        out->blocks        = own->layout.blocks.data();
+        out->stages        = own->layout.stages.data();
+        out->order         = own->layout.order.data();
+        out->combine       = own->layout.combine.data();
+        out->stream        = own->stream.data();
+        out->owner         = own;
+    } catch (const std::exception &ex) {
+        return fail(HTB_ERR_INVALID, ex.what());
+    }
+    return HTB_OK;
+}
+
+int htb_pack_free(htb_packed_side *packed) {
+    if (packed && packed->owner) {
+        delete static_cast<PackedOwner *>(packed->owner);
+        packed->owner = nullptr;
+    }
+    return HTB_OK;
+}
+
+int htb_add_vector_product_user_numbering(htb_handle h, char trans, const void *alpha, const void *in, const void *beta, void *out, int mem_kind) {
+    return product_user(h, trans, alpha, in, beta, out, 1, mem_kind, false);
+}
+
+int htb_add_matrix_product_user_numbering(htb_handle h, char trans, const void *alpha, const void *in, const void *beta, void *out, int mu, int mem_kind) {
+    return product_user(h, trans, alpha, in, beta, out, mu, mem_kind, true);
+}
+
+} // extern "C"

@@ -1,0 +1,59 @@
+// htool_b200/csrc/handle.hpp — the object behind htb_handle (include/htool_b200.h).
+#ifndef HTB_HANDLE_HPP
+#define HTB_HANDLE_HPP
+
+#include "kernels.cuh"
+#include "packer.hpp"
+#include <cuda_runtime.h>
+#include <htool_b200.h>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace htb {
+struct DistState; // dist.cu
+// Distributed 'N' product: the source-side REDUCE is launched in two parts, the blocks that lie inside the
+// rank's own partition (they only need the local x) and the others, which wait for the allgather.
+struct DistSplit {
+    const uint32_t *order_local  = nullptr;
+    const uint32_t *order_remote = nullptr;
+    int n_local = 0, n_remote = 0;
+    cudaEvent_t gather_done = nullptr;
+};
+}
+
+struct htb_operator {
+    int device = 0, dtype = 0, sm_count = 0;
+    size_t esize = 8;
+    int nb_rows = 0, nb_cols = 0, row_offset = 0, col_offset = 0;
+    char symmetry = 'N', uplo = 'N';
+    htb::SideDevice side[2];
+    std::vector<htb::BlockDesc> host_blocks[2]; // host copies, used to split passes by index range (dist.cu)
+    std::vector<uint32_t> host_order[2];
+    htb::LaunchConfig launch_cfg;
+    std::vector<void *> owned; // device allocations of the store
+    void *d_scratch      = nullptr;
+    uint64_t scratch_elems = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    // host-pointer entry points: pinned + device staging, grown on demand
+    void *d_in = nullptr, *d_out = nullptr, *h_in = nullptr, *h_out = nullptr;
+    size_t in_cap = 0, out_cap = 0;
+    // user-numbering front ends
+    void *d_perm[2]  = {nullptr, nullptr};
+    void *d_work_in = nullptr, *d_work_out = nullptr;
+    size_t work_cap = 0;
+    int64_t launches = 0;
+    size_t store_bytes = 0, descriptor_bytes = 0, workspace_bytes = 0;
+    htb_info info{};
+    htb::DistState *dist = nullptr;
+};
+
+namespace htb {
+extern thread_local std::string g_last_error;
+int fail(int status, const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what);
+int product_device(htb_operator *h, char trans, const void *alpha, const void *in, const void *beta, void *out, int mu, const DistSplit *split = nullptr);
+int ensure_staging(htb_operator *h, size_t in_bytes, size_t out_bytes);
+void dist_destroy(htb_operator *h);
+} // namespace htb
+#endif

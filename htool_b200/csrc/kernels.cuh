@@ -1,0 +1,74 @@
+// htool_b200/csrc/kernels.cuh — launch interface of the sm_100a kernels (kernels.cu).
+#ifndef HTB_KERNELS_CUH
+#define HTB_KERNELS_CUH
+
+#include "store.hpp"
+#include <cuda_runtime.h>
+
+namespace htb {
+
+struct cplx {
+    double x, y;
+};
+
+// Device view of one side of the store.
+struct SideDevice {
+    const BlockDesc *blocks    = nullptr;
+    const StageDesc *stages    = nullptr;
+    const uint32_t *order      = nullptr;
+    const unsigned char *stream = nullptr;
+    const CombineEntry *combine = nullptr;
+    int n_blocks               = 0;
+    int n_combine              = 0;
+    int n                      = 0;
+    bool any_twice             = false;
+};
+
+struct LaunchConfig {
+    int block_rows   = 64;
+    int stage_bytes  = 16384;
+    int ring_stages  = 4;
+    int evict_first  = 1; // L2 evict_first hint on the coefficient stream
+};
+
+// One pass over a side. Vectors are addressed as v[index * stride + column] (stride = mu, column = RHS).
+template <typename T>
+struct PassArgs {
+    const T *in   = nullptr; // REDUCE: multiplied vector. APPLY: source of the dense units' c vectors
+    long long in_len = 0;
+    int in_shift  = 0; // REDUCE: in index = block index + in_shift. APPLY(dense): in index = aux_apply + in_shift
+    T *out        = nullptr; // APPLY only
+    long long out_len = 0;
+    int out_shift = 0; // APPLY: out index = block index + out_shift
+    T *scratch    = nullptr; // REDUCE: destination of the partial sums. APPLY: t / z vectors
+    T alpha{}, beta{};
+    int beta_is_zero = 0; // APPLY: do not read out
+    int twice_only   = 0; // only units of leaves applied twice (second, transposed application of symmetric storage)
+    int conj         = 0; // conjugate the coefficients (trans == 'C', Hermitian second application)
+    int stride       = 1; // distance between consecutive vector entries (mu for row-major multi-RHS)
+};
+
+template <typename T>
+cudaError_t launch_reduce(const SideDevice &side, const LaunchConfig &cfg, const PassArgs<T> &args, cudaStream_t stream);
+template <typename T>
+cudaError_t launch_apply(const SideDevice &side, const LaunchConfig &cfg, const PassArgs<T> &args, cudaStream_t stream);
+// scratch[dst..dst+w) = sum_c scratch[src + c*w ..): folds the per-chunk partials of the leaves that span several blocks
+template <typename T>
+cudaError_t launch_combine(const SideDevice &side, T *scratch, int twice_only, cudaStream_t stream);
+
+// out[i] = in[perm[i]] (gather) / out[perm[i]] = in[i] (scatter), i < n, for mu interleaved columns:
+// cluster_node.hpp:150-175 (user_to_cluster / cluster_to_user) on the device.
+// transpose_in/out: the non-permuted side is column-major n x mu (user layout of add_hmatrix_matrix_product)
+// while the permuted side is row-major (mu contiguous).
+template <typename T>
+cudaError_t launch_permute(const T *in, T *out, const int32_t *perm, int n, int mu, bool gather, bool colmajor_user, cudaStream_t stream);
+// y <- beta * y (used when an operator has no block at all on the output side)
+template <typename T>
+cudaError_t launch_scale(T *y, long long n, T beta, cudaStream_t stream);
+
+size_t reduce_smem_bytes(const LaunchConfig &cfg, size_t esize);
+size_t apply_smem_bytes(const LaunchConfig &cfg, size_t esize);
+cudaError_t configure_kernels(const LaunchConfig &cfg); // sets the dynamic shared memory attributes once
+
+} // namespace htb
+#endif

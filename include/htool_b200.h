@@ -7,7 +7,7 @@
  *     htool::VirtualGlobalToLocalOperator<T>  include/htool/distributed_operator/interfaces/virtual_global_to_local_operator.hpp:8-35
  * (three virtuals each: add_vector_product :16, add_matrix_product_row_major :25,
  * add_sub_matrix_product_to_local :33). The header-only shim in
- * htool_b200/cpp/htool_b200/*.hpp subclasses them and forwards every call to the entry points
+ * htool_b200/cpp/htool_b200/ (operators.hpp) subclasses them and forwards every call to the entry points
  * below, so this file declares exactly what those virtuals (and the free functions
  * add_hmatrix_vector_product / add_hmatrix_matrix_product,
  * include/htool/hmatrix/linalg/add_hmatrix_vector_product.hpp:173,
@@ -178,6 +178,28 @@ int htb_launch_count(htb_handle h, int64_t *count);
 /* Tunables (stage bytes, block rows, ...) for experiments; unknown keys return HTB_ERR_INVALID. Must be
  * set before htb_create, they are read when the store is packed. */
 int htb_set_option(const char *key, int64_t value);
+
+/* ---- packer introspection (host only, no CUDA) ----------------------------------------------------- */
+
+/* The bytes htb_create would upload for one side of the store (0: target rows = U panels + dense leaves,
+ * 1: source columns = V^T panels), with the tables that index them (layouts in htool_b200/csrc/store.hpp).
+ * It exists so the CPU test-suite can check the stream format without a GPU; it computes no product. */
+typedef struct htb_packed_side {
+    int32_t n;                /* length of the side's index space */
+    int32_t n_blocks;
+    int64_t n_stages;
+    int64_t n_combine;
+    int64_t stream_bytes;
+    int64_t scratch_elems;    /* elements of ONE scratch copy (final t / z vectors + per-chunk partials) */
+    const void *blocks;       /* n_blocks x 32 B  (BlockDesc) */
+    const void *stages;       /* n_stages x 16 B  (StageDesc) */
+    const void *order;        /* n_blocks x uint32: launch order, heaviest block first */
+    const void *combine;      /* n_combine x 16 B (CombineEntry) */
+    const void *stream;       /* stream_bytes */
+    void *owner;              /* opaque, released by htb_pack_free */
+} htb_packed_side;
+int htb_pack_host(const htb_hmatrix_desc *desc, int side, htb_packed_side *out);
+int htb_pack_free(htb_packed_side *packed);
 
 #ifdef __cplusplus
 }
