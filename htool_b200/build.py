@@ -50,7 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 print(" ".join(cmd), flush=True)
             subprocess.run(cmd, check=True)
     if force or _newer(LIB, objs):
-        cmd = [NVCC, *ARCH, "-shared", "-ccbin", "/usr/bin/g++", "-o", LIB, *objs, "-lnccl", "-Xcompiler", "-fopenmp", "-lgomp"]
+        cmd = [NVCC, *ARCH, "-shared", "-ccbin", "/usr/bin/g++", "-o", LIB, *objs, "-ldl", "-Xcompiler", "-fopenmp", "-lgomp"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.run(cmd, check=True)

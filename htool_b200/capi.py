@@ -119,6 +119,8 @@ SYMBOLS = {
     "htb_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "htb_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "htb_set_option": (C.c_int, [C.c_char_p, C.c_int64]),
+    "htb_profile_passes": (C.c_int, [C.c_void_p, C.c_int]),
+    "htb_get_pass_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "htb_pack_host": (C.c_int, [C.POINTER(htb_hmatrix_desc), C.c_int, C.POINTER(htb_packed_side)]),
     "htb_pack_free": (C.c_int, [C.POINTER(htb_packed_side)]),
 }
@@ -134,7 +136,7 @@ def load(path: str | None = None):
     p = path or LIB_PATH
     if not os.path.exists(p):
         raise RuntimeError(f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)")
-    lib = C.CDLL(p, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(p)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)
         fn.restype = res
@@ -208,6 +210,15 @@ class Operator:
         n = C.c_int64()
         check(self.lib, self.lib.htb_launch_count(self.handle, C.byref(n)))
         return n.value
+
+    def profile_passes(self, enable: bool):
+        check(self.lib, self.lib.htb_profile_passes(self.handle, 1 if enable else 0))
+
+    def pass_times(self) -> dict:
+        ms = (C.c_double * 4)()
+        n = (C.c_int64 * 4)()
+        check(self.lib, self.lib.htb_get_pass_times(self.handle, ms, n))
+        return {k: {"ms": ms[i], "launches": n[i]} for i, k in enumerate(("reduce", "combine", "apply", "other"))}
 
     # host numpy arrays (HTB_MEM_HOST) -----------------------------------------------------------
     def add_vector_product(self, trans, alpha, x, beta, y):

@@ -176,12 +176,25 @@ static int run_product(htb_operator *h, char trans, T alpha, const T *in, T beta
     std::memset(&one, 0, sizeof(T));
     *reinterpret_cast<double *>(&one) = 1.0;
 
-    auto count = [&](cudaError_t e, const char *what) -> int {
+    // every launch goes through here: counts it and, when profiling, brackets it with events on its stream
+    auto timed = [&](int kind, auto &&launch, const char *what) -> int {
+        htb_operator::TimedLaunch tl{nullptr, nullptr, kind};
+        if (h->profiling) {
+            cudaEventCreate(&tl.start);
+            cudaEventCreate(&tl.stop);
+            cudaEventRecord(tl.start, st);
+        }
+        cudaError_t e = launch();
+        if (h->profiling) {
+            cudaEventRecord(tl.stop, st);
+            h->timed.push_back(tl);
+        }
         if (e != cudaSuccess)
             return cuda_fail(e, what);
         h->launches++;
         return HTB_OK;
     };
+#define count(expr, what) timed(std::strstr(what, "reduce") ? HTB_PASS_REDUCE : (std::strstr(what, "combine") ? HTB_PASS_COMBINE : HTB_PASS_APPLY), [&]() { return (expr); }, what)
     int rc;
     if (trans == 'N') {
         // t = V x for every low-rank leaf (side 1 holds the V^T panels)
@@ -259,6 +272,7 @@ static int run_product(htb_operator *h, char trans, T alpha, const T *in, T beta
         }
     }
     return HTB_OK;
+#undef count
 }
 
 static int check_trans(const htb_operator *h, char trans) {
@@ -503,6 +517,35 @@ int htb_launch_count(htb_handle h, int64_t *count) {
     if (!h || !count)
         return fail(HTB_ERR_INVALID, "null argument");
     *count = h->launches;
+    return HTB_OK;
+}
+
+int htb_profile_passes(htb_handle h, int enable) {
+    if (!h)
+        return fail(HTB_ERR_INVALID, "null handle");
+    h->profiling = enable != 0;
+    return HTB_OK;
+}
+
+int htb_get_pass_times(htb_handle h, double ms[HTB_PASS_KINDS], int64_t launches[HTB_PASS_KINDS]) {
+    if (!h || !ms || !launches)
+        return fail(HTB_ERR_INVALID, "null argument");
+    DeviceGuard guard(h->device);
+    HTB_CUDA(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < HTB_PASS_KINDS; k++) {
+        ms[k]       = 0;
+        launches[k] = 0;
+    }
+    for (auto &tl : h->timed) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, tl.start, tl.stop) == cudaSuccess) {
+            ms[tl.kind] += t;
+            launches[tl.kind]++;
+        }
+        cudaEventDestroy(tl.start);
+        cudaEventDestroy(tl.stop);
+    }
+    h->timed.clear();
     return HTB_OK;
 }
 

@@ -12,9 +12,55 @@
 #include "handle.hpp"
 
 #include <cstring>
-#include <nccl.h>
+#include <dlfcn.h>
+#include <mutex>
+#include <nccl.h> // types only: the library is bound at run time, see NcclApi
 
 namespace htb {
+
+// NCCL is bound lazily with dlopen instead of being a link-time dependency: a process that also imports
+// PyTorch already holds PyTorch's own libnccl.so.2, and two different NCCL builds under one SONAME cannot
+// coexist. An already loaded libnccl.so.2 is reused (RTLD_NOLOAD); otherwise the system library is opened.
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *)                                                                   = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int)                                            = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t)                                                                       = nullptr;
+    ncclResult_t (*GroupStart)()                                                                                  = nullptr;
+    ncclResult_t (*GroupEnd)()                                                                                    = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t)        = nullptr;
+    const char *(*GetErrorString)(ncclResult_t)                                                                   = nullptr;
+    bool ok = false;
+    std::string error;
+};
+
+static NcclApi &nccl() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!lib)
+            lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (!lib) {
+            api.error = std::string("cannot load libnccl.so.2: ") + dlerror();
+            return;
+        }
+        auto sym = [&](const char *name) -> void * {
+            void *p = dlsym(lib, name);
+            if (!p)
+                api.error = std::string("libnccl.so.2 lacks ") + name;
+            return p;
+        };
+        api.GetUniqueId    = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+        api.CommInitRank   = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+        api.CommDestroy    = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+        api.GroupStart     = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+        api.GroupEnd       = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+        api.Broadcast      = reinterpret_cast<decltype(api.Broadcast)>(sym("ncclBroadcast"));
+        api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+        api.ok             = api.error.empty();
+    });
+    return api;
+}
 
 struct DistState {
     ncclComm_t comm = nullptr;
@@ -29,7 +75,7 @@ struct DistState {
 };
 
 static int nccl_fail(ncclResult_t r, const char *what) {
-    return fail(HTB_ERR_NCCL, std::string(what) + ": " + ncclGetErrorString(r));
+    return fail(HTB_ERR_NCCL, std::string(what) + ": " + nccl().GetErrorString(r));
 }
 
 void dist_destroy(htb_operator *h) {
@@ -39,7 +85,7 @@ void dist_destroy(htb_operator *h) {
     if (d->comm_stream)
         cudaStreamSynchronize(d->comm_stream);
     if (d->comm)
-        ncclCommDestroy(d->comm);
+        nccl().CommDestroy(d->comm);
     for (void *p : {static_cast<void *>(d->d_xglobal), static_cast<void *>(d->d_order_local), static_cast<void *>(d->d_order_remote)})
         if (p)
             cudaFree(p);
@@ -76,8 +122,10 @@ int htb_nccl_get_unique_id(void *id128) {
     if (!id128)
         return fail(HTB_ERR_INVALID, "null argument");
     static_assert(sizeof(ncclUniqueId) == HTB_NCCL_UNIQUE_ID_BYTES, "ncclUniqueId size");
+    if (!nccl().ok)
+        return fail(HTB_ERR_NCCL, nccl().error);
     ncclUniqueId id;
-    HTB_NCCL(ncclGetUniqueId(&id));
+    HTB_NCCL(nccl().GetUniqueId(&id));
     std::memcpy(id128, &id, sizeof(id));
     return HTB_OK;
 }
@@ -92,6 +140,8 @@ int htb_comm_init(htb_handle h, const void *id128, int world_size, int rank, con
         return fail(HTB_ERR_INVALID, "partition offsets must cover [0, nb_cols) of the row strip");
     if (partition_offsets[rank + 1] - partition_offsets[rank] != h->nb_rows || partition_offsets[rank] != h->row_offset - h->col_offset)
         return fail(HTB_ERR_INVALID, "the handle is not the row strip of this rank's partition");
+    if (!nccl().ok)
+        return fail(HTB_ERR_NCCL, nccl().error);
     int prev = 0;
     cudaGetDevice(&prev);
     HTB_CUDA(cudaSetDevice(h->device));
@@ -103,7 +153,7 @@ int htb_comm_init(htb_handle h, const void *id128, int world_size, int rank, con
     d->offsets.assign(partition_offsets, partition_offsets + world_size + 1);
     ncclUniqueId id;
     std::memcpy(&id, id128, sizeof(id));
-    HTB_NCCL(ncclCommInitRank(&d->comm, world_size, id, rank));
+    HTB_NCCL(nccl().CommInitRank(&d->comm, world_size, id, rank));
     HTB_CUDA(cudaStreamCreateWithFlags(&d->comm_stream, cudaStreamNonBlocking));
     HTB_CUDA(cudaEventCreateWithFlags(&d->in_ready, cudaEventDisableTiming));
     HTB_CUDA(cudaEventCreateWithFlags(&d->gather_done, cudaEventDisableTiming));
@@ -185,15 +235,15 @@ int htb_dist_add_product_local_to_local(htb_handle h, const void *alpha, const v
     HTB_CUDA(cudaEventRecord(d->in_ready, st));
     HTB_CUDA(cudaStreamWaitEvent(d->comm_stream, d->in_ready, 0));
     if (d->world > 1) {
-        HTB_NCCL(ncclGroupStart());
+        HTB_NCCL(nccl().GroupStart());
         for (int r = 0; r < d->world; r++) {
             const size_t count = size_t(d->offsets[r + 1] - d->offsets[r]) * es;
             if (count == 0)
                 continue;
             char *seg = xg + size_t(d->offsets[r]) * es;
-            HTB_NCCL(ncclBroadcast(seg, seg, count, ncclChar, r, d->comm, d->comm_stream));
+            HTB_NCCL(nccl().Broadcast(seg, seg, count, ncclChar, r, d->comm, d->comm_stream));
         }
-        HTB_NCCL(ncclGroupEnd());
+        HTB_NCCL(nccl().GroupEnd());
     }
     HTB_CUDA(cudaEventRecord(d->gather_done, d->comm_stream));
 

@@ -43,6 +43,13 @@ struct htb_operator {
     void *d_work_in = nullptr, *d_work_out = nullptr;
     size_t work_cap = 0;
     int64_t launches = 0;
+    // optional per-kernel timing (htb_profile_passes)
+    bool profiling = false;
+    struct TimedLaunch {
+        cudaEvent_t start, stop;
+        int kind;
+    };
+    std::vector<TimedLaunch> timed;
     size_t store_bytes = 0, descriptor_bytes = 0, workspace_bytes = 0;
     htb_info info{};
     htb::DistState *dist = nullptr;

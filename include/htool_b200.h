@@ -175,6 +175,16 @@ const char *htb_last_error(void);
 int htb_device_count(int *count);
 /* Number of kernel launches issued by the handle since creation (bench.py reports it). */
 int htb_launch_count(htb_handle h, int64_t *count);
+/* Per-kernel timing with CUDA events recorded on the launching stream around every launch (off by
+ * default; serialises nothing that was not already serial). htb_get_pass_times synchronises, returns the
+ * accumulated device milliseconds and launch counts per kernel kind since the last call, and resets them. */
+enum { HTB_PASS_REDUCE = 0, /* t = V x / op(U)^T x / op(A)^T x, streams one side of the store */
+       HTB_PASS_COMBINE = 1, /* folds per-block partial t vectors */
+       HTB_PASS_APPLY = 2,   /* y = beta y + alpha (U t + A x) / op(V)^T t, streams one side of the store */
+       HTB_PASS_OTHER = 3,   /* permutations, scaling */
+       HTB_PASS_KINDS = 4 };
+int htb_profile_passes(htb_handle h, int enable);
+int htb_get_pass_times(htb_handle h, double ms[HTB_PASS_KINDS], int64_t launches[HTB_PASS_KINDS]);
 /* Tunables (stage bytes, block rows, ...) for experiments; unknown keys return HTB_ERR_INVALID. Must be
  * set before htb_create, they are read when the store is packed. */
 int htb_set_option(const char *key, int64_t value);

@@ -1,0 +1,151 @@
+"""CPU tests of the host logic: C-ABI surface, packer / stream format and pass sequences.
+
+The packed bytes (what htb_create would upload) are obtained through htb_pack_host and interpreted by
+tests/stream_emulator.py with the same walk as the CUDA kernels; results are compared with the oracle and
+the golden reference vectors. No compute entry point is called (there is no GPU here and no CPU fallback:
+htb_create must fail with HTB_ERR_CUDA).
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+from conftest import GOLDEN, REPO, load_golden, rel_err, rnd, valid_trans
+
+from htool_b200 import capi
+from oracle.flatcase import random_flatcase
+from stream_emulator import Emulator, PackedSide
+
+TOL = 1e-13
+
+
+def test_library_exports_every_declared_symbol():
+    lib = capi.load()
+    header = open(os.path.join(REPO, "include", "htool_b200.h")).read()
+    declared = set(re.findall(r"\b(htb_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(capi.htb_leaf) == 40
+    assert C.sizeof(capi.htb_hmatrix_desc) == 48
+    assert C.sizeof(capi.htb_info) == 8 * 9 + 4 * 10
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    flat = random_flatcase(seed=0)
+    with pytest.raises(capi.HtbError) as ei:
+        capi.Operator(flat.desc)
+    assert ei.value.status == capi.HTB_ERR_CUDA
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_invalid_descriptions_are_rejected():
+    lib = capi.load()
+    flat = random_flatcase(seed=1, n_leaves=5)
+    bad = random_flatcase(seed=1, n_leaves=5)
+    bad.table[2, 0] = bad.nb_rows  # leaf outside the root block
+    bad._build_desc()
+    p = capi.htb_packed_side()
+    assert lib.htb_pack_host(C.byref(bad.desc), 0, C.byref(p)) == capi.HTB_ERR_INVALID
+    assert b"outside" in lib.htb_last_error()
+    assert lib.htb_pack_host(C.byref(flat.desc), 2, C.byref(p)) == capi.HTB_ERR_INVALID
+    assert lib.htb_set_option(b"no_such_option", 1) == capi.HTB_ERR_INVALID
+
+
+def _check(flat, tol=TOL):
+    em = Emulator(flat)
+    rng = np.random.default_rng(3)
+    for trans in "NTC":
+        ni, no = (flat.nb_cols, flat.nb_rows) if trans == "N" else (flat.nb_rows, flat.nb_cols)
+        for alpha, beta in [(1.0, 0.0), (0.7, -1.3)]:
+            if flat.np_dtype == np.complex128:
+                alpha, beta = alpha * (1 + 0.5j), beta * (1 - 0.25j)
+            x, y0 = rnd(rng, ni, flat.np_dtype), rnd(rng, no, flat.np_dtype)
+            yo, ye = y0.copy(), y0.copy()
+            st = flat.oracle_vector_product(trans, alpha, x, beta, yo)
+            assert em.vector_product(trans, alpha, x, beta, ye) == st
+            if st == 0:
+                assert rel_err(ye, yo) < tol, (trans, alpha, beta)
+    return em
+
+
+@pytest.mark.parametrize("seed", range(3))
+@pytest.mark.parametrize("dtype_code,symmetric", [(0, None), (1, None), (0, "S"), (1, "S"), (1, "H")])
+def test_packed_stream_random_leaves(seed, dtype_code, symmetric):
+    _check(random_flatcase(seed=seed, dtype_code=dtype_code, symmetric=symmetric))
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_packed_stream_matches_golden(name):
+    flat, entries, _ = load_golden(name)
+    em = Emulator(flat)
+    for e in entries:
+        if e["mu"] != 1:
+            continue
+        y = e["y_in"].copy()
+        assert em.vector_product(e["trans"], e["alpha"], e["x"], e["beta"], y) == 0
+        assert rel_err(y, e["y_seq"]) < TOL, (name, e["trans"])
+
+
+@pytest.mark.parametrize("opts", [dict(block_rows=32, unit_elems=128, stage_bytes=4096), dict(block_rows=128, unit_elems=1024, stage_bytes=32768)])
+def test_packer_options(opts):
+    try:
+        for k, v in opts.items():
+            capi.set_option(k, v)
+        _check(random_flatcase(seed=5, symmetric="S"))
+        _check(random_flatcase(seed=6, dtype_code=1))
+    finally:
+        for k, v in dict(block_rows=64, unit_elems=512, stage_bytes=16384).items():
+            capi.set_option(k, v)
+
+
+def test_stream_invariants():
+    flat, _, _ = load_golden("d_N")
+    for s in (0, 1):
+        side = PackedSide(flat.desc, s)
+        # blocks tile the index space, in order
+        assert side.blocks["row_start"][0] == 0
+        assert (side.blocks["row_start"][1:] == side.blocks["row_start"][:-1] + side.blocks["nrows"][:-1]).all()
+        assert side.blocks["row_start"][-1] + side.blocks["nrows"][-1] == side.n
+        assert (side.blocks["nrows"] <= 64).all() and (side.blocks["nrows"] > 0).all()
+        # stages are 16-byte aligned, contiguous and within the granule
+        assert (side.stages["byte_off"] % 16 == 0).all() and (side.stages["nbytes"] % 16 == 0).all()
+        assert (side.stages["nbytes"] <= 16384).all()
+        assert (side.stages["byte_off"][1:] == side.stages["byte_off"][:-1] + side.stages["nbytes"][:-1]).all()
+        assert sorted(side.order.tolist()) == list(range(side.n_blocks))
+    # every coefficient is stored exactly once per side it is needed on: U + dense on side 0, V on side 1
+    tbl = flat.table
+    dense = tbl[:, 4] < 0
+    side0 = int((tbl[dense, 2].astype(np.int64) * tbl[dense, 3]).sum() + (tbl[~dense, 2].astype(np.int64) * tbl[~dense, 4]).sum())
+    side1 = int((tbl[~dense, 3].astype(np.int64) * tbl[~dense, 4]).sum())
+    for s, expect in ((0, side0), (1, side1)):
+        side = PackedSide(flat.desc, s)
+        n = 0
+        for st in range(len(side.stages)):
+            for u, row0, h, w, kind, twice, panel in side.units_of_stage(st, flat.np_dtype):
+                n += 0 if panel is None else h * w
+        assert n == expect
+
+
+def test_empty_and_degenerate_operators():
+    from oracle.flatcase import FlatCase
+
+    # no leaves at all: out <- beta * out
+    f = FlatCase(0, 37, 21, 0, 0, "N", "N", np.zeros((0, 6), np.int32), np.zeros(0))
+    em = Emulator(f)
+    x, y = np.ones(21), np.full(37, 2.0)
+    assert em.vector_product("N", 1.0, x, 0.5, y) == 0
+    assert np.allclose(y, 1.0)
+    # rank-0 low-rank leaf and 1 x 1 leaves
+    tbl = np.array([[0, 0, 5, 4, 0, 0], [3, 2, 1, 1, -1, 0], [1, 1, 1, 1, 1, 0]], np.int32)
+    f = FlatCase(0, 6, 5, 0, 0, "N", "N", tbl, np.array([2.0, 3.0, 4.0]))
+    _check(f)
