@@ -50,16 +50,20 @@ def parse_args():
     return ap.parse_args()
 
 
-def min_depth_for(n: int) -> int:
-    """Smallest d with n / 2^d < 46341 (reference int overflow in sympartialACA.hpp:100)."""
+def min_depth_for(n: int, n_partitions: int = 1) -> int:
+    """Smallest block-tree depth at which every cluster has < 46341 points, so that m * n of an admissible
+    block fits an int (reference overflow in sympartialACA.hpp:100). A binary cluster tree built
+    with size_partition == 1 has ONE child under the root (the partition level,
+    clustering/tree_builder/tree_builder.hpp:125-137), so depth d holds 2^(d-1) clusters there and 2^d
+    clusters when size_partition is a power of two >= 2."""
     d = 0
     while n / (2**d) >= 46341:
         d += 1
-    return d
+    return d + 1 if (n_partitions == 1 and d > 0) else d
 
 
 def case_kwargs(args, n_partitions=1, partition_rank=-1):
-    kw = dict(n=args.n, geometry="sphere_surface", epsilon=1e-4, eta=10.0, min_depth=min_depth_for(args.n), n_partitions=n_partitions, partition_rank=partition_rank)
+    kw = dict(n=args.n, geometry="sphere_surface", epsilon=1e-4, eta=10.0, min_depth=min_depth_for(args.n, n_partitions), n_partitions=n_partitions, partition_rank=partition_rank)
     if args.dtype == "double":
         kw.update(dtype="double", kernel="laplace_reg")
     else:
@@ -71,7 +75,7 @@ def case_kwargs(args, n_partitions=1, partition_rank=-1):
 
 def workload_name(args):
     k = "laplace" if args.dtype == "double" else "helmholtz_k5"
-    return f"{k}_N{args.n}_eps1e-4_eta10_leaf10_mindepth{min_depth_for(args.n)}_sym{args.symmetry}_mu{args.mu}"
+    return f"{k}_N{args.n}_eps1e-4_eta10_leaf10_mindepth{min_depth_for(args.n, args.gpus)}_sym{args.symmetry}_mu{args.mu}"
 
 
 class ClockSampler:
@@ -252,7 +256,10 @@ def run_ours(args):
         raise SystemExit(f"PARITY FAILURE: relative l2 error vs the reference CPU product = {parity:.3e} > 1e-12; no number is reported")
 
     # ---- device-resident timing -----------------------------------------------------------------------
-    stream = torch.cuda.current_stream()
+    # a dedicated, non-default stream: htb_set_stream(NULL) means "the handle's own stream", and the events that
+    # bracket the timed region must be recorded on the very stream the kernels are launched on
+    stream = torch.cuda.Stream()
+    assert stream.cuda_stream != 0
     op.set_stream(stream.cuda_stream)
     tdt = torch.float64 if dtype == np.float64 else torch.complex128
     if world > 1:
@@ -260,6 +267,7 @@ def run_ours(args):
     else:
         x_d = torch.from_numpy(x_global).cuda()
     y_d = torch.zeros(n_local * mu, dtype=tdt, device="cuda")
+    torch.cuda.synchronize()
 
     def step():
         if world > 1:

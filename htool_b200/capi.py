@@ -119,6 +119,7 @@ SYMBOLS = {
     "htb_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "htb_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "htb_set_option": (C.c_int, [C.c_char_p, C.c_int64]),
+    "htb_get_option": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64)]),
     "htb_profile_passes": (C.c_int, [C.c_void_p, C.c_int]),
     "htb_get_pass_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "htb_pack_host": (C.c_int, [C.POINTER(htb_hmatrix_desc), C.c_int, C.POINTER(htb_packed_side)]),
@@ -282,6 +283,13 @@ def nccl_unique_id() -> bytes:
 def set_option(key: str, value: int):
     lib = load()
     check(lib, lib.htb_set_option(key.encode(), int(value)))
+
+
+def get_option(key: str) -> int:
+    lib = load()
+    v = C.c_int64(0)
+    check(lib, lib.htb_get_option(key.encode(), C.byref(v)))
+    return int(v.value)
 
 
 def leaves_from_arrays(rows, cols, m, n, rank, flags, data0, data1):

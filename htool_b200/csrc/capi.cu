@@ -377,6 +377,17 @@ int htb_set_option(const char *key, int64_t value) {
     return HTB_OK;
 }
 
+int htb_get_option(const char *key, int64_t *value) {
+    if (!key || !value)
+        return fail(HTB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lock(g_option_mutex);
+    auto it = g_options.find(key);
+    if (it == g_options.end())
+        return fail(HTB_ERR_INVALID, std::string("unknown option ") + key);
+    *value = it->second;
+    return HTB_OK;
+}
+
 int htb_create(const htb_hmatrix_desc *desc, htb_handle *out) {
     if (!desc || !out)
         return fail(HTB_ERR_INVALID, "null argument");

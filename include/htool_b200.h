@@ -188,6 +188,7 @@ int htb_get_pass_times(htb_handle h, double ms[HTB_PASS_KINDS], int64_t launches
 /* Tunables (stage bytes, block rows, ...) for experiments; unknown keys return HTB_ERR_INVALID. Must be
  * set before htb_create, they are read when the store is packed. */
 int htb_set_option(const char *key, int64_t value);
+int htb_get_option(const char *key, int64_t *value);
 
 /* ---- packer introspection (host only, no CUDA) ----------------------------------------------------- */
 

@@ -95,27 +95,32 @@ INFO_KEYS = [
 ]
 
 
+def make_spec(*, dtype="double", kernel="laplace_reg", n=1000, n_source=None, geometry="sphere_surface",
+              geometry_source=None, same_cluster=True, z_target=0.0, z_source=0.0, epsilon=1e-4, eta=10.0,
+              symmetry="N", uplo="N", min_depth=0, leaf_size=0, n_partitions=1, partition_rank=-1, local_block=False,
+              compressor="sympartialACA", wavenumber=5.0) -> ref_case_spec:
+    s = ref_case_spec()
+    s.dtype = 0 if dtype in ("double", np.float64) else 1
+    s.kernel = KERNELS[kernel]
+    s.geometry_target = GEOMETRIES[geometry]
+    s.geometry_source = GEOMETRIES[geometry_source or geometry]
+    s.n_target = n
+    s.n_source = n_source or n
+    s.same_cluster = 1 if same_cluster else 0
+    s.min_depth, s.leaf_size = min_depth, leaf_size
+    s.n_partitions, s.partition_rank, s.local_block = n_partitions, partition_rank, 1 if local_block else 0
+    s.compressor = COMPRESSORS[compressor]
+    s.symmetry, s.uplo = ord(symmetry), ord(uplo)
+    s.z_target, s.z_source, s.epsilon, s.eta, s.wavenumber = z_target, z_source, epsilon, eta, wavenumber
+    return s
+
+
 class RefCase:
     """An H-matrix assembled by the reference + the reference's CPU products on it."""
 
-    def __init__(self, *, dtype="double", kernel="laplace_reg", n=1000, n_source=None, geometry="sphere_surface",
-                 geometry_source=None, same_cluster=True, z_target=0.0, z_source=0.0, epsilon=1e-4, eta=10.0,
-                 symmetry="N", uplo="N", min_depth=0, leaf_size=0, n_partitions=1, partition_rank=-1, local_block=False,
-                 compressor="sympartialACA", wavenumber=5.0):
+    def __init__(self, **kw):
         self.lib = load()
-        s = ref_case_spec()
-        s.dtype = 0 if dtype in ("double", np.float64) else 1
-        s.kernel = KERNELS[kernel]
-        s.geometry_target = GEOMETRIES[geometry]
-        s.geometry_source = GEOMETRIES[geometry_source or geometry]
-        s.n_target = n
-        s.n_source = n_source or n
-        s.same_cluster = 1 if same_cluster else 0
-        s.min_depth, s.leaf_size = min_depth, leaf_size
-        s.n_partitions, s.partition_rank, s.local_block = n_partitions, partition_rank, 1 if local_block else 0
-        s.compressor = COMPRESSORS[compressor]
-        s.symmetry, s.uplo = ord(symmetry), ord(uplo)
-        s.z_target, s.z_source, s.epsilon, s.eta, s.wavenumber = z_target, z_source, epsilon, eta, wavenumber
+        s = make_spec(**kw)
         self.spec = s
         self.np_dtype = np.float64 if s.dtype == 0 else np.complex128
         self.handle = self.lib.ref_case_create(C.byref(s))

@@ -116,9 +116,9 @@ def test_deterministic_bitwise(capi):
 
 
 @pytest.mark.parametrize("opts", [dict(block_rows=32, unit_elems=128, stage_bytes=4096, ring_stages=2), dict(block_rows=128, unit_elems=1024, stage_bytes=32768, ring_stages=3),
-                                  dict(evict_first=0, ring_stages=8, stage_bytes=8192)])
+                                  dict(evict_first=0, ring_stages=8, stage_bytes=8192, unit_elems=256)])
 def test_packer_and_launch_options(capi, opts):
-    defaults = dict(block_rows=64, unit_elems=512, stage_bytes=16384, ring_stages=4, evict_first=1)
+    defaults = {k: capi.get_option(k) for k in ("block_rows", "unit_elems", "stage_bytes", "ring_stages", "evict_first")}
     try:
         for k, v in opts.items():
             capi.set_option(k, v)
