@@ -88,12 +88,20 @@ class htb_packed_side(C.Structure):
         ("n_blocks", C.c_int32),
         ("n_stages", C.c_int64),
         ("n_combine", C.c_int64),
+        ("n_combine_dst", C.c_int64),
         ("stream_bytes", C.c_int64),
         ("scratch_elems", C.c_int64),
+        ("cs_base", C.c_int64),
+        ("cs_elems", C.c_int64),
+        ("part_base", C.c_int64),
+        ("part_elems", C.c_int64),
+        ("piece_cols", C.c_int32),
+        ("reserved", C.c_int32),
         ("blocks", C.c_void_p),
         ("stages", C.c_void_p),
         ("order", C.c_void_p),
         ("combine", C.c_void_p),
+        ("combine_dst", C.c_void_p),
         ("stream", C.c_void_p),
         ("owner", C.c_void_p),
     ]

@@ -28,7 +28,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 namespace {
 std::mutex g_option_mutex;
 std::map<std::string, int64_t> g_options = {
-    {"block_rows", 64}, {"unit_elems", 512}, {"stage_bytes", 16384}, {"ring_stages", 4}, {"evict_first", 1}, {"upload_chunk_mb", 256}};
+    {"block_rows", 64}, {"piece_cols", 16}, {"stage_bytes", 16384}, {"cseg_bytes", 2048}, {"ring_stages", 3}, {"reduce_ring_stages", 4}, {"evict_first", 1}, {"upload_chunk_mb", 256}};
 
 int64_t option(const char *key) {
     std::lock_guard<std::mutex> lock(g_option_mutex);
@@ -105,6 +105,7 @@ static int upload_store(htb_operator *h, const Packer &pk) {
         sd.n_blocks          = static_cast<int>(sl.blocks.size());
         sd.n_combine         = static_cast<int>(sl.combine.size());
         sd.any_twice         = sl.any_twice;
+        sd.cs_base           = sl.cs_base;
         h->host_blocks[s]    = sl.blocks;
         h->host_order[s]     = sl.order;
         if ((status = upload_vector(sl.blocks, &sd.blocks, h->owned)) != HTB_OK)
@@ -115,7 +116,9 @@ static int upload_store(htb_operator *h, const Packer &pk) {
             break;
         if ((status = upload_vector(sl.combine, &sd.combine, h->owned)) != HTB_OK)
             break;
-        h->descriptor_bytes += sl.blocks.size() * sizeof(BlockDesc) + sl.stages.size() * sizeof(StageDesc) + sl.order.size() * 4 + sl.combine.size() * sizeof(CombineEntry);
+        if ((status = upload_vector(sl.combine_dst, &sd.combine_dst, h->owned)) != HTB_OK)
+            break;
+        h->descriptor_bytes += sl.blocks.size() * sizeof(BlockDesc) + sl.stages.size() * sizeof(StageDesc) + sl.order.size() * 4 + sl.combine.size() * sizeof(CombineEntry) + sl.combine_dst.size() * sizeof(CombineDst);
         if (sl.stream_bytes == 0)
             continue;
         void *dstream = nullptr;
@@ -197,7 +200,8 @@ static int run_product(htb_operator *h, char trans, T alpha, const T *in, T beta
 #define count(expr, what) timed(std::strstr(what, "reduce") ? HTB_PASS_REDUCE : (std::strstr(what, "combine") ? HTB_PASS_COMBINE : HTB_PASS_APPLY), [&]() { return (expr); }, what)
     int rc;
     if (trans == 'N') {
-        // t = V x for every low-rank leaf (side 1 holds the V^T panels)
+        // direction 0 producers: t = V x for every low-rank leaf (side 1 holds the V^T panels) and the x slices of
+        // the dense leaves, written into the c-stream of side 0 (or into partials when a piece has several chunks)
         PassArgs<T> r1;
         r1.in = in, r1.in_len = h->nb_cols, r1.scratch = T1, r1.stride = stride;
         if (h->side[1].stream && !split) {
@@ -212,12 +216,12 @@ static int run_product(htb_operator *h, char trans, T alpha, const T *in, T beta
         }
         if (twice) {
             // second application of the leaves stored once under symmetry (add_hmatrix_vector_product.hpp:154-163):
-            // t' = op(U)^T x[target], z = op(A)^T x[target], op = conj for 'H'
+            // direction 1 producers restricted to those leaves, t' = op(U)^T x[target], z = op(A)^T x[target], op = conj for 'H'
             PassArgs<T> r0;
             r0.in = in, r0.in_len = h->nb_cols, r0.in_shift = D, r0.scratch = T2, r0.twice_only = 1, r0.conj = (sym == 'H' && is_complex), r0.stride = stride;
             if ((rc = count(launch_reduce<T>(h->side[0], h->launch_cfg, r0, st), "reduce(U, twice)")) != HTB_OK)
                 return rc;
-            if (h->side[0].n_combine && (rc = count(launch_combine<T>(h->side[0], T2, 1, st), "combine(U, twice)")) != HTB_OK)
+            if (h->side[1].n_combine && (rc = count(launch_combine<T>(h->side[1], T2, 1, st), "combine(U, twice)")) != HTB_OK)
                 return rc;
         }
         if (h->side[1].stream && split) {
@@ -229,11 +233,11 @@ static int run_product(htb_operator *h, char trans, T alpha, const T *in, T beta
             if (part.n_blocks && (rc = count(launch_reduce<T>(part, h->launch_cfg, r1, st), "reduce(V, remote)")) != HTB_OK)
                 return rc;
         }
-        if (h->side[1].stream && h->side[1].n_combine && (rc = count(launch_combine<T>(h->side[1], T1, 0, st), "combine(V)")) != HTB_OK)
+        if (h->side[1].stream && h->side[0].n_combine && (rc = count(launch_combine<T>(h->side[0], T1, 0, st), "combine(V)")) != HTB_OK)
             return rc;
         // y = beta y + alpha (U t + A x), rows owned by one CTA each
         PassArgs<T> a0;
-        a0.in = in, a0.in_len = h->nb_cols, a0.out = out, a0.out_len = h->nb_rows, a0.scratch = T1, a0.alpha = alpha, a0.beta = beta, a0.stride = stride;
+        a0.out = out, a0.out_len = h->nb_rows, a0.scratch = T1, a0.alpha = alpha, a0.beta = beta, a0.stride = stride;
         if ((rc = count(launch_apply<T>(h->side[0], h->launch_cfg, a0, st), "apply(U, A)")) != HTB_OK)
             return rc;
         if (twice) {
@@ -249,7 +253,7 @@ static int run_product(htb_operator *h, char trans, T alpha, const T *in, T beta
         if (h->side[0].stream) {
             if ((rc = count(launch_reduce<T>(h->side[0], h->launch_cfg, r0, st), "reduce(U, A)")) != HTB_OK)
                 return rc;
-            if (h->side[0].n_combine && (rc = count(launch_combine<T>(h->side[0], T1, 0, st), "combine(U)")) != HTB_OK)
+            if (h->side[1].n_combine && (rc = count(launch_combine<T>(h->side[1], T1, 0, st), "combine(U)")) != HTB_OK)
                 return rc;
         }
         if (twice) {
@@ -257,7 +261,7 @@ static int run_product(htb_operator *h, char trans, T alpha, const T *in, T beta
             r1.in = in, r1.in_len = h->nb_rows, r1.in_shift = -D, r1.scratch = T2, r1.twice_only = 1, r1.stride = stride;
             if ((rc = count(launch_reduce<T>(h->side[1], h->launch_cfg, r1, st), "reduce(V, twice)")) != HTB_OK)
                 return rc;
-            if (h->side[1].n_combine && (rc = count(launch_combine<T>(h->side[1], T2, 1, st), "combine(V, twice)")) != HTB_OK)
+            if (h->side[0].n_combine && (rc = count(launch_combine<T>(h->side[0], T2, 1, st), "combine(V, twice)")) != HTB_OK)
                 return rc;
         }
         PassArgs<T> a1;
@@ -266,7 +270,7 @@ static int run_product(htb_operator *h, char trans, T alpha, const T *in, T beta
             return rc;
         if (twice) {
             PassArgs<T> a0;
-            a0.in = in, a0.in_len = h->nb_rows, a0.in_shift = -D, a0.out = out, a0.out_len = h->nb_cols, a0.out_shift = D, a0.scratch = T2, a0.alpha = alpha, a0.beta = one, a0.twice_only = 1, a0.stride = stride;
+            a0.out = out, a0.out_len = h->nb_cols, a0.out_shift = D, a0.scratch = T2, a0.alpha = alpha, a0.beta = one, a0.twice_only = 1, a0.stride = stride;
             if ((rc = count(launch_apply<T>(h->side[0], h->launch_cfg, a0, st), "apply(U, A, twice)")) != HTB_OK)
                 return rc;
         }
@@ -404,8 +408,9 @@ int htb_create(const htb_hmatrix_desc *desc, htb_handle *out) {
 
     PackOptions popt;
     popt.block_rows  = static_cast<int>(option("block_rows"));
-    popt.unit_elems  = static_cast<int>(option("unit_elems"));
+    popt.piece_cols  = static_cast<int>(option("piece_cols"));
     popt.stage_bytes = static_cast<int>(option("stage_bytes"));
+    popt.cseg_bytes  = static_cast<int>(option("cseg_bytes"));
     std::unique_ptr<Packer> pk;
     try {
         pk = std::make_unique<Packer>(*desc, popt);
@@ -429,14 +434,16 @@ int htb_create(const htb_hmatrix_desc *desc, htb_handle *out) {
     h->scratch_elems  = pk->scratch_elems;
     h->launch_cfg.block_rows  = popt.block_rows;
     h->launch_cfg.stage_bytes = popt.stage_bytes;
+    h->launch_cfg.cseg_bytes  = popt.cseg_bytes;
     h->launch_cfg.ring_stages = static_cast<int>(option("ring_stages"));
+    h->launch_cfg.reduce_ring_stages = static_cast<int>(option("reduce_ring_stages"));
     h->launch_cfg.evict_first = static_cast<int>(option("evict_first"));
-    if (h->launch_cfg.ring_stages < 2 || h->launch_cfg.ring_stages > 16)
-        return fail(HTB_ERR_INVALID, "ring_stages must be in [2, 16]");
+    if (h->launch_cfg.ring_stages < 2 || h->launch_cfg.ring_stages > 16 || h->launch_cfg.reduce_ring_stages < 2 || h->launch_cfg.reduce_ring_stages > 16)
+        return fail(HTB_ERR_INVALID, "ring_stages / reduce_ring_stages must be in [2, 16]");
     cudaDeviceProp prop{};
     HTB_CUDA(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
-    if (apply_smem_bytes(h->launch_cfg, 16) > static_cast<size_t>(prop.sharedMemPerBlockOptin))
+    if (std::max(apply_smem_bytes(h->launch_cfg, 16), reduce_smem_bytes(h->launch_cfg, 16)) > static_cast<size_t>(prop.sharedMemPerBlockOptin))
         return fail(HTB_ERR_INVALID, "ring_stages * stage_bytes exceeds the shared memory of an SM");
     HTB_CUDA(configure_kernels(h->launch_cfg));
     HTB_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
@@ -447,8 +454,9 @@ int htb_create(const htb_hmatrix_desc *desc, htb_handle *out) {
         htb_destroy(h.release());
         return rc;
     }
-    // two scratch copies: first application, and the transposed second application under symmetric storage
-    const size_t scratch_bytes = std::max<size_t>(1, h->scratch_elems) * h->esize * 2;
+    // scratch copies: one for the product, a second one for the transposed second application under symmetric storage
+    const bool needs_second    = h->symmetry != 'N' && (h->side[0].any_twice || h->side[1].any_twice);
+    const size_t scratch_bytes = std::max<size_t>(2, h->scratch_elems) * h->esize * (needs_second ? 2 : 1);
     e                          = cudaMalloc(&h->d_scratch, scratch_bytes);
     if (e != cudaSuccess) {
         htb_destroy(h.release());
@@ -674,8 +682,9 @@ int htb_pack_host(const htb_hmatrix_desc *desc, int side, htb_packed_side *out) 
         return fail(HTB_ERR_INVALID, "invalid argument");
     PackOptions popt;
     popt.block_rows  = static_cast<int>(option("block_rows"));
-    popt.unit_elems  = static_cast<int>(option("unit_elems"));
+    popt.piece_cols  = static_cast<int>(option("piece_cols"));
     popt.stage_bytes = static_cast<int>(option("stage_bytes"));
+    popt.cseg_bytes  = static_cast<int>(option("cseg_bytes"));
     try {
         Packer pk(*desc, popt);
         auto *own   = new PackedOwner();
@@ -687,8 +696,15 @@ int htb_pack_host(const htb_hmatrix_desc *desc, int side, htb_packed_side *out) 
         out->n_blocks      = static_cast<int32_t>(own->layout.blocks.size());
         out->n_stages      = static_cast<int64_t>(own->layout.stages.size());
         out->n_combine     = static_cast<int64_t>(own->layout.combine.size());
+        out->n_combine_dst = static_cast<int64_t>(own->layout.combine_dst.size());
         out->stream_bytes  = static_cast<int64_t>(own->stream.size());
         out->scratch_elems = static_cast<int64_t>(pk.scratch_elems);
+        out->cs_base       = static_cast<int64_t>(own->layout.cs_base);
+        out->cs_elems      = static_cast<int64_t>(own->layout.cs_elems);
+        out->part_base     = static_cast<int64_t>(own->layout.part_base);
+        out->part_elems    = static_cast<int64_t>(own->layout.part_elems);
+        out->piece_cols    = pk.piece;
+        out->combine_dst   = own->layout.combine_dst.data();
         out->blocks        = own->layout.blocks.data();
         out->stages        = own->layout.stages.data();
         out->order         = own->layout.order.data();

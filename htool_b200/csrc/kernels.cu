@@ -8,13 +8,17 @@
 //     copies and a serialised axpy reduction.
 // How: every CTA owns one BLOCK of a side (store.hpp) and consumes that block's stream, stage by stage,
 // through a shared-memory ring filled by 1-D bulk-async copies (cp.async.bulk, the TMA engine; SASS
-// UBLKCP) that a single producer lane issues and mbarriers track. Eight consumer warps walk the units
-// of each stage out of shared memory:
-//   REDUCE  t[k] = sum_i op(P[i,k]) x[i]: the block's x sub-vector is staged in shared memory once,
-//           per-lane FMAs then a fixed-order warp-shuffle butterfly;
-//   APPLY   y[i] += sum_k op(P[i,k]) c[k]: per-warp private y accumulators in shared memory, summed over
-//           warps in warp order at the end and written once (y rows are owned by exactly one CTA):
-//           deterministic, no atomics, beta/alpha fused in the same epilogue.
+// UBLKCP) that a single producer lane issues and mbarriers track. Eight consumer warps take the units of
+// the stream round-robin (one unit = one h x w column-major panel, h <= block_rows, w <= 32):
+//   REDUCE  t[k] = sum_i op(P[i,k]) x[i]: the block's x sub-vector is staged in shared memory once. Lanes run
+//           along the rows (several columns side by side when h <= 16); the per-lane products of up to 8
+//           columns are folded with a TRANSPOSING butterfly (7 + log2(seg) - 3 shuffles for 8 columns
+//           instead of 8 * log2(seg)), in a fixed order;
+//   APPLY   y[i] += sum_k op(P[i,k]) c[k]: the c vectors of a stage (t pieces, x slices) arrive in shared
+//           memory with the stage itself (the c-stream segment, a second bulk copy on the same mbarrier).
+//           Lanes run along the rows, per-warp private y accumulators live in shared memory, are summed
+//           over the warps in warp order at the end and written once (y rows are owned by exactly one
+//           CTA): deterministic, no atomics, beta/alpha fused in the same epilogue.
 // Bandwidth-bound: every coefficient crosses HBM->SMEM once per pass and is used for one FMA.
 #include "kernels.cuh"
 
@@ -40,17 +44,14 @@ __device__ __forceinline__ double fma_(double a, double b, double c) { return fm
 __device__ __forceinline__ cplx fma_(cplx a, cplx b, cplx c) {
     return cplx{fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y))};
 }
-__device__ __forceinline__ double cj(double a, int) { return a; }
-__device__ __forceinline__ cplx cj(cplx a, int conj) { return conj ? cplx{a.x, -a.y} : a; }
+template <bool CONJ>
+__device__ __forceinline__ double cj(double a) { return a; }
+template <bool CONJ>
+__device__ __forceinline__ cplx cj(cplx a) { return CONJ ? cplx{a.x, -a.y} : a; }
 __device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 __device__ __forceinline__ cplx shfl_xor(cplx v, int m) { return cplx{__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m)}; }
-template <typename T>
-__device__ __forceinline__ T warp_sum(T v) {
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1)
-        v = add(v, shfl_xor(v, m));
-    return v;
-}
+__device__ __forceinline__ double select(bool p, double a, double b) { return p ? a : b; }
+__device__ __forceinline__ cplx select(bool p, cplx a, cplx b) { return cplx{p ? a.x : b.x, p ? a.y : b.y}; }
 
 // ---- mbarrier / bulk copy (inline PTX) -------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -91,38 +92,49 @@ struct KernelSide {
     const StageDesc *stages;
     const uint32_t *order;
     const unsigned char *stream;
-    int block_rows, stage_bytes, ring_stages, evict_first;
+    unsigned long long cs_base;
+    int block_rows, stage_bytes, cseg_bytes, ring_stages, evict_first;
 };
 
-// Shared-memory carve-up common to both kernels: [ring | vec | cbuf | barriers]
+// Shared-memory carve-up common to both kernels: [ring (slot = stage [+ c segment]) | vec | barriers]
 struct SmemLayout {
     unsigned char *ring;
-    unsigned char *vec;  // REDUCE: x sub-vector (block_rows). APPLY: per-warp y accumulators (warps x block_rows)
-    unsigned char *cbuf; // APPLY: per-warp c vector (warps x 32)
+    unsigned char *vec; // REDUCE: x sub-vector (block_rows). APPLY: per-warp y accumulators (warps x block_rows)
     uint64_t *full, *empty;
+    uint32_t slot_bytes;
 };
-__device__ __forceinline__ SmemLayout carve(unsigned char *base, const KernelSide &ks, size_t vec_bytes, size_t cbuf_bytes) {
+__device__ __forceinline__ SmemLayout carve(unsigned char *base, const KernelSide &ks, uint32_t slot_bytes, size_t vec_bytes) {
     SmemLayout s;
-    s.ring  = base;
-    s.vec   = base + static_cast<size_t>(ks.ring_stages) * ks.stage_bytes;
-    s.cbuf  = s.vec + vec_bytes;
-    s.full  = reinterpret_cast<uint64_t *>(s.cbuf + cbuf_bytes);
-    s.empty = s.full + ks.ring_stages;
+    s.ring       = base;
+    s.slot_bytes = slot_bytes;
+    s.vec        = base + static_cast<size_t>(ks.ring_stages) * slot_bytes;
+    s.full       = reinterpret_cast<uint64_t *>(s.vec + vec_bytes);
+    s.empty      = s.full + ks.ring_stages;
     return s;
 }
 
-// Producer: one lane streams the block's stages into the ring.
-__device__ __forceinline__ void produce(const KernelSide &ks, const BlockDesc &bd, const SmemLayout &sm, int twice_only) {
+// Producer: one lane streams the block's stages (and, for APPLY, their c segments) into the ring.
+template <typename T, bool WITH_C>
+__device__ __forceinline__ void produce(const KernelSide &ks, const BlockDesc &bd, const SmemLayout &sm, int ring, int twice_only, const T *cs) {
     const uint64_t policy = ks.evict_first ? l2_evict_first_policy() : 0;
     uint32_t it           = 0;
+    if (bd.n_stages == 0)
+        return;
+    StageDesc next = ks.stages[bd.first_stage];
     for (uint32_t st = 0; st < bd.n_stages; st++) {
-        const StageDesc sd = ks.stages[bd.first_stage + st];
+        const StageDesc sd = next;
+        if (st + 1 < bd.n_stages)
+            next = ks.stages[bd.first_stage + st + 1]; // in flight while this stage waits for its slot
         if (twice_only && !(sd.flags & 1u))
             continue;
-        const uint32_t slot = it % ks.ring_stages, round = it / ks.ring_stages;
+        const uint32_t slot = it % ring, round = it / ring;
+        const uint32_t cbytes = WITH_C ? static_cast<uint32_t>(sd.c_len * sizeof(T)) : 0u;
         mbar_wait(smem_u32(&sm.empty[slot]), (round & 1u) ^ 1u);
-        mbar_arrive_expect_tx(smem_u32(&sm.full[slot]), sd.nbytes);
-        bulk_g2s(smem_u32(sm.ring + static_cast<size_t>(slot) * ks.stage_bytes), ks.stream + sd.byte_off, sd.nbytes, smem_u32(&sm.full[slot]), policy, ks.evict_first != 0);
+        mbar_arrive_expect_tx(smem_u32(&sm.full[slot]), sd.nbytes + cbytes);
+        const uint32_t dst = smem_u32(sm.ring + static_cast<size_t>(slot) * sm.slot_bytes);
+        bulk_g2s(dst, ks.stream + sd.byte_off, sd.nbytes, smem_u32(&sm.full[slot]), policy, ks.evict_first != 0);
+        if (WITH_C && cbytes)
+            bulk_g2s(dst + ks.stage_bytes, cs + sd.c_off, cbytes, smem_u32(&sm.full[slot]), 0, false);
         it++;
     }
 }
@@ -138,14 +150,90 @@ __device__ __forceinline__ void init_barriers(const KernelSide &ks, const SmemLa
     }
 }
 
+// Lane geometry of a unit of height h: lanes are grouped in segments of seg = 2^seglog >= min(h, 32) lanes, lane li
+// of a segment owns row li (rows li + 32 q when h > 32) and the G = 32 / seg segments work on different columns.
+struct LaneMap {
+    int seglog, li, g, G;
+};
+__device__ __forceinline__ LaneMap lane_map(uint32_t h, int lane) {
+    LaneMap m;
+    m.seglog = h > 16 ? 5 : (h > 8 ? 4 : (h > 4 ? 3 : (h > 2 ? 2 : (h > 1 ? 1 : 0))));
+    m.li     = lane & ((1 << m.seglog) - 1);
+    m.g      = lane >> m.seglog;
+    m.G      = 32 >> m.seglog;
+    return m;
+}
+
+// v[c], c < J, per lane. For every c, sums v[c] over the lanes of each segment in a fixed order. On return the
+// first nv entries of v hold the totals of indices cbase .. cbase + nv - 1, and all lanes that agree on the bits
+// above lowmask hold the same totals. Halving steps exchange half of the values, so J values cost J - 1 (+ the
+// remaining butterfly steps) shuffles instead of J * log2(seg).
+template <typename T, int J>
+__device__ __forceinline__ void seg_reduce(T (&v)[J], int seglog, int li, int &cbase, int &nv, int &lowmask) {
+    int d     = (1 << seglog) >> 1;
+    int lastd = 1 << seglog;
+    cbase     = 0;
+    nv        = J;
+#pragma unroll
+    for (int n = J / 2; n >= 1; n /= 2) {
+        if (d >= 1) {
+            const bool up = (li & d) != 0;
+#pragma unroll
+            for (int c = 0; c < n; c++) {
+                const T keep = select(up, v[c + n], v[c]);
+                const T send = select(up, v[c], v[c + n]);
+                v[c]         = add(keep, shfl_xor(send, d));
+            }
+            cbase += up ? n : 0;
+            nv    = n;
+            lastd = d;
+            d >>= 1;
+        }
+    }
+    while (d >= 1) {
+        v[0] = add(v[0], shfl_xor(v[0], d));
+        d >>= 1;
+    }
+    lowmask = lastd - 1;
+}
+
+// Columns kb + c*G + g, c < J, of the panel: per-lane products with x, segment reduction, store of the totals.
+template <typename T, bool CONJ, int J>
+__device__ __forceinline__ void reduce_batch(const T *P, uint32_t h, uint32_t w, uint32_t kb, const LaneMap &m, int Q, const uint32_t (&ic)[kMaxQ], const T (&xv)[kMaxQ], T *out) {
+    T v[J];
+#pragma unroll
+    for (int c = 0; c < J; c++) {
+        const uint32_t k = kb + c * m.G + m.g;
+        const T *col     = P + static_cast<size_t>(k < w ? k : w - 1) * h; // clamped: the total of a column >= w is never stored
+        T s              = mul(cj<CONJ>(col[ic[0]]), xv[0]);
+        if (Q > 1)
+            s = fma_(cj<CONJ>(col[ic[1]]), xv[1], s);
+        if (Q > 2) {
+            s = fma_(cj<CONJ>(col[ic[2]]), xv[2], s);
+            s = fma_(cj<CONJ>(col[ic[3]]), xv[3], s);
+        }
+        v[c] = s;
+    }
+    int cbase, nv, lowmask;
+    seg_reduce<T, J>(v, m.seglog, m.li, cbase, nv, lowmask);
+    if ((m.li & lowmask) == 0) {
+#pragma unroll
+        for (int c = 0; c < J; c++) {
+            const uint32_t k = kb + (cbase + c) * m.G + m.g;
+            if (c < nv && k < w)
+                out[k] = v[c];
+        }
+    }
+}
+
 // ---- REDUCE -------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool CONJ>
 __global__ void __launch_bounds__(kThreads) reduce_kernel(KernelSide ks, PassArgs<T> a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const BlockDesc bd = ks.blocks[ks.order[blockIdx.x]];
     if (bd.n_stages == 0 || (a.twice_only && !(bd.flags & 1u)))
         return;
-    const SmemLayout sm = carve(smem_raw, ks, sizeof(T) * ks.block_rows, 0);
+    const SmemLayout sm = carve(smem_raw, ks, ks.stage_bytes, sizeof(T) * ks.block_rows);
     T *xin              = reinterpret_cast<T *>(sm.vec);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -159,50 +247,61 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(KernelSide ks, PassArg
 
     if (warp == kConsumerWarps) {
         if (lane == 0)
-            produce(ks, bd, sm, a.twice_only);
+            produce<T, false>(ks, bd, sm, ks.ring_stages, a.twice_only, nullptr);
         return;
     }
 
-    uint32_t it = 0;
+    uint32_t it = 0, ubase = 0;
     for (uint32_t st = 0; st < bd.n_stages; st++) {
         if (a.twice_only && !(ks.stages[bd.first_stage + st].flags & 1u))
             continue;
         const uint32_t slot = it % ks.ring_stages, round = it / ks.ring_stages;
         mbar_wait(smem_u32(&sm.full[slot]), round & 1u);
-        const unsigned char *stage = sm.ring + static_cast<size_t>(slot) * ks.stage_bytes;
+        const unsigned char *stage = sm.ring + static_cast<size_t>(slot) * sm.slot_bytes;
         const StageHeader hdr      = *reinterpret_cast<const StageHeader *>(stage);
         const Unit *units          = reinterpret_cast<const Unit *>(stage + sizeof(StageHeader));
         const T *data              = reinterpret_cast<const T *>(stage + hdr.data_byte_off);
-        for (uint32_t u = warp; u < hdr.n_units; u += kConsumerWarps) {
+        // units are dealt round-robin over the warps ACROSS stages, so that a stage with few units does not
+        // always land on the same warps
+        for (uint32_t u = (warp - ubase) & (kConsumerWarps - 1); u < hdr.n_units; u += kConsumerWarps) {
             const Unit un       = units[u];
             const uint32_t kind = unit_kind(un.geom);
-            if (kind == UNIT_ADDVEC || (a.twice_only && !unit_twice(un.geom)))
+            if (a.twice_only && !unit_twice(un.geom))
                 continue;
             const uint32_t row0 = unit_row0(un.geom), h = unit_h(un.geom), w = unit_w(un.geom);
-            const T *P = data + un.data_off;
+            T *out = a.scratch + un.out;
+            if (kind == UNIT_ADDVEC) {
+                // dense leaf, direction 0: hand its x slice to the APPLY pass through the c-stream
+                for (uint32_t i = lane; i < h; i += 32)
+                    out[i] = xin[row0 + i];
+                continue;
+            }
+            const T *P       = data + un.data_off;
+            const LaneMap m  = lane_map(h, lane);
+            const int Q      = (h + 31) >> 5;
+            uint32_t ic[kMaxQ];
             T xv[kMaxQ];
 #pragma unroll
             for (int q = 0; q < kMaxQ; q++) {
-                const uint32_t i = lane + 32u * q;
+                const uint32_t i = m.li + 32u * q;
+                ic[q]            = i < h ? i : h - 1;
                 xv[q]            = i < h ? xin[row0 + i] : zero_of(T{});
             }
-            T mine = zero_of(T{});
-            for (uint32_t k = 0; k < w; k++) {
-                const T *col = P + static_cast<size_t>(k) * h;
-                T s          = zero_of(T{});
-#pragma unroll
-                for (int q = 0; q < kMaxQ; q++) {
-                    const uint32_t i = lane + 32u * q;
-                    if (i < h)
-                        s = fma_(cj(col[i], a.conj), xv[q], s);
+            for (uint32_t kb = 0; kb < w;) {
+                const uint32_t per_seg = (w - kb + m.G - 1) / m.G; // columns left for each segment
+                if (per_seg > 4) {
+                    reduce_batch<T, CONJ, 8>(P, h, w, kb, m, Q, ic, xv, out);
+                    kb += 8 * m.G;
+                } else if (per_seg > 2) {
+                    reduce_batch<T, CONJ, 4>(P, h, w, kb, m, Q, ic, xv, out);
+                    kb += 4 * m.G;
+                } else {
+                    reduce_batch<T, CONJ, 2>(P, h, w, kb, m, Q, ic, xv, out);
+                    kb += 2 * m.G;
                 }
-                s = warp_sum(s);
-                if (lane == k)
-                    mine = s;
             }
-            if (lane < w)
-                a.scratch[static_cast<size_t>(un.aux_reduce) + lane] = mine;
         }
+        ubase = (ubase + hdr.n_units) & (kConsumerWarps - 1);
         __syncwarp();
         if (lane == 0)
             mbar_arrive(smem_u32(&sm.empty[slot]));
@@ -211,13 +310,13 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(KernelSide ks, PassArg
 }
 
 // ---- APPLY --------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool CONJ>
 __global__ void __launch_bounds__(kThreads) apply_kernel(KernelSide ks, PassArgs<T> a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const BlockDesc bd = ks.blocks[ks.order[blockIdx.x]];
     if (a.twice_only && !(bd.flags & 1u))
         return; // accumulate-only pass and nothing to add
-    const SmemLayout sm = carve(smem_raw, ks, sizeof(T) * ks.block_rows * kConsumerWarps, sizeof(T) * 32 * kConsumerWarps);
+    const SmemLayout sm = carve(smem_raw, ks, ks.stage_bytes + ks.cseg_bytes, sizeof(T) * ks.block_rows * kConsumerWarps);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     T *yacc_all = reinterpret_cast<T *>(sm.vec);
 
@@ -228,68 +327,87 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(KernelSide ks, PassArgs
 
     if (warp == kConsumerWarps) {
         if (lane == 0)
-            produce(ks, bd, sm, a.twice_only);
+            produce<T, true>(ks, bd, sm, ks.ring_stages, a.twice_only, a.scratch + ks.cs_base);
     } else {
-        T *yacc = yacc_all + static_cast<size_t>(warp) * ks.block_rows;
-        T *cbuf = reinterpret_cast<T *>(sm.cbuf) + warp * 32;
-        uint32_t it = 0;
+        T *yacc     = yacc_all + static_cast<size_t>(warp) * ks.block_rows;
+        uint32_t it = 0, ubase = 0;
         for (uint32_t st = 0; st < bd.n_stages; st++) {
             if (a.twice_only && !(ks.stages[bd.first_stage + st].flags & 1u))
                 continue;
             const uint32_t slot = it % ks.ring_stages, round = it / ks.ring_stages;
             mbar_wait(smem_u32(&sm.full[slot]), round & 1u);
-            const unsigned char *stage = sm.ring + static_cast<size_t>(slot) * ks.stage_bytes;
+            const unsigned char *stage = sm.ring + static_cast<size_t>(slot) * sm.slot_bytes;
             const StageHeader hdr      = *reinterpret_cast<const StageHeader *>(stage);
             const Unit *units          = reinterpret_cast<const Unit *>(stage + sizeof(StageHeader));
             const T *data              = reinterpret_cast<const T *>(stage + hdr.data_byte_off);
-            for (uint32_t u = warp; u < hdr.n_units; u += kConsumerWarps) {
+            const T *cseg              = reinterpret_cast<const T *>(stage + ks.stage_bytes);
+            for (uint32_t u = (warp - ubase) & (kConsumerWarps - 1); u < hdr.n_units; u += kConsumerWarps) {
                 const Unit un = units[u];
                 if (a.twice_only && !unit_twice(un.geom))
                     continue;
                 const uint32_t kind = unit_kind(un.geom);
                 const uint32_t row0 = unit_row0(un.geom), h = unit_h(un.geom), w = unit_w(un.geom);
+                const T *c = cseg + un.cslot;
                 if (kind == UNIT_ADDVEC) {
                     // dense leaf applied transposed: its z = op(A)^T x was produced by the REDUCE pass of side 0
                     for (uint32_t i = lane; i < h; i += 32)
-                        yacc[row0 + i] = add(yacc[row0 + i], a.scratch[static_cast<size_t>(un.aux_apply) + i]);
+                        yacc[row0 + i] = add(yacc[row0 + i], c[i]);
                     continue;
                 }
-                // c vector: t (low rank) from scratch, or the x slice (dense) from the input vector
-                T cv = zero_of(T{});
-                if (lane < w) {
-                    if (kind == UNIT_LOWRANK) {
-                        cv = a.scratch[static_cast<size_t>(un.aux_apply) + lane];
-                    } else {
-                        const long long g = static_cast<long long>(un.aux_apply) + lane + a.in_shift;
-                        if (g >= 0 && g < a.in_len)
-                            cv = a.in[g * a.stride];
-                    }
-                }
-                __syncwarp();
-                cbuf[lane] = cv;
-                __syncwarp();
                 const T *P = data + un.data_off;
-                T acc[kMaxQ];
+                if (h > 16) {
+                    // lanes along the rows, every lane walks all the columns
+                    const int Q = (h + 31) >> 5;
+                    uint32_t ic[kMaxQ];
+                    T acc[kMaxQ];
 #pragma unroll
-                for (int q = 0; q < kMaxQ; q++)
-                    acc[q] = zero_of(T{});
-                for (uint32_t k = 0; k < w; k++) {
-                    const T c    = cbuf[k];
-                    const T *col = P + static_cast<size_t>(k) * h;
+                    for (int q = 0; q < kMaxQ; q++) {
+                        const uint32_t i = lane + 32u * q;
+                        ic[q]            = i < h ? i : h - 1;
+                        acc[q]           = zero_of(T{});
+                    }
+                    if (Q == 1) {
+#pragma unroll 4
+                        for (uint32_t k = 0; k < w; k++)
+                            acc[0] = fma_(cj<CONJ>(P[k * h + ic[0]]), c[k], acc[0]);
+                    } else if (Q == 2) {
+#pragma unroll 4
+                        for (uint32_t k = 0; k < w; k++) {
+                            const T ck   = c[k];
+                            const T *col = P + k * h;
+                            acc[0]       = fma_(cj<CONJ>(col[ic[0]]), ck, acc[0]);
+                            acc[1]       = fma_(cj<CONJ>(col[ic[1]]), ck, acc[1]);
+                        }
+                    } else {
+#pragma unroll 2
+                        for (uint32_t k = 0; k < w; k++) {
+                            const T ck   = c[k];
+                            const T *col = P + k * h;
+#pragma unroll
+                            for (int q = 0; q < kMaxQ; q++)
+                                acc[q] = fma_(cj<CONJ>(col[ic[q]]), ck, acc[q]);
+                        }
+                    }
 #pragma unroll
                     for (int q = 0; q < kMaxQ; q++) {
                         const uint32_t i = lane + 32u * q;
                         if (i < h)
-                            acc[q] = fma_(cj(col[i], a.conj), c, acc[q]);
+                            yacc[row0 + i] = add(yacc[row0 + i], acc[q]);
                     }
-                }
-#pragma unroll
-                for (int q = 0; q < kMaxQ; q++) {
-                    const uint32_t i = lane + 32u * q;
-                    if (i < h)
-                        yacc[row0 + i] = add(yacc[row0 + i], acc[q]);
+                } else {
+                    // short unit: G segments of lanes work on interleaved columns, then a butterfly over the segments
+                    const LaneMap m   = lane_map(h, lane);
+                    const uint32_t ic = static_cast<uint32_t>(m.li) < h ? m.li : h - 1;
+                    T acc             = zero_of(T{});
+                    for (uint32_t k = m.g; k < w; k += m.G)
+                        acc = fma_(cj<CONJ>(P[k * h + ic]), c[k], acc);
+                    for (int d = 1 << m.seglog; d < 32; d <<= 1)
+                        acc = add(acc, shfl_xor(acc, d));
+                    if (m.g == 0 && static_cast<uint32_t>(m.li) < h)
+                        yacc[row0 + m.li] = add(yacc[row0 + m.li], acc);
                 }
             }
+            ubase = (ubase + hdr.n_units) & (kConsumerWarps - 1);
             __syncwarp();
             if (lane == 0)
                 mbar_arrive(smem_u32(&sm.empty[slot]));
@@ -314,21 +432,29 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(KernelSide ks, PassArgs
 }
 
 // ---- small kernels ------------------------------------------------------------------------------------
+// One warp per piece: v = sum of its partials in chunk order (fixed summation order), then v (or the
+// sub-range a consumer asked for) is written into every consumer slot of the c-stream.
 template <typename T>
-__global__ void combine_kernel(const CombineEntry *entries, int n, T *scratch, int twice_only) {
+__global__ void combine_kernel(const CombineEntry *entries, const CombineDst *dsts, int n, T *scratch, int twice_only) {
     const int warps_per_block = blockDim.x >> 5;
     const int e               = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
     if (e >= n)
         return;
     const CombineEntry ce = entries[e];
-    if (twice_only && !(ce.n_chunks & 0x80000000u))
+    if (twice_only && !combine_twice(ce.packed))
         return;
-    const uint32_t nc = ce.n_chunks & 0x7fffffffu;
-    for (uint32_t k = threadIdx.x & 31; k < ce.w; k += 32) {
-        T s = zero_of(T{});
-        for (uint32_t c = 0; c < nc; c++) // chunk order: fixed summation order
-            s = add(s, scratch[static_cast<size_t>(ce.src) + static_cast<size_t>(c) * ce.w + k]);
-        scratch[static_cast<size_t>(ce.dst) + k] = s;
+    const uint32_t lane = threadIdx.x & 31, len = combine_len(ce.packed), n_sum = combine_n_sum(ce.packed);
+    T v = zero_of(T{});
+    if (lane < len) {
+        const T *p = scratch + ce.src + lane;
+#pragma unroll 4
+        for (uint32_t j = 0; j < n_sum; j++)
+            v = add(v, p[static_cast<size_t>(j) * len]);
+    }
+    for (uint32_t q = 0; q < ce.n_dst; q++) {
+        const CombineDst d = dsts[ce.dst_first + q];
+        if (lane >= d.sub_off && lane < static_cast<uint32_t>(d.sub_off) + d.sub_len)
+            scratch[d.slot + lane - d.sub_off] = v;
     }
 }
 
@@ -340,13 +466,11 @@ __global__ void permute_kernel(const T *in, T *out, const int32_t *perm, int n, 
     const int i = static_cast<int>(idx / mu), c = static_cast<int>(idx % mu);
     const int p = perm[i];
     // cluster side is row-major (i*mu + c); user side is row-major or column-major (c*n + i)
-    if (gather) { // cluster[i] = user[perm[i]]
-        const long long u = colmajor_user ? static_cast<long long>(c) * n + p : static_cast<long long>(p) * mu + c;
-        out[idx]          = in[u];
-    } else { // user[perm[i]] = cluster[i]
-        const long long u = colmajor_user ? static_cast<long long>(c) * n + p : static_cast<long long>(p) * mu + c;
-        out[u]            = in[idx];
-    }
+    const long long u = colmajor_user ? static_cast<long long>(c) * n + p : static_cast<long long>(p) * mu + c;
+    if (gather) // cluster[i] = user[perm[i]]
+        out[idx] = in[u];
+    else // user[perm[i]] = cluster[i]
+        out[u] = in[idx];
 }
 
 template <typename T>
@@ -356,40 +480,71 @@ __global__ void scale_kernel(T *y, long long n, T beta, int beta_is_zero) {
         y[i] = beta_is_zero ? zero_of(T{}) : mul(beta, y[i]);
 }
 
-inline KernelSide make_kernel_side(const SideDevice &s, const LaunchConfig &cfg) {
-    return KernelSide{s.blocks, s.stages, s.order, s.stream, cfg.block_rows, cfg.stage_bytes, cfg.ring_stages, cfg.evict_first};
+inline KernelSide make_kernel_side(const SideDevice &s, const LaunchConfig &cfg, int ring) {
+    return KernelSide{s.blocks, s.stages, s.order, s.stream, s.cs_base, cfg.block_rows, cfg.stage_bytes, cfg.cseg_bytes, ring, cfg.evict_first};
 }
 
 inline bool is_zero(double v) { return v == 0.; }
 inline bool is_zero(cplx v) { return v.x == 0. && v.y == 0.; }
 
+template <typename T>
+struct Kernels;
+template <>
+struct Kernels<double> {
+    static void reduce(const KernelSide &ks, const PassArgs<double> &a, int grid, size_t smem, cudaStream_t st) { reduce_kernel<double, false><<<grid, kThreads, smem, st>>>(ks, a); }
+    static void apply(const KernelSide &ks, const PassArgs<double> &a, int grid, size_t smem, cudaStream_t st) { apply_kernel<double, false><<<grid, kThreads, smem, st>>>(ks, a); }
+    static cudaError_t configure(int rs, int as) {
+        cudaError_t e = cudaFuncSetAttribute(reduce_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs);
+        return e != cudaSuccess ? e : cudaFuncSetAttribute(apply_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, as);
+    }
+};
+template <>
+struct Kernels<cplx> {
+    static void reduce(const KernelSide &ks, const PassArgs<cplx> &a, int grid, size_t smem, cudaStream_t st) {
+        if (a.conj)
+            reduce_kernel<cplx, true><<<grid, kThreads, smem, st>>>(ks, a);
+        else
+            reduce_kernel<cplx, false><<<grid, kThreads, smem, st>>>(ks, a);
+    }
+    static void apply(const KernelSide &ks, const PassArgs<cplx> &a, int grid, size_t smem, cudaStream_t st) {
+        if (a.conj)
+            apply_kernel<cplx, true><<<grid, kThreads, smem, st>>>(ks, a);
+        else
+            apply_kernel<cplx, false><<<grid, kThreads, smem, st>>>(ks, a);
+    }
+    static cudaError_t configure(int rs, int as) {
+        cudaError_t e;
+        if ((e = cudaFuncSetAttribute(reduce_kernel<cplx, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs)) != cudaSuccess)
+            return e;
+        if ((e = cudaFuncSetAttribute(reduce_kernel<cplx, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs)) != cudaSuccess)
+            return e;
+        if ((e = cudaFuncSetAttribute(apply_kernel<cplx, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, as)) != cudaSuccess)
+            return e;
+        return cudaFuncSetAttribute(apply_kernel<cplx, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, as);
+    }
+};
+
 } // namespace
 
 size_t reduce_smem_bytes(const LaunchConfig &cfg, size_t esize) {
-    return static_cast<size_t>(cfg.ring_stages) * cfg.stage_bytes + esize * cfg.block_rows + 16 * static_cast<size_t>(cfg.ring_stages);
+    return static_cast<size_t>(cfg.reduce_ring_stages) * cfg.stage_bytes + esize * cfg.block_rows + 16 * static_cast<size_t>(cfg.reduce_ring_stages);
 }
 size_t apply_smem_bytes(const LaunchConfig &cfg, size_t esize) {
-    return static_cast<size_t>(cfg.ring_stages) * cfg.stage_bytes + esize * cfg.block_rows * kConsumerWarps + esize * 32 * kConsumerWarps + 16 * static_cast<size_t>(cfg.ring_stages);
+    return static_cast<size_t>(cfg.ring_stages) * (cfg.stage_bytes + cfg.cseg_bytes) + esize * cfg.block_rows * kConsumerWarps + 16 * static_cast<size_t>(cfg.ring_stages);
 }
 
 cudaError_t configure_kernels(const LaunchConfig &cfg) {
-    cudaError_t e;
-    if ((e = cudaFuncSetAttribute(reduce_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(reduce_smem_bytes(cfg, 8)))) != cudaSuccess)
+    cudaError_t e = Kernels<double>::configure(static_cast<int>(reduce_smem_bytes(cfg, 8)), static_cast<int>(apply_smem_bytes(cfg, 8)));
+    if (e != cudaSuccess)
         return e;
-    if ((e = cudaFuncSetAttribute(reduce_kernel<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(reduce_smem_bytes(cfg, 16)))) != cudaSuccess)
-        return e;
-    if ((e = cudaFuncSetAttribute(apply_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(apply_smem_bytes(cfg, 8)))) != cudaSuccess)
-        return e;
-    if ((e = cudaFuncSetAttribute(apply_kernel<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(apply_smem_bytes(cfg, 16)))) != cudaSuccess)
-        return e;
-    return cudaSuccess;
+    return Kernels<cplx>::configure(static_cast<int>(reduce_smem_bytes(cfg, 16)), static_cast<int>(apply_smem_bytes(cfg, 16)));
 }
 
 template <typename T>
 cudaError_t launch_reduce(const SideDevice &side, const LaunchConfig &cfg, const PassArgs<T> &args, cudaStream_t stream) {
     if (side.n_blocks == 0)
         return cudaSuccess;
-    reduce_kernel<T><<<side.n_blocks, kThreads, reduce_smem_bytes(cfg, sizeof(T)), stream>>>(make_kernel_side(side, cfg), args);
+    Kernels<T>::reduce(make_kernel_side(side, cfg, cfg.reduce_ring_stages), args, side.n_blocks, reduce_smem_bytes(cfg, sizeof(T)), stream);
     return cudaGetLastError();
 }
 
@@ -399,7 +554,7 @@ cudaError_t launch_apply(const SideDevice &side, const LaunchConfig &cfg, const 
         return cudaSuccess;
     PassArgs<T> a  = args;
     a.beta_is_zero = is_zero(args.beta) ? 1 : 0;
-    apply_kernel<T><<<side.n_blocks, kThreads, apply_smem_bytes(cfg, sizeof(T)), stream>>>(make_kernel_side(side, cfg), a);
+    Kernels<T>::apply(make_kernel_side(side, cfg, cfg.ring_stages), a, side.n_blocks, apply_smem_bytes(cfg, sizeof(T)), stream);
     return cudaGetLastError();
 }
 
@@ -408,7 +563,7 @@ cudaError_t launch_combine(const SideDevice &side, T *scratch, int twice_only, c
     if (side.n_combine == 0)
         return cudaSuccess;
     const int warps = 8;
-    combine_kernel<T><<<(side.n_combine + warps - 1) / warps, warps * 32, 0, stream>>>(side.combine, side.n_combine, scratch, twice_only);
+    combine_kernel<T><<<(side.n_combine + warps - 1) / warps, warps * 32, 0, stream>>>(side.combine, side.combine_dst, side.n_combine, scratch, twice_only);
     return cudaGetLastError();
 }
 
@@ -429,11 +584,11 @@ cudaError_t launch_scale(T *y, long long n, T beta, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-#define HTB_INSTANTIATE(T)                                                                                                    \
-    template cudaError_t launch_reduce<T>(const SideDevice &, const LaunchConfig &, const PassArgs<T> &, cudaStream_t);       \
-    template cudaError_t launch_apply<T>(const SideDevice &, const LaunchConfig &, const PassArgs<T> &, cudaStream_t);        \
-    template cudaError_t launch_combine<T>(const SideDevice &, T *, int, cudaStream_t);                                       \
-    template cudaError_t launch_permute<T>(const T *, T *, const int32_t *, int, int, bool, bool, cudaStream_t);              \
+#define HTB_INSTANTIATE(T)                                                                                              \
+    template cudaError_t launch_reduce<T>(const SideDevice &, const LaunchConfig &, const PassArgs<T> &, cudaStream_t); \
+    template cudaError_t launch_apply<T>(const SideDevice &, const LaunchConfig &, const PassArgs<T> &, cudaStream_t);  \
+    template cudaError_t launch_combine<T>(const SideDevice &, T *, int, cudaStream_t);                                 \
+    template cudaError_t launch_permute<T>(const T *, T *, const int32_t *, int, int, bool, bool, cudaStream_t);        \
     template cudaError_t launch_scale<T>(T *, long long, T, cudaStream_t);
 HTB_INSTANTIATE(double)
 HTB_INSTANTIATE(cplx)

@@ -7,40 +7,44 @@
 
 namespace htb {
 
-struct cplx {
+struct __align__(16) cplx {
     double x, y;
 };
 
 // Device view of one side of the store.
 struct SideDevice {
-    const BlockDesc *blocks    = nullptr;
-    const StageDesc *stages    = nullptr;
-    const uint32_t *order      = nullptr;
-    const unsigned char *stream = nullptr;
-    const CombineEntry *combine = nullptr;
-    int n_blocks               = 0;
-    int n_combine              = 0;
-    int n                      = 0;
-    bool any_twice             = false;
+    const BlockDesc *blocks         = nullptr;
+    const StageDesc *stages         = nullptr;
+    const uint32_t *order           = nullptr;
+    const unsigned char *stream     = nullptr;
+    const CombineEntry *combine     = nullptr; // direction whose consumer is this side
+    const CombineDst *combine_dst   = nullptr;
+    int n_blocks                    = 0;
+    int n_combine                   = 0;
+    int n                           = 0;
+    uint64_t cs_base                = 0; // element offset of CS[side] inside a scratch copy
+    bool any_twice                  = false;
 };
 
 struct LaunchConfig {
-    int block_rows   = 64;
-    int stage_bytes  = 16384;
-    int ring_stages  = 4;
-    int evict_first  = 1; // L2 evict_first hint on the coefficient stream
+    int block_rows  = 64;
+    int stage_bytes = 16384;
+    int cseg_bytes  = 2048;
+    int ring_stages = 3;        // APPLY ring depth (slot = stage + c segment)
+    int reduce_ring_stages = 4; // REDUCE ring depth (slot = stage)
+    int evict_first = 1; // L2 evict_first hint on the coefficient stream
 };
 
 // One pass over a side. Vectors are addressed as v[index * stride + column] (stride = mu, column = RHS).
 template <typename T>
 struct PassArgs {
-    const T *in   = nullptr; // REDUCE: multiplied vector. APPLY: source of the dense units' c vectors
+    const T *in      = nullptr; // REDUCE: multiplied vector
     long long in_len = 0;
-    int in_shift  = 0; // REDUCE: in index = block index + in_shift. APPLY(dense): in index = aux_apply + in_shift
-    T *out        = nullptr; // APPLY only
+    int in_shift     = 0; // REDUCE: in index = block index + in_shift
+    T *out           = nullptr; // APPLY only
     long long out_len = 0;
-    int out_shift = 0; // APPLY: out index = block index + out_shift
-    T *scratch    = nullptr; // REDUCE: destination of the partial sums. APPLY: t / z vectors
+    int out_shift    = 0; // APPLY: out index = block index + out_shift
+    T *scratch       = nullptr; // one scratch copy: REDUCE writes unit results, APPLY reads its c-stream
     T alpha{}, beta{};
     int beta_is_zero = 0; // APPLY: do not read out
     int twice_only   = 0; // only units of leaves applied twice (second, transposed application of symmetric storage)
@@ -52,13 +56,13 @@ template <typename T>
 cudaError_t launch_reduce(const SideDevice &side, const LaunchConfig &cfg, const PassArgs<T> &args, cudaStream_t stream);
 template <typename T>
 cudaError_t launch_apply(const SideDevice &side, const LaunchConfig &cfg, const PassArgs<T> &args, cudaStream_t stream);
-// scratch[dst..dst+w) = sum_c scratch[src + c*w ..): folds the per-chunk partials of the leaves that span several blocks
+// Folds the partials of the direction whose consumer is `side` and replicates them into the consumer slots.
 template <typename T>
 cudaError_t launch_combine(const SideDevice &side, T *scratch, int twice_only, cudaStream_t stream);
 
 // out[i] = in[perm[i]] (gather) / out[perm[i]] = in[i] (scatter), i < n, for mu interleaved columns:
 // cluster_node.hpp:150-175 (user_to_cluster / cluster_to_user) on the device.
-// transpose_in/out: the non-permuted side is column-major n x mu (user layout of add_hmatrix_matrix_product)
+// colmajor_user: the non-permuted side is column-major n x mu (user layout of add_hmatrix_matrix_product)
 // while the permuted side is row-major (mu contiguous).
 template <typename T>
 cudaError_t launch_permute(const T *in, T *out, const int32_t *perm, int n, int mu, bool gather, bool colmajor_user, cudaStream_t stream);

@@ -9,40 +9,47 @@
 
 namespace htb {
 
-namespace {
-
-struct UnitSpec {
+struct Packer::UnitSpec {
     uint32_t leaf;
+    uint64_t ui;      // unit index on its side
+    int chunk;        // chunk index of the leaf on this side
+    int piece;        // piece index of the leaf
     uint32_t row0, h; // rows [row0, row0+h) of the block
-    uint32_t p0;      // first panel row of the chunk (offset inside the leaf along this side)
-    uint32_t k0, w;   // panel columns [k0, k0+w)
+    uint32_t p0;      // offset of the unit's first row inside the leaf (along this side)
+    uint32_t k0, w;   // panel columns [k0, k0+w) (0, 0 for ADDVEC)
+    uint32_t sub_off; // ADDVEC: offset of the unit inside its piece
     uint32_t kind, twice;
-    uint32_t aux_apply, aux_reduce;
     uint32_t elems() const { return kind == UNIT_ADDVEC ? 0u : h * w; }
+    uint32_t celems() const { return kind == UNIT_ADDVEC ? h : w; }
 };
+
+namespace {
 
 inline uint32_t round16(uint64_t v) { return static_cast<uint32_t>((v + 15u) & ~uint64_t(15)); }
 
 // Greedy stage cutter shared by the layout pass and the fill pass so both see the same stages.
 struct StageCutter {
     size_t esize;
-    uint32_t stage_bytes;
-    uint32_t nu = 0;
-    uint64_t data_elems = 0;
-    bool fits(uint32_t elems) const {
+    uint32_t stage_bytes, cseg_bytes;
+    uint32_t nu         = 0;
+    uint64_t data_elems = 0, c_elems = 0;
+    bool fits(uint32_t elems, uint32_t celems) const {
         if (nu == 0)
             return true;
-        return 16u + 16u * (nu + 1u) + (data_elems + elems) * esize <= stage_bytes;
+        return 16u + 16u * (nu + 1u) + (data_elems + elems) * esize <= stage_bytes && (c_elems + celems) * esize <= cseg_bytes;
     }
-    void add(uint32_t elems) {
+    void add(uint32_t elems, uint32_t celems) {
         nu++;
         data_elems += elems;
+        c_elems += celems;
     }
     uint32_t header_bytes() const { return 16u + 16u * nu; }
     uint32_t nbytes() const { return round16(header_bytes() + data_elems * esize); }
+    uint32_t c_len_padded() const { return static_cast<uint32_t>(esize == 8 ? (c_elems + 1u) & ~uint64_t(1) : c_elems); }
     void reset() {
         nu         = 0;
         data_elems = 0;
+        c_elems    = 0;
     }
 };
 
@@ -53,13 +60,23 @@ Packer::Packer(const htb_hmatrix_desc &desc, const PackOptions &o) : dtype(desc.
         throw std::runtime_error("unknown dtype");
     if (desc.nb_rows < 0 || desc.nb_cols < 0 || desc.nb_leaves < 0 || (desc.nb_leaves > 0 && !desc.leaves))
         throw std::runtime_error("invalid H-matrix description");
-    if (opt.block_rows < 32 || opt.block_rows > 128 || opt.block_rows % 32)
-        throw std::runtime_error("block_rows must be 32, 64, 96 or 128");
-    if (opt.unit_elems < 32 || opt.stage_bytes % 16 || static_cast<size_t>(opt.stage_bytes) < 48 + static_cast<size_t>(std::max(opt.unit_elems, 32 * opt.block_rows / 32)) * 16)
-        throw std::runtime_error("invalid unit_elems / stage_bytes");
+    if (opt.block_rows != 32 && opt.block_rows != 64 && opt.block_rows != 128)
+        throw std::runtime_error("block_rows must be 32, 64 or 128");
+    if (opt.stage_bytes % 16 || opt.cseg_bytes % 16 || opt.stage_bytes > 65536 || opt.piece_cols < 1 || opt.piece_cols > 32)
+        throw std::runtime_error("invalid piece_cols / stage_bytes / cseg_bytes");
+    // a unit (block_rows x piece) and its descriptor must fit one stage; its c vector one c segment
+    piece = 1;
+    while (piece * 2 <= opt.piece_cols && 32u + static_cast<size_t>(opt.block_rows) * (piece * 2) * esize <= static_cast<size_t>(opt.stage_bytes))
+        piece *= 2;
+    if (32u + static_cast<size_t>(opt.block_rows) * piece * esize > static_cast<size_t>(opt.stage_bytes))
+        throw std::runtime_error("stage_bytes too small for one unit");
+    if (static_cast<size_t>(std::max(opt.block_rows, piece)) * esize > static_cast<size_t>(opt.cseg_bytes) || opt.cseg_bytes / esize > 65535)
+        throw std::runtime_error("cseg_bytes too small for one unit (or too large)");
     nb_rows  = desc.nb_rows;
     nb_cols  = desc.nb_cols;
     n_leaves = desc.nb_leaves;
+    if (n_leaves >= (int64_t(1) << 32))
+        throw std::runtime_error("too many leaves");
 
     // validation + statistics
     rank_min = INT32_MAX;
@@ -92,74 +109,61 @@ Packer::Packer(const htb_hmatrix_desc &desc, const PackOptions &o) : dtype(desc.
     if (n_lowrank == 0)
         rank_min = 0;
 
+    m_piece_ptr.assign(n_leaves + 1, 0);
+    for (int64_t i = 0; i < n_leaves; i++)
+        m_piece_ptr[i + 1] = m_piece_ptr[i] + (active(m_leaves[i]) ? n_pieces(m_leaves[i]) : 0);
+
     side[0].n = nb_rows;
     side[1].n = nb_cols;
     for (int s = 0; s < 2; s++)
         make_blocks(s);
     for (int s = 0; s < 2; s++)
         make_incidence(s);
-
-    // scratch layout: [final vectors | side-0 partials | side-1 partials]
-    m_toff.assign(n_leaves, 0);
-    uint64_t off = 0;
-    for (int64_t i = 0; i < n_leaves; i++) {
-        const htb_leaf &l = m_leaves[i];
-        m_toff[i]         = static_cast<uint32_t>(off);
-        off += l.rank < 0 ? l.nb_cols : l.rank;
-    }
-    for (int s = 0; s < 2; s++) {
-        m_pbase[s].assign(n_leaves, 0);
-        for (int64_t i = 0; i < n_leaves; i++) {
-            const htb_leaf &l = m_leaves[i];
-            uint64_t W        = l.rank < 0 ? (s == 0 ? l.nb_cols : 0) : l.rank; // dense leaves only reduce on side 0
-            if (m_nchunks[s][i] > 1 && W > 0) {
-                m_pbase[s][i] = static_cast<uint32_t>(off);
-                side[s].combine.push_back(CombineEntry{m_toff[i], static_cast<uint32_t>(off), static_cast<uint32_t>(W), static_cast<uint32_t>(m_nchunks[s][i]) | ((l.flags & HTB_LEAF_APPLY_TRANSPOSED_TOO) ? 0x80000000u : 0u)});
-                off += W * static_cast<uint64_t>(m_nchunks[s][i]);
-            } else {
-                m_pbase[s][i] = m_toff[i];
-            }
-            if (off >= (uint64_t(1) << 32))
-                throw std::runtime_error("scratch exceeds 2^32 elements");
-        }
-    }
-    scratch_elems = off;
+    make_partials();
 
     // per-block stage layout
+    std::vector<uint32_t> unit_stage[2];
     for (int s = 0; s < 2; s++) {
         const int nb = static_cast<int>(side[s].blocks.size());
+        const uint64_t nu = m_unit_ptr[s].back();
+        unit_stage[s].assign(nu, 0);
+        m_unit_cslot[s].assign(nu, 0);
+        m_unit_slot[s].assign(nu, 0);
         std::vector<std::vector<StageDesc>> per_block(nb);
         std::vector<uint64_t> units(nb, 0);
         std::vector<char> twice(nb, 0);
 #pragma omp parallel for schedule(dynamic, 16)
         for (int b = 0; b < nb; b++) {
             bool t = false;
-            layout_block(s, b, per_block[b], units[b], t);
+            layout_block(s, b, per_block[b], unit_stage[s], units[b], t);
             twice[b] = t;
         }
         m_block_off[s].assign(nb + 1, 0);
-        uint64_t stream = 0;
+        uint64_t stream = 0, c_off = 0;
         size_t nstages  = 0;
         for (int b = 0; b < nb; b++)
             nstages += per_block[b].size();
         side[s].stages.reserve(nstages);
         for (int b = 0; b < nb; b++) {
-            m_block_off[s][b]       = stream;
-            BlockDesc &bd           = side[s].blocks[b];
-            bd.first_stage          = static_cast<uint32_t>(side[s].stages.size());
-            bd.n_stages             = static_cast<uint32_t>(per_block[b].size());
-            bd.flags                = twice[b] ? 1u : 0u;
-            side[s].any_twice       = side[s].any_twice || twice[b];
+            m_block_off[s][b] = stream;
+            BlockDesc &bd     = side[s].blocks[b];
+            bd.first_stage    = static_cast<uint32_t>(side[s].stages.size());
+            bd.n_stages       = static_cast<uint32_t>(per_block[b].size());
+            bd.flags          = twice[b] ? 1u : 0u;
+            side[s].any_twice = side[s].any_twice || twice[b];
             side[s].n_units += units[b];
             for (StageDesc sd : per_block[b]) {
                 sd.byte_off += stream;
+                sd.c_off = static_cast<uint32_t>(c_off);
+                c_off += sd.c_len;
                 side[s].stages.push_back(sd);
             }
             if (!per_block[b].empty())
                 stream = side[s].stages.back().byte_off + side[s].stages.back().nbytes;
         }
-        m_block_off[s][nb]  = stream;
+        m_block_off[s][nb]   = stream;
         side[s].stream_bytes = stream;
+        side[s].cs_elems     = c_off;
         // heaviest blocks first: the hardware block scheduler then balances the tail
         side[s].order.resize(nb);
         std::iota(side[s].order.begin(), side[s].order.end(), 0u);
@@ -167,6 +171,29 @@ Packer::Packer(const htb_hmatrix_desc &desc, const PackOptions &o) : dtype(desc.
             return (m_block_off[s][a + 1] - m_block_off[s][a]) > (m_block_off[s][b + 1] - m_block_off[s][b]);
         });
     }
+
+    // scratch copy: [PART[0] | PART[1] | CS[0] | CS[1]], c-stream bases 16 B aligned
+    side[0].part_base = 0;
+    side[1].part_base = side[0].part_elems;
+    side[0].cs_base   = (side[1].part_base + side[1].part_elems + 1u) & ~uint64_t(1);
+    side[1].cs_base   = side[0].cs_base + side[0].cs_elems;
+    scratch_elems     = (side[1].cs_base + side[1].cs_elems + 1u) & ~uint64_t(1); // even: a second copy stays 16 B aligned
+    if (scratch_elems >= (uint64_t(1) << 32))
+        throw std::runtime_error("scratch exceeds 2^32 elements");
+    for (int s = 0; s < 2; s++) {
+        for (auto &p : m_part_off[s])
+            if (p != kDirect)
+                p += static_cast<uint32_t>(side[s].part_base);
+        const int nb = static_cast<int>(side[s].blocks.size());
+#pragma omp parallel for schedule(dynamic, 64)
+        for (int b = 0; b < nb; b++) {
+            const uint64_t u0 = m_unit_ptr[s][m_csr_ptr[s][b]], u1 = m_unit_ptr[s][m_csr_ptr[s][b + 1]];
+            for (uint64_t ui = u0; ui < u1; ui++)
+                m_unit_slot[s][ui] = static_cast<uint32_t>(side[s].cs_base + side[s].stages[side[s].blocks[b].first_stage + unit_stage[s][ui]].c_off + m_unit_cslot[s][ui]);
+        }
+    }
+    for (int s = 0; s < 2; s++)
+        make_combine(s);
 }
 
 // Cut [0, n) into blocks of <= block_rows indices. Cut points are taken where no small leaf (<= block_rows
@@ -178,9 +205,9 @@ void Packer::make_blocks(int s) {
     std::vector<int32_t> cost(static_cast<size_t>(n) + 2, 0);
     for (int64_t i = 0; i < n_leaves; i++) {
         const htb_leaf &l = m_leaves[i];
-        if (l.nb_rows == 0 || l.nb_cols == 0 || l.rank == 0)
+        if (!active(l))
             continue;
-        int a = s == 0 ? l.row_offset : l.col_offset, len = s == 0 ? l.nb_rows : l.nb_cols;
+        int a = start_of(s, l), len = extent_of(s, l);
         if (len >= 2 && len <= BR) {
             cost[a + 1]++;
             cost[a + len]--;
@@ -207,96 +234,244 @@ void Packer::make_blocks(int s) {
     }
     const int nb = static_cast<int>(start.size()) - 1;
     side[s].blocks.assign(nb, BlockDesc{});
+    m_blk_of[s].assign(static_cast<size_t>(n) + 1, 0);
     for (int b = 0; b < nb; b++) {
         side[s].blocks[b].row_start = start[b];
         side[s].blocks[b].nrows     = start[b + 1] - start[b];
+        for (int i = start[b]; i < start[b + 1]; i++)
+            m_blk_of[s][i] = b;
     }
 }
 
+void Packer::chunk_range(int s, uint32_t li, int c, int &lo, int &hi) const {
+    const htb_leaf &l = m_leaves[li];
+    const int a = start_of(s, l), len = extent_of(s, l), b = m_first_blk[s][li] + c;
+    lo = std::max(a, m_block_start[s][b]) - a;
+    hi = std::min(a + len, m_block_start[s][b + 1]) - a;
+}
+
+void Packer::addvec_pieces(uint32_t li, int c, int &p_lo, int &p_hi) const {
+    int lo, hi;
+    chunk_range(1, li, c, lo, hi);
+    p_lo = lo / piece;
+    p_hi = (hi - 1) / piece;
+}
+
+int Packer::units_in_incidence(int s, uint32_t li, int c) const {
+    const htb_leaf &l = m_leaves[li];
+    if (l.rank < 0 && s == 1) {
+        int p_lo, p_hi;
+        addvec_pieces(li, c, p_lo, p_hi);
+        return p_hi - p_lo + 1;
+    }
+    return n_pieces(l);
+}
+
 void Packer::make_incidence(int s) {
-    const int n  = side[s].n;
     const int nb = static_cast<int>(side[s].blocks.size());
-    std::vector<int32_t> blk_of(static_cast<size_t>(n) + 1, 0);
-    for (int b = 0; b < nb; b++)
-        for (int i = m_block_start[s][b]; i < m_block_start[s][b + 1]; i++)
-            blk_of[i] = b;
     m_first_blk[s].assign(n_leaves, 0);
     m_nchunks[s].assign(n_leaves, 0);
+    m_chunk_ptr[s].assign(n_leaves + 1, 0);
     m_csr_ptr[s].assign(static_cast<size_t>(nb) + 1, 0);
     for (int64_t i = 0; i < n_leaves; i++) {
         const htb_leaf &l = m_leaves[i];
-        if (l.nb_rows == 0 || l.nb_cols == 0 || l.rank == 0)
-            continue;
-        int a = s == 0 ? l.row_offset : l.col_offset, len = s == 0 ? l.nb_rows : l.nb_cols;
-        int b0 = blk_of[a], b1 = blk_of[a + len - 1];
-        m_first_blk[s][i] = b0;
-        m_nchunks[s][i]   = b1 - b0 + 1;
-        for (int b = b0; b <= b1; b++)
-            m_csr_ptr[s][b + 1]++;
+        if (active(l)) {
+            int a = start_of(s, l), len = extent_of(s, l);
+            int b0 = m_blk_of[s][a], b1 = m_blk_of[s][a + len - 1];
+            m_first_blk[s][i] = b0;
+            m_nchunks[s][i]   = b1 - b0 + 1;
+            for (int b = b0; b <= b1; b++)
+                m_csr_ptr[s][b + 1]++;
+        }
+        m_chunk_ptr[s][i + 1] = m_chunk_ptr[s][i] + m_nchunks[s][i];
     }
     for (int b = 0; b < nb; b++)
         m_csr_ptr[s][b + 1] += m_csr_ptr[s][b];
-    m_csr_leaf[s].assign(m_csr_ptr[s][nb], 0);
+    const uint64_t n_inc = m_csr_ptr[s][nb];
+    m_csr_leaf[s].assign(n_inc, 0);
+    m_inc_index[s].assign(n_inc, 0);
     std::vector<uint64_t> cursor(m_csr_ptr[s].begin(), m_csr_ptr[s].end() - 1);
     for (int64_t i = 0; i < n_leaves; i++) // leaf order is kept inside every block: fixed summation order
-        for (int c = 0; c < m_nchunks[s][i]; c++)
-            m_csr_leaf[s][cursor[m_first_blk[s][i] + c]++] = static_cast<uint32_t>(i);
+        for (int c = 0; c < m_nchunks[s][i]; c++) {
+            const uint64_t e                      = cursor[m_first_blk[s][i] + c]++;
+            m_csr_leaf[s][e]                      = static_cast<uint32_t>(i);
+            m_inc_index[s][m_chunk_ptr[s][i] + c] = e;
+        }
+    m_unit_ptr[s].assign(n_inc + 1, 0);
+    for (int b = 0; b < nb; b++)
+        for (uint64_t e = m_csr_ptr[s][b]; e < m_csr_ptr[s][b + 1]; e++) {
+            const uint32_t li    = m_csr_leaf[s][e];
+            m_unit_ptr[s][e + 1] = static_cast<uint64_t>(units_in_incidence(s, li, b - m_first_blk[s][li]));
+        }
+    for (uint64_t e = 0; e < n_inc; e++)
+        m_unit_ptr[s][e + 1] += m_unit_ptr[s][e];
+}
+
+// For every piece and direction (= consumer side cs): can its single producer write straight into its single
+// consumer slot, or does it go through partials + COMBINE? Offsets are relative to PART[cs] here.
+void Packer::make_partials() {
+    for (int cs = 0; cs < 2; cs++) {
+        const int ps = 1 - cs;
+        m_part_off[cs].assign(m_piece_ptr[n_leaves], kDirect);
+        uint64_t off = 0;
+        for (int64_t i = 0; i < n_leaves; i++) {
+            const htb_leaf &l = m_leaves[i];
+            if (!active(l))
+                continue;
+            const uint32_t li = static_cast<uint32_t>(i);
+            for (int p = 0; p < n_pieces(l); p++) {
+                const int len = piece_len(l, p);
+                int n_prod = m_nchunks[ps][i], n_cons = m_nchunks[cs][i];
+                bool sum_kind = true;
+                if (l.rank < 0) {
+                    // the ADDVEC units of side 1 that meet this piece
+                    const int a  = l.col_offset;
+                    const int c0 = m_blk_of[1][a + p * piece] - m_first_blk[1][li];
+                    const int c1 = m_blk_of[1][a + p * piece + len - 1] - m_first_blk[1][li];
+                    if (cs == 0) {
+                        n_prod   = c1 - c0 + 1;
+                        sum_kind = false; // x slices are copied, not summed
+                    } else {
+                        n_cons = c1 - c0 + 1;
+                    }
+                }
+                if (n_prod == 1 && n_cons == 1)
+                    continue;
+                m_part_off[cs][m_piece_ptr[i] + p] = static_cast<uint32_t>(off);
+                off += static_cast<uint64_t>(sum_kind ? n_prod : 1) * len;
+                if (off >= (uint64_t(1) << 32))
+                    throw std::runtime_error("scratch exceeds 2^32 elements");
+            }
+        }
+        side[cs].part_elems = off;
+    }
+}
+
+void Packer::make_combine(int cs) {
+    const int ps = 1 - cs;
+    SideLayout &sl = side[cs];
+    for (int64_t i = 0; i < n_leaves; i++) {
+        const htb_leaf &l = m_leaves[i];
+        if (!active(l))
+            continue;
+        const uint32_t li = static_cast<uint32_t>(i);
+        for (int p = 0; p < n_pieces(l); p++) {
+            const uint32_t po = m_part_off[cs][m_piece_ptr[i] + p];
+            if (po == kDirect)
+                continue;
+            const int len        = piece_len(l, p);
+            const bool sum_kind  = !(l.rank < 0 && cs == 0);
+            const uint32_t n_sum = sum_kind ? static_cast<uint32_t>(m_nchunks[ps][i]) : 1u;
+            if (n_sum >= (1u << 24))
+                throw std::runtime_error("too many chunks in one leaf");
+            CombineEntry ce{po, static_cast<uint32_t>(sl.combine_dst.size()), 0u, n_sum | (static_cast<uint32_t>(len) << 24) | ((l.flags & HTB_LEAF_APPLY_TRANSPOSED_TOO) ? 0x80000000u : 0u)};
+            if (l.rank < 0 && cs == 1) {
+                // consumers are the ADDVEC units that meet the piece, each wants its sub-range of z
+                const int a  = l.col_offset;
+                const int c0 = m_blk_of[1][a + p * piece] - m_first_blk[1][li];
+                const int c1 = m_blk_of[1][a + p * piece + len - 1] - m_first_blk[1][li];
+                for (int c = c0; c <= c1; c++) {
+                    int lo, hi, p_lo, p_hi;
+                    chunk_range(1, li, c, lo, hi);
+                    addvec_pieces(li, c, p_lo, p_hi);
+                    const int sub_lo = std::max(lo, p * piece), sub_hi = std::min(hi, p * piece + len);
+                    sl.combine_dst.push_back(CombineDst{m_unit_slot[1][unit_of(1, li, c, p - p_lo)], static_cast<uint16_t>(sub_lo - p * piece), static_cast<uint16_t>(sub_hi - sub_lo)});
+                }
+            } else {
+                for (int c = 0; c < m_nchunks[cs][i]; c++)
+                    sl.combine_dst.push_back(CombineDst{m_unit_slot[cs][unit_of(cs, li, c, p)], 0, static_cast<uint16_t>(len)});
+            }
+            ce.n_dst = static_cast<uint32_t>(sl.combine_dst.size()) - ce.dst_first;
+            sl.combine.push_back(ce);
+        }
+    }
+}
+
+// Where the REDUCE result of a producer unit of side ps goes.
+uint32_t Packer::producer_out(int ps, const UnitSpec &u) const {
+    const int cs      = 1 - ps;
+    const htb_leaf &l = m_leaves[u.leaf];
+    const uint32_t po = m_part_off[cs][m_piece_ptr[u.leaf] + u.piece];
+    if (po != kDirect) {
+        if (u.kind == UNIT_ADDVEC)
+            return po + u.sub_off; // copy kind: every producer fills its sub-range of the piece
+        return po + static_cast<uint32_t>(u.chunk) * static_cast<uint32_t>(piece_len(l, u.piece));
+    }
+    // direct: the single consumer unit of the piece
+    if (l.rank < 0 && cs == 1) {
+        const int c = m_blk_of[1][l.col_offset + u.piece * piece] - m_first_blk[1][u.leaf];
+        int p_lo, p_hi;
+        addvec_pieces(u.leaf, c, p_lo, p_hi);
+        return m_unit_slot[1][unit_of(1, u.leaf, c, u.piece - p_lo)];
+    }
+    return m_unit_slot[cs][unit_of(cs, u.leaf, 0, u.piece)];
 }
 
 template <typename Emit>
 void Packer::walk_block(int s, int b, Emit &&emit) const {
-    const int bs = m_block_start[s][b], be = m_block_start[s][b + 1];
+    const int bs = m_block_start[s][b];
     for (uint64_t e = m_csr_ptr[s][b]; e < m_csr_ptr[s][b + 1]; e++) {
         const uint32_t li = m_csr_leaf[s][e];
         const htb_leaf &l = m_leaves[li];
-        const int a = s == 0 ? l.row_offset : l.col_offset, len = s == 0 ? l.nb_rows : l.nb_cols;
-        const int lo = std::max(a, bs), hi = std::min(a + len, be);
+        const int a       = start_of(s, l);
+        const int chunk   = b - m_first_blk[s][li];
+        int lo, hi;
+        chunk_range(s, li, chunk, lo, hi);
         UnitSpec u{};
         u.leaf  = li;
-        u.row0  = static_cast<uint32_t>(lo - bs);
-        u.h     = static_cast<uint32_t>(hi - lo);
-        u.p0    = static_cast<uint32_t>(lo - a);
+        u.chunk = chunk;
         u.twice = (l.flags & HTB_LEAF_APPLY_TRANSPOSED_TOO) ? 1u : 0u;
-        const uint32_t chunk = static_cast<uint32_t>(b - m_first_blk[s][li]);
+        uint64_t ui = m_unit_ptr[s][e];
         if (l.rank < 0 && s == 1) {
-            u.kind       = UNIT_ADDVEC;
-            u.k0         = 0;
-            u.w          = 0;
-            u.aux_apply  = m_toff[li] + u.p0;
-            u.aux_reduce = 0;
-            emit(u);
+            int p_lo, p_hi;
+            addvec_pieces(li, chunk, p_lo, p_hi);
+            for (int p = p_lo; p <= p_hi; p++) {
+                const int sub_lo = std::max(lo, p * piece), sub_hi = std::min(hi, p * piece + piece_len(l, p));
+                u.ui      = ui++;
+                u.piece   = p;
+                u.kind    = UNIT_ADDVEC;
+                u.row0    = static_cast<uint32_t>(a + sub_lo - bs);
+                u.h       = static_cast<uint32_t>(sub_hi - sub_lo);
+                u.p0      = static_cast<uint32_t>(sub_lo);
+                u.k0      = 0;
+                u.w       = 0;
+                u.sub_off = static_cast<uint32_t>(sub_lo - p * piece);
+                emit(u);
+            }
             continue;
         }
-        const uint32_t W    = l.rank < 0 ? static_cast<uint32_t>(l.nb_cols) : static_cast<uint32_t>(l.rank);
-        const uint32_t wmax = std::min<uint32_t>(32u, std::max<uint32_t>(1u, static_cast<uint32_t>(opt.unit_elems) / u.h));
-        u.kind              = l.rank < 0 ? UNIT_DENSE : UNIT_LOWRANK;
-        const uint32_t red0 = m_pbase[s][li] + (m_nchunks[s][li] > 1 ? chunk * W : 0u);
-        for (uint32_t k0 = 0; k0 < W; k0 += wmax) {
-            u.k0         = k0;
-            u.w          = std::min(wmax, W - k0);
-            u.aux_apply  = l.rank < 0 ? static_cast<uint32_t>(l.col_offset) + k0 : m_toff[li] + k0;
-            u.aux_reduce = red0 + k0;
+        u.kind = l.rank < 0 ? UNIT_DENSE : UNIT_LOWRANK;
+        u.row0 = static_cast<uint32_t>(a + lo - bs);
+        u.h    = static_cast<uint32_t>(hi - lo);
+        u.p0   = static_cast<uint32_t>(lo);
+        for (int p = 0; p < n_pieces(l); p++) {
+            u.ui    = ui++;
+            u.piece = p;
+            u.k0    = static_cast<uint32_t>(p * piece);
+            u.w     = static_cast<uint32_t>(piece_len(l, p));
             emit(u);
         }
     }
 }
 
-void Packer::layout_block(int s, int b, std::vector<StageDesc> &stages, uint64_t &n_units, bool &any_twice) const {
-    StageCutter cut{esize, static_cast<uint32_t>(opt.stage_bytes)};
+void Packer::layout_block(int s, int b, std::vector<StageDesc> &stages, std::vector<uint32_t> &unit_stage, uint64_t &n_units, bool &any_twice) {
+    StageCutter cut{esize, static_cast<uint32_t>(opt.stage_bytes), static_cast<uint32_t>(opt.cseg_bytes)};
     uint64_t off     = 0;
-    uint32_t stflags = 0;
+    uint16_t stflags = 0;
     auto close       = [&]() {
         if (cut.nu == 0)
             return;
-        stages.push_back(StageDesc{off, cut.nbytes(), stflags});
+        stages.push_back(StageDesc{off, cut.nbytes(), 0u, static_cast<uint16_t>(cut.c_len_padded()), stflags, 0u});
         off += cut.nbytes();
         cut.reset();
         stflags = 0;
     };
     walk_block(s, b, [&](const UnitSpec &u) {
-        if (!cut.fits(u.elems()))
+        if (!cut.fits(u.elems(), u.celems()))
             close();
-        cut.add(u.elems());
+        unit_stage[u.ui]      = static_cast<uint32_t>(stages.size());
+        m_unit_cslot[s][u.ui] = static_cast<uint16_t>(cut.c_elems);
+        cut.add(u.elems(), u.celems());
         n_units++;
         if (u.twice) {
             stflags |= 1u;
@@ -323,7 +498,7 @@ inline std::complex<double> real_of(std::complex<double> v) { return std::comple
 
 template <typename T>
 void Packer::fill_block(int s, int b, char *dst) const {
-    StageCutter cut{esize, static_cast<uint32_t>(opt.stage_bytes)};
+    StageCutter cut{esize, static_cast<uint32_t>(opt.stage_bytes), static_cast<uint32_t>(opt.cseg_bytes)};
     std::vector<UnitSpec> pending;
     char *cursor = dst;
     auto close   = [&]() {
@@ -332,19 +507,19 @@ void Packer::fill_block(int s, int b, char *dst) const {
         const uint32_t nbytes = cut.nbytes();
         StageHeader hdr{cut.nu, cut.header_bytes(), {0, 0}};
         std::memcpy(cursor, &hdr, sizeof(hdr));
-        Unit *units = reinterpret_cast<Unit *>(cursor + sizeof(StageHeader));
-        T *data     = reinterpret_cast<T *>(cursor + cut.header_bytes());
+        Unit *units   = reinterpret_cast<Unit *>(cursor + sizeof(StageHeader));
+        T *data       = reinterpret_cast<T *>(cursor + cut.header_bytes());
         uint32_t eoff = 0;
         for (uint32_t i = 0; i < cut.nu; i++) {
             const UnitSpec &u = pending[i];
-            units[i]          = Unit{eoff, make_geom(u.row0, u.h, u.w, u.kind, u.twice), u.aux_apply, u.aux_reduce};
+            units[i]          = Unit{eoff, make_geom(u.row0, u.h, u.w, u.kind, u.twice), producer_out(s, u), m_unit_cslot[s][u.ui], 0};
             if (u.kind == UNIT_ADDVEC)
                 continue;
             const htb_leaf &l = m_leaves[u.leaf];
             T *out            = data + eoff;
             if (u.kind == UNIT_LOWRANK && s == 1) {
                 // Vt panel: element (i, k) = V[k + (p0+i) * r], V is r x n column-major
-                const T *V  = static_cast<const T *>(l.data1);
+                const T *V     = static_cast<const T *>(l.data1);
                 const size_t r = static_cast<size_t>(l.rank);
                 for (uint32_t k = 0; k < u.w; k++)
                     for (uint32_t i = 0; i < u.h; i++)
@@ -352,8 +527,8 @@ void Packer::fill_block(int s, int b, char *dst) const {
             } else if (u.kind == UNIT_DENSE && (l.flags & (HTB_LEAF_DIAG_SYMMETRIC | HTB_LEAF_DIAG_HERMITIAN))) {
                 // symv / hemv read only the UPLO triangle (add_matrix_vector_product.hpp:26-52): rebuild the full
                 // block from that triangle so the kernels see an ordinary dense leaf
-                const T *A     = static_cast<const T *>(l.data0);
-                const size_t m = static_cast<size_t>(l.nb_rows);
+                const T *A       = static_cast<const T *>(l.data0);
+                const size_t m   = static_cast<size_t>(l.nb_rows);
                 const bool upper = (l.flags & HTB_LEAF_UPLO_UPPER) != 0;
                 const bool herm  = (l.flags & HTB_LEAF_DIAG_HERMITIAN) != 0;
                 for (uint32_t k = 0; k < u.w; k++)
@@ -386,9 +561,9 @@ void Packer::fill_block(int s, int b, char *dst) const {
         pending.clear();
     };
     walk_block(s, b, [&](const UnitSpec &u) {
-        if (!cut.fits(u.elems()))
+        if (!cut.fits(u.elems(), u.celems()))
             close();
-        cut.add(u.elems());
+        cut.add(u.elems(), u.celems());
         pending.push_back(u);
     });
     close();

@@ -1,5 +1,5 @@
 // htool_b200/csrc/store.hpp — the device-resident flattened leaf store: formats shared by the host
-// packer (store.cpp) and the sm_100a kernels (kernels.cu).
+// packer (packer.cpp) and the sm_100a kernels (kernels.cu).
 //
 // Reference data model being re-laid-out (read-only, via htb_leaf): dense leaves are m x n column-major
 // (include/htool/matrix/matrix.hpp:20-26), low-rank leaves are U (m x r column-major) and V (r x n
@@ -10,18 +10,31 @@
 //     BLOCKS of <= block_rows consecutive indices, cut points chosen on leaf boundaries;
 //   * side 0 holds the U panels (m x r) and the dense leaves (m x n); side 1 holds the transposed V panels
 //     Vt = V^T (n x r), so every panel is "long dimension fast". A panel is cut by the side's blocks into
-//     CHUNKS (h x W, h <= block_rows), a chunk into UNITS of <= unit_elems coefficients (h x w, w <= 32),
-//     stored column-major with leading dimension h;
+//     CHUNKS (h x W, h <= block_rows) and along its short dimension into PIECES of <= piece_cols columns
+//     (the same cut on both sides of a leaf); one (chunk, piece) is a UNIT (h x w), stored column-major
+//     with leading dimension h. Rank and size bucketing happen through the (h, w) unit shape;
 //   * all units of one block are concatenated, in leaf order, into the block's STREAM, itself cut into
 //     STAGES (<= stage_bytes, 16 B aligned) = one bulk-async copy each. A stage starts with its own
-//     unit descriptors, so a CTA needs nothing but the stream: [StageHeader | Unit x n | coefficients].
-//   Every coefficient is stored exactly once per side it is needed on and is read exactly once per
-//   pass; rank and size bucketing happen through the (h, w) unit shape, not through separate arrays.
+//     unit descriptors, so a CTA needs nothing but the stream: [StageHeader | Unit x n | coefficients];
+//   * every coefficient is stored exactly once per side it is needed on and read exactly once per pass.
 //
 // Two generic passes run over a side (kernels.cu):
 //   REDUCE  partial[k] = sum_i op(P[i,k]) * in[i]     (t = V x, or t = op(U)^T x / z = op(A)^T x)
 //   APPLY   out[i]    += sum_k op(P[i,k]) * c[k]      (U t, A x, or op(Vt) t; + ADDVEC z)
 // and every product of the reference (N / T / C, plain / symmetric-twice) is a fixed sequence of them.
+//
+// How the c vectors reach APPLY (the "c-stream"): the scratch holds, for each side s, an array CS[s] with one
+// slot per unit of side s, IN THE ORDER OF THE SIDE'S STREAM, so that the slots of one stage are one
+// contiguous segment which the APPLY producer bulk-copies into shared memory next to the stage itself.
+// The slots are filled by the pass over the OTHER side:
+//   direction 0 (consumer side 0: y = A x):      REDUCE over side 1 writes t pieces (low rank) and x slices
+//                                                (dense leaves, through the coefficient-less ADDVEC units);
+//   direction 1 (consumer side 1: y = op(A)^T x): REDUCE over side 0 writes t' = op(U)^T x pieces and
+//                                                z = op(A)^T x slices (consumed by the ADDVEC units).
+// When a piece has exactly one producer unit and one consumer unit the producer writes straight into the
+// consumer's slot; otherwise producers write partials (PART[dir]) and a COMBINE pass sums them in chunk
+// order and replicates the result into every consumer slot.
+// One scratch copy = [PART[0] | PART[1] | CS[0] | CS[1]]; all offsets below are element offsets into a copy.
 #ifndef HTB_STORE_HPP
 #define HTB_STORE_HPP
 
@@ -39,15 +52,17 @@ namespace htb {
 
 enum UnitKind : uint32_t { UNIT_LOWRANK = 0, // panel of U (side 0) or of Vt (side 1)
                            UNIT_DENSE   = 1, // panel of a dense leaf (side 0 only)
-                           UNIT_ADDVEC  = 2  // side 1 only, no coefficients: out[i] += z[i] (dense leaf, transposed application)
+                           UNIT_ADDVEC  = 2  // side 1 only, no coefficients. REDUCE: slot <- in[rows] (x slice of a dense leaf).
+                                             //                               APPLY:  out[rows] += slot (z of a dense leaf applied transposed)
 };
 
 // geom: row0 [0:8) | h-1 [8:16) | w [16:24) | kind [24:26) | applied_twice [26]
 struct Unit {
-    uint32_t data_off;   // element offset of the h x w panel inside the stage's coefficient region
+    uint32_t data_off; // element offset of the h x w panel inside the stage's coefficient region
     uint32_t geom;
-    uint32_t aux_apply;  // LOWRANK: scratch offset of t[k0..k0+w). DENSE: first input index (leaf col_offset + k0). ADDVEC: scratch offset of z for row0
-    uint32_t aux_reduce; // LOWRANK/DENSE: scratch offset receiving this unit's w partial sums
+    uint32_t out;   // REDUCE: scratch offset receiving this unit's result (w values; ADDVEC: h values)
+    uint16_t cslot; // APPLY: element offset of this unit's c vector inside the stage's c segment (w values; ADDVEC: h values)
+    uint16_t reserved;
 };
 static_assert(sizeof(Unit) == 16, "Unit must be 16 bytes");
 
@@ -70,8 +85,12 @@ static_assert(sizeof(StageHeader) == 16, "StageHeader must be 16 bytes");
 struct StageDesc {
     uint64_t byte_off; // into the side's stream, multiple of 16
     uint32_t nbytes;   // multiple of 16
-    uint32_t flags;    // bit 0: holds at least one applied-twice unit
+    uint32_t c_off;    // first element of the stage's c segment in CS[side] (segment start is 16 B aligned)
+    uint16_t c_len;    // elements of the c segment, padded so that its byte size is a multiple of 16
+    uint16_t flags;    // bit 0: holds at least one applied-twice unit
+    uint32_t reserved;
 };
+static_assert(sizeof(StageDesc) == 24, "StageDesc must be 24 bytes");
 
 struct BlockDesc {
     int32_t row_start; // first index of the block in the side's index space
@@ -83,18 +102,31 @@ struct BlockDesc {
 };
 static_assert(sizeof(BlockDesc) == 32, "BlockDesc must be 32 bytes");
 
-// t = sum of the per-chunk partial vectors of a leaf that spans several blocks on the reduce side
+// One piece that could not be written producer -> consumer directly: v[0..len) = sum_{j < n_sum} scratch[src + j*len ..],
+// then v is copied (whole or a sub-range) into each of its n_dst consumer slots.
 struct CombineEntry {
-    uint32_t dst;      // scratch offset of the final vector
-    uint32_t src;      // scratch offset of the first partial (partials are consecutive, w apart)
-    uint32_t w;        // vector length (rank, or nb_cols for a dense leaf's z)
-    uint32_t n_chunks; // bit 31: leaf is applied twice
+    uint32_t src;
+    uint32_t dst_first; // index of the first CombineDst
+    uint32_t n_dst;
+    uint32_t packed; // n_sum [0:24) | len [24:31) | applied_twice [31]
 };
+static_assert(sizeof(CombineEntry) == 16, "CombineEntry must be 16 bytes");
+HTB_HD inline uint32_t combine_n_sum(uint32_t p) { return p & 0xffffffu; }
+HTB_HD inline uint32_t combine_len(uint32_t p) { return (p >> 24) & 0x7fu; }
+HTB_HD inline uint32_t combine_twice(uint32_t p) { return p >> 31; }
+
+struct CombineDst {
+    uint32_t slot;    // scratch offset of the consumer's slot
+    uint16_t sub_off; // the consumer wants v[sub_off .. sub_off + sub_len)
+    uint16_t sub_len;
+};
+static_assert(sizeof(CombineDst) == 8, "CombineDst must be 8 bytes");
 
 struct PackOptions {
-    int block_rows  = 64;    // <= 128, multiple of 32
-    int unit_elems  = 512;   // coefficients per unit
-    int stage_bytes = 16384; // bulk-copy granule, multiple of 16
+    int block_rows  = 64;    // 32, 64 or 128
+    int piece_cols  = 16;    // columns of a unit (<= 32); lowered automatically so that a unit fits a stage
+    int stage_bytes = 16384; // bulk-copy granule of the coefficient stream, multiple of 16
+    int cseg_bytes  = 2048;  // capacity of a stage's c segment, multiple of 16
 };
 
 // Host description of one side, produced by the packer. Device copies are owned by the handle.
@@ -103,10 +135,14 @@ struct SideLayout {
     std::vector<BlockDesc> blocks;
     std::vector<StageDesc> stages;
     std::vector<uint32_t> order; // block ids, heaviest stream first
+    // direction whose CONSUMER is this side (producers are the units of the other side)
     std::vector<CombineEntry> combine;
+    std::vector<CombineDst> combine_dst;
     uint64_t stream_bytes = 0;
     uint64_t n_units      = 0;
-    bool any_twice        = false;
+    uint64_t part_base = 0, part_elems = 0; // PART[this side as consumer]
+    uint64_t cs_base = 0, cs_elems = 0;     // CS[this side]
+    bool any_twice = false;
 };
 
 } // namespace htb

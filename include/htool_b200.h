@@ -179,33 +179,41 @@ int htb_launch_count(htb_handle h, int64_t *count);
  * default; serialises nothing that was not already serial). htb_get_pass_times synchronises, returns the
  * accumulated device milliseconds and launch counts per kernel kind since the last call, and resets them. */
 enum { HTB_PASS_REDUCE = 0, /* t = V x / op(U)^T x / op(A)^T x, streams one side of the store */
-       HTB_PASS_COMBINE = 1, /* folds per-block partial t vectors */
+       HTB_PASS_COMBINE = 1, /* folds per-chunk partials and replicates them into the c-stream slots */
        HTB_PASS_APPLY = 2,   /* y = beta y + alpha (U t + A x) / op(V)^T t, streams one side of the store */
        HTB_PASS_OTHER = 3,   /* permutations, scaling */
        HTB_PASS_KINDS = 4 };
 int htb_profile_passes(htb_handle h, int enable);
 int htb_get_pass_times(htb_handle h, double ms[HTB_PASS_KINDS], int64_t launches[HTB_PASS_KINDS]);
-/* Tunables (stage bytes, block rows, ...) for experiments; unknown keys return HTB_ERR_INVALID. Must be
- * set before htb_create, they are read when the store is packed. */
+/* Tunables for experiments: block_rows, piece_cols, stage_bytes, cseg_bytes, ring_stages, evict_first,
+ * upload_chunk_mb; unknown keys return HTB_ERR_INVALID. Must be set before htb_create, they are read when the
+ * store is packed. */
 int htb_set_option(const char *key, int64_t value);
 int htb_get_option(const char *key, int64_t *value);
 
 /* ---- packer introspection (host only, no CUDA) ----------------------------------------------------- */
 
-/* The bytes htb_create would upload for one side of the store (0: target rows = U panels + dense leaves,
- * 1: source columns = V^T panels), with the tables that index them (layouts in htool_b200/csrc/store.hpp).
- * It exists so the CPU test-suite can check the stream format without a GPU; it computes no product. */
+/* The bytes and tables htb_create would upload for one side of the store (0: target rows = U panels + dense
+ * leaves, 1: source columns = V^T panels), layouts in htool_b200/csrc/store.hpp. The combine tables are those of
+ * the direction whose CONSUMER is this side. It exists so the CPU test-suite can check the stream format without
+ * a GPU; it computes no product. */
 typedef struct htb_packed_side {
     int32_t n;                /* length of the side's index space */
     int32_t n_blocks;
     int64_t n_stages;
     int64_t n_combine;
+    int64_t n_combine_dst;
     int64_t stream_bytes;
-    int64_t scratch_elems;    /* elements of ONE scratch copy (final t / z vectors + per-chunk partials) */
+    int64_t scratch_elems;    /* elements of ONE scratch copy: PART[0] | PART[1] | CS[0] | CS[1] */
+    int64_t cs_base, cs_elems;     /* c-stream of this side inside a scratch copy */
+    int64_t part_base, part_elems; /* partials of the direction whose consumer is this side */
+    int32_t piece_cols;       /* effective unit width */
+    int32_t reserved;
     const void *blocks;       /* n_blocks x 32 B  (BlockDesc) */
-    const void *stages;       /* n_stages x 16 B  (StageDesc) */
+    const void *stages;       /* n_stages x 24 B  (StageDesc) */
     const void *order;        /* n_blocks x uint32: launch order, heaviest block first */
     const void *combine;      /* n_combine x 16 B (CombineEntry) */
+    const void *combine_dst;  /* n_combine_dst x 8 B (CombineDst) */
     const void *stream;       /* stream_bytes */
     void *owner;              /* opaque, released by htb_pack_free */
 } htb_packed_side;

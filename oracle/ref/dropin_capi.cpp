@@ -15,6 +15,8 @@
 
 #include <htool_b200/operators.hpp>
 
+#include <cstdio>
+#include <cstdlib>
 #include <random>
 
 namespace {
@@ -89,7 +91,12 @@ int run(htb_ref::Case<T> &c, double *results, int n_results) {
     using namespace htool;
     const bool is_complex = !std::is_same<T, double>::value;
     std::vector<double> worst(N_GROUPS, -1.); // -1: group not run for this case
-    auto upd = [&](int k, double e) { worst[k] = std::max(worst[k], e); };
+    const bool verbose = std::getenv("HTB_DROPIN_VERBOSE") != nullptr;
+    auto upd = [&](int k, double e) {
+        worst[k] = std::max(worst[k], e);
+        if (verbose)
+            std::fprintf(stderr, "[dropin] group %d err %.3e\n", k, e);
+    };
     std::mt19937 gen(7);
     const HMatrix<T, double> &H = *c.hmatrix;
     const char sym              = H.get_symmetry_for_leaves();
@@ -230,8 +237,14 @@ int run(htb_ref::Case<T> &c, double *results, int n_results) {
             upd(DIST_SUB_PRODUCT, rel_err(yg, yr));
         }
         // ---- free functions, user numbering (use_hmatrix.cpp:107) -------------------------------------------------
+        // NOTE the reference's user-numbering front ends permute `in` with the SOURCE cluster and `out` with the TARGET
+        // cluster whatever trans is (add_hmatrix_vector_product.hpp:178-179,196): for trans != 'N' they are only
+        // meaningful (and only stay inside the caller's buffers) when both clusters are the same object, so that is
+        // the only case compared here. The twin permutes the input of op(H) with the cluster of its input.
         htool_b200::DeviceHMatrix<T, double> DH(H);
         for (char trans : valid_trans(sym, is_complex)) {
+            if (trans != 'N' && !c.spec.same_cluster)
+                continue;
             const size_t ni = trans == 'N' ? NS : NT, no = trans == 'N' ? NT : NS;
             T alpha = rnd_scalar<T>(gen), beta = rnd_scalar<T>(gen);
             auto x = rnd_vector<T>(gen, ni), y0 = rnd_vector<T>(gen, no);

@@ -1,10 +1,10 @@
 """tests/stream_emulator.py — a numpy interpreter of the packed leaf store, for the CPU test-suite.
 
-It consumes the very bytes htb_create uploads (obtained through htb_pack_host, no GPU needed) with the same
-unit / stage / block walk, pass sequence and index shifts as htool_b200/csrc/kernels.cu and capi.cu
-(run_product). It checks the HOST logic — packer, stream format, scratch offsets, pass sequences — against
-the oracle; it is not a product path (tests only, pure Python, slow) and it never runs in place of the CUDA
-kernels: the `-m gpu` tests exercise those through the C ABI.
+It consumes the very bytes and tables htb_create uploads (obtained through htb_pack_host, no GPU needed) with
+the same unit / stage / block walk, c-stream addressing, combine tables, pass sequence and index shifts as
+htool_b200/csrc/kernels.cu and capi.cu (run_product). It checks the HOST logic — packer, stream format,
+scratch offsets, pass sequences — against the oracle; it is not a product path (tests only, pure Python, slow)
+and it never runs in place of the CUDA kernels: the `-m gpu` tests exercise those through the C ABI.
 """
 from __future__ import annotations
 
@@ -15,10 +15,12 @@ import numpy as np
 from htool_b200 import capi
 
 BLOCK_DT = np.dtype([("row_start", "<i4"), ("nrows", "<i4"), ("first_stage", "<u4"), ("n_stages", "<u4"), ("flags", "<u4"), ("r0", "<u4"), ("r1", "<u4"), ("r2", "<u4")])
-STAGE_DT = np.dtype([("byte_off", "<u8"), ("nbytes", "<u4"), ("flags", "<u4")])
-COMBINE_DT = np.dtype([("dst", "<u4"), ("src", "<u4"), ("w", "<u4"), ("n_chunks", "<u4")])
-UNIT_DT = np.dtype([("data_off", "<u4"), ("geom", "<u4"), ("aux_apply", "<u4"), ("aux_reduce", "<u4")])
+STAGE_DT = np.dtype([("byte_off", "<u8"), ("nbytes", "<u4"), ("c_off", "<u4"), ("c_len", "<u2"), ("flags", "<u2"), ("reserved", "<u4")])
+COMBINE_DT = np.dtype([("src", "<u4"), ("dst_first", "<u4"), ("n_dst", "<u4"), ("packed", "<u4")])
+COMBINE_DST_DT = np.dtype([("slot", "<u4"), ("sub_off", "<u2"), ("sub_len", "<u2")])
+UNIT_DT = np.dtype([("data_off", "<u4"), ("geom", "<u4"), ("out", "<u4"), ("cslot", "<u2"), ("reserved", "<u2")])
 UNIT_LOWRANK, UNIT_DENSE, UNIT_ADDVEC = 0, 1, 2
+assert BLOCK_DT.itemsize == 32 and STAGE_DT.itemsize == 24 and COMBINE_DT.itemsize == 16 and COMBINE_DST_DT.itemsize == 8 and UNIT_DT.itemsize == 16
 
 
 def _view(addr, count, dt):
@@ -35,21 +37,24 @@ class PackedSide:
         capi.check(lib, lib.htb_pack_host(C.byref(desc), side, C.byref(p)))
         self.n, self.n_blocks = p.n, p.n_blocks
         self.scratch_elems = p.scratch_elems
+        self.cs_base, self.cs_elems, self.part_base, self.part_elems, self.piece_cols = p.cs_base, p.cs_elems, p.part_base, p.part_elems, p.piece_cols
         self.blocks = _view(p.blocks, p.n_blocks, BLOCK_DT)
         self.stages = _view(p.stages, p.n_stages, STAGE_DT)
         self.order = _view(p.order, p.n_blocks, np.dtype("<u4"))
         self.combine = _view(p.combine, p.n_combine, COMBINE_DT)
+        self.combine_dst = _view(p.combine_dst, p.n_combine_dst, COMBINE_DST_DT)
         self.stream = _view(p.stream, p.stream_bytes, np.dtype("u1"))
         self.stream_bytes = p.stream_bytes
         lib.htb_pack_free(C.byref(p))
 
     def units_of_stage(self, st, dtype):
-        """Yields (unit record, panel as an (h, w) array) for one stage."""
+        """Yields (unit record, row0, h, w, kind, twice, panel as an (h, w) array) for one stage."""
         sd = self.stages[st]
         raw = self.stream[int(sd["byte_off"]): int(sd["byte_off"]) + int(sd["nbytes"])]
         n_units, data_off = np.frombuffer(raw[:8].tobytes(), dtype="<u4")
         units = np.frombuffer(raw[16:16 + 16 * int(n_units)].tobytes(), dtype=UNIT_DT)
-        data = np.frombuffer(raw[int(data_off):].tobytes()[: (len(raw) - int(data_off)) // np.dtype(dtype).itemsize * np.dtype(dtype).itemsize], dtype=dtype)
+        isz = np.dtype(dtype).itemsize
+        data = np.frombuffer(raw[int(data_off):].tobytes()[: (len(raw) - int(data_off)) // isz * isz], dtype=dtype)
         for u in units:
             g = int(u["geom"])
             row0, h, w, kind, twice = g & 0xFF, ((g >> 8) & 0xFF) + 1, (g >> 16) & 0xFF, (g >> 24) & 3, (g >> 26) & 1
@@ -72,6 +77,10 @@ class Emulator:
         self.D = flatcase.row_offset - flatcase.col_offset
         self.any_twice = any(bool((s.blocks["flags"] & 1).any()) for s in self.side)
 
+    def new_scratch(self):
+        # NaN-poisoned: a slot that is read must have been written by this product
+        return np.full(max(2, self.scratch_elems), np.nan, self.dtype)
+
     # REDUCE pass (reduce_kernel)
     def reduce(self, s, vec, in_shift, scratch, twice_only, conj):
         side = self.side[s]
@@ -88,20 +97,31 @@ class Emulator:
                 if twice_only and not (side.stages[st]["flags"] & 1):
                     continue
                 for u, row0, h, w, kind, twice, panel in side.units_of_stage(st, self.dtype):
-                    if kind == UNIT_ADDVEC or (twice_only and not twice):
+                    if twice_only and not twice:
+                        continue
+                    o = int(u["out"])
+                    if kind == UNIT_ADDVEC:
+                        scratch[o: o + h] = xin[row0: row0 + h]
                         continue
                     P = np.conj(panel) if conj else panel
-                    scratch[int(u["aux_reduce"]): int(u["aux_reduce"]) + w] = P.T @ xin[row0: row0 + h]
+                    scratch[o: o + w] = P.T @ xin[row0: row0 + h]
 
+    # COMBINE pass of the direction whose consumer is side s (combine_kernel)
     def combine(self, s, scratch, twice_only):
-        for ce in self.side[s].combine:
-            if twice_only and not (int(ce["n_chunks"]) & 0x80000000):
+        side = self.side[s]
+        for ce in side.combine:
+            pk = int(ce["packed"])
+            n_sum, ln, tw = pk & 0xFFFFFF, (pk >> 24) & 0x7F, pk >> 31
+            if twice_only and not tw:
                 continue
-            nc, w, src, dst = int(ce["n_chunks"]) & 0x7FFFFFFF, int(ce["w"]), int(ce["src"]), int(ce["dst"])
-            scratch[dst: dst + w] = scratch[src: src + nc * w].reshape(nc, w).sum(axis=0)
+            src = int(ce["src"])
+            v = scratch[src: src + n_sum * ln].reshape(n_sum, ln).sum(axis=0)
+            for d in side.combine_dst[int(ce["dst_first"]): int(ce["dst_first"]) + int(ce["n_dst"])]:
+                so, sl = int(d["sub_off"]), int(d["sub_len"])
+                scratch[int(d["slot"]): int(d["slot"]) + sl] = v[so: so + sl]
 
     # APPLY pass (apply_kernel)
-    def apply(self, s, vec_in, in_shift, out, out_shift, scratch, alpha, beta, twice_only, conj):
+    def apply(self, s, out, out_shift, scratch, alpha, beta, twice_only, conj):
         side = self.side[s]
         for b in side.order:
             bd = side.blocks[b]
@@ -109,25 +129,21 @@ class Emulator:
                 continue
             acc = np.zeros(int(bd["nrows"]), self.dtype)
             for st in range(int(bd["first_stage"]), int(bd["first_stage"] + bd["n_stages"])):
-                if twice_only and not (side.stages[st]["flags"] & 1):
+                sd = side.stages[st]
+                if twice_only and not (sd["flags"] & 1):
                     continue
+                c0 = side.cs_base + int(sd["c_off"])
+                assert c0 % (1 if self.dtype == np.complex128 else 2) == 0  # 16 B aligned bulk copy
+                cseg = scratch[c0: c0 + int(sd["c_len"])]
                 for u, row0, h, w, kind, twice, panel in side.units_of_stage(st, self.dtype):
                     if twice_only and not twice:
                         continue
-                    a = int(u["aux_apply"])
+                    a = int(u["cslot"])
                     if kind == UNIT_ADDVEC:
-                        acc[row0: row0 + h] += scratch[a: a + h]
+                        acc[row0: row0 + h] += cseg[a: a + h]
                         continue
-                    if kind == UNIT_LOWRANK:
-                        c = scratch[a: a + w]
-                    else:
-                        c = np.zeros(w, self.dtype)
-                        for k in range(w):
-                            g = a + k + in_shift
-                            if 0 <= g < len(vec_in):
-                                c[k] = vec_in[g]
                     P = np.conj(panel) if conj else panel
-                    acc[row0: row0 + h] += P @ c
+                    acc[row0: row0 + h] += P @ cseg[a: a + w]
             for i in range(int(bd["nrows"])):
                 g = int(bd["row_start"]) + i + out_shift
                 if 0 <= g < len(out):
@@ -139,26 +155,25 @@ class Emulator:
             return 2
         twice = sym != "N" and self.any_twice
         is_complex = self.dtype == np.complex128
-        T1 = np.zeros(max(1, self.scratch_elems), self.dtype)
-        T2 = np.zeros(max(1, self.scratch_elems), self.dtype)
+        T1, T2 = self.new_scratch(), self.new_scratch()
         D = self.D
         if trans == "N":
             self.reduce(1, x, 0, T1, False, False)
             if twice:
                 self.reduce(0, x, D, T2, True, sym == "H" and is_complex)
-                self.combine(0, T2, True)
-            self.combine(1, T1, False)
-            self.apply(0, x, 0, y, 0, T1, alpha, beta, False, False)
+                self.combine(1, T2, True)
+            self.combine(0, T1, False)
+            self.apply(0, y, 0, T1, alpha, beta, False, False)
             if twice:
-                self.apply(1, x, 0, y, -D, T2, alpha, 1.0, True, sym == "H" and is_complex)
+                self.apply(1, y, -D, T2, alpha, 1.0, True, sym == "H" and is_complex)
         else:
             conj = trans == "C" and is_complex
             self.reduce(0, x, 0, T1, False, conj)
-            self.combine(0, T1, False)
+            self.combine(1, T1, False)
             if twice:
                 self.reduce(1, x, -D, T2, True, False)
-                self.combine(1, T2, True)
-            self.apply(1, x, 0, y, 0, T1, alpha, beta, False, conj)
+                self.combine(0, T2, True)
+            self.apply(1, y, 0, T1, alpha, beta, False, conj)
             if twice:
-                self.apply(0, x, -D, y, D, T2, alpha, 1.0, True, False)
+                self.apply(0, y, D, T2, alpha, 1.0, True, False)
         return 0

@@ -43,6 +43,7 @@ def test_reference_code_runs_unchanged_on_the_gpu_operators(kw):
     assert torch.cuda.is_available()
     from oracle import refharness as R
 
+    R.load()  # pins OPENBLAS_NUM_THREADS=1 before any BLAS call from inside an OpenMP region
     lib = C.CDLL(DROPIN_LIB)
     lib.dropin_n_groups.restype = C.c_int
     lib.dropin_run.restype = C.c_int

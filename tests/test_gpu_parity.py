@@ -115,10 +115,10 @@ def test_deterministic_bitwise(capi):
     op.close()
 
 
-@pytest.mark.parametrize("opts", [dict(block_rows=32, unit_elems=128, stage_bytes=4096, ring_stages=2), dict(block_rows=128, unit_elems=1024, stage_bytes=32768, ring_stages=3),
-                                  dict(evict_first=0, ring_stages=8, stage_bytes=8192, unit_elems=256)])
+@pytest.mark.parametrize("opts", [dict(block_rows=32, piece_cols=4, stage_bytes=4096, cseg_bytes=512, ring_stages=2), dict(block_rows=128, piece_cols=32, stage_bytes=65536, cseg_bytes=4096, ring_stages=2, reduce_ring_stages=3),
+                                  dict(evict_first=0, ring_stages=8, stage_bytes=8192, piece_cols=8, cseg_bytes=1024)])
 def test_packer_and_launch_options(capi, opts):
-    defaults = {k: capi.get_option(k) for k in ("block_rows", "unit_elems", "stage_bytes", "ring_stages", "evict_first")}
+    defaults = {k: capi.get_option(k) for k in ("block_rows", "piece_cols", "stage_bytes", "cseg_bytes", "ring_stages", "reduce_ring_stages", "evict_first")}
     try:
         for k, v in opts.items():
             capi.set_option(k, v)

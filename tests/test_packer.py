@@ -96,15 +96,17 @@ def test_packed_stream_matches_golden(name):
         assert rel_err(y, e["y_seq"]) < TOL, (name, e["trans"])
 
 
-@pytest.mark.parametrize("opts", [dict(block_rows=32, unit_elems=128, stage_bytes=4096), dict(block_rows=128, unit_elems=1024, stage_bytes=32768)])
+@pytest.mark.parametrize("opts", [dict(block_rows=32, piece_cols=4, stage_bytes=4096, cseg_bytes=512), dict(block_rows=128, piece_cols=32, stage_bytes=65536, cseg_bytes=4096),
+                                  dict(piece_cols=8, stage_bytes=8192, cseg_bytes=1024)])
 def test_packer_options(opts):
+    DEFAULTS = {k: capi.get_option(k) for k in ("block_rows", "piece_cols", "stage_bytes", "cseg_bytes")}
     try:
         for k, v in opts.items():
             capi.set_option(k, v)
         _check(random_flatcase(seed=5, symmetric="S"))
         _check(random_flatcase(seed=6, dtype_code=1))
     finally:
-        for k, v in dict(block_rows=64, unit_elems=512, stage_bytes=16384).items():
+        for k, v in DEFAULTS.items():
             capi.set_option(k, v)
 
 

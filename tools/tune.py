@@ -1,0 +1,103 @@
+#!/usr/bin/env python
+"""tools/tune.py — packer / launch option sweep on one GPU (development aid, not the bench).
+
+Assembles the workload ONCE with the reference (oracle/_ref, as bench.py does), then for every option set
+packs + uploads a fresh leaf store and times device-resident products with CUDA events on the launching
+stream, printing one JSON line per option set (total ms, per-pass ms, achieved GB/s, parity vs the reference).
+
+  python tools/tune.py --n 1000000 --set ring_stages=3 --set ring_stages=4,stage_bytes=32768 ...
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--dtype", default="double", choices=["double", "complex"])
+    ap.add_argument("--symmetry", default="N", choices=["N", "S"])
+    ap.add_argument("--trans", default="N")
+    ap.add_argument("--set", action="append", default=[], help="comma separated key=value list; one product configuration per --set")
+    args = ap.parse_args()
+
+    import torch
+
+    import bench
+    from htool_b200 import capi
+    from oracle import refharness as R
+
+    R.set_num_threads(os.cpu_count() or 1)
+    bargs = argparse.Namespace(n=args.n, dtype=args.dtype, symmetry=args.symmetry, mu=1, gpus=1)
+    t0 = time.perf_counter()
+    case = R.RefCase(**bench.case_kwargs(bargs))
+    print(json.dumps({"assembly_s": time.perf_counter() - t0, **{k: v for k, v in case.info().items() if k in ("nb_leaves", "coefficients", "coefficients_twice")}}), flush=True)
+    dtype = case.np_dtype
+    esize = np.dtype(dtype).itemsize
+    ni, no = (case.nb_cols, case.nb_rows) if args.trans == "N" else (case.nb_rows, case.nb_cols)
+    x = bench.seeded_x(ni, dtype)
+    y_ref = np.zeros(no, dtype)
+    case.vector_product(args.trans, 1.0, x, 0.0, y_ref, variant="openmp")
+    defaults = {k: capi.get_option(k) for k in ("block_rows", "piece_cols", "stage_bytes", "cseg_bytes", "ring_stages", "reduce_ring_stages", "evict_first")}
+    stream = torch.cuda.Stream()
+    x_d = torch.from_numpy(x).cuda()
+    tdt = torch.float64 if dtype == np.float64 else torch.complex128
+    for spec in args.set or [""]:
+        opts = dict(defaults)
+        for kv in filter(None, spec.split(",")):
+            k, v = kv.split("=")
+            opts[k] = int(v)
+        try:
+            for k, v in opts.items():
+                capi.set_option(k, v)
+            t0 = time.perf_counter()
+            case.desc.device = 0
+            op = capi.Operator(case.desc)
+            t_pack = time.perf_counter() - t0
+            info = op.info()
+            y = np.zeros(no, dtype)
+            op.add_vector_product(args.trans, 1.0, x, 0.0, y)
+            parity = float(np.linalg.norm(y - y_ref) / np.linalg.norm(y_ref))
+            op.set_stream(stream.cuda_stream)
+            y_d = torch.zeros(no, dtype=tdt, device="cuda")
+            torch.cuda.synchronize()
+            for _ in range(3):
+                op.add_vector_product_device(args.trans, 1.0, x_d.data_ptr(), 0.0, y_d.data_ptr())
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(args.steps):
+                op.add_vector_product_device(args.trans, 1.0, x_d.data_ptr(), 0.0, y_d.data_ptr())
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.steps
+            op.profile_passes(True)
+            for _ in range(5):
+                op.add_vector_product_device(args.trans, 1.0, x_d.data_ptr(), 0.0, y_d.data_ptr())
+            pt = op.pass_times()
+            op.profile_passes(False)
+            nbytes = esize * (info["coefficients"] + ni + no)
+            print(json.dumps({"opts": {k: v for k, v in opts.items() if v != defaults[k]}, "ms": ms, "gbs": nbytes / ms / 1e6, "parity": parity,
+                              "passes_ms": {k: v["ms"] / 5 for k, v in pt.items()}, "pack_s": t_pack, "store_gb": info["store_bytes"] / 1e9,
+                              "workspace_gb": info["workspace_bytes"] / 1e9, "descriptor_mb": info["descriptor_bytes"] / 1e6}), flush=True)
+            op.set_stream(None)
+            op.close()
+        except Exception as ex:  # keep sweeping
+            print(json.dumps({"opts": spec, "error": str(ex)}), flush=True)
+        finally:
+            for k, v in defaults.items():
+                capi.set_option(k, v)
+
+
+if __name__ == "__main__":
+    main()
