@@ -435,16 +435,16 @@ int htb_create(const htb_hmatrix_desc *desc, htb_handle *out) {
     h->launch_cfg.block_rows  = popt.block_rows;
     h->launch_cfg.stage_bytes = popt.stage_bytes;
     h->launch_cfg.cseg_bytes  = popt.cseg_bytes;
-    h->launch_cfg.ring_stages = static_cast<int>(option("ring_stages"));
+    h->launch_cfg.ring_stages        = static_cast<int>(option("ring_stages"));
     h->launch_cfg.reduce_ring_stages = static_cast<int>(option("reduce_ring_stages"));
     h->launch_cfg.evict_first = static_cast<int>(option("evict_first"));
-    if (h->launch_cfg.ring_stages < 2 || h->launch_cfg.ring_stages > 16 || h->launch_cfg.reduce_ring_stages < 2 || h->launch_cfg.reduce_ring_stages > 16)
-        return fail(HTB_ERR_INVALID, "ring_stages / reduce_ring_stages must be in [2, 16]");
+    if (h->launch_cfg.ring_stages < 2 || h->launch_cfg.ring_stages > 32 || h->launch_cfg.reduce_ring_stages < 2 || h->launch_cfg.reduce_ring_stages > 32)
+        return fail(HTB_ERR_INVALID, "ring_stages / reduce_ring_stages must be in [2, 32]");
     cudaDeviceProp prop{};
     HTB_CUDA(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
     if (std::max(apply_smem_bytes(h->launch_cfg, 16), reduce_smem_bytes(h->launch_cfg, 16)) > static_cast<size_t>(prop.sharedMemPerBlockOptin))
-        return fail(HTB_ERR_INVALID, "ring_stages * stage_bytes exceeds the shared memory of an SM");
+        return fail(HTB_ERR_INVALID, "the shared-memory ring (ring_stages x stage_bytes) exceeds the shared memory of an SM");
     HTB_CUDA(configure_kernels(h->launch_cfg));
     HTB_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;

@@ -30,7 +30,7 @@ namespace {
 
 constexpr int kConsumerWarps = 8;
 constexpr int kThreads       = (kConsumerWarps + 1) * 32; // + 1 producer warp
-constexpr int kMaxQ          = 4;                         // block_rows <= 128 -> <= 4 rows per lane
+constexpr int kMaxQ          = 2;                         // a lane owns at most 2 row slabs (block_rows * sizeof(T) <= 1024)
 
 // ---- scalar helpers -------------------------------------------------------------------------------
 __device__ __forceinline__ double zero_of(double) { return 0.; }
@@ -53,6 +53,24 @@ __device__ __forceinline__ cplx shfl_xor(cplx v, int m) { return cplx{__shfl_xor
 __device__ __forceinline__ double select(bool p, double a, double b) { return p ? a : b; }
 __device__ __forceinline__ cplx select(bool p, cplx a, cplx b) { return cplx{p ? a.x : b.x, p ? a.y : b.y}; }
 
+// R consecutive rows of one column are fetched with ONE 128-bit shared-memory load: 2 doubles or 1 complex
+template <typename T>
+struct Rows;
+template <>
+struct Rows<double> {
+    static constexpr int R = 2;
+};
+template <>
+struct Rows<cplx> {
+    static constexpr int R = 1;
+};
+__device__ __forceinline__ void load_rows(const double *p, double (&f)[2]) {
+    const double2 v = *reinterpret_cast<const double2 *>(p);
+    f[0]            = v.x;
+    f[1]            = v.y;
+}
+__device__ __forceinline__ void load_rows(const cplx *p, cplx (&f)[1]) { f[0] = *p; }
+
 // ---- mbarrier / bulk copy (inline PTX) -------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -64,12 +82,13 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait suspends the thread in hardware up to the time hint, so a waiting warp costs few issue slots
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
     do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done)
-                     : "r"(bar), "r"(parity)
+                     : "r"(bar), "r"(parity), "r"(0x989680u)
                      : "memory");
     } while (!done);
 }
@@ -113,13 +132,25 @@ __device__ __forceinline__ SmemLayout carve(unsigned char *base, const KernelSid
     return s;
 }
 
+// Position of consecutive stages in the shared-memory ring: slot and phase parity, advanced without divisions.
+struct RingPos {
+    uint32_t slot, phase;
+    __device__ __forceinline__ RingPos() : slot(0), phase(0) {}
+    __device__ __forceinline__ void advance(uint32_t ring) {
+        if (++slot == ring) {
+            slot = 0;
+            phase ^= 1u;
+        }
+    }
+};
+
 // Producer: one lane streams the block's stages (and, for APPLY, their c segments) into the ring.
 template <typename T, bool WITH_C>
-__device__ __forceinline__ void produce(const KernelSide &ks, const BlockDesc &bd, const SmemLayout &sm, int ring, int twice_only, const T *cs) {
+__device__ __forceinline__ void produce(const KernelSide &ks, const BlockDesc &bd, const SmemLayout &sm, int twice_only, const T *cs) {
     const uint64_t policy = ks.evict_first ? l2_evict_first_policy() : 0;
-    uint32_t it           = 0;
     if (bd.n_stages == 0)
         return;
+    RingPos pos;
     StageDesc next = ks.stages[bd.first_stage];
     for (uint32_t st = 0; st < bd.n_stages; st++) {
         const StageDesc sd = next;
@@ -127,40 +158,45 @@ __device__ __forceinline__ void produce(const KernelSide &ks, const BlockDesc &b
             next = ks.stages[bd.first_stage + st + 1]; // in flight while this stage waits for its slot
         if (twice_only && !(sd.flags & 1u))
             continue;
-        const uint32_t slot = it % ring, round = it / ring;
         const uint32_t cbytes = WITH_C ? static_cast<uint32_t>(sd.c_len * sizeof(T)) : 0u;
-        mbar_wait(smem_u32(&sm.empty[slot]), (round & 1u) ^ 1u);
-        mbar_arrive_expect_tx(smem_u32(&sm.full[slot]), sd.nbytes + cbytes);
+        const uint32_t slot   = pos.slot;
+        const uint32_t full   = smem_u32(&sm.full[slot]);
+        mbar_wait(smem_u32(&sm.empty[slot]), pos.phase ^ 1u);
+        mbar_arrive_expect_tx(full, sd.nbytes + cbytes);
         const uint32_t dst = smem_u32(sm.ring + static_cast<size_t>(slot) * sm.slot_bytes);
-        bulk_g2s(dst, ks.stream + sd.byte_off, sd.nbytes, smem_u32(&sm.full[slot]), policy, ks.evict_first != 0);
+        bulk_g2s(dst, ks.stream + sd.byte_off, sd.nbytes, full, policy, ks.evict_first != 0);
         if (WITH_C && cbytes)
-            bulk_g2s(dst + ks.stage_bytes, cs + sd.c_off, cbytes, smem_u32(&sm.full[slot]), 0, false);
-        it++;
+            bulk_g2s(dst + ks.stage_bytes, cs + sd.c_off, cbytes, full, 0, false);
+        pos.advance(ks.ring_stages);
     }
 }
 
 __device__ __forceinline__ void init_barriers(const KernelSide &ks, const SmemLayout &sm) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < ks.ring_stages; s++) {
-            mbar_init(smem_u32(&sm.full[s]), 1);
-            mbar_init(smem_u32(&sm.empty[s]), kConsumerWarps);
+            mbar_init(smem_u32(&sm.full[s]), 1);               // the producer's arrive.expect_tx
+            mbar_init(smem_u32(&sm.empty[s]), kConsumerWarps); // every consumer warp walks every stage
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
 }
 
-// Lane geometry of a unit of height h: lanes are grouped in segments of seg = 2^seglog >= min(h, 32) lanes, lane li
-// of a segment owns row li (rows li + 32 q when h > 32) and the G = 32 / seg segments work on different columns.
+// Lane geometry of a unit of height h. A lane owns R consecutive rows (Rows<T>::R); hp = ceil(h / R) lane-rows are
+// needed. Lanes are grouped in segments of seg = 2^seglog >= min(hp, 32) lanes: lane li of a segment owns rows
+// R*li .. R*li + R - 1 (and R*(li + 32) .. when hp > 32) and the G = 32 / seg segments work on different columns.
 struct LaneMap {
-    int seglog, li, g, G;
+    int seglog, li, g, logG, Q;
 };
+template <int R>
 __device__ __forceinline__ LaneMap lane_map(uint32_t h, int lane) {
+    const uint32_t hp = (h + R - 1) / R;
     LaneMap m;
-    m.seglog = h > 16 ? 5 : (h > 8 ? 4 : (h > 4 ? 3 : (h > 2 ? 2 : (h > 1 ? 1 : 0))));
+    m.seglog = hp > 16 ? 5 : (hp > 8 ? 4 : (hp > 4 ? 3 : (hp > 2 ? 2 : (hp > 1 ? 1 : 0))));
     m.li     = lane & ((1 << m.seglog) - 1);
     m.g      = lane >> m.seglog;
-    m.G      = 32 >> m.seglog;
+    m.logG   = 5 - m.seglog;
+    m.Q      = hp > 32 ? 2 : 1;
     return m;
 }
 
@@ -197,31 +233,42 @@ __device__ __forceinline__ void seg_reduce(T (&v)[J], int seglog, int li, int &c
     lowmask = lastd - 1;
 }
 
-// Columns kb + c*G + g, c < J, of the panel: per-lane products with x, segment reduction, store of the totals.
+// Columns kb + (c << logG) + g, c < J, of the panel: per-lane products with x, segment reduction, store of the totals.
 template <typename T, bool CONJ, int J>
-__device__ __forceinline__ void reduce_batch(const T *P, uint32_t h, uint32_t w, uint32_t kb, const LaneMap &m, int Q, const uint32_t (&ic)[kMaxQ], const T (&xv)[kMaxQ], T *out) {
+__device__ __forceinline__ void reduce_batch(const T *P, uint32_t ld, uint32_t w, uint32_t kb, const LaneMap &m, const uint32_t (&off)[kMaxQ], const T (&xv)[kMaxQ][Rows<T>::R], T *out) {
+    constexpr int R = Rows<T>::R;
     T v[J];
 #pragma unroll
     for (int c = 0; c < J; c++) {
-        const uint32_t k = kb + c * m.G + m.g;
-        const T *col     = P + static_cast<size_t>(k < w ? k : w - 1) * h; // clamped: the total of a column >= w is never stored
-        T s              = mul(cj<CONJ>(col[ic[0]]), xv[0]);
-        if (Q > 1)
-            s = fma_(cj<CONJ>(col[ic[1]]), xv[1], s);
-        if (Q > 2) {
-            s = fma_(cj<CONJ>(col[ic[2]]), xv[2], s);
-            s = fma_(cj<CONJ>(col[ic[3]]), xv[3], s);
+        const uint32_t k = kb + (c << m.logG) + m.g;
+        const T *col     = P + (k < w ? k : w - 1) * ld; // clamped: the total of a column >= w is never stored
+        T f[R];
+        load_rows(col + off[0], f);
+        T s = mul(cj<CONJ>(f[0]), xv[0][0]);
+        if (R > 1)
+            s = fma_(cj<CONJ>(f[R - 1]), xv[0][R - 1], s);
+        if (m.Q > 1) {
+            load_rows(col + off[1], f);
+            s = fma_(cj<CONJ>(f[0]), xv[1][0], s);
+            if (R > 1)
+                s = fma_(cj<CONJ>(f[R - 1]), xv[1][R - 1], s);
         }
         v[c] = s;
     }
     int cbase, nv, lowmask;
     seg_reduce<T, J>(v, m.seglog, m.li, cbase, nv, lowmask);
     if ((m.li & lowmask) == 0) {
+        if (nv == 1) { // the usual case: one total per writer lane
+            const uint32_t k = kb + (cbase << m.logG) + m.g;
+            if (k < w)
+                out[k] = v[0];
+        } else {
 #pragma unroll
-        for (int c = 0; c < J; c++) {
-            const uint32_t k = kb + (cbase + c) * m.G + m.g;
-            if (c < nv && k < w)
-                out[k] = v[c];
+            for (int c = 0; c < J; c++) {
+                const uint32_t k = kb + ((cbase + c) << m.logG) + m.g;
+                if (c < nv && k < w)
+                    out[k] = v[c];
+            }
         }
     }
 }
@@ -229,9 +276,11 @@ __device__ __forceinline__ void reduce_batch(const T *P, uint32_t h, uint32_t w,
 // ---- REDUCE -------------------------------------------------------------------------------------------
 template <typename T, bool CONJ>
 __global__ void __launch_bounds__(kThreads) reduce_kernel(KernelSide ks, PassArgs<T> a) {
+    constexpr int R = Rows<T>::R;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const BlockDesc bd = ks.blocks[ks.order[blockIdx.x]];
-    if (bd.n_stages == 0 || (a.twice_only && !(bd.flags & 1u)))
+    const uint32_t n_my_stages = a.twice_only ? bd.n_twice_stages : bd.n_stages;
+    if (n_my_stages == 0)
         return;
     const SmemLayout sm = carve(smem_raw, ks, ks.stage_bytes, sizeof(T) * ks.block_rows);
     T *xin              = reinterpret_cast<T *>(sm.vec);
@@ -247,28 +296,27 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(KernelSide ks, PassArg
 
     if (warp == kConsumerWarps) {
         if (lane == 0)
-            produce<T, false>(ks, bd, sm, ks.ring_stages, a.twice_only, nullptr);
+            produce<T, false>(ks, bd, sm, a.twice_only, nullptr);
         return;
     }
 
-    uint32_t it = 0, ubase = 0;
-    for (uint32_t st = 0; st < bd.n_stages; st++) {
-        if (a.twice_only && !(ks.stages[bd.first_stage + st].flags & 1u))
-            continue;
-        const uint32_t slot = it % ks.ring_stages, round = it / ks.ring_stages;
-        mbar_wait(smem_u32(&sm.full[slot]), round & 1u);
+    // Every warp walks every stage (in the producer's order); the units are dealt round-robin over the warps ACROSS
+    // stages (ubase), so that a stage with few units does not always land on the same warps.
+    RingPos pos;
+    uint32_t ubase = warp;
+    for (uint32_t q = 0; q < n_my_stages; q++, pos.advance(ks.ring_stages)) {
+        const uint32_t slot = pos.slot;
+        mbar_wait(smem_u32(&sm.full[slot]), pos.phase);
         const unsigned char *stage = sm.ring + static_cast<size_t>(slot) * sm.slot_bytes;
         const StageHeader hdr      = *reinterpret_cast<const StageHeader *>(stage);
         const Unit *units          = reinterpret_cast<const Unit *>(stage + sizeof(StageHeader));
         const T *data              = reinterpret_cast<const T *>(stage + hdr.data_byte_off);
-        // units are dealt round-robin over the warps ACROSS stages, so that a stage with few units does not
-        // always land on the same warps
-        for (uint32_t u = (warp - ubase) & (kConsumerWarps - 1); u < hdr.n_units; u += kConsumerWarps) {
-            const Unit un       = units[u];
-            const uint32_t kind = unit_kind(un.geom);
+        uint32_t u = ubase;
+        for (; u < hdr.n_units; u += kConsumerWarps) {
+            const Unit un = units[u];
             if (a.twice_only && !unit_twice(un.geom))
                 continue;
-            const uint32_t row0 = unit_row0(un.geom), h = unit_h(un.geom), w = unit_w(un.geom);
+            const uint32_t kind = unit_kind(un.geom), row0 = unit_row0(un.geom), h = unit_h(un.geom), w = unit_w(un.geom);
             T *out = a.scratch + un.out;
             if (kind == UNIT_ADDVEC) {
                 // dense leaf, direction 0: hand its x slice to the APPLY pass through the c-stream
@@ -276,46 +324,49 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(KernelSide ks, PassArg
                     out[i] = xin[row0 + i];
                 continue;
             }
-            const T *P       = data + un.data_off;
-            const LaneMap m  = lane_map(h, lane);
-            const int Q      = (h + 31) >> 5;
-            uint32_t ic[kMaxQ];
-            T xv[kMaxQ];
+            const T *P        = data + un.data_off;
+            const uint32_t ld = unit_ld(h, sizeof(T));
+            const LaneMap m   = lane_map<R>(h, lane);
+            uint32_t off[kMaxQ];
+            T xv[kMaxQ][R];
 #pragma unroll
-            for (int q = 0; q < kMaxQ; q++) {
-                const uint32_t i = m.li + 32u * q;
-                ic[q]            = i < h ? i : h - 1;
-                xv[q]            = i < h ? xin[row0 + i] : zero_of(T{});
+            for (int qq = 0; qq < kMaxQ; qq++) {
+                const uint32_t i0 = R * (m.li + 32u * qq);
+                off[qq]           = i0 < ld ? i0 : 0u;
+#pragma unroll
+                for (int r = 0; r < R; r++)
+                    xv[qq][r] = i0 + r < h ? xin[row0 + i0 + r] : zero_of(T{});
             }
             for (uint32_t kb = 0; kb < w;) {
-                const uint32_t per_seg = (w - kb + m.G - 1) / m.G; // columns left for each segment
+                const uint32_t per_seg = (w - kb + (1u << m.logG) - 1u) >> m.logG; // columns left for each segment
                 if (per_seg > 4) {
-                    reduce_batch<T, CONJ, 8>(P, h, w, kb, m, Q, ic, xv, out);
-                    kb += 8 * m.G;
+                    reduce_batch<T, CONJ, 8>(P, ld, w, kb, m, off, xv, out);
+                    kb += 8u << m.logG;
                 } else if (per_seg > 2) {
-                    reduce_batch<T, CONJ, 4>(P, h, w, kb, m, Q, ic, xv, out);
-                    kb += 4 * m.G;
+                    reduce_batch<T, CONJ, 4>(P, ld, w, kb, m, off, xv, out);
+                    kb += 4u << m.logG;
                 } else {
-                    reduce_batch<T, CONJ, 2>(P, h, w, kb, m, Q, ic, xv, out);
-                    kb += 2 * m.G;
+                    reduce_batch<T, CONJ, 2>(P, ld, w, kb, m, off, xv, out);
+                    kb += 2u << m.logG;
                 }
             }
         }
-        ubase = (ubase + hdr.n_units) & (kConsumerWarps - 1);
+        ubase = (ubase - hdr.n_units) & (kConsumerWarps - 1); // == (warp - units dealt so far) mod 8
         __syncwarp();
         if (lane == 0)
             mbar_arrive(smem_u32(&sm.empty[slot]));
-        it++;
     }
 }
 
 // ---- APPLY --------------------------------------------------------------------------------------------
 template <typename T, bool CONJ>
 __global__ void __launch_bounds__(kThreads) apply_kernel(KernelSide ks, PassArgs<T> a) {
+    constexpr int R = Rows<T>::R;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const BlockDesc bd = ks.blocks[ks.order[blockIdx.x]];
     if (a.twice_only && !(bd.flags & 1u))
         return; // accumulate-only pass and nothing to add
+    const uint32_t n_my_stages = a.twice_only ? bd.n_twice_stages : bd.n_stages;
     const SmemLayout sm = carve(smem_raw, ks, ks.stage_bytes + ks.cseg_bytes, sizeof(T) * ks.block_rows * kConsumerWarps);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     T *yacc_all = reinterpret_cast<T *>(sm.vec);
@@ -327,26 +378,27 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(KernelSide ks, PassArgs
 
     if (warp == kConsumerWarps) {
         if (lane == 0)
-            produce<T, true>(ks, bd, sm, ks.ring_stages, a.twice_only, a.scratch + ks.cs_base);
+            produce<T, true>(ks, bd, sm, a.twice_only, a.scratch + ks.cs_base);
     } else {
-        T *yacc     = yacc_all + static_cast<size_t>(warp) * ks.block_rows;
-        uint32_t it = 0, ubase = 0;
-        for (uint32_t st = 0; st < bd.n_stages; st++) {
-            if (a.twice_only && !(ks.stages[bd.first_stage + st].flags & 1u))
-                continue;
-            const uint32_t slot = it % ks.ring_stages, round = it / ks.ring_stages;
-            mbar_wait(smem_u32(&sm.full[slot]), round & 1u);
+        T *yacc = yacc_all + static_cast<size_t>(warp) * ks.block_rows;
+        // Every warp walks every stage; units are dealt round-robin over the warps across stages. The deal is a
+        // function of the stream only, so the split of the y contributions over the warps (hence the rounding) is
+        // the same in every run.
+        RingPos pos;
+        uint32_t ubase = warp;
+        for (uint32_t q = 0; q < n_my_stages; q++, pos.advance(ks.ring_stages)) {
+            const uint32_t slot = pos.slot;
+            mbar_wait(smem_u32(&sm.full[slot]), pos.phase);
             const unsigned char *stage = sm.ring + static_cast<size_t>(slot) * sm.slot_bytes;
             const StageHeader hdr      = *reinterpret_cast<const StageHeader *>(stage);
             const Unit *units          = reinterpret_cast<const Unit *>(stage + sizeof(StageHeader));
             const T *data              = reinterpret_cast<const T *>(stage + hdr.data_byte_off);
             const T *cseg              = reinterpret_cast<const T *>(stage + ks.stage_bytes);
-            for (uint32_t u = (warp - ubase) & (kConsumerWarps - 1); u < hdr.n_units; u += kConsumerWarps) {
+            for (uint32_t u = ubase; u < hdr.n_units; u += kConsumerWarps) {
                 const Unit un = units[u];
                 if (a.twice_only && !unit_twice(un.geom))
                     continue;
-                const uint32_t kind = unit_kind(un.geom);
-                const uint32_t row0 = unit_row0(un.geom), h = unit_h(un.geom), w = unit_w(un.geom);
+                const uint32_t kind = unit_kind(un.geom), row0 = unit_row0(un.geom), h = unit_h(un.geom), w = unit_w(un.geom);
                 const T *c = cseg + un.cslot;
                 if (kind == UNIT_ADDVEC) {
                     // dense leaf applied transposed: its z = op(A)^T x was produced by the REDUCE pass of side 0
@@ -354,64 +406,78 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(KernelSide ks, PassArgs
                         yacc[row0 + i] = add(yacc[row0 + i], c[i]);
                     continue;
                 }
-                const T *P = data + un.data_off;
-                if (h > 16) {
-                    // lanes along the rows, every lane walks all the columns
-                    const int Q = (h + 31) >> 5;
-                    uint32_t ic[kMaxQ];
-                    T acc[kMaxQ];
+                const T *P        = data + un.data_off;
+                const uint32_t ld = unit_ld(h, sizeof(T));
+                const LaneMap m   = lane_map<R>(h, lane);
+                T acc[kMaxQ][R];
 #pragma unroll
-                    for (int q = 0; q < kMaxQ; q++) {
-                        const uint32_t i = lane + 32u * q;
-                        ic[q]            = i < h ? i : h - 1;
-                        acc[q]           = zero_of(T{});
-                    }
-                    if (Q == 1) {
-#pragma unroll 4
-                        for (uint32_t k = 0; k < w; k++)
-                            acc[0] = fma_(cj<CONJ>(P[k * h + ic[0]]), c[k], acc[0]);
-                    } else if (Q == 2) {
+                for (int qq = 0; qq < kMaxQ; qq++)
+#pragma unroll
+                    for (int r = 0; r < R; r++)
+                        acc[qq][r] = zero_of(T{});
+                const uint32_t i0   = R * m.li;
+                const uint32_t off0 = i0 < ld ? i0 : 0u;
+                if (m.logG == 0) {
+                    // tall unit: lanes along the rows, every lane walks all the columns
+                    const uint32_t i1   = i0 + 32u * R;
+                    const uint32_t off1 = i1 < ld ? i1 : 0u;
+                    if (m.Q == 1) {
 #pragma unroll 4
                         for (uint32_t k = 0; k < w; k++) {
-                            const T ck   = c[k];
-                            const T *col = P + k * h;
-                            acc[0]       = fma_(cj<CONJ>(col[ic[0]]), ck, acc[0]);
-                            acc[1]       = fma_(cj<CONJ>(col[ic[1]]), ck, acc[1]);
+                            T f[R];
+                            load_rows(P + k * ld + off0, f);
+                            const T ck = c[k];
+#pragma unroll
+                            for (int r = 0; r < R; r++)
+                                acc[0][r] = fma_(cj<CONJ>(f[r]), ck, acc[0][r]);
                         }
                     } else {
-#pragma unroll 2
+#pragma unroll 4
                         for (uint32_t k = 0; k < w; k++) {
-                            const T ck   = c[k];
-                            const T *col = P + k * h;
+                            T f[R], f1[R];
+                            load_rows(P + k * ld + off0, f);
+                            load_rows(P + k * ld + off1, f1);
+                            const T ck = c[k];
 #pragma unroll
-                            for (int q = 0; q < kMaxQ; q++)
-                                acc[q] = fma_(cj<CONJ>(col[ic[q]]), ck, acc[q]);
+                            for (int r = 0; r < R; r++) {
+                                acc[0][r] = fma_(cj<CONJ>(f[r]), ck, acc[0][r]);
+                                acc[1][r] = fma_(cj<CONJ>(f1[r]), ck, acc[1][r]);
+                            }
                         }
                     }
-#pragma unroll
-                    for (int q = 0; q < kMaxQ; q++) {
-                        const uint32_t i = lane + 32u * q;
-                        if (i < h)
-                            yacc[row0 + i] = add(yacc[row0 + i], acc[q]);
-                    }
                 } else {
-                    // short unit: G segments of lanes work on interleaved columns, then a butterfly over the segments
-                    const LaneMap m   = lane_map(h, lane);
-                    const uint32_t ic = static_cast<uint32_t>(m.li) < h ? m.li : h - 1;
-                    T acc             = zero_of(T{});
-                    for (uint32_t k = m.g; k < w; k += m.G)
-                        acc = fma_(cj<CONJ>(P[k * h + ic]), c[k], acc);
+                    // short unit: the G segments of lanes work on interleaved columns, then a butterfly over the segments
+                    for (uint32_t kk = 0; kk < w; kk += 1u << m.logG) {
+                        const uint32_t k  = kk + m.g;
+                        const bool valid  = k < w;
+                        const uint32_t kc = valid ? k : 0u;
+                        T f[R];
+                        load_rows(P + kc * ld + off0, f);
+                        const T ck = valid ? c[kc] : zero_of(T{});
+#pragma unroll
+                        for (int r = 0; r < R; r++)
+                            acc[0][r] = fma_(cj<CONJ>(f[r]), ck, acc[0][r]);
+                    }
                     for (int d = 1 << m.seglog; d < 32; d <<= 1)
-                        acc = add(acc, shfl_xor(acc, d));
-                    if (m.g == 0 && static_cast<uint32_t>(m.li) < h)
-                        yacc[row0 + m.li] = add(yacc[row0 + m.li], acc);
+#pragma unroll
+                        for (int r = 0; r < R; r++)
+                            acc[0][r] = add(acc[0][r], shfl_xor(acc[0][r], d));
+                }
+                if (m.g == 0) {
+#pragma unroll
+                    for (int qq = 0; qq < kMaxQ; qq++)
+#pragma unroll
+                        for (int r = 0; r < R; r++) {
+                            const uint32_t i = i0 + 32u * R * qq + r;
+                            if (i < h && (qq == 0 || m.Q > 1))
+                                yacc[row0 + i] = add(yacc[row0 + i], acc[qq][r]);
+                        }
                 }
             }
-            ubase = (ubase + hdr.n_units) & (kConsumerWarps - 1);
+            ubase = (ubase - hdr.n_units) & (kConsumerWarps - 1);
             __syncwarp();
             if (lane == 0)
                 mbar_arrive(smem_u32(&sm.empty[slot]));
-            it++;
         }
     }
     __syncthreads();
@@ -432,8 +498,11 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(KernelSide ks, PassArgs
 }
 
 // ---- small kernels ------------------------------------------------------------------------------------
-// One warp per piece: v = sum of its partials in chunk order (fixed summation order), then v (or the
-// sub-range a consumer asked for) is written into every consumer slot of the c-stream.
+// One warp per piece. Phase 1: v[k] = sum of the piece's partials; the 32 / len2 lane groups (len2 = len rounded up to a
+// power of two) take the chunks round-robin and a butterfly folds the groups: a fixed order that depends only on
+// (len, n_sum), hence deterministic. Phase 2: v (or the sub-range a consumer asked for) is written into every
+// consumer slot of the c-stream; pieces with many consumers (large leaves span hundreds of blocks) spread them over
+// the lanes instead of walking them one by one.
 template <typename T>
 __global__ void combine_kernel(const CombineEntry *entries, const CombineDst *dsts, int n, T *scratch, int twice_only) {
     const int warps_per_block = blockDim.x >> 5;
@@ -444,17 +513,35 @@ __global__ void combine_kernel(const CombineEntry *entries, const CombineDst *ds
     if (twice_only && !combine_twice(ce.packed))
         return;
     const uint32_t lane = threadIdx.x & 31, len = combine_len(ce.packed), n_sum = combine_n_sum(ce.packed);
+    const int log2len   = len > 16 ? 5 : (len > 8 ? 4 : (len > 4 ? 3 : (len > 2 ? 2 : (len > 1 ? 1 : 0))));
+    const uint32_t k = lane & ((1u << log2len) - 1u), jg = lane >> log2len, G = 32u >> log2len;
     T v = zero_of(T{});
-    if (lane < len) {
-        const T *p = scratch + ce.src + lane;
+    if (k < len) {
+        const T *p = scratch + ce.src + k;
 #pragma unroll 4
-        for (uint32_t j = 0; j < n_sum; j++)
+        for (uint32_t j = jg; j < n_sum; j += G)
             v = add(v, p[static_cast<size_t>(j) * len]);
     }
-    for (uint32_t q = 0; q < ce.n_dst; q++) {
-        const CombineDst d = dsts[ce.dst_first + q];
-        if (lane >= d.sub_off && lane < static_cast<uint32_t>(d.sub_off) + d.sub_len)
-            scratch[d.slot + lane - d.sub_off] = v;
+    for (int d = 1 << log2len; d < 32; d <<= 1)
+        v = add(v, shfl_xor(v, d));
+    // every lane now holds v[lane % len2]
+    if (ce.n_dst <= 4) {
+        for (uint32_t q = 0; q < ce.n_dst; q++) {
+            const CombineDst d = dsts[ce.dst_first + q];
+            if (lane >= d.sub_off && lane < static_cast<uint32_t>(d.sub_off) + d.sub_len)
+                scratch[d.slot + lane - d.sub_off] = v;
+        }
+    } else {
+        for (uint32_t q0 = 0; q0 < ce.n_dst; q0 += 32) {
+            const uint32_t q   = q0 + lane;
+            const bool mine    = q < ce.n_dst;
+            const CombineDst d = mine ? dsts[ce.dst_first + q] : CombineDst{0u, 0, 0};
+            for (uint32_t el = 0; el < len; el++) {
+                const T val = shfl_xor(v, static_cast<int>(lane ^ el)); // value of lane el
+                if (mine && el >= d.sub_off && el < static_cast<uint32_t>(d.sub_off) + d.sub_len)
+                    scratch[d.slot + el - d.sub_off] = val;
+            }
+        }
     }
 }
 
@@ -527,10 +614,12 @@ struct Kernels<cplx> {
 } // namespace
 
 size_t reduce_smem_bytes(const LaunchConfig &cfg, size_t esize) {
-    return static_cast<size_t>(cfg.reduce_ring_stages) * cfg.stage_bytes + esize * cfg.block_rows + 16 * static_cast<size_t>(cfg.reduce_ring_stages);
+    const size_t slots = static_cast<size_t>(cfg.reduce_ring_stages);
+    return slots * cfg.stage_bytes + esize * cfg.block_rows + 16 * slots;
 }
 size_t apply_smem_bytes(const LaunchConfig &cfg, size_t esize) {
-    return static_cast<size_t>(cfg.ring_stages) * (cfg.stage_bytes + cfg.cseg_bytes) + esize * cfg.block_rows * kConsumerWarps + 16 * static_cast<size_t>(cfg.ring_stages);
+    const size_t slots = static_cast<size_t>(cfg.ring_stages);
+    return slots * (cfg.stage_bytes + cfg.cseg_bytes) + esize * cfg.block_rows * kConsumerWarps + 16 * slots;
 }
 
 cudaError_t configure_kernels(const LaunchConfig &cfg) {

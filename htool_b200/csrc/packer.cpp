@@ -19,7 +19,8 @@ struct Packer::UnitSpec {
     uint32_t k0, w;   // panel columns [k0, k0+w) (0, 0 for ADDVEC)
     uint32_t sub_off; // ADDVEC: offset of the unit inside its piece
     uint32_t kind, twice;
-    uint32_t elems() const { return kind == UNIT_ADDVEC ? 0u : h * w; }
+    uint32_t ld; // leading dimension of the stored panel
+    uint32_t elems() const { return kind == UNIT_ADDVEC ? 0u : ld * w; }
     uint32_t celems() const { return kind == UNIT_ADDVEC ? h : w; }
 };
 
@@ -60,8 +61,8 @@ Packer::Packer(const htb_hmatrix_desc &desc, const PackOptions &o) : dtype(desc.
         throw std::runtime_error("unknown dtype");
     if (desc.nb_rows < 0 || desc.nb_cols < 0 || desc.nb_leaves < 0 || (desc.nb_leaves > 0 && !desc.leaves))
         throw std::runtime_error("invalid H-matrix description");
-    if (opt.block_rows != 32 && opt.block_rows != 64 && opt.block_rows != 128)
-        throw std::runtime_error("block_rows must be 32, 64 or 128");
+    if ((opt.block_rows != 32 && opt.block_rows != 64 && opt.block_rows != 128) || static_cast<size_t>(opt.block_rows) * esize > 1024)
+        throw std::runtime_error("block_rows must be 32, 64 or 128 (32 or 64 for complex)");
     if (opt.stage_bytes % 16 || opt.cseg_bytes % 16 || opt.stage_bytes > 65536 || opt.piece_cols < 1 || opt.piece_cols > 32)
         throw std::runtime_error("invalid piece_cols / stage_bytes / cseg_bytes");
     // a unit (block_rows x piece) and its descriptor must fit one stage; its c vector one c segment
@@ -150,6 +151,9 @@ Packer::Packer(const htb_hmatrix_desc &desc, const PackOptions &o) : dtype(desc.
             bd.first_stage    = static_cast<uint32_t>(side[s].stages.size());
             bd.n_stages       = static_cast<uint32_t>(per_block[b].size());
             bd.flags          = twice[b] ? 1u : 0u;
+            bd.n_twice_stages = 0;
+            for (const StageDesc &sd : per_block[b])
+                bd.n_twice_stages += sd.flags & 1u;
             side[s].any_twice = side[s].any_twice || twice[b];
             side[s].n_units += units[b];
             for (StageDesc sd : per_block[b]) {
@@ -436,6 +440,7 @@ void Packer::walk_block(int s, int b, Emit &&emit) const {
                 u.k0      = 0;
                 u.w       = 0;
                 u.sub_off = static_cast<uint32_t>(sub_lo - p * piece);
+                u.ld      = 0;
                 emit(u);
             }
             continue;
@@ -444,6 +449,7 @@ void Packer::walk_block(int s, int b, Emit &&emit) const {
         u.row0 = static_cast<uint32_t>(a + lo - bs);
         u.h    = static_cast<uint32_t>(hi - lo);
         u.p0   = static_cast<uint32_t>(lo);
+        u.ld   = unit_ld(u.h, esize);
         for (int p = 0; p < n_pieces(l); p++) {
             u.ui    = ui++;
             u.piece = p;
@@ -523,7 +529,7 @@ void Packer::fill_block(int s, int b, char *dst) const {
                 const size_t r = static_cast<size_t>(l.rank);
                 for (uint32_t k = 0; k < u.w; k++)
                     for (uint32_t i = 0; i < u.h; i++)
-                        out[i + static_cast<size_t>(k) * u.h] = V[(u.k0 + k) + (u.p0 + i) * r];
+                        out[i + static_cast<size_t>(k) * u.ld] = V[(u.k0 + k) + (u.p0 + i) * r];
             } else if (u.kind == UNIT_DENSE && (l.flags & (HTB_LEAF_DIAG_SYMMETRIC | HTB_LEAF_DIAG_HERMITIAN))) {
                 // symv / hemv read only the UPLO triangle (add_matrix_vector_product.hpp:26-52): rebuild the full
                 // block from that triangle so the kernels see an ordinary dense leaf
@@ -542,15 +548,18 @@ void Packer::fill_block(int s, int b, char *dst) const {
                             v = A[gi + gj * m];
                         else
                             v = herm ? conj_of<T>(A[gj + gi * m]) : A[gj + gi * m];
-                        out[i + static_cast<size_t>(k) * u.h] = v;
+                        out[i + static_cast<size_t>(k) * u.ld] = v;
                     }
             } else {
                 // U panel or dense leaf: column-major with lda = nb_rows
                 const T *A     = static_cast<const T *>(l.data0);
                 const size_t m = static_cast<size_t>(l.nb_rows);
                 for (uint32_t k = 0; k < u.w; k++)
-                    std::memcpy(out + static_cast<size_t>(k) * u.h, A + u.p0 + (u.k0 + k) * m, sizeof(T) * u.h);
+                    std::memcpy(out + static_cast<size_t>(k) * u.ld, A + u.p0 + (u.k0 + k) * m, sizeof(T) * u.h);
             }
+            if (u.ld != u.h) // zero pad row
+                for (uint32_t k = 0; k < u.w; k++)
+                    out[u.h + static_cast<size_t>(k) * u.ld] = T(0);
             eoff += u.elems();
         }
         const size_t used = cut.header_bytes() + static_cast<size_t>(cut.data_elems) * esize;

@@ -12,7 +12,9 @@
 //     Vt = V^T (n x r), so every panel is "long dimension fast". A panel is cut by the side's blocks into
 //     CHUNKS (h x W, h <= block_rows) and along its short dimension into PIECES of <= piece_cols columns
 //     (the same cut on both sides of a leaf); one (chunk, piece) is a UNIT (h x w), stored column-major
-//     with leading dimension h. Rank and size bucketing happen through the (h, w) unit shape;
+//     with leading dimension ld = h rounded up to an even number for double (so that every column starts on a
+//     16 B boundary and a lane can fetch two rows with one 128-bit shared-memory load; pad rows are zero) and
+//     ld = h for complex<double>. Rank and size bucketing happen through the (h, w) unit shape;
 //   * all units of one block are concatenated, in leaf order, into the block's STREAM, itself cut into
 //     STAGES (<= stage_bytes, 16 B aligned) = one bulk-async copy each. A stage starts with its own
 //     unit descriptors, so a CTA needs nothing but the stream: [StageHeader | Unit x n | coefficients];
@@ -71,6 +73,8 @@ HTB_HD inline uint32_t unit_h(uint32_t g) { return ((g >> 8) & 0xffu) + 1u; }
 HTB_HD inline uint32_t unit_w(uint32_t g) { return (g >> 16) & 0xffu; }
 HTB_HD inline uint32_t unit_kind(uint32_t g) { return (g >> 24) & 0x3u; }
 HTB_HD inline uint32_t unit_twice(uint32_t g) { return (g >> 26) & 0x1u; }
+// leading dimension of a unit of height h
+HTB_HD inline uint32_t unit_ld(uint32_t h, size_t esize) { return esize == 8 ? (h + 1u) & ~1u : h; }
 inline uint32_t make_geom(uint32_t row0, uint32_t h, uint32_t w, uint32_t kind, uint32_t twice) {
     return (row0 & 0xffu) | (((h - 1u) & 0xffu) << 8) | ((w & 0xffu) << 16) | ((kind & 3u) << 24) | ((twice & 1u) << 26);
 }
@@ -97,8 +101,9 @@ struct BlockDesc {
     int32_t nrows;
     uint32_t first_stage;
     uint32_t n_stages;
-    uint32_t flags; // bit 0: holds at least one applied-twice unit
-    uint32_t reserved[3];
+    uint32_t flags;          // bit 0: holds at least one applied-twice unit
+    uint32_t n_twice_stages; // stages holding at least one applied-twice unit
+    uint32_t reserved[2];
 };
 static_assert(sizeof(BlockDesc) == 32, "BlockDesc must be 32 bytes");
 

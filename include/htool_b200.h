@@ -185,7 +185,7 @@ enum { HTB_PASS_REDUCE = 0, /* t = V x / op(U)^T x / op(A)^T x, streams one side
        HTB_PASS_KINDS = 4 };
 int htb_profile_passes(htb_handle h, int enable);
 int htb_get_pass_times(htb_handle h, double ms[HTB_PASS_KINDS], int64_t launches[HTB_PASS_KINDS]);
-/* Tunables for experiments: block_rows, piece_cols, stage_bytes, cseg_bytes, ring_stages, evict_first,
+/* Tunables for experiments: block_rows, piece_cols, stage_bytes, cseg_bytes, ring_stages, reduce_ring_stages, evict_first,
  * upload_chunk_mb; unknown keys return HTB_ERR_INVALID. Must be set before htb_create, they are read when the
  * store is packed. */
 int htb_set_option(const char *key, int64_t value);

@@ -60,7 +60,10 @@ class PackedSide:
             row0, h, w, kind, twice = g & 0xFF, ((g >> 8) & 0xFF) + 1, (g >> 16) & 0xFF, (g >> 24) & 3, (g >> 26) & 1
             panel = None
             if kind != UNIT_ADDVEC:
-                panel = data[int(u["data_off"]): int(u["data_off"]) + h * w].reshape(w, h).T  # column-major, ld = h
+                ld = (h + 1) & ~1 if isz == 8 else h  # unit_ld (store.hpp): even leading dimension for double
+                full = data[int(u["data_off"]): int(u["data_off"]) + ld * w].reshape(w, ld).T  # column-major
+                assert not full[h:, :].any()  # pad rows are zero
+                panel = full[:h, :]
             yield u, row0, h, w, kind, twice, panel
 
 

@@ -115,8 +115,8 @@ def test_deterministic_bitwise(capi):
     op.close()
 
 
-@pytest.mark.parametrize("opts", [dict(block_rows=32, piece_cols=4, stage_bytes=4096, cseg_bytes=512, ring_stages=2), dict(block_rows=128, piece_cols=32, stage_bytes=65536, cseg_bytes=4096, ring_stages=2, reduce_ring_stages=3),
-                                  dict(evict_first=0, ring_stages=8, stage_bytes=8192, piece_cols=8, cseg_bytes=1024)])
+@pytest.mark.parametrize("opts", [dict(block_rows=32, piece_cols=4, stage_bytes=4096, cseg_bytes=512, ring_stages=2, reduce_ring_stages=9), dict(block_rows=128, piece_cols=16, stage_bytes=16448, cseg_bytes=2048),
+                                  dict(evict_first=0, ring_stages=5, reduce_ring_stages=2, stage_bytes=8192, piece_cols=8, cseg_bytes=2048)])
 def test_packer_and_launch_options(capi, opts):
     defaults = {k: capi.get_option(k) for k in ("block_rows", "piece_cols", "stage_bytes", "cseg_bytes", "ring_stages", "reduce_ring_stages", "evict_first")}
     try:
@@ -124,6 +124,10 @@ def test_packer_and_launch_options(capi, opts):
             capi.set_option(k, v)
         for name in ("d_SL", "z_HU", "d_strip_SU"):
             flat, entries, _ = load_golden(name)
+            if flat.np_dtype == np.complex128 and opts.get("block_rows", 64) > 64:
+                with pytest.raises(capi.HtbError):  # block_rows * sizeof(T) <= 1024
+                    capi.Operator(flat.desc)
+                continue
             op = capi.Operator(flat.desc)
             for e in entries:
                 if e["mu"] != 1:

@@ -97,14 +97,18 @@ def test_packed_stream_matches_golden(name):
 
 
 @pytest.mark.parametrize("opts", [dict(block_rows=32, piece_cols=4, stage_bytes=4096, cseg_bytes=512), dict(block_rows=128, piece_cols=32, stage_bytes=65536, cseg_bytes=4096),
-                                  dict(piece_cols=8, stage_bytes=8192, cseg_bytes=1024)])
+                                  dict(piece_cols=8, stage_bytes=16384, cseg_bytes=2048)])
 def test_packer_options(opts):
     DEFAULTS = {k: capi.get_option(k) for k in ("block_rows", "piece_cols", "stage_bytes", "cseg_bytes")}
     try:
         for k, v in opts.items():
             capi.set_option(k, v)
         _check(random_flatcase(seed=5, symmetric="S"))
-        _check(random_flatcase(seed=6, dtype_code=1))
+        if opts.get("block_rows", 64) * 16 <= 1024:
+            _check(random_flatcase(seed=6, dtype_code=1))
+        else:  # a lane owns at most two row slabs: block_rows * sizeof(T) <= 1024
+            with pytest.raises(capi.HtbError):
+                PackedSide(random_flatcase(seed=6, dtype_code=1).desc, 0)
     finally:
         for k, v in DEFAULTS.items():
             capi.set_option(k, v)
@@ -121,7 +125,7 @@ def test_stream_invariants():
         assert (side.blocks["nrows"] <= 64).all() and (side.blocks["nrows"] > 0).all()
         # stages are 16-byte aligned, contiguous and within the granule
         assert (side.stages["byte_off"] % 16 == 0).all() and (side.stages["nbytes"] % 16 == 0).all()
-        assert (side.stages["nbytes"] <= 16384).all()
+        assert (side.stages["nbytes"] <= capi.get_option("stage_bytes")).all()
         assert (side.stages["byte_off"][1:] == side.stages["byte_off"][:-1] + side.stages["nbytes"][:-1]).all()
         assert sorted(side.order.tolist()) == list(range(side.n_blocks))
     # every coefficient is stored exactly once per side it is needed on: U + dense on side 0, V on side 1
