@@ -409,7 +409,7 @@ def run_ours(args):
             "achieved_hbm_gbs": achieved_total,
             "achieved_hbm_frac_per_gpu": achieved_total / world / peak,
             "algorithmic_bytes_per_step": bytes_step,
-            "roofline": {"bound": "hbm", "kernel": f"{dom}_kernel<double>" if dtype == np.float64 else f"{dom}_kernel<cplx>", "achieved": dom_achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": f"{dom}_kernel<double, false>" if dtype == np.float64 else f"{dom}_kernel<cplx, false>", "achieved": dom_achieved, "peak": peak, "unit": "GB/s",
                          "frac": dom_achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
                          "other_kernels_ms_per_step": {"reduce": reduce_ms_step, "apply": apply_ms_step, "combine": pt["combine"]["ms"] / prof_steps}},

@@ -28,7 +28,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 namespace {
 std::mutex g_option_mutex;
 std::map<std::string, int64_t> g_options = {
-    {"block_rows", 64}, {"piece_cols", 16}, {"stage_bytes", 16384}, {"cseg_bytes", 2048}, {"ring_stages", 3}, {"reduce_ring_stages", 4}, {"evict_first", 1}, {"upload_chunk_mb", 256}};
+    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 2048}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}};
 
 int64_t option(const char *key) {
     std::lock_guard<std::mutex> lock(g_option_mutex);
@@ -432,7 +432,7 @@ int htb_create(const htb_hmatrix_desc *desc, htb_handle *out) {
     h->symmetry       = desc->symmetry_for_leaves ? desc->symmetry_for_leaves : 'N';
     h->uplo           = desc->uplo_for_leaves ? desc->uplo_for_leaves : 'N';
     h->scratch_elems  = pk->scratch_elems;
-    h->launch_cfg.block_rows  = popt.block_rows;
+    h->launch_cfg.block_rows  = pk->opt.block_rows; // resolved (0 = automatic)
     h->launch_cfg.stage_bytes = popt.stage_bytes;
     h->launch_cfg.cseg_bytes  = popt.cseg_bytes;
     h->launch_cfg.ring_stages        = static_cast<int>(option("ring_stages"));

@@ -311,19 +311,23 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(KernelSide ks, PassArg
         const StageHeader hdr      = *reinterpret_cast<const StageHeader *>(stage);
         const Unit *units          = reinterpret_cast<const Unit *>(stage + sizeof(StageHeader));
         const T *data              = reinterpret_cast<const T *>(stage + hdr.data_byte_off);
-        uint32_t u = ubase;
-        for (; u < hdr.n_units; u += kConsumerWarps) {
+        // ADDVEC units (dense leaves, direction 0): hand their x slices to the APPLY pass through the c-stream. They
+        // hold no coefficients: one unit per LANE, over all the consumer lanes of the CTA.
+        for (uint32_t u = hdr.n_panel + warp * 32 + lane; u < hdr.n_units; u += kConsumerWarps * 32) {
             const Unit un = units[u];
             if (a.twice_only && !unit_twice(un.geom))
                 continue;
-            const uint32_t kind = unit_kind(un.geom), row0 = unit_row0(un.geom), h = unit_h(un.geom), w = unit_w(un.geom);
+            const uint32_t row0 = unit_row0(un.geom), h = unit_h(un.geom);
             T *out = a.scratch + un.out;
-            if (kind == UNIT_ADDVEC) {
-                // dense leaf, direction 0: hand its x slice to the APPLY pass through the c-stream
-                for (uint32_t i = lane; i < h; i += 32)
-                    out[i] = xin[row0 + i];
+            for (uint32_t i = 0; i < h; i++)
+                out[i] = xin[row0 + i];
+        }
+        for (uint32_t u = ubase; u < hdr.n_panel; u += kConsumerWarps) {
+            const Unit un = units[u];
+            if (a.twice_only && !unit_twice(un.geom))
                 continue;
-            }
+            const uint32_t row0 = unit_row0(un.geom), h = unit_h(un.geom), w = unit_w(un.geom);
+            T *out = a.scratch + un.out;
             const T *P        = data + un.data_off;
             const uint32_t ld = unit_ld(h, sizeof(T));
             const LaneMap m   = lane_map<R>(h, lane);
@@ -351,7 +355,7 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(KernelSide ks, PassArg
                 }
             }
         }
-        ubase = (ubase - hdr.n_units) & (kConsumerWarps - 1); // == (warp - units dealt so far) mod 8
+        ubase = (ubase - hdr.n_panel) & (kConsumerWarps - 1); // == (warp - units dealt so far) mod 8
         __syncwarp();
         if (lane == 0)
             mbar_arrive(smem_u32(&sm.empty[slot]));
@@ -394,18 +398,22 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(KernelSide ks, PassArgs
             const Unit *units          = reinterpret_cast<const Unit *>(stage + sizeof(StageHeader));
             const T *data              = reinterpret_cast<const T *>(stage + hdr.data_byte_off);
             const T *cseg              = reinterpret_cast<const T *>(stage + ks.stage_bytes);
-            for (uint32_t u = ubase; u < hdr.n_units; u += kConsumerWarps) {
+            // ADDVEC units: dense leaves applied transposed, their z = op(A)^T x was produced by the REDUCE pass of side 0
+            for (uint32_t u = hdr.n_panel + warp; u < hdr.n_units; u += kConsumerWarps) {
                 const Unit un = units[u];
                 if (a.twice_only && !unit_twice(un.geom))
                     continue;
-                const uint32_t kind = unit_kind(un.geom), row0 = unit_row0(un.geom), h = unit_h(un.geom), w = unit_w(un.geom);
+                const uint32_t row0 = unit_row0(un.geom), h = unit_h(un.geom);
                 const T *c = cseg + un.cslot;
-                if (kind == UNIT_ADDVEC) {
-                    // dense leaf applied transposed: its z = op(A)^T x was produced by the REDUCE pass of side 0
-                    for (uint32_t i = lane; i < h; i += 32)
-                        yacc[row0 + i] = add(yacc[row0 + i], c[i]);
+                for (uint32_t i = lane; i < h; i += 32)
+                    yacc[row0 + i] = add(yacc[row0 + i], c[i]);
+            }
+            for (uint32_t u = ubase; u < hdr.n_panel; u += kConsumerWarps) {
+                const Unit un = units[u];
+                if (a.twice_only && !unit_twice(un.geom))
                     continue;
-                }
+                const uint32_t row0 = unit_row0(un.geom), h = unit_h(un.geom), w = unit_w(un.geom);
+                const T *c = cseg + un.cslot;
                 const T *P        = data + un.data_off;
                 const uint32_t ld = unit_ld(h, sizeof(T));
                 const LaneMap m   = lane_map<R>(h, lane);
@@ -474,7 +482,7 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(KernelSide ks, PassArgs
                         }
                 }
             }
-            ubase = (ubase - hdr.n_units) & (kConsumerWarps - 1);
+            ubase = (ubase - hdr.n_panel) & (kConsumerWarps - 1);
             __syncwarp();
             if (lane == 0)
                 mbar_arrive(smem_u32(&sm.empty[slot]));

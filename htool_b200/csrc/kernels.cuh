@@ -27,11 +27,11 @@ struct SideDevice {
 };
 
 struct LaunchConfig {
-    int block_rows  = 64;
-    int stage_bytes = 16384;
+    int block_rows  = 128;
+    int stage_bytes = 24576;
     int cseg_bytes  = 2048;
-    int ring_stages = 3;        // APPLY ring depth (slot = stage + c segment)
-    int reduce_ring_stages = 4; // REDUCE ring depth (slot = stage)
+    int ring_stages = 2;        // APPLY ring depth (slot = stage + c segment)
+    int reduce_ring_stages = 3; // REDUCE ring depth (slot = stage)
     int evict_first = 1; // L2 evict_first hint on the coefficient stream
 };
 

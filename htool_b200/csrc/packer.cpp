@@ -61,6 +61,8 @@ Packer::Packer(const htb_hmatrix_desc &desc, const PackOptions &o) : dtype(desc.
         throw std::runtime_error("unknown dtype");
     if (desc.nb_rows < 0 || desc.nb_cols < 0 || desc.nb_leaves < 0 || (desc.nb_leaves > 0 && !desc.leaves))
         throw std::runtime_error("invalid H-matrix description");
+    if (opt.block_rows == 0)
+        opt.block_rows = esize == 8 ? 128 : 64;
     if ((opt.block_rows != 32 && opt.block_rows != 64 && opt.block_rows != 128) || static_cast<size_t>(opt.block_rows) * esize > 1024)
         throw std::runtime_error("block_rows must be 32, 64 or 128 (32 or 64 for complex)");
     if (opt.stage_bytes % 16 || opt.cseg_bytes % 16 || opt.stage_bytes > 65536 || opt.piece_cols < 1 || opt.piece_cols > 32)
@@ -511,7 +513,10 @@ void Packer::fill_block(int s, int b, char *dst) const {
         if (cut.nu == 0)
             return;
         const uint32_t nbytes = cut.nbytes();
-        StageHeader hdr{cut.nu, cut.header_bytes(), {0, 0}};
+        // coefficient-carrying units first, ADDVEC units last (the kernels walk the two groups differently)
+        std::stable_partition(pending.begin(), pending.end(), [](const UnitSpec &u) { return u.kind != UNIT_ADDVEC; });
+        const uint32_t n_panel = static_cast<uint32_t>(std::count_if(pending.begin(), pending.end(), [](const UnitSpec &u) { return u.kind != UNIT_ADDVEC; }));
+        StageHeader hdr{cut.nu, cut.header_bytes(), n_panel, 0};
         std::memcpy(cursor, &hdr, sizeof(hdr));
         Unit *units   = reinterpret_cast<Unit *>(cursor + sizeof(StageHeader));
         T *data       = reinterpret_cast<T *>(cursor + cut.header_bytes());

@@ -82,7 +82,8 @@ inline uint32_t make_geom(uint32_t row0, uint32_t h, uint32_t w, uint32_t kind, 
 struct StageHeader {
     uint32_t n_units;
     uint32_t data_byte_off; // from the start of the stage to the coefficient region (multiple of 16)
-    uint32_t reserved[2];
+    uint32_t n_panel;       // units [0, n_panel) hold coefficients; [n_panel, n_units) are ADDVEC units
+    uint32_t reserved;
 };
 static_assert(sizeof(StageHeader) == 16, "StageHeader must be 16 bytes");
 
@@ -128,9 +129,9 @@ struct CombineDst {
 static_assert(sizeof(CombineDst) == 8, "CombineDst must be 8 bytes");
 
 struct PackOptions {
-    int block_rows  = 64;    // 32, 64 or 128
+    int block_rows  = 0;     // 32, 64 or 128; 0 = automatic (128 for double, 64 for complex<double>)
     int piece_cols  = 16;    // columns of a unit (<= 32); lowered automatically so that a unit fits a stage
-    int stage_bytes = 16384; // bulk-copy granule of the coefficient stream, multiple of 16
+    int stage_bytes = 24576; // bulk-copy granule of the coefficient stream, multiple of 16
     int cseg_bytes  = 2048;  // capacity of a stage's c segment, multiple of 16
 };
 

@@ -122,7 +122,7 @@ def test_stream_invariants():
         assert side.blocks["row_start"][0] == 0
         assert (side.blocks["row_start"][1:] == side.blocks["row_start"][:-1] + side.blocks["nrows"][:-1]).all()
         assert side.blocks["row_start"][-1] + side.blocks["nrows"][-1] == side.n
-        assert (side.blocks["nrows"] <= 64).all() and (side.blocks["nrows"] > 0).all()
+        assert (side.blocks["nrows"] <= 128).all() and (side.blocks["nrows"] > 0).all()
         # stages are 16-byte aligned, contiguous and within the granule
         assert (side.stages["byte_off"] % 16 == 0).all() and (side.stages["nbytes"] % 16 == 0).all()
         assert (side.stages["nbytes"] <= capi.get_option("stage_bytes")).all()
