@@ -160,6 +160,7 @@ Packer::Packer(const htb_hmatrix_desc &desc, const PackOptions &o) : dtype(desc.
             side[s].n_units += units[b];
             for (StageDesc sd : per_block[b]) {
                 sd.byte_off += stream;
+                sd.first_unit += static_cast<uint32_t>(m_unit_ptr[s][m_csr_ptr[s][b]]); // block-local -> side-wide
                 sd.c_off = static_cast<uint32_t>(c_off);
                 c_off += sd.c_len;
                 side[s].stages.push_back(sd);
@@ -200,6 +201,7 @@ Packer::Packer(const htb_hmatrix_desc &desc, const PackOptions &o) : dtype(desc.
     }
     for (int s = 0; s < 2; s++)
         make_combine(s);
+    make_mtables();
 }
 
 // Cut [0, n) into blocks of <= block_rows indices. Cut points are taken where no small leaf (<= block_rows
@@ -393,6 +395,108 @@ void Packer::make_combine(int cs) {
     }
 }
 
+// Side tables of the multi-RHS path (store.hpp, MUnit): TF offsets per piece, partial areas for pieces with several
+// producer chunks, one MUnit per unit in stage order, and the panel-buffer batches of every stage.
+void Packer::make_mtables() {
+    const uint64_t n_pieces_total = m_piece_ptr[n_leaves];
+    m_tf_off.assign(n_pieces_total, 0);
+    uint64_t tf = 0;
+    for (int64_t i = 0; i < n_leaves; i++) {
+        const htb_leaf &l = m_leaves[i];
+        if (!active(l))
+            continue;
+        for (int p = 0; p < n_pieces(l); p++) {
+            m_tf_off[m_piece_ptr[i] + p] = static_cast<uint32_t>(tf);
+            tf += piece_len(l, p);
+        }
+    }
+    tf_elems = tf;
+    uint64_t base = tf;
+    for (int cs = 0; cs < 2; cs++) {
+        const int ps = 1 - cs;
+        m_partm_off[cs].assign(n_pieces_total, kDirect);
+        side[cs].partm_base = base;
+        uint64_t off        = 0;
+        for (int64_t i = 0; i < n_leaves; i++) {
+            const htb_leaf &l = m_leaves[i];
+            if (!active(l) || (l.rank < 0 && cs == 0)) // dense leaves, direction 0: x rows are read from the input directly
+                continue;
+            const int n_prod = m_nchunks[ps][i];
+            if (n_prod <= 1)
+                continue;
+            for (int p = 0; p < n_pieces(l); p++) {
+                const int len                       = piece_len(l, p);
+                m_partm_off[cs][m_piece_ptr[i] + p] = static_cast<uint32_t>(base + off);
+                side[cs].combine_m.push_back(CombineEntry{static_cast<uint32_t>(base + off), m_tf_off[m_piece_ptr[i] + p], 0u,
+                                                          static_cast<uint32_t>(n_prod) | (static_cast<uint32_t>(len) << 24) | ((l.flags & HTB_LEAF_APPLY_TRANSPOSED_TOO) ? 0x80000000u : 0u)});
+                off += static_cast<uint64_t>(n_prod) * len;
+            }
+        }
+        side[cs].partm_elems = off;
+        base += off;
+    }
+    mscratch_elems = base;
+    if (mscratch_elems >= (uint64_t(1) << 31))
+        throw std::runtime_error("multi-RHS scratch exceeds 2^31 vectors");
+
+    for (int s = 0; s < 2; s++) {
+        const int nb = static_cast<int>(side[s].blocks.size());
+        side[s].munits.assign(m_unit_ptr[s].back(), MUnit{0, 0, 0, 0});
+#pragma omp parallel for schedule(dynamic, 64)
+        for (int b = 0; b < nb; b++) {
+            // same walk and the same cuts as layout_block / fill_block; inside a stage panel units come first
+            StageCutter cut{esize, static_cast<uint32_t>(opt.stage_bytes), static_cast<uint32_t>(opt.cseg_bytes)};
+            std::vector<UnitSpec> pending;
+            uint64_t pos = m_unit_ptr[s][m_csr_ptr[s][b]];
+            auto close   = [&]() {
+                if (cut.nu == 0)
+                    return;
+                std::stable_partition(pending.begin(), pending.end(), [](const UnitSpec &u) { return u.kind != UNIT_ADDVEC; });
+                uint32_t poff = 0;
+                bool first    = true;
+                for (const UnitSpec &u : pending) {
+                    const htb_leaf &l = m_leaves[u.leaf];
+                    const uint64_t gp = m_piece_ptr[u.leaf] + u.piece;
+                    MUnit mu{0, 0, 0, 0};
+                    // producer role: this unit's side is ps, the consumer side is 1 - s
+                    const int cs = 1 - s;
+                    if (u.kind != UNIT_ADDVEC && !(l.rank < 0 && cs == 0)) {
+                        const uint32_t po = m_partm_off[cs][gp];
+                        mu.out            = po == kDirect ? m_tf_off[gp] : po + static_cast<uint32_t>(u.chunk) * static_cast<uint32_t>(piece_len(l, u.piece));
+                    }
+                    // consumer role: this unit's side is the consumer side
+                    if (u.kind == UNIT_LOWRANK)
+                        mu.src = m_tf_off[gp];
+                    else if (u.kind == UNIT_DENSE)
+                        mu.src = 0x80000000u | (static_cast<uint32_t>(l.col_offset) + u.k0);
+                    else
+                        mu.src = m_tf_off[gp] + u.sub_off;
+                    if (u.kind != UNIT_ADDVEC) {
+                        const uint32_t need = munit_ld(u.row0, u.h) * u.w;
+                        if (first || poff + need > kPanelBufferElems) {
+                            mu.flags |= 1u;
+                            poff = 0;
+                            first = false;
+                        }
+                        mu.poff = poff;
+                        poff += need;
+                    }
+                    side[s].munits[pos++] = mu;
+                }
+                cut.reset();
+                pending.clear();
+            };
+            walk_block(s, b, [&](const UnitSpec &u) {
+                if (!cut.fits(u.elems(), u.celems()))
+                    close();
+                cut.add(u.elems(), u.celems());
+                pending.push_back(u);
+            });
+            close();
+        }
+    }
+}
+
 // Where the REDUCE result of a producer unit of side ps goes.
 uint32_t Packer::producer_out(int ps, const UnitSpec &u) const {
     const int cs      = 1 - ps;
@@ -466,11 +570,13 @@ void Packer::layout_block(int s, int b, std::vector<StageDesc> &stages, std::vec
     StageCutter cut{esize, static_cast<uint32_t>(opt.stage_bytes), static_cast<uint32_t>(opt.cseg_bytes)};
     uint64_t off     = 0;
     uint16_t stflags = 0;
+    uint32_t first   = 0; // units of the block before the current stage
     auto close       = [&]() {
         if (cut.nu == 0)
             return;
-        stages.push_back(StageDesc{off, cut.nbytes(), 0u, static_cast<uint16_t>(cut.c_len_padded()), stflags, 0u});
+        stages.push_back(StageDesc{off, cut.nbytes(), 0u, static_cast<uint16_t>(cut.c_len_padded()), stflags, first});
         off += cut.nbytes();
+        first += cut.nu;
         cut.reset();
         stflags = 0;
     };

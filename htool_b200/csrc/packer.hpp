@@ -30,6 +30,7 @@ class Packer {
     int piece = 16; // effective piece_cols
     SideLayout side[2];
     uint64_t scratch_elems = 0; // elements of one scratch copy: PART[0] | PART[1] | CS[0] | CS[1]
+    uint64_t tf_elems = 0, mscratch_elems = 0; // multi-RHS scratch copy, in vectors: TF | PARTM[0] | PARTM[1]
 
     // statistics
     int64_t n_leaves = 0, n_dense = 0, n_lowrank = 0, n_twice = 0, coefficients = 0, coefficients_twice = 0;
@@ -73,6 +74,9 @@ class Packer {
     void make_incidence(int s);
     void make_partials();
     void make_combine(int cs);
+    void make_mtables();
+    std::vector<uint32_t> m_partm_off[2]; // [consumer side] per global piece: PARTM offset (vectors) or kDirect
+    std::vector<uint32_t> m_tf_off;       // per global piece: TF offset (vectors)
     template <typename Emit>
     void walk_block(int s, int b, Emit &&emit) const;
     void layout_block(int s, int b, std::vector<StageDesc> &stages, std::vector<uint32_t> &unit_stage, uint64_t &n_units, bool &any_twice);

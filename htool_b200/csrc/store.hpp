@@ -93,7 +93,7 @@ struct StageDesc {
     uint32_t c_off;    // first element of the stage's c segment in CS[side] (segment start is 16 B aligned)
     uint16_t c_len;    // elements of the c segment, padded so that its byte size is a multiple of 16
     uint16_t flags;    // bit 0: holds at least one applied-twice unit
-    uint32_t reserved;
+    uint32_t first_unit; // index of the stage's first unit in the side's MUnit table
 };
 static_assert(sizeof(StageDesc) == 24, "StageDesc must be 24 bytes");
 
@@ -128,6 +128,25 @@ struct CombineDst {
 };
 static_assert(sizeof(CombineDst) == 8, "CombineDst must be 8 bytes");
 
+// ---- multi-RHS (mu >= 8, double) side tables ---------------------------------------------------------------------
+// The multi-RHS kernels (mkernels.cu) work on groups of MC <= 64 right-hand sides. Their vectors are MC wide, so the
+// c-stream (one replicated slot per consumer unit) would cost MC times its single-RHS size; instead the first pass
+// writes each piece ONCE into TF[piece] (or per-chunk partials + COMBINE_M when a piece has several producer chunks)
+// and the second pass reads TF / the input matrix rows directly. Offsets are in VECTORS (multiply by MC).
+// One MUnit per unit, in the order the units appear in the stages (StageDesc.first_unit + index in the stage).
+struct MUnit {
+    uint32_t out;  // REDUCE_M: TF / PARTM offset receiving the unit's w result vectors (unused for ADDVEC)
+    uint32_t src;  // APPLY_M: TF offset of the unit's w (ADDVEC: h) input vectors; bit 31 set: row index of the INPUT matrix (dense leaf, direction 0)
+    uint32_t poff; // APPLY_M: element offset of the unit's padded copy inside the CTA's panel buffer (see mkernels.cu)
+    uint32_t flags; // bit 0: this unit starts a new panel-buffer batch
+};
+static_assert(sizeof(MUnit) == 16, "MUnit must be 16 bytes");
+// padded panel-buffer geometry of a unit: rows are shifted by row0 & 7 so that 8-row tiles coincide with the
+// block's 8-row tiles, and the leading dimension is = 4 (mod 8) doubles: conflict-free DMMA fragment loads
+HTB_HD inline uint32_t munit_rows8(uint32_t row0, uint32_t h) { return (((row0 & 7u) + h + 7u) >> 3) << 3; }
+HTB_HD inline uint32_t munit_ld(uint32_t row0, uint32_t h) { return munit_rows8(row0, h) + 4u; }
+constexpr uint32_t kPanelBufferElems = 4608; // 36 KiB of doubles
+
 struct PackOptions {
     int block_rows  = 0;     // 32, 64 or 128; 0 = automatic (128 for double, 64 for complex<double>)
     int piece_cols  = 16;    // columns of a unit (<= 32); lowered automatically so that a unit fits a stage
@@ -149,6 +168,10 @@ struct SideLayout {
     uint64_t part_base = 0, part_elems = 0; // PART[this side as consumer]
     uint64_t cs_base = 0, cs_elems = 0;     // CS[this side]
     bool any_twice = false;
+    // multi-RHS tables (this side as CONSUMER for combine_m / partm)
+    std::vector<MUnit> munits;
+    std::vector<CombineEntry> combine_m; // src = PARTM offset, dst_first = TF offset, n_dst unused
+    uint64_t partm_base = 0, partm_elems = 0; // in vectors, inside the multi-RHS scratch [TF | PARTM[0] | PARTM[1]]
 };
 
 } // namespace htb
