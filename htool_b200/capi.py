@@ -96,13 +96,18 @@ class htb_packed_side(C.Structure):
         ("part_base", C.c_int64),
         ("part_elems", C.c_int64),
         ("piece_cols", C.c_int32),
-        ("reserved", C.c_int32),
+        ("block_rows", C.c_int32),
+        ("n_munits", C.c_int64),
+        ("n_combine_m", C.c_int64),
+        ("mscratch_elems", C.c_int64),
         ("blocks", C.c_void_p),
         ("stages", C.c_void_p),
         ("order", C.c_void_p),
         ("combine", C.c_void_p),
         ("combine_dst", C.c_void_p),
         ("stream", C.c_void_p),
+        ("munits", C.c_void_p),
+        ("combine_m", C.c_void_p),
         ("owner", C.c_void_p),
     ]
 

@@ -28,7 +28,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 namespace {
 std::mutex g_option_mutex;
 std::map<std::string, int64_t> g_options = {
-    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 2048}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}};
+    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 2048}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 2}, {"mrhs_min", 8}};
 
 int64_t option(const char *key) {
     std::lock_guard<std::mutex> lock(g_option_mutex);
@@ -118,6 +118,12 @@ static int upload_store(htb_operator *h, const Packer &pk) {
             break;
         if ((status = upload_vector(sl.combine_dst, &sd.combine_dst, h->owned)) != HTB_OK)
             break;
+        if ((status = upload_vector(sl.munits, &sd.munits, h->owned)) != HTB_OK)
+            break;
+        if ((status = upload_vector(sl.combine_m, &sd.combine_m, h->owned)) != HTB_OK)
+            break;
+        sd.n_combine_m = static_cast<int>(sl.combine_m.size());
+        h->descriptor_bytes += sl.munits.size() * sizeof(MUnit) + sl.combine_m.size() * sizeof(CombineEntry);
         h->descriptor_bytes += sl.blocks.size() * sizeof(BlockDesc) + sl.stages.size() * sizeof(StageDesc) + sl.order.size() * 4 + sl.combine.size() * sizeof(CombineEntry) + sl.combine_dst.size() * sizeof(CombineDst);
         if (sl.stream_bytes == 0)
             continue;
@@ -279,6 +285,82 @@ static int run_product(htb_operator *h, char trans, T alpha, const T *in, T beta
 #undef count
 }
 
+// ---- multi-RHS products on the FP64 tensor cores (double, mu >= mrhs_min) -------------------------------------------
+static int ensure_mscratch(htb_operator *h, int vs) {
+    if (h->d_mscratch && h->mscratch_vs >= vs)
+        return HTB_OK;
+    if (h->d_mscratch)
+        cudaFree(h->d_mscratch);
+    h->d_mscratch  = nullptr;
+    h->mscratch_vs = 0;
+    const size_t bytes = std::max<size_t>(1, h->mscratch_elems) * vs * sizeof(double) * (h->needs_second_copy ? 2 : 1);
+    cudaError_t e      = cudaMalloc(&h->d_mscratch, bytes);
+    if (e != cudaSuccess)
+        return cuda_fail(e, "cudaMalloc(multi-RHS scratch)");
+    h->mscratch_vs = vs;
+    return HTB_OK;
+}
+
+static int run_product_m(htb_operator *h, char trans, double alpha, const double *in, double beta, double *out, int mu) {
+    const char sym   = h->symmetry;
+    const bool twice = sym != 'N' && (h->side[0].any_twice || h->side[1].any_twice);
+    const int D      = h->row_offset - h->col_offset;
+    cudaStream_t st  = h->stream;
+    int rc;
+    auto timed = [&](int kind, auto &&launch, const char *what) -> int {
+        htb_operator::TimedLaunch tl{nullptr, nullptr, kind};
+        if (h->profiling) {
+            cudaEventCreate(&tl.start);
+            cudaEventCreate(&tl.stop);
+            cudaEventRecord(tl.start, st);
+        }
+        cudaError_t e = launch();
+        if (h->profiling) {
+            cudaEventRecord(tl.stop, st);
+            h->timed.push_back(tl);
+        }
+        if (e != cudaSuccess)
+            return cuda_fail(e, what);
+        h->launches++;
+        return HTB_OK;
+    };
+    for (int col0 = 0; col0 < mu; col0 += 64) {
+        const int mc = std::min(64, mu - col0), vs = (mc + 7) & ~7;
+        if ((rc = ensure_mscratch(h, (std::min(64, mu) + 7) & ~7)) != HTB_OK)
+            return rc;
+        double *M1 = static_cast<double *>(h->d_mscratch);
+        double *M2 = M1 + h->mscratch_elems * static_cast<size_t>(h->mscratch_vs);
+        MArgs base;
+        base.ld_in = mu, base.ld_out = mu, base.col0 = col0, base.mc = mc, base.vs = vs, base.alpha = alpha;
+        // ps: side streamed by REDUCE_M (producers), cs: side streamed by APPLY_M (consumers)
+        auto direction = [&](int cs, double *M, int in_shift, long long in_rows, int out_shift, long long out_rows, double b, int twice_only) -> int {
+            const int ps = 1 - cs;
+            MArgs r      = base;
+            r.in = in, r.in_rows = in_rows, r.in_shift = in_shift, r.mscratch = M, r.twice_only = twice_only;
+            int rc2;
+            if (h->side[ps].stream && (rc2 = timed(HTB_PASS_REDUCE, [&]() { return launch_reduce_m(h->side[ps], h->launch_cfg, r, st); }, "reduce_m")) != HTB_OK)
+                return rc2;
+            if (h->side[cs].n_combine_m && (rc2 = timed(HTB_PASS_COMBINE, [&]() { return launch_combine_m(h->side[cs], M, vs, twice_only, st); }, "combine_m")) != HTB_OK)
+                return rc2;
+            MArgs ap = r;
+            ap.out = out, ap.out_rows = out_rows, ap.out_shift = out_shift, ap.beta = b;
+            return timed(HTB_PASS_APPLY, [&]() { return launch_apply_m(h->side[cs], h->launch_cfg, ap, st); }, "apply_m");
+        };
+        if (trans == 'N') {
+            if ((rc = direction(0, M1, 0, h->nb_cols, 0, h->nb_rows, beta, 0)) != HTB_OK)
+                return rc;
+            if (twice && (rc = direction(1, M2, D, h->nb_cols, -D, h->nb_rows, 1.0, 1)) != HTB_OK)
+                return rc;
+        } else {
+            if ((rc = direction(1, M1, 0, h->nb_rows, 0, h->nb_cols, beta, 0)) != HTB_OK)
+                return rc;
+            if (twice && (rc = direction(0, M2, -D, h->nb_rows, D, h->nb_cols, 1.0, 1)) != HTB_OK)
+                return rc;
+        }
+    }
+    return HTB_OK;
+}
+
 static int check_trans(const htb_operator *h, char trans) {
     if (trans != 'N' && trans != 'T' && trans != 'C')
         return fail(HTB_ERR_INVALID, std::string("unknown trans '") + trans + "'");
@@ -293,6 +375,8 @@ int product_device(htb_operator *h, char trans, const void *alpha, const void *i
     int rc = check_trans(h, trans);
     if (rc != HTB_OK)
         return rc;
+    if (h->dtype == HTB_DOUBLE && !split && mu >= static_cast<int>(option("mrhs_min")))
+        return run_product_m(h, trans, *static_cast<const double *>(alpha), static_cast<const double *>(in), *static_cast<const double *>(beta), static_cast<double *>(out), mu);
     for (int c = 0; c < mu; c++) {
         if (h->dtype == HTB_DOUBLE)
             rc = run_product<double>(h, trans, *static_cast<const double *>(alpha), static_cast<const double *>(in) + c, *static_cast<const double *>(beta), static_cast<double *>(out) + c, mu, c == 0 ? split : nullptr);
@@ -325,6 +409,38 @@ int ensure_staging(htb_operator *h, size_t in_bytes, size_t out_bytes) {
     return grow(&h->d_out, &h->h_out, &h->out_cap, out_bytes);
 }
 
+constexpr size_t kStageChunk = size_t(1) << 20;
+
+int staged_h2d(htb_operator *, void *dev, void *pinned, const void *host, size_t bytes, cudaStream_t st) {
+    for (size_t off = 0; off < bytes; off += kStageChunk) {
+        const size_t n = std::min(kStageChunk, bytes - off);
+        std::memcpy(static_cast<char *>(pinned) + off, static_cast<const char *>(host) + off, n);
+        HTB_CUDA(cudaMemcpyAsync(static_cast<char *>(dev) + off, static_cast<char *>(pinned) + off, n, cudaMemcpyHostToDevice, st));
+    }
+    return HTB_OK;
+}
+
+int staged_d2h(htb_operator *h, void *host, void *pinned, const void *dev, size_t bytes, cudaStream_t st) {
+    const size_t n_chunks = (bytes + kStageChunk - 1) / kStageChunk;
+    while (h->chunk_events.size() < n_chunks) {
+        cudaEvent_t ev;
+        HTB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        h->chunk_events.push_back(ev);
+    }
+    for (size_t c = 0; c < n_chunks; c++) {
+        const size_t off = c * kStageChunk, n = std::min(kStageChunk, bytes - off);
+        HTB_CUDA(cudaMemcpyAsync(static_cast<char *>(pinned) + off, static_cast<const char *>(dev) + off, n, cudaMemcpyDeviceToHost, st));
+        HTB_CUDA(cudaEventRecord(h->chunk_events[c], st));
+    }
+    for (size_t c = 0; c < n_chunks; c++) {
+        const size_t off = c * kStageChunk, n = std::min(kStageChunk, bytes - off);
+        HTB_CUDA(cudaEventSynchronize(h->chunk_events[c]));
+        std::memcpy(static_cast<char *>(host) + off, static_cast<char *>(pinned) + off, n);
+    }
+    HTB_CUDA(cudaStreamSynchronize(st));
+    return HTB_OK;
+}
+
 static bool beta_is_zero(const htb_operator *h, const void *beta) {
     const double *b = static_cast<const double *>(beta);
     return b[0] == 0. && (h->dtype == HTB_DOUBLE || b[1] == 0.);
@@ -340,18 +456,13 @@ static int product_host(htb_operator *h, char trans, const void *alpha, const vo
     if ((rc = ensure_staging(h, in_bytes, out_bytes)) != HTB_OK)
         return rc;
     cudaStream_t st = h->stream;
-    std::memcpy(h->h_in, in, in_bytes);
-    HTB_CUDA(cudaMemcpyAsync(h->d_in, h->h_in, in_bytes, cudaMemcpyHostToDevice, st));
-    if (!beta_is_zero(h, beta)) {
-        std::memcpy(h->h_out, out, out_bytes);
-        HTB_CUDA(cudaMemcpyAsync(h->d_out, h->h_out, out_bytes, cudaMemcpyHostToDevice, st));
-    }
+    if ((rc = staged_h2d(h, h->d_in, h->h_in, in, in_bytes, st)) != HTB_OK)
+        return rc;
+    if (!beta_is_zero(h, beta) && (rc = staged_h2d(h, h->d_out, h->h_out, out, out_bytes, st)) != HTB_OK)
+        return rc;
     if ((rc = product_device(h, trans, alpha, h->d_in, beta, h->d_out, mu)) != HTB_OK)
         return rc;
-    HTB_CUDA(cudaMemcpyAsync(h->h_out, h->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
-    HTB_CUDA(cudaStreamSynchronize(st));
-    std::memcpy(out, h->h_out, out_bytes);
-    return HTB_OK;
+    return staged_d2h(h, out, h->h_out, h->d_out, out_bytes, st);
 }
 
 } // namespace htb
@@ -445,7 +556,13 @@ int htb_create(const htb_hmatrix_desc *desc, htb_handle *out) {
     h->sm_count = prop.multiProcessorCount;
     if (std::max(apply_smem_bytes(h->launch_cfg, 16), reduce_smem_bytes(h->launch_cfg, 16)) > static_cast<size_t>(prop.sharedMemPerBlockOptin))
         return fail(HTB_ERR_INVALID, "the shared-memory ring (ring_stages x stage_bytes) exceeds the shared memory of an SM");
+    h->launch_cfg.m_ring_stages = static_cast<int>(option("m_ring_stages"));
+    if (h->launch_cfg.m_ring_stages < 2 || h->launch_cfg.m_ring_stages > 8)
+        return fail(HTB_ERR_INVALID, "m_ring_stages must be in [2, 8]");
     HTB_CUDA(configure_kernels(h->launch_cfg));
+    if (h->dtype == HTB_DOUBLE && reduce_m_smem_bytes(h->launch_cfg, 64) <= static_cast<size_t>(prop.sharedMemPerBlockOptin))
+        HTB_CUDA(configure_mkernels(h->launch_cfg));
+    h->mscratch_elems = pk->mscratch_elems;
     HTB_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
 
@@ -456,6 +573,7 @@ int htb_create(const htb_hmatrix_desc *desc, htb_handle *out) {
     }
     // scratch copies: one for the product, a second one for the transposed second application under symmetric storage
     const bool needs_second    = h->symmetry != 'N' && (h->side[0].any_twice || h->side[1].any_twice);
+    h->needs_second_copy       = needs_second;
     const size_t scratch_bytes = std::max<size_t>(2, h->scratch_elems) * h->esize * (needs_second ? 2 : 1);
     e                          = cudaMalloc(&h->d_scratch, scratch_bytes);
     if (e != cudaSuccess) {
@@ -495,12 +613,14 @@ int htb_destroy(htb_handle h) {
         cudaStreamSynchronize(h->own_stream);
     for (void *p : h->owned)
         cudaFree(p);
-    for (void *p : {h->d_scratch, h->d_in, h->d_out, h->d_perm[0], h->d_perm[1], h->d_work_in, h->d_work_out})
+    for (void *p : {h->d_mscratch, h->d_scratch, h->d_in, h->d_out, h->d_perm[0], h->d_perm[1], h->d_work_in, h->d_work_out})
         if (p)
             cudaFree(p);
     for (void *p : {h->h_in, h->h_out})
         if (p)
             cudaFreeHost(p);
+    for (cudaEvent_t ev : h->chunk_events)
+        cudaEventDestroy(ev);
     if (h->own_stream)
         cudaStreamDestroy(h->own_stream);
     delete h;
@@ -637,12 +757,10 @@ static int product_user(htb_handle h, char trans, const void *alpha, const void 
     if (mem_kind == HTB_MEM_HOST) {
         if ((rc = ensure_staging(h, in_bytes, out_bytes)) != HTB_OK)
             return rc;
-        std::memcpy(h->h_in, in, in_bytes);
-        HTB_CUDA(cudaMemcpyAsync(h->d_in, h->h_in, in_bytes, cudaMemcpyHostToDevice, st));
-        if (!beta_is_zero(h, beta)) {
-            std::memcpy(h->h_out, out, out_bytes);
-            HTB_CUDA(cudaMemcpyAsync(h->d_out, h->h_out, out_bytes, cudaMemcpyHostToDevice, st));
-        }
+        if ((rc = staged_h2d(h, h->d_in, h->h_in, in, in_bytes, st)) != HTB_OK)
+            return rc;
+        if (!beta_is_zero(h, beta) && (rc = staged_h2d(h, h->d_out, h->h_out, out, out_bytes, st)) != HTB_OK)
+            return rc;
         din  = h->d_in;
         dout = h->d_out;
     }
@@ -664,11 +782,8 @@ static int product_user(htb_handle h, char trans, const void *alpha, const void 
     else
         HTB_CUDA(launch_permute<cplx>(static_cast<const cplx *>(h->d_work_out), static_cast<cplx *>(dout), pout, no, mu, false, colmajor, st));
     h->launches++;
-    if (mem_kind == HTB_MEM_HOST) {
-        HTB_CUDA(cudaMemcpyAsync(h->h_out, h->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
-        HTB_CUDA(cudaStreamSynchronize(st));
-        std::memcpy(out, h->h_out, out_bytes);
-    }
+    if (mem_kind == HTB_MEM_HOST)
+        return staged_d2h(h, out, h->h_out, h->d_out, out_bytes, st);
     return HTB_OK;
 }
 
@@ -704,6 +819,12 @@ int htb_pack_host(const htb_hmatrix_desc *desc, int side, htb_packed_side *out) 
         out->part_base     = static_cast<int64_t>(own->layout.part_base);
         out->part_elems    = static_cast<int64_t>(own->layout.part_elems);
         out->piece_cols    = pk.piece;
+        out->block_rows    = pk.opt.block_rows;
+        out->n_munits      = static_cast<int64_t>(own->layout.munits.size());
+        out->n_combine_m   = static_cast<int64_t>(own->layout.combine_m.size());
+        out->mscratch_elems = static_cast<int64_t>(pk.mscratch_elems);
+        out->munits        = own->layout.munits.data();
+        out->combine_m     = own->layout.combine_m.data();
         out->combine_dst   = own->layout.combine_dst.data();
         out->blocks        = own->layout.blocks.data();
         out->stages        = own->layout.stages.data();

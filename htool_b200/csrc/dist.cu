@@ -221,12 +221,10 @@ int htb_dist_add_product_local_to_local(htb_handle h, const void *alpha, const v
         int rc = ensure_staging(h, n_local * es, n_local * es);
         if (rc != HTB_OK)
             return rc;
-        std::memcpy(h->h_in, in_local, n_local * es);
-        HTB_CUDA(cudaMemcpyAsync(xg + size_t(d->offsets[d->rank]) * es, h->h_in, n_local * es, cudaMemcpyHostToDevice, st));
-        if (!beta_zero) {
-            std::memcpy(h->h_out, out_local, n_local * es);
-            HTB_CUDA(cudaMemcpyAsync(h->d_out, h->h_out, n_local * es, cudaMemcpyHostToDevice, st));
-        }
+        if ((rc = staged_h2d(h, xg + size_t(d->offsets[d->rank]) * es, h->h_in, in_local, n_local * es, st)) != HTB_OK)
+            return rc;
+        if (!beta_zero && (rc = staged_h2d(h, h->d_out, h->h_out, out_local, n_local * es, st)) != HTB_OK)
+            return rc;
         dout = h->d_out;
     } else {
         HTB_CUDA(cudaMemcpyAsync(xg + size_t(d->offsets[d->rank]) * es, in_local, n_local * es, cudaMemcpyDeviceToDevice, st));
@@ -256,11 +254,8 @@ int htb_dist_add_product_local_to_local(htb_handle h, const void *alpha, const v
     int rc = product_device(h, 'N', alpha, xg, beta, dout, mu, &split);
     if (rc != HTB_OK)
         return rc;
-    if (mem_kind == HTB_MEM_HOST) {
-        HTB_CUDA(cudaMemcpyAsync(h->h_out, h->d_out, n_local * es, cudaMemcpyDeviceToHost, st));
-        HTB_CUDA(cudaStreamSynchronize(st));
-        std::memcpy(out_local, h->h_out, n_local * es);
-    }
+    if (mem_kind == HTB_MEM_HOST)
+        return staged_d2h(h, out_local, h->h_out, h->d_out, n_local * es, st);
     return HTB_OK;
 }
 

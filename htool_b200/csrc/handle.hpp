@@ -3,6 +3,7 @@
 #define HTB_HANDLE_HPP
 
 #include "kernels.cuh"
+#include "mkernels.cuh"
 #include "packer.hpp"
 #include <cuda_runtime.h>
 #include <htool_b200.h>
@@ -34,10 +35,16 @@ struct htb_operator {
     std::vector<void *> owned; // device allocations of the store
     void *d_scratch      = nullptr;
     uint64_t scratch_elems = 0;
+    // multi-RHS scratch ([TF | PARTM[0] | PARTM[1]] x vector stride), allocated at the first multi-RHS product
+    void *d_mscratch        = nullptr;
+    uint64_t mscratch_elems = 0; // vectors per copy
+    int mscratch_vs         = 0; // vector stride it was allocated for
+    bool needs_second_copy  = false;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     // host-pointer entry points: pinned + device staging, grown on demand
     void *d_in = nullptr, *d_out = nullptr, *h_in = nullptr, *h_out = nullptr;
     size_t in_cap = 0, out_cap = 0;
+    std::vector<cudaEvent_t> chunk_events; // D2H pipeline of the host-pointer entry points
     // user-numbering front ends
     void *d_perm[2]  = {nullptr, nullptr};
     void *d_work_in = nullptr, *d_work_out = nullptr;
@@ -61,6 +68,10 @@ int fail(int status, const std::string &msg);
 int cuda_fail(cudaError_t e, const char *what);
 int product_device(htb_operator *h, char trans, const void *alpha, const void *in, const void *beta, void *out, int mu, const DistSplit *split = nullptr);
 int ensure_staging(htb_operator *h, size_t in_bytes, size_t out_bytes);
+// pageable host <-> device through the pinned staging buffers, in 1 MiB chunks so that the CPU copy of one chunk
+// overlaps the DMA of the previous one
+int staged_h2d(htb_operator *h, void *dev, void *pinned, const void *host, size_t bytes, cudaStream_t st);
+int staged_d2h(htb_operator *h, void *host, void *pinned, const void *dev, size_t bytes, cudaStream_t st); // returns when host is complete
 void dist_destroy(htb_operator *h);
 } // namespace htb
 #endif

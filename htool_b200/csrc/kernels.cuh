@@ -19,6 +19,9 @@ struct SideDevice {
     const unsigned char *stream     = nullptr;
     const CombineEntry *combine     = nullptr; // direction whose consumer is this side
     const CombineDst *combine_dst   = nullptr;
+    const MUnit *munits             = nullptr; // multi-RHS side table, stage order
+    const CombineEntry *combine_m   = nullptr; // multi-RHS partial sums of the direction whose consumer is this side
+    int n_combine_m                 = 0;
     int n_blocks                    = 0;
     int n_combine                   = 0;
     int n                           = 0;
@@ -32,6 +35,7 @@ struct LaunchConfig {
     int cseg_bytes  = 2048;
     int ring_stages = 2;        // APPLY ring depth (slot = stage + c segment)
     int reduce_ring_stages = 3; // REDUCE ring depth (slot = stage)
+    int m_ring_stages      = 2; // multi-RHS kernels
     int evict_first = 1; // L2 evict_first hint on the coefficient stream
 };
 

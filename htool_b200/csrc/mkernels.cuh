@@ -1,0 +1,36 @@
+// htool_b200/csrc/mkernels.cuh — launch interface of the multi-RHS (FP64 tensor core) kernels (mkernels.cu).
+#ifndef HTB_MKERNELS_CUH
+#define HTB_MKERNELS_CUH
+
+#include "kernels.cuh"
+
+namespace htb {
+
+// One pass over a side for a group of mc <= 64 right-hand sides starting at column col0 of ROW-major matrices.
+struct MArgs {
+    const double *in  = nullptr; // input matrix (REDUCE_M: multiplied rows; APPLY_M: rows of dense leaves, direction 0)
+    long long in_rows = 0;
+    int in_shift      = 0; // row index = block / leaf index + in_shift
+    int ld_in         = 0; // mu
+    double *out       = nullptr; // APPLY_M only
+    long long out_rows = 0;
+    int out_shift     = 0;
+    int ld_out        = 0;
+    int col0 = 0, mc = 0; // column group
+    int vs            = 0; // vector stride of the scratch = mc rounded up to a multiple of 8
+    double *mscratch  = nullptr; // one multi-RHS scratch copy: [TF | PARTM[0] | PARTM[1]] x vs
+    double alpha = 0., beta = 0.;
+    int beta_is_zero = 0;
+    int twice_only   = 0;
+};
+
+cudaError_t launch_reduce_m(const SideDevice &side, const LaunchConfig &cfg, const MArgs &args, cudaStream_t stream);
+cudaError_t launch_apply_m(const SideDevice &side, const LaunchConfig &cfg, const MArgs &args, cudaStream_t stream);
+// Sums the partials of the direction whose consumer is `side` into TF.
+cudaError_t launch_combine_m(const SideDevice &side, double *mscratch, int vs, int twice_only, cudaStream_t stream);
+size_t reduce_m_smem_bytes(const LaunchConfig &cfg, int vs);
+size_t apply_m_smem_bytes(const LaunchConfig &cfg);
+cudaError_t configure_mkernels(const LaunchConfig &cfg);
+
+} // namespace htb
+#endif

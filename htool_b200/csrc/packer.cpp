@@ -452,7 +452,7 @@ void Packer::make_mtables() {
                 if (cut.nu == 0)
                     return;
                 std::stable_partition(pending.begin(), pending.end(), [](const UnitSpec &u) { return u.kind != UNIT_ADDVEC; });
-                uint32_t poff = 0;
+                uint32_t poff = 0, in_batch = 0;
                 bool first    = true;
                 for (const UnitSpec &u : pending) {
                     const htb_leaf &l = m_leaves[u.leaf];
@@ -473,13 +473,15 @@ void Packer::make_mtables() {
                         mu.src = m_tf_off[gp] + u.sub_off;
                     if (u.kind != UNIT_ADDVEC) {
                         const uint32_t need = munit_ld(u.row0, u.h) * u.w;
-                        if (first || poff + need > kPanelBufferElems) {
+                        if (first || poff + need > kPanelBufferElems || in_batch == 32) { // <= 32 units per batch: one lane each
                             mu.flags |= 1u;
-                            poff = 0;
-                            first = false;
+                            poff     = 0;
+                            in_batch = 0;
+                            first    = false;
                         }
                         mu.poff = poff;
                         poff += need;
+                        in_batch++;
                     }
                     side[s].munits[pos++] = mu;
                 }
@@ -614,15 +616,17 @@ template <typename T>
 void Packer::fill_block(int s, int b, char *dst) const {
     StageCutter cut{esize, static_cast<uint32_t>(opt.stage_bytes), static_cast<uint32_t>(opt.cseg_bytes)};
     std::vector<UnitSpec> pending;
-    char *cursor = dst;
-    auto close   = [&]() {
+    char *cursor        = dst;
+    uint64_t first_unit = m_unit_ptr[s][m_csr_ptr[s][b]]; // index of the stage's first unit in the side's MUnit table
+    auto close          = [&]() {
         if (cut.nu == 0)
             return;
         const uint32_t nbytes = cut.nbytes();
         // coefficient-carrying units first, ADDVEC units last (the kernels walk the two groups differently)
         std::stable_partition(pending.begin(), pending.end(), [](const UnitSpec &u) { return u.kind != UNIT_ADDVEC; });
         const uint32_t n_panel = static_cast<uint32_t>(std::count_if(pending.begin(), pending.end(), [](const UnitSpec &u) { return u.kind != UNIT_ADDVEC; }));
-        StageHeader hdr{cut.nu, cut.header_bytes(), n_panel, 0};
+        StageHeader hdr{cut.nu, cut.header_bytes(), n_panel, static_cast<uint32_t>(first_unit)};
+        first_unit += cut.nu;
         std::memcpy(cursor, &hdr, sizeof(hdr));
         Unit *units   = reinterpret_cast<Unit *>(cursor + sizeof(StageHeader));
         T *data       = reinterpret_cast<T *>(cursor + cut.header_bytes());

@@ -83,7 +83,7 @@ struct StageHeader {
     uint32_t n_units;
     uint32_t data_byte_off; // from the start of the stage to the coefficient region (multiple of 16)
     uint32_t n_panel;       // units [0, n_panel) hold coefficients; [n_panel, n_units) are ADDVEC units
-    uint32_t reserved;
+    uint32_t first_unit;    // index of the stage's first unit in the side's MUnit table (multi-RHS kernels)
 };
 static_assert(sizeof(StageHeader) == 16, "StageHeader must be 16 bytes");
 

@@ -208,13 +208,17 @@ typedef struct htb_packed_side {
     int64_t cs_base, cs_elems;     /* c-stream of this side inside a scratch copy */
     int64_t part_base, part_elems; /* partials of the direction whose consumer is this side */
     int32_t piece_cols;       /* effective unit width */
-    int32_t reserved;
+    int32_t block_rows;       /* effective block height */
+    int64_t n_munits, n_combine_m; /* multi-RHS side tables (store.hpp: MUnit, CombineEntry) */
+    int64_t mscratch_elems;   /* vectors of ONE multi-RHS scratch copy: TF | PARTM[0] | PARTM[1] */
     const void *blocks;       /* n_blocks x 32 B  (BlockDesc) */
     const void *stages;       /* n_stages x 24 B  (StageDesc) */
     const void *order;        /* n_blocks x uint32: launch order, heaviest block first */
     const void *combine;      /* n_combine x 16 B (CombineEntry) */
     const void *combine_dst;  /* n_combine_dst x 8 B (CombineDst) */
     const void *stream;       /* stream_bytes */
+    const void *munits;       /* n_munits x 16 B (MUnit), stage order */
+    const void *combine_m;    /* n_combine_m x 16 B (CombineEntry: src = PARTM offset, dst_first = TF offset) */
     void *owner;              /* opaque, released by htb_pack_free */
 } htb_packed_side;
 int htb_pack_host(const htb_hmatrix_desc *desc, int side, htb_packed_side *out);

@@ -15,11 +15,13 @@ import numpy as np
 from htool_b200 import capi
 
 BLOCK_DT = np.dtype([("row_start", "<i4"), ("nrows", "<i4"), ("first_stage", "<u4"), ("n_stages", "<u4"), ("flags", "<u4"), ("r0", "<u4"), ("r1", "<u4"), ("r2", "<u4")])
-STAGE_DT = np.dtype([("byte_off", "<u8"), ("nbytes", "<u4"), ("c_off", "<u4"), ("c_len", "<u2"), ("flags", "<u2"), ("reserved", "<u4")])
+STAGE_DT = np.dtype([("byte_off", "<u8"), ("nbytes", "<u4"), ("c_off", "<u4"), ("c_len", "<u2"), ("flags", "<u2"), ("first_unit", "<u4")])
 COMBINE_DT = np.dtype([("src", "<u4"), ("dst_first", "<u4"), ("n_dst", "<u4"), ("packed", "<u4")])
 COMBINE_DST_DT = np.dtype([("slot", "<u4"), ("sub_off", "<u2"), ("sub_len", "<u2")])
 UNIT_DT = np.dtype([("data_off", "<u4"), ("geom", "<u4"), ("out", "<u4"), ("cslot", "<u2"), ("reserved", "<u2")])
+MUNIT_DT = np.dtype([("out", "<u4"), ("src", "<u4"), ("poff", "<u4"), ("flags", "<u4")])
 UNIT_LOWRANK, UNIT_DENSE, UNIT_ADDVEC = 0, 1, 2
+PANEL_BUFFER_ELEMS = 4608
 assert BLOCK_DT.itemsize == 32 and STAGE_DT.itemsize == 24 and COMBINE_DT.itemsize == 16 and COMBINE_DST_DT.itemsize == 8 and UNIT_DT.itemsize == 16
 
 
@@ -43,6 +45,9 @@ class PackedSide:
         self.order = _view(p.order, p.n_blocks, np.dtype("<u4"))
         self.combine = _view(p.combine, p.n_combine, COMBINE_DT)
         self.combine_dst = _view(p.combine_dst, p.n_combine_dst, COMBINE_DST_DT)
+        self.munits = _view(p.munits, p.n_munits, MUNIT_DT)
+        self.combine_m = _view(p.combine_m, p.n_combine_m, COMBINE_DT)
+        self.mscratch_elems, self.block_rows = p.mscratch_elems, p.block_rows
         self.stream = _view(p.stream, p.stream_bytes, np.dtype("u1"))
         self.stream_bytes = p.stream_bytes
         lib.htb_pack_free(C.byref(p))
@@ -51,8 +56,10 @@ class PackedSide:
         """Yields (unit record, row0, h, w, kind, twice, panel as an (h, w) array) for one stage."""
         sd = self.stages[st]
         raw = self.stream[int(sd["byte_off"]): int(sd["byte_off"]) + int(sd["nbytes"])]
-        n_units, data_off = np.frombuffer(raw[:8].tobytes(), dtype="<u4")
+        n_units, data_off, n_panel, first_unit = np.frombuffer(raw[:16].tobytes(), dtype="<u4")
+        assert int(first_unit) == int(sd["first_unit"])
         units = np.frombuffer(raw[16:16 + 16 * int(n_units)].tobytes(), dtype=UNIT_DT)
+        self.last_header = (int(n_units), int(n_panel), int(first_unit))
         isz = np.dtype(dtype).itemsize
         data = np.frombuffer(raw[int(data_off):].tobytes()[: (len(raw) - int(data_off)) // isz * isz], dtype=dtype)
         for u in units:
@@ -151,6 +158,115 @@ class Emulator:
                 g = int(bd["row_start"]) + i + out_shift
                 if 0 <= g < len(out):
                     out[g] = alpha * acc[i] + (0 if beta == 0 else beta * out[g])
+
+    # ---- multi-RHS path (mkernels.cu / run_product_m of capi.cu): same streams, MUnit side tables --------------------
+    def _munits_of_stage(self, s, st):
+        """(unit tuple, MUnit) pairs of a stage, in stage order (panel units first)."""
+        side = self.side[s]
+        units = list(side.units_of_stage(st, self.dtype))
+        n_units, n_panel, first = side.last_header
+        kinds = [u[4] for u in units]
+        assert all(k != UNIT_ADDVEC for k in kinds[:n_panel]) and all(k == UNIT_ADDVEC for k in kinds[n_panel:])
+        return [(u, side.munits[first + i]) for i, u in enumerate(units)], n_panel
+
+    def reduce_m(self, s, X, in_shift, M, twice_only):
+        side = self.side[s]
+        for b in side.order:
+            bd = side.blocks[b]
+            if bd["n_stages"] == 0 or (twice_only and not (bd["flags"] & 1)):
+                continue
+            rows = int(bd["row_start"]) + np.arange(int(bd["nrows"])) + in_shift
+            ok = (rows >= 0) & (rows < X.shape[0])
+            xin = np.zeros((int(bd["nrows"]), X.shape[1]), self.dtype)
+            xin[ok] = X[rows[ok]]
+            for st in range(int(bd["first_stage"]), int(bd["first_stage"] + bd["n_stages"])):
+                if twice_only and not (side.stages[st]["flags"] & 1):
+                    continue
+                pairs, n_panel = self._munits_of_stage(s, st)
+                for (u, row0, h, w, kind, twice, panel), mu in pairs[:n_panel]:
+                    if twice_only and not twice:
+                        continue
+                    o = int(mu["out"])
+                    M[o: o + w] = panel.T @ xin[row0: row0 + h]
+
+    def combine_m(self, s, M, twice_only):
+        for ce in self.side[s].combine_m:
+            pk = int(ce["packed"])
+            n_sum, ln, tw = pk & 0xFFFFFF, (pk >> 24) & 0x7F, pk >> 31
+            if twice_only and not tw:
+                continue
+            src, dst = int(ce["src"]), int(ce["dst_first"])
+            M[dst: dst + ln] = M[src: src + n_sum * ln].reshape(n_sum, ln, -1).sum(axis=0)
+
+    def apply_m(self, s, X, in_shift, out, out_shift, M, alpha, beta, twice_only):
+        side = self.side[s]
+        for b in side.order:
+            bd = side.blocks[b]
+            if twice_only and not (bd["flags"] & 1):
+                continue
+            acc = np.zeros((int(bd["nrows"]), out.shape[1]), self.dtype)
+            for st in range(int(bd["first_stage"]), int(bd["first_stage"] + bd["n_stages"])):
+                if twice_only and not (side.stages[st]["flags"] & 1):
+                    continue
+                pairs, n_panel = self._munits_of_stage(s, st)
+                poff_end, in_batch = 0, 0
+                for i, ((u, row0, h, w, kind, twice, panel), mu) in enumerate(pairs):
+                    src = int(mu["src"])
+                    if kind != UNIT_ADDVEC:
+                        # panel-buffer batches: disjoint regions inside the buffer, <= 32 units per batch
+                        rows8 = (((row0 & 7) + h + 7) >> 3) << 3
+                        need = (rows8 + 4) * w
+                        if int(mu["flags"]) & 1:
+                            poff_end, in_batch = 0, 0
+                        else:
+                            assert i > 0
+                        assert int(mu["poff"]) == poff_end and poff_end + need <= PANEL_BUFFER_ELEMS and in_batch < 32
+                        poff_end += need
+                        in_batch += 1
+                    if twice_only and not twice:
+                        continue
+                    if kind == UNIT_ADDVEC:
+                        acc[row0: row0 + h] += M[src: src + h]
+                        continue
+                    if src & 0x80000000:
+                        rows = (src & 0x7FFFFFFF) + np.arange(w) + in_shift
+                        ok = (rows >= 0) & (rows < X.shape[0])
+                        c = np.zeros((w, X.shape[1]), self.dtype)
+                        c[ok] = X[rows[ok]]
+                    else:
+                        c = M[src: src + w]
+                    acc[row0: row0 + h] += panel @ c
+            for i in range(int(bd["nrows"])):
+                g = int(bd["row_start"]) + i + out_shift
+                if 0 <= g < out.shape[0]:
+                    out[g] = alpha * acc[i] + (0 if beta == 0 else beta * out[g])
+
+    def matrix_product_row_major(self, trans, alpha, X, beta, Y, mu):
+        """run_product_m (double only): X, Y row-major (n x mu)."""
+        sym = self.sym
+        if (trans == "T" and sym == "H") or (trans == "C" and sym == "S"):
+            return 2
+        assert self.dtype == np.float64
+        twice = sym != "N" and self.any_twice
+        X, Y = X.reshape(-1, mu), Y.reshape(-1, mu)
+        nvec = max(1, self.side[0].mscratch_elems)
+        M1, M2 = np.full((nvec, mu), np.nan), np.full((nvec, mu), np.nan)
+        D = self.D
+
+        def direction(cs, M, in_shift, out_shift, b, twice_only):
+            self.reduce_m(1 - cs, X, in_shift, M, twice_only)
+            self.combine_m(cs, M, twice_only)
+            self.apply_m(cs, X, in_shift, Y, out_shift, M, alpha, b, twice_only)
+
+        if trans == "N":
+            direction(0, M1, 0, 0, beta, False)
+            if twice:
+                direction(1, M2, D, -D, 1.0, True)
+        else:
+            direction(1, M1, 0, 0, beta, False)
+            if twice:
+                direction(0, M2, -D, D, 1.0, True)
+        return 0
 
     def vector_product(self, trans, alpha, x, beta, y):
         sym = self.sym

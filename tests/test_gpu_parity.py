@@ -80,12 +80,19 @@ def test_random_leaf_lists_vs_oracle(capi, seed, dtype_code, symmetric):
             assert flat.oracle_vector_product(trans, alpha, x, beta, yo) == 0
             op.add_vector_product(trans, alpha, x, beta, yg)
             assert rel_err(yg, yo) < TOL, (trans, alpha, beta, rel_err(yg, yo))
-        mu = 5
-        X, Y0 = rnd(rng, ni * mu, flat.np_dtype), rnd(rng, no * mu, flat.np_dtype)
-        Yo, Yg = Y0.copy(), Y0.copy()
-        flat.oracle_matrix_product_row_major(trans, 0.5, X, 2.0, Yo, mu)
-        op.add_matrix_product_row_major(trans, 0.5, X, 2.0, Yg, mu)
-        assert rel_err(Yg, Yo) < TOL
+        # mu = 5: column loop over the single-RHS kernels; mu >= 8 (double): FP64 tensor-core kernels, column groups of 64
+        for mu in (5, 8, 13, 64, 70):
+            X, Y0 = rnd(rng, ni * mu, flat.np_dtype), rnd(rng, no * mu, flat.np_dtype)
+            Yo, Yg = Y0.copy(), Y0.copy()
+            flat.oracle_matrix_product_row_major(trans, 0.5, X, 2.0, Yo, mu)
+            op.add_matrix_product_row_major(trans, 0.5, X, 2.0, Yg, mu)
+            assert rel_err(Yg, Yo) < TOL, (trans, mu, rel_err(Yg, Yo))
+            if mu == 13:  # beta == 0 must not read the output
+                Yg = np.full(no * mu, np.nan, flat.np_dtype)
+                Yo = np.zeros(no * mu, flat.np_dtype)
+                flat.oracle_matrix_product_row_major(trans, 0.5, X, 0.0, Yo, mu)
+                op.add_matrix_product_row_major(trans, 0.5, X, 0.0, Yg, mu)
+                assert rel_err(Yg, Yo) < TOL
     op.close()
 
 
@@ -200,12 +207,12 @@ def test_live_reference(capi, kw, have_ref):
         case.vector_product(trans, alpha, x, beta, yr, variant="openmp")
         op.add_vector_product(trans, alpha, x, beta, yg)
         assert rel_err(yg, yr) < TOL, (kw, trans, rel_err(yg, yr))
-    mu = 3
-    X, Y0 = rnd(rng, case.nb_cols * mu, case.np_dtype), rnd(rng, case.nb_rows * mu, case.np_dtype)
-    Yr, Yg = Y0.copy(), Y0.copy()
-    case.matrix_product_row_major("N", 1.0, X, 0.5, Yr, mu, variant="openmp")
-    op.add_matrix_product_row_major("N", 1.0, X, 0.5, Yg, mu)
-    assert rel_err(Yg, Yr) < TOL
+    for mu in (3, 16):
+        X, Y0 = rnd(rng, case.nb_cols * mu, case.np_dtype), rnd(rng, case.nb_rows * mu, case.np_dtype)
+        Yr, Yg = Y0.copy(), Y0.copy()
+        case.matrix_product_row_major("N", 1.0, X, 0.5, Yr, mu, variant="openmp")
+        op.add_matrix_product_row_major("N", 1.0, X, 0.5, Yg, mu)
+        assert rel_err(Yg, Yr) < TOL, (kw, mu, rel_err(Yg, Yr))
     # size-independent property: linearity in x
     x1, x2 = rnd(rng, case.nb_cols, case.np_dtype), rnd(rng, case.nb_cols, case.np_dtype)
     y1, y2, y12 = (np.zeros(case.nb_rows, case.np_dtype) for _ in range(3))

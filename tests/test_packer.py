@@ -155,3 +155,32 @@ def test_empty_and_degenerate_operators():
     tbl = np.array([[0, 0, 5, 4, 0, 0], [3, 2, 1, 1, -1, 0], [1, 1, 1, 1, 1, 0]], np.int32)
     f = FlatCase(0, 6, 5, 0, 0, "N", "N", tbl, np.array([2.0, 3.0, 4.0]))
     _check(f)
+
+
+@pytest.mark.parametrize("seed", range(2))
+@pytest.mark.parametrize("symmetric", [None, "S"])
+def test_multi_rhs_side_tables(seed, symmetric):
+    """MUnit tables / TF + PARTM layout / panel-buffer batches of the multi-RHS path (mkernels.cu), emulated."""
+    flat = random_flatcase(seed=seed, symmetric=symmetric)
+    em = Emulator(flat)
+    rng = np.random.default_rng(1)
+    for trans in "NT":
+        ni, no = (flat.nb_cols, flat.nb_rows) if trans == "N" else (flat.nb_rows, flat.nb_cols)
+        mu = 5
+        X, Y0 = rnd(rng, ni * mu, np.float64), rnd(rng, no * mu, np.float64)
+        Yo, Ye = Y0.copy(), Y0.copy()
+        assert flat.oracle_matrix_product_row_major(trans, 0.5, X, 2.0, Yo, mu) == 0
+        assert em.matrix_product_row_major(trans, 0.5, X, 2.0, Ye, mu) == 0
+        assert rel_err(Ye, Yo) < TOL
+
+
+def test_multi_rhs_side_tables_golden():
+    for name in ("d_N", "d_SL", "d_strip_SU", "d_rect"):
+        flat, entries, _ = load_golden(name)
+        em = Emulator(flat)
+        for e in entries:
+            if e["mu"] == 1:
+                continue
+            y = e["y_in"].copy()
+            assert em.matrix_product_row_major(e["trans"], e["alpha"], e["x"], e["beta"], y, e["mu"]) == 0
+            assert rel_err(y, e["y_seq"]) < TOL, (name, e["trans"])

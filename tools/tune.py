@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--dtype", default="double", choices=["double", "complex"])
     ap.add_argument("--symmetry", default="N", choices=["N", "S"])
     ap.add_argument("--trans", default="N")
+    ap.add_argument("--mu", type=int, default=1)
     ap.add_argument("--set", action="append", default=[], help="comma separated key=value list; one product configuration per --set")
     args = ap.parse_args()
 
@@ -45,10 +46,14 @@ def main():
     dtype = case.np_dtype
     esize = np.dtype(dtype).itemsize
     ni, no = (case.nb_cols, case.nb_rows) if args.trans == "N" else (case.nb_rows, case.nb_cols)
-    x = bench.seeded_x(ni, dtype)
-    y_ref = np.zeros(no, dtype)
-    case.vector_product(args.trans, 1.0, x, 0.0, y_ref, variant="openmp")
-    defaults = {k: capi.get_option(k) for k in ("block_rows", "piece_cols", "stage_bytes", "cseg_bytes", "ring_stages", "reduce_ring_stages", "evict_first")}
+    mu = args.mu
+    x = bench.seeded_x(ni * mu, dtype)
+    y_ref = np.zeros(no * mu, dtype)
+    if mu == 1:
+        case.vector_product(args.trans, 1.0, x, 0.0, y_ref, variant="openmp")
+    else:
+        case.matrix_product_row_major(args.trans, 1.0, x, 0.0, y_ref, mu, variant="openmp")
+    defaults = {k: capi.get_option(k) for k in ("block_rows", "piece_cols", "stage_bytes", "cseg_bytes", "ring_stages", "reduce_ring_stages", "evict_first", "m_ring_stages", "mrhs_min")}
     stream = torch.cuda.Stream()
     x_d = torch.from_numpy(x).cuda()
     tdt = torch.float64 if dtype == np.float64 else torch.complex128
@@ -65,29 +70,37 @@ def main():
             op = capi.Operator(case.desc)
             t_pack = time.perf_counter() - t0
             info = op.info()
-            y = np.zeros(no, dtype)
-            op.add_vector_product(args.trans, 1.0, x, 0.0, y)
+            y = np.zeros(no * mu, dtype)
+
+            def product(xp, yp, device):
+                if mu == 1:
+                    (op.add_vector_product_device if device else op.add_vector_product)(args.trans, 1.0, xp, 0.0, yp)
+                else:
+                    (op.add_matrix_product_row_major_device if device else op.add_matrix_product_row_major)(args.trans, 1.0, xp, 0.0, yp, mu)
+
+            product(x, y, False)
             parity = float(np.linalg.norm(y - y_ref) / np.linalg.norm(y_ref))
             op.set_stream(stream.cuda_stream)
-            y_d = torch.zeros(no, dtype=tdt, device="cuda")
+            y_d = torch.zeros(no * mu, dtype=tdt, device="cuda")
             torch.cuda.synchronize()
             for _ in range(3):
-                op.add_vector_product_device(args.trans, 1.0, x_d.data_ptr(), 0.0, y_d.data_ptr())
+                product(x_d.data_ptr(), y_d.data_ptr(), True)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             for _ in range(args.steps):
-                op.add_vector_product_device(args.trans, 1.0, x_d.data_ptr(), 0.0, y_d.data_ptr())
+                product(x_d.data_ptr(), y_d.data_ptr(), True)
             e1.record(stream)
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / args.steps
             op.profile_passes(True)
             for _ in range(5):
-                op.add_vector_product_device(args.trans, 1.0, x_d.data_ptr(), 0.0, y_d.data_ptr())
+                product(x_d.data_ptr(), y_d.data_ptr(), True)
             pt = op.pass_times()
             op.profile_passes(False)
-            nbytes = esize * (info["coefficients"] + ni + no)
-            print(json.dumps({"opts": {k: v for k, v in opts.items() if v != defaults[k]}, "ms": ms, "gbs": nbytes / ms / 1e6, "parity": parity,
+            nbytes = esize * (info["coefficients"] + mu * (ni + no))
+            flops = 2.0 * mu * (info["coefficients"] + info["coefficients_twice"]) * (1 if dtype == np.float64 else 4)
+            print(json.dumps({"opts": {k: v for k, v in opts.items() if v != defaults[k]}, "mu": mu, "ms": ms, "gbs": nbytes / ms / 1e6, "tflops": flops / ms / 1e9, "parity": parity,
                               "passes_ms": {k: v["ms"] / 5 for k, v in pt.items()}, "pack_s": t_pack, "store_gb": info["store_bytes"] / 1e9,
                               "workspace_gb": info["workspace_bytes"] / 1e9, "descriptor_mb": info["descriptor_bytes"] / 1e6}), flush=True)
             op.set_stream(None)
