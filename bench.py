@@ -372,6 +372,20 @@ def run_ours(args):
     dom = "apply" if apply_ms_step >= reduce_ms_step else "reduce"
     dom_bytes, dom_ms = (apply_bytes, apply_ms_step) if dom == "apply" else (reduce_bytes, reduce_ms_step)
     dom_achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    roof = {"bound": "hbm", "kernel": f"{dom}_kernel<double, false>" if dtype == np.float64 else f"{dom}_kernel<cplx, false>", "achieved": dom_achieved, "peak": peak,
+            "unit": "GB/s", "frac": dom_achieved / peak, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms}
+    if dtype == np.float64 and mu >= 8 and world == 1:
+        # multi-RHS: the leaves are batched contractions on the FP64 tensor cores (mkernels.cu); flops = 2 mu C
+        fpath = os.path.join(REPO, "profiles", "r01_fp64_peak_b200.json")
+        tpeak = json.load(open(fpath))["dmma_m8n8k4_tflops"] if os.path.exists(fpath) else 37.0
+        groups = (mu + 63) // 64  # one launch per group of 64 columns
+        dom_flops = 2.0 * min(mu, 64) * (rank_sides[0] if dom == "apply" else rank_sides[1])
+        dom_ms_launch = dom_ms / groups
+        tf = dom_flops / (dom_ms_launch * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": f"{dom}_m_kernel (DMMA m8n8k4 f64)", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
+                "peak_source": "FP64 DMMA peak measured with tools/fp64_peak.cu on this pool's B200 (profiles/r01_fp64_peak_b200.json); MEASURED_PEAKS.json has no FP64 figure",
+                "algorithmic_flops_per_launch": dom_flops, "ms_per_launch": dom_ms_launch,
+                "whole_product_tflops": 2.0 * mu * C_total / (ms_step * 1e-3) / 1e12}
     traffic = None
     tpath = os.path.join(REPO, "profiles", "traffic_r01.json")
     if os.path.exists(tpath) and world == 1 and args.n == 1_000_000 and mu == 1:
@@ -409,9 +423,7 @@ def run_ours(args):
             "achieved_hbm_gbs": achieved_total,
             "achieved_hbm_frac_per_gpu": achieved_total / world / peak,
             "algorithmic_bytes_per_step": bytes_step,
-            "roofline": {"bound": "hbm", "kernel": f"{dom}_kernel<double, false>" if dtype == np.float64 else f"{dom}_kernel<cplx, false>", "achieved": dom_achieved, "peak": peak, "unit": "GB/s",
-                         "frac": dom_achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
+            "roofline": {**roof, "traffic": traffic,
                          "other_kernels_ms_per_step": {"reduce": reduce_ms_step, "apply": apply_ms_step, "combine": pt["combine"]["ms"] / prof_steps}},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "matvec/s", "h2d_bytes_per_step": int(esize * mu * n_global), "d2h_bytes_per_step": int(esize * mu * n_global), "ms_per_step": 1e3 * e2e_s / args.steps},

@@ -28,7 +28,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 namespace {
 std::mutex g_option_mutex;
 std::map<std::string, int64_t> g_options = {
-    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 2048}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 2}, {"mrhs_min", 8}};
+    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 2048}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 5}, {"m_reduce_ring_stages", 5}, {"mrhs_min", 8}};
 
 int64_t option(const char *key) {
     std::lock_guard<std::mutex> lock(g_option_mutex);
@@ -293,7 +293,7 @@ static int ensure_mscratch(htb_operator *h, int vs) {
         cudaFree(h->d_mscratch);
     h->d_mscratch  = nullptr;
     h->mscratch_vs = 0;
-    const size_t bytes = std::max<size_t>(1, h->mscratch_elems) * vs * sizeof(double) * (h->needs_second_copy ? 2 : 1);
+    const size_t bytes = std::max<size_t>(1, h->mscratch_elems) * (vs + 8) * sizeof(double) * (h->needs_second_copy ? 2 : 1);
     cudaError_t e      = cudaMalloc(&h->d_mscratch, bytes);
     if (e != cudaSuccess)
         return cuda_fail(e, "cudaMalloc(multi-RHS scratch)");
@@ -329,9 +329,9 @@ static int run_product_m(htb_operator *h, char trans, double alpha, const double
         if ((rc = ensure_mscratch(h, (std::min(64, mu) + 7) & ~7)) != HTB_OK)
             return rc;
         double *M1 = static_cast<double *>(h->d_mscratch);
-        double *M2 = M1 + h->mscratch_elems * static_cast<size_t>(h->mscratch_vs);
+        double *M2 = M1 + h->mscratch_elems * static_cast<size_t>(h->mscratch_vs + 8);
         MArgs base;
-        base.ld_in = mu, base.ld_out = mu, base.col0 = col0, base.mc = mc, base.vs = vs, base.alpha = alpha;
+        base.ld_in = mu, base.ld_out = mu, base.col0 = col0, base.mc = mc, base.vs = vs, base.vsp = vs + 8, base.alpha = alpha;
         // ps: side streamed by REDUCE_M (producers), cs: side streamed by APPLY_M (consumers)
         auto direction = [&](int cs, double *M, int in_shift, long long in_rows, int out_shift, long long out_rows, double b, int twice_only) -> int {
             const int ps = 1 - cs;
@@ -375,7 +375,7 @@ int product_device(htb_operator *h, char trans, const void *alpha, const void *i
     int rc = check_trans(h, trans);
     if (rc != HTB_OK)
         return rc;
-    if (h->dtype == HTB_DOUBLE && !split && mu >= static_cast<int>(option("mrhs_min")))
+    if (h->m_path_ok && !split && mu >= static_cast<int>(option("mrhs_min")))
         return run_product_m(h, trans, *static_cast<const double *>(alpha), static_cast<const double *>(in), *static_cast<const double *>(beta), static_cast<double *>(out), mu);
     for (int c = 0; c < mu; c++) {
         if (h->dtype == HTB_DOUBLE)
@@ -556,11 +556,13 @@ int htb_create(const htb_hmatrix_desc *desc, htb_handle *out) {
     h->sm_count = prop.multiProcessorCount;
     if (std::max(apply_smem_bytes(h->launch_cfg, 16), reduce_smem_bytes(h->launch_cfg, 16)) > static_cast<size_t>(prop.sharedMemPerBlockOptin))
         return fail(HTB_ERR_INVALID, "the shared-memory ring (ring_stages x stage_bytes) exceeds the shared memory of an SM");
-    h->launch_cfg.m_ring_stages = static_cast<int>(option("m_ring_stages"));
-    if (h->launch_cfg.m_ring_stages < 2 || h->launch_cfg.m_ring_stages > 8)
-        return fail(HTB_ERR_INVALID, "m_ring_stages must be in [2, 8]");
+    h->launch_cfg.m_ring_stages        = static_cast<int>(option("m_ring_stages"));
+    h->launch_cfg.m_reduce_ring_stages = static_cast<int>(option("m_reduce_ring_stages"));
+    if (h->launch_cfg.m_ring_stages < 2 || h->launch_cfg.m_ring_stages > 8 || h->launch_cfg.m_reduce_ring_stages < 2 || h->launch_cfg.m_reduce_ring_stages > 8)
+        return fail(HTB_ERR_INVALID, "m_ring_stages / m_reduce_ring_stages must be in [2, 8]");
     HTB_CUDA(configure_kernels(h->launch_cfg));
-    if (h->dtype == HTB_DOUBLE && reduce_m_smem_bytes(h->launch_cfg, 64) <= static_cast<size_t>(prop.sharedMemPerBlockOptin))
+    h->m_path_ok = h->dtype == HTB_DOUBLE && std::max(reduce_m_smem_bytes(h->launch_cfg, 64), apply_m_smem_bytes(h->launch_cfg)) <= static_cast<size_t>(prop.sharedMemPerBlockOptin);
+    if (h->m_path_ok)
         HTB_CUDA(configure_mkernels(h->launch_cfg));
     h->mscratch_elems = pk->mscratch_elems;
     HTB_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));

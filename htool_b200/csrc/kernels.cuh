@@ -35,7 +35,8 @@ struct LaunchConfig {
     int cseg_bytes  = 2048;
     int ring_stages = 2;        // APPLY ring depth (slot = stage + c segment)
     int reduce_ring_stages = 3; // REDUCE ring depth (slot = stage)
-    int m_ring_stages      = 2; // multi-RHS kernels
+    int m_ring_stages        = 5; // APPLY_M ring depth (slot = stage + 16 KiB c area + offset table), 1 CTA / SM
+    int m_reduce_ring_stages = 5; // REDUCE_M ring depth (1 CTA / SM: the X block takes 76 KiB)
     int evict_first = 1; // L2 evict_first hint on the coefficient stream
 };
 

@@ -17,8 +17,9 @@ struct MArgs {
     int out_shift     = 0;
     int ld_out        = 0;
     int col0 = 0, mc = 0; // column group
-    int vs            = 0; // vector stride of the scratch = mc rounded up to a multiple of 8
-    double *mscratch  = nullptr; // one multi-RHS scratch copy: [TF | PARTM[0] | PARTM[1]] x vs
+    int vs            = 0; // mc rounded up to a multiple of 8
+    int vsp           = 0; // vector stride of the scratch = vs + 8 (padded: conflict-free fragments once staged in shared memory)
+    double *mscratch  = nullptr; // one multi-RHS scratch copy: [TF | PARTM[0] | PARTM[1]] x vsp
     double alpha = 0., beta = 0.;
     int beta_is_zero = 0;
     int twice_only   = 0;

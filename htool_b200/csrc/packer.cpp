@@ -465,8 +465,11 @@ void Packer::make_mtables() {
                         mu.out            = po == kDirect ? m_tf_off[gp] : po + static_cast<uint32_t>(u.chunk) * static_cast<uint32_t>(piece_len(l, u.piece));
                     }
                     // consumer role: this unit's side is the consumer side
-                    if (u.kind == UNIT_LOWRANK)
+                    mu.flags = (u.kind == UNIT_ADDVEC ? u.h : u.w) << 8;
+                    if (u.kind == UNIT_LOWRANK) {
                         mu.src = m_tf_off[gp];
+                        mu.flags |= 2u;
+                    }
                     else if (u.kind == UNIT_DENSE)
                         mu.src = 0x80000000u | (static_cast<uint32_t>(l.col_offset) + u.k0);
                     else
@@ -573,10 +576,12 @@ void Packer::layout_block(int s, int b, std::vector<StageDesc> &stages, std::vec
     uint64_t off     = 0;
     uint16_t stflags = 0;
     uint32_t first   = 0; // units of the block before the current stage
+    uint32_t n_panel = 0; // coefficient-carrying units of the current stage
     auto close       = [&]() {
         if (cut.nu == 0)
             return;
-        stages.push_back(StageDesc{off, cut.nbytes(), 0u, static_cast<uint16_t>(cut.c_len_padded()), stflags, first});
+        stages.push_back(StageDesc{off, cut.nbytes(), 0u, static_cast<uint16_t>(cut.c_len_padded()), stflags, first, static_cast<uint16_t>(cut.nu), static_cast<uint16_t>(n_panel), 0u});
+        n_panel = 0;
         off += cut.nbytes();
         first += cut.nu;
         cut.reset();
@@ -588,6 +593,7 @@ void Packer::layout_block(int s, int b, std::vector<StageDesc> &stages, std::vec
         unit_stage[u.ui]      = static_cast<uint32_t>(stages.size());
         m_unit_cslot[s][u.ui] = static_cast<uint16_t>(cut.c_elems);
         cut.add(u.elems(), u.celems());
+        n_panel += u.kind != UNIT_ADDVEC ? 1u : 0u;
         n_units++;
         if (u.twice) {
             stflags |= 1u;

@@ -94,8 +94,11 @@ struct StageDesc {
     uint16_t c_len;    // elements of the c segment, padded so that its byte size is a multiple of 16
     uint16_t flags;    // bit 0: holds at least one applied-twice unit
     uint32_t first_unit; // index of the stage's first unit in the side's MUnit table
+    uint16_t n_units;    // units of the stage
+    uint16_t n_panel;    // of which coefficient-carrying (they come first)
+    uint32_t reserved;
 };
-static_assert(sizeof(StageDesc) == 24, "StageDesc must be 24 bytes");
+static_assert(sizeof(StageDesc) == 32, "StageDesc must be 32 bytes");
 
 struct BlockDesc {
     int32_t row_start; // first index of the block in the side's index space
@@ -138,7 +141,8 @@ struct MUnit {
     uint32_t out;  // REDUCE_M: TF / PARTM offset receiving the unit's w result vectors (unused for ADDVEC)
     uint32_t src;  // APPLY_M: TF offset of the unit's w (ADDVEC: h) input vectors; bit 31 set: row index of the INPUT matrix (dense leaf, direction 0)
     uint32_t poff; // APPLY_M: element offset of the unit's padded copy inside the CTA's panel buffer (see mkernels.cu)
-    uint32_t flags; // bit 0: this unit starts a new panel-buffer batch
+    uint32_t flags; // bit 0: this unit starts a new panel-buffer batch; bit 1: low-rank panel (its input vectors live in TF);
+                    // bits [8, 16): w (ADDVEC: h), the number of input vectors
 };
 static_assert(sizeof(MUnit) == 16, "MUnit must be 16 bytes");
 // padded panel-buffer geometry of a unit: rows are shifted by row0 & 7 so that 8-row tiles coincide with the

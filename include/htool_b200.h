@@ -212,7 +212,7 @@ typedef struct htb_packed_side {
     int64_t n_munits, n_combine_m; /* multi-RHS side tables (store.hpp: MUnit, CombineEntry) */
     int64_t mscratch_elems;   /* vectors of ONE multi-RHS scratch copy: TF | PARTM[0] | PARTM[1] */
     const void *blocks;       /* n_blocks x 32 B  (BlockDesc) */
-    const void *stages;       /* n_stages x 24 B  (StageDesc) */
+    const void *stages;       /* n_stages x 32 B  (StageDesc) */
     const void *order;        /* n_blocks x uint32: launch order, heaviest block first */
     const void *combine;      /* n_combine x 16 B (CombineEntry) */
     const void *combine_dst;  /* n_combine_dst x 8 B (CombineDst) */

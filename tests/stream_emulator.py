@@ -15,14 +15,14 @@ import numpy as np
 from htool_b200 import capi
 
 BLOCK_DT = np.dtype([("row_start", "<i4"), ("nrows", "<i4"), ("first_stage", "<u4"), ("n_stages", "<u4"), ("flags", "<u4"), ("r0", "<u4"), ("r1", "<u4"), ("r2", "<u4")])
-STAGE_DT = np.dtype([("byte_off", "<u8"), ("nbytes", "<u4"), ("c_off", "<u4"), ("c_len", "<u2"), ("flags", "<u2"), ("first_unit", "<u4")])
+STAGE_DT = np.dtype([("byte_off", "<u8"), ("nbytes", "<u4"), ("c_off", "<u4"), ("c_len", "<u2"), ("flags", "<u2"), ("first_unit", "<u4"), ("n_units", "<u2"), ("n_panel", "<u2"), ("reserved", "<u4")])
 COMBINE_DT = np.dtype([("src", "<u4"), ("dst_first", "<u4"), ("n_dst", "<u4"), ("packed", "<u4")])
 COMBINE_DST_DT = np.dtype([("slot", "<u4"), ("sub_off", "<u2"), ("sub_len", "<u2")])
 UNIT_DT = np.dtype([("data_off", "<u4"), ("geom", "<u4"), ("out", "<u4"), ("cslot", "<u2"), ("reserved", "<u2")])
 MUNIT_DT = np.dtype([("out", "<u4"), ("src", "<u4"), ("poff", "<u4"), ("flags", "<u4")])
 UNIT_LOWRANK, UNIT_DENSE, UNIT_ADDVEC = 0, 1, 2
 PANEL_BUFFER_ELEMS = 4608
-assert BLOCK_DT.itemsize == 32 and STAGE_DT.itemsize == 24 and COMBINE_DT.itemsize == 16 and COMBINE_DST_DT.itemsize == 8 and UNIT_DT.itemsize == 16
+assert BLOCK_DT.itemsize == 32 and STAGE_DT.itemsize == 32 and COMBINE_DT.itemsize == 16 and COMBINE_DST_DT.itemsize == 8 and UNIT_DT.itemsize == 16
 
 
 def _view(addr, count, dt):
@@ -57,7 +57,7 @@ class PackedSide:
         sd = self.stages[st]
         raw = self.stream[int(sd["byte_off"]): int(sd["byte_off"]) + int(sd["nbytes"])]
         n_units, data_off, n_panel, first_unit = np.frombuffer(raw[:16].tobytes(), dtype="<u4")
-        assert int(first_unit) == int(sd["first_unit"])
+        assert int(first_unit) == int(sd["first_unit"]) and int(n_units) == int(sd["n_units"]) and int(n_panel) == int(sd["n_panel"])
         units = np.frombuffer(raw[16:16 + 16 * int(n_units)].tobytes(), dtype=UNIT_DT)
         self.last_header = (int(n_units), int(n_panel), int(first_unit))
         isz = np.dtype(dtype).itemsize
@@ -212,6 +212,7 @@ class Emulator:
                 poff_end, in_batch = 0, 0
                 for i, ((u, row0, h, w, kind, twice, panel), mu) in enumerate(pairs):
                     src = int(mu["src"])
+                    assert (int(mu["flags"]) >> 8) & 0xFF == (h if kind == UNIT_ADDVEC else w) and bool(int(mu["flags"]) & 2) == (kind == UNIT_LOWRANK)
                     if kind != UNIT_ADDVEC:
                         # panel-buffer batches: disjoint regions inside the buffer, <= 32 units per batch
                         rows8 = (((row0 & 7) + h + 7) >> 3) << 3
