@@ -78,50 +78,82 @@ def workload_name(args):
     return f"{k}_N{args.n}_eps1e-4_eta10_leaf10_mindepth{min_depth_for(args.n, args.gpus)}_sym{args.symmetry}_mu{args.mu}"
 
 
+def workload_label(args):
+    base = args.n == 1_000_000 and args.mu == 1 and args.dtype == "double" and args.symmetry == "N"
+    return workload_name(args) + (" (BASELINE.json configs[1])" if base else "")
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line): NVML polled
+    every few milliseconds from a thread (the timed region of 20 products lasts ~65 ms, too short for
+    `nvidia-smi -lms`), nvidia-smi as the fallback when NVML cannot be loaded."""
 
     QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASON_BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
-    def __init__(self, device_index: int):
-        self.rows = []
+    def __init__(self, device_index: int, period_s: float = 0.004):
+        self.rows = []  # (t, sm_mhz, sm_max_mhz, reason names)
         self.proc = None
+        self.stop_flag = False
+        self.source = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(device_index)],
+            import pynvml
+
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[device_index]) if visible and all(v.strip().isdigit() for v in visible.split(",")) else device_index
+            self.nvml, self.handle = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.period = period_s
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.source = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(device_index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.source = "nvidia-smi"
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
+    def _poll_nvml(self):
+        n = self.nvml
+        reasons_fn = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                mask = int(reasons_fn(self.handle))
+                self.rows.append((time.perf_counter(), sm, self.sm_max, [k for k, b in self.REASON_BITS.items() if mask & b]))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def _read_smi(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), line.strip()))
+            f = [c.strip() for c in line.split(",")]
+            try:
+                self.rows.append((time.perf_counter(), float(f[0]), float(f[1]), [nm for nm, v in zip(names, f[3:7]) if v.lower().startswith("active")]))
+            except Exception:
+                continue
 
     def window(self, t0, t1):
-        return [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        return [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-3:]
 
     def stop(self):
+        self.stop_flag = True
         if self.proc:
             self.proc.terminate()
 
-    @staticmethod
-    def summarise(rows):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            f = [c.strip() for c in r.split(",")]
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except Exception:
-                continue
-            for name, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+    def summarise(self, rows):
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
+        reasons = sorted({name for r in rows for name in r[3]})
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": float(max(r[2] for r in rows)), "reasons": reasons, "samples": len(rows), "source": self.source}
 
 
 def peaks():
@@ -169,7 +201,7 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": "H-matvecs/s", "value": value, "unit": "matvec/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64" if args.dtype == "double" else "c128",
-        "data": "synthetic", "config": {"workload": workload_name(args), "n": args.n, "mu": args.mu, "coefficients": info["coefficients"]},
+        "data": "synthetic", "config": {"workload": workload_label(args), "n": args.n, "mu": args.mu, "coefficients": info["coefficients"]},
         "cpu_baseline": {"value": value, "unit": "matvec/s", "cores": threads, "kind": "reference",
                          "sample": f"{args.steps} full H-matvecs (openmp_internal_add_hmatrix_vector_product, OPENBLAS_NUM_THREADS=1) after {args.warmup} warm-ups"},
         "e2e": {"value": value, "unit": "matvec/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -315,7 +347,10 @@ def run_ours(args):
     op.profile_passes(False)
 
     # ---- end to end through the host-pointer C ABI (H2D of x and D2H of y inside the timed region) --------
-    x_host = x_local if world > 1 else x_global
+    # host buffers: page-locked once with htb_host_register (what a Krylov solver does with its vectors before the
+    # solve), so each step is DMA H2D of x -> product -> DMA D2H of y. The pageable variant (staged through the
+    # handle's pinned buffers with host memcpys) is timed beside it.
+    x_host = np.array(x_local if world > 1 else x_global, copy=True)
     y_host = np.zeros(n_local * mu, dtype)
 
     def step_e2e():
@@ -326,23 +361,35 @@ def run_ours(args):
         else:
             op.add_matrix_product_row_major("N", 1.0, x_host, 0.0, y_host, mu)
 
-    for _ in range(3):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    def time_e2e():
+        for _ in range(3):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt
+
+    e2e_pageable_s = time_e2e()
+    capi.host_register(x_host)
+    capi.host_register(y_host)
+    te0 = time.perf_counter()
+    e2e_s = time_e2e()
+    te1 = time.perf_counter()
+    capi.host_unregister(x_host)
+    capi.host_unregister(y_host)
+    assert np.array_equal(y_host, y_gpu), "end-to-end result differs from the parity-checked one"
     e2e_value = args.steps / e2e_s
     clocks = None
     if sampler:
         time.sleep(0.15)
-        clocks = ClockSampler.summarise(sampler.window(tw0, tw1))
+        clocks = sampler.summarise(sampler.window(tw0, tw1))
         sampler.stop()
 
     # ---- algorithmic bytes: s*C + s*mu*(n_src + n_tgt), descriptors excluded -------------
@@ -414,7 +461,7 @@ def run_ours(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64" if dtype == np.float64 else "c128", "data": "synthetic",
             "config": {
-                "workload": workload_name(args) + " (BASELINE.json configs[1])" if (args.n == 1_000_000 and mu == 1 and args.dtype == "double" and args.symmetry == "N") else workload_name(args),
+                "workload": workload_label(args),
                 "n": args.n, "mu": mu, "parallelism": f"row-strips x{world}" if world > 1 else "single GPU",
                 "l2": f"inputs larger than L2: {esize * C_total / world / 1e9:.2f} GB of coefficients streamed per GPU per step vs 126 MB L2 (no flush needed)",
                 "coefficients": C_total, "leaves": int(oinfo["nb_leaves"]) if world == 1 else None,
@@ -426,7 +473,8 @@ def run_ours(args):
             "roofline": {**roof, "traffic": traffic,
                          "other_kernels_ms_per_step": {"reduce": reduce_ms_step, "apply": apply_ms_step, "combine": pt["combine"]["ms"] / prof_steps}},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "matvec/s", "h2d_bytes_per_step": int(esize * mu * n_global), "d2h_bytes_per_step": int(esize * mu * n_global), "ms_per_step": 1e3 * e2e_s / args.steps},
+            "e2e": {"value": e2e_value, "unit": "matvec/s", "h2d_bytes_per_step": int(esize * mu * n_global), "d2h_bytes_per_step": int(esize * mu * n_global), "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "host_buffers": "page-locked (htb_host_register), direct DMA", "pageable_value": args.steps / e2e_pageable_s},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "parity_rel_l2_vs_reference": parity,

@@ -119,6 +119,8 @@ SYMBOLS = {
     "htb_get_info": (C.c_int, [C.c_void_p, C.POINTER(htb_info)]),
     "htb_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "htb_synchronize": (C.c_int, [C.c_void_p]),
+    "htb_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "htb_host_unregister": (C.c_int, [C.c_void_p]),
     "htb_add_vector_product": (C.c_int, [C.c_void_p, C.c_char, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "htb_add_matrix_product_row_major": (C.c_int, [C.c_void_p, C.c_char, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "htb_set_permutations": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -291,6 +293,17 @@ def nccl_unique_id() -> bytes:
     buf = C.create_string_buffer(HTB_NCCL_UNIQUE_ID_BYTES)
     check(lib, lib.htb_nccl_get_unique_id(C.cast(buf, C.c_void_p)))
     return buf.raw
+
+
+def host_register(array: np.ndarray):
+    """Page-locks a numpy buffer for direct DMA by the host-pointer entry points (htb_host_register)."""
+    lib = load()
+    check(lib, lib.htb_host_register(C.c_void_p(array.ctypes.data), array.nbytes))
+
+
+def host_unregister(array: np.ndarray):
+    lib = load()
+    check(lib, lib.htb_host_unregister(C.c_void_p(array.ctypes.data)))
 
 
 def set_option(key: str, value: int):

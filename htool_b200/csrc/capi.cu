@@ -28,7 +28,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 namespace {
 std::mutex g_option_mutex;
 std::map<std::string, int64_t> g_options = {
-    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 2048}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 5}, {"m_reduce_ring_stages", 5}, {"mrhs_min", 8}};
+    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 2048}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 5}, {"m_reduce_ring_stages", 5}, {"mrhs_min", 8}, {"fused_symmetric", 1}};
 
 int64_t option(const char *key) {
     std::lock_guard<std::mutex> lock(g_option_mutex);
@@ -220,7 +220,8 @@ static int run_product(htb_operator *h, char trans, T alpha, const T *in, T beta
             if (part.n_blocks && (rc = count(launch_reduce<T>(part, h->launch_cfg, r1, st), "reduce(V, local)")) != HTB_OK)
                 return rc;
         }
-        if (twice) {
+        const bool fuse = twice && h->fused_symmetric;
+        if (twice && !fuse) {
             // second application of the leaves stored once under symmetry (add_hmatrix_vector_product.hpp:154-163):
             // direction 1 producers restricted to those leaves, t' = op(U)^T x[target], z = op(A)^T x[target], op = conj for 'H'
             PassArgs<T> r0;
@@ -241,10 +242,15 @@ static int run_product(htb_operator *h, char trans, T alpha, const T *in, T beta
         }
         if (h->side[1].stream && h->side[0].n_combine && (rc = count(launch_combine<T>(h->side[0], T1, 0, st), "combine(V)")) != HTB_OK)
             return rc;
-        // y = beta y + alpha (U t + A x), rows owned by one CTA each
+        // y = beta y + alpha (U t + A x), rows owned by one CTA each. Under symmetric storage the same pass ALSO reduces the
+        // stored-once leaves against x[target] (fused): side 0 is streamed once for both applications
         PassArgs<T> a0;
         a0.out = out, a0.out_len = h->nb_rows, a0.scratch = T1, a0.alpha = alpha, a0.beta = beta, a0.stride = stride;
+        if (fuse)
+            a0.fused = 1, a0.in = in, a0.in_len = h->nb_cols, a0.in_shift = D, a0.scratch2 = T2, a0.conj2 = (sym == 'H' && is_complex);
         if ((rc = count(launch_apply<T>(h->side[0], h->launch_cfg, a0, st), "apply(U, A)")) != HTB_OK)
+            return rc;
+        if (fuse && h->side[1].n_combine && (rc = count(launch_combine<T>(h->side[1], T2, 1, st), "combine(U, twice)")) != HTB_OK)
             return rc;
         if (twice) {
             PassArgs<T> a1;
@@ -262,7 +268,8 @@ static int run_product(htb_operator *h, char trans, T alpha, const T *in, T beta
             if (h->side[1].n_combine && (rc = count(launch_combine<T>(h->side[1], T1, 0, st), "combine(U)")) != HTB_OK)
                 return rc;
         }
-        if (twice) {
+        const bool fuse = twice && h->fused_symmetric;
+        if (twice && !fuse) {
             PassArgs<T> r1;
             r1.in = in, r1.in_len = h->nb_rows, r1.in_shift = -D, r1.scratch = T2, r1.twice_only = 1, r1.stride = stride;
             if ((rc = count(launch_reduce<T>(h->side[1], h->launch_cfg, r1, st), "reduce(V, twice)")) != HTB_OK)
@@ -272,7 +279,11 @@ static int run_product(htb_operator *h, char trans, T alpha, const T *in, T beta
         }
         PassArgs<T> a1;
         a1.out = out, a1.out_len = h->nb_cols, a1.scratch = T1, a1.alpha = alpha, a1.beta = beta, a1.conj = conj, a1.stride = stride;
+        if (fuse)
+            a1.fused = 1, a1.in = in, a1.in_len = h->nb_rows, a1.in_shift = -D, a1.scratch2 = T2, a1.conj2 = 0;
         if ((rc = count(launch_apply<T>(h->side[1], h->launch_cfg, a1, st), "apply(V^T)")) != HTB_OK)
+            return rc;
+        if (fuse && h->side[0].n_combine && (rc = count(launch_combine<T>(h->side[0], T2, 1, st), "combine(V, twice)")) != HTB_OK)
             return rc;
         if (twice) {
             PassArgs<T> a0;
@@ -411,16 +422,46 @@ int ensure_staging(htb_operator *h, size_t in_bytes, size_t out_bytes) {
 
 constexpr size_t kStageChunk = size_t(1) << 20;
 
+// Page-locked host memory (cudaMallocHost / cudaHostRegister / htb_host_register) is copied by the DMA engines directly
+bool is_pinned_host(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// pageable -> pinned copy of one chunk, split over the OpenMP threads of the caller's process
+void host_copy(char *dst, const char *src, size_t n) {
+    constexpr size_t kPiece = size_t(128) << 10;
+    const long long pieces  = static_cast<long long>((n + kPiece - 1) / kPiece);
+#pragma omp parallel for schedule(static) if (pieces >= 4)
+    for (long long i = 0; i < pieces; i++) {
+        const size_t off = static_cast<size_t>(i) * kPiece;
+        std::memcpy(dst + off, src + off, std::min(kPiece, n - off));
+    }
+}
+
 int staged_h2d(htb_operator *, void *dev, void *pinned, const void *host, size_t bytes, cudaStream_t st) {
+    if (is_pinned_host(host)) {
+        HTB_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, st));
+        return HTB_OK;
+    }
     for (size_t off = 0; off < bytes; off += kStageChunk) {
         const size_t n = std::min(kStageChunk, bytes - off);
-        std::memcpy(static_cast<char *>(pinned) + off, static_cast<const char *>(host) + off, n);
+        host_copy(static_cast<char *>(pinned) + off, static_cast<const char *>(host) + off, n);
         HTB_CUDA(cudaMemcpyAsync(static_cast<char *>(dev) + off, static_cast<char *>(pinned) + off, n, cudaMemcpyHostToDevice, st));
     }
     return HTB_OK;
 }
 
 int staged_d2h(htb_operator *h, void *host, void *pinned, const void *dev, size_t bytes, cudaStream_t st) {
+    if (is_pinned_host(host)) {
+        HTB_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, st));
+        HTB_CUDA(cudaStreamSynchronize(st));
+        return HTB_OK;
+    }
     const size_t n_chunks = (bytes + kStageChunk - 1) / kStageChunk;
     while (h->chunk_events.size() < n_chunks) {
         cudaEvent_t ev;
@@ -435,7 +476,7 @@ int staged_d2h(htb_operator *h, void *host, void *pinned, const void *dev, size_
     for (size_t c = 0; c < n_chunks; c++) {
         const size_t off = c * kStageChunk, n = std::min(kStageChunk, bytes - off);
         HTB_CUDA(cudaEventSynchronize(h->chunk_events[c]));
-        std::memcpy(static_cast<char *>(host) + off, static_cast<char *>(pinned) + off, n);
+        host_copy(static_cast<char *>(host) + off, static_cast<char *>(pinned) + off, n);
     }
     HTB_CUDA(cudaStreamSynchronize(st));
     return HTB_OK;
@@ -478,6 +519,20 @@ int htb_device_count(int *count) {
         return fail(HTB_ERR_INVALID, "null argument");
     *count = 0;
     HTB_CUDA(cudaGetDeviceCount(count));
+    return HTB_OK;
+}
+
+int htb_host_register(void *ptr, size_t bytes) {
+    if (!ptr || !bytes)
+        return fail(HTB_ERR_INVALID, "null buffer");
+    HTB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return HTB_OK;
+}
+
+int htb_host_unregister(void *ptr) {
+    if (!ptr)
+        return fail(HTB_ERR_INVALID, "null buffer");
+    HTB_CUDA(cudaHostUnregister(ptr));
     return HTB_OK;
 }
 
@@ -564,7 +619,8 @@ int htb_create(const htb_hmatrix_desc *desc, htb_handle *out) {
     h->m_path_ok = h->dtype == HTB_DOUBLE && std::max(reduce_m_smem_bytes(h->launch_cfg, 64), apply_m_smem_bytes(h->launch_cfg)) <= static_cast<size_t>(prop.sharedMemPerBlockOptin);
     if (h->m_path_ok)
         HTB_CUDA(configure_mkernels(h->launch_cfg));
-    h->mscratch_elems = pk->mscratch_elems;
+    h->mscratch_elems  = pk->mscratch_elems;
+    h->fused_symmetric = option("fused_symmetric") != 0 && fused_smem_bytes(h->launch_cfg, 16) <= static_cast<size_t>(prop.sharedMemPerBlockOptin);
     HTB_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
 

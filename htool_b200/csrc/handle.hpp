@@ -40,6 +40,7 @@ struct htb_operator {
     uint64_t mscratch_elems = 0; // vectors per copy
     int mscratch_vs         = 0; // vector stride it was allocated for
     bool needs_second_copy  = false;
+    bool fused_symmetric    = true;  // symmetric storage: second application fused into the first APPLY pass
     bool m_path_ok          = false; // double, and the multi-RHS kernels fit the shared memory with the current options
     cudaStream_t own_stream = nullptr, stream = nullptr;
     // host-pointer entry points: pinned + device staging, grown on demand

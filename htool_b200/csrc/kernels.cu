@@ -273,10 +273,43 @@ __device__ __forceinline__ void reduce_batch(const T *P, uint32_t ld, uint32_t w
     }
 }
 
+// REDUCE of one coefficient-carrying unit: out[k] = sum_i op(P[i,k]) xin[row0 + i], k < w
+template <typename T, bool CONJ>
+__device__ __forceinline__ void reduce_unit(const Unit &un, const T *data, const T *xin, T *scratch, int lane) {
+    constexpr int R = Rows<T>::R;
+    const uint32_t row0 = unit_row0(un.geom), h = unit_h(un.geom), w = unit_w(un.geom);
+    T *out            = scratch + un.out;
+    const T *P        = data + un.data_off;
+    const uint32_t ld = unit_ld(h, sizeof(T));
+    const LaneMap m   = lane_map<R>(h, lane);
+    uint32_t off[kMaxQ];
+    T xv[kMaxQ][R];
+#pragma unroll
+    for (int qq = 0; qq < kMaxQ; qq++) {
+        const uint32_t i0 = R * (m.li + 32u * qq);
+        off[qq]           = i0 < ld ? i0 : 0u;
+#pragma unroll
+        for (int r = 0; r < R; r++)
+            xv[qq][r] = i0 + r < h ? xin[row0 + i0 + r] : zero_of(T{});
+    }
+    for (uint32_t kb = 0; kb < w;) {
+        const uint32_t per_seg = (w - kb + (1u << m.logG) - 1u) >> m.logG; // columns left for each segment
+        if (per_seg > 4) {
+            reduce_batch<T, CONJ, 8>(P, ld, w, kb, m, off, xv, out);
+            kb += 8u << m.logG;
+        } else if (per_seg > 2) {
+            reduce_batch<T, CONJ, 4>(P, ld, w, kb, m, off, xv, out);
+            kb += 4u << m.logG;
+        } else {
+            reduce_batch<T, CONJ, 2>(P, ld, w, kb, m, off, xv, out);
+            kb += 2u << m.logG;
+        }
+    }
+}
+
 // ---- REDUCE -------------------------------------------------------------------------------------------
 template <typename T, bool CONJ>
 __global__ void __launch_bounds__(kThreads) reduce_kernel(KernelSide ks, PassArgs<T> a) {
-    constexpr int R = Rows<T>::R;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const BlockDesc bd = ks.blocks[ks.order[blockIdx.x]];
     const uint32_t n_my_stages = a.twice_only ? bd.n_twice_stages : bd.n_stages;
@@ -326,34 +359,7 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(KernelSide ks, PassArg
             const Unit un = units[u];
             if (a.twice_only && !unit_twice(un.geom))
                 continue;
-            const uint32_t row0 = unit_row0(un.geom), h = unit_h(un.geom), w = unit_w(un.geom);
-            T *out = a.scratch + un.out;
-            const T *P        = data + un.data_off;
-            const uint32_t ld = unit_ld(h, sizeof(T));
-            const LaneMap m   = lane_map<R>(h, lane);
-            uint32_t off[kMaxQ];
-            T xv[kMaxQ][R];
-#pragma unroll
-            for (int qq = 0; qq < kMaxQ; qq++) {
-                const uint32_t i0 = R * (m.li + 32u * qq);
-                off[qq]           = i0 < ld ? i0 : 0u;
-#pragma unroll
-                for (int r = 0; r < R; r++)
-                    xv[qq][r] = i0 + r < h ? xin[row0 + i0 + r] : zero_of(T{});
-            }
-            for (uint32_t kb = 0; kb < w;) {
-                const uint32_t per_seg = (w - kb + (1u << m.logG) - 1u) >> m.logG; // columns left for each segment
-                if (per_seg > 4) {
-                    reduce_batch<T, CONJ, 8>(P, ld, w, kb, m, off, xv, out);
-                    kb += 8u << m.logG;
-                } else if (per_seg > 2) {
-                    reduce_batch<T, CONJ, 4>(P, ld, w, kb, m, off, xv, out);
-                    kb += 4u << m.logG;
-                } else {
-                    reduce_batch<T, CONJ, 2>(P, ld, w, kb, m, off, xv, out);
-                    kb += 2u << m.logG;
-                }
-            }
+            reduce_unit<T, CONJ>(un, data, xin, a.scratch, lane);
         }
         ubase = (ubase - hdr.n_panel) & (kConsumerWarps - 1); // == (warp - units dealt so far) mod 8
         __syncwarp();
@@ -363,21 +369,31 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(KernelSide ks, PassArg
 }
 
 // ---- APPLY --------------------------------------------------------------------------------------------
-template <typename T, bool CONJ>
-__global__ void __launch_bounds__(kThreads) apply_kernel(KernelSide ks, PassArgs<T> a) {
+// FUSED (symmetric / Hermitian storage, north_star item 4): while a stage is in shared memory for y += op(P) c, the units
+// of the leaves stored once are ALSO reduced against the second input (t' = op2(P)^T x2): the transposed second
+// application reads the side's coefficients from the same bulk copy instead of streaming them again.
+template <typename T, bool CONJ, bool FUSED, bool CONJ2>
+__global__ void __launch_bounds__(kThreads, (FUSED && sizeof(T) == 16) ? 2 : 0) apply_kernel(KernelSide ks, PassArgs<T> a) {
     constexpr int R = Rows<T>::R;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const BlockDesc bd = ks.blocks[ks.order[blockIdx.x]];
     if (a.twice_only && !(bd.flags & 1u))
         return; // accumulate-only pass and nothing to add
     const uint32_t n_my_stages = a.twice_only ? bd.n_twice_stages : bd.n_stages;
-    const SmemLayout sm = carve(smem_raw, ks, ks.stage_bytes + ks.cseg_bytes, sizeof(T) * ks.block_rows * kConsumerWarps);
+    const SmemLayout sm = carve(smem_raw, ks, ks.stage_bytes + ks.cseg_bytes, sizeof(T) * ks.block_rows * (kConsumerWarps + (FUSED ? 1 : 0)));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     T *yacc_all = reinterpret_cast<T *>(sm.vec);
+    T *xin      = yacc_all + static_cast<size_t>(ks.block_rows) * kConsumerWarps; // FUSED only
 
     init_barriers(ks, sm);
     for (int i = threadIdx.x; i < ks.block_rows * kConsumerWarps; i += kThreads)
         yacc_all[i] = zero_of(T{});
+    if (FUSED) {
+        for (int i = threadIdx.x; i < ks.block_rows; i += kThreads) {
+            const long long g = static_cast<long long>(bd.row_start) + i + a.in_shift;
+            xin[i]            = (i < bd.nrows && g >= 0 && g < a.in_len) ? a.in[g * a.stride] : zero_of(T{});
+        }
+    }
     __syncthreads();
 
     if (warp == kConsumerWarps) {
@@ -407,6 +423,11 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(KernelSide ks, PassArgs
                 const T *c = cseg + un.cslot;
                 for (uint32_t i = lane; i < h; i += 32)
                     yacc[row0 + i] = add(yacc[row0 + i], c[i]);
+                if (FUSED && unit_twice(un.geom)) { // second application, direction 0: hand the x2 slice over
+                    T *out = a.scratch2 + un.out;
+                    for (uint32_t i = lane; i < h; i += 32)
+                        out[i] = xin[row0 + i];
+                }
             }
             for (uint32_t u = ubase; u < hdr.n_panel; u += kConsumerWarps) {
                 const Unit un = units[u];
@@ -481,6 +502,8 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(KernelSide ks, PassArgs
                                 yacc[row0 + i] = add(yacc[row0 + i], acc[qq][r]);
                         }
                 }
+                if (FUSED && unit_twice(un.geom))
+                    reduce_unit<T, CONJ2>(un, data, xin, a.scratch2, lane);
             }
             ubase = (ubase - hdr.n_panel) & (kConsumerWarps - 1);
             __syncwarp();
@@ -587,10 +610,19 @@ struct Kernels;
 template <>
 struct Kernels<double> {
     static void reduce(const KernelSide &ks, const PassArgs<double> &a, int grid, size_t smem, cudaStream_t st) { reduce_kernel<double, false><<<grid, kThreads, smem, st>>>(ks, a); }
-    static void apply(const KernelSide &ks, const PassArgs<double> &a, int grid, size_t smem, cudaStream_t st) { apply_kernel<double, false><<<grid, kThreads, smem, st>>>(ks, a); }
-    static cudaError_t configure(int rs, int as) {
-        cudaError_t e = cudaFuncSetAttribute(reduce_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs);
-        return e != cudaSuccess ? e : cudaFuncSetAttribute(apply_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, as);
+    static void apply(const KernelSide &ks, const PassArgs<double> &a, int grid, size_t smem, cudaStream_t st) {
+        if (a.fused)
+            apply_kernel<double, false, true, false><<<grid, kThreads, smem, st>>>(ks, a);
+        else
+            apply_kernel<double, false, false, false><<<grid, kThreads, smem, st>>>(ks, a);
+    }
+    static cudaError_t configure(int rs, int as, int fs) {
+        cudaError_t e;
+        if ((e = cudaFuncSetAttribute(reduce_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs)) != cudaSuccess)
+            return e;
+        if ((e = cudaFuncSetAttribute(apply_kernel<double, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, as)) != cudaSuccess)
+            return e;
+        return cudaFuncSetAttribute(apply_kernel<double, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fs);
     }
 };
 template <>
@@ -602,20 +634,33 @@ struct Kernels<cplx> {
             reduce_kernel<cplx, false><<<grid, kThreads, smem, st>>>(ks, a);
     }
     static void apply(const KernelSide &ks, const PassArgs<cplx> &a, int grid, size_t smem, cudaStream_t st) {
-        if (a.conj)
-            apply_kernel<cplx, true><<<grid, kThreads, smem, st>>>(ks, a);
+        if (a.fused) { // (conj, conj2): (0,0) symmetric, (0,1) Hermitian 'N', (1,0) Hermitian 'C'
+            if (a.conj)
+                apply_kernel<cplx, true, true, false><<<grid, kThreads, smem, st>>>(ks, a);
+            else if (a.conj2)
+                apply_kernel<cplx, false, true, true><<<grid, kThreads, smem, st>>>(ks, a);
+            else
+                apply_kernel<cplx, false, true, false><<<grid, kThreads, smem, st>>>(ks, a);
+        } else if (a.conj)
+            apply_kernel<cplx, true, false, false><<<grid, kThreads, smem, st>>>(ks, a);
         else
-            apply_kernel<cplx, false><<<grid, kThreads, smem, st>>>(ks, a);
+            apply_kernel<cplx, false, false, false><<<grid, kThreads, smem, st>>>(ks, a);
     }
-    static cudaError_t configure(int rs, int as) {
+    static cudaError_t configure(int rs, int as, int fs) {
         cudaError_t e;
         if ((e = cudaFuncSetAttribute(reduce_kernel<cplx, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs)) != cudaSuccess)
             return e;
         if ((e = cudaFuncSetAttribute(reduce_kernel<cplx, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs)) != cudaSuccess)
             return e;
-        if ((e = cudaFuncSetAttribute(apply_kernel<cplx, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, as)) != cudaSuccess)
+        if ((e = cudaFuncSetAttribute(apply_kernel<cplx, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, as)) != cudaSuccess)
             return e;
-        return cudaFuncSetAttribute(apply_kernel<cplx, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, as);
+        if ((e = cudaFuncSetAttribute(apply_kernel<cplx, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, as)) != cudaSuccess)
+            return e;
+        if ((e = cudaFuncSetAttribute(apply_kernel<cplx, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fs)) != cudaSuccess)
+            return e;
+        if ((e = cudaFuncSetAttribute(apply_kernel<cplx, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fs)) != cudaSuccess)
+            return e;
+        return cudaFuncSetAttribute(apply_kernel<cplx, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fs);
     }
 };
 
@@ -630,11 +675,19 @@ size_t apply_smem_bytes(const LaunchConfig &cfg, size_t esize) {
     return slots * (cfg.stage_bytes + cfg.cseg_bytes) + esize * cfg.block_rows * kConsumerWarps + 16 * slots;
 }
 
+// The fused complex kernel is register-limited to 2 CTAs per SM (the others run 3): the shared memory that frees
+// pays for one more ring slot (measured: Helmholtz N = 1e6 'S', 7.78 -> 7.13 ms)
+static int fused_ring_stages(const LaunchConfig &cfg, size_t esize) { return cfg.ring_stages + (esize == 16 ? 1 : 0); }
+size_t fused_smem_bytes(const LaunchConfig &cfg, size_t esize) {
+    const size_t slots = static_cast<size_t>(fused_ring_stages(cfg, esize));
+    return slots * (cfg.stage_bytes + cfg.cseg_bytes) + esize * cfg.block_rows * (kConsumerWarps + 1) + 16 * slots;
+}
+
 cudaError_t configure_kernels(const LaunchConfig &cfg) {
-    cudaError_t e = Kernels<double>::configure(static_cast<int>(reduce_smem_bytes(cfg, 8)), static_cast<int>(apply_smem_bytes(cfg, 8)));
+    cudaError_t e = Kernels<double>::configure(static_cast<int>(reduce_smem_bytes(cfg, 8)), static_cast<int>(apply_smem_bytes(cfg, 8)), static_cast<int>(fused_smem_bytes(cfg, 8)));
     if (e != cudaSuccess)
         return e;
-    return Kernels<cplx>::configure(static_cast<int>(reduce_smem_bytes(cfg, 16)), static_cast<int>(apply_smem_bytes(cfg, 16)));
+    return Kernels<cplx>::configure(static_cast<int>(reduce_smem_bytes(cfg, 16)), static_cast<int>(apply_smem_bytes(cfg, 16)), static_cast<int>(fused_smem_bytes(cfg, 16)));
 }
 
 template <typename T>
@@ -651,7 +704,10 @@ cudaError_t launch_apply(const SideDevice &side, const LaunchConfig &cfg, const 
         return cudaSuccess;
     PassArgs<T> a  = args;
     a.beta_is_zero = is_zero(args.beta) ? 1 : 0;
-    Kernels<T>::apply(make_kernel_side(side, cfg, cfg.ring_stages), a, side.n_blocks, apply_smem_bytes(cfg, sizeof(T)), stream);
+    if (a.fused)
+        Kernels<T>::apply(make_kernel_side(side, cfg, fused_ring_stages(cfg, sizeof(T))), a, side.n_blocks, fused_smem_bytes(cfg, sizeof(T)), stream);
+    else
+        Kernels<T>::apply(make_kernel_side(side, cfg, cfg.ring_stages), a, side.n_blocks, apply_smem_bytes(cfg, sizeof(T)), stream);
     return cudaGetLastError();
 }
 

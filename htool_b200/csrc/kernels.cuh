@@ -55,6 +55,11 @@ struct PassArgs {
     int twice_only   = 0; // only units of leaves applied twice (second, transposed application of symmetric storage)
     int conj         = 0; // conjugate the coefficients (trans == 'C', Hermitian second application)
     int stride       = 1; // distance between consecutive vector entries (mu for row-major multi-RHS)
+    // fused APPLY + REDUCE (symmetric storage): the units of the leaves stored once are also reduced against `in`
+    // (with in_shift / in_len above) into scratch2, conjugated when conj2
+    int fused        = 0;
+    T *scratch2      = nullptr;
+    int conj2        = 0;
 };
 
 template <typename T>
@@ -77,6 +82,7 @@ cudaError_t launch_scale(T *y, long long n, T beta, cudaStream_t stream);
 
 size_t reduce_smem_bytes(const LaunchConfig &cfg, size_t esize);
 size_t apply_smem_bytes(const LaunchConfig &cfg, size_t esize);
+size_t fused_smem_bytes(const LaunchConfig &cfg, size_t esize);
 cudaError_t configure_kernels(const LaunchConfig &cfg); // sets the dynamic shared memory attributes once
 
 } // namespace htb

@@ -125,6 +125,14 @@ int htb_set_stream(htb_handle h, void *cuda_stream);
 /* Blocks until every product enqueued on the handle has finished. */
 int htb_synchronize(htb_handle h);
 
+/* Optional: page-locks a caller-owned host buffer (cudaHostRegister) so that the HTB_MEM_HOST entry points copy it
+ * with the DMA engines directly instead of staging it through the handle's pinned buffers. The reference's callers
+ * (HPDDM's Krylov vectors, wrapper_hpddm.hpp:118-124; DistributedOperator work buffers) reuse the same buffers for
+ * every product, so one registration serves a whole solve. Buffers that are already page-locked (cudaMallocHost,
+ * torch pin_memory) are detected without this call. Unregister before freeing the buffer. */
+int htb_host_register(void *ptr, size_t bytes);
+int htb_host_unregister(void *ptr);
+
 /* ---- products ------------------------------------------------------------------------------------- */
 
 /* out <- beta*out + alpha*op(H)*in, op = N | T | C. Replaces openmp_internal_add_hmatrix_vector_product

@@ -123,9 +123,10 @@ def test_deterministic_bitwise(capi):
 
 
 @pytest.mark.parametrize("opts", [dict(block_rows=32, piece_cols=4, stage_bytes=4096, cseg_bytes=512, ring_stages=2, reduce_ring_stages=9), dict(block_rows=128, piece_cols=16, stage_bytes=16448, cseg_bytes=2048),
-                                  dict(evict_first=0, ring_stages=5, reduce_ring_stages=2, stage_bytes=8192, piece_cols=8, cseg_bytes=2048)])
+                                  dict(evict_first=0, ring_stages=5, reduce_ring_stages=2, stage_bytes=8192, piece_cols=8, cseg_bytes=2048),
+                                  dict(fused_symmetric=0)])
 def test_packer_and_launch_options(capi, opts):
-    defaults = {k: capi.get_option(k) for k in ("block_rows", "piece_cols", "stage_bytes", "cseg_bytes", "ring_stages", "reduce_ring_stages", "evict_first")}
+    defaults = {k: capi.get_option(k) for k in ("block_rows", "piece_cols", "stage_bytes", "cseg_bytes", "ring_stages", "reduce_ring_stages", "evict_first", "fused_symmetric")}
     try:
         for k, v in opts.items():
             capi.set_option(k, v)
