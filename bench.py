@@ -40,7 +40,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=1_000_000, help="number of points (default: the BASELINE config)")
+    # (--points: torchrun's own parser rejects "--n" as an ambiguous abbreviation of --nnodes / --nproc-per-node)
+    ap.add_argument("--n", "--points", dest="n", type=int, default=int(os.environ.get("HTB_BENCH_POINTS", 1_000_000)), help="number of points (default: the BASELINE config)")
     ap.add_argument("--mu", type=int, default=1, help="right-hand sides (row-major), default 1")
     ap.add_argument("--dtype", default="double", choices=["double", "complex"])
     ap.add_argument("--symmetry", default="N", choices=["N", "S"])

@@ -129,7 +129,8 @@ SYMBOLS = {
     "htb_nccl_get_unique_id": (C.c_int, [C.c_void_p]),
     "htb_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "htb_comm_destroy": (C.c_int, [C.c_void_p]),
-    "htb_dist_add_product_local_to_local": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "htb_dist_add_product_local_to_local": (C.c_int, [C.c_void_p, C.c_char, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "htb_dist_add_product_global_to_global": (C.c_int, [C.c_void_p, C.c_char, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "htb_last_error": (C.c_char_p, []),
     "htb_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "htb_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
@@ -280,11 +281,18 @@ class Operator:
         buf = C.create_string_buffer(unique_id, HTB_NCCL_UNIQUE_ID_BYTES)
         check(self.lib, self.lib.htb_comm_init(self.handle, C.cast(buf, C.c_void_p), world_size, rank, _ptr(po)))
 
-    def dist_add_product_local_to_local(self, alpha, x, beta, y, mu=1, mem_kind=HTB_MEM_HOST):
+    def dist_add_product_local_to_local(self, alpha, x, beta, y, mu=1, mem_kind=HTB_MEM_HOST, trans="N"):
         a, b = self._scalar(alpha), self._scalar(beta)
         xp = C.c_void_p(x) if isinstance(x, int) else _ptr(x)
         yp = C.c_void_p(y) if isinstance(y, int) else _ptr(y)
-        check(self.lib, self.lib.htb_dist_add_product_local_to_local(self.handle, _ptr(a), xp, _ptr(b), yp, mu, mem_kind))
+        check(self.lib, self.lib.htb_dist_add_product_local_to_local(self.handle, trans.encode(), _ptr(a), xp, _ptr(b), yp, mu, mem_kind))
+        return y
+
+    def dist_add_product_global_to_global(self, trans, alpha, x, beta, y, mu=1, mem_kind=HTB_MEM_HOST):
+        a, b = self._scalar(alpha), self._scalar(beta)
+        xp = C.c_void_p(x) if isinstance(x, int) else _ptr(x)
+        yp = C.c_void_p(y) if isinstance(y, int) else _ptr(y)
+        check(self.lib, self.lib.htb_dist_add_product_global_to_global(self.handle, trans.encode(), _ptr(a), xp, _ptr(b), yp, mu, mem_kind))
         return y
 
 

@@ -1,0 +1,122 @@
+// htool_b200/distributed.hpp — the row-sharded product over the GPUs of one box, behind the reference's names.
+//
+// The reference distributes an operator as one row strip per MPI rank (DistributedOperator,
+// distributed_operator/distributed_operator.hpp:18-71) and moves vectors with MPI collectives on HOST memory
+// (linalg/utility.hpp:11-28, add_distributed_operator_vector_product_local_to_local.hpp:19-89,
+// add_distributed_operator_vector_product_global_to_global.hpp:18-85). With the GPU twins of operators.hpp
+// plugged into a DistributedOperator those functions keep working unchanged — every product then crosses
+// PCIe twice and the exchange stays on the host.
+//
+// DeviceDistributedOperator is the alternative for one process per GPU: same strip (built exactly as
+// DefaultApproximationBuilder does, distributed_operator/utility.hpp:56), same partition object, same MPI
+// communicator for the bootstrap only (one MPI_Bcast of the 128-byte NCCL id); afterwards the exchange of x /
+// of the partial results runs over NVLink with NCCL, overlapped with the local-source leaves
+// (htb_dist_add_product_local_to_local / htb_dist_add_product_global_to_global). The free functions below have
+// the reference's names and argument meaning so that call sites (HPDDMOperator::GMV,
+// wrappers/wrapper_hpddm.hpp:118-124) only change the operator type; `work` is accepted and ignored.
+#ifndef HTOOL_B200_DISTRIBUTED_HPP
+#define HTOOL_B200_DISTRIBUTED_HPP
+
+#include "device_hmatrix.hpp"
+#include <htool/distributed_operator/interfaces/virtual_partition.hpp>
+#include <mpi.h>
+#include <vector>
+
+namespace htool_b200 {
+
+template <typename CoefficientPrecision, typename CoordinatePrecision = htool::underlying_type<CoefficientPrecision>>
+class DeviceDistributedOperator {
+    DeviceHMatrix<CoefficientPrecision, CoordinatePrecision> m_data;
+    const htool::VirtualPartition<CoefficientPrecision> &m_partition;
+    MPI_Comm m_comm;
+    int m_rank = 0, m_size = 1;
+    bool m_ready = false;
+
+  public:
+    /// `strip` = this rank's block row, HMatrixTreeBuilder::build(generator, target, source, rank, rank)
+    /// (distributed_operator/utility.hpp:56); `partition` = the partition of BOTH the target and the source
+    /// cluster tree (square operator, as in DefaultApproximationBuilder's symmetric constructor, utility.hpp:61).
+    DeviceDistributedOperator(const htool::HMatrix<CoefficientPrecision, CoordinatePrecision> &strip, const htool::VirtualPartition<CoefficientPrecision> &partition, MPI_Comm comm, int device = -1)
+        : m_data(strip, device), m_partition(partition), m_comm(comm) {
+        MPI_Comm_rank(comm, &m_rank);
+        MPI_Comm_size(comm, &m_size);
+        if (!m_data.is_valid()) {
+            return;
+        }
+        unsigned char id[HTB_NCCL_UNIQUE_ID_BYTES] = {0};
+        if (m_rank == 0 && !check(htb_nccl_get_unique_id(id), "htb_nccl_get_unique_id")) {
+            return;
+        }
+        MPI_Bcast(id, HTB_NCCL_UNIQUE_ID_BYTES, MPI_UNSIGNED_CHAR, 0, comm);
+        std::vector<int32_t> offsets(m_size + 1, 0);
+        for (int r = 0; r < m_size; r++) {
+            offsets[r]     = partition.get_offset_of_partition(r);
+            offsets[r + 1] = offsets[r] + partition.get_size_of_partition(r);
+        }
+        m_ready = check(htb_comm_init(m_data.get(), id, m_size, m_rank, offsets.data()), "htb_comm_init");
+    }
+    ~DeviceDistributedOperator() {
+        if (m_ready) {
+            htb_comm_destroy(m_data.get());
+        }
+    }
+    DeviceDistributedOperator(const DeviceDistributedOperator &)            = delete;
+    DeviceDistributedOperator &operator=(const DeviceDistributedOperator &) = delete;
+
+    bool is_valid() const { return m_ready; }
+    MPI_Comm get_comm() const { return m_comm; }
+    const htool::VirtualPartition<CoefficientPrecision> &get_target_partition() const { return m_partition; }
+    const htool::VirtualPartition<CoefficientPrecision> &get_source_partition() const { return m_partition; }
+    const DeviceHMatrix<CoefficientPrecision, CoordinatePrecision> &get_device_hmatrix() const { return m_data; }
+
+    void local_to_local(char trans, CoefficientPrecision alpha, const CoefficientPrecision *in, CoefficientPrecision beta, CoefficientPrecision *out, int mu) const {
+        if (m_ready) {
+            check(htb_dist_add_product_local_to_local(m_data.get(), trans, &alpha, in, &beta, out, mu, HTB_MEM_HOST), "htb_dist_add_product_local_to_local");
+        }
+    }
+    void global_to_global(char trans, CoefficientPrecision alpha, const CoefficientPrecision *in, CoefficientPrecision beta, CoefficientPrecision *out, int mu) const {
+        if (m_ready) {
+            check(htb_dist_add_product_global_to_global(m_data.get(), trans, &alpha, in, &beta, out, mu, HTB_MEM_HOST), "htb_dist_add_product_global_to_global");
+        }
+    }
+};
+
+// ---- the reference's entry points, overloaded on the device operator (partition numbering, host pointers) --------
+
+/// add_distributed_operator_vector_product_local_to_local.hpp:19 — what HPDDMOperator::GMV calls per Krylov iteration.
+template <typename T, typename U>
+void internal_add_distributed_operator_vector_product_local_to_local(char trans, T alpha, const DeviceDistributedOperator<T, U> &A, const T *const in, T beta, T *const out, T * /*work*/ = nullptr) {
+    A.local_to_local(trans, alpha, in, beta, out, 1);
+}
+/// add_distributed_operator_matrix_product_row_major_local_to_local.hpp:25 with raw row-major pointers (mu contiguous).
+template <typename T, typename U>
+void internal_add_distributed_operator_matrix_product_row_major_local_to_local(char trans, T alpha, const DeviceDistributedOperator<T, U> &A, const T *const in, T beta, T *const out, int mu, T * /*work*/ = nullptr) {
+    A.local_to_local(trans, alpha, in, beta, out, mu);
+}
+/// add_distributed_operator_vector_product_global_to_global.hpp:18 (partition numbering in and out).
+template <typename T, typename U>
+void internal_add_distributed_operator_vector_product_global_to_global(char trans, T alpha, const DeviceDistributedOperator<T, U> &A, const T *const in, T beta, T *const out, T * /*work*/ = nullptr) {
+    A.global_to_global(trans, alpha, in, beta, out, 1);
+}
+/// add_distributed_operator_matrix_product_row_major_global_to_global.hpp:18 with raw row-major pointers.
+template <typename T, typename U>
+void internal_add_distributed_operator_matrix_product_row_major_global_to_global(char trans, T alpha, const DeviceDistributedOperator<T, U> &A, const T *const in, T beta, T *const out, int mu, T * /*work*/ = nullptr) {
+    A.global_to_global(trans, alpha, in, beta, out, mu);
+}
+/// add_distributed_operator_vector_product_global_to_global.hpp:97-118: user numbering around the internal product,
+/// with the partition's own renumbering (PartitionFromCluster::global_to_partition_numbering, partition_from_cluster.hpp:27-32).
+template <typename T, typename U>
+void add_distributed_operator_vector_product_global_to_global(char trans, T alpha, const DeviceDistributedOperator<T, U> &A, const T *const in, T beta, T *const out, T * /*work*/ = nullptr) {
+    const auto &partition = A.get_source_partition();
+    const int n           = partition.get_global_size();
+    std::vector<T> in_p(n), out_p(n);
+    partition.global_to_partition_numbering(in, in_p.data());
+    if (beta != T(0)) {
+        partition.global_to_partition_numbering(out, out_p.data());
+    }
+    A.global_to_global(trans, alpha, in_p.data(), beta, out_p.data(), 1);
+    partition.partition_to_global_numbering(out_p.data(), out);
+}
+
+} // namespace htool_b200
+#endif

@@ -28,13 +28,15 @@ int cuda_fail(cudaError_t e, const char *what) {
 namespace {
 std::mutex g_option_mutex;
 std::map<std::string, int64_t> g_options = {
-    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 2048}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 5}, {"m_reduce_ring_stages", 5}, {"mrhs_min", 8}, {"fused_symmetric", 1}};
+    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 2048}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 5}, {"m_reduce_ring_stages", 5}, {"mrhs_min", 8}, {"fused_symmetric", 1}, {"dist_p2p", 1}};
 
 int64_t option(const char *key) {
     std::lock_guard<std::mutex> lock(g_option_mutex);
     return g_options.at(key);
 }
 } // namespace
+
+int64_t option_value(const char *key) { return option(key); }
 
 #define HTB_CUDA(call)                       \
     do {                                     \
@@ -213,6 +215,15 @@ static int run_product(htb_operator *h, char trans, T alpha, const T *in, T beta
         if (h->side[1].stream && !split) {
             if ((rc = count(launch_reduce<T>(h->side[1], h->launch_cfg, r1, st), "reduce(V)")) != HTB_OK)
                 return rc;
+        } else if (h->side[1].stream && split->flags) {
+            // distributed, x gathered through peer memory: one launch, own-partition blocks first, the others wait in
+            // the kernel for the arrival flag of the rank that owns their slice
+            SideDevice part = h->side[1];
+            part.order = split->order_all, part.n_blocks = split->n_all;
+            PassArgs<T> rw = r1;
+            rw.wait_flags = split->flags, rw.wait_owner = split->owner, rw.wait_epoch = split->epoch;
+            if (part.n_blocks && (rc = count(launch_reduce<T>(part, h->launch_cfg, rw, st), "reduce(V, peer gather)")) != HTB_OK)
+                return rc;
         } else if (h->side[1].stream) {
             // distributed: source blocks inside the rank's own partition first, they overlap the allgather of x
             SideDevice part = h->side[1];
@@ -231,7 +242,7 @@ static int run_product(htb_operator *h, char trans, T alpha, const T *in, T beta
             if (h->side[1].n_combine && (rc = count(launch_combine<T>(h->side[1], T2, 1, st), "combine(U, twice)")) != HTB_OK)
                 return rc;
         }
-        if (h->side[1].stream && split) {
+        if (h->side[1].stream && split && !split->flags) {
             cudaError_t we = cudaStreamWaitEvent(st, split->gather_done, 0);
             if (we != cudaSuccess)
                 return cuda_fail(we, "cudaStreamWaitEvent(allgather)");
@@ -386,8 +397,14 @@ int product_device(htb_operator *h, char trans, const void *alpha, const void *i
     int rc = check_trans(h, trans);
     if (rc != HTB_OK)
         return rc;
-    if (h->m_path_ok && !split && mu >= static_cast<int>(option("mrhs_min")))
+    if (h->m_path_ok && mu >= static_cast<int>(option("mrhs_min"))) {
+        // tensor-core path: one pass over all columns, so a distributed product first waits for the gather of x
+        if (split && split->flags)
+            HTB_CUDA(launch_wait_flags(split->flags, split->world, split->epoch, h->stream));
+        else if (split && split->gather_done)
+            HTB_CUDA(cudaStreamWaitEvent(h->stream, split->gather_done, 0));
         return run_product_m(h, trans, *static_cast<const double *>(alpha), static_cast<const double *>(in), *static_cast<const double *>(beta), static_cast<double *>(out), mu);
+    }
     for (int c = 0; c < mu; c++) {
         if (h->dtype == HTB_DOUBLE)
             rc = run_product<double>(h, trans, *static_cast<const double *>(alpha), static_cast<const double *>(in) + c, *static_cast<const double *>(beta), static_cast<double *>(out) + c, mu, c == 0 ? split : nullptr);

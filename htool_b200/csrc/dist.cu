@@ -7,10 +7,20 @@
 // starts when it has returned. Here the gather runs on its own stream while the source blocks that lie
 // inside the rank's own partition are already being reduced (t = V x needs nothing remote for them).
 // Partition sizes differ between ranks (RegularSplitting gives the remainder to the last child,
-// clustering/implementations/partitioning.hpp:241-246), so the gather is a group of in-place broadcasts,
-// one per rank, rather than an equal-count ncclAllGather. Rows are owned: no reduction is needed.
+// clustering/implementations/partitioning.hpp:241-246). Rows are owned: no reduction is needed for 'N'.
+//
+// The gather of x, two implementations:
+//   * peer memory (default on one box): every rank maps the x buffers and arrival flags of its peers (CUDA IPC over
+//     NVLink / NVSwitch). A PUSH kernel stores the rank's slice of x straight into every peer's buffer and then
+//     releases an epoch flag on each peer; the REDUCE kernel of the product is ONE launch whose own-partition
+//     blocks start at once and whose other blocks wait, block by block, for the flag of the rank that owns their
+//     slice — transfer and compute overlap at block granularity and no collective call sits on the critical path.
+//     Buffers are double-buffered by epoch parity and the push waits for its peers' previous epoch (WAR guard).
+//   * NCCL (fallback, and the T / C and global-to-global paths): a group of in-place ncclBroadcasts, one per rank,
+//     on a second stream; the remote part of the REDUCE waits for an event.
 #include "handle.hpp"
 
+#include <algorithm>
 #include <cstring>
 #include <dlfcn.h>
 #include <mutex>
@@ -28,6 +38,9 @@ struct NcclApi {
     ncclResult_t (*GroupStart)()                                                                                  = nullptr;
     ncclResult_t (*GroupEnd)()                                                                                    = nullptr;
     ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t)        = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t)                     = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t)                           = nullptr;
     const char *(*GetErrorString)(ncclResult_t)                                                                   = nullptr;
     bool ok = false;
     std::string error;
@@ -56,6 +69,9 @@ static NcclApi &nccl() {
         api.GroupStart     = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
         api.GroupEnd       = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
         api.Broadcast      = reinterpret_cast<decltype(api.Broadcast)>(sym("ncclBroadcast"));
+        api.AllReduce      = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+        api.Send           = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+        api.Recv           = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
         api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
         api.ok             = api.error.empty();
     });
@@ -68,14 +84,41 @@ struct DistState {
     std::vector<int32_t> offsets;
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t in_ready = nullptr, gather_done = nullptr;
-    void *d_xglobal = nullptr;
+    void *d_xglobal = nullptr; // gathered x ('N'), full-length partial result (T / C)
     size_t xglobal_cap = 0;
+    void *d_rbuf = nullptr; // T / C local-to-local: the world slices received for the own partition
+    size_t rbuf_cap = 0;
+    void *d_old = nullptr; // T / C global-to-global with beta != 0: out before the product
+    size_t old_cap = 0;
     uint32_t *d_order_local = nullptr, *d_order_remote = nullptr;
     int n_local = 0, n_remote = 0;
+    // ---- peer-memory gather ------------------------------------------------------------------------------------------
+    bool p2p = false;                  // decided collectively at htb_comm_init
+    std::string p2p_why;               // why not, when disabled
+    void *xg[2] = {nullptr, nullptr};  // own gathered-x buffers (epoch parity)
+    size_t xg_cap = 0;
+    unsigned long long *flags = nullptr; // own arrival flags [world]
+    unsigned int *arrive      = nullptr; // push kernel: CTAs done
+    std::vector<void *> peer_xg[2];      // peers' buffers mapped here (own entry = own pointer)
+    std::vector<unsigned long long *> peer_flags;
+    void **d_peer_xg[2]                 = {nullptr, nullptr}; // the same pointer tables on the device
+    unsigned long long **d_peer_flags   = nullptr;
+    unsigned long long epoch            = 0;
+    uint32_t *d_order_all = nullptr, *d_owner = nullptr;
+    void *d_hbuf = nullptr; // handle exchange
 };
 
 static int nccl_fail(ncclResult_t r, const char *what) {
     return fail(HTB_ERR_NCCL, std::string(what) + ": " + nccl().GetErrorString(r));
+}
+
+static void close_peer_buffers(DistState *d) {
+    for (int k = 0; k < 2; k++) {
+        for (size_t r = 0; r < d->peer_xg[k].size(); r++)
+            if (static_cast<int>(r) != d->rank && d->peer_xg[k][r])
+                cudaIpcCloseMemHandle(d->peer_xg[k][r]);
+        d->peer_xg[k].clear();
+    }
 }
 
 void dist_destroy(htb_operator *h) {
@@ -84,9 +127,19 @@ void dist_destroy(htb_operator *h) {
         return;
     if (d->comm_stream)
         cudaStreamSynchronize(d->comm_stream);
+    cudaStreamSynchronize(h->stream);
+    close_peer_buffers(d);
+    for (size_t r = 0; r < d->peer_flags.size(); r++)
+        if (static_cast<int>(r) != d->rank && d->peer_flags[r])
+            cudaIpcCloseMemHandle(d->peer_flags[r]);
+    d->peer_flags.clear();
+    for (void *p : {d->xg[0], d->xg[1], static_cast<void *>(d->flags), static_cast<void *>(d->arrive), static_cast<void *>(d->d_peer_xg[0]), static_cast<void *>(d->d_peer_xg[1]),
+                    static_cast<void *>(d->d_peer_flags), static_cast<void *>(d->d_order_all), static_cast<void *>(d->d_owner), d->d_hbuf})
+        if (p)
+            cudaFree(p);
     if (d->comm)
         nccl().CommDestroy(d->comm);
-    for (void *p : {static_cast<void *>(d->d_xglobal), static_cast<void *>(d->d_order_local), static_cast<void *>(d->d_order_remote)})
+    for (void *p : {static_cast<void *>(d->d_xglobal), static_cast<void *>(d->d_rbuf), static_cast<void *>(d->d_old), static_cast<void *>(d->d_order_local), static_cast<void *>(d->d_order_remote)})
         if (p)
             cudaFree(p);
     if (d->in_ready)
@@ -97,6 +150,95 @@ void dist_destroy(htb_operator *h) {
         cudaStreamDestroy(d->comm_stream);
     delete d;
     h->dist = nullptr;
+}
+
+// out[i] = beta out[i] + sum_r rbuf[r][i], r = 0 .. world-1 in rank order: the scal + world axpys that follow the
+// MPI_Alltoallv of the reference (add_distributed_operator_vector_product_local_to_local.hpp:79-86), same order.
+// Arrays are addressed as doubles (a complex sum is two real sums); only the beta product is complex.
+template <bool CPLX>
+__global__ void sum_slices_kernel(double *out, const double *rbuf, long long n_doubles, int world, double beta_re, double beta_im, int beta_is_zero) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n_doubles)
+        return;
+    double v = 0.;
+    if (!beta_is_zero) {
+        if (CPLX) {
+            const double re = out[i & ~1ll], im = out[i | 1ll];
+            v = (i & 1) ? beta_re * im + beta_im * re : beta_re * re - beta_im * im;
+        } else
+            v = beta_re * out[i];
+    }
+    for (int r = 0; r < world; r++)
+        v += rbuf[static_cast<size_t>(r) * n_doubles + i];
+    out[i] = v;
+}
+
+// out[i] = sum[i] + beta old[i] (global-to-global T / C: the axpy after MPI_Allreduce,
+// add_distributed_operator_vector_product_global_to_global.hpp:77-83)
+template <bool CPLX>
+__global__ void add_scaled_kernel(double *out, const double *sum, const double *old, long long n_doubles, double beta_re, double beta_im) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n_doubles)
+        return;
+    double v;
+    if (CPLX) {
+        const double re = old[i & ~1ll], im = old[i | 1ll];
+        v = (i & 1) ? beta_re * im + beta_im * re : beta_re * re - beta_im * im;
+    } else
+        v = beta_re * old[i];
+    out[i] = sum[i] + v;
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// PUSH: this rank's slice of x (n8 8-byte words) is stored into the gathered-x buffer of EVERY rank of the box (own
+// included) at the slice's global offset, over NVLink peer mappings; when all CTAs are done the last one releases
+// flags[rank] = epoch on every peer. Replaces the MPI_Allgatherv of linalg/utility.hpp:27 on the 'N' path.
+// WAR guard: buffer (epoch & 1) was last read by the peers' products of epoch - 2; a peer that has published epoch - 1
+// has finished that product (its push is stream-ordered after it), so wait for flags >= epoch - 1 first.
+__global__ void push_x_kernel(const unsigned long long *src, size_t n8, void *const *peer_xg, size_t my_off8, unsigned long long *const *peer_flags, int world, int rank,
+                              unsigned long long epoch, const unsigned long long *own_flags, unsigned int *arrive) {
+    if (epoch >= 2 && static_cast<int>(threadIdx.x) < world && static_cast<int>(threadIdx.x) != rank)
+        while (ld_acquire_sys_u64(own_flags + threadIdx.x) < epoch - 1)
+            __nanosleep(64);
+    __syncthreads();
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        const unsigned long long v = src[i];
+        for (int p = 0; p < world; p++)
+            static_cast<unsigned long long *>(peer_xg[p])[my_off8 + i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(arrive, 1u);
+        if (prev == gridDim.x - 1) {
+            *arrive = 0; // next launch is stream-ordered after this one
+            __threadfence_system();
+            for (int p = 0; p < world; p++)
+                st_release_sys_u64(peer_flags[p] + rank, epoch);
+        }
+    }
+}
+
+static cudaError_t grow_device(void **p, size_t *cap, size_t need) {
+    if (need <= *cap)
+        return cudaSuccess;
+    if (*p)
+        cudaFree(*p);
+    *p   = nullptr;
+    *cap = 0;
+    cudaError_t e = cudaMalloc(p, need);
+    if (e == cudaSuccess)
+        *cap = need;
+    return e;
 }
 
 } // namespace htb
@@ -115,6 +257,158 @@ using namespace htb;
         if (r__ != ncclSuccess)           \
             return nccl_fail(r__, #call); \
     } while (0)
+
+// ---- peer-memory plumbing (collective calls: every rank of the communicator makes them in the same order) -------------
+// min over the ranks of a local 0/1 verdict: the ranks must AGREE on the gather implementation
+static int agree(DistState *d, bool local_ok, bool *all_ok) {
+    double v = local_ok ? 1. : 0.;
+    double *dv = reinterpret_cast<double *>(static_cast<char *>(d->d_hbuf) + size_t(d->world) * sizeof(cudaIpcMemHandle_t));
+    HTB_CUDA(cudaMemcpyAsync(dv, &v, sizeof(double), cudaMemcpyHostToDevice, d->comm_stream));
+    if (d->world > 1)
+        HTB_NCCL(nccl().AllReduce(dv, dv, 1, ncclDouble, ncclMin, d->comm, d->comm_stream));
+    HTB_CUDA(cudaMemcpyAsync(&v, dv, sizeof(double), cudaMemcpyDeviceToHost, d->comm_stream));
+    HTB_CUDA(cudaStreamSynchronize(d->comm_stream));
+    *all_ok = v > 0.5;
+    return HTB_OK;
+}
+
+// Every rank exports `own` (a cudaMalloc allocation) and maps the allocations of the others: mapped[r] on return
+// (mapped[rank] = own). *ok is the local verdict; mappings that were opened stay in `mapped` for the caller to close.
+static int exchange_and_map(DistState *d, void *own, std::vector<void *> &mapped, bool *ok) {
+    const size_t hs = sizeof(cudaIpcMemHandle_t);
+    std::vector<cudaIpcMemHandle_t> handles(d->world);
+    *ok = true;
+    std::memset(handles.data(), 0, hs * d->world);
+    if (cudaIpcGetMemHandle(&handles[d->rank], own) != cudaSuccess) {
+        cudaGetLastError();
+        *ok = false;
+    }
+    char *hb = static_cast<char *>(d->d_hbuf);
+    HTB_CUDA(cudaMemcpyAsync(hb + hs * d->rank, &handles[d->rank], hs, cudaMemcpyHostToDevice, d->comm_stream));
+    if (d->world > 1) {
+        HTB_NCCL(nccl().GroupStart());
+        for (int r = 0; r < d->world; r++)
+            HTB_NCCL(nccl().Broadcast(hb + hs * r, hb + hs * r, hs, ncclChar, r, d->comm, d->comm_stream));
+        HTB_NCCL(nccl().GroupEnd());
+    }
+    HTB_CUDA(cudaMemcpyAsync(handles.data(), hb, hs * d->world, cudaMemcpyDeviceToHost, d->comm_stream));
+    HTB_CUDA(cudaStreamSynchronize(d->comm_stream));
+    mapped.assign(d->world, nullptr);
+    mapped[d->rank] = own;
+    for (int r = 0; r < d->world && *ok; r++) {
+        if (r == d->rank)
+            continue;
+        if (cudaIpcOpenMemHandle(&mapped[r], handles[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            d->p2p_why = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(cudaGetLastError());
+            mapped[r]  = nullptr;
+            *ok        = false;
+        }
+    }
+    return HTB_OK;
+}
+
+static int upload_table(void **dev_table, const void *host_table, size_t bytes) {
+    if (!*dev_table)
+        HTB_CUDA(cudaMalloc(dev_table, bytes));
+    HTB_CUDA(cudaMemcpy(*dev_table, host_table, bytes, cudaMemcpyHostToDevice));
+    return HTB_OK;
+}
+
+// flags + tables, once per communicator (htb_comm_init)
+static int p2p_init(htb_operator *h, DistState *d) {
+    int rc;
+    bool ok = option_value("dist_p2p") != 0 && d->world <= 32, all = false;
+    if (!ok)
+        d->p2p_why = d->world > 32 ? "more than 32 ranks" : "disabled (option dist_p2p = 0)";
+    HTB_CUDA(cudaMalloc(&d->d_hbuf, size_t(d->world) * sizeof(cudaIpcMemHandle_t) + 16));
+    HTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d->flags), sizeof(unsigned long long) * d->world));
+    HTB_CUDA(cudaMemset(d->flags, 0, sizeof(unsigned long long) * d->world));
+    HTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d->arrive), sizeof(unsigned int)));
+    HTB_CUDA(cudaMemset(d->arrive, 0, sizeof(unsigned int)));
+    if ((rc = agree(d, ok, &all)) != HTB_OK)
+        return rc;
+    if (!all)
+        return HTB_OK; // NCCL gather
+    std::vector<void *> mapped;
+    if ((rc = exchange_and_map(d, d->flags, mapped, &ok)) != HTB_OK)
+        return rc;
+    d->peer_flags.resize(d->world);
+    for (int r = 0; r < d->world; r++)
+        d->peer_flags[r] = static_cast<unsigned long long *>(mapped[r]);
+    if (ok && (rc = upload_table(reinterpret_cast<void **>(&d->d_peer_flags), d->peer_flags.data(), sizeof(void *) * d->world)) != HTB_OK)
+        return rc;
+    if ((rc = agree(d, ok, &all)) != HTB_OK)
+        return rc;
+    d->p2p = all;
+    // launch order of the single REDUCE: own-partition blocks first; owners of every block's index range
+    const std::vector<BlockDesc> &blocks = h->host_blocks[1];
+    std::vector<uint32_t> owner(blocks.size(), 0xFFFFFFFFu), order_all;
+    const int lo = d->offsets[d->rank], hi = d->offsets[d->rank + 1];
+    auto owner_of = [&](int idx) {
+        int q = static_cast<int>(std::upper_bound(d->offsets.begin(), d->offsets.end(), idx) - d->offsets.begin()) - 1;
+        return std::min(std::max(q, 0), d->world - 1);
+    };
+    for (size_t b = 0; b < blocks.size(); b++) {
+        const BlockDesc &bd = blocks[b];
+        if (bd.nrows > 0 && !(bd.row_start >= lo && bd.row_start + bd.nrows <= hi))
+            owner[b] = static_cast<uint32_t>(owner_of(bd.row_start)) | (static_cast<uint32_t>(owner_of(bd.row_start + bd.nrows - 1)) << 16);
+    }
+    for (uint32_t b : h->host_order[1])
+        if (owner[b] == 0xFFFFFFFFu)
+            order_all.push_back(b);
+    for (uint32_t b : h->host_order[1])
+        if (owner[b] != 0xFFFFFFFFu)
+            order_all.push_back(b);
+    HTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d->d_owner), std::max<size_t>(1, owner.size()) * 4));
+    HTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d->d_order_all), std::max<size_t>(1, order_all.size()) * 4));
+    HTB_CUDA(cudaMemcpy(d->d_owner, owner.data(), owner.size() * 4, cudaMemcpyHostToDevice));
+    HTB_CUDA(cudaMemcpy(d->d_order_all, order_all.data(), order_all.size() * 4, cudaMemcpyHostToDevice));
+    return HTB_OK;
+}
+
+// (re)allocation of the double-buffered gathered x when a product needs more room: collective, rare (first product,
+// or a larger mu). Falls back to the NCCL gather for good if any rank cannot map its peers.
+static int p2p_ensure_buffers(htb_operator *h, DistState *d, size_t bytes) {
+    if (!d->p2p || bytes <= d->xg_cap)
+        return HTB_OK;
+    int rc;
+    bool ok = true, all = false;
+    HTB_CUDA(cudaStreamSynchronize(h->stream));
+    close_peer_buffers(d);
+    if ((rc = agree(d, true, &all)) != HTB_OK) // barrier: nobody still maps the buffers about to be freed
+        return rc;
+    for (int k = 0; k < 2; k++) {
+        if (d->xg[k])
+            cudaFree(d->xg[k]);
+        d->xg[k] = nullptr;
+    }
+    d->xg_cap = 0;
+    for (int k = 0; k < 2 && ok; k++) {
+        if (cudaMalloc(&d->xg[k], bytes) != cudaSuccess) {
+            cudaGetLastError();
+            d->p2p_why = "cudaMalloc of the gathered-x buffers";
+            ok         = false;
+        }
+    }
+    for (int k = 0; k < 2; k++) {
+        bool okk = ok;
+        void *own = ok ? d->xg[k] : static_cast<void *>(d->flags); // keep the collective sequence identical on every rank
+        if ((rc = exchange_and_map(d, own, d->peer_xg[k], &okk)) != HTB_OK)
+            return rc;
+        ok = ok && okk;
+        if (ok && (rc = upload_table(reinterpret_cast<void **>(&d->d_peer_xg[k]), d->peer_xg[k].data(), sizeof(void *) * d->world)) != HTB_OK)
+            return rc;
+    }
+    if ((rc = agree(d, ok, &all)) != HTB_OK)
+        return rc;
+    if (all)
+        d->xg_cap = bytes;
+    else {
+        close_peer_buffers(d);
+        d->p2p = false;
+    }
+    return HTB_OK;
+}
 
 extern "C" {
 
@@ -173,8 +467,9 @@ int htb_comm_init(htb_handle h, const void *id128, int world_size, int rank, con
     HTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d->d_order_remote), std::max<size_t>(1, remote.size()) * 4));
     HTB_CUDA(cudaMemcpy(d->d_order_local, local.data(), local.size() * 4, cudaMemcpyHostToDevice));
     HTB_CUDA(cudaMemcpy(d->d_order_remote, remote.data(), remote.size() * 4, cudaMemcpyHostToDevice));
+    const int prc = p2p_init(h, d);
     cudaSetDevice(prev);
-    return HTB_OK;
+    return prc;
 }
 
 int htb_comm_destroy(htb_handle h) {
@@ -188,74 +483,230 @@ int htb_comm_destroy(htb_handle h) {
     return HTB_OK;
 }
 
-int htb_dist_add_product_local_to_local(htb_handle h, const void *alpha, const void *in_local, const void *beta, void *out_local, int mu, int mem_kind) {
+// in-place gather of the per-rank segments of a global vector: a group of broadcasts, one per rank (partition sizes differ)
+static int gather_segments(DistState *d, char *base, size_t es, cudaStream_t st) {
+    if (d->world <= 1)
+        return HTB_OK;
+    HTB_NCCL(nccl().GroupStart());
+    for (int r = 0; r < d->world; r++) {
+        const size_t count = size_t(d->offsets[r + 1] - d->offsets[r]) * es;
+        if (count == 0)
+            continue;
+        char *seg = base + size_t(d->offsets[r]) * es;
+        HTB_NCCL(nccl().Broadcast(seg, seg, count, ncclChar, r, d->comm, st));
+    }
+    HTB_NCCL(nccl().GroupEnd());
+    return HTB_OK;
+}
+
+namespace {
+struct DeviceGuard {
+    int prev = 0;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        cudaSetDevice(dev);
+    }
+    ~DeviceGuard() { cudaSetDevice(prev); }
+};
+bool scalar_is_zero(const htb_operator *h, const void *s) {
+    const double *b = static_cast<const double *>(s);
+    return b[0] == 0. && (h->dtype == HTB_DOUBLE || b[1] == 0.);
+}
+} // namespace
+
+int htb_dist_add_product_local_to_local(htb_handle h, char trans, const void *alpha, const void *in_local, const void *beta, void *out_local, int mu, int mem_kind) {
     if (!h || !alpha || !beta || !in_local || !out_local || mu < 1)
         return fail(HTB_ERR_INVALID, "invalid argument");
     DistState *d = h->dist;
     if (!d)
         return fail(HTB_ERR_INVALID, "htb_comm_init has not been called");
-    int prev = 0;
-    cudaGetDevice(&prev);
-    HTB_CUDA(cudaSetDevice(h->device));
-    struct Restore {
-        int dev;
-        ~Restore() { cudaSetDevice(dev); }
-    } restore{prev};
+    DeviceGuard guard(h->device);
 
     const size_t es = h->esize * mu;
     const size_t n_local = h->nb_rows, n_global = h->nb_cols;
-    if (n_global * es > d->xglobal_cap) {
-        if (d->d_xglobal)
-            cudaFree(d->d_xglobal);
-        d->d_xglobal   = nullptr;
-        d->xglobal_cap = 0;
-        HTB_CUDA(cudaMalloc(&d->d_xglobal, n_global * es));
-        d->xglobal_cap = n_global * es;
-    }
     cudaStream_t st = h->stream;
-    char *xg        = static_cast<char *>(d->d_xglobal);
+    char *xg        = nullptr;
     void *dout      = out_local;
-    const double *b = static_cast<const double *>(beta);
-    const bool beta_zero = b[0] == 0. && (h->dtype == HTB_DOUBLE || b[1] == 0.);
-    if (mem_kind == HTB_MEM_HOST) {
-        int rc = ensure_staging(h, n_local * es, n_local * es);
-        if (rc != HTB_OK)
+    const bool beta_zero = scalar_is_zero(h, beta);
+    int rc;
+    if (trans == 'N') {
+        if ((rc = p2p_ensure_buffers(h, d, n_global * es)) != HTB_OK)
             return rc;
-        if ((rc = staged_h2d(h, xg + size_t(d->offsets[d->rank]) * es, h->h_in, in_local, n_local * es, st)) != HTB_OK)
+        if (mem_kind == HTB_MEM_HOST) {
+            if ((rc = ensure_staging(h, n_local * es, n_local * es)) != HTB_OK)
+                return rc;
+            if (!beta_zero && (rc = staged_h2d(h, h->d_out, h->h_out, out_local, n_local * es, st)) != HTB_OK)
+                return rc;
+            dout = h->d_out;
+        }
+        DistSplit split;
+        split.world = d->world;
+        if (d->p2p) {
+            // peer-memory gather: push the own slice into every rank's buffer of this epoch's parity, then ONE reduce launch
+            const unsigned long long epoch = ++d->epoch;
+            const int k = static_cast<int>(epoch & 1ull);
+            xg          = static_cast<char *>(d->xg[k]);
+            const void *src = in_local;
+            if (mem_kind == HTB_MEM_HOST) {
+                if ((rc = staged_h2d(h, xg + size_t(d->offsets[d->rank]) * es, h->h_in, in_local, n_local * es, st)) != HTB_OK)
+                    return rc;
+                src = xg + size_t(d->offsets[d->rank]) * es;
+            }
+            const size_t n8 = n_local * es / 8;
+            const int grid  = static_cast<int>(std::min<size_t>(std::max<size_t>(1, (n8 + 1023) / 1024), 2 * size_t(h->sm_count)));
+            push_x_kernel<<<grid, 256, 0, st>>>(static_cast<const unsigned long long *>(src), n8, d->d_peer_xg[k], size_t(d->offsets[d->rank]) * es / 8, d->d_peer_flags, d->world, d->rank, epoch,
+                                                d->flags, d->arrive);
+            HTB_CUDA(cudaGetLastError());
+            h->launches++;
+            split.order_all = d->d_order_all;
+            split.n_all     = d->n_local + d->n_remote;
+            split.owner     = d->d_owner;
+            split.flags     = d->flags;
+            split.epoch     = epoch;
+        } else {
+            HTB_CUDA(grow_device(&d->d_xglobal, &d->xglobal_cap, n_global * es));
+            xg = static_cast<char *>(d->d_xglobal);
+            if (mem_kind == HTB_MEM_HOST) {
+                if ((rc = staged_h2d(h, xg + size_t(d->offsets[d->rank]) * es, h->h_in, in_local, n_local * es, st)) != HTB_OK)
+                    return rc;
+            } else {
+                HTB_CUDA(cudaMemcpyAsync(xg + size_t(d->offsets[d->rank]) * es, in_local, n_local * es, cudaMemcpyDeviceToDevice, st));
+            }
+            // allgather of x on the communication stream
+            HTB_CUDA(cudaEventRecord(d->in_ready, st));
+            HTB_CUDA(cudaStreamWaitEvent(d->comm_stream, d->in_ready, 0));
+            if ((rc = gather_segments(d, xg, es, d->comm_stream)) != HTB_OK)
+                return rc;
+            HTB_CUDA(cudaEventRecord(d->gather_done, d->comm_stream));
+            split.order_local  = d->d_order_local;
+            split.order_remote = d->d_order_remote;
+            split.n_local      = d->n_local;
+            split.n_remote     = d->n_remote;
+            split.gather_done  = d->gather_done;
+        }
+        if ((rc = product_device(h, 'N', alpha, xg, beta, dout, mu, &split)) != HTB_OK)
             return rc;
-        if (!beta_zero && (rc = staged_h2d(h, h->d_out, h->h_out, out_local, n_local * es, st)) != HTB_OK)
-            return rc;
-        dout = h->d_out;
     } else {
-        HTB_CUDA(cudaMemcpyAsync(xg + size_t(d->offsets[d->rank]) * es, in_local, n_local * es, cudaMemcpyDeviceToDevice, st));
-    }
-    // allgather of x on the communication stream
-    HTB_CUDA(cudaEventRecord(d->in_ready, st));
-    HTB_CUDA(cudaStreamWaitEvent(d->comm_stream, d->in_ready, 0));
-    if (d->world > 1) {
+        // T / C (add_distributed_operator_vector_product_local_to_local.hpp:47-87): z = alpha op(H_strip)^T x_local has the
+        // GLOBAL length; slice r of z goes to rank r (MPI_Alltoallv there, grouped ncclSend / ncclRecv here), and the owner
+        // adds the world slices it received in rank order to beta out_local.
+        const void *din = in_local;
+        if (mem_kind == HTB_MEM_HOST) {
+            if ((rc = ensure_staging(h, n_local * es, n_local * es)) != HTB_OK)
+                return rc;
+            if ((rc = staged_h2d(h, h->d_in, h->h_in, in_local, n_local * es, st)) != HTB_OK)
+                return rc;
+            if (!beta_zero && (rc = staged_h2d(h, h->d_out, h->h_out, out_local, n_local * es, st)) != HTB_OK)
+                return rc;
+            din  = h->d_in;
+            dout = h->d_out;
+        }
+        HTB_CUDA(grow_device(&d->d_rbuf, &d->rbuf_cap, size_t(d->world) * n_local * es));
+        HTB_CUDA(grow_device(&d->d_xglobal, &d->xglobal_cap, n_global * es));
+        xg = static_cast<char *>(d->d_xglobal);
+        alignas(16) const double zero[2] = {0., 0.};
+        if ((rc = product_device(h, trans, alpha, din, zero, xg, mu)) != HTB_OK)
+            return rc;
+        char *rbuf = static_cast<char *>(d->d_rbuf);
         HTB_NCCL(nccl().GroupStart());
         for (int r = 0; r < d->world; r++) {
-            const size_t count = size_t(d->offsets[r + 1] - d->offsets[r]) * es;
-            if (count == 0)
-                continue;
-            char *seg = xg + size_t(d->offsets[r]) * es;
-            HTB_NCCL(nccl().Broadcast(seg, seg, count, ncclChar, r, d->comm, d->comm_stream));
+            const size_t scount = size_t(d->offsets[r + 1] - d->offsets[r]) * es;
+            if (scount)
+                HTB_NCCL(nccl().Send(xg + size_t(d->offsets[r]) * es, scount, ncclChar, r, d->comm, st));
+            if (n_local)
+                HTB_NCCL(nccl().Recv(rbuf + size_t(r) * n_local * es, n_local * es, ncclChar, r, d->comm, st));
         }
         HTB_NCCL(nccl().GroupEnd());
+        const long long nd = static_cast<long long>(n_local * es / sizeof(double));
+        if (nd) {
+            const double *b   = static_cast<const double *>(beta);
+            const unsigned grid = static_cast<unsigned>((nd + 255) / 256);
+            if (h->dtype == HTB_DOUBLE)
+                sum_slices_kernel<false><<<grid, 256, 0, st>>>(static_cast<double *>(dout), static_cast<const double *>(d->d_rbuf), nd, d->world, b[0], 0., beta_zero ? 1 : 0);
+            else
+                sum_slices_kernel<true><<<grid, 256, 0, st>>>(static_cast<double *>(dout), static_cast<const double *>(d->d_rbuf), nd, d->world, b[0], b[1], beta_zero ? 1 : 0);
+            HTB_CUDA(cudaGetLastError());
+            h->launches++;
+        }
     }
-    HTB_CUDA(cudaEventRecord(d->gather_done, d->comm_stream));
-
-    DistSplit split;
-    split.order_local  = d->d_order_local;
-    split.order_remote = d->d_order_remote;
-    split.n_local      = d->n_local;
-    split.n_remote     = d->n_remote;
-    split.gather_done  = d->gather_done;
-    int rc = product_device(h, 'N', alpha, xg, beta, dout, mu, &split);
-    if (rc != HTB_OK)
-        return rc;
     if (mem_kind == HTB_MEM_HOST)
         return staged_d2h(h, out_local, h->h_out, h->d_out, n_local * es, st);
+    return HTB_OK;
+}
+
+int htb_dist_add_product_global_to_global(htb_handle h, char trans, const void *alpha, const void *in_global, const void *beta, void *out_global, int mu, int mem_kind) {
+    if (!h || !alpha || !beta || !in_global || !out_global || mu < 1)
+        return fail(HTB_ERR_INVALID, "invalid argument");
+    DistState *d = h->dist;
+    if (!d)
+        return fail(HTB_ERR_INVALID, "htb_comm_init has not been called");
+    DeviceGuard guard(h->device);
+
+    const size_t es = h->esize * mu;
+    const size_t n_local = h->nb_rows, n_global = h->nb_cols; // square operator partitioned the same way on both sides
+    const size_t my_off  = size_t(d->offsets[d->rank]) * es;
+    cudaStream_t st = h->stream;
+    const bool beta_zero = scalar_is_zero(h, beta);
+    const bool host      = mem_kind == HTB_MEM_HOST;
+    int rc;
+    if (host && (rc = ensure_staging(h, n_global * es, n_global * es)) != HTB_OK)
+        return rc;
+    char *dout = host ? static_cast<char *>(h->d_out) : static_cast<char *>(out_global);
+    if (trans == 'N') {
+        // y_local = beta out[own rows] + alpha H_strip x, then the gather of y (MPI_Allgatherv,
+        // add_distributed_operator_vector_product_global_to_global.hpp:43-50,74-76)
+        const void *din = in_global;
+        if (host) {
+            if ((rc = staged_h2d(h, h->d_in, h->h_in, in_global, n_global * es, st)) != HTB_OK)
+                return rc;
+            if (!beta_zero && (rc = staged_h2d(h, dout + my_off, static_cast<char *>(h->h_out) + my_off, static_cast<const char *>(out_global) + my_off, n_local * es, st)) != HTB_OK)
+                return rc;
+            din = h->d_in;
+        }
+        if ((rc = product_device(h, 'N', alpha, din, beta, dout + my_off, mu)) != HTB_OK)
+            return rc;
+        if ((rc = gather_segments(d, dout, es, st)) != HTB_OK)
+            return rc;
+    } else {
+        // partial = alpha op(H_strip)^T in[own rows] (global length), MPI_Allreduce(SUM), out = sum + beta out_before (:51-57,77-83)
+        const char *din = static_cast<const char *>(in_global) + my_off;
+        if (host) {
+            if ((rc = staged_h2d(h, h->d_in, h->h_in, din, n_local * es, st)) != HTB_OK)
+                return rc;
+            din = static_cast<const char *>(h->d_in);
+        }
+        HTB_CUDA(grow_device(&d->d_xglobal, &d->xglobal_cap, n_global * es));
+        alignas(16) const double zero[2] = {0., 0.};
+        if ((rc = product_device(h, trans, alpha, din, zero, d->d_xglobal, mu)) != HTB_OK)
+            return rc;
+        const size_t nd = n_global * es / sizeof(double);
+        if (beta_zero) {
+            if (d->world > 1)
+                HTB_NCCL(nccl().AllReduce(d->d_xglobal, dout, nd, ncclDouble, ncclSum, d->comm, st));
+            else
+                HTB_CUDA(cudaMemcpyAsync(dout, d->d_xglobal, n_global * es, cudaMemcpyDeviceToDevice, st));
+        } else {
+            if (d->world > 1)
+                HTB_NCCL(nccl().AllReduce(d->d_xglobal, d->d_xglobal, nd, ncclDouble, ncclSum, d->comm, st));
+            const void *old = out_global;
+            if (host) {
+                HTB_CUDA(grow_device(&d->d_old, &d->old_cap, n_global * es));
+                if ((rc = staged_h2d(h, d->d_old, h->h_out, out_global, n_global * es, st)) != HTB_OK)
+                    return rc;
+                old = d->d_old;
+            }
+            const double *b     = static_cast<const double *>(beta);
+            const unsigned grid = static_cast<unsigned>((nd + 255) / 256);
+            if (h->dtype == HTB_DOUBLE)
+                add_scaled_kernel<false><<<grid, 256, 0, st>>>(reinterpret_cast<double *>(dout), static_cast<const double *>(d->d_xglobal), static_cast<const double *>(old), static_cast<long long>(nd), b[0], 0.);
+            else
+                add_scaled_kernel<true><<<grid, 256, 0, st>>>(reinterpret_cast<double *>(dout), static_cast<const double *>(d->d_xglobal), static_cast<const double *>(old), static_cast<long long>(nd), b[0], b[1]);
+            HTB_CUDA(cudaGetLastError());
+            h->launches++;
+        }
+    }
+    if (host)
+        return staged_d2h(h, out_global, h->h_out, dout, n_global * es, st);
     return HTB_OK;
 }
 

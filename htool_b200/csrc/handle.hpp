@@ -19,7 +19,15 @@ struct DistSplit {
     const uint32_t *order_local  = nullptr;
     const uint32_t *order_remote = nullptr;
     int n_local = 0, n_remote = 0;
-    cudaEvent_t gather_done = nullptr;
+    cudaEvent_t gather_done = nullptr; // NCCL gather: the remote part waits for this event
+    // peer-memory gather (preferred): ONE launch over order_all (local blocks first); remote blocks wait in the kernel
+    // for the arrival flag of the rank that owns their slice of x
+    const uint32_t *order_all            = nullptr;
+    int n_all                            = 0;
+    const uint32_t *owner                = nullptr;
+    const unsigned long long *flags      = nullptr;
+    unsigned long long epoch             = 0;
+    int world                            = 1;
 };
 }
 
@@ -67,6 +75,7 @@ struct htb_operator {
 namespace htb {
 extern thread_local std::string g_last_error;
 int fail(int status, const std::string &msg);
+int64_t option_value(const char *key); // htb_set_option / htb_get_option table
 int cuda_fail(cudaError_t e, const char *what);
 int product_device(htb_operator *h, char trans, const void *alpha, const void *in, const void *beta, void *out, int mu, const DistSplit *split = nullptr);
 int ensure_staging(htb_operator *h, size_t in_bytes, size_t out_bytes);

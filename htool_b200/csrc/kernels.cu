@@ -106,6 +106,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 struct KernelSide {
     const BlockDesc *blocks;
     const StageDesc *stages;
@@ -320,6 +326,16 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(KernelSide ks, PassArg
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     init_barriers(ks, sm);
+    if (a.wait_flags) { // distributed: the slice of x this block reads is written by its owner's push kernel (dist.cu)
+        if (threadIdx.x == 0) {
+            const uint32_t ow = a.wait_owner[ks.order[blockIdx.x]];
+            if (ow != 0xFFFFFFFFu)
+                for (uint32_t q = ow & 0xFFFFu; q <= (ow >> 16); q++)
+                    while (ld_acquire_sys(a.wait_flags + q) < a.wait_epoch)
+                        __nanosleep(64);
+        }
+        __syncthreads();
+    }
     // stage the block's x sub-vector in shared memory (every unit of the block multiplies a slice of it)
     for (int i = threadIdx.x; i < ks.block_rows; i += kThreads) {
         const long long g = static_cast<long long>(bd.row_start) + i + a.in_shift;
@@ -598,6 +614,12 @@ __global__ void scale_kernel(T *y, long long n, T beta, int beta_is_zero) {
         y[i] = beta_is_zero ? zero_of(T{}) : mul(beta, y[i]);
 }
 
+__global__ void wait_flags_kernel(const unsigned long long *flags, int world, unsigned long long epoch) {
+    if (static_cast<int>(threadIdx.x) < world)
+        while (ld_acquire_sys(flags + threadIdx.x) < epoch)
+            __nanosleep(64);
+}
+
 inline KernelSide make_kernel_side(const SideDevice &s, const LaunchConfig &cfg, int ring) {
     return KernelSide{s.blocks, s.stages, s.order, s.stream, s.cs_base, cfg.block_rows, cfg.stage_bytes, cfg.cseg_bytes, ring, cfg.evict_first};
 }
@@ -734,6 +756,11 @@ cudaError_t launch_scale(T *y, long long n, T beta, cudaStream_t stream) {
     if (n == 0)
         return cudaSuccess;
     scale_kernel<T><<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(y, n, beta, is_zero(beta) ? 1 : 0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_wait_flags(const unsigned long long *flags, int world, unsigned long long epoch, cudaStream_t stream) {
+    wait_flags_kernel<<<1, 32, 0, stream>>>(flags, world, epoch);
     return cudaGetLastError();
 }
 

@@ -60,6 +60,11 @@ struct PassArgs {
     int fused        = 0;
     T *scratch2      = nullptr;
     int conj2        = 0;
+    // distributed REDUCE over peer memory (dist.cu): before a block stages its x sub-vector it waits until the ranks
+    // owning that index range have published their slice of x (arrival flags written over NVLink, >= wait_epoch)
+    const unsigned long long *wait_flags = nullptr; // [world], this rank's copy
+    const uint32_t *wait_owner           = nullptr; // per block id: first owner | last owner << 16, 0xFFFFFFFF = own partition
+    unsigned long long wait_epoch        = 0;
 };
 
 template <typename T>
@@ -79,6 +84,9 @@ cudaError_t launch_permute(const T *in, T *out, const int32_t *perm, int n, int 
 // y <- beta * y (used when an operator has no block at all on the output side)
 template <typename T>
 cudaError_t launch_scale(T *y, long long n, T beta, cudaStream_t stream);
+
+// one warp spinning until flags[q] >= epoch for every q < world (peer-memory gather, multi-RHS path)
+cudaError_t launch_wait_flags(const unsigned long long *flags, int world, unsigned long long epoch, cudaStream_t stream);
 
 size_t reduce_smem_bytes(const LaunchConfig &cfg, size_t esize);
 size_t apply_smem_bytes(const LaunchConfig &cfg, size_t esize);

@@ -169,13 +169,24 @@ int htb_nccl_get_unique_id(void *id128);
  * distributed_operator/utility.hpp:56). */
 int htb_comm_init(htb_handle h, const void *id128, int world_size, int rank, const int32_t *partition_offsets);
 int htb_comm_destroy(htb_handle h);
-/* out_local <- beta*out_local + alpha*H_strip*allgather(in_local) (trans == 'N' only), mu >= 1 row-major.
- * Replaces internal_add_distributed_operator_vector_product_local_to_local
- * (add_distributed_operator_vector_product_local_to_local.hpp:19-59: MPI_Allgatherv of x at
- * linalg/utility.hpp:27, then the global-to-local product) and its row-major matrix twin
- * (add_distributed_operator_matrix_product_row_major_local_to_local.hpp:25-66). The allgather runs on a
- * second stream and overlaps with the leaves whose source range lies inside the rank's own partition. */
-int htb_dist_add_product_local_to_local(htb_handle h, const void *alpha, const void *in_local, const void *beta, void *out_local, int mu, int mem_kind);
+/* Local-to-local distributed product, mu >= 1 row-major. Replaces
+ * internal_add_distributed_operator_vector_product_local_to_local
+ * (add_distributed_operator_vector_product_local_to_local.hpp:19-89) and its row-major matrix twin
+ * (add_distributed_operator_matrix_product_row_major_local_to_local.hpp:25-95).
+ *   trans == 'N': out_local <- beta*out_local + alpha*H_strip*allgather(in_local). The gather (MPI_Allgatherv at
+ *     linalg/utility.hpp:27) runs on a second stream and overlaps with the leaves whose source range lies inside
+ *     the rank's own partition.
+ *   trans == 'T' | 'C': z = alpha*op(H_strip)^T*in_local has the global length; slice r of z is sent to rank r
+ *     (MPI_Alltoallv at :77, grouped ncclSend/ncclRecv here) and out_local <- beta*out_local + sum_r z_r[own slice],
+ *     added in rank order like the reference's axpy loop (:83-86). */
+int htb_dist_add_product_local_to_local(htb_handle h, char trans, const void *alpha, const void *in_local, const void *beta, void *out_local, int mu, int mem_kind);
+/* Global-to-global distributed product in partition (cluster) numbering, square operator, mu >= 1 row-major. Replaces
+ * internal_add_distributed_operator_vector_product_global_to_global
+ * (add_distributed_operator_vector_product_global_to_global.hpp:18-85) and the row-major matrix twin
+ * (add_distributed_operator_matrix_product_row_major_global_to_global.hpp:18-84).
+ *   'N': own rows of out <- beta*out + alpha*H_strip*in_global, then the gather of out (MPI_Allgatherv, :75).
+ *   'T' | 'C': partial = alpha*op(H_strip)^T*in_global[own rows]; out <- allreduce_sum(partial) + beta*out (:77-83). */
+int htb_dist_add_product_global_to_global(htb_handle h, char trans, const void *alpha, const void *in_global, const void *beta, void *out_global, int mu, int mem_kind);
 
 /* ---- misc ------------------------------------------------------------------------------------------ */
 

@@ -13,6 +13,7 @@
 #include <htool/distributed_operator/linalg/add_distributed_operator_vector_product_local_to_local.hpp>
 #include <htool/distributed_operator/linalg/add_distributed_operator_vector_sub_product_global_to_local.hpp>
 
+#include <htool_b200/distributed.hpp>
 #include <htool_b200/operators.hpp>
 
 #include <cstdio>
@@ -75,6 +76,7 @@ enum { G2L_VECTOR = 0,
        FREE_VECTOR_USER,
        FREE_MATRIX_USER,
        LOGGED_UNSUPPORTED,
+       DEVICE_DIST,
        N_GROUPS };
 
 struct CountingWriter : htool::IObjectWriter {
@@ -235,6 +237,42 @@ int run(htb_ref::Case<T> &c, double *results, int n_results) {
             internal_add_distributed_operator_vector_sub_product_global_to_local(RA, x.data(), yr.data(), mu, offset, size);
             internal_add_distributed_operator_vector_sub_product_global_to_local(GA, x.data(), yg.data(), mu, offset, size);
             upd(DIST_SUB_PRODUCT, rel_err(yg, yr));
+        }
+        // ---- DeviceDistributedOperator (htool_b200/distributed.hpp): the NCCL-backed twin of the linalg above, same names,
+        // against the reference's DistributedOperator (one rank here: the collectives degenerate, the call path does not)
+        if (c.spec.same_cluster) {
+            htool_b200::DeviceDistributedOperator<T, double> DA(H, RA.get_target_partition(), MPI_COMM_WORLD);
+            if (DA.is_valid()) {
+                for (char trans : valid_trans(sym, is_complex)) {
+                    T alpha = rnd_scalar<T>(gen), beta = rnd_scalar<T>(gen);
+                    auto x = rnd_vector<T>(gen, NS), y0 = rnd_vector<T>(gen, NT);
+                    auto yr = y0, yg = y0;
+                    std::vector<T> work(2 * size_t(NS + NT));
+                    internal_add_distributed_operator_vector_product_local_to_local(trans, alpha, RA, x.data(), beta, yr.data(), work.data());
+                    htool_b200::internal_add_distributed_operator_vector_product_local_to_local(trans, alpha, DA, x.data(), beta, yg.data());
+                    upd(DEVICE_DIST, rel_err(yg, yr));
+                    yr = y0, yg = y0;
+                    internal_add_distributed_operator_vector_product_global_to_global(trans, alpha, RA, x.data(), beta, yr.data(), static_cast<T *>(nullptr));
+                    htool_b200::internal_add_distributed_operator_vector_product_global_to_global(trans, alpha, DA, x.data(), beta, yg.data());
+                    upd(DEVICE_DIST, rel_err(yg, yr));
+                    yr = y0, yg = y0;
+                    add_distributed_operator_vector_product_global_to_global(trans, alpha, RA, x.data(), beta, yr.data(), static_cast<T *>(nullptr));
+                    htool_b200::add_distributed_operator_vector_product_global_to_global(trans, alpha, DA, x.data(), beta, yg.data());
+                    upd(DEVICE_DIST, rel_err(yg, yr));
+                    const int mu = 3;
+                    Matrix<T> Xr(mu, NS), Yrr(mu, NT);
+                    auto xv = rnd_vector<T>(gen, size_t(NS) * mu), yv = rnd_vector<T>(gen, size_t(NT) * mu);
+                    std::copy(xv.begin(), xv.end(), Xr.data());
+                    std::copy(yv.begin(), yv.end(), Yrr.data());
+                    auto ygm = yv;
+                    std::vector<T> workm(2 * size_t(NS + NT) * mu);
+                    internal_add_distributed_operator_matrix_product_row_major_local_to_local(trans, alpha, RA, Xr, beta, Yrr, workm.data());
+                    htool_b200::internal_add_distributed_operator_matrix_product_row_major_local_to_local(trans, alpha, DA, xv.data(), beta, ygm.data(), mu);
+                    upd(DEVICE_DIST, rel_err(ygm, std::vector<T>(Yrr.data(), Yrr.data() + size_t(NT) * mu)));
+                }
+            } else {
+                upd(DEVICE_DIST, 1.);
+            }
         }
         // ---- free functions, user numbering (use_hmatrix.cpp:107) -------------------------------------------------
         // NOTE the reference's user-numbering front ends permute `in` with the SOURCE cluster and `out` with the TARGET

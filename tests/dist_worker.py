@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--scalar", default="double")
     ap.add_argument("--sym", default="N")
     ap.add_argument("--rhs", type=int, default=1)
+    ap.add_argument("--p2p", type=int, default=1, help="0: NCCL gather of x instead of the peer-memory push (htb_set_option dist_p2p)")
     args = ap.parse_args()
 
     import torch
@@ -76,8 +77,57 @@ def main():
     else:
         case.matrix_product_row_major("N", alpha, x_global, beta, y_ref, mu, variant="global_to_local_operator")
 
-    def err(y):
-        return float(np.linalg.norm(y - y_ref) / np.linalg.norm(y_ref))
+    def err(y, ref=None):
+        ref = y_ref if ref is None else ref
+        return float(np.linalg.norm(y - ref) / np.linalg.norm(ref))
+
+    # ---- reference results of the transposed local-to-local and the global-to-global products -----------------------
+    # What the reference's DistributedOperator linalg does around the per-rank operator, with the MPI collectives
+    # replaced by torch.distributed on CPU tensors (gloo):
+    #   l2l T/C (add_distributed_operator_vector_product_local_to_local.hpp:47-87): z_r = alpha op(H_r)^T x_r (global
+    #     length), Alltoallv of the slices, out = beta out + sum_r z_r[own slice] in rank order;
+    #   g2g N (…global_to_global.hpp:43-76): own rows of out = beta out + alpha H_r x, Allgatherv;
+    #   g2g T/C (:51-83): Allreduce(sum) of z_r, + beta out.
+    cpu = dist.new_group(backend="gloo") if args.backend == "nccl" else None
+    tt = torch.from_numpy
+
+    def prod(trans, a, x, b, y):
+        if mu == 1:
+            case.vector_product(trans, a, x, b, y, variant="global_to_local_operator")
+        else:
+            case.matrix_product_row_major(trans, a, x, b, y, mu, variant="global_to_local_operator")
+        return y
+
+    def as_real(a):
+        return a.view(np.float64) if a.dtype == np.complex128 else a
+
+    transposes = ["T"] if (dtype == np.float64 or args.sym == "S") else ["C"]
+    if dtype == np.complex128 and args.sym == "N":
+        transposes = ["T", "C"]
+    y0_global = (rng.random(n_global * mu) - 0.5).astype(dtype)  # same on every rank
+    lo_e, hi_e = int(offsets[rank]) * mu, int(offsets[rank + 1]) * mu
+    ref_l2l, ref_g2g = {}, {}
+    for t in transposes:
+        z = prod(t, alpha, x_local, 0.0, np.zeros(n_global * mu, dtype))
+        send = [tt(as_real(np.ascontiguousarray(z[int(offsets[r]) * mu: int(offsets[r + 1]) * mu]))) for r in range(world)]
+        recv = [torch.zeros(as_real(x_local).size, dtype=torch.float64) for _ in range(world)]
+        # gloo has no all_to_all: every slice owner gathers its slices instead
+        for r in range(world):
+            got = [torch.zeros_like(send[r]) for _ in range(world)] if rank == r else None
+            dist.gather(send[r], got, dst=r, group=cpu)
+            if rank == r:
+                recv = got
+        out = beta * y0
+        for r in range(world):
+            out = out + recv[r].numpy().view(dtype)
+        ref_l2l[t] = out
+        zsum = tt(as_real(z.copy()))
+        dist.all_reduce(zsum, group=cpu)
+        ref_g2g[t] = zsum.numpy().view(dtype) + beta * y0_global
+    yl = prod("N", alpha, x_global, beta, y0_global[lo_e:hi_e].copy())
+    parts = [torch.zeros(int(offsets[r + 1] - offsets[r]) * mu * (2 if dtype == np.complex128 else 1), dtype=torch.float64) for r in range(world)]
+    dist.all_gather(parts, tt(as_real(yl)), group=cpu)
+    ref_g2g["N"] = torch.cat(parts).numpy().view(dtype)
 
     errs = []
     if args.backend == "gloo":
@@ -113,24 +163,68 @@ def main():
         em.reduce(1, x_masked, 0, s_mask, False, False)
         side1.order = order
         assert np.array_equal(np.nan_to_num(s_full), np.nan_to_num(s_mask))
+        # transposed local-to-local and global-to-global: strip product through the emulator, exchange through gloo
+        for t in transposes:
+            z = np.zeros(n_global, dtype)
+            assert em.vector_product(t, alpha, x_local, 0.0, z) == 0
+            out = beta * y0
+            for r in range(world):
+                piece = tt(as_real(np.ascontiguousarray(z[offsets[r]: offsets[r + 1]])))
+                got = [torch.zeros_like(piece) for _ in range(world)] if rank == r else None
+                dist.gather(piece, got, dst=r)
+                if rank == r:
+                    for g in got:
+                        out = out + g.numpy().view(dtype)
+            errs.append(err(out, ref_l2l[t]))
+            zs = tt(as_real(z.copy()))
+            dist.all_reduce(zs)
+            errs.append(err(zs.numpy().view(dtype) + beta * y0_global, ref_g2g[t]))
+        yl = y0_global[lo_e:hi_e].copy()
+        assert em.vector_product("N", alpha, gathered, beta, yl) == 0
+        parts = [torch.zeros(int(offsets[r + 1] - offsets[r]) * (2 if dtype == np.complex128 else 1), dtype=torch.float64) for r in range(world)]
+        dist.all_gather(parts, tt(as_real(yl)))
+        errs.append(err(torch.cat(parts).numpy().view(dtype), ref_g2g["N"]))
     else:
         from htool_b200 import capi
 
         case.desc.device = local_rank
+        capi.set_option("dist_p2p", args.p2p)
         op = capi.Operator(case.desc)
         uid = torch.zeros(capi.HTB_NCCL_UNIQUE_ID_BYTES, dtype=torch.uint8, device="cuda")
         if rank == 0:
             uid = torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8).cuda()
         dist.broadcast(uid, 0)
         op.comm_init(bytes(uid.cpu().numpy().tobytes()), world, rank, offsets)
-        for _ in range(3):  # repeated: the gather buffer / events are reused across calls
+        for it in range(5):  # repeated: gather buffers (double-buffered by epoch), flags and events are reused across calls
             y = y0.copy()
-            op.dist_add_product_local_to_local(alpha, x_local, beta, y, mu)
-            errs.append(err(y))
+            xs = x_local * (1.0 + it)  # a different x every time: a stale buffer would show
+            op.dist_add_product_local_to_local(alpha, xs, beta, y, mu)
+            errs.append(err((y - beta * y0) / (1.0 + it) + beta * y0))
         x_d, y_d = torch.from_numpy(x_local).cuda(), torch.from_numpy(y0.copy()).cuda()
         op.dist_add_product_local_to_local(alpha, x_d.data_ptr(), beta, y_d.data_ptr(), mu, capi.HTB_MEM_DEVICE)
         op.synchronize()
         errs.append(err(y_d.cpu().numpy()))
+        tdt = torch.float64 if dtype == np.float64 else torch.complex128
+        for t in transposes:  # T / C local-to-local: grouped send/recv of the slices + rank-ordered sum
+            y = y0.copy()
+            op.dist_add_product_local_to_local(alpha, x_local, beta, y, mu, trans=t)
+            errs.append(err(y, ref_l2l[t]))
+            y_d = torch.from_numpy(y0.copy()).cuda()
+            op.dist_add_product_local_to_local(alpha, x_d.data_ptr(), beta, y_d.data_ptr(), mu, capi.HTB_MEM_DEVICE, trans=t)
+            op.synchronize()
+            errs.append(err(y_d.cpu().numpy(), ref_l2l[t]))
+            y = np.full(n_local * mu, np.nan, dtype)  # beta == 0 ignores out
+            op.dist_add_product_local_to_local(alpha, x_local, 0.0, y, mu, trans=t)
+            errs.append(err(y, ref_l2l[t] - beta * y0))
+        xg_d = torch.from_numpy(x_global).cuda()
+        for t in ["N"] + transposes:  # global-to-global
+            y = y0_global.copy()
+            op.dist_add_product_global_to_global(t, alpha, x_global, beta, y, mu)
+            errs.append(err(y, ref_g2g[t]))
+            yg_d = torch.from_numpy(y0_global.copy()).cuda()
+            op.dist_add_product_global_to_global(t, alpha, xg_d.data_ptr(), beta, yg_d.data_ptr(), mu, capi.HTB_MEM_DEVICE)
+            op.synchronize()
+            errs.append(err(yg_d.cpu().numpy(), ref_g2g[t]))
         op.close()
 
     worst = torch.tensor([max(errs)], dtype=torch.float64, device=dev)

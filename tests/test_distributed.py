@@ -39,8 +39,9 @@ def test_two_gloo_ranks_host_logic(extra, have_ref):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("extra", [["--points", "20000"], ["--points", "16000", "--sym", "S"], ["--points", "12000", "--scalar", "complex", "--sym", "S"], ["--points", "8000", "--rhs", "3"]],
-                         ids=["double", "double_S", "complex_S", "mu3"])
+@pytest.mark.parametrize("extra", [["--points", "20000"], ["--points", "16000", "--sym", "S"], ["--points", "12000", "--scalar", "complex", "--sym", "S"], ["--points", "8000", "--rhs", "3"],
+                                   ["--points", "8000", "--rhs", "16"], ["--points", "16000", "--sym", "S", "--p2p", "0"], ["--points", "8000", "--rhs", "3", "--p2p", "0"]],
+                         ids=["double", "double_S", "complex_S", "mu3", "mu16_dmma", "double_S_nccl_gather", "mu3_nccl_gather"])
 def test_two_nccl_ranks(extra, have_ref):
     import torch
 

@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--symmetry", default="N", choices=["N", "S"])
     ap.add_argument("--trans", default="N")
     ap.add_argument("--mu", type=int, default=1)
+    ap.add_argument("--partitions", type=int, default=1, help="tune ONE row strip of a P-way distributed operator on one GPU")
+    ap.add_argument("--rank", type=int, default=0)
     ap.add_argument("--set", action="append", default=[], help="comma separated key=value list; one product configuration per --set")
     args = ap.parse_args()
 
@@ -41,7 +43,7 @@ def main():
     R.set_num_threads(os.cpu_count() or 1)
     bargs = argparse.Namespace(n=args.n, dtype=args.dtype, symmetry=args.symmetry, mu=1, gpus=1)
     t0 = time.perf_counter()
-    case = R.RefCase(**bench.case_kwargs(bargs))
+    case = R.RefCase(**(bench.case_kwargs(bargs, args.partitions, args.rank) if args.partitions > 1 else bench.case_kwargs(bargs)))
     print(json.dumps({"assembly_s": time.perf_counter() - t0, **{k: v for k, v in case.info().items() if k in ("nb_leaves", "coefficients", "coefficients_twice")}}), flush=True)
     dtype = case.np_dtype
     esize = np.dtype(dtype).itemsize
@@ -101,7 +103,7 @@ def main():
             nbytes = esize * (info["coefficients"] + mu * (ni + no))
             flops = 2.0 * mu * (info["coefficients"] + info["coefficients_twice"]) * (1 if dtype == np.float64 else 4)
             print(json.dumps({"opts": {k: v for k, v in opts.items() if v != defaults[k]}, "mu": mu, "ms": ms, "gbs": nbytes / ms / 1e6, "tflops": flops / ms / 1e9, "parity": parity,
-                              "passes_ms": {k: v["ms"] / 5 for k, v in pt.items()}, "pack_s": t_pack, "store_gb": info["store_bytes"] / 1e9,
+                              "passes_ms": {k: v["ms"] / 5 for k, v in pt.items()}, "pack_s": t_pack, "store_gb": info["store_bytes"] / 1e9, "blocks": [info["nb_target_blocks"], info["nb_source_blocks"]],
                               "workspace_gb": info["workspace_bytes"] / 1e9, "descriptor_mb": info["descriptor_bytes"] / 1e6}), flush=True)
             op.set_stream(None)
             op.close()
