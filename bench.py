@@ -463,7 +463,7 @@ def run_ours(args):
             "dtype": "f64" if dtype == np.float64 else "c128", "data": "synthetic",
             "config": {
                 "workload": workload_label(args),
-                "n": args.n, "mu": mu, "parallelism": f"row-strips x{world}" if world > 1 else "single GPU",
+                "n": args.n, "mu": mu, "parallelism": (f"row-strips x{world}, gather of x: " + {0: "none", 1: "NCCL broadcasts", 2: "peer-memory push over NVLink"}[op.info()["dist_gather"]]) if world > 1 else "single GPU",
                 "l2": f"inputs larger than L2: {esize * C_total / world / 1e9:.2f} GB of coefficients streamed per GPU per step vs 126 MB L2 (no flush needed)",
                 "coefficients": C_total, "leaves": int(oinfo["nb_leaves"]) if world == 1 else None,
                 "packer": {k: int(v) for k, v in (kv.split("=") for kv in args.opt)},

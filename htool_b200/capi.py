@@ -75,7 +75,7 @@ class htb_info(C.Structure):
         ("nb_target_blocks", C.c_int32),
         ("nb_source_blocks", C.c_int32),
         ("sm_count", C.c_int32),
-        ("reserved", C.c_int32),
+        ("dist_gather", C.c_int32),
     ]
 
     def as_dict(self):

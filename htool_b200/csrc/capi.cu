@@ -706,6 +706,7 @@ int htb_get_info(htb_handle h, htb_info *info) {
     if (!h || !info)
         return fail(HTB_ERR_INVALID, "null argument");
     *info                  = h->info;
+    info->dist_gather      = dist_gather_mode(h);
     info->store_bytes      = static_cast<int64_t>(h->store_bytes);
     info->descriptor_bytes = static_cast<int64_t>(h->descriptor_bytes);
     info->workspace_bytes  = static_cast<int64_t>(h->workspace_bytes + h->in_cap + h->out_cap + h->work_cap * 2);

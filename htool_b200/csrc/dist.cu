@@ -121,6 +121,8 @@ static void close_peer_buffers(DistState *d) {
     }
 }
 
+int dist_gather_mode(const htb_operator *h) { return !h->dist ? 0 : (h->dist->p2p ? 2 : 1); }
+
 void dist_destroy(htb_operator *h) {
     DistState *d = h->dist;
     if (!d)

@@ -109,7 +109,8 @@ typedef struct htb_info {
     int32_t dtype, device;
     int32_t nb_rows, nb_cols;
     int32_t nb_target_blocks, nb_source_blocks;
-    int32_t sm_count, reserved;
+    int32_t sm_count;
+    int32_t dist_gather;          /* 0: no communicator, 1: NCCL gather of x, 2: peer-memory push over NVLink (htb_comm_init) */
 } htb_info;
 
 /* ---- life cycle ---------------------------------------------------------------------------------- */

@@ -195,6 +195,7 @@ def main():
             uid = torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8).cuda()
         dist.broadcast(uid, 0)
         op.comm_init(bytes(uid.cpu().numpy().tobytes()), world, rank, offsets)
+        assert op.info()["dist_gather"] == (2 if args.p2p else 1), op.info()["dist_gather"]  # NVLink box: peer mappings must work
         for it in range(5):  # repeated: gather buffers (double-buffered by epoch), flags and events are reused across calls
             y = y0.copy()
             xs = x_local * (1.0 + it)  # a different x every time: a stale buffer would show
