@@ -112,6 +112,18 @@ class htb_packed_side(C.Structure):
     ]
 
 
+class htb_gmres_options(C.Structure):
+    _fields_ = [("restart", C.c_int32), ("max_iterations", C.c_int32), ("tolerance", C.c_double), ("orthogonalization", C.c_int32), ("verbosity", C.c_int32),
+                ("compute_true_residual", C.c_int32), ("reserved", C.c_int32)]
+
+
+class htb_gmres_result(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("converged", C.c_int32), ("matvecs", C.c_int32), ("reserved", C.c_int32), ("relative_residual", C.c_double),
+                ("true_relative_residual", C.c_double)]
+
+
+HTB_GMRES_CGS, HTB_GMRES_CGS2 = 0, 1
+
 # name -> (restype, argtypes): every symbol include/htool_b200.h declares
 SYMBOLS = {
     "htb_create": (C.c_int, [C.POINTER(htb_hmatrix_desc), C.POINTER(C.c_void_p)]),
@@ -131,6 +143,8 @@ SYMBOLS = {
     "htb_comm_destroy": (C.c_int, [C.c_void_p]),
     "htb_dist_add_product_local_to_local": (C.c_int, [C.c_void_p, C.c_char, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "htb_dist_add_product_global_to_global": (C.c_int, [C.c_void_p, C.c_char, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "htb_gmres_default_options": (C.c_int, [C.POINTER(htb_gmres_options)]),
+    "htb_gmres": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(htb_gmres_options), C.POINTER(htb_gmres_result), C.c_int]),
     "htb_last_error": (C.c_char_p, []),
     "htb_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "htb_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
@@ -294,6 +308,24 @@ class Operator:
         yp = C.c_void_p(y) if isinstance(y, int) else _ptr(y)
         check(self.lib, self.lib.htb_dist_add_product_global_to_global(self.handle, trans.encode(), _ptr(a), xp, _ptr(b), yp, mu, mem_kind))
         return y
+
+
+def _gmres(self, rhs, x, mem_kind=HTB_MEM_HOST, **options):
+    """Device-resident restarted GMRES (htb_gmres). rhs / x: numpy arrays (host) or device addresses; x = initial guess in,
+    solution out. options: restart, max_iterations, tolerance, orthogonalization, verbosity, compute_true_residual."""
+    opt = htb_gmres_options()
+    check(self.lib, self.lib.htb_gmres_default_options(C.byref(opt)))
+    for k, v in options.items():
+        assert hasattr(opt, k), k
+        setattr(opt, k, v)
+    res = htb_gmres_result()
+    bp = C.c_void_p(rhs) if isinstance(rhs, int) else _ptr(rhs)
+    xp = C.c_void_p(x) if isinstance(x, int) else _ptr(x)
+    check(self.lib, self.lib.htb_gmres(self.handle, bp, xp, C.byref(opt), C.byref(res), mem_kind))
+    return {k: getattr(res, k) for k, _ in res._fields_ if k != "reserved"}
+
+
+Operator.gmres = _gmres
 
 
 def nccl_unique_id() -> bytes:

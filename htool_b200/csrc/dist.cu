@@ -121,6 +121,19 @@ static void close_peer_buffers(DistState *d) {
     }
 }
 
+int dist_world(const htb_operator *h) { return h->dist ? h->dist->world : 0; }
+
+// in-place sum over the ranks of n doubles on the device (inner products of the Krylov loop, gmres.cu)
+int dist_allreduce_sum(htb_operator *h, double *dev, size_t n, cudaStream_t st) {
+    DistState *d = h->dist;
+    if (!d || d->world <= 1 || n == 0)
+        return HTB_OK;
+    ncclResult_t r = nccl().AllReduce(dev, dev, n, ncclDouble, ncclSum, d->comm, st);
+    if (r != ncclSuccess)
+        return fail(HTB_ERR_NCCL, std::string("ncclAllReduce: ") + nccl().GetErrorString(r));
+    return HTB_OK;
+}
+
 int dist_gather_mode(const htb_operator *h) { return !h->dist ? 0 : (h->dist->p2p ? 2 : 1); }
 
 void dist_destroy(htb_operator *h) {

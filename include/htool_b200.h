@@ -189,6 +189,33 @@ int htb_dist_add_product_local_to_local(htb_handle h, char trans, const void *al
  *   'T' | 'C': partial = alpha*op(H_strip)^T*in_global[own rows]; out <- allreduce_sum(partial) + beta*out (:77-83). */
 int htb_dist_add_product_global_to_global(htb_handle h, char trans, const void *alpha, const void *in_global, const void *beta, void *out_global, int mu, int mem_kind);
 
+/* ---- device-resident Krylov loop ------------------------------------------------------------------------ */
+
+/* Restarted GMRES on A x = rhs with A = the handle's operator, all vectors resident in HBM. Stands for
+ * DDM::solve with "-hpddm_schwarz_method none" (solvers/ddm.hpp:134-193), i.e. HPDDM's unpreconditioned GMRES calling
+ * HPDDMOperator::GMV (wrappers/wrapper_hpddm.hpp:102-145) per iteration; HPDDM is not vendored in the reference, so the
+ * Krylov arithmetic restates the published algorithm with HPDDM's defaults (restart 40, 100 iterations, tolerance 1e-6
+ * relative to ||rhs||, classical Gram-Schmidt). With a communicator (htb_comm_init) rhs / x are the rank's LOCAL slices,
+ * the product is htb_dist_add_product_local_to_local and the inner products are summed over the ranks; without one the
+ * operator must be square. x holds the initial guess on entry and the solution on return. Collective when distributed. */
+enum { HTB_GMRES_CGS = 0, HTB_GMRES_CGS2 = 1 };
+typedef struct htb_gmres_options {
+    int32_t restart;               /* Krylov vectors kept before restarting */
+    int32_t max_iterations;        /* total inner iterations (products, not counting the residual of each cycle) */
+    double tolerance;              /* stop when ||rhs - A x|| <= tolerance * ||rhs|| (recurrence estimate) */
+    int32_t orthogonalization;     /* HTB_GMRES_CGS (HPDDM default) | HTB_GMRES_CGS2 */
+    int32_t verbosity;             /* 0 silent, 1 summary, 2 every iteration (stderr) */
+    int32_t compute_true_residual; /* one more product at the end */
+    int32_t reserved;
+} htb_gmres_options;
+typedef struct htb_gmres_result {
+    int32_t iterations, converged, matvecs, reserved;
+    double relative_residual;      /* from the Givens recurrence */
+    double true_relative_residual; /* ||rhs - A x|| / ||rhs||, -1 if not computed */
+} htb_gmres_result;
+int htb_gmres_default_options(htb_gmres_options *options);
+int htb_gmres(htb_handle h, const void *rhs, void *x, const htb_gmres_options *options, htb_gmres_result *result, int mem_kind);
+
 /* ---- misc ------------------------------------------------------------------------------------------ */
 
 const char *htb_last_error(void);
