@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--cpu-reps", type=int, default=3)
     ap.add_argument("--opt", action="append", default=[], help="packer/launch option key=value (htb_set_option)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gmres-iterations", type=int, default=200, help="BASELINE.json configs[4]: repeated matvecs inside a device-resident GMRES solve (0: skip)")
     return ap.parse_args()
 
 
@@ -393,6 +394,23 @@ def run_ours(args):
         clocks = sampler.summarise(sampler.window(tw0, tw1))
         sampler.stop()
 
+    # ---- BASELINE.json configs[4]: K repeated products inside a (device-resident) GMRES solve, restart 40 ---------------
+    # (extra key, not the headline: HPDDM is absent from the reference tree, so there is no reference arm for the solver)
+    gm = None
+    if args.gmres_iterations > 0 and mu == 1:
+        b_host = seeded_x(n_local, dtype, seed=2 + rank)
+        b_d = torch.from_numpy(b_host).cuda()
+        xs_d = torch.zeros(n_local, dtype=tdt, device="cuda")
+        op.gmres(b_d.data_ptr(), xs_d.data_ptr(), mem_kind=capi.HTB_MEM_DEVICE, restart=40, max_iterations=5, tolerance=0.0, compute_true_residual=0)  # warm-up (allocations)
+        xs_d.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        gi = op.gmres(b_d.data_ptr(), xs_d.data_ptr(), mem_kind=capi.HTB_MEM_DEVICE, restart=40, max_iterations=args.gmres_iterations, tolerance=0.0, compute_true_residual=1)
+        barrier()
+        dt = time.perf_counter() - t0
+        gm = {"iterations": gi["iterations"], "matvecs": gi["matvecs"], "restart": 40, "seconds": dt, "matvec_per_s_inside_solver": gi["matvecs"] / dt,
+              "fraction_of_bare_matvec_rate": (gi["matvecs"] / dt) / value, "true_relative_residual": gi["true_relative_residual"], "orthogonalization": "cgs"}
+
     # ---- algorithmic bytes: s*C + s*mu*(n_src + n_tgt), descriptors excluded -------------
     coeffs = torch.tensor([float(oinfo["coefficients"])], device="cuda", dtype=torch.float64)
     leaf = case.leaves()
@@ -476,6 +494,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "matvec/s", "h2d_bytes_per_step": int(esize * mu * n_global), "d2h_bytes_per_step": int(esize * mu * n_global), "ms_per_step": 1e3 * e2e_s / args.steps,
                     "host_buffers": "page-locked (htb_host_register), direct DMA", "pageable_value": args.steps / e2e_pageable_s},
+            "gmres": gm,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "parity_rel_l2_vs_reference": parity,

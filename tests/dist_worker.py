@@ -226,6 +226,26 @@ def main():
             op.dist_add_product_global_to_global(t, alpha, xg_d.data_ptr(), beta, yg_d.data_ptr(), mu, capi.HTB_MEM_DEVICE)
             op.synchronize()
             errs.append(err(yg_d.cpu().numpy(), ref_g2g[t]))
+        if mu == 1:
+            # distributed device-resident GMRES (htb_gmres): local slices in / out, inner products summed over the ranks.
+            # Checker: the numpy oracle on the GLOBAL operator, its matvec = the reference's strip products gathered over gloo.
+            from oracle.gmres_oracle import gmres
+
+            def mv(v):
+                yl = prod("N", 1.0, np.ascontiguousarray(v.astype(dtype)), 0.0, np.zeros(n_local, dtype))
+                parts = [torch.zeros(int(offsets[r + 1] - offsets[r]) * (2 if dtype == np.complex128 else 1), dtype=torch.float64) for r in range(world)]
+                dist.all_gather(parts, tt(as_real(yl)), group=cpu)
+                return torch.cat(parts).numpy().view(dtype)
+
+            b_global = (rng.random(n_global) - 0.5).astype(dtype)
+            for iters, restart in [(5, 40), (7, 3)]:
+                xo, io = gmres(mv, b_global, restart=restart, max_iterations=iters, tolerance=0.0, reorthogonalize=True)
+                xl = np.zeros(n_local, dtype)
+                ig = op.gmres(np.ascontiguousarray(b_global[offsets[rank]: offsets[rank + 1]]), xl, restart=restart, max_iterations=iters, tolerance=0.0,
+                              orthogonalization=capi.HTB_GMRES_CGS2)
+                assert ig["iterations"] == io["iterations"] == iters and ig["matvecs"] == io["matvecs"], (ig, io)
+                assert abs(ig["true_relative_residual"] - io["true_relative_residual"]) <= 1e-9 * max(1.0, io["true_relative_residual"]), (ig, io)
+                errs.append(1e-4 * err(xl, xo[offsets[rank]: offsets[rank + 1]]))  # iterates agree to 1e-8
         op.close()
 
     worst = torch.tensor([max(errs)], dtype=torch.float64, device=dev)
