@@ -402,14 +402,17 @@ def run_ours(args):
         b_d = torch.from_numpy(b_host).cuda()
         xs_d = torch.zeros(n_local, dtype=tdt, device="cuda")
         op.gmres(b_d.data_ptr(), xs_d.data_ptr(), mem_kind=capi.HTB_MEM_DEVICE, restart=40, max_iterations=5, tolerance=0.0, compute_true_residual=0)  # warm-up (allocations)
-        xs_d.zero_()
         barrier()
         t0 = time.perf_counter()
-        gi = op.gmres(b_d.data_ptr(), xs_d.data_ptr(), mem_kind=capi.HTB_MEM_DEVICE, restart=40, max_iterations=args.gmres_iterations, tolerance=0.0, compute_true_residual=1)
+        n_mv, n_it, n_solves, worst = 0, 0, 0, 0.0
+        while n_mv < args.gmres_iterations:  # well-conditioned operator: a solve converges in a few iterations, so solve repeatedly
+            xs_d.zero_()
+            gi = op.gmres(b_d.data_ptr(), xs_d.data_ptr(), mem_kind=capi.HTB_MEM_DEVICE, restart=40, max_iterations=100, tolerance=1e-10, compute_true_residual=1)
+            n_mv, n_it, n_solves, worst = n_mv + gi["matvecs"], n_it + gi["iterations"], n_solves + 1, max(worst, gi["true_relative_residual"])
         barrier()
         dt = time.perf_counter() - t0
-        gm = {"iterations": gi["iterations"], "matvecs": gi["matvecs"], "restart": 40, "seconds": dt, "matvec_per_s_inside_solver": gi["matvecs"] / dt,
-              "fraction_of_bare_matvec_rate": (gi["matvecs"] / dt) / value, "true_relative_residual": gi["true_relative_residual"], "orthogonalization": "cgs"}
+        gm = {"solves": n_solves, "iterations": n_it, "matvecs": n_mv, "restart": 40, "tolerance": 1e-10, "seconds": dt, "matvec_per_s_inside_solver": n_mv / dt,
+              "fraction_of_bare_matvec_rate": (n_mv / dt) / value, "worst_true_relative_residual": worst, "orthogonalization": "cgs"}
 
     # ---- algorithmic bytes: s*C + s*mu*(n_src + n_tgt), descriptors excluded -------------
     coeffs = torch.tensor([float(oinfo["coefficients"])], device="cuda", dtype=torch.float64)

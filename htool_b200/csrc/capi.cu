@@ -688,10 +688,10 @@ int htb_destroy(htb_handle h) {
         cudaStreamSynchronize(h->own_stream);
     for (void *p : h->owned)
         cudaFree(p);
-    for (void *p : {h->d_mscratch, h->d_scratch, h->d_in, h->d_out, h->d_perm[0], h->d_perm[1], h->d_work_in, h->d_work_out})
+    for (void *p : {h->d_mscratch, h->d_scratch, h->d_in, h->d_out, h->d_perm[0], h->d_perm[1], h->d_work_in, h->d_work_out, h->d_krylov})
         if (p)
             cudaFree(p);
-    for (void *p : {h->h_in, h->h_out})
+    for (void *p : {h->h_in, h->h_out, h->h_krylov})
         if (p)
             cudaFreeHost(p);
     for (cudaEvent_t ev : h->chunk_events)
@@ -709,7 +709,7 @@ int htb_get_info(htb_handle h, htb_info *info) {
     info->dist_gather      = dist_gather_mode(h);
     info->store_bytes      = static_cast<int64_t>(h->store_bytes);
     info->descriptor_bytes = static_cast<int64_t>(h->descriptor_bytes);
-    info->workspace_bytes  = static_cast<int64_t>(h->workspace_bytes + h->in_cap + h->out_cap + h->work_cap * 2);
+    info->workspace_bytes  = static_cast<int64_t>(h->workspace_bytes + h->in_cap + h->out_cap + h->work_cap * 2 + h->krylov_cap);
     return HTB_OK;
 }
 

@@ -161,22 +161,34 @@ struct Solver {
     hc *hpin = nullptr; // pinned host mirror of hdev
     int64_t matvecs = 0, launches = 0;
 
-    ~Solver() {
-        for (void *p : {static_cast<void *>(V), static_cast<void *>(w), static_cast<void *>(x), static_cast<void *>(b), static_cast<void *>(partial), static_cast<void *>(hdev)})
-            if (p)
-                cudaFree(p);
-        if (hpin)
-            cudaFreeHost(hpin);
-    }
+    // one device allocation and one pinned block, owned by the handle and kept between solves
     int alloc() {
         ldv = (n + 1) & ~size_t(1);
-        HTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&V), sizeof(T) * ldv * (m + 1)));
-        HTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&w), sizeof(T) * ldv));
-        HTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&x), sizeof(T) * ldv));
-        HTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&b), sizeof(T) * ldv));
-        HTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&partial), sizeof(T) * grid * (m + 2)));
-        HTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&hdev), sizeof(T) * (m + 2)));
-        HTB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&hpin), sizeof(hc) * 2 * (m + 2)));
+        const size_t need = sizeof(T) * (ldv * (m + 4) + static_cast<size_t>(grid) * (m + 2) + (m + 2)), pin = sizeof(hc) * 2 * (m + 2);
+        if (need > h->krylov_cap) {
+            if (h->d_krylov)
+                cudaFree(h->d_krylov);
+            h->d_krylov   = nullptr;
+            h->krylov_cap = 0;
+            HTB_CUDA(cudaMalloc(&h->d_krylov, need));
+            h->krylov_cap = need;
+        }
+        if (pin > h->krylov_pin_cap) {
+            if (h->h_krylov)
+                cudaFreeHost(h->h_krylov);
+            h->h_krylov       = nullptr;
+            h->krylov_pin_cap = 0;
+            HTB_CUDA(cudaMallocHost(&h->h_krylov, pin));
+            h->krylov_pin_cap = pin;
+        }
+        T *p    = static_cast<T *>(h->d_krylov);
+        V       = p, p += ldv * (m + 1);
+        w       = p, p += ldv;
+        x       = p, p += ldv;
+        b       = p, p += ldv;
+        partial = p, p += static_cast<size_t>(grid) * (m + 2);
+        hdev    = p;
+        hpin    = static_cast<hc *>(h->h_krylov);
         return HTB_OK;
     }
     // out = A in (device, local numbering). Distributed: what GMV asks the reference for, here without leaving the device

@@ -70,6 +70,9 @@ struct htb_operator {
     size_t store_bytes = 0, descriptor_bytes = 0, workspace_bytes = 0;
     htb_info info{};
     htb::DistState *dist = nullptr;
+    // Krylov workspace (gmres.cu), grown on demand and kept between solves
+    void *d_krylov = nullptr, *h_krylov = nullptr;
+    size_t krylov_cap = 0, krylov_pin_cap = 0;
 };
 
 namespace htb {
