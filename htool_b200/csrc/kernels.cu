@@ -313,6 +313,109 @@ __device__ __forceinline__ void reduce_unit(const Unit &un, const T *data, const
     }
 }
 
+// ---- fused APPLY + REDUCE of one unit (symmetric storage, second application) ---------------------------------------
+// One walk over the panel serves both products: every 128-bit shared-memory load of P feeds y[i] += op(P[i,k]) c[k]
+// (accumulated per lane in acc) AND t'[k] = sum_i op2(P[i,k]) x2[i] (per-lane products folded by the transposing
+// butterfly). Same lane / segment geometry as reduce_batch; column k belongs to segment k mod G in both.
+template <typename T, bool CONJ, bool CONJ2, int J>
+__device__ __forceinline__ void fused_batch(const T *P, uint32_t ld, uint32_t w, uint32_t kb, const LaneMap &m, const uint32_t (&off)[kMaxQ], const T (&xv)[kMaxQ][Rows<T>::R],
+                                            const T *c, T (&acc)[kMaxQ][Rows<T>::R], T *out) {
+    constexpr int R = Rows<T>::R;
+    T v[J];
+#pragma unroll
+    for (int cc = 0; cc < J; cc++) {
+        const uint32_t k  = kb + (cc << m.logG) + m.g;
+        const bool valid  = k < w;
+        const uint32_t kc = valid ? k : w - 1;
+        const T *col      = P + kc * ld;
+        const T ck        = valid ? c[kc] : zero_of(T{});
+        T f[R];
+        load_rows(col + off[0], f);
+        T s = mul(cj<CONJ2>(f[0]), xv[0][0]);
+        if (R > 1)
+            s = fma_(cj<CONJ2>(f[R - 1]), xv[0][R - 1], s);
+#pragma unroll
+        for (int r = 0; r < R; r++)
+            acc[0][r] = fma_(cj<CONJ>(f[r]), ck, acc[0][r]);
+        if (m.Q > 1) {
+            load_rows(col + off[1], f);
+            s = fma_(cj<CONJ2>(f[0]), xv[1][0], s);
+            if (R > 1)
+                s = fma_(cj<CONJ2>(f[R - 1]), xv[1][R - 1], s);
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                acc[1][r] = fma_(cj<CONJ>(f[r]), ck, acc[1][r]);
+        }
+        v[cc] = s;
+    }
+    int cbase, nv, lowmask;
+    seg_reduce<T, J>(v, m.seglog, m.li, cbase, nv, lowmask);
+    if ((m.li & lowmask) == 0) {
+        if (nv == 1) {
+            const uint32_t k = kb + (cbase << m.logG) + m.g;
+            if (k < w)
+                out[k] = v[0];
+        } else {
+#pragma unroll
+            for (int cc = 0; cc < J; cc++) {
+                const uint32_t k = kb + ((cbase + cc) << m.logG) + m.g;
+                if (cc < nv && k < w)
+                    out[k] = v[cc];
+            }
+        }
+    }
+}
+
+template <typename T, bool CONJ, bool CONJ2>
+__device__ __forceinline__ void fused_unit(const Unit &un, const T *data, const T *c, const T *xin, T *yacc, T *scratch2, int lane) {
+    constexpr int R = Rows<T>::R;
+    const uint32_t row0 = unit_row0(un.geom), h = unit_h(un.geom), w = unit_w(un.geom);
+    T *out            = scratch2 + un.out;
+    const T *P        = data + un.data_off;
+    const uint32_t ld = unit_ld(h, sizeof(T));
+    const LaneMap m   = lane_map<R>(h, lane);
+    uint32_t off[kMaxQ];
+    T xv[kMaxQ][R], acc[kMaxQ][R];
+#pragma unroll
+    for (int qq = 0; qq < kMaxQ; qq++) {
+        const uint32_t i0 = R * (m.li + 32u * qq);
+        off[qq]           = i0 < ld ? i0 : 0u;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            xv[qq][r]  = i0 + r < h ? xin[row0 + i0 + r] : zero_of(T{});
+            acc[qq][r] = zero_of(T{});
+        }
+    }
+    for (uint32_t kb = 0; kb < w;) {
+        const uint32_t per_seg = (w - kb + (1u << m.logG) - 1u) >> m.logG;
+        if (per_seg > 4) {
+            fused_batch<T, CONJ, CONJ2, 8>(P, ld, w, kb, m, off, xv, c, acc, out);
+            kb += 8u << m.logG;
+        } else if (per_seg > 2) {
+            fused_batch<T, CONJ, CONJ2, 4>(P, ld, w, kb, m, off, xv, c, acc, out);
+            kb += 4u << m.logG;
+        } else {
+            fused_batch<T, CONJ, CONJ2, 2>(P, ld, w, kb, m, off, xv, c, acc, out);
+            kb += 2u << m.logG;
+        }
+    }
+    // y: the G segments worked on interleaved columns, fold them, then one lane per row adds into the warp's accumulator
+    for (int d = 1 << m.seglog; d < 32; d <<= 1)
+#pragma unroll
+        for (int r = 0; r < R; r++)
+            acc[0][r] = add(acc[0][r], shfl_xor(acc[0][r], d));
+    if (m.g == 0) {
+#pragma unroll
+        for (int qq = 0; qq < kMaxQ; qq++)
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const uint32_t i = R * (m.li + 32u * qq) + r;
+                if (i < h && (qq == 0 || m.Q > 1))
+                    yacc[row0 + i] = add(yacc[row0 + i], acc[qq][r]);
+            }
+    }
+}
+
 // ---- REDUCE -------------------------------------------------------------------------------------------
 template <typename T, bool CONJ>
 __global__ void __launch_bounds__(kThreads) reduce_kernel(KernelSide ks, PassArgs<T> a) {
@@ -389,7 +492,7 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(KernelSide ks, PassArg
 // of the leaves stored once are ALSO reduced against the second input (t' = op2(P)^T x2): the transposed second
 // application reads the side's coefficients from the same bulk copy instead of streaming them again.
 template <typename T, bool CONJ, bool FUSED, bool CONJ2>
-__global__ void __launch_bounds__(kThreads, (FUSED && sizeof(T) == 16) ? 2 : 0) apply_kernel(KernelSide ks, PassArgs<T> a) {
+__global__ void __launch_bounds__(kThreads, FUSED ? (sizeof(T) == 16 ? 2 : 3) : 0) apply_kernel(KernelSide ks, PassArgs<T> a) {
     constexpr int R = Rows<T>::R;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const BlockDesc bd = ks.blocks[ks.order[blockIdx.x]];
@@ -449,6 +552,10 @@ __global__ void __launch_bounds__(kThreads, (FUSED && sizeof(T) == 16) ? 2 : 0) 
                 const Unit un = units[u];
                 if (a.twice_only && !unit_twice(un.geom))
                     continue;
+                if (FUSED && unit_twice(un.geom)) { // both applications from one walk over the panel
+                    fused_unit<T, CONJ, CONJ2>(un, data, cseg + un.cslot, xin, yacc, a.scratch2, lane);
+                    continue;
+                }
                 const uint32_t row0 = unit_row0(un.geom), h = unit_h(un.geom), w = unit_w(un.geom);
                 const T *c = cseg + un.cslot;
                 const T *P        = data + un.data_off;
@@ -518,8 +625,6 @@ __global__ void __launch_bounds__(kThreads, (FUSED && sizeof(T) == 16) ? 2 : 0) 
                                 yacc[row0 + i] = add(yacc[row0 + i], acc[qq][r]);
                         }
                 }
-                if (FUSED && unit_twice(un.geom))
-                    reduce_unit<T, CONJ2>(un, data, xin, a.scratch2, lane);
             }
             ubase = (ubase - hdr.n_panel) & (kConsumerWarps - 1);
             __syncwarp();

@@ -65,6 +65,8 @@ Packer::Packer(const htb_hmatrix_desc &desc, const PackOptions &o) : dtype(desc.
         opt.block_rows = esize == 8 ? 128 : 64;
     if ((opt.block_rows != 32 && opt.block_rows != 64 && opt.block_rows != 128) || static_cast<size_t>(opt.block_rows) * esize > 1024)
         throw std::runtime_error("block_rows must be 32, 64 or 128 (32 or 64 for complex)");
+    if (opt.target_block_rows != 0 && opt.target_block_rows != 32 && opt.target_block_rows != 64 && opt.target_block_rows != 128)
+        throw std::runtime_error("target_block_rows must be 0 (automatic), 32, 64 or 128");
     if (opt.stage_bytes % 16 || opt.cseg_bytes % 16 || opt.stage_bytes > 65536 || opt.piece_cols < 1 || opt.piece_cols > 32)
         throw std::runtime_error("invalid piece_cols / stage_bytes / cseg_bytes");
     // a unit (block_rows x piece) and its descriptor must fit one stage; its c vector one c segment
@@ -208,8 +210,10 @@ Packer::Packer(const htb_hmatrix_desc &desc, const PackOptions &o) : dtype(desc.
 // long on this side) is split, whenever such a point exists within reach: for the nested ranges of a
 // cluster tree this yields cluster-aligned blocks, so small leaves are never split.
 void Packer::make_blocks(int s) {
-    const int n  = side[s].n;
-    const int BR = opt.block_rows;
+    const int n = side[s].n;
+    int BR      = opt.block_rows;
+    if (s == 0 && opt.target_block_rows > 0)
+        BR = std::min(opt.block_rows, opt.target_block_rows);
     std::vector<int32_t> cost(static_cast<size_t>(n) + 2, 0);
     for (int64_t i = 0; i < n_leaves; i++) {
         const htb_leaf &l = m_leaves[i];

@@ -156,6 +156,11 @@ struct PackOptions {
     int piece_cols  = 16;    // columns of a unit (<= 32); lowered automatically so that a unit fits a stage
     int stage_bytes = 24576; // bulk-copy granule of the coefficient stream, multiple of 16
     int cseg_bytes  = 2048;  // capacity of a stage's c segment, multiple of 16
+    // Side 0 (target rows) may use smaller blocks than side 1 (0 = same as block_rows). Tried for the row strips of a
+    // distributed operator (few target rows, all the source columns: 1024 APPLY blocks = 2.3 waves at 8 GPUs): halving
+    // the target blocks speeds APPLY up by 8 % but the extra chunks cost the same in COMBINE (gpurun_out/t32), so the
+    // default keeps one height; the knob stays for experiments.
+    int target_block_rows = 0;
 };
 
 // Host description of one side, produced by the packer. Device copies are owned by the handle.

@@ -114,6 +114,19 @@ def test_packer_options(opts):
             capi.set_option(k, v)
 
 
+def test_target_side_block_height():
+    """Side 0 may be cut into smaller blocks than side 1 (store.hpp: PackOptions.target_block_rows); products stay the same."""
+    flat = random_flatcase(seed=8, nb_rows=900, nb_cols=700, n_leaves=200, max_dim=400)
+    try:
+        assert PackedSide(flat.desc, 0).blocks["nrows"].max() > 64
+        for tb in (64, 32):
+            capi.set_option("target_block_rows", tb)
+            assert PackedSide(flat.desc, 0).blocks["nrows"].max() <= tb < PackedSide(flat.desc, 1).blocks["nrows"].max()
+            _check(flat)
+    finally:
+        capi.set_option("target_block_rows", 0)
+
+
 def test_stream_invariants():
     flat, _, _ = load_golden("d_N")
     for s in (0, 1):
