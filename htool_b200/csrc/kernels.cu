@@ -112,6 +112,9 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
+// barrier among the consumer warps only (the producer warp is busy streaming)
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory"); }
+
 struct KernelSide {
     const BlockDesc *blocks;
     const StageDesc *stages;
@@ -429,6 +432,14 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(KernelSide ks, PassArg
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     init_barriers(ks, sm);
+    __syncthreads();
+    // the producer starts streaming coefficients at once: the first bulk copies are in flight while the consumers
+    // wait for / stage the block's x sub-vector (a consumer-only named barrier orders that hand-off)
+    if (warp == kConsumerWarps) {
+        if (lane == 0)
+            produce<T, false>(ks, bd, sm, a.twice_only, nullptr);
+        return;
+    }
     if (a.wait_flags) { // distributed: the slice of x this block reads is written by its owner's push kernel (dist.cu)
         if (threadIdx.x == 0) {
             const uint32_t ow = a.wait_owner[ks.order[blockIdx.x]];
@@ -437,20 +448,14 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(KernelSide ks, PassArg
                     while (ld_acquire_sys(a.wait_flags + q) < a.wait_epoch)
                         __nanosleep(64);
         }
-        __syncthreads();
+        consumer_barrier();
     }
     // stage the block's x sub-vector in shared memory (every unit of the block multiplies a slice of it)
-    for (int i = threadIdx.x; i < ks.block_rows; i += kThreads) {
+    for (int i = threadIdx.x; i < ks.block_rows; i += kConsumerWarps * 32) {
         const long long g = static_cast<long long>(bd.row_start) + i + a.in_shift;
         xin[i]            = (i < bd.nrows && g >= 0 && g < a.in_len) ? a.in[g * a.stride] : zero_of(T{});
     }
-    __syncthreads();
-
-    if (warp == kConsumerWarps) {
-        if (lane == 0)
-            produce<T, false>(ks, bd, sm, a.twice_only, nullptr);
-        return;
-    }
+    consumer_barrier();
 
     // Every warp walks every stage (in the producer's order); the units are dealt round-robin over the warps ACROSS
     // stages (ubase), so that a stage with few units does not always land on the same warps.
@@ -505,21 +510,24 @@ __global__ void __launch_bounds__(kThreads, FUSED ? (sizeof(T) == 16 ? 2 : 3) : 
     T *xin      = yacc_all + static_cast<size_t>(ks.block_rows) * kConsumerWarps; // FUSED only
 
     init_barriers(ks, sm);
-    for (int i = threadIdx.x; i < ks.block_rows * kConsumerWarps; i += kThreads)
-        yacc_all[i] = zero_of(T{});
-    if (FUSED) {
-        for (int i = threadIdx.x; i < ks.block_rows; i += kThreads) {
-            const long long g = static_cast<long long>(bd.row_start) + i + a.in_shift;
-            xin[i]            = (i < bd.nrows && g >= 0 && g < a.in_len) ? a.in[g * a.stride] : zero_of(T{});
-        }
-    }
     __syncthreads();
 
     if (warp == kConsumerWarps) {
         if (lane == 0)
             produce<T, true>(ks, bd, sm, a.twice_only, a.scratch + ks.cs_base);
     } else {
+        // (the producer is already streaming) every warp clears its own accumulator; FUSED: the consumers stage x2
         T *yacc = yacc_all + static_cast<size_t>(warp) * ks.block_rows;
+        for (int i = lane; i < ks.block_rows; i += 32)
+            yacc[i] = zero_of(T{});
+        if (FUSED) {
+            for (int i = threadIdx.x; i < ks.block_rows; i += kConsumerWarps * 32) {
+                const long long g = static_cast<long long>(bd.row_start) + i + a.in_shift;
+                xin[i]            = (i < bd.nrows && g >= 0 && g < a.in_len) ? a.in[g * a.stride] : zero_of(T{});
+            }
+            consumer_barrier();
+        }
+        __syncwarp();
         // Every warp walks every stage; units are dealt round-robin over the warps across stages. The deal is a
         // function of the stream only, so the split of the y contributions over the warps (hence the rounding) is
         // the same in every run.

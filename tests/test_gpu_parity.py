@@ -222,3 +222,54 @@ def test_live_reference(capi, kw, have_ref):
     op.add_vector_product("N", 1.0, 2.0 * x1 - 3.0 * x2, 0.0, y12)
     assert rel_err(y12, 2.0 * y1 - 3.0 * y2) < 1e-11
     op.close()
+
+
+def test_full_size_properties(capi, have_ref):
+    """BASELINE.json configs[1] at FULL size (Laplace N = 1e6, eps = 1e-4): parity against the reference's OpenMP product
+    on the same compressed HMatrix, plus size-independent properties of the GPU path alone — linearity in x, the
+    beta term, the adjoint identity <H x, y> = <x, H^T y> through the transposed passes, bit-reproducibility, and the
+    device-pointer path agreeing with the host-pointer path."""
+    if not have_ref:
+        pytest.skip("oracle/_ref did not travel with the repo")
+    import torch
+
+    import bench
+    from oracle import refharness as R
+
+    R.set_num_threads(__import__("os").cpu_count() or 1)
+    args = __import__("argparse").Namespace(n=1_000_000, dtype="double", symmetry="N", mu=1, gpus=1)
+    case = R.RefCase(**bench.case_kwargs(args))
+    n = case.nb_rows
+    op = capi.Operator(case.desc)
+    assert op.info()["coefficients"] == case.info()["coefficients"] > 2_000_000_000
+    rng = np.random.default_rng(17)
+    x1, x2, w = rng.random(n) - 0.5, rng.random(n) - 0.5, rng.random(n) - 0.5
+    y1, y2, y12, yr = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n)
+    op.add_vector_product("N", 1.0, x1, 0.0, y1)
+    case.vector_product("N", 1.0, x1, 0.0, yr, variant="openmp")
+    assert rel_err(y1, yr) < TOL
+    op.add_vector_product("N", 1.0, x2, 0.0, y2)
+    op.add_vector_product("N", 1.0, 2.0 * x1 - 3.0 * x2, 0.0, y12)
+    assert rel_err(y12, 2.0 * y1 - 3.0 * y2) < 1e-11  # linearity
+    yb = w.copy()
+    op.add_vector_product("N", 0.5, x1, -2.0, yb)
+    assert rel_err(yb, 0.5 * y1 - 2.0 * w) < 1e-11  # alpha / beta
+    z = np.zeros(n)
+    op.add_vector_product("T", 1.0, w, 0.0, z)
+    lhs, rhs = float(y1 @ w), float(x1 @ z)
+    assert abs(lhs - rhs) <= 1e-10 * (np.linalg.norm(y1) * np.linalg.norm(w))  # adjoint identity: REDUCE/APPLY roles swapped
+    again = np.zeros(n)
+    op.add_vector_product("N", 1.0, x1, 0.0, again)
+    assert np.array_equal(again, y1)  # fixed summation order
+    xd, yd = torch.from_numpy(x1).cuda(), torch.zeros(n, dtype=torch.float64, device="cuda")
+    op.add_vector_product_device("N", 1.0, xd.data_ptr(), 0.0, yd.data_ptr())
+    op.synchronize()
+    assert np.array_equal(yd.cpu().numpy(), y1)
+    # multi-RHS at full size on the tensor-core path: column c of the result equals the single-RHS product of column c
+    mu = 8
+    X = np.ascontiguousarray(np.stack([x1, x2, w, x1 + x2, x1 - w, 2 * x2, -x1, w + x2], axis=1))
+    Y = np.zeros((n, mu))
+    op.add_matrix_product_row_major("N", 1.0, X.reshape(-1), 0.0, Y.reshape(-1), mu)
+    assert rel_err(Y[:, 0], y1) < TOL and rel_err(Y[:, 1], y2) < TOL
+    assert rel_err(Y[:, 3], y1 + y2) < 1e-11
+    op.close()
