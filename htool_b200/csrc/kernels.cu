@@ -303,7 +303,7 @@ __device__ __forceinline__ void reduce_unit(const Unit &un, const T *data, const
     }
     for (uint32_t kb = 0; kb < w;) {
         const uint32_t per_seg = (w - kb + (1u << m.logG) - 1u) >> m.logG; // columns left for each segment
-        if (per_seg > 4) {
+        if (sizeof(T) == 8 && per_seg > 4) { // (complex: batches of 4 at most, 8 complex partial sums cost an occupancy step)
             reduce_batch<T, CONJ, 8>(P, ld, w, kb, m, off, xv, out);
             kb += 8u << m.logG;
         } else if (per_seg > 2) {
@@ -391,7 +391,7 @@ __device__ __forceinline__ void fused_unit(const Unit &un, const T *data, const 
     }
     for (uint32_t kb = 0; kb < w;) {
         const uint32_t per_seg = (w - kb + (1u << m.logG) - 1u) >> m.logG;
-        if (per_seg > 4) {
+        if (sizeof(T) == 8 && per_seg > 4) {
             fused_batch<T, CONJ, CONJ2, 8>(P, ld, w, kb, m, off, xv, c, acc, out);
             kb += 8u << m.logG;
         } else if (per_seg > 2) {
@@ -421,7 +421,7 @@ __device__ __forceinline__ void fused_unit(const Unit &un, const T *data, const 
 
 // ---- REDUCE -------------------------------------------------------------------------------------------
 template <typename T, bool CONJ>
-__global__ void __launch_bounds__(kThreads) reduce_kernel(KernelSide ks, PassArgs<T> a) {
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 16 ? 3 : 0) reduce_kernel(KernelSide ks, PassArgs<T> a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const BlockDesc bd = ks.blocks[ks.order[blockIdx.x]];
     const uint32_t n_my_stages = a.twice_only ? bd.n_twice_stages : bd.n_stages;
