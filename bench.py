@@ -496,7 +496,7 @@ def run_ours(args):
                          "other_kernels_ms_per_step": {"reduce": reduce_ms_step, "apply": apply_ms_step, "combine": pt["combine"]["ms"] / prof_steps}},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "matvec/s", "h2d_bytes_per_step": int(esize * mu * n_global), "d2h_bytes_per_step": int(esize * mu * n_global), "ms_per_step": 1e3 * e2e_s / args.steps,
-                    "host_buffers": "page-locked (htb_host_register), direct DMA", "pageable_value": args.steps / e2e_pageable_s},
+                    "host_buffers": "page-locked and mapped (htb_host_register): the kernels read x from and write y to the host vectors over PCIe inside the product (zero copy, mu = 1)" if mu == 1 else "page-locked (htb_host_register), direct DMA", "pageable_value": args.steps / e2e_pageable_s},
             "gmres": gm,
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -547,13 +547,27 @@ int htb_dist_add_product_local_to_local(htb_handle h, char trans, const void *al
     if (trans == 'N') {
         if ((rc = p2p_ensure_buffers(h, d, n_global * es)) != HTB_OK)
             return rc;
-        if (mem_kind == HTB_MEM_HOST) {
+        // zero copy (single RHS, page-locked mapped host vectors, peer-memory gather): the push kernel reads x_local from
+        // the host buffer and the APPLY epilogue writes y_local into it, no staging copies
+        void *zc_in = nullptr, *zc_out = nullptr;
+        if (mem_kind == HTB_MEM_HOST && mu == 1 && d->p2p && option_value("zero_copy") != 0) {
+            zc_in  = mapped_device_pointer(in_local);
+            zc_out = mapped_device_pointer(out_local);
+            if (!zc_in || !zc_out)
+                zc_in = zc_out = nullptr;
+        }
+        if (zc_in) {
+            mem_kind = HTB_MEM_DEVICE;
+            in_local = zc_in;
+            dout     = zc_out;
+        } else if (mem_kind == HTB_MEM_HOST) {
             if ((rc = ensure_staging(h, n_local * es, n_local * es)) != HTB_OK)
                 return rc;
             if (!beta_zero && (rc = staged_h2d(h, h->d_out, h->h_out, out_local, n_local * es, st)) != HTB_OK)
                 return rc;
             dout = h->d_out;
         }
+        const bool zero_copy = zc_in != nullptr;
         DistSplit split;
         split.world = d->world;
         if (d->p2p) {
@@ -601,6 +615,10 @@ int htb_dist_add_product_local_to_local(htb_handle h, char trans, const void *al
         }
         if ((rc = product_device(h, 'N', alpha, xg, beta, dout, mu, &split)) != HTB_OK)
             return rc;
+        if (zero_copy) { // the caller's host vector is the output: complete before returning
+            HTB_CUDA(cudaStreamSynchronize(st));
+            return HTB_OK;
+        }
     } else {
         // T / C (add_distributed_operator_vector_product_local_to_local.hpp:47-87): z = alpha op(H_strip)^T x_local has the
         // GLOBAL length; slice r of z goes to rank r (MPI_Alltoallv there, grouped ncclSend / ncclRecv here), and the owner

@@ -201,6 +201,14 @@ def main():
             xs = x_local * (1.0 + it)  # a different x every time: a stale buffer would show
             op.dist_add_product_local_to_local(alpha, xs, beta, y, mu)
             errs.append(err((y - beta * y0) / (1.0 + it) + beta * y0))
+        # page-locked host vectors (htb_host_register): zero copy when mu == 1 and the gather goes through peer memory
+        x_pin, y_pin = x_local.copy(), y0.copy()
+        capi.host_register(x_pin)
+        capi.host_register(y_pin)
+        op.dist_add_product_local_to_local(alpha, x_pin, beta, y_pin, mu)
+        errs.append(err(y_pin))
+        capi.host_unregister(x_pin)
+        capi.host_unregister(y_pin)
         x_d, y_d = torch.from_numpy(x_local).cuda(), torch.from_numpy(y0.copy()).cuda()
         op.dist_add_product_local_to_local(alpha, x_d.data_ptr(), beta, y_d.data_ptr(), mu, capi.HTB_MEM_DEVICE)
         op.synchronize()

@@ -273,3 +273,37 @@ def test_full_size_properties(capi, have_ref):
     assert rel_err(Y[:, 0], y1) < TOL and rel_err(Y[:, 1], y2) < TOL
     assert rel_err(Y[:, 3], y1 + y2) < 1e-11
     op.close()
+
+
+@pytest.mark.parametrize("name", ["d_N", "d_SL", "z_HU"])
+def test_page_locked_host_vectors_zero_copy(capi, name):
+    """htb_host_register: the kernels then read x from / write y to the caller's HOST buffers directly (zero copy, mu = 1),
+    or DMA them without staging (zero_copy = 0, mu > 1). Same bits as the pageable path."""
+    flat, entries, _ = load_golden(name)
+    op = capi.Operator(flat.desc)
+    for e in entries:
+        y_page = e["y_in"].copy()
+        x_pin, y_pin = e["x"].copy(), e["y_in"].copy()
+
+        def run(x, y):
+            if e["mu"] == 1:
+                op.add_vector_product(e["trans"], e["alpha"], x, e["beta"], y)
+            else:
+                op.add_matrix_product_row_major(e["trans"], e["alpha"], x, e["beta"], y, e["mu"])
+
+        run(e["x"], y_page)
+        capi.host_register(x_pin)
+        capi.host_register(y_pin)
+        try:
+            run(x_pin, y_pin)
+            assert np.array_equal(y_pin, y_page)
+            capi.set_option("zero_copy", 0)
+            y_pin[:] = e["y_in"]
+            run(x_pin, y_pin)
+            assert np.array_equal(y_pin, y_page)
+        finally:
+            capi.set_option("zero_copy", 1)
+            capi.host_unregister(x_pin)
+            capi.host_unregister(y_pin)
+        assert rel_err(y_page, e["y_seq"]) < TOL
+    op.close()
