@@ -27,6 +27,30 @@ inline bool check(int status, const char *where) {
     return false;
 }
 
+/// RAII page-lock of a caller-owned host buffer (htb_host_register): while it lives, products given pointers inside
+/// [ptr, ptr + n) touch the buffer directly from the kernels (single RHS: zero copy over PCIe) or by DMA without
+/// staging. Meant for the vectors a Krylov solver reuses for every product of a solve (HPDDM's work vectors around
+/// HPDDMOperator::GMV, wrappers/wrapper_hpddm.hpp:118-124).
+template <typename T>
+class PinnedHostBuffer {
+    T *m_ptr = nullptr;
+
+  public:
+    PinnedHostBuffer(T *ptr, std::size_t n) {
+        if (ptr != nullptr && n > 0 && check(htb_host_register(ptr, n * sizeof(T)), "htb_host_register")) {
+            m_ptr = ptr;
+        }
+    }
+    ~PinnedHostBuffer() {
+        if (m_ptr != nullptr) {
+            htb_host_unregister(m_ptr);
+        }
+    }
+    PinnedHostBuffer(const PinnedHostBuffer &)            = delete;
+    PinnedHostBuffer &operator=(const PinnedHostBuffer &) = delete;
+    bool is_pinned() const { return m_ptr != nullptr; }
+};
+
 /// The leaf store of `hmatrix` on one B200: flattened with flatten() and uploaded once, at construction
 /// (north_star item 1). The HMatrix can be destroyed afterwards: nothing on the host is referenced again.
 template <typename CoefficientPrecision, typename CoordinatePrecision = htool::underlying_type<CoefficientPrecision>>
