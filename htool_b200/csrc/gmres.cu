@@ -92,16 +92,20 @@ __global__ void __launch_bounds__(kDotThreads) multi_dot_kernel(const T *V, size
     }
 }
 
-// out[k] = sum_b partial[b * nk + k] in block order (fixed: deterministic)
+// out[k] = sum_b partial[b * nk + k]: one warp per k, lane l sums blocks l, l + 32, ... and a butterfly folds the lanes
+// (a fixed order that depends only on n_blocks: deterministic)
 template <typename T>
 __global__ void fold_partials_kernel(const T *partial, int n_blocks, int nk, T *out) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (k >= nk)
         return;
     T s = g_zero(T{});
-    for (int b = 0; b < n_blocks; b++)
+    for (int b = lane; b < n_blocks; b += 32)
         s = g_add(s, partial[static_cast<size_t>(b) * nk + k]);
-    out[k] = s;
+    for (int d = 16; d >= 1; d >>= 1)
+        s = g_add(s, g_shfl(s, d));
+    if (lane == 0)
+        out[k] = s;
 }
 
 // w[i] += sign * sum_k V[k][i] * c[k]
@@ -155,7 +159,7 @@ struct Solver {
     htb_operator *h;
     cudaStream_t st;
     size_t n, ldv;
-    int m, grid;
+    int m, grid, hcap = 0; // hcap: entries of hdev / of each half of hpin
     bool distributed;
     T *V = nullptr, *w = nullptr, *x = nullptr, *b = nullptr, *partial = nullptr, *hdev = nullptr;
     hc *hpin = nullptr; // pinned host mirror of hdev
@@ -164,7 +168,8 @@ struct Solver {
     // one device allocation and one pinned block, owned by the handle and kept between solves
     int alloc() {
         ldv = (n + 1) & ~size_t(1);
-        const size_t need = sizeof(T) * (ldv * (m + 4) + static_cast<size_t>(grid) * (m + 2) + (m + 2)), pin = sizeof(hc) * 2 * (m + 2);
+        hcap              = 2 * (m + 2) + 2;
+        const size_t need = sizeof(T) * (ldv * (m + 4) + static_cast<size_t>(grid) * (m + 2) + hcap), pin = sizeof(hc) * 2 * hcap;
         if (need > h->krylov_cap) {
             if (h->d_krylov)
                 cudaFree(h->d_krylov);
@@ -199,26 +204,31 @@ struct Solver {
             return htb_dist_add_product_local_to_local(h, 'N', one, in, zero, out, 1, HTB_MEM_DEVICE);
         return htb_add_vector_product(h, 'N', one, in, zero, out, HTB_MEM_DEVICE);
     }
-    // hdev[0..nk) = <V_k, vec> summed over the ranks; mirrored to hpin (synchronises)
-    int dots(const T *basis, int nk, const T *vec) {
+    // hdev[at .. at + nk) = <basis_k, vec> summed over the ranks, left on the device (no synchronisation)
+    int dots_async(const T *basis, int nk, const T *vec, int at) {
         multi_dot_kernel<T><<<grid, kDotThreads, 0, st>>>(basis, ldv, nk, vec, n, partial);
-        fold_partials_kernel<T><<<(nk + 63) / 64, 64, 0, st>>>(partial, grid, nk, hdev);
+        fold_partials_kernel<T><<<(nk + 3) / 4, 128, 0, st>>>(partial, grid, nk, hdev + at);
         HTB_CUDA(cudaGetLastError());
         launches += 2;
-        int rc = dist_allreduce_sum(h, reinterpret_cast<double *>(hdev), size_t(nk) * sizeof(T) / sizeof(double), st);
-        if (rc != HTB_OK)
-            return rc;
+        return dist_allreduce_sum(h, reinterpret_cast<double *>(hdev + at), size_t(nk) * sizeof(T) / sizeof(double), st);
+    }
+    // hpin[0 .. count) <- hdev[0 .. count): the ONE synchronisation of an iteration
+    int fetch(int count) {
         if (sizeof(T) == sizeof(double)) {
-            double *tmp = reinterpret_cast<double *>(hpin + (m + 2)); // second half of the pinned block
-            HTB_CUDA(cudaMemcpyAsync(tmp, hdev, sizeof(double) * nk, cudaMemcpyDeviceToHost, st));
+            double *tmp = reinterpret_cast<double *>(hpin + hcap); // second half of the pinned block
+            HTB_CUDA(cudaMemcpyAsync(tmp, hdev, sizeof(double) * count, cudaMemcpyDeviceToHost, st));
             HTB_CUDA(cudaStreamSynchronize(st));
-            for (int k = 0; k < nk; k++)
+            for (int k = 0; k < count; k++)
                 hpin[k] = hc(tmp[k], 0.);
         } else {
-            HTB_CUDA(cudaMemcpyAsync(hpin, hdev, sizeof(hc) * nk, cudaMemcpyDeviceToHost, st));
+            HTB_CUDA(cudaMemcpyAsync(hpin, hdev, sizeof(hc) * count, cudaMemcpyDeviceToHost, st));
             HTB_CUDA(cudaStreamSynchronize(st));
         }
         return HTB_OK;
+    }
+    int dots(const T *basis, int nk, const T *vec) {
+        int rc = dots_async(basis, nk, vec, 0);
+        return rc != HTB_OK ? rc : fetch(nk);
     }
     int norm(const T *vec, double *out) {
         int rc = dots(vec, 1, vec);
@@ -242,9 +252,9 @@ struct Solver {
         launches++;
         return HTB_OK;
     }
-    // vec -= sum_k hdev[k] basis_k with the coefficients already on the device (straight after dots())
-    int axpys_device(const T *basis, int nk, T *vec) {
-        multi_axpy_kernel<T><<<grid, 256, sizeof(T) * nk, st>>>(basis, ldv, nk, hdev, -1., vec, n);
+    // vec -= sum_k hdev[at + k] basis_k with the coefficients already on the device (straight after dots_async())
+    int axpys_device(const T *basis, int nk, T *vec, int at = 0) {
+        multi_axpy_kernel<T><<<grid, 256, sizeof(T) * nk, st>>>(basis, ldv, nk, hdev + at, -1., vec, n);
         HTB_CUDA(cudaGetLastError());
         launches++;
         return HTB_OK;
@@ -281,6 +291,7 @@ int gmres(htb_operator *h, const void *rhs, void *x0, const htb_gmres_options &o
     if ((rc = s.norm(s.b, &bnorm)) != HTB_OK)
         return rc;
     const int m = s.m;
+    const bool eager_sync = option_value("gmres_eager_sync") != 0;
     std::vector<hc> H(static_cast<size_t>(m + 1) * m), g(m + 1), sn(m), y(m);
     std::vector<double> cs(m);
     int it = 0, converged = 0;
@@ -310,26 +321,28 @@ int gmres(htb_operator *h, const void *rhs, void *x0, const htb_gmres_options &o
             T *vj = s.V + static_cast<size_t>(j) * s.ldv;
             if ((rc = s.matvec(vj, s.w)) != HTB_OK)
                 return rc;
-            // classical Gram-Schmidt: all projections from ONE pass over w, then one update pass
-            if ((rc = s.dots(s.V, j + 1, s.w)) != HTB_OK)
+            // classical Gram-Schmidt: all projections from ONE pass over w, one update pass, then the norm; the
+            // coefficients stay on the device between the passes and reach the host in ONE copy per iteration
+            const int nk = j + 1;
+            if ((rc = s.dots_async(s.V, nk, s.w, 0)) != HTB_OK)
+                return rc;
+            if (eager_sync && (rc = s.fetch(nk)) != HTB_OK) // experiment knob: the host waits for the projections first
+                return rc;
+            if ((rc = s.axpys_device(s.V, nk, s.w, 0)) != HTB_OK)
+                return rc;
+            int at = nk;
+            if (opt.orthogonalization == HTB_GMRES_CGS2) { // second pass ("twice is enough")
+                if ((rc = s.dots_async(s.V, nk, s.w, at)) != HTB_OK || (rc = s.axpys_device(s.V, nk, s.w, at)) != HTB_OK)
+                    return rc;
+                at += nk;
+            }
+            if ((rc = s.dots_async(s.w, 1, s.w, at)) != HTB_OK || (rc = s.fetch(at + 1)) != HTB_OK)
                 return rc;
             hc *Hj = &H[static_cast<size_t>(j) * (m + 1)];
-            for (int k = 0; k <= j; k++)
-                Hj[k] = s.hpin[k];
-            if ((rc = s.axpys_device(s.V, j + 1, s.w)) != HTB_OK)
-                return rc;
-            if (opt.orthogonalization == HTB_GMRES_CGS2) { // second pass ("twice is enough")
-                if ((rc = s.dots(s.V, j + 1, s.w)) != HTB_OK)
-                    return rc;
-                for (int k = 0; k <= j; k++)
-                    Hj[k] += s.hpin[k];
-                if ((rc = s.axpys_device(s.V, j + 1, s.w)) != HTB_OK)
-                    return rc;
-            }
-            double hn = 0.;
-            if ((rc = s.norm(s.w, &hn)) != HTB_OK)
-                return rc;
-            Hj[j + 1] = hn;
+            for (int k = 0; k < nk; k++)
+                Hj[k] = s.hpin[k] + (opt.orthogonalization == HTB_GMRES_CGS2 ? s.hpin[nk + k] : hc(0.));
+            const double hn = std::sqrt(std::max(0., s.hpin[at].real()));
+            Hj[j + 1]       = hn;
             if (hn > 0. && (rc = s.scale_copy(s.w, 1. / hn, s.V + static_cast<size_t>(j + 1) * s.ldv)) != HTB_OK)
                 return rc;
             // Givens rotations on the new column, then the one that annihilates H[j+1][j]
