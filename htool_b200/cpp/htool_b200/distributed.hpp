@@ -9,9 +9,10 @@
 //
 // DeviceDistributedOperator is the alternative for one process per GPU: same strip (built exactly as
 // DefaultApproximationBuilder does, distributed_operator/utility.hpp:56), same partition object, same MPI
-// communicator for the bootstrap only (one MPI_Bcast of the 128-byte NCCL id); afterwards the exchange of x /
-// of the partial results runs over NVLink with NCCL, overlapped with the local-source leaves
-// (htb_dist_add_product_local_to_local / htb_dist_add_product_global_to_global). The free functions below have
+// communicator for the bootstrap only (one MPI_Bcast of the 128-byte NCCL id); afterwards the exchange runs over
+// NVLink: for 'N' a push kernel stores the rank's slice of x into every peer's buffer (CUDA IPC peer mappings) and the
+// product's first pass waits block by block for the slices it needs; T / C and global-to-global use NCCL
+// (htb_dist_add_product_local_to_local / htb_dist_add_product_global_to_global, htool_b200/csrc/dist.cu). The free functions below have
 // the reference's names and argument meaning so that call sites (HPDDMOperator::GMV,
 // wrappers/wrapper_hpddm.hpp:118-124) only change the operator type; `work` is accepted and ignored.
 #ifndef HTOOL_B200_DISTRIBUTED_HPP
@@ -73,6 +74,17 @@ class DeviceDistributedOperator {
         if (m_ready) {
             check(htb_dist_add_product_local_to_local(m_data.get(), trans, &alpha, in, &beta, out, mu, HTB_MEM_HOST), "htb_dist_add_product_local_to_local");
         }
+    }
+    /// Unpreconditioned restarted GMRES with the Krylov loop resident on the device (htb_gmres): the counterpart of
+    /// DDM::solve with "-hpddm_schwarz_method none" (solvers/ddm.hpp:134-193). rhs / x: this rank's slices in partition
+    /// numbering; x = initial guess on entry. options == nullptr: HPDDM's defaults (restart 40, 100 iterations, 1e-6).
+    htb_gmres_result solve(const CoefficientPrecision *rhs, CoefficientPrecision *x, const htb_gmres_options *options = nullptr) const {
+        htb_gmres_result result{};
+        result.true_relative_residual = -1.;
+        if (m_ready) {
+            check(htb_gmres(m_data.get(), rhs, x, options, &result, HTB_MEM_HOST), "htb_gmres");
+        }
+        return result;
     }
     void global_to_global(char trans, CoefficientPrecision alpha, const CoefficientPrecision *in, CoefficientPrecision beta, CoefficientPrecision *out, int mu) const {
         if (m_ready) {

@@ -270,6 +270,25 @@ int run(htb_ref::Case<T> &c, double *results, int n_results) {
                     htool_b200::internal_add_distributed_operator_matrix_product_row_major_local_to_local(trans, alpha, DA, xv.data(), beta, ygm.data(), mu);
                     upd(DEVICE_DIST, rel_err(ygm, std::vector<T>(Yrr.data(), Yrr.data() + size_t(NT) * mu)));
                 }
+                // device-resident GMRES through the twin; the residual is measured with the REFERENCE's product
+                if (NS == NT) {
+                    htb_gmres_options gopt;
+                    htb_gmres_default_options(&gopt);
+                    gopt.tolerance = 1e-8;
+                    auto b         = rnd_vector<T>(gen, NT);
+                    std::vector<T> xs(NS, T(0)), r = b, work(2 * size_t(NS + NT));
+                    const htb_gmres_result gr = DA.solve(b.data(), xs.data(), &gopt);
+                    if (gr.converged) {
+                        internal_add_distributed_operator_vector_product_local_to_local('N', T(-1), RA, xs.data(), T(1), r.data(), work.data());
+                        double rn = 0, bn = 0;
+                        for (int i = 0; i < NT; i++) {
+                            rn += std::norm(r[i]);
+                            bn += std::norm(b[i]);
+                        }
+                        const double rel = std::sqrt(rn / bn);
+                        upd(DEVICE_DIST, rel < 1e-7 ? 0. : rel);
+                    }
+                }
             } else {
                 upd(DEVICE_DIST, 1.);
             }
