@@ -28,7 +28,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 namespace {
 std::mutex g_option_mutex;
 std::map<std::string, int64_t> g_options = {
-    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 2048}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 5}, {"m_reduce_ring_stages", 5}, {"mrhs_min", 8}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"gmres_eager_sync", 0}};
+    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 2048}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 5}, {"m_reduce_ring_stages", 5}, {"mrhs_min", 8}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"gmres_eager_sync", 0}, {"tail_split", 1}, {"cta_slots", 0}};
 
 int64_t option(const char *key) {
     std::lock_guard<std::mutex> lock(g_option_mutex);
@@ -620,6 +620,14 @@ int htb_create(const htb_hmatrix_desc *desc, htb_handle *out) {
     popt.stage_bytes = static_cast<int>(option("stage_bytes"));
     popt.cseg_bytes  = static_cast<int>(option("cseg_bytes"));
     popt.target_block_rows = static_cast<int>(option("target_block_rows"));
+    popt.tail_split        = static_cast<int>(option("tail_split"));
+    {
+        cudaDeviceProp dp;
+        if (cudaGetDeviceProperties(&dp, device) == cudaSuccess)
+            popt.cta_slots = dp.multiProcessorCount * 3;
+        if (option("cta_slots") > 0) // tests
+            popt.cta_slots = static_cast<int>(option("cta_slots"));
+    }
     std::unique_ptr<Packer> pk;
     try {
         pk = std::make_unique<Packer>(*desc, popt);
@@ -903,6 +911,9 @@ int htb_pack_host(const htb_hmatrix_desc *desc, int side, htb_packed_side *out) 
     popt.stage_bytes = static_cast<int>(option("stage_bytes"));
     popt.cseg_bytes  = static_cast<int>(option("cseg_bytes"));
     popt.target_block_rows = static_cast<int>(option("target_block_rows"));
+    popt.tail_split        = static_cast<int>(option("tail_split"));
+    if (option("cta_slots") > 0)
+        popt.cta_slots = static_cast<int>(option("cta_slots"));
     try {
         Packer pk(*desc, popt);
         auto *own   = new PackedOwner();

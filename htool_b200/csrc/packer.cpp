@@ -214,37 +214,56 @@ void Packer::make_blocks(int s) {
     int BR      = opt.block_rows;
     if (s == 0 && opt.target_block_rows > 0)
         BR = std::min(opt.block_rows, opt.target_block_rows);
-    std::vector<int32_t> cost(static_cast<size_t>(n) + 2, 0);
-    for (int64_t i = 0; i < n_leaves; i++) {
-        const htb_leaf &l = m_leaves[i];
-        if (!active(l))
-            continue;
-        int a = start_of(s, l), len = extent_of(s, l);
-        if (len >= 2 && len <= BR) {
-            cost[a + 1]++;
-            cost[a + len]--;
-        }
-    }
-    for (int i = 1; i <= n; i++)
-        cost[i] += cost[i - 1];
     std::vector<int32_t> &start = m_block_start[s];
+    // appends the cut points of [from, to) for blocks of <= br indices
+    auto cut_range = [&](int from, int to, int br) {
+        std::vector<int32_t> cost(static_cast<size_t>(n) + 2, 0);
+        for (int64_t i = 0; i < n_leaves; i++) {
+            const htb_leaf &l = m_leaves[i];
+            if (!active(l))
+                continue;
+            int a = start_of(s, l), len = extent_of(s, l);
+            if (len >= 2 && len <= br) {
+                cost[a + 1]++;
+                cost[a + len]--;
+            }
+        }
+        for (int i = 1; i <= n; i++)
+            cost[i] += cost[i - 1];
+        int c = from;
+        while (c < to) {
+            int limit = std::min(to, c + br);
+            int p     = limit;
+            if (limit < to) {
+                for (int q = limit; q > c; q--)
+                    if (cost[q] == 0) {
+                        p = q;
+                        break;
+                    }
+            }
+            start.push_back(p);
+            c = p;
+        }
+    };
     start.clear();
     start.push_back(0);
-    int c = 0;
-    while (c < n) {
-        int limit = std::min(n, c + BR);
-        int p     = limit;
-        if (limit < n) {
-            for (int q = limit; q > c; q--)
-                if (cost[q] == 0) {
-                    p = q;
-                    break;
-                }
+    cut_range(0, n, BR);
+    // Tail split (side 0 of a small shard, e.g. a row strip of a distributed operator): APPLY blocks are nearly uniform,
+    // so nb blocks over `cta_slots` resident CTAs run as floor(nb / slots) full rounds plus a last round of r blocks
+    // during which most SMs idle (1024 blocks on 444 slots: 2.31 rounds, the last one at a third of the bandwidth).
+    // The rows of those last r blocks are re-cut into quarter-height blocks: they sort last in the heaviest-first launch
+    // order and fill every slot, so the tail streams at full rate.
+    const int slots = opt.cta_slots, small = std::max(32, BR / 4);
+    int nb = static_cast<int>(start.size()) - 1;
+    if (s == 0 && opt.tail_split && slots > 0 && nb > slots && nb <= 6 * slots && small < BR) {
+        const int r = nb % slots;
+        if (r > 0 && r * 5 <= slots * 4) {
+            const int tail_from = start[nb - r];
+            start.resize(static_cast<size_t>(nb - r) + 1);
+            cut_range(tail_from, n, small);
+            nb = static_cast<int>(start.size()) - 1;
         }
-        start.push_back(p);
-        c = p;
     }
-    const int nb = static_cast<int>(start.size()) - 1;
     side[s].blocks.assign(nb, BlockDesc{});
     m_blk_of[s].assign(static_cast<size_t>(n) + 1, 0);
     for (int b = 0; b < nb; b++) {

@@ -161,6 +161,10 @@ struct PackOptions {
     // the target blocks speeds APPLY up by 8 % but the extra chunks cost the same in COMBINE (gpurun_out/t32), so the
     // default keeps one height; the knob stays for experiments.
     int target_block_rows = 0;
+    // Tail split of side 0 (packer.cpp: make_blocks): quarter-height blocks for the rows of the last, partial round of
+    // APPLY CTAs when the side has between 1 and 6 rounds of blocks. cta_slots = resident APPLY CTAs of the device.
+    int tail_split = 1;
+    int cta_slots  = 148 * 3;
 };
 
 // Host description of one side, produced by the packer. Device copies are owned by the handle.

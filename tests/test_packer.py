@@ -127,6 +127,29 @@ def test_target_side_block_height():
         capi.set_option("target_block_rows", 0)
 
 
+def test_tail_split_of_target_blocks():
+    """Side 0 of a shard with a partial last round of APPLY CTAs: the rows of that round are re-cut into quarter-height
+    blocks (packer.cpp: make_blocks); the product does not change."""
+    flat = random_flatcase(seed=9, nb_rows=1000, nb_cols=700, n_leaves=220, max_dim=400)
+    try:
+        capi.set_option("tail_split", 0)
+        plain = PackedSide(flat.desc, 0)
+        nb = plain.n_blocks
+        slots = next(sl for sl in range(3, nb) if 0 < nb % sl <= 0.8 * sl and nb <= 6 * sl)
+        capi.set_option("tail_split", 1)
+        capi.set_option("cta_slots", slots)
+        split = PackedSide(flat.desc, 0)
+        r = nb % slots
+        assert split.n_blocks > nb
+        assert np.array_equal(split.blocks["row_start"][: nb - r], plain.blocks["row_start"][: nb - r])  # full rounds untouched
+        assert split.blocks["nrows"][nb - r:].max() <= 32
+        assert PackedSide(flat.desc, 1).n_blocks == (lambda: (capi.set_option("tail_split", 0), PackedSide(flat.desc, 1).n_blocks, capi.set_option("tail_split", 1))[1])()
+        _check(flat)
+    finally:
+        capi.set_option("tail_split", 1)
+        capi.set_option("cta_slots", 0)
+
+
 def test_stream_invariants():
     flat, _, _ = load_golden("d_N")
     for s in (0, 1):
