@@ -441,7 +441,7 @@ def run_ours(args):
     dom = "apply" if apply_ms_step >= reduce_ms_step else "reduce"
     dom_bytes, dom_ms = (apply_bytes, apply_ms_step) if dom == "apply" else (reduce_bytes, reduce_ms_step)
     dom_achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    roof = {"bound": "hbm", "kernel": f"{dom}_kernel<double, false>" if dtype == np.float64 else f"{dom}_kernel<cplx, false>", "achieved": dom_achieved, "peak": peak,
+    roof = {"bound": "hbm", "kernel": f"{dom}_kernel<{'double' if dtype == np.float64 else 'cplx'}>" + (" (fused with the second application's REDUCE)" if (dom == "apply" and args.symmetry != "N") else ""), "achieved": dom_achieved, "peak": peak,
             "unit": "GB/s", "frac": dom_achieved / peak, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms}
     if dtype == np.float64 and mu >= 8 and world == 1:
         # multi-RHS: the leaves are batched contractions on the FP64 tensor cores (mkernels.cu); flops = 2 mu C

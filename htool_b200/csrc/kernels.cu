@@ -678,7 +678,9 @@ __global__ void combine_kernel(const CombineEntry *entries, const CombineDst *ds
     T v = zero_of(T{});
     if (k < len) {
         const T *p = scratch + ce.src + k;
-#pragma unroll 4
+        // (deep unroll: the loads are independent, the adds keep their order; a piece of a 32k-row leaf sums 256 partials
+        // and the slowest warp sets the duration of this latency-bound kernel)
+#pragma unroll 16
         for (uint32_t j = jg; j < n_sum; j += G)
             v = add(v, p[static_cast<size_t>(j) * len]);
     }
