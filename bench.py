@@ -398,21 +398,24 @@ def run_ours(args):
     # (extra key, not the headline: HPDDM is absent from the reference tree, so there is no reference arm for the solver)
     gm = None
     if args.gmres_iterations > 0 and mu == 1:
-        b_host = seeded_x(n_local, dtype, seed=2 + rank)
-        b_d = torch.from_numpy(b_host).cuda()
-        xs_d = torch.zeros(n_local, dtype=tdt, device="cuda")
-        op.gmres(b_d.data_ptr(), xs_d.data_ptr(), mem_kind=capi.HTB_MEM_DEVICE, restart=40, max_iterations=5, tolerance=0.0, compute_true_residual=0)  # warm-up (allocations)
-        barrier()
-        t0 = time.perf_counter()
-        n_mv, n_it, n_solves, worst = 0, 0, 0, 0.0
-        while n_mv < args.gmres_iterations:  # well-conditioned operator: a solve converges in a few iterations, so solve repeatedly
-            xs_d.zero_()
-            gi = op.gmres(b_d.data_ptr(), xs_d.data_ptr(), mem_kind=capi.HTB_MEM_DEVICE, restart=40, max_iterations=100, tolerance=1e-10, compute_true_residual=1)
-            n_mv, n_it, n_solves, worst = n_mv + gi["matvecs"], n_it + gi["iterations"], n_solves + 1, max(worst, gi["true_relative_residual"])
-        barrier()
-        dt = time.perf_counter() - t0
-        gm = {"solves": n_solves, "iterations": n_it, "matvecs": n_mv, "restart": 40, "tolerance": 1e-10, "seconds": dt, "matvec_per_s_inside_solver": n_mv / dt,
-              "fraction_of_bare_matvec_rate": (n_mv / dt) / value, "worst_true_relative_residual": worst, "orthogonalization": "cgs"}
+        try:
+            b_host = seeded_x(n_local, dtype, seed=2 + rank)
+            b_d = torch.from_numpy(b_host).cuda()
+            xs_d = torch.zeros(n_local, dtype=tdt, device="cuda")
+            op.gmres(b_d.data_ptr(), xs_d.data_ptr(), mem_kind=capi.HTB_MEM_DEVICE, restart=40, max_iterations=5, tolerance=0.0, compute_true_residual=0)  # warm-up (allocations)
+            barrier()
+            t0 = time.perf_counter()
+            n_mv, n_it, n_solves, worst = 0, 0, 0, 0.0
+            while n_mv < args.gmres_iterations:  # well-conditioned operator: a solve converges in a few iterations, so solve repeatedly
+                xs_d.zero_()
+                gi = op.gmres(b_d.data_ptr(), xs_d.data_ptr(), mem_kind=capi.HTB_MEM_DEVICE, restart=40, max_iterations=100, tolerance=1e-10, compute_true_residual=1)
+                n_mv, n_it, n_solves, worst = n_mv + gi["matvecs"], n_it + gi["iterations"], n_solves + 1, max(worst, gi["true_relative_residual"])
+            barrier()
+            dt = time.perf_counter() - t0
+            gm = {"solves": n_solves, "iterations": n_it, "matvecs": n_mv, "restart": 40, "tolerance": 1e-10, "seconds": dt, "matvec_per_s_inside_solver": n_mv / dt,
+                  "fraction_of_bare_matvec_rate": (n_mv / dt) / value, "worst_true_relative_residual": worst, "orthogonalization": "cgs"}
+        except Exception as ex:  # an extra key must never cost the headline line
+            gm = {"error": str(ex)}
 
     # ---- algorithmic bytes: s*C + s*mu*(n_src + n_tgt), descriptors excluded -------------
     coeffs = torch.tensor([float(oinfo["coefficients"])], device="cuda", dtype=torch.float64)

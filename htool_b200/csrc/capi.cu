@@ -28,7 +28,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 namespace {
 std::mutex g_option_mutex;
 std::map<std::string, int64_t> g_options = {
-    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 2048}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 5}, {"m_reduce_ring_stages", 5}, {"mrhs_min", 8}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"gmres_eager_sync", 0}, {"tail_split", 1}, {"cta_slots", 0}};
+    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 2048}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 5}, {"m_reduce_ring_stages", 5}, {"mrhs_min", 8}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}};
 
 int64_t option(const char *key) {
     std::lock_guard<std::mutex> lock(g_option_mutex);
@@ -671,6 +671,7 @@ int htb_create(const htb_hmatrix_desc *desc, htb_handle *out) {
     if (h->m_path_ok)
         HTB_CUDA(configure_mkernels(h->launch_cfg));
     h->mscratch_elems  = pk->mscratch_elems;
+    g_pdl              = option("pdl") != 0;
     h->fused_symmetric = option("fused_symmetric") != 0 && fused_smem_bytes(h->launch_cfg, 16) <= static_cast<size_t>(prop.sharedMemPerBlockOptin);
     HTB_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;

@@ -14,8 +14,10 @@
 // ||b||, 100 iterations) and is checked against oracle/gmres_oracle.py: "parity unpinned" for bit-level agreement with
 // HPDDM, pinned for the solution (tests/test_gpu_gmres.py). Defaults follow HPDDM's.
 //
-// Kernels: multi_dot (h_k = <v_k, w> for all k <= j in one pass over w, per-CTA partials folded in a fixed order:
-// deterministic), multi_axpy (w -= sum_k h_k v_k in one pass), scale. All bandwidth-bound over (j+2) n elements, small
+// Kernels: multi_dot (h_k = <v_k, w> for all k <= j AND <w, w> in one pass over w, per-CTA partials folded in a fixed
+// order: deterministic; ONE sum over the ranks and ONE host synchronisation per iteration, the norm of the projected
+// vector comes from Pythagoras with an explicit fallback under cancellation), multi_axpy (w -= sum_k h_k v_k in one
+// pass), scale. All bandwidth-bound over (j+2) n elements, small
 // next to the product (N = 1e6: 20 GB per product vs <= 0.35 GB per orthogonalisation at restart 40).
 #include "handle.hpp"
 
@@ -291,7 +293,6 @@ int gmres(htb_operator *h, const void *rhs, void *x0, const htb_gmres_options &o
     if ((rc = s.norm(s.b, &bnorm)) != HTB_OK)
         return rc;
     const int m = s.m;
-    const bool eager_sync = option_value("gmres_eager_sync") != 0;
     std::vector<hc> H(static_cast<size_t>(m + 1) * m), g(m + 1), sn(m), y(m);
     std::vector<double> cs(m);
     int it = 0, converged = 0;
@@ -318,32 +319,40 @@ int gmres(htb_operator *h, const void *rhs, void *x0, const htb_gmres_options &o
         int j = 0;
         for (; j < m && it < opt.max_iterations; j++) {
             it++;
-            T *vj = s.V + static_cast<size_t>(j) * s.ldv;
-            if ((rc = s.matvec(vj, s.w)) != HTB_OK)
+            T *vj = s.V + static_cast<size_t>(j) * s.ldv, *vn = vj + s.ldv; // w = A v_j is produced in the slot of v_{j+1}
+            if ((rc = s.matvec(vj, vn)) != HTB_OK)
                 return rc;
-            // classical Gram-Schmidt: all projections from ONE pass over w, one update pass, then the norm; the
-            // coefficients stay on the device between the passes and reach the host in ONE copy per iteration
+            // Classical Gram-Schmidt with ONE reduction per pass: the basis handed to the dot kernel is v_0 .. v_j AND w
+            // itself, so a single pass over w (and a single sum over the ranks) yields the projections h_k = <v_k, w> and
+            // <w, w>; the norm of the projected vector then follows from Pythagoras, ||w - V h||^2 = ||w||^2 - ||h||^2
+            // (V orthonormal). The coefficients stay on the device for the update pass and reach the host in ONE copy.
             const int nk = j + 1;
-            if ((rc = s.dots_async(s.V, nk, s.w, 0)) != HTB_OK)
+            if ((rc = s.dots_async(s.V, nk + 1, vn, 0)) != HTB_OK || (rc = s.axpys_device(s.V, nk, vn, 0)) != HTB_OK)
                 return rc;
-            if (eager_sync && (rc = s.fetch(nk)) != HTB_OK) // experiment knob: the host waits for the projections first
-                return rc;
-            if ((rc = s.axpys_device(s.V, nk, s.w, 0)) != HTB_OK)
-                return rc;
-            int at = nk;
-            if (opt.orthogonalization == HTB_GMRES_CGS2) { // second pass ("twice is enough")
-                if ((rc = s.dots_async(s.V, nk, s.w, at)) != HTB_OK || (rc = s.axpys_device(s.V, nk, s.w, at)) != HTB_OK)
+            int at = nk + 1;
+            const bool cgs2 = opt.orthogonalization == HTB_GMRES_CGS2;
+            if (cgs2) { // second pass ("twice is enough"), same single reduction
+                if ((rc = s.dots_async(s.V, nk + 1, vn, at)) != HTB_OK || (rc = s.axpys_device(s.V, nk, vn, at)) != HTB_OK)
                     return rc;
-                at += nk;
+                at += nk + 1;
             }
-            if ((rc = s.dots_async(s.w, 1, s.w, at)) != HTB_OK || (rc = s.fetch(at + 1)) != HTB_OK)
+            if ((rc = s.fetch(at)) != HTB_OK)
                 return rc;
             hc *Hj = &H[static_cast<size_t>(j) * (m + 1)];
             for (int k = 0; k < nk; k++)
-                Hj[k] = s.hpin[k] + (opt.orthogonalization == HTB_GMRES_CGS2 ? s.hpin[nk + k] : hc(0.));
-            const double hn = std::sqrt(std::max(0., s.hpin[at].real()));
-            Hj[j + 1]       = hn;
-            if (hn > 0. && (rc = s.scale_copy(s.w, 1. / hn, s.V + static_cast<size_t>(j + 1) * s.ldv)) != HTB_OK)
+                Hj[k] = s.hpin[k] + (cgs2 ? s.hpin[nk + 1 + k] : hc(0.));
+            const hc *last = s.hpin + (cgs2 ? nk + 1 : 0); // coefficients of the LAST projection pass and <w, w> before it
+            const double ww = last[nk].real();
+            double hh = 0.;
+            for (int k = 0; k < nk; k++)
+                hh += std::norm(last[k]);
+            double hn = 0.;
+            if (ww - hh > 1e-2 * ww)
+                hn = std::sqrt(ww - hh);
+            else if ((rc = s.norm(vn, &hn)) != HTB_OK) // cancellation (w almost inside the Krylov space): explicit norm
+                return rc;
+            Hj[j + 1] = hn;
+            if (hn > 0. && (rc = s.scale_copy(vn, 1. / hn, vn)) != HTB_OK)
                 return rc;
             // Givens rotations on the new column, then the one that annihilates H[j+1][j]
             for (int k = 0; k < j; k++) {

@@ -26,6 +26,8 @@
 
 namespace htb {
 
+bool g_pdl = true; // programmatic dependent launch of the pass kernels (option "pdl", read at htb_create)
+
 namespace {
 
 constexpr int kConsumerWarps = 8;
@@ -114,6 +116,10 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 
 // barrier among the consumer warps only (the producer warp is busy streaming)
 __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory"); }
+
+// programmatic dependent launch (see launch_pdl): let the successor be scheduled / wait for the predecessor's results
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 struct KernelSide {
     const BlockDesc *blocks;
@@ -432,6 +438,8 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 16 ? 3 : 0) reduce_kern
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     init_barriers(ks, sm);
+    pdl_launch_dependents();
+    pdl_wait(); // everything below reads or writes vectors / scratch shared with the previous kernel of the stream
     __syncthreads();
     // the producer starts streaming coefficients at once: the first bulk copies are in flight while the consumers
     // wait for / stage the block's x sub-vector (a consumer-only named barrier orders that hand-off)
@@ -510,6 +518,8 @@ __global__ void __launch_bounds__(kThreads, FUSED ? (sizeof(T) == 16 ? 2 : 3) : 
     T *xin      = yacc_all + static_cast<size_t>(ks.block_rows) * kConsumerWarps; // FUSED only
 
     init_barriers(ks, sm);
+    pdl_launch_dependents();
+    pdl_wait(); // the c-stream and the partials were written by the previous kernels of the stream
     __syncthreads();
 
     if (warp == kConsumerWarps) {
@@ -667,6 +677,8 @@ template <typename T>
 __global__ void combine_kernel(const CombineEntry *entries, const CombineDst *dsts, int n, T *scratch, int twice_only) {
     const int warps_per_block = blockDim.x >> 5;
     const int e               = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    pdl_launch_dependents();
+    pdl_wait();
     if (e >= n)
         return;
     const CombineEntry ce = entries[e];
@@ -735,6 +747,24 @@ __global__ void wait_flags_kernel(const unsigned long long *flags, int world, un
             __nanosleep(64);
 }
 
+// Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream drains its last
+// wave; its CTAs set up their barriers, then block in griddepcontrol.wait until the predecessor has completed and
+// flushed (pdl_wait() below), so the launch latency and the CTA ramp-up at every pass boundary are hidden.
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim            = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim           = dim3(static_cast<unsigned>(block));
+    cfg.dynamicSmemBytes   = smem;
+    cfg.stream             = st;
+    cudaLaunchAttribute attr;
+    attr.id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cfg.attrs                                       = &attr;
+    cfg.numAttrs                                    = 1;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline KernelSide make_kernel_side(const SideDevice &s, const LaunchConfig &cfg, int ring) {
     return KernelSide{s.blocks, s.stages, s.order, s.stream, s.cs_base, cfg.block_rows, cfg.stage_bytes, cfg.cseg_bytes, ring, cfg.evict_first};
 }
@@ -746,12 +776,12 @@ template <typename T>
 struct Kernels;
 template <>
 struct Kernels<double> {
-    static void reduce(const KernelSide &ks, const PassArgs<double> &a, int grid, size_t smem, cudaStream_t st) { reduce_kernel<double, false><<<grid, kThreads, smem, st>>>(ks, a); }
+    static void reduce(const KernelSide &ks, const PassArgs<double> &a, int grid, size_t smem, cudaStream_t st) { launch_pdl(reduce_kernel<double, false>, grid, kThreads, smem, st, ks, a); }
     static void apply(const KernelSide &ks, const PassArgs<double> &a, int grid, size_t smem, cudaStream_t st) {
         if (a.fused)
-            apply_kernel<double, false, true, false><<<grid, kThreads, smem, st>>>(ks, a);
+            launch_pdl(apply_kernel<double, false, true, false>, grid, kThreads, smem, st, ks, a);
         else
-            apply_kernel<double, false, false, false><<<grid, kThreads, smem, st>>>(ks, a);
+            launch_pdl(apply_kernel<double, false, false, false>, grid, kThreads, smem, st, ks, a);
     }
     static cudaError_t configure(int rs, int as, int fs) {
         cudaError_t e;
@@ -766,22 +796,22 @@ template <>
 struct Kernels<cplx> {
     static void reduce(const KernelSide &ks, const PassArgs<cplx> &a, int grid, size_t smem, cudaStream_t st) {
         if (a.conj)
-            reduce_kernel<cplx, true><<<grid, kThreads, smem, st>>>(ks, a);
+            launch_pdl(reduce_kernel<cplx, true>, grid, kThreads, smem, st, ks, a);
         else
-            reduce_kernel<cplx, false><<<grid, kThreads, smem, st>>>(ks, a);
+            launch_pdl(reduce_kernel<cplx, false>, grid, kThreads, smem, st, ks, a);
     }
     static void apply(const KernelSide &ks, const PassArgs<cplx> &a, int grid, size_t smem, cudaStream_t st) {
         if (a.fused) { // (conj, conj2): (0,0) symmetric, (0,1) Hermitian 'N', (1,0) Hermitian 'C'
             if (a.conj)
-                apply_kernel<cplx, true, true, false><<<grid, kThreads, smem, st>>>(ks, a);
+                launch_pdl(apply_kernel<cplx, true, true, false>, grid, kThreads, smem, st, ks, a);
             else if (a.conj2)
-                apply_kernel<cplx, false, true, true><<<grid, kThreads, smem, st>>>(ks, a);
+                launch_pdl(apply_kernel<cplx, false, true, true>, grid, kThreads, smem, st, ks, a);
             else
-                apply_kernel<cplx, false, true, false><<<grid, kThreads, smem, st>>>(ks, a);
+                launch_pdl(apply_kernel<cplx, false, true, false>, grid, kThreads, smem, st, ks, a);
         } else if (a.conj)
-            apply_kernel<cplx, true, false, false><<<grid, kThreads, smem, st>>>(ks, a);
+            launch_pdl(apply_kernel<cplx, true, false, false>, grid, kThreads, smem, st, ks, a);
         else
-            apply_kernel<cplx, false, false, false><<<grid, kThreads, smem, st>>>(ks, a);
+            launch_pdl(apply_kernel<cplx, false, false, false>, grid, kThreads, smem, st, ks, a);
     }
     static cudaError_t configure(int rs, int as, int fs) {
         cudaError_t e;
@@ -853,7 +883,7 @@ cudaError_t launch_combine(const SideDevice &side, T *scratch, int twice_only, c
     if (side.n_combine == 0)
         return cudaSuccess;
     const int warps = 8;
-    combine_kernel<T><<<(side.n_combine + warps - 1) / warps, warps * 32, 0, stream>>>(side.combine, side.combine_dst, side.n_combine, scratch, twice_only);
+    launch_pdl(combine_kernel<T>, (side.n_combine + warps - 1) / warps, warps * 32, 0, stream, side.combine, side.combine_dst, side.n_combine, scratch, twice_only);
     return cudaGetLastError();
 }
 

@@ -88,6 +88,8 @@ cudaError_t launch_scale(T *y, long long n, T beta, cudaStream_t stream);
 // one warp spinning until flags[q] >= epoch for every q < world (peer-memory gather, multi-RHS path)
 cudaError_t launch_wait_flags(const unsigned long long *flags, int world, unsigned long long epoch, cudaStream_t stream);
 
+extern bool g_pdl; // programmatic dependent launch of the pass kernels (option "pdl")
+
 size_t reduce_smem_bytes(const LaunchConfig &cfg, size_t esize);
 size_t apply_smem_bytes(const LaunchConfig &cfg, size_t esize);
 size_t fused_smem_bytes(const LaunchConfig &cfg, size_t esize);
