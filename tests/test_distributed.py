@@ -38,6 +38,13 @@ def test_two_gloo_ranks_host_logic(extra, have_ref):
     _run("gloo", 2, extra)
 
 
+def test_four_gloo_ranks_host_logic(have_ref):
+    """Four row strips (unequal partition sizes, symmetric storage inside the diagonal blocks only)."""
+    if not have_ref:
+        pytest.skip("oracle/_ref is not built")
+    _run("gloo", 4, ["--points", "3500", "--sym", "S"])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("extra", [["--points", "20000"], ["--points", "16000", "--sym", "S"], ["--points", "12000", "--scalar", "complex", "--sym", "S"], ["--points", "8000", "--rhs", "3"],
                                    ["--points", "8000", "--rhs", "16"], ["--points", "16000", "--sym", "S", "--p2p", "0"], ["--points", "8000", "--rhs", "3", "--p2p", "0"]],
