@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--opt", action="append", default=[], help="packer/launch option key=value (htb_set_option)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gmres-iterations", type=int, default=200, help="BASELINE.json configs[4]: repeated matvecs inside a device-resident GMRES solve (0: skip)")
+    ap.add_argument("--gmres-dist", action="store_true", help="also run the GMRES section with N > 1 GPUs (off by default: the scaling runs time the product only)")
     return ap.parse_args()
 
 
@@ -397,7 +398,7 @@ def run_ours(args):
     # ---- BASELINE.json configs[4]: K repeated products inside a (device-resident) GMRES solve, restart 40 ---------------
     # (extra key, not the headline: HPDDM is absent from the reference tree, so there is no reference arm for the solver)
     gm = None
-    if args.gmres_iterations > 0 and mu == 1:
+    if args.gmres_iterations > 0 and mu == 1 and (world == 1 or args.gmres_dist):
         try:
             b_host = seeded_x(n_local, dtype, seed=2 + rank)
             b_d = torch.from_numpy(b_host).cuda()
