@@ -33,6 +33,40 @@ class DeviceDistributedOperator {
     int m_rank = 0, m_size = 1;
     bool m_ready = false;
 
+    /// true iff `local_ok` holds on EVERY rank of the communicator
+    bool agree(bool local_ok) const {
+        int mine = local_ok ? 1 : 0, all = 0;
+        MPI_Allreduce(&mine, &all, 1, MPI_INT, MPI_MIN, m_comm);
+        return all == 1;
+    }
+
+    /// The bootstrap is failure-COLLECTIVE: every rank takes part in every collective below whatever happened to it
+    /// locally, and the ranks agree (MPI_Allreduce MIN) on success after each step, so that no rank is ever left alone
+    /// inside MPI_Bcast / ncclCommInitRank / a later NCCL call or flag wait (the reference never leaves a rank inside a
+    /// collective alone either: its products have no per-rank early exit).
+    bool bootstrap() {
+        unsigned char id[HTB_NCCL_UNIQUE_ID_BYTES] = {0};
+        bool ok = m_data.is_valid();
+        if (m_rank == 0) {
+            ok = check(htb_nccl_get_unique_id(id), "htb_nccl_get_unique_id") && ok;
+        }
+        MPI_Bcast(id, HTB_NCCL_UNIQUE_ID_BYTES, MPI_UNSIGNED_CHAR, 0, m_comm);
+        if (!agree(ok)) {
+            return false;
+        }
+        std::vector<int32_t> offsets(m_size + 1, 0);
+        for (int r = 0; r < m_size; r++) {
+            offsets[r]     = m_partition.get_offset_of_partition(r);
+            offsets[r + 1] = offsets[r] + m_partition.get_size_of_partition(r);
+        }
+        ok             = check(htb_comm_init(m_data.get(), id, m_size, m_rank, offsets.data()), "htb_comm_init");
+        const bool all = agree(ok);
+        if (!all && ok) {
+            htb_comm_destroy(m_data.get());
+        }
+        return all;
+    }
+
   public:
     /// `strip` = this rank's block row, HMatrixTreeBuilder::build(generator, target, source, rank, rank)
     /// (distributed_operator/utility.hpp:56); `partition` = the partition of BOTH the target and the source
@@ -41,20 +75,7 @@ class DeviceDistributedOperator {
         : m_data(strip, device), m_partition(partition), m_comm(comm) {
         MPI_Comm_rank(comm, &m_rank);
         MPI_Comm_size(comm, &m_size);
-        if (!m_data.is_valid()) {
-            return;
-        }
-        unsigned char id[HTB_NCCL_UNIQUE_ID_BYTES] = {0};
-        if (m_rank == 0 && !check(htb_nccl_get_unique_id(id), "htb_nccl_get_unique_id")) {
-            return;
-        }
-        MPI_Bcast(id, HTB_NCCL_UNIQUE_ID_BYTES, MPI_UNSIGNED_CHAR, 0, comm);
-        std::vector<int32_t> offsets(m_size + 1, 0);
-        for (int r = 0; r < m_size; r++) {
-            offsets[r]     = partition.get_offset_of_partition(r);
-            offsets[r + 1] = offsets[r] + partition.get_size_of_partition(r);
-        }
-        m_ready = check(htb_comm_init(m_data.get(), id, m_size, m_rank, offsets.data()), "htb_comm_init");
+        m_ready = bootstrap();
     }
     ~DeviceDistributedOperator() {
         if (m_ready) {

@@ -440,13 +440,17 @@ int ensure_staging(htb_operator *h, size_t in_bytes, size_t out_bytes) {
 constexpr size_t kStageChunk = size_t(1) << 20;
 
 // Page-locked host memory (cudaMallocHost / cudaHostRegister / htb_host_register) is copied by the DMA engines directly
-bool is_pinned_host(const void *p) {
+// (both ends of the span are checked: a vector that starts inside a registered range but runs past its end must be staged)
+static bool is_pinned_host_byte(const void *p) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
         cudaGetLastError();
         return false;
     }
     return at.type == cudaMemoryTypeHost;
+}
+bool is_pinned_host(const void *p, size_t bytes) {
+    return is_pinned_host_byte(p) && (bytes <= 1 || is_pinned_host_byte(static_cast<const char *>(p) + bytes - 1));
 }
 
 // pageable -> pinned copy of one chunk, split over the OpenMP threads of the caller's process
@@ -461,7 +465,7 @@ void host_copy(char *dst, const char *src, size_t n) {
 }
 
 int staged_h2d(htb_operator *, void *dev, void *pinned, const void *host, size_t bytes, cudaStream_t st) {
-    if (is_pinned_host(host)) {
+    if (is_pinned_host(host, bytes)) {
         HTB_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, st));
         return HTB_OK;
     }
@@ -474,7 +478,7 @@ int staged_h2d(htb_operator *, void *dev, void *pinned, const void *host, size_t
 }
 
 int staged_d2h(htb_operator *h, void *host, void *pinned, const void *dev, size_t bytes, cudaStream_t st) {
-    if (is_pinned_host(host)) {
+    if (is_pinned_host(host, bytes)) {
         HTB_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, st));
         HTB_CUDA(cudaStreamSynchronize(st));
         return HTB_OK;
@@ -505,8 +509,8 @@ static bool beta_is_zero(const htb_operator *h, const void *beta) {
 }
 
 // Device address of a page-locked, mapped host buffer (cudaHostRegister / htb_host_register / cudaMallocHost), or nullptr
-void *mapped_device_pointer(const void *host) {
-    if (!is_pinned_host(host))
+void *mapped_device_pointer(const void *host, size_t bytes) {
+    if (!is_pinned_host(host, bytes))
         return nullptr;
     void *dev = nullptr;
     if (cudaHostGetDevicePointer(&dev, const_cast<void *>(host), 0) != cudaSuccess) {
@@ -526,7 +530,8 @@ static int product_host(htb_operator *h, char trans, const void *alpha, const vo
     // directly over PCIe — no H2D / D2H phase before and after the product, the 8 B per row ride along with the
     // 20 kB per row of coefficients streamed from HBM.
     if (mu == 1 && option("zero_copy") != 0) {
-        void *din = mapped_device_pointer(in), *dout = mapped_device_pointer(out);
+        void *din  = mapped_device_pointer(in, static_cast<size_t>(trans == 'N' ? h->nb_cols : h->nb_rows) * h->esize);
+        void *dout = mapped_device_pointer(out, static_cast<size_t>(trans == 'N' ? h->nb_rows : h->nb_cols) * h->esize);
         if (din && dout) {
             if ((rc = product_device(h, trans, alpha, din, beta, dout, 1)) != HTB_OK)
                 return rc;

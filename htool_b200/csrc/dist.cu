@@ -106,6 +106,10 @@ struct DistState {
     unsigned long long epoch            = 0;
     uint32_t *d_order_all = nullptr, *d_owner = nullptr;
     void *d_hbuf = nullptr; // handle exchange
+    // the WAR guard of the peer-memory gather assumes that a rank's push is ordered after its previous product; that is
+    // stream order as long as the caller keeps one stream, and this event when htb_set_stream switched streams in between
+    cudaEvent_t product_done    = nullptr;
+    cudaStream_t product_stream = nullptr;
 };
 
 static int nccl_fail(ncclResult_t r, const char *what) {
@@ -142,7 +146,13 @@ void dist_destroy(htb_operator *h) {
         return;
     if (d->comm_stream)
         cudaStreamSynchronize(d->comm_stream);
-    cudaStreamSynchronize(h->stream);
+    // (not h->stream: a caller-owned stream set with htb_set_stream may be gone by now; the event covers the last product)
+    if (d->product_done) {
+        cudaEventSynchronize(d->product_done);
+        cudaEventDestroy(d->product_done);
+    }
+    if (h->own_stream)
+        cudaStreamSynchronize(h->own_stream);
     close_peer_buffers(d);
     for (size_t r = 0; r < d->peer_flags.size(); r++)
         if (static_cast<int>(r) != d->rank && d->peer_flags[r])
@@ -169,39 +179,52 @@ void dist_destroy(htb_operator *h) {
 
 // out[i] = beta out[i] + sum_r rbuf[r][i], r = 0 .. world-1 in rank order: the scal + world axpys that follow the
 // MPI_Alltoallv of the reference (add_distributed_operator_vector_product_local_to_local.hpp:79-86), same order.
-// Arrays are addressed as doubles (a complex sum is two real sums); only the beta product is complex.
+// One ELEMENT per thread (a complex element = both of its words: the beta product reads re and im of the old value, so
+// the two words must be read before either is written — out may be updated in place).
 template <bool CPLX>
-__global__ void sum_slices_kernel(double *out, const double *rbuf, long long n_doubles, int world, double beta_re, double beta_im, int beta_is_zero) {
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n_doubles)
+__global__ void sum_slices_kernel(double *out, const double *rbuf, long long n_elems, int world, double beta_re, double beta_im, int beta_is_zero) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= n_elems)
         return;
-    double v = 0.;
+    constexpr int W       = CPLX ? 2 : 1;
+    const long long i     = e * W;
+    const long long n_dbl = n_elems * W;
+    double v[W];
+#pragma unroll
+    for (int j = 0; j < W; j++)
+        v[j] = 0.;
     if (!beta_is_zero) {
         if (CPLX) {
-            const double re = out[i & ~1ll], im = out[i | 1ll];
-            v = (i & 1) ? beta_re * im + beta_im * re : beta_re * re - beta_im * im;
+            const double re = out[i], im = out[i + 1];
+            v[0]     = beta_re * re - beta_im * im;
+            v[W - 1] = beta_re * im + beta_im * re;
         } else
-            v = beta_re * out[i];
+            v[0] = beta_re * out[i];
     }
     for (int r = 0; r < world; r++)
-        v += rbuf[static_cast<size_t>(r) * n_doubles + i];
-    out[i] = v;
+#pragma unroll
+        for (int j = 0; j < W; j++)
+            v[j] += rbuf[static_cast<size_t>(r) * n_dbl + i + j];
+#pragma unroll
+    for (int j = 0; j < W; j++)
+        out[i + j] = v[j];
 }
 
 // out[i] = sum[i] + beta old[i] (global-to-global T / C: the axpy after MPI_Allreduce,
-// add_distributed_operator_vector_product_global_to_global.hpp:77-83)
+// add_distributed_operator_vector_product_global_to_global.hpp:77-83). One element per thread: old may alias out.
 template <bool CPLX>
-__global__ void add_scaled_kernel(double *out, const double *sum, const double *old, long long n_doubles, double beta_re, double beta_im) {
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n_doubles)
+__global__ void add_scaled_kernel(double *out, const double *sum, const double *old, long long n_elems, double beta_re, double beta_im) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= n_elems)
         return;
-    double v;
     if (CPLX) {
-        const double re = old[i & ~1ll], im = old[i | 1ll];
-        v = (i & 1) ? beta_re * im + beta_im * re : beta_re * re - beta_im * im;
+        const long long i = 2 * e;
+        const double re = old[i], im = old[i + 1];
+        const double s0 = sum[i], s1 = sum[i + 1];
+        out[i]     = s0 + (beta_re * re - beta_im * im);
+        out[i + 1] = s1 + (beta_re * im + beta_im * re);
     } else
-        v = beta_re * old[i];
-    out[i] = sum[i] + v;
+        out[e] = sum[e] + beta_re * old[e];
 }
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
@@ -466,6 +489,7 @@ int htb_comm_init(htb_handle h, const void *id128, int world_size, int rank, con
     HTB_CUDA(cudaStreamCreateWithFlags(&d->comm_stream, cudaStreamNonBlocking));
     HTB_CUDA(cudaEventCreateWithFlags(&d->in_ready, cudaEventDisableTiming));
     HTB_CUDA(cudaEventCreateWithFlags(&d->gather_done, cudaEventDisableTiming));
+    HTB_CUDA(cudaEventCreateWithFlags(&d->product_done, cudaEventDisableTiming));
     // source blocks entirely inside the own partition vs the rest, each keeping the heaviest-first order
     std::vector<uint32_t> local, remote;
     const int lo = d->offsets[rank], hi = d->offsets[rank + 1];
@@ -551,8 +575,8 @@ int htb_dist_add_product_local_to_local(htb_handle h, char trans, const void *al
         // the host buffer and the APPLY epilogue writes y_local into it, no staging copies
         void *zc_in = nullptr, *zc_out = nullptr;
         if (mem_kind == HTB_MEM_HOST && mu == 1 && d->p2p && option_value("zero_copy") != 0) {
-            zc_in  = mapped_device_pointer(in_local);
-            zc_out = mapped_device_pointer(out_local);
+            zc_in  = mapped_device_pointer(in_local, n_local * es);
+            zc_out = mapped_device_pointer(out_local, n_local * es);
             if (!zc_in || !zc_out)
                 zc_in = zc_out = nullptr;
         }
@@ -574,6 +598,8 @@ int htb_dist_add_product_local_to_local(htb_handle h, char trans, const void *al
             // peer-memory gather: push the own slice into every rank's buffer of this epoch's parity, then ONE reduce launch
             const unsigned long long epoch = ++d->epoch;
             const int k = static_cast<int>(epoch & 1ull);
+            if (d->product_stream && d->product_stream != st) // the caller switched streams: order this push after the previous product
+                HTB_CUDA(cudaStreamWaitEvent(st, d->product_done, 0));
             xg          = static_cast<char *>(d->xg[k]);
             const void *src = in_local;
             if (mem_kind == HTB_MEM_HOST) {
@@ -615,6 +641,10 @@ int htb_dist_add_product_local_to_local(htb_handle h, char trans, const void *al
         }
         if ((rc = product_device(h, 'N', alpha, xg, beta, dout, mu, &split)) != HTB_OK)
             return rc;
+        if (d->p2p) {
+            HTB_CUDA(cudaEventRecord(d->product_done, st));
+            d->product_stream = st;
+        }
         if (zero_copy) { // the caller's host vector is the output: complete before returning
             HTB_CUDA(cudaStreamSynchronize(st));
             return HTB_OK;
@@ -650,7 +680,7 @@ int htb_dist_add_product_local_to_local(htb_handle h, char trans, const void *al
                 HTB_NCCL(nccl().Recv(rbuf + size_t(r) * n_local * es, n_local * es, ncclChar, r, d->comm, st));
         }
         HTB_NCCL(nccl().GroupEnd());
-        const long long nd = static_cast<long long>(n_local * es / sizeof(double));
+        const long long nd = static_cast<long long>(n_local * es / h->esize); // elements (a complex element is one work item)
         if (nd) {
             const double *b   = static_cast<const double *>(beta);
             const unsigned grid = static_cast<unsigned>((nd + 255) / 256);
@@ -729,11 +759,12 @@ int htb_dist_add_product_global_to_global(htb_handle h, char trans, const void *
                 old = d->d_old;
             }
             const double *b     = static_cast<const double *>(beta);
-            const unsigned grid = static_cast<unsigned>((nd + 255) / 256);
+            const long long ne  = static_cast<long long>(n_global * es / h->esize); // elements
+            const unsigned grid = static_cast<unsigned>((ne + 255) / 256);
             if (h->dtype == HTB_DOUBLE)
-                add_scaled_kernel<false><<<grid, 256, 0, st>>>(reinterpret_cast<double *>(dout), static_cast<const double *>(d->d_xglobal), static_cast<const double *>(old), static_cast<long long>(nd), b[0], 0.);
+                add_scaled_kernel<false><<<grid, 256, 0, st>>>(reinterpret_cast<double *>(dout), static_cast<const double *>(d->d_xglobal), static_cast<const double *>(old), ne, b[0], 0.);
             else
-                add_scaled_kernel<true><<<grid, 256, 0, st>>>(reinterpret_cast<double *>(dout), static_cast<const double *>(d->d_xglobal), static_cast<const double *>(old), static_cast<long long>(nd), b[0], b[1]);
+                add_scaled_kernel<true><<<grid, 256, 0, st>>>(reinterpret_cast<double *>(dout), static_cast<const double *>(d->d_xglobal), static_cast<const double *>(old), ne, b[0], b[1]);
             HTB_CUDA(cudaGetLastError());
             h->launches++;
         }

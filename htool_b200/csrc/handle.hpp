@@ -86,7 +86,7 @@ int ensure_staging(htb_operator *h, size_t in_bytes, size_t out_bytes);
 // overlaps the DMA of the previous one
 int staged_h2d(htb_operator *h, void *dev, void *pinned, const void *host, size_t bytes, cudaStream_t st);
 int staged_d2h(htb_operator *h, void *host, void *pinned, const void *dev, size_t bytes, cudaStream_t st); // returns when host is complete
-void *mapped_device_pointer(const void *host); // device address of a page-locked mapped host buffer, or nullptr
+void *mapped_device_pointer(const void *host, size_t bytes); // device address of a page-locked mapped host buffer covering [host, host + bytes), or nullptr
 void dist_destroy(htb_operator *h);
 int dist_gather_mode(const htb_operator *h); // 0 none, 1 NCCL, 2 peer memory
 } // namespace htb

@@ -1,5 +1,6 @@
 import glob
 import os
+import subprocess
 import sys
 
 import numpy as np
@@ -19,7 +20,10 @@ def pytest_configure(config):
     import __graft_entry__ as g
 
     g.build_oracle(quiet=True)
-    g.build_product(quiet=True)
+    try:
+        g.build_product(quiet=True)
+    except (OSError, subprocess.CalledProcessError) as ex:  # no nvcc on this machine: only the tests that load the library fail
+        print(f"[conftest] product library not rebuilt ({ex}); tests that need libhtool_b200.so will fail or skip", file=sys.stderr)
 
 
 def load_golden(name):

@@ -63,71 +63,21 @@ def main():
     offsets = np.concatenate([[0], np.cumsum(sizes.cpu().numpy())]).astype(np.int32)
     assert offsets[-1] == n_global and case.desc.row_offset - case.desc.col_offset == offsets[rank]
 
-    rng = np.random.default_rng(5)  # same global x on every rank; each rank only USES its slice
-    x_global = rng.random(n_global * mu) - 0.5
-    if dtype == np.complex128:
-        x_global = x_global + 1j * (rng.random(n_global * mu) - 0.5)
-    x_global = x_global.astype(dtype)
-    x_local = np.ascontiguousarray(x_global[offsets[rank] * mu: offsets[rank + 1] * mu])
-    alpha, beta = (0.7, -1.3) if dtype == np.float64 else (0.7 + 0.2j, -1.3 + 0.4j)
-    y0 = (rng.random(n_local * mu) - 0.5).astype(dtype)
-    y_ref = y0.copy()
-    if mu == 1:
-        case.vector_product("N", alpha, x_global, beta, y_ref, variant="global_to_local_operator")
-    else:
-        case.matrix_product_row_major("N", alpha, x_global, beta, y_ref, mu, variant="global_to_local_operator")
+    # ---- reference results of every distributed product (oracle/dist_parity.py: the reference's strip products + the
+    # MPI collectives of its DistributedOperator linalg replaced by torch.distributed on CPU tensors) --------------------
+    from oracle.dist_parity import DistReference, as_real, nccl_sweep
 
-    def err(y, ref=None):
-        ref = y_ref if ref is None else ref
-        return float(np.linalg.norm(y - ref) / np.linalg.norm(ref))
-
-    # ---- reference results of the transposed local-to-local and the global-to-global products -----------------------
-    # What the reference's DistributedOperator linalg does around the per-rank operator, with the MPI collectives
-    # replaced by torch.distributed on CPU tensors (gloo):
-    #   l2l T/C (add_distributed_operator_vector_product_local_to_local.hpp:47-87): z_r = alpha op(H_r)^T x_r (global
-    #     length), Alltoallv of the slices, out = beta out + sum_r z_r[own slice] in rank order;
-    #   g2g N (…global_to_global.hpp:43-76): own rows of out = beta out + alpha H_r x, Allgatherv;
-    #   g2g T/C (:51-83): Allreduce(sum) of z_r, + beta out.
     cpu = dist.new_group(backend="gloo") if args.backend == "nccl" else None
     tt = torch.from_numpy
+    ref = DistReference(case, world, rank, offsets, mu, sym=args.sym, cpu_group=cpu)
+    rng = np.random.default_rng(6)
+    x_global, x_local, alpha, beta, y0, y0_global = ref.x_global, ref.x_local, ref.alpha, ref.beta, ref.y0, ref.y0_global
+    transposes, ref_l2l, ref_g2g, prod = ref.transposes, ref.ref_l2l, ref.ref_g2g, ref.prod
+    lo_e, hi_e = ref.lo_e, ref.hi_e
+    y_ref = ref_l2l["N"]
 
-    def prod(trans, a, x, b, y):
-        if mu == 1:
-            case.vector_product(trans, a, x, b, y, variant="global_to_local_operator")
-        else:
-            case.matrix_product_row_major(trans, a, x, b, y, mu, variant="global_to_local_operator")
-        return y
-
-    def as_real(a):
-        return a.view(np.float64) if a.dtype == np.complex128 else a
-
-    transposes = ["T"] if (dtype == np.float64 or args.sym == "S") else ["C"]
-    if dtype == np.complex128 and args.sym == "N":
-        transposes = ["T", "C"]
-    y0_global = (rng.random(n_global * mu) - 0.5).astype(dtype)  # same on every rank
-    lo_e, hi_e = int(offsets[rank]) * mu, int(offsets[rank + 1]) * mu
-    ref_l2l, ref_g2g = {}, {}
-    for t in transposes:
-        z = prod(t, alpha, x_local, 0.0, np.zeros(n_global * mu, dtype))
-        send = [tt(as_real(np.ascontiguousarray(z[int(offsets[r]) * mu: int(offsets[r + 1]) * mu]))) for r in range(world)]
-        recv = [torch.zeros(as_real(x_local).size, dtype=torch.float64) for _ in range(world)]
-        # gloo has no all_to_all: every slice owner gathers its slices instead
-        for r in range(world):
-            got = [torch.zeros_like(send[r]) for _ in range(world)] if rank == r else None
-            dist.gather(send[r], got, dst=r, group=cpu)
-            if rank == r:
-                recv = got
-        out = beta * y0
-        for r in range(world):
-            out = out + recv[r].numpy().view(dtype)
-        ref_l2l[t] = out
-        zsum = tt(as_real(z.copy()))
-        dist.all_reduce(zsum, group=cpu)
-        ref_g2g[t] = zsum.numpy().view(dtype) + beta * y0_global
-    yl = prod("N", alpha, x_global, beta, y0_global[lo_e:hi_e].copy())
-    parts = [torch.zeros(int(offsets[r + 1] - offsets[r]) * mu * (2 if dtype == np.complex128 else 1), dtype=torch.float64) for r in range(world)]
-    dist.all_gather(parts, tt(as_real(yl)), group=cpu)
-    ref_g2g["N"] = torch.cat(parts).numpy().view(dtype)
+    def err(y, r=None):
+        return ref.err(y, y_ref if r is None else r)
 
     errs = []
     if args.backend == "gloo":
@@ -196,44 +146,10 @@ def main():
         dist.broadcast(uid, 0)
         op.comm_init(bytes(uid.cpu().numpy().tobytes()), world, rank, offsets)
         assert op.info()["dist_gather"] == (2 if args.p2p else 1), op.info()["dist_gather"]  # NVLink box: peer mappings must work
-        for it in range(5):  # repeated: gather buffers (double-buffered by epoch), flags and events are reused across calls
-            y = y0.copy()
-            xs = x_local * (1.0 + it)  # a different x every time: a stale buffer would show
-            op.dist_add_product_local_to_local(alpha, xs, beta, y, mu)
-            errs.append(err((y - beta * y0) / (1.0 + it) + beta * y0))
-        # page-locked host vectors (htb_host_register): zero copy when mu == 1 and the gather goes through peer memory
-        x_pin, y_pin = x_local.copy(), y0.copy()
-        capi.host_register(x_pin)
-        capi.host_register(y_pin)
-        op.dist_add_product_local_to_local(alpha, x_pin, beta, y_pin, mu)
-        errs.append(err(y_pin))
-        capi.host_unregister(x_pin)
-        capi.host_unregister(y_pin)
-        x_d, y_d = torch.from_numpy(x_local).cuda(), torch.from_numpy(y0.copy()).cuda()
-        op.dist_add_product_local_to_local(alpha, x_d.data_ptr(), beta, y_d.data_ptr(), mu, capi.HTB_MEM_DEVICE)
-        op.synchronize()
-        errs.append(err(y_d.cpu().numpy()))
-        tdt = torch.float64 if dtype == np.float64 else torch.complex128
-        for t in transposes:  # T / C local-to-local: grouped send/recv of the slices + rank-ordered sum
-            y = y0.copy()
-            op.dist_add_product_local_to_local(alpha, x_local, beta, y, mu, trans=t)
-            errs.append(err(y, ref_l2l[t]))
-            y_d = torch.from_numpy(y0.copy()).cuda()
-            op.dist_add_product_local_to_local(alpha, x_d.data_ptr(), beta, y_d.data_ptr(), mu, capi.HTB_MEM_DEVICE, trans=t)
-            op.synchronize()
-            errs.append(err(y_d.cpu().numpy(), ref_l2l[t]))
-            y = np.full(n_local * mu, np.nan, dtype)  # beta == 0 ignores out
-            op.dist_add_product_local_to_local(alpha, x_local, 0.0, y, mu, trans=t)
-            errs.append(err(y, ref_l2l[t] - beta * y0))
-        xg_d = torch.from_numpy(x_global).cuda()
-        for t in ["N"] + transposes:  # global-to-global
-            y = y0_global.copy()
-            op.dist_add_product_global_to_global(t, alpha, x_global, beta, y, mu)
-            errs.append(err(y, ref_g2g[t]))
-            yg_d = torch.from_numpy(y0_global.copy()).cuda()
-            op.dist_add_product_global_to_global(t, alpha, xg_d.data_ptr(), beta, yg_d.data_ptr(), mu, capi.HTB_MEM_DEVICE)
-            op.synchronize()
-            errs.append(err(yg_d.cpu().numpy(), ref_g2g[t]))
+        sweep = nccl_sweep(op, ref, capi)
+        if rank == 0:
+            print("dist_worker sweep:", {k: f"{v:.1e}" for k, v in sweep.items()}, flush=True)
+        errs.extend(sweep.values())
         if mu == 1:
             # distributed device-resident GMRES (htb_gmres): local slices in / out, inner products summed over the ranks.
             # Checker: the numpy oracle on the GLOBAL operator, its matvec = the reference's strip products gathered over gloo.
