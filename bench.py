@@ -1,10 +1,10 @@
 #!/usr/bin/env python
 """bench.py — H-matvecs/s and achieved HBM GB/s of the B200 H-matrix product (BASELINE.json metric).
 
-Workload (BASELINE.json configs[1]): Laplace kernel 1/(1e-5 + 4 pi r), N = 1e6 points on the
+Headline workload (BASELINE.json configs[1]): Laplace kernel 1/(1e-5 + 4 pi r), N = 1e6 points on the
 unit sphere surface (create_sphere seed mt19937(0), normalised), eps = 1e-4, eta = 10, leaf size 10, binary
-cluster tree, minimal block depth 5 (the reference's int-overflow work-around), double,
-single right-hand side, y = H x in cluster numbering (alpha = 1, beta = 0).
+cluster tree, minimal block depth = the reference's int-overflow work-around, double, single right-hand
+side, y = H x in cluster numbering (alpha = 1, beta = 0).
 
 Who does what
   * clustering, block tree and ACA compression: the UNMODIFIED reference on the host (north_star), through
@@ -12,13 +12,24 @@ Who does what
     checker and the cpu_baseline / `--impl reference` arm; it is never inside a timed region of our arm);
   * the product: libhtool_b200.so through the C ABI (include/htool_b200.h), nothing else.
 
-One JSON line is printed by rank 0. N > 1 (torchrun, one process per GPU): strong scaling, the same N = 1e6
-operator row-sharded over the ranks (strip r built with target partition r), NCCL allgather of x inside the
-timed step (htb_dist_add_product_local_to_local).
+ONE JSON line is printed by rank 0 (everything else goes to stderr). N > 1 (torchrun, one process per GPU): strong
+scaling, the same N = 1e6 operator row-sharded over the ranks (strip r built with target partition r), gather of x
+inside the timed step (htb_dist_add_product_local_to_local).
+
+Besides the headline the line carries, under "configs", the other BASELINE.json configurations that fit the run, each
+parity-gated against the reference and with its own roofline object (SECTIONS below):
+  N = 1 : configs[2] (mu = 64 on the FP64 tensor cores), small mu, symmetric storage, Helmholtz complex mu = 1 / 64, and
+          the device-resident GMRES ("gmres");
+  N > 1 : a parity sweep of every distributed entry point ('T'/'C', global-to-global, mu = 3 / 16, NCCL-gather fallback)
+          BEFORE any timing ("dist_parity"; a failure aborts the run), configs[3] (Helmholtz 'S' N = 2e6) and, from 4 GPUs
+          up, configs[4] (Laplace N = 8e6, 200 products inside a distributed GMRES solve).
+Extras start only while the run is inside its time budget (HTB_BENCH_BUDGET_S, default 560 s) and can never cost the
+headline: each is wrapped, and a watchdog prints what is complete and exits at HTB_BENCH_HARD_S (default 800 s).
 """
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -31,7 +42,18 @@ import numpy as np
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
-L2_BYTES = 126e6
+T_START = time.perf_counter()
+BUDGET_S = float(os.environ.get("HTB_BENCH_BUDGET_S", "560"))
+HARD_S = float(os.environ.get("HTB_BENCH_HARD_S", "800"))
+FP64_PEAK_FILE = os.path.join(REPO, "profiles", "r01_fp64_peak_b200.json")
+
+
+def elapsed():
+    return time.perf_counter() - T_START
+
+
+def log(*a):
+    print(f"[bench {elapsed():7.1f}s]", *a, file=sys.stderr, flush=True)
 
 
 def parse_args():
@@ -42,14 +64,16 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     # (--points: torchrun's own parser rejects "--n" as an ambiguous abbreviation of --nnodes / --nproc-per-node)
     ap.add_argument("--n", "--points", dest="n", type=int, default=int(os.environ.get("HTB_BENCH_POINTS", 1_000_000)), help="number of points (default: the BASELINE config)")
-    ap.add_argument("--mu", type=int, default=1, help="right-hand sides (row-major), default 1")
+    ap.add_argument("--mu", type=int, default=1, help="right-hand sides (row-major) of the HEADLINE workload, default 1")
     ap.add_argument("--dtype", default="double", choices=["double", "complex"])
     ap.add_argument("--symmetry", default="N", choices=["N", "S"])
     ap.add_argument("--cpu-reps", type=int, default=3)
     ap.add_argument("--opt", action="append", default=[], help="packer/launch option key=value (htb_set_option)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gmres-iterations", type=int, default=200, help="BASELINE.json configs[4]: repeated matvecs inside a device-resident GMRES solve (0: skip)")
-    ap.add_argument("--gmres-dist", action="store_true", help="also run the GMRES section with N > 1 GPUs (off by default: the scaling runs time the product only)")
+    ap.add_argument("--sections", default=os.environ.get("HTB_BENCH_SECTIONS", "all"),
+                    help="comma-separated extra sections (all | none | mu64,mu5,symmetric,helmholtz,gmres,dist_parity,config3,config4)")
+    ap.add_argument("--extra-points", type=int, default=0, help="override the point count of the extra sections (tests)")
     return ap.parse_args()
 
 
@@ -65,25 +89,29 @@ def min_depth_for(n: int, n_partitions: int = 1) -> int:
     return d + 1 if (n_partitions == 1 and d > 0) else d
 
 
-def case_kwargs(args, n_partitions=1, partition_rank=-1):
-    kw = dict(n=args.n, geometry="sphere_surface", epsilon=1e-4, eta=10.0, min_depth=min_depth_for(args.n, n_partitions), n_partitions=n_partitions, partition_rank=partition_rank)
-    if args.dtype == "double":
+def case_kwargs(n, dtype="double", symmetry="N", n_partitions=1, partition_rank=-1):
+    kw = dict(n=n, geometry="sphere_surface", epsilon=1e-4, eta=10.0, min_depth=min_depth_for(n, n_partitions), n_partitions=n_partitions, partition_rank=partition_rank)
+    if dtype == "double":
         kw.update(dtype="double", kernel="laplace_reg")
     else:
         kw.update(dtype="complex", kernel="helmholtz", wavenumber=5.0)
-    if args.symmetry == "S":
+    if symmetry == "S":
         kw.update(symmetry="S", uplo="L")
     return kw
 
 
-def workload_name(args):
-    k = "laplace" if args.dtype == "double" else "helmholtz_k5"
-    return f"{k}_N{args.n}_eps1e-4_eta10_leaf10_mindepth{min_depth_for(args.n, args.gpus)}_sym{args.symmetry}_mu{args.mu}"
+def workload_name(n, dtype, symmetry, mu, n_partitions):
+    k = "laplace" if dtype == "double" else "helmholtz_k5"
+    return f"{k}_N{n}_eps1e-4_eta10_leaf10_partitions{n_partitions}_mindepth{min_depth_for(n, n_partitions)}_sym{symmetry}_mu{mu}"
 
 
-def workload_label(args):
+def config_dict(args):
+    """The SAME dict in both arms (ours and --impl reference): the operator is the one the reference assembles on a cluster
+    tree with `--gpus` partitions; our arm shards its row strips over the GPUs, the reference arm applies it whole."""
     base = args.n == 1_000_000 and args.mu == 1 and args.dtype == "double" and args.symmetry == "N"
-    return workload_name(args) + (" (BASELINE.json configs[1])" if base else "")
+    return {"workload": workload_name(args.n, args.dtype, args.symmetry, args.mu, args.gpus) + (" (BASELINE.json configs[1])" if base else ""),
+            "n": args.n, "mu": args.mu, "n_partitions": args.gpus, "min_block_depth": min_depth_for(args.n, args.gpus),
+            "l2": "inputs larger than L2: every product streams all the coefficients (20 GB at N = 1e6) vs 126 MB of L2, no flush needed"}
 
 
 class ClockSampler:
@@ -166,6 +194,12 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def fp64_tensor_peak():
+    if os.path.exists(FP64_PEAK_FILE):
+        return float(json.load(open(FP64_PEAK_FILE))["dmma_m8n8k4_tflops"]), "FP64 DMMA peak measured with tools/fp64_peak.cu on this pool's B200 (profiles/r01_fp64_peak_b200.json); MEASURED_PEAKS.json has no FP64 figure"
+    return 37.0, "fallback: public FP64 tensor figure"
+
+
 def seeded_x(n, dtype, seed=1):
     rng = np.random.default_rng(seed)
     x = rng.random(n)
@@ -174,8 +208,10 @@ def seeded_x(n, dtype, seed=1):
     return x.astype(dtype)
 
 
+# ---- the reference arm ---------------------------------------------------------------------------------------------
 def run_reference(args):
-    """--impl reference: the reference's own OpenMP product on the host cores, same workload and metric."""
+    """--impl reference: the reference's own OpenMP product on the host cores, same workload, config and metric. Under
+    torchrun rank 0 alone works; the operator is the whole matrix on the `--gpus`-partition cluster tree."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -183,7 +219,7 @@ def run_reference(args):
 
     threads = os.cpu_count() or 1
     R.set_num_threads(threads)
-    case = R.RefCase(**case_kwargs(args))
+    case = R.RefCase(**case_kwargs(args.n, args.dtype, args.symmetry, args.gpus, -1))
     x = seeded_x(case.nb_cols * args.mu, case.np_dtype)
     y = np.zeros(case.nb_rows * args.mu, case.np_dtype)
 
@@ -204,7 +240,7 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": "H-matvecs/s", "value": value, "unit": "matvec/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64" if args.dtype == "double" else "c128",
-        "data": "synthetic", "config": {"workload": workload_label(args), "n": args.n, "mu": args.mu, "coefficients": info["coefficients"]},
+        "data": "synthetic", "config": config_dict(args), "coefficients": info["coefficients"],
         "cpu_baseline": {"value": value, "unit": "matvec/s", "cores": threads, "kind": "reference",
                          "sample": f"{args.steps} full H-matvecs (openmp_internal_add_hmatrix_vector_product, OPENBLAS_NUM_THREADS=1) after {args.warmup} warm-ups"},
         "e2e": {"value": value, "unit": "matvec/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -212,308 +248,579 @@ def run_reference(args):
     }), flush=True)
 
 
-def run_ours(args):
-    import torch
+# ---- our arm --------------------------------------------------------------------------------------------------------
+class Ctx:
+    """Process-wide state of our arm: ranks, process group, stream."""
 
+    def __init__(self, args):
+        import torch
+
+        self.args = args
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        assert self.world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={self.world}: launch with torchrun --nproc-per-node {args.gpus}"
+        torch.cuda.set_device(self.local_rank)
+        self.dist = None
+        self.cpu_group = None
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.init_process_group(backend="nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist = dist
+            self.cpu_group = dist.new_group(backend="gloo")
+        self.cores = os.cpu_count() or 1
+        # a dedicated, non-default stream: htb_set_stream(NULL) means "the handle's own stream", and the events that
+        # bracket a timed region must be recorded on the very stream the kernels are launched on
+        self.stream = torch.cuda.Stream()
+        assert self.stream.cuda_stream != 0
+
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        if not self.dist:
+            return float(v)
+        t = self.torch.tensor([float(v)], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, vals):
+        t = self.torch.tensor([float(v) for v in vals], device="cuda", dtype=self.torch.float64)
+        if self.dist:
+            self.dist.all_reduce(t)
+        return [float(v) for v in t.cpu().numpy()]
+
+    def agree_continue(self, ok: bool) -> bool:
+        """True iff EVERY rank is inside its budget (collective: extras hold collectives, all ranks must take the same branch)."""
+        if not self.dist:
+            return ok
+        t = self.torch.tensor([1.0 if ok else 0.0], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return bool(t.item() > 0.5)
+
+    def time_steps(self, step, steps, warmup):
+        """W untimed steps, then EXACTLY `steps` steps bracketed by barrier + synchronize and CUDA events on the launching
+        stream; max over the ranks. Returns (ms per step, wall-clock window)."""
+        torch = self.torch
+        for _ in range(max(3, warmup)):
+            step()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tw0 = time.perf_counter()
+        e0.record(self.stream)
+        for _ in range(steps):
+            step()
+        e1.record(self.stream)
+        self.barrier()
+        tw1 = time.perf_counter()
+        return self.max_over_ranks(e0.elapsed_time(e1)) / steps, (tw0, tw1)
+
+    def time_wall(self, step, steps, warmup=3):
+        for _ in range(warmup):
+            step()
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        self.barrier()
+        return self.max_over_ranks(time.perf_counter() - t0) / steps
+
+
+class Workload:
+    """One operator: assembled by the reference on the host (this rank's strip when N > 1), packed and uploaded once."""
+
+    def __init__(self, ctx: Ctx, n, dtype="double", symmetry="N"):
+        from htool_b200 import capi
+        from oracle import refharness as R
+
+        self.ctx, self.capi = ctx, capi
+        self.n, self.dtype_name, self.symmetry = n, dtype, symmetry
+        world, rank = ctx.world, ctx.rank
+        R.set_num_threads(max(1, ctx.cores // world))
+        t0 = time.perf_counter()
+        self.case = R.RefCase(**case_kwargs(n, dtype, symmetry, world, rank if world > 1 else -1))
+        self.t_build = time.perf_counter() - t0
+        self.dtype = self.case.np_dtype
+        self.esize = np.dtype(self.dtype).itemsize
+        t0 = time.perf_counter()
+        self.case.desc.device = ctx.local_rank
+        self.op = capi.Operator(self.case.desc)
+        self.t_upload = time.perf_counter() - t0
+        self.oinfo = self.op.info()
+        self.n_local, self.n_global = self.case.nb_rows, self.case.nb_cols
+        self.offsets = None
+        if world > 1:
+            torch, dist = ctx.torch, ctx.dist
+            sizes = torch.zeros(world, dtype=torch.int64, device="cuda")
+            sizes[rank] = self.n_local
+            dist.all_reduce(sizes)
+            self.offsets = np.concatenate([[0], np.cumsum(sizes.cpu().numpy())]).astype(np.int32)
+            uid = torch.zeros(capi.HTB_NCCL_UNIQUE_ID_BYTES, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                uid = torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8).cuda()
+            dist.broadcast(uid, 0)
+            self.op.comm_init(bytes(uid.cpu().numpy().tobytes()), world, rank, self.offsets)
+        self.op.set_stream(ctx.stream.cuda_stream)
+        # coefficients per side of this rank's store (SURVEY.md 8d): side 0 = dense + U panels, side 1 = V^T panels
+        leaf = self.case.leaves()
+        dense = leaf["rank"] < 0
+        self.c_side = [float((leaf["nb_rows"][dense].astype(np.int64) * leaf["nb_cols"][dense]).sum() + (leaf["nb_rows"][~dense].astype(np.int64) * leaf["rank"][~dense]).sum()),
+                       float((leaf["nb_cols"][~dense].astype(np.int64) * leaf["rank"][~dense]).sum())]
+        twice = (leaf["flags"] & 1) != 0
+        self.c_twice_local = float((leaf["nb_rows"][dense & twice].astype(np.int64) * leaf["nb_cols"][dense & twice]).sum()
+                                   + ((leaf["nb_rows"][~dense & twice].astype(np.int64) + leaf["nb_cols"][~dense & twice]) * leaf["rank"][~dense & twice]).sum())
+        # side-1 coefficients (V^T panels) of the leaves applied twice: streamed a second time by the transposed application
+        self.c_side1_twice = float((leaf["nb_cols"][~dense & twice].astype(np.int64) * leaf["rank"][~dense & twice]).sum())
+        self.C_total, self.C_twice = ctx.sum_over_ranks([float(self.oinfo["coefficients"]), self.c_twice_local])
+
+    def close(self):
+        self.op.close()
+        self.case.close()
+        gc.collect()
+
+    # ---- reference product on this rank's operator (host) -------------------------------------------------------------
+    def reference(self, x_global, mu, threads=None):
+        from oracle import refharness as R
+
+        R.set_num_threads(threads or max(1, self.ctx.cores // self.ctx.world))
+        y = np.zeros(self.n_local * mu, self.dtype)
+        t0 = time.perf_counter()
+        if mu == 1:
+            self.case.vector_product("N", 1.0, x_global, 0.0, y, variant="openmp")
+        else:
+            self.case.matrix_product_row_major("N", 1.0, x_global, 0.0, y, mu, variant="openmp")
+        return y, time.perf_counter() - t0
+
+    def x_local_of(self, x_global, mu):
+        if self.ctx.world == 1:
+            return x_global
+        lo = int(self.offsets[self.ctx.rank]) * mu
+        return np.ascontiguousarray(x_global[lo: lo + self.n_local * mu])
+
+    def host_product(self, x_local, y, mu):
+        op = self.op
+        if self.ctx.world > 1:
+            op.dist_add_product_local_to_local(1.0, x_local, 0.0, y, mu, self.capi.HTB_MEM_HOST)
+        elif mu == 1:
+            op.add_vector_product("N", 1.0, x_local, 0.0, y)
+        else:
+            op.add_matrix_product_row_major("N", 1.0, x_local, 0.0, y, mu)
+        return y
+
+    def device_step(self, x_d, y_d, mu):
+        op, capi = self.op, self.capi
+        if self.ctx.world > 1:
+            return lambda: op.dist_add_product_local_to_local(1.0, x_d.data_ptr(), 0.0, y_d.data_ptr(), mu, capi.HTB_MEM_DEVICE)
+        if mu == 1:
+            return lambda: op.add_vector_product_device("N", 1.0, x_d.data_ptr(), 0.0, y_d.data_ptr())
+        return lambda: op.add_matrix_product_row_major_device("N", 1.0, x_d.data_ptr(), 0.0, y_d.data_ptr(), mu)
+
+    def parity_gate(self, mu, what, threads=None):
+        """Same HMatrix object: the reference's CPU product vs the GPU product through the host-pointer C ABI. Raises
+        SystemExit when > 1e-12 (no number is reported for a product that differs from the reference's)."""
+        x_global = seeded_x(self.n_global * mu, self.dtype)
+        y_ref, t_ref = self.reference(x_global, mu, threads)
+        x_local = self.x_local_of(x_global, mu)
+        y_gpu = self.host_product(x_local, np.zeros(self.n_local * mu, self.dtype), mu)
+        parity = self.ctx.max_over_ranks(float(np.linalg.norm(y_gpu - y_ref) / np.linalg.norm(y_ref)))
+        if not parity <= 1e-12:
+            raise SystemExit(f"PARITY FAILURE ({what}): relative l2 error vs the reference CPU product = {parity:.3e} > 1e-12; no number is reported")
+        return dict(parity=parity, x_global=x_global, x_local=x_local, y_ref=y_ref, y_gpu=y_gpu, t_ref=t_ref)
+
+    def bytes_per_step(self, mu):
+        n_out_total = self.n_global  # square operator: sum of the strips' rows
+        return self.esize * self.C_total + self.esize * mu * (self.n_global + n_out_total)
+
+    def measure(self, mu, steps, warmup, gate, with_e2e=True):
+        """Device-resident rate, per-kernel times, and the end-to-end rate through host pointers for `mu` right-hand sides."""
+        ctx, torch, capi, op = self.ctx, self.ctx.torch, self.capi, self.op
+        tdt = torch.float64 if self.dtype == np.float64 else torch.complex128
+        x_d = torch.from_numpy(gate["x_local"]).cuda()
+        y_d = torch.zeros(self.n_local * mu, dtype=tdt, device="cuda")
+        torch.cuda.synchronize()
+        step = self.device_step(x_d, y_d, mu)
+        l0 = op.launch_count()
+        ms_step, window = ctx.time_steps(step, steps, warmup)
+        launches_per_step = (op.launch_count() - l0) / (steps + max(3, warmup))
+        # per-kernel durations (CUDA events on the launching stream) for the roofline
+        op.profile_passes(True)
+        prof_steps = min(steps, 10)
+        for _ in range(prof_steps):
+            step()
+        ctx.barrier()
+        pt = op.pass_times()
+        op.profile_passes(False)
+        passes = {k: {"ms_per_step": v["ms"] / prof_steps, "launches_per_step": v["launches"] / prof_steps} for k, v in pt.items()}
+        same = bool(np.array_equal(y_d.cpu().numpy(), gate["y_gpu"]))
+        out = dict(ms_step=ms_step, window=window, launches=int(round(launches_per_step * steps)), passes=passes, device_equals_host_result=same)
+        if with_e2e:
+            # end to end through the host-pointer C ABI (H2D of x and D2H of y inside the timed region). Page-locked once with
+            # htb_host_register (what a Krylov solver does with its vectors before the solve); the pageable variant (staged
+            # through the handle's pinned buffers with host memcpys) is timed beside it.
+            x_host = np.array(gate["x_local"], copy=True)
+            y_host = np.zeros(self.n_local * mu, self.dtype)
+            e2e_steps = steps if mu == 1 else min(steps, 5)
+            pageable_s = ctx.time_wall(lambda: self.host_product(x_host, y_host, mu), e2e_steps)
+            capi.host_register(x_host)
+            capi.host_register(y_host)
+            pinned_s = ctx.time_wall(lambda: self.host_product(x_host, y_host, mu), e2e_steps)
+            capi.host_unregister(x_host)
+            capi.host_unregister(y_host)
+            assert np.array_equal(y_host, gate["y_gpu"]), "end-to-end result differs from the parity-checked one"
+            out.update(e2e_s=pinned_s, e2e_pageable_s=pageable_s)
+        del x_d, y_d
+        return out
+
+    def hbm_roofline(self, m, mu, stored_note=""):
+        """HBM roofline of the dominant single-RHS kernel from its live per-launch time (SURVEY.md 8d bytes)."""
+        peak, peak_src = peaks()
+        p = m["passes"]
+        apply_ms, reduce_ms = p["apply"]["ms_per_step"], p["reduce"]["ms_per_step"]
+        tw = 1.0 if self.C_twice == 0 else 2.0  # symmetric storage: the APPLY kind has two launches per product (side 0 fused with
+        # the second application's REDUCE, then the transposed application over the V^T panels of the leaves stored once)
+        apply_bytes = self.esize * (self.c_side[0] + (self.c_side1_twice if tw > 1 else 0.0)) + self.esize * mu * (self.n_local + self.n_global) * tw  # coefficients + x + y
+        reduce_bytes = self.esize * self.c_side[1] + self.esize * mu * self.n_global                  # coefficients + x
+        dom = "apply" if apply_ms >= reduce_ms else "reduce"
+        dom_bytes, dom_ms = (apply_bytes, apply_ms) if dom == "apply" else (reduce_bytes, reduce_ms)
+        ach = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        kname = f"{dom}_kernel<{'double' if self.dtype == np.float64 else 'cplx'}>"
+        if tw > 1:
+            kname += " (symmetric storage: per-step sum of the launches of this pass kind; bytes = the coefficients each launch must stream once)"
+        return {"bound": "hbm", "kernel": kname + stored_note, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
+                "other_kernels_ms_per_step": {k: v["ms_per_step"] for k, v in p.items()}}
+
+    def tensor_roofline(self, m, mu):
+        """FP64 tensor roofline of the dominant multi-RHS kernel: USEFUL flops (2 mu C of its side, x4 for complex) / time —
+        not the pipe-active counter, which also counts the zero padding of small leaves."""
+        tpeak, src = fp64_tensor_peak()
+        p = m["passes"]
+        apply_ms, reduce_ms = p["apply"]["ms_per_step"], p["reduce"]["ms_per_step"]
+        cf = 4.0 if self.dtype == np.complex128 else 1.0
+        dom = "apply" if apply_ms >= reduce_ms else "reduce"
+        dom_ms = apply_ms if dom == "apply" else reduce_ms
+        flops = 2.0 * cf * mu * (self.c_side[0] if dom == "apply" else self.c_side[1])
+        tf = flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+        whole = 2.0 * cf * mu * (self.C_total + self.C_twice) / (m["ms_step"] * 1e-3) / 1e12
+        return {"bound": "tensor", "kernel": f"{dom}_m_kernel (DMMA m8n8k4 f64)", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak, "peak_source": src,
+                "algorithmic_flops_per_step": flops, "ms_per_step_of_kernel": dom_ms, "whole_product_tflops": whole, "whole_product_frac": whole / tpeak / self.ctx.world,
+                "other_kernels_ms_per_step": {k: v["ms_per_step"] for k, v in p.items()}}
+
+
+# ---- extra sections (each returns a dict; exceptions are caught by the caller) -----------------------------------------
+def section_multi_rhs(w: Workload, mu, steps=5):
+    """configs[2] when mu == 64: add_matrix_product_row_major on the operator of the headline."""
+    ctx = w.ctx
+    gate = w.parity_gate(mu, f"mu = {mu}", threads=ctx.cores // ctx.world)
+    m = w.measure(mu, steps, 3, gate)
+    roof = w.tensor_roofline(m, mu) if mu >= 8 else w.hbm_roofline(m, mu)
+    flops = 2.0 * mu * (4.0 if w.dtype == np.complex128 else 1.0) * (w.C_total + w.C_twice)
+    return {"workload": workload_name(w.n, w.dtype_name, w.symmetry, mu, ctx.world), "mu": mu, "value": 1e3 / m["ms_step"], "unit": "products/s (each of mu right-hand sides)",
+            "ms_per_step": m["ms_step"], "rhs_per_s": mu * 1e3 / m["ms_step"], "tflops": flops / (m["ms_step"] * 1e-3) / 1e12, "parity_rel_l2_vs_reference": gate["parity"],
+            "roofline": roof, "e2e": {"value": 1.0 / m["e2e_s"], "unit": "products/s", "pageable_value": 1.0 / m["e2e_pageable_s"], "h2d_bytes_per_step": int(w.esize * mu * w.n_global),
+                                      "d2h_bytes_per_step": int(w.esize * mu * w.n_global)},
+            "cpu_baseline": {"value": 1.0 / gate["t_ref"], "unit": "products/s", "cores": ctx.cores // ctx.world, "kind": "reference",
+                             "sample": "1 product (openmp_internal_add_hmatrix_matrix_product_row_major) on the same HMatrix object"},
+            "gpu_launches_per_step": m["launches"] / steps, "steps": steps}
+
+
+def section_single(w: Workload, steps, warmup, label):
+    ctx = w.ctx
+    gate = w.parity_gate(1, label)
+    m = w.measure(1, steps, warmup, gate)
+    bytes_step = w.bytes_per_step(1)
+    peak, _ = peaks()
+    ach = bytes_step / (m["ms_step"] * 1e-3) / 1e9
+    return {"workload": workload_name(w.n, w.dtype_name, w.symmetry, 1, ctx.world), "value": 1e3 / m["ms_step"], "unit": "matvec/s", "ms_per_step": m["ms_step"],
+            "parity_rel_l2_vs_reference": gate["parity"], "coefficients_stored": w.C_total, "coefficients_applied_twice": w.C_twice,
+            "algorithmic_bytes_per_step": bytes_step, "achieved_hbm_gbs": ach, "achieved_hbm_frac_per_gpu": ach / ctx.world / peak,
+            "roofline": w.hbm_roofline(m, 1), "e2e": {"value": 1.0 / m["e2e_s"], "unit": "matvec/s", "pageable_value": 1.0 / m["e2e_pageable_s"]},
+            "cpu_baseline": {"value": 1.0 / gate["t_ref"], "unit": "matvec/s (this rank's strip)" if ctx.world > 1 else "matvec/s", "cores": ctx.cores // ctx.world, "kind": "reference", "sample": "1 product on the same HMatrix object"},
+            "setup_seconds": {"reference_assembly": w.t_build, "pack_and_upload": w.t_upload}, "steps": steps,
+            "store_bytes_this_rank": w.oinfo["store_bytes"]}
+
+
+def section_gmres(w: Workload, n_products, bare_value, restart=40):
+    """BASELINE.json configs[4]: products INSIDE a device-resident restarted GMRES (htb_gmres; with N > 1 the product is the
+    distributed one and the inner products are summed over the ranks). Call sequence per iteration = what
+    HPDDMOperator::GMV does (wrapper_hpddm.hpp:118-124): one local-to-local product per Krylov vector. HPDDM is absent
+    from the reference tree: the Krylov arithmetic is parity-unpinned, its matvec is the parity-gated product."""
+    ctx, torch, capi, op = w.ctx, w.ctx.torch, w.capi, w.op
+    tdt = torch.float64 if w.dtype == np.float64 else torch.complex128
+    b_host = seeded_x(w.n_local, w.dtype, seed=2 + ctx.rank)
+    b_d = torch.from_numpy(b_host).cuda()
+    xs_d = torch.zeros(w.n_local, dtype=tdt, device="cuda")
+    op.gmres(b_d.data_ptr(), xs_d.data_ptr(), mem_kind=capi.HTB_MEM_DEVICE, restart=restart, max_iterations=5, tolerance=0.0, compute_true_residual=0)  # warm-up (allocations)
+    ctx.barrier()
+    # (a) ONE solve of exactly n_products iterations (tolerance 0: every iteration is performed, restart every 40)
+    xs_d.zero_()
+    ctx.barrier()
+    t0 = time.perf_counter()
+    g1 = op.gmres(b_d.data_ptr(), xs_d.data_ptr(), mem_kind=capi.HTB_MEM_DEVICE, restart=restart, max_iterations=n_products, tolerance=0.0, compute_true_residual=0)
+    ctx.barrier()
+    dt1 = ctx.max_over_ranks(time.perf_counter() - t0)
+    # (b) solves to 1e-10 repeated until n_products products have been spent (a well-conditioned operator converges in a few iterations)
+    ctx.barrier()
+    t0 = time.perf_counter()
+    n_mv, n_it, n_solves, worst = 0, 0, 0, 0.0
+    while n_mv < n_products:
+        xs_d.zero_()
+        gi = op.gmres(b_d.data_ptr(), xs_d.data_ptr(), mem_kind=capi.HTB_MEM_DEVICE, restart=restart, max_iterations=100, tolerance=1e-10, compute_true_residual=1)
+        n_mv, n_it, n_solves, worst = n_mv + gi["matvecs"], n_it + gi["iterations"], n_solves + 1, max(worst, gi["true_relative_residual"])
+    ctx.barrier()
+    dt2 = ctx.max_over_ranks(time.perf_counter() - t0)
+    return {"restart": restart, "orthogonalization": "cgs",
+            "one_solve": {"iterations": g1["iterations"], "matvecs": g1["matvecs"], "seconds": dt1, "matvec_per_s_inside_solver": g1["matvecs"] / dt1,
+                          "fraction_of_bare_matvec_rate": (g1["matvecs"] / dt1) / bare_value, "tolerance": 0.0},
+            "repeated_solves": {"solves": n_solves, "iterations": n_it, "matvecs": n_mv, "tolerance": 1e-10, "seconds": dt2, "matvec_per_s_inside_solver": n_mv / dt2,
+                                "fraction_of_bare_matvec_rate": (n_mv / dt2) / bare_value, "worst_true_relative_residual": worst},
+            "matvec_per_s_inside_solver": g1["matvecs"] / dt1, "fraction_of_bare_matvec_rate": (g1["matvecs"] / dt1) / bare_value}
+
+
+def section_dist_parity(ctx: Ctx, n_points):
+    """Every distributed entry point against the reference BEFORE any timing: l2l N / T / C, g2g N / T / C, host, pinned-host
+    and device pointers, mu in {1, 3, 16}, double and complex 'S', peer-memory and NCCL gathers. > 1e-12 aborts the run."""
     from htool_b200 import capi
     from oracle import refharness as R
+    from oracle.dist_parity import DistReference, nccl_sweep
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
-    for kv in args.opt:
-        k, v = kv.split("=")
-        capi.set_option(k, int(v))
-
-    cores = os.cpu_count() or 1
-    R.set_num_threads(max(1, cores // world))
-
-    # ---- assembly by the reference (host) ---------------------------------------------------------
-    t0 = time.perf_counter()
-    case = R.RefCase(**(case_kwargs(args, world, rank) if world > 1 else case_kwargs(args)))
-    t_build = time.perf_counter() - t0
-    info = case.info()
-    dtype = case.np_dtype
-    esize = np.dtype(dtype).itemsize
-    mu = args.mu
-
-    # ---- flatten + pack + upload (once per assembly) -------------------------------------------------
-    t0 = time.perf_counter()
-    case.desc.device = local_rank
-    op = capi.Operator(case.desc)
-    t_upload = time.perf_counter() - t0
-    oinfo = op.info()
-
-    n_local, n_global = case.nb_rows, case.nb_cols
-    offsets = None
-    if world > 1:
+    torch, dist, world, rank = ctx.torch, ctx.dist, ctx.world, ctx.rank
+    R.set_num_threads(max(1, ctx.cores // world))
+    report, worst = {}, 0.0
+    cases = [("double_mu1", dict(), 1, 1), ("double_mu3", dict(), 3, 1), ("double_mu16", dict(), 16, 1), ("double_S_mu1_nccl_gather", dict(symmetry="S", uplo="L"), 1, 0),
+             ("complex_S_mu1", dict(dtype="complex", kernel="helmholtz", symmetry="S", uplo="L"), 1, 1), ("complex_mu5", dict(dtype="complex", kernel="helmholtz"), 5, 1)]
+    for name, kw, mu, p2p in cases:
+        case = R.RefCase(n=n_points, n_partitions=world, partition_rank=rank, **kw)
         sizes = torch.zeros(world, dtype=torch.int64, device="cuda")
-        sizes[rank] = n_local
+        sizes[rank] = case.nb_rows
         dist.all_reduce(sizes)
         offsets = np.concatenate([[0], np.cumsum(sizes.cpu().numpy())]).astype(np.int32)
+        ref = DistReference(case, world, rank, offsets, mu, sym=kw.get("symmetry", "N"), cpu_group=ctx.cpu_group)
+        case.desc.device = ctx.local_rank
+        capi.set_option("dist_p2p", p2p)
+        op = capi.Operator(case.desc)
         uid = torch.zeros(capi.HTB_NCCL_UNIQUE_ID_BYTES, dtype=torch.uint8, device="cuda")
         if rank == 0:
             uid = torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8).cuda()
         dist.broadcast(uid, 0)
         op.comm_init(bytes(uid.cpu().numpy().tobytes()), world, rank, offsets)
-
-    # ---- parity gate (before any timing counts): same HMatrix object, reference CPU product vs GPU ------
-    x_global = seeded_x(n_global * mu, dtype)
-    y_ref = np.zeros(n_local * mu, dtype)
-    t0 = time.perf_counter()
-    if mu == 1:
-        case.vector_product("N", 1.0, x_global, 0.0, y_ref, variant="openmp")
-    else:
-        case.matrix_product_row_major("N", 1.0, x_global, 0.0, y_ref, mu, variant="openmp")
-    t_ref_once = time.perf_counter() - t0
-    y_gpu = np.zeros(n_local * mu, dtype)
-    if world > 1:
-        lo = int(offsets[rank]) * mu
-        x_local = np.ascontiguousarray(x_global[lo: lo + n_local * mu])
-        op.dist_add_product_local_to_local(1.0, x_local, 0.0, y_gpu, mu)
-    elif mu == 1:
-        op.add_vector_product("N", 1.0, x_global, 0.0, y_gpu)
-    else:
-        op.add_matrix_product_row_major("N", 1.0, x_global, 0.0, y_gpu, mu)
-    parity = float(np.linalg.norm(y_gpu - y_ref) / np.linalg.norm(y_ref))
-    if world > 1:
-        p = torch.tensor([parity], device="cuda", dtype=torch.float64)
-        dist.all_reduce(p, op=dist.ReduceOp.MAX)
-        parity = float(p.item())
-    if not parity <= 1e-12:
-        raise SystemExit(f"PARITY FAILURE: relative l2 error vs the reference CPU product = {parity:.3e} > 1e-12; no number is reported")
-
-    # ---- device-resident timing -----------------------------------------------------------------------
-    # a dedicated, non-default stream: htb_set_stream(NULL) means "the handle's own stream", and the events that
-    # bracket the timed region must be recorded on the very stream the kernels are launched on
-    stream = torch.cuda.Stream()
-    assert stream.cuda_stream != 0
-    op.set_stream(stream.cuda_stream)
-    tdt = torch.float64 if dtype == np.float64 else torch.complex128
-    if world > 1:
-        x_d = torch.from_numpy(x_local).cuda()
-    else:
-        x_d = torch.from_numpy(x_global).cuda()
-    y_d = torch.zeros(n_local * mu, dtype=tdt, device="cuda")
-    torch.cuda.synchronize()
-
-    def step():
-        if world > 1:
-            op.dist_add_product_local_to_local(1.0, x_d.data_ptr(), 0.0, y_d.data_ptr(), mu, capi.HTB_MEM_DEVICE)
-        elif mu == 1:
-            op.add_vector_product_device("N", 1.0, x_d.data_ptr(), 0.0, y_d.data_ptr())
-        else:
-            op.add_matrix_product_row_major_device("N", 1.0, x_d.data_ptr(), 0.0, y_d.data_ptr(), mu)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    for _ in range(max(3, args.warmup)):
-        step()
-    barrier()
-    launches0 = op.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    tw0 = time.perf_counter()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    barrier()
-    tw1 = time.perf_counter()
-    launches = op.launch_count() - launches0
-    ms_total = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        capi.set_option("dist_p2p", 1)
+        errs = nccl_sweep(op, ref, capi, repeats=3)
+        gather = op.info()["dist_gather"]
+        op.close()
+        case.close()
+        keys = sorted(errs)
+        t = torch.tensor([errs[k] for k in keys], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    value = 1e3 / ms_step
-    assert np.allclose(y_d.cpu().numpy(), y_gpu, rtol=0, atol=0) or True
+        errs = {k: float(v) for k, v in zip(keys, t.cpu().numpy())}
+        report[name] = {"worst": max(errs.values()), "paths": len(errs), "gather": {1: "nccl", 2: "peer-memory"}.get(gather, str(gather)),
+                        "worst_path": max(errs, key=errs.get), "l2l_T_or_C": max(v for k, v in errs.items() if k.startswith("l2l_") and not k.startswith("l2l_N")),
+                        "g2g": max(v for k, v in errs.items() if k.startswith("g2g_"))}
+        worst = max(worst, report[name]["worst"])
+    report["worst_rel_l2_vs_reference"] = worst
+    report["points"] = n_points
+    if not worst <= 1e-12:
+        raise SystemExit(f"DISTRIBUTED PARITY FAILURE: {json.dumps(report)}")
+    return report
 
-    # ---- per-kernel durations (CUDA events on the launching stream) for the roofline ---------------------
-    op.profile_passes(True)
-    prof_steps = min(args.steps, 10)
-    for _ in range(prof_steps):
-        step()
-    barrier()
-    pt = op.pass_times()
-    op.profile_passes(False)
 
-    # ---- end to end through the host-pointer C ABI (H2D of x and D2H of y inside the timed region) --------
-    # host buffers: page-locked once with htb_host_register (what a Krylov solver does with its vectors before the
-    # solve), so each step is DMA H2D of x -> product -> DMA D2H of y. The pageable variant (staged through the
-    # handle's pinned buffers with host memcpys) is timed beside it.
-    x_host = np.array(x_local if world > 1 else x_global, copy=True)
-    y_host = np.zeros(n_local * mu, dtype)
+RESULT = {"line": None, "printed": False}
+PRINT_LOCK = threading.Lock()
 
-    def step_e2e():
-        if world > 1:
-            op.dist_add_product_local_to_local(1.0, x_host, 0.0, y_host, mu, capi.HTB_MEM_HOST)
-        elif mu == 1:
-            op.add_vector_product("N", 1.0, x_host, 0.0, y_host)
-        else:
-            op.add_matrix_product_row_major("N", 1.0, x_host, 0.0, y_host, mu)
 
-    def time_e2e():
-        for _ in range(3):
-            step_e2e()
-        barrier()
+def print_line_once():
+    with PRINT_LOCK:
+        if RESULT["printed"] or RESULT["line"] is None:
+            return
+        RESULT["printed"] = True
+        print(json.dumps(RESULT["line"]), flush=True)
+
+
+def start_watchdog(rank):
+    """Extras must never cost the headline: at HARD_S every rank leaves; rank 0 first prints the line with what is complete."""
+
+    def fire():
+        log("watchdog: hard time limit reached, leaving with what is complete")
+        if rank == 0 and RESULT["line"] is not None:
+            RESULT["line"].setdefault("configs", {})["watchdog"] = f"hard limit {HARD_S:.0f} s reached: the sections missing here did not finish"
+            print_line_once()
+        sys.stdout.flush()
+        os._exit(0 if RESULT["line"] is not None or rank != 0 else 3)
+
+    t = threading.Timer(max(1.0, HARD_S - elapsed()), fire)
+    t.daemon = True
+    t.start()
+    return t
+
+
+def run_ours(args):
+    from htool_b200 import capi
+
+    ctx = Ctx(args)
+    world, rank = ctx.world, ctx.rank
+    watchdog = start_watchdog(rank)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        capi.set_option(k, int(v))
+    wanted = set(s for s in args.sections.split(",") if s)
+
+    def want(name):
+        return "none" not in wanted and ("all" in wanted or name in wanted)
+
+    extras = {}
+
+    def run_section(name, fn, need_s):
+        """Runs an extra section if every rank is inside the budget; failures are recorded, never raised (SystemExit =
+        parity failure is the exception: a wrong product must stop the run)."""
+        if not want(name):
+            return
+        ok = ctx.agree_continue(elapsed() + need_s < BUDGET_S)
+        if not ok:
+            extras[name] = {"skipped": f"time budget ({elapsed():.0f} s elapsed, section needs ~{need_s:.0f} s, budget {BUDGET_S:.0f} s)"}
+            return
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_e2e()
-        barrier()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        return dt
+        log(f"section {name} ...")
+        try:
+            extras[name] = fn()
+            extras[name]["section_seconds"] = time.perf_counter() - t0
+        except SystemExit:
+            raise
+        except Exception as ex:  # an extra key must never cost the headline line
+            extras[name] = {"error": f"{type(ex).__name__}: {ex}"}
+        log(f"section {name} done in {time.perf_counter() - t0:.1f} s")
 
-    e2e_pageable_s = time_e2e()
-    capi.host_register(x_host)
-    capi.host_register(y_host)
-    te0 = time.perf_counter()
-    e2e_s = time_e2e()
-    te1 = time.perf_counter()
-    capi.host_unregister(x_host)
-    capi.host_unregister(y_host)
-    assert np.array_equal(y_host, y_gpu), "end-to-end result differs from the parity-checked one"
-    e2e_value = args.steps / e2e_s
+    # ---- N > 1: parity of every distributed path before any timing ------------------------------------------------------
+    dist_parity = None
+    if world > 1 and want("dist_parity"):
+        log("distributed parity sweep ...")
+        dist_parity = section_dist_parity(ctx, args.extra_points or 20000)
+        log(f"distributed parity sweep: worst {dist_parity['worst_rel_l2_vs_reference']:.2e}")
+
+    # ---- headline ---------------------------------------------------------------------------------------------------------
+    mu = args.mu
+    w = Workload(ctx, args.n, args.dtype, args.symmetry)
+    log(f"headline operator assembled in {w.t_build:.1f} s, uploaded in {w.t_upload:.1f} s")
+    gate = w.parity_gate(mu, "headline", threads=ctx.cores // world)
+    sampler = ClockSampler(ctx.local_rank) if rank == 0 else None
+    m = w.measure(mu, args.steps, args.warmup, gate)
     clocks = None
     if sampler:
         time.sleep(0.15)
-        clocks = sampler.summarise(sampler.window(tw0, tw1))
+        clocks = sampler.summarise(sampler.window(*m["window"]))
         sampler.stop()
-
-    # ---- BASELINE.json configs[4]: K repeated products inside a (device-resident) GMRES solve, restart 40 ---------------
-    # (extra key, not the headline: HPDDM is absent from the reference tree, so there is no reference arm for the solver)
-    gm = None
-    if args.gmres_iterations > 0 and mu == 1 and (world == 1 or args.gmres_dist):
-        try:
-            b_host = seeded_x(n_local, dtype, seed=2 + rank)
-            b_d = torch.from_numpy(b_host).cuda()
-            xs_d = torch.zeros(n_local, dtype=tdt, device="cuda")
-            op.gmres(b_d.data_ptr(), xs_d.data_ptr(), mem_kind=capi.HTB_MEM_DEVICE, restart=40, max_iterations=5, tolerance=0.0, compute_true_residual=0)  # warm-up (allocations)
-            barrier()
-            t0 = time.perf_counter()
-            n_mv, n_it, n_solves, worst = 0, 0, 0, 0.0
-            while n_mv < args.gmres_iterations:  # well-conditioned operator: a solve converges in a few iterations, so solve repeatedly
-                xs_d.zero_()
-                gi = op.gmres(b_d.data_ptr(), xs_d.data_ptr(), mem_kind=capi.HTB_MEM_DEVICE, restart=40, max_iterations=100, tolerance=1e-10, compute_true_residual=1)
-                n_mv, n_it, n_solves, worst = n_mv + gi["matvecs"], n_it + gi["iterations"], n_solves + 1, max(worst, gi["true_relative_residual"])
-            barrier()
-            dt = time.perf_counter() - t0
-            gm = {"solves": n_solves, "iterations": n_it, "matvecs": n_mv, "restart": 40, "tolerance": 1e-10, "seconds": dt, "matvec_per_s_inside_solver": n_mv / dt,
-                  "fraction_of_bare_matvec_rate": (n_mv / dt) / value, "worst_true_relative_residual": worst, "orthogonalization": "cgs"}
-        except Exception as ex:  # an extra key must never cost the headline line
-            gm = {"error": str(ex)}
-
-    # ---- algorithmic bytes: s*C + s*mu*(n_src + n_tgt), descriptors excluded -------------
-    coeffs = torch.tensor([float(oinfo["coefficients"])], device="cuda", dtype=torch.float64)
-    leaf = case.leaves()
-    dense = leaf["rank"] < 0
-    c_side0 = float((leaf["nb_rows"][dense].astype(np.int64) * leaf["nb_cols"][dense]).sum() + (leaf["nb_rows"][~dense].astype(np.int64) * leaf["rank"][~dense]).sum())
-    c_side1 = float((leaf["nb_cols"][~dense].astype(np.int64) * leaf["rank"][~dense]).sum())
-    sides = torch.tensor([c_side0, c_side1], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(coeffs)
-        dist.all_reduce(sides)
-    C_total = float(coeffs.item())
-    bytes_step = esize * C_total + esize * mu * (n_global + (n_global if world == 1 else int(offsets[-1])))
-    achieved_total = bytes_step / (ms_step * 1e-3) / 1e9
-    peak, peak_src = peaks()
-
-    # dominant kernel on this rank: APPLY over side 0 (U panels + dense leaves) — per launch
-    apply_ms = pt["apply"]["ms"] / max(1, pt["apply"]["launches"])
-    reduce_ms = pt["reduce"]["ms"] / max(1, pt["reduce"]["launches"])
-    rank_sides = [c_side0, c_side1]
-    apply_bytes = esize * rank_sides[0] + esize * mu * (n_local + n_global)       # coefficients + x (dense leaves) + y
-    reduce_bytes = esize * rank_sides[1] + esize * mu * n_global                  # coefficients + x
-    # with several REDUCE launches per step (distributed split) use the per-step sum
-    reduce_ms_step = pt["reduce"]["ms"] / prof_steps
-    apply_ms_step = pt["apply"]["ms"] / prof_steps
-    dom = "apply" if apply_ms_step >= reduce_ms_step else "reduce"
-    dom_bytes, dom_ms = (apply_bytes, apply_ms_step) if dom == "apply" else (reduce_bytes, reduce_ms_step)
-    dom_achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    roof = {"bound": "hbm", "kernel": f"{dom}_kernel<{'double' if dtype == np.float64 else 'cplx'}>" + (" (fused with the second application's REDUCE)" if (dom == "apply" and args.symmetry != "N") else ""), "achieved": dom_achieved, "peak": peak,
-            "unit": "GB/s", "frac": dom_achieved / peak, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms}
-    if dtype == np.float64 and mu >= 8 and world == 1:
-        # multi-RHS: the leaves are batched contractions on the FP64 tensor cores (mkernels.cu); flops = 2 mu C
-        fpath = os.path.join(REPO, "profiles", "r01_fp64_peak_b200.json")
-        tpeak = json.load(open(fpath))["dmma_m8n8k4_tflops"] if os.path.exists(fpath) else 37.0
-        groups = (mu + 63) // 64  # one launch per group of 64 columns
-        dom_flops = 2.0 * min(mu, 64) * (rank_sides[0] if dom == "apply" else rank_sides[1])
-        dom_ms_launch = dom_ms / groups
-        tf = dom_flops / (dom_ms_launch * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": f"{dom}_m_kernel (DMMA m8n8k4 f64)", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
-                "peak_source": "FP64 DMMA peak measured with tools/fp64_peak.cu on this pool's B200 (profiles/r01_fp64_peak_b200.json); MEASURED_PEAKS.json has no FP64 figure",
-                "algorithmic_flops_per_launch": dom_flops, "ms_per_launch": dom_ms_launch,
-                "whole_product_tflops": 2.0 * mu * C_total / (ms_step * 1e-3) / 1e12}
+    value = 1e3 / m["ms_step"]
+    bytes_step = w.bytes_per_step(mu)
+    achieved_total = bytes_step / (m["ms_step"] * 1e-3) / 1e9
+    peak, _ = peaks()
+    if w.dtype == np.float64 and mu >= 8:
+        roof = w.tensor_roofline(m, mu)
+    else:
+        roof = w.hbm_roofline(m, mu)
     traffic = None
-    tpath = os.path.join(REPO, "profiles", "traffic_r01.json")
-    if os.path.exists(tpath) and world == 1 and args.n == 1_000_000 and mu == 1:
-        traffic = json.load(open(tpath)).get(dom + "_kernel_dram_bytes_per_launch")
+    for tname in ("traffic_r02.json", "traffic_r01.json"):
+        tpath = os.path.join(REPO, "profiles", tname)
+        if os.path.exists(tpath) and world == 1 and args.n == 1_000_000 and mu == 1 and args.symmetry == "N" and args.dtype == "double":
+            dom = "apply" if roof["kernel"].startswith("apply") else "reduce"
+            traffic = json.load(open(tpath)).get(dom + "_kernel_dram_bytes_per_launch")
+            break
+    roof["traffic"] = traffic
 
-    # ---- CPU baseline: the reference's OpenMP product on the same HMatrix object (rank 0, N = 1) ----------
+    # CPU baseline: the reference's OpenMP product on the same HMatrix object (rank 0, N = 1)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        R.set_num_threads(cores)
-        times = [t_ref_once]
+        times = [gate["t_ref"]]
         for _ in range(max(0, args.cpu_reps - 1)):
-            t0 = time.perf_counter()
-            if mu == 1:
-                case.vector_product("N", 1.0, x_global, 0.0, y_ref, variant="openmp")
-            else:
-                case.matrix_product_row_major("N", 1.0, x_global, 0.0, y_ref, mu, variant="openmp")
-            times.append(time.perf_counter() - t0)
+            times.append(w.reference(gate["x_global"], mu, threads=ctx.cores)[1])
         med = float(np.median(times[1:] if len(times) > 1 else times))
-        cpu = {"value": 1.0 / med, "unit": "matvec/s", "cores": cores, "kind": "reference",
+        cpu = {"value": 1.0 / med, "unit": "matvec/s", "cores": ctx.cores, "kind": "reference",
                "sample": f"{len(times)} full H-matvecs of this workload (1 warm-up + median of the rest), openmp_internal_add_hmatrix_{'vector' if mu == 1 else 'matrix'}_product, OPENBLAS_NUM_THREADS=1",
                "effective_gbs": bytes_step / med / 1e9}
 
+    oinfo = w.oinfo
+    line = {
+        "metric": "H-matvecs/s", "value": value, "unit": "matvec/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": m["ms_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64" if w.dtype == np.float64 else "c128", "data": "synthetic",
+        "config": config_dict(args),
+        "coefficients": w.C_total,
+        "details": {"parallelism": (f"row-strips x{world}, gather of x: " + {0: "none", 1: "NCCL broadcasts", 2: "peer-memory push over NVLink"}[w.op.info()["dist_gather"]]) if world > 1 else "single GPU",
+                    "coefficient_gb_per_gpu_per_step": w.esize * w.C_total / world / 1e9, "leaves": int(oinfo["nb_leaves"]) if world == 1 else None,
+                    "packer": {k: int(v) for k, v in (kv.split("=") for kv in args.opt)}},
+        "achieved_hbm_gbs": achieved_total,
+        "achieved_hbm_frac_per_gpu": achieved_total / world / peak,
+        "algorithmic_bytes_per_step": bytes_step,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "e2e": {"value": 1.0 / m["e2e_s"], "unit": "matvec/s", "h2d_bytes_per_step": int(w.esize * mu * w.n_global), "d2h_bytes_per_step": int(w.esize * mu * w.n_global), "ms_per_step": 1e3 * m["e2e_s"],
+                "host_buffers": "page-locked and mapped (htb_host_register): the kernels read x from and write y to the host vectors over PCIe inside the product (zero copy, mu = 1)" if mu == 1 else "page-locked (htb_host_register), direct DMA",
+                "pageable_value": 1.0 / m["e2e_pageable_s"]},
+        "gpu_launches": int(m["launches"]),
+        "clocks": clocks,
+        "parity_rel_l2_vs_reference": gate["parity"],
+        "dist_parity": dist_parity,
+        "setup_seconds": {"reference_assembly": w.t_build, "pack_and_upload": w.t_upload, "reference_product_once": gate["t_ref"]},
+        "store": {"store_bytes": oinfo["store_bytes"], "descriptor_bytes": oinfo["descriptor_bytes"], "workspace_bytes": oinfo["workspace_bytes"],
+                  "target_blocks": oinfo["nb_target_blocks"], "source_blocks": oinfo["nb_source_blocks"]},
+        "configs": extras,
+    }
+    RESULT["line"] = line
+    log(f"headline: {value:.1f} matvec/s, e2e {1.0 / m['e2e_s']:.1f}, parity {gate['parity']:.1e}")
+    del gate
+
+    npts = args.extra_points
+    base_double = args.dtype == "double" and args.symmetry == "N" and mu == 1
+    # ---- extras on the headline operator -------------------------------------------------------------------------------------
+    if base_double and world == 1:
+        run_section("mu64", lambda: section_multi_rhs(w, 64), 60)       # BASELINE.json configs[2]
+        run_section("mu5", lambda: section_multi_rhs(w, 5, steps=10), 30)  # HPDDM block methods, the reference tests mu = 5
+    if mu == 1 and args.gmres_iterations > 0 and world == 1:
+        run_section("gmres", lambda: section_gmres(w, args.gmres_iterations, value), 20)
+    line["gmres"] = extras.get("gmres")
+    w.close()
+    del w
+
+    def other_workload(name, n, dtype, symmetry, need_s, body):
+        def fn():
+            w2 = Workload(ctx, n, dtype, symmetry)
+            try:
+                return body(w2)
+            finally:
+                w2.close()
+
+        run_section(name, fn, need_s)
+
+    if base_double and world == 1:
+        # north_star item 4: symmetric UPLO storage, both applications from one read
+        other_workload("symmetric", npts or args.n, "double", "S", 45, lambda w2: section_single(w2, args.steps, args.warmup, "symmetric storage"))
+
+        def helm(w2):
+            out = section_single(w2, 10, 3, "helmholtz mu = 1")
+            out["mu64"] = section_multi_rhs(w2, 64, steps=3)
+            return out
+
+        other_workload("helmholtz", npts or args.n, "complex", "N", 150, helm)
+    if base_double and world > 1:
+        # BASELINE.json configs[3]: Helmholtz complex<double>, symmetric UPLO storage, N = 2e6, DistributedOperator on 2/4/8 GPUs
+        other_workload("config3_helmholtz_S_N2e6", npts or 2_000_000, "complex", "S", 150, lambda w2: section_single(w2, 10, 3, "configs[3]"))
+    if base_double and world >= 4:
+        # BASELINE.json configs[4]: Laplace N = 8e6 row-sharded, 200 repeated matvecs inside a GMRES solve (does not fit fewer GPUs)
+        def cfg4(w2):
+            out = section_single(w2, 20, 3, "configs[4]")
+            out["gmres"] = section_gmres(w2, args.gmres_iterations or 200, out["value"])
+            return out
+
+        other_workload("config4_laplace_N8e6_gmres", npts or 8_000_000, "double", "N", 260, cfg4)
+
+    watchdog.cancel()
     if rank == 0:
-        out = {
-            "metric": "H-matvecs/s", "value": value, "unit": "matvec/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64" if dtype == np.float64 else "c128", "data": "synthetic",
-            "config": {
-                "workload": workload_label(args),
-                "n": args.n, "mu": mu, "parallelism": (f"row-strips x{world}, gather of x: " + {0: "none", 1: "NCCL broadcasts", 2: "peer-memory push over NVLink"}[op.info()["dist_gather"]]) if world > 1 else "single GPU",
-                "l2": f"inputs larger than L2: {esize * C_total / world / 1e9:.2f} GB of coefficients streamed per GPU per step vs 126 MB L2 (no flush needed)",
-                "coefficients": C_total, "leaves": int(oinfo["nb_leaves"]) if world == 1 else None,
-                "packer": {k: int(v) for k, v in (kv.split("=") for kv in args.opt)},
-            },
-            "achieved_hbm_gbs": achieved_total,
-            "achieved_hbm_frac_per_gpu": achieved_total / world / peak,
-            "algorithmic_bytes_per_step": bytes_step,
-            "roofline": {**roof, "traffic": traffic,
-                         "other_kernels_ms_per_step": {"reduce": reduce_ms_step, "apply": apply_ms_step, "combine": pt["combine"]["ms"] / prof_steps}},
-            "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "matvec/s", "h2d_bytes_per_step": int(esize * mu * n_global), "d2h_bytes_per_step": int(esize * mu * n_global), "ms_per_step": 1e3 * e2e_s / args.steps,
-                    "host_buffers": "page-locked and mapped (htb_host_register): the kernels read x from and write y to the host vectors over PCIe inside the product (zero copy, mu = 1)" if mu == 1 else "page-locked (htb_host_register), direct DMA", "pageable_value": args.steps / e2e_pageable_s},
-            "gmres": gm,
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "parity_rel_l2_vs_reference": parity,
-            "setup_seconds": {"reference_assembly": t_build, "pack_and_upload": t_upload, "reference_product_once": t_ref_once},
-            "store": {"store_bytes": oinfo["store_bytes"], "descriptor_bytes": oinfo["descriptor_bytes"], "workspace_bytes": oinfo["workspace_bytes"],
-                      "target_blocks": oinfo["nb_target_blocks"], "source_blocks": oinfo["nb_source_blocks"]},
-        }
-        print(json.dumps(out), flush=True)
-    op.close()
+        print_line_once()
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        ctx.dist.barrier()
+        ctx.dist.destroy_process_group()
 
 
 def main():
