@@ -109,6 +109,9 @@ class htb_packed_side(C.Structure):
         ("munits", C.c_void_p),
         ("combine_m", C.c_void_p),
         ("owner", C.c_void_p),
+        ("aux_bytes", C.c_int64),
+        ("aux_reduce", C.c_void_p),
+        ("aux_apply", C.c_void_p),
     ]
 
 

@@ -124,6 +124,11 @@ static int upload_store(htb_operator *h, const Packer &pk) {
             break;
         if ((status = upload_vector(sl.combine_m, &sd.combine_m, h->owned)) != HTB_OK)
             break;
+        if ((status = upload_vector(sl.aux_reduce, &sd.aux_reduce, h->owned)) != HTB_OK)
+            break;
+        if ((status = upload_vector(sl.aux_apply, &sd.aux_apply, h->owned)) != HTB_OK)
+            break;
+        h->descriptor_bytes += 2 * sl.aux_reduce.size();
         sd.n_combine_m = static_cast<int>(sl.combine_m.size());
         h->descriptor_bytes += sl.munits.size() * sizeof(MUnit) + sl.combine_m.size() * sizeof(CombineEntry);
         h->descriptor_bytes += sl.blocks.size() * sizeof(BlockDesc) + sl.stages.size() * sizeof(StageDesc) + sl.order.size() * 4 + sl.combine.size() * sizeof(CombineEntry) + sl.combine_dst.size() * sizeof(CombineDst);
@@ -323,10 +328,13 @@ static int ensure_mscratch(htb_operator *h, int vs) {
     return HTB_OK;
 }
 
-static int run_product_m(htb_operator *h, char trans, double alpha, const double *in, double beta, double *out, int mu) {
+static int run_product_m(htb_operator *h, char trans, const double *alpha, const double *in, const double *beta, double *out, int mu) {
     const char sym   = h->symmetry;
     const bool twice = sym != 'N' && (h->side[0].any_twice || h->side[1].any_twice);
     const int D      = h->row_offset - h->col_offset;
+    const bool cplx  = h->dtype == HTB_COMPLEX_DOUBLE;
+    const int W      = cplx ? 2 : 1; // doubles per entry: the kernels address complex matrices through their real view
+    const int group  = 64 / W;       // right-hand sides per pass
     cudaStream_t st  = h->stream;
     int rc;
     auto timed = [&](int kind, auto &&launch, const char *what) -> int {
@@ -346,37 +354,41 @@ static int run_product_m(htb_operator *h, char trans, double alpha, const double
         h->launches++;
         return HTB_OK;
     };
-    for (int col0 = 0; col0 < mu; col0 += 64) {
-        const int mc = std::min(64, mu - col0), vs = (mc + 7) & ~7;
-        if ((rc = ensure_mscratch(h, (std::min(64, mu) + 7) & ~7)) != HTB_OK)
+    for (int col0 = 0; col0 < mu; col0 += group) {
+        const int mc = std::min(group, mu - col0) * W, vs = (mc + 7) & ~7;
+        if ((rc = ensure_mscratch(h, (std::min(group, mu) * W + 7) & ~7)) != HTB_OK)
             return rc;
         double *M1 = static_cast<double *>(h->d_mscratch);
         double *M2 = M1 + h->mscratch_elems * static_cast<size_t>(h->mscratch_vs + 8);
         MArgs base;
-        base.ld_in = mu, base.ld_out = mu, base.col0 = col0, base.mc = mc, base.vs = vs, base.vsp = vs + 8, base.alpha = alpha;
+        base.ld_in = mu * W, base.ld_out = mu * W, base.col0 = col0 * W, base.mc = mc, base.vs = vs, base.vsp = vs + 8, base.cplx = cplx ? 1 : 0;
+        base.alpha = alpha[0], base.alpha_im = cplx ? alpha[1] : 0.;
         // ps: side streamed by REDUCE_M (producers), cs: side streamed by APPLY_M (consumers)
-        auto direction = [&](int cs, double *M, int in_shift, long long in_rows, int out_shift, long long out_rows, double b, int twice_only) -> int {
+        auto direction = [&](int cs, double *M, int in_shift, long long in_rows, int out_shift, long long out_rows, double b_re, double b_im, int twice_only, int conj) -> int {
             const int ps = 1 - cs;
             MArgs r      = base;
-            r.in = in, r.in_rows = in_rows, r.in_shift = in_shift, r.mscratch = M, r.twice_only = twice_only;
+            r.in = in, r.in_rows = in_rows, r.in_shift = in_shift, r.mscratch = M, r.twice_only = twice_only, r.conj = conj;
             int rc2;
             if (h->side[ps].stream && (rc2 = timed(HTB_PASS_REDUCE, [&]() { return launch_reduce_m(h->side[ps], h->launch_cfg, r, st); }, "reduce_m")) != HTB_OK)
                 return rc2;
             if (h->side[cs].n_combine_m && (rc2 = timed(HTB_PASS_COMBINE, [&]() { return launch_combine_m(h->side[cs], M, vs, twice_only, st); }, "combine_m")) != HTB_OK)
                 return rc2;
             MArgs ap = r;
-            ap.out = out, ap.out_rows = out_rows, ap.out_shift = out_shift, ap.beta = b;
+            ap.out = out, ap.out_rows = out_rows, ap.out_shift = out_shift, ap.beta = b_re, ap.beta_im = b_im;
             return timed(HTB_PASS_APPLY, [&]() { return launch_apply_m(h->side[cs], h->launch_cfg, ap, st); }, "apply_m");
         };
+        const double b_re = beta[0], b_im = cplx ? beta[1] : 0.;
+        const int herm = (sym == 'H' && cplx) ? 1 : 0; // second application of a Hermitian leaf stored once: conjugate-transposed
         if (trans == 'N') {
-            if ((rc = direction(0, M1, 0, h->nb_cols, 0, h->nb_rows, beta, 0)) != HTB_OK)
+            if ((rc = direction(0, M1, 0, h->nb_cols, 0, h->nb_rows, b_re, b_im, 0, 0)) != HTB_OK)
                 return rc;
-            if (twice && (rc = direction(1, M2, D, h->nb_cols, -D, h->nb_rows, 1.0, 1)) != HTB_OK)
+            if (twice && (rc = direction(1, M2, D, h->nb_cols, -D, h->nb_rows, 1.0, 0.0, 1, herm)) != HTB_OK)
                 return rc;
         } else {
-            if ((rc = direction(1, M1, 0, h->nb_rows, 0, h->nb_cols, beta, 0)) != HTB_OK)
+            const int conj = (trans == 'C' && cplx) ? 1 : 0;
+            if ((rc = direction(1, M1, 0, h->nb_rows, 0, h->nb_cols, b_re, b_im, 0, conj)) != HTB_OK)
                 return rc;
-            if (twice && (rc = direction(0, M2, -D, h->nb_rows, D, h->nb_cols, 1.0, 1)) != HTB_OK)
+            if (twice && (rc = direction(0, M2, -D, h->nb_rows, D, h->nb_cols, 1.0, 0.0, 1, 0)) != HTB_OK)
                 return rc;
         }
     }
@@ -403,7 +415,7 @@ int product_device(htb_operator *h, char trans, const void *alpha, const void *i
             HTB_CUDA(launch_wait_flags(split->flags, split->world, split->epoch, h->stream));
         else if (split && split->gather_done)
             HTB_CUDA(cudaStreamWaitEvent(h->stream, split->gather_done, 0));
-        return run_product_m(h, trans, *static_cast<const double *>(alpha), static_cast<const double *>(in), *static_cast<const double *>(beta), static_cast<double *>(out), mu);
+        return run_product_m(h, trans, static_cast<const double *>(alpha), static_cast<const double *>(in), static_cast<const double *>(beta), static_cast<double *>(out), mu);
     }
     for (int c = 0; c < mu; c++) {
         if (h->dtype == HTB_DOUBLE)
@@ -672,9 +684,9 @@ int htb_create(const htb_hmatrix_desc *desc, htb_handle *out) {
     if (h->launch_cfg.m_ring_stages < 2 || h->launch_cfg.m_ring_stages > 8 || h->launch_cfg.m_reduce_ring_stages < 2 || h->launch_cfg.m_reduce_ring_stages > 8)
         return fail(HTB_ERR_INVALID, "m_ring_stages / m_reduce_ring_stages must be in [2, 8]");
     HTB_CUDA(configure_kernels(h->launch_cfg));
-    h->m_path_ok = h->dtype == HTB_DOUBLE && std::max(reduce_m_smem_bytes(h->launch_cfg, 64), apply_m_smem_bytes(h->launch_cfg)) <= static_cast<size_t>(prop.sharedMemPerBlockOptin);
+    h->m_path_ok = std::max(reduce_m_smem_bytes(h->launch_cfg, 64, h->esize), apply_m_smem_bytes(h->launch_cfg)) <= static_cast<size_t>(prop.sharedMemPerBlockOptin);
     if (h->m_path_ok)
-        HTB_CUDA(configure_mkernels(h->launch_cfg));
+        HTB_CUDA(configure_mkernels(h->launch_cfg, h->esize));
     h->mscratch_elems  = pk->mscratch_elems;
     g_pdl              = option("pdl") != 0;
     h->fused_symmetric = option("fused_symmetric") != 0 && fused_smem_bytes(h->launch_cfg, 16) <= static_cast<size_t>(prop.sharedMemPerBlockOptin);
@@ -952,6 +964,9 @@ int htb_pack_host(const htb_hmatrix_desc *desc, int side, htb_packed_side *out) 
         out->combine       = own->layout.combine.data();
         out->stream        = own->stream.data();
         out->owner         = own;
+        out->aux_bytes     = static_cast<int64_t>(own->layout.aux_reduce.size());
+        out->aux_reduce    = own->layout.aux_reduce.data();
+        out->aux_apply     = own->layout.aux_apply.data();
     } catch (const std::exception &ex) {
         return fail(HTB_ERR_INVALID, ex.what());
     }

@@ -20,6 +20,8 @@ struct SideDevice {
     const CombineEntry *combine     = nullptr; // direction whose consumer is this side
     const CombineDst *combine_dst   = nullptr;
     const MUnit *munits             = nullptr; // multi-RHS side table, stage order
+    const unsigned char *aux_reduce = nullptr; // multi-RHS aux records (runs + column tables), REDUCE_M role
+    const unsigned char *aux_apply  = nullptr; // same offsets, APPLY_M role
     const CombineEntry *combine_m   = nullptr; // multi-RHS partial sums of the direction whose consumer is this side
     int n_combine_m                 = 0;
     int n_blocks                    = 0;

@@ -6,7 +6,9 @@
 
 namespace htb {
 
-// One pass over a side for a group of mc <= 64 right-hand sides starting at column col0 of ROW-major matrices.
+// One pass over a side for a group of mc <= 64 REAL columns starting at real column col0 of ROW-major matrices. A
+// complex<double> matrix is addressed through its real view (re / im interleaved): ld_in, ld_out, col0, mc, vs count
+// doubles (twice the complex counts), rows stay rows.
 struct MArgs {
     const double *in  = nullptr; // input matrix (REDUCE_M: multiplied rows; APPLY_M: rows of dense leaves, direction 0)
     long long in_rows = 0;
@@ -21,17 +23,20 @@ struct MArgs {
     int vsp           = 0; // vector stride of the scratch = vs + 8 (padded: conflict-free fragments once staged in shared memory)
     double *mscratch  = nullptr; // one multi-RHS scratch copy: [TF | PARTM[0] | PARTM[1]] x vsp
     double alpha = 0., beta = 0.;
+    double alpha_im = 0., beta_im = 0.; // complex<double> only
     int beta_is_zero = 0;
     int twice_only   = 0;
+    int cplx         = 0; // coefficients are complex<double>
+    int conj         = 0; // conjugate the coefficients (trans == 'C', Hermitian second application)
 };
 
 cudaError_t launch_reduce_m(const SideDevice &side, const LaunchConfig &cfg, const MArgs &args, cudaStream_t stream);
 cudaError_t launch_apply_m(const SideDevice &side, const LaunchConfig &cfg, const MArgs &args, cudaStream_t stream);
 // Sums the partials of the direction whose consumer is `side` into TF.
 cudaError_t launch_combine_m(const SideDevice &side, double *mscratch, int vs, int twice_only, cudaStream_t stream);
-size_t reduce_m_smem_bytes(const LaunchConfig &cfg, int vs);
+size_t reduce_m_smem_bytes(const LaunchConfig &cfg, int vs, size_t esize);
 size_t apply_m_smem_bytes(const LaunchConfig &cfg);
-cudaError_t configure_mkernels(const LaunchConfig &cfg);
+cudaError_t configure_mkernels(const LaunchConfig &cfg, size_t esize);
 
 } // namespace htb
 #endif

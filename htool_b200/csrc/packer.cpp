@@ -328,6 +328,25 @@ void Packer::make_incidence(int s) {
             m_csr_leaf[s][e]                      = static_cast<uint32_t>(i);
             m_inc_index[s][m_chunk_ptr[s][i] + c] = e;
         }
+    // Inside a block, order the incidences by (first row, height, applied-twice): the panels acting on the same rows of
+    // the block become consecutive in the stream and form RUNS (store.hpp) for the multi-RHS kernels. The sort is stable,
+    // so leaf order — hence the summation order — stays fixed inside a run.
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int b = 0; b < nb; b++) {
+        const uint64_t e0 = m_csr_ptr[s][b], e1 = m_csr_ptr[s][b + 1];
+        auto key = [&](uint32_t li) {
+            int lo, hi;
+            chunk_range(s, li, b - m_first_blk[s][li], lo, hi);
+            const htb_leaf &l = m_leaves[li];
+            const uint64_t r0 = static_cast<uint64_t>(start_of(s, l) + lo - m_block_start[s][b]);
+            return (r0 << 32) | (static_cast<uint64_t>(hi - lo) << 1) | ((l.flags & HTB_LEAF_APPLY_TRANSPOSED_TOO) ? 1u : 0u);
+        };
+        std::stable_sort(m_csr_leaf[s].begin() + e0, m_csr_leaf[s].begin() + e1, [&](uint32_t a, uint32_t c) { return key(a) < key(c); });
+        for (uint64_t e = e0; e < e1; e++) {
+            const uint32_t li                                              = m_csr_leaf[s][e];
+            m_inc_index[s][m_chunk_ptr[s][li] + (b - m_first_blk[s][li])] = e;
+        }
+    }
     m_unit_ptr[s].assign(n_inc + 1, 0);
     for (int b = 0; b < nb; b++)
         for (uint64_t e = m_csr_ptr[s][b]; e < m_csr_ptr[s][b + 1]; e++) {
@@ -465,6 +484,10 @@ void Packer::make_mtables() {
     for (int s = 0; s < 2; s++) {
         const int nb = static_cast<int>(side[s].blocks.size());
         side[s].munits.assign(m_unit_ptr[s].back(), MUnit{0, 0, 0, 0});
+        // aux records (runs + column tables, store.hpp) of every block, concatenated below
+        std::vector<std::vector<unsigned char>> aux_r(nb), aux_a(nb);
+        std::vector<std::vector<uint32_t>> aux_len(nb); // per stage of the block, bytes
+        bool aux_overflow = false;
 #pragma omp parallel for schedule(dynamic, 64)
         for (int b = 0; b < nb; b++) {
             // same walk and the same cuts as layout_block / fill_block; inside a stage panel units come first
@@ -475,6 +498,51 @@ void Packer::make_mtables() {
                 if (cut.nu == 0)
                     return;
                 std::stable_partition(pending.begin(), pending.end(), [](const UnitSpec &u) { return u.kind != UNIT_ADDVEC; });
+                // runs: consecutive panel units on the same rows (and the same applied-twice flag) are one h x K panel
+                {
+                    std::vector<RunDesc> runs;
+                    std::vector<uint32_t> col_out, col_src;
+                    uint32_t eoff = 0;
+                    for (const UnitSpec &u : pending) {
+                        if (u.kind == UNIT_ADDVEC)
+                            break;
+                        const htb_leaf &l = m_leaves[u.leaf];
+                        const uint64_t gp = m_piece_ptr[u.leaf] + u.piece;
+                        if (runs.empty() || runs.back().row0 != u.row0 || static_cast<uint32_t>(runs.back().h_minus_1) + 1u != u.h || (runs.back().flags & 1u) != u.twice ||
+                            static_cast<uint32_t>(runs.back().K) + u.w > 0xffffu)
+                            runs.push_back(RunDesc{eoff, static_cast<uint16_t>(col_out.size()), 0, static_cast<uint8_t>(u.row0), static_cast<uint8_t>(u.h - 1u), static_cast<uint8_t>(u.twice), 0, 0u});
+                        runs.back().K = static_cast<uint16_t>(runs.back().K + u.w);
+                        // producer role (this side is streamed by REDUCE_M; consumer side cs = 1 - s)
+                        uint32_t out = 0;
+                        if (!(l.rank < 0 && s == 1)) { // (dense leaves hold no panel on side 1)
+                            const uint32_t po = m_partm_off[1 - s][gp];
+                            out               = po == kDirect ? m_tf_off[gp] : po + static_cast<uint32_t>(u.chunk) * static_cast<uint32_t>(piece_len(l, u.piece));
+                        }
+                        for (uint32_t k = 0; k < u.w; k++) {
+                            col_out.push_back(out + k);
+                            col_src.push_back(u.kind == UNIT_LOWRANK ? m_tf_off[gp] + k : (0x80000000u | (static_cast<uint32_t>(l.col_offset) + u.k0 + k)));
+                        }
+                        eoff += u.elems();
+                    }
+                    const size_t ncols4 = (col_out.size() + 3u) & ~size_t(3);
+                    const size_t bytes  = sizeof(AuxHeader) + runs.size() * sizeof(RunDesc) + ncols4 * 4u;
+                    if (bytes > aux_slot_bytes(static_cast<uint32_t>(opt.cseg_bytes)) || bytes / 16u > 0x7fffu)
+                        aux_overflow = true; // (cannot happen: a stage holds <= cseg_bytes / esize columns; reported after the parallel loop)
+                    col_out.resize(ncols4, 0u);
+                    col_src.resize(ncols4, 0u);
+                    const AuxHeader ah{static_cast<uint32_t>(runs.size()), static_cast<uint32_t>(col_out.size()), {0u, 0u}};
+                    for (int role = 0; role < 2; role++) {
+                        std::vector<unsigned char> &dst = role == 0 ? aux_r[b] : aux_a[b];
+                        const size_t at                 = dst.size();
+                        dst.resize(at + bytes);
+                        std::memcpy(dst.data() + at, &ah, sizeof(ah));
+                        if (!runs.empty())
+                            std::memcpy(dst.data() + at + sizeof(ah), runs.data(), runs.size() * sizeof(RunDesc));
+                        if (ncols4)
+                            std::memcpy(dst.data() + at + sizeof(ah) + runs.size() * sizeof(RunDesc), (role == 0 ? col_out : col_src).data(), ncols4 * 4u);
+                    }
+                    aux_len[b].push_back(static_cast<uint32_t>(bytes));
+                }
                 uint32_t poff = 0, in_batch = 0;
                 bool first    = true;
                 for (const UnitSpec &u : pending) {
@@ -521,6 +589,36 @@ void Packer::make_mtables() {
                 pending.push_back(u);
             });
             close();
+        }
+        if (aux_overflow)
+            throw std::runtime_error("multi-RHS aux record exceeds its slot");
+        // concatenate the per-block aux records; every stage learns where its record is
+        uint64_t total = 0;
+        for (int b = 0; b < nb; b++)
+            total += aux_r[b].size();
+        if (total / 16u >= (uint64_t(1) << 32))
+            throw std::runtime_error("multi-RHS aux tables too large");
+        side[s].aux_reduce.resize(total);
+        side[s].aux_apply.resize(total);
+        uint64_t at = 0;
+        for (int b = 0; b < nb; b++) {
+            const BlockDesc &bd = side[s].blocks[b];
+            if (aux_len[b].size() != bd.n_stages)
+                throw std::runtime_error("internal: aux records do not match the stages");
+            if (!aux_r[b].empty()) {
+                std::memcpy(side[s].aux_reduce.data() + at, aux_r[b].data(), aux_r[b].size());
+                std::memcpy(side[s].aux_apply.data() + at, aux_a[b].data(), aux_a[b].size());
+            }
+            uint64_t off = at;
+            for (uint32_t q = 0; q < bd.n_stages; q++) {
+                StageDesc &sd = side[s].stages[bd.first_stage + q];
+                sd.aux_off16  = static_cast<uint32_t>(off / 16u);
+                sd.flags      = static_cast<uint16_t>((sd.flags & 1u) | ((aux_len[b][q] / 16u) << 1));
+                off += aux_len[b][q];
+            }
+            at += aux_r[b].size();
+            std::vector<unsigned char>().swap(aux_r[b]);
+            std::vector<unsigned char>().swap(aux_a[b]);
         }
     }
 }

@@ -92,11 +92,11 @@ struct StageDesc {
     uint32_t nbytes;   // multiple of 16
     uint32_t c_off;    // first element of the stage's c segment in CS[side] (segment start is 16 B aligned)
     uint16_t c_len;    // elements of the c segment, padded so that its byte size is a multiple of 16
-    uint16_t flags;    // bit 0: holds at least one applied-twice unit
+    uint16_t flags;    // bit 0: holds at least one applied-twice unit; bits [1, 16): length of the stage's multi-RHS aux record in 16 B units
     uint32_t first_unit; // index of the stage's first unit in the side's MUnit table
     uint16_t n_units;    // units of the stage
     uint16_t n_panel;    // of which coefficient-carrying (they come first)
-    uint32_t reserved;
+    uint32_t aux_off16;  // offset of the stage's multi-RHS aux record in the side's aux arrays, in 16 B units
 };
 static_assert(sizeof(StageDesc) == 32, "StageDesc must be 32 bytes");
 
@@ -151,6 +151,36 @@ HTB_HD inline uint32_t munit_rows8(uint32_t row0, uint32_t h) { return (((row0 &
 HTB_HD inline uint32_t munit_ld(uint32_t row0, uint32_t h) { return munit_rows8(row0, h) + 4u; }
 constexpr uint32_t kPanelBufferElems = 4608; // 36 KiB of doubles
 
+// ---- multi-RHS aux records: RUNS ----------------------------------------------------------------------------------
+// Inside a block the packer orders the units by (first row, height): all the panels that act on the same rows of the
+// block (the U panels / dense leaves of one target cluster, or the V^T panels of one source cluster) are then
+// CONSECUTIVE in the stream and, having the same leading dimension, form ONE column-major panel h x K (K = sum of the
+// unit widths): a RUN. The multi-RHS kernels contract whole runs — C[rows] += Panel (h x K) . B (K x mu) with K in the
+// hundreds — instead of unit by unit, so that no DMMA tile is padded along K (the rank of a leaf is not a multiple of the
+// 8 / 4 of m8n8k4) and the per-unit overhead disappears. What a column of a run multiplies / produces is listed per
+// COLUMN in the stage's aux record, which the producer lane bulk-copies next to the stage:
+//   [AuxHeader | RunDesc x n_runs | uint32 x n_cols (padded to a multiple of 4)]
+// Two arrays with identical offsets exist per side: aux_reduce (column entry = scratch vector receiving the column's
+// result in REDUCE_M) and aux_apply (column entry = scratch vector, or input-matrix row | bit 31, the column multiplies
+// in APPLY_M).
+struct AuxHeader {
+    uint32_t n_runs, n_cols, reserved[2];
+};
+static_assert(sizeof(AuxHeader) == 16, "AuxHeader must be 16 bytes");
+struct RunDesc {
+    uint32_t data_off; // element offset of the run's panel inside the stage's coefficient region
+    uint16_t col0;     // first column of the run in the stage's column table
+    uint16_t K;        // columns of the run
+    uint8_t row0;      // first row inside the block
+    uint8_t h_minus_1;
+    uint8_t flags;     // bit 0: applied-twice units (runs are homogeneous)
+    uint8_t reserved8;
+    uint32_t reserved;
+};
+static_assert(sizeof(RunDesc) == 16, "RunDesc must be 16 bytes");
+// capacity of a stage's aux record: a stage holds <= cseg_bytes / esize columns (c-segment limit), one run per column at worst
+HTB_HD inline uint32_t aux_slot_bytes(uint32_t cseg_bytes) { return (16u + 20u * (cseg_bytes / 8u) + 127u) & ~127u; }
+
 struct PackOptions {
     int block_rows  = 0;     // 32, 64 or 128; 0 = automatic (128 for double, 64 for complex<double>)
     int piece_cols  = 16;    // columns of a unit (<= 32); lowered automatically so that a unit fits a stage
@@ -185,6 +215,7 @@ struct SideLayout {
     std::vector<MUnit> munits;
     std::vector<CombineEntry> combine_m; // src = PARTM offset, dst_first = TF offset, n_dst unused
     uint64_t partm_base = 0, partm_elems = 0; // in vectors, inside the multi-RHS scratch [TF | PARTM[0] | PARTM[1]]
+    std::vector<unsigned char> aux_reduce, aux_apply; // per-stage aux records (runs + column tables), same offsets in both
 };
 
 } // namespace htb

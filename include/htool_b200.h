@@ -267,6 +267,9 @@ typedef struct htb_packed_side {
     const void *munits;       /* n_munits x 16 B (MUnit), stage order */
     const void *combine_m;    /* n_combine_m x 16 B (CombineEntry: src = PARTM offset, dst_first = TF offset) */
     void *owner;              /* opaque, released by htb_pack_free */
+    int64_t aux_bytes;        /* multi-RHS aux records of the side's stages (store.hpp: AuxHeader | RunDesc[] | column table) */
+    const void *aux_reduce;   /* column entry = scratch vector receiving the column's REDUCE_M result */
+    const void *aux_apply;    /* column entry = scratch vector (or input row | bit 31) the column multiplies in APPLY_M */
 } htb_packed_side;
 int htb_pack_host(const htb_hmatrix_desc *desc, int side, htb_packed_side *out);
 int htb_pack_free(htb_packed_side *packed);

@@ -15,11 +15,13 @@ import numpy as np
 from htool_b200 import capi
 
 BLOCK_DT = np.dtype([("row_start", "<i4"), ("nrows", "<i4"), ("first_stage", "<u4"), ("n_stages", "<u4"), ("flags", "<u4"), ("r0", "<u4"), ("r1", "<u4"), ("r2", "<u4")])
-STAGE_DT = np.dtype([("byte_off", "<u8"), ("nbytes", "<u4"), ("c_off", "<u4"), ("c_len", "<u2"), ("flags", "<u2"), ("first_unit", "<u4"), ("n_units", "<u2"), ("n_panel", "<u2"), ("reserved", "<u4")])
+STAGE_DT = np.dtype([("byte_off", "<u8"), ("nbytes", "<u4"), ("c_off", "<u4"), ("c_len", "<u2"), ("flags", "<u2"), ("first_unit", "<u4"), ("n_units", "<u2"), ("n_panel", "<u2"), ("aux_off16", "<u4")])
 COMBINE_DT = np.dtype([("src", "<u4"), ("dst_first", "<u4"), ("n_dst", "<u4"), ("packed", "<u4")])
 COMBINE_DST_DT = np.dtype([("slot", "<u4"), ("sub_off", "<u2"), ("sub_len", "<u2")])
 UNIT_DT = np.dtype([("data_off", "<u4"), ("geom", "<u4"), ("out", "<u4"), ("cslot", "<u2"), ("reserved", "<u2")])
 MUNIT_DT = np.dtype([("out", "<u4"), ("src", "<u4"), ("poff", "<u4"), ("flags", "<u4")])
+RUN_DT = np.dtype([("data_off", "<u4"), ("col0", "<u2"), ("K", "<u2"), ("row0", "u1"), ("h_minus_1", "u1"), ("flags", "u1"), ("r8", "u1"), ("r32", "<u4")])
+assert RUN_DT.itemsize == 16
 UNIT_LOWRANK, UNIT_DENSE, UNIT_ADDVEC = 0, 1, 2
 PANEL_BUFFER_ELEMS = 4608
 assert BLOCK_DT.itemsize == 32 and STAGE_DT.itemsize == 32 and COMBINE_DT.itemsize == 16 and COMBINE_DST_DT.itemsize == 8 and UNIT_DT.itemsize == 16
@@ -50,7 +52,34 @@ class PackedSide:
         self.mscratch_elems, self.block_rows = p.mscratch_elems, p.block_rows
         self.stream = _view(p.stream, p.stream_bytes, np.dtype("u1"))
         self.stream_bytes = p.stream_bytes
+        self.aux = {"reduce": _view(p.aux_reduce, p.aux_bytes, np.dtype("u1")), "apply": _view(p.aux_apply, p.aux_bytes, np.dtype("u1"))}
         lib.htb_pack_free(C.byref(p))
+
+    def runs_of_stage(self, st, dtype, role):
+        """The stage's aux record (store.hpp): yields (row0, h, twice, panel (h, K), column entries (K,)) per RUN, the
+        panel being read from the stage bytes at the run's data offset, exactly as the multi-RHS kernels do."""
+        sd = self.stages[st]
+        raw = self.stream[int(sd["byte_off"]): int(sd["byte_off"]) + int(sd["nbytes"])]
+        n_units, data_off, n_panel, _ = np.frombuffer(raw[:16].tobytes(), dtype="<u4")
+        isz = np.dtype(dtype).itemsize
+        data = np.frombuffer(raw[int(data_off):].tobytes()[: (len(raw) - int(data_off)) // isz * isz], dtype=dtype)
+        aux_len = (int(sd["flags"]) >> 1) * 16
+        rec = self.aux[role][int(sd["aux_off16"]) * 16: int(sd["aux_off16"]) * 16 + aux_len].tobytes()
+        assert aux_len >= 16
+        n_runs, n_cols = (int(v) for v in np.frombuffer(rec[:8], dtype="<u4"))
+        assert aux_len == 16 + 16 * n_runs + 4 * n_cols and n_cols % 4 == 0
+        runs = np.frombuffer(rec[16: 16 + 16 * n_runs], dtype=RUN_DT)
+        cols = np.frombuffer(rec[16 + 16 * n_runs:], dtype="<u4")
+        covered = 0
+        for rd in runs:
+            h, K = int(rd["h_minus_1"]) + 1, int(rd["K"])
+            ld = (h + 1) & ~1 if isz == 8 else h
+            panel = data[int(rd["data_off"]): int(rd["data_off"]) + ld * K].reshape(K, ld).T[:h, :]
+            covered += K
+            yield int(rd["row0"]), h, int(rd["flags"]) & 1, panel, cols[int(rd["col0"]): int(rd["col0"]) + K]
+        # the runs cover exactly the panel columns of the stage
+        units = np.frombuffer(raw[16:16 + 16 * int(n_units)].tobytes(), dtype=UNIT_DT)[: int(n_panel)]
+        assert covered == sum((int(u["geom"]) >> 16) & 0xFF for u in units)
 
     def units_of_stage(self, st, dtype):
         """Yields (unit record, row0, h, w, kind, twice, panel as an (h, w) array) for one stage."""
@@ -169,7 +198,8 @@ class Emulator:
         assert all(k != UNIT_ADDVEC for k in kinds[:n_panel]) and all(k == UNIT_ADDVEC for k in kinds[n_panel:])
         return [(u, side.munits[first + i]) for i, u in enumerate(units)], n_panel
 
-    def reduce_m(self, s, X, in_shift, M, twice_only):
+    def reduce_m(self, s, X, in_shift, M, twice_only, conj=False):
+        """REDUCE_M: per RUN, T = op(panel)^T X[rows]; row k of the result goes to the scratch vector cols[k]."""
         side = self.side[s]
         for b in side.order:
             bd = side.blocks[b]
@@ -182,12 +212,16 @@ class Emulator:
             for st in range(int(bd["first_stage"]), int(bd["first_stage"] + bd["n_stages"])):
                 if twice_only and not (side.stages[st]["flags"] & 1):
                     continue
+                # the unit view and the run view of a stage describe the same panels
                 pairs, n_panel = self._munits_of_stage(s, st)
-                for (u, row0, h, w, kind, twice, panel), mu in pairs[:n_panel]:
+                unit_out = np.concatenate([int(mu["out"]) + np.arange(w) for (u, row0, h, w, kind, twice, panel), mu in pairs[:n_panel]] or [np.zeros(0, np.int64)])
+                col = 0
+                for row0, h, twice, panel, cols in side.runs_of_stage(st, self.dtype, "reduce"):
+                    assert np.array_equal(cols, unit_out[col: col + len(cols)])
+                    col += len(cols)
                     if twice_only and not twice:
                         continue
-                    o = int(mu["out"])
-                    M[o: o + w] = panel.T @ xin[row0: row0 + h]
+                    M[cols.astype(np.int64)] = (panel.conj() if conj else panel).T @ xin[row0: row0 + h]
 
     def combine_m(self, s, M, twice_only):
         for ce in self.side[s].combine_m:
@@ -198,7 +232,8 @@ class Emulator:
             src, dst = int(ce["src"]), int(ce["dst_first"])
             M[dst: dst + ln] = M[src: src + n_sum * ln].reshape(n_sum, ln, -1).sum(axis=0)
 
-    def apply_m(self, s, X, in_shift, out, out_shift, M, alpha, beta, twice_only):
+    def apply_m(self, s, X, in_shift, out, out_shift, M, alpha, beta, twice_only, conj=False):
+        """APPLY_M: per RUN, C[rows] += op(panel) B with B row k = scratch vector cols[k] or input row (cols[k] & ~bit31)."""
         side = self.side[s]
         for b in side.order:
             bd = side.blocks[b]
@@ -208,65 +243,56 @@ class Emulator:
             for st in range(int(bd["first_stage"]), int(bd["first_stage"] + bd["n_stages"])):
                 if twice_only and not (side.stages[st]["flags"] & 1):
                     continue
-                pairs, n_panel = self._munits_of_stage(s, st)
-                poff_end, in_batch = 0, 0
-                for i, ((u, row0, h, w, kind, twice, panel), mu) in enumerate(pairs):
-                    src = int(mu["src"])
-                    assert (int(mu["flags"]) >> 8) & 0xFF == (h if kind == UNIT_ADDVEC else w) and bool(int(mu["flags"]) & 2) == (kind == UNIT_LOWRANK)
-                    if kind != UNIT_ADDVEC:
-                        # panel-buffer batches: disjoint regions inside the buffer, <= 32 units per batch
-                        rows8 = (((row0 & 7) + h + 7) >> 3) << 3
-                        need = (rows8 + 4) * w
-                        if int(mu["flags"]) & 1:
-                            poff_end, in_batch = 0, 0
-                        else:
-                            assert i > 0
-                        assert int(mu["poff"]) == poff_end and poff_end + need <= PANEL_BUFFER_ELEMS and in_batch < 32
-                        poff_end += need
-                        in_batch += 1
+                for row0, h, twice, panel, cols in side.runs_of_stage(st, self.dtype, "apply"):
                     if twice_only and not twice:
                         continue
-                    if kind == UNIT_ADDVEC:
-                        acc[row0: row0 + h] += M[src: src + h]
+                    B = np.zeros((len(cols), X.shape[1]), self.dtype)
+                    dense = (cols & 0x80000000) != 0
+                    rows = (cols[dense] & 0x7FFFFFFF).astype(np.int64) + in_shift
+                    ok = (rows >= 0) & (rows < X.shape[0])
+                    Bd = np.zeros((int(dense.sum()), X.shape[1]), self.dtype)
+                    Bd[ok] = X[rows[ok]]
+                    B[dense] = Bd
+                    B[~dense] = M[cols[~dense].astype(np.int64)]
+                    acc[row0: row0 + h] += (panel.conj() if conj else panel) @ B
+                pairs, n_panel = self._munits_of_stage(s, st)
+                for (u, row0, h, w, kind, twice, panel), mu in pairs[n_panel:]:
+                    assert kind == UNIT_ADDVEC and (int(mu["flags"]) >> 8) & 0xFF == h
+                    if twice_only and not twice:
                         continue
-                    if src & 0x80000000:
-                        rows = (src & 0x7FFFFFFF) + np.arange(w) + in_shift
-                        ok = (rows >= 0) & (rows < X.shape[0])
-                        c = np.zeros((w, X.shape[1]), self.dtype)
-                        c[ok] = X[rows[ok]]
-                    else:
-                        c = M[src: src + w]
-                    acc[row0: row0 + h] += panel @ c
+                    src = int(mu["src"])
+                    acc[row0: row0 + h] += M[src: src + h]
             for i in range(int(bd["nrows"])):
                 g = int(bd["row_start"]) + i + out_shift
                 if 0 <= g < out.shape[0]:
                     out[g] = alpha * acc[i] + (0 if beta == 0 else beta * out[g])
 
     def matrix_product_row_major(self, trans, alpha, X, beta, Y, mu):
-        """run_product_m (double only): X, Y row-major (n x mu)."""
+        """run_product_m of capi.cu (double and complex<double>): X, Y row-major (n x mu)."""
         sym = self.sym
         if (trans == "T" and sym == "H") or (trans == "C" and sym == "S"):
             return 2
-        assert self.dtype == np.float64
         twice = sym != "N" and self.any_twice
+        cplx = self.dtype == np.complex128
         X, Y = X.reshape(-1, mu), Y.reshape(-1, mu)
         nvec = max(1, self.side[0].mscratch_elems)
-        M1, M2 = np.full((nvec, mu), np.nan), np.full((nvec, mu), np.nan)
+        M1, M2 = np.full((nvec, mu), np.nan, self.dtype), np.full((nvec, mu), np.nan, self.dtype)
         D = self.D
 
-        def direction(cs, M, in_shift, out_shift, b, twice_only):
-            self.reduce_m(1 - cs, X, in_shift, M, twice_only)
+        def direction(cs, M, in_shift, out_shift, b, twice_only, conj):
+            self.reduce_m(1 - cs, X, in_shift, M, twice_only, conj)
             self.combine_m(cs, M, twice_only)
-            self.apply_m(cs, X, in_shift, Y, out_shift, M, alpha, b, twice_only)
+            self.apply_m(cs, X, in_shift, Y, out_shift, M, alpha, b, twice_only, conj)
 
+        herm = sym == "H" and cplx
         if trans == "N":
-            direction(0, M1, 0, 0, beta, False)
+            direction(0, M1, 0, 0, beta, False, False)
             if twice:
-                direction(1, M2, D, -D, 1.0, True)
+                direction(1, M2, D, -D, 1.0, True, herm)
         else:
-            direction(1, M1, 0, 0, beta, False)
+            direction(1, M1, 0, 0, beta, False, trans == "C" and cplx)
             if twice:
-                direction(0, M2, -D, D, 1.0, True)
+                direction(0, M2, -D, D, 1.0, True, False)
         return 0
 
     def vector_product(self, trans, alpha, x, beta, y):

@@ -80,18 +80,19 @@ def test_random_leaf_lists_vs_oracle(capi, seed, dtype_code, symmetric):
             assert flat.oracle_vector_product(trans, alpha, x, beta, yo) == 0
             op.add_vector_product(trans, alpha, x, beta, yg)
             assert rel_err(yg, yo) < TOL, (trans, alpha, beta, rel_err(yg, yo))
-        # mu = 5: column loop over the single-RHS kernels; mu >= 8 (double): FP64 tensor-core kernels, column groups of 64
-        for mu in (5, 8, 13, 64, 70):
+        # mu >= 2: FP64 tensor-core kernels on RUNS (mkernels.cu), column groups of 64 real / 32 complex right-hand sides
+        am, bm = (0.5, 2.0) if flat.np_dtype == np.float64 else (0.5 - 0.3j, 2.0 + 0.25j)
+        for mu in (2, 5, 8, 13, 33, 64, 70):
             X, Y0 = rnd(rng, ni * mu, flat.np_dtype), rnd(rng, no * mu, flat.np_dtype)
             Yo, Yg = Y0.copy(), Y0.copy()
-            flat.oracle_matrix_product_row_major(trans, 0.5, X, 2.0, Yo, mu)
-            op.add_matrix_product_row_major(trans, 0.5, X, 2.0, Yg, mu)
+            flat.oracle_matrix_product_row_major(trans, am, X, bm, Yo, mu)
+            op.add_matrix_product_row_major(trans, am, X, bm, Yg, mu)
             assert rel_err(Yg, Yo) < TOL, (trans, mu, rel_err(Yg, Yo))
             if mu == 13:  # beta == 0 must not read the output
                 Yg = np.full(no * mu, np.nan, flat.np_dtype)
                 Yo = np.zeros(no * mu, flat.np_dtype)
-                flat.oracle_matrix_product_row_major(trans, 0.5, X, 0.0, Yo, mu)
-                op.add_matrix_product_row_major(trans, 0.5, X, 0.0, Yg, mu)
+                flat.oracle_matrix_product_row_major(trans, am, X, 0.0, Yo, mu)
+                op.add_matrix_product_row_major(trans, am, X, 0.0, Yg, mu)
                 assert rel_err(Yg, Yo) < TOL
     op.close()
 
@@ -237,8 +238,7 @@ def test_full_size_properties(capi, have_ref):
     from oracle import refharness as R
 
     R.set_num_threads(__import__("os").cpu_count() or 1)
-    args = __import__("argparse").Namespace(n=1_000_000, dtype="double", symmetry="N", mu=1, gpus=1)
-    case = R.RefCase(**bench.case_kwargs(args))
+    case = R.RefCase(**bench.case_kwargs(1_000_000, "double", "N"))
     n = case.nb_rows
     op = capi.Operator(case.desc)
     assert op.info()["coefficients"] == case.info()["coefficients"] > 2_000_000_000

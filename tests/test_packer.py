@@ -194,24 +194,40 @@ def test_empty_and_degenerate_operators():
 
 
 @pytest.mark.parametrize("seed", range(2))
-@pytest.mark.parametrize("symmetric", [None, "S"])
-def test_multi_rhs_side_tables(seed, symmetric):
-    """MUnit tables / TF + PARTM layout / panel-buffer batches of the multi-RHS path (mkernels.cu), emulated."""
-    flat = random_flatcase(seed=seed, symmetric=symmetric)
+@pytest.mark.parametrize("symmetric,dtype", [(None, 0), ("S", 0), (None, 1), ("S", 1), ("H", 1)])
+def test_multi_rhs_side_tables(seed, symmetric, dtype):
+    """RUNS + column tables (aux records), TF / PARTM layout and MUnit tables of the multi-RHS path (mkernels.cu), emulated,
+    for double and complex<double>."""
+    flat = random_flatcase(seed=seed, symmetric=symmetric, dtype_code=dtype)
     em = Emulator(flat)
     rng = np.random.default_rng(1)
-    for trans in "NT":
+    dt = flat.np_dtype
+    for trans in valid_trans(flat.symmetry):
         ni, no = (flat.nb_cols, flat.nb_rows) if trans == "N" else (flat.nb_rows, flat.nb_cols)
         mu = 5
-        X, Y0 = rnd(rng, ni * mu, np.float64), rnd(rng, no * mu, np.float64)
+        a, b = (0.5, 2.0) if dt == np.float64 else (0.5 - 0.3j, 2.0 + 0.25j)
+        X, Y0 = rnd(rng, ni * mu, dt), rnd(rng, no * mu, dt)
         Yo, Ye = Y0.copy(), Y0.copy()
-        assert flat.oracle_matrix_product_row_major(trans, 0.5, X, 2.0, Yo, mu) == 0
-        assert em.matrix_product_row_major(trans, 0.5, X, 2.0, Ye, mu) == 0
-        assert rel_err(Ye, Yo) < TOL
+        assert flat.oracle_matrix_product_row_major(trans, a, X, b, Yo, mu) == 0
+        assert em.matrix_product_row_major(trans, a, X, b, Ye, mu) == 0
+        assert rel_err(Ye, Yo) < TOL, trans
+
+
+def test_runs_group_the_units_of_a_cluster():
+    """Inside a block the packer orders the units by the rows they act on: a stage's runs are few and wide."""
+    flat, _, _ = load_golden("d_N")
+    em = Emulator(flat)
+    for s in range(2):
+        side = em.side[s]
+        n_runs = n_units = 0
+        for st in range(len(side.stages)):
+            n_runs += sum(1 for _ in side.runs_of_stage(st, em.dtype, "apply"))
+            n_units += int(side.stages[st]["n_panel"])
+        assert n_runs * 2 <= n_units, (s, n_runs, n_units)
 
 
 def test_multi_rhs_side_tables_golden():
-    for name in ("d_N", "d_SL", "d_strip_SU", "d_rect"):
+    for name in ("d_N", "d_SL", "d_strip_SU", "d_rect", "z_HL", "z_SL", "z_N_helmholtz"):
         flat, entries, _ = load_golden(name)
         em = Emulator(flat)
         for e in entries:
