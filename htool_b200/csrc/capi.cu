@@ -28,7 +28,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 namespace {
 std::mutex g_option_mutex;
 std::map<std::string, int64_t> g_options = {
-    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 2048}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 5}, {"m_reduce_ring_stages", 5}, {"mrhs_min", 2}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}};
+    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 2048}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 4}, {"m_b_ring_log2", 2}, {"m_reduce_ring_stages", 5}, {"mrhs_min", 2}, {"m_apply_ctas", 1}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}};
 
 int64_t option(const char *key) {
     std::lock_guard<std::mutex> lock(g_option_mutex);
@@ -681,6 +681,10 @@ int htb_create(const htb_hmatrix_desc *desc, htb_handle *out) {
         return fail(HTB_ERR_INVALID, "the shared-memory ring (ring_stages x stage_bytes) exceeds the shared memory of an SM");
     h->launch_cfg.m_ring_stages        = static_cast<int>(option("m_ring_stages"));
     h->launch_cfg.m_reduce_ring_stages = static_cast<int>(option("m_reduce_ring_stages"));
+    h->launch_cfg.m_apply_ctas         = static_cast<int>(option("m_apply_ctas"));
+    h->launch_cfg.m_b_ring_log2        = static_cast<int>(option("m_b_ring_log2"));
+    if (h->launch_cfg.m_b_ring_log2 < 1 || h->launch_cfg.m_b_ring_log2 > 3)
+        return fail(HTB_ERR_INVALID, "m_b_ring_log2 must be in [1, 3]");
     if (h->launch_cfg.m_ring_stages < 2 || h->launch_cfg.m_ring_stages > 8 || h->launch_cfg.m_reduce_ring_stages < 2 || h->launch_cfg.m_reduce_ring_stages > 8)
         return fail(HTB_ERR_INVALID, "m_ring_stages / m_reduce_ring_stages must be in [2, 8]");
     HTB_CUDA(configure_kernels(h->launch_cfg));

@@ -241,40 +241,116 @@ __global__ void __launch_bounds__((kReduceWarps + 1) * 32) reduce_m_kernel(MSide
 }
 
 // ---- APPLY_M --------------------------------------------------------------------------------------------------------
-// Warp w: column tile ct = w & 7 (real columns 8 ct .. 8 ct + 7 of the group), parity par = w >> 3: it owns the 8-row
+// Warp w < 16: column tile ct = w & 7 (real columns 8 ct .. 8 ct + 7 of the group), parity par = w >> 3: it owns the 8-row
 // tiles 2 j + par, j < 8, of the block for those columns: acc[j] = C[8 (2 j + par) + g][8 ct + 2 tig + {0, 1}].
 //   D[i][c] += A[i][k] B[k][c]:  A = panel fragment P[row][k0 + tig] read from the ring slot, one per row tile the run
-//   meets; B = row (k0 + tig) of what the run's columns multiply, columns 8 ct + g — ONE load per k-step, straight from
-//   global memory (the T vectors REDUCE_M / COMBINE_M just wrote, or rows of the input matrix for dense columns), issued
-//   one k-step ahead of its DMMAs.
-// smem: [ring: slot = stage | aux] [barriers]
+//   meets; B = row (k0 + tig) of what the run's columns multiply, columns 8 ct + g.
+// The B rows (T vectors REDUCE_M / COMBINE_M just wrote, rows of the input matrix for dense columns) form a STREAM in the
+// order of the block's columns. Warp 17, the B producer, walks the column tables of the stages as they arrive and copies
+// the rows with cp.async into a ring of chunks of 32 rows (row stride VSP: conflict-free B fragments), 1 - 2 chunks ahead of
+// the consumers, so that the DRAM latency of the B rows never meets a DMMA. Every run starts at a multiple of 4 in the
+// stream: a k-step never straddles two chunks.
+// smem: [stage ring: slot = stage | aux] [B ring: chunk = 32 x VSP doubles] [barriers]
+constexpr int kBChunk = 32;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct BRing {
+    unsigned char *base;
+    uint64_t *full, *empty;
+    uint32_t chunk_bytes, mask, log2n; // ring of 2^log2n chunks
+};
+
+// The B producer warp: see above. Mirrors the consumers' walk (stages, runs, the applied-twice filter, the 4-alignment of
+// run starts) so that both sides agree on the position of every column in the stream.
 template <bool CPLX>
-__device__ __forceinline__ double load_b(const MArgs &a, const uint32_t *cols, uint32_t col0, uint32_t Kr, uint32_t kk, int ct, int g) {
-    // kk = contraction index of this lane (k0 + tig). complex: kk = 2 k + j, B[2k][c] = T[k][c], B[2k+1][c] = (i T[k])[c]
-    constexpr int CS = CPLX ? 1 : 0;
-    if (kk >= Kr)
-        return 0.;
-    const uint32_t src = cols[col0 + (kk >> CS)];
-    const int c        = 8 * ct + g;
-    if (c >= a.mc)
-        return 0.;
-    const double *p;
-    if (src & 0x80000000u) { // dense column: row of the input matrix
-        const long long r = static_cast<long long>(src & 0x7fffffffu) + a.in_shift;
-        if (r < 0 || r >= a.in_rows)
-            return 0.;
-        p = a.in + r * a.ld_in + a.col0;
-    } else
-        p = a.mscratch + static_cast<size_t>(src) * a.vsp;
-    if (!CPLX || !(kk & 1u))
-        return p[c];
-    // odd contraction index: (i v)[c] = c even ? -im(v) : re(v); conjugated panel: (-i v)[c] = c even ? im(v) : -re(v)
-    const double o = p[c ^ 1];
-    return ((c & 1) != 0) == (a.conj == 0) ? o : -o;
+__device__ __forceinline__ void produce_b(const MSide &ks, const BlockDesc &bd, const MArgs &a, unsigned char *ring, uint32_t slot_bytes, uint64_t *full, uint64_t *empty, const BRing &br, uint32_t n_my_stages, int lane) {
+    const bool in16 = (a.ld_in % 2 == 0) && (a.col0 % 2 == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 15u) == 0); // rows of the input matrix are 16 B aligned
+    RingPos pos;
+    uint32_t bpos       = 0;  // position in the B stream
+    long long open      = -1; // chunk being filled
+    long long published = -1; // chunks <= published have been handed to the consumers
+    auto publish_upto   = [&](long long c) { // all copies of chunks <= c have landed (callers waited for the groups)
+        __syncwarp();
+        if (lane == 0)
+            for (long long q = published + 1; q <= c; q++)
+                mbar_arrive(smem_u32(&br.full[q & br.mask]));
+        if (c > published)
+            published = c;
+    };
+    for (uint32_t q = 0; q < n_my_stages; q++, pos.advance(ks.ring_stages)) {
+        mbar_wait(smem_u32(&full[pos.slot]), pos.phase);
+        const unsigned char *stage = ring + static_cast<size_t>(pos.slot) * slot_bytes;
+        const AuxHeader ah         = *reinterpret_cast<const AuxHeader *>(stage + ks.stage_bytes);
+        const RunDesc *runs        = reinterpret_cast<const RunDesc *>(stage + ks.stage_bytes + sizeof(AuxHeader));
+        const uint32_t *cols       = reinterpret_cast<const uint32_t *>(runs + ah.n_runs);
+        bpos                       = (bpos + 31u) & ~31u; // a chunk never spans two stages: everything is published when the stage ends
+        for (uint32_t r = 0; r < ah.n_runs; r++) {
+            const RunDesc rd = runs[r];
+            if (a.twice_only && !(rd.flags & 1u))
+                continue;
+            bpos             = (bpos + 3u) & ~3u;
+            const uint32_t K = rd.K;
+            for (uint32_t j = 0; j < K;) {
+                const long long chunk = static_cast<long long>((bpos + j) >> 5);
+                const uint32_t first  = (bpos + j) & 31u;
+                const uint32_t n      = (K - j) < (32u - first) ? (K - j) : (32u - first);
+                if (chunk != open) {
+                    if (open >= 0) {
+                        cp_async_commit();   // the group of chunk `open`
+                        cp_async_wait<1>();  // everything but that group has landed: chunks < open are complete
+                        publish_upto(open - 1);
+                    }
+                    if (lane == 0)
+                        mbar_wait(smem_u32(&br.empty[chunk & br.mask]), static_cast<uint32_t>((chunk >> br.log2n) & 1) ^ 1u);
+                    __syncwarp();
+                    open = chunk;
+                }
+                unsigned char *cbase = br.base + static_cast<size_t>(chunk & br.mask) * br.chunk_bytes;
+                // column jj = j + c of the run goes to row first + c of the chunk; the 32 lanes copy one row together
+                for (uint32_t c = 0; c < n; c++) {
+                    const uint32_t src = cols[rd.col0 + j + c];
+                    const uint32_t dst = smem_u32(cbase + static_cast<size_t>(first + c) * a.vsp * 8u);
+                    if (src & 0x80000000u) { // dense column: a row of the input matrix, mc doubles
+                        const long long row = static_cast<long long>(src & 0x7fffffffu) + a.in_shift;
+                        if (row < 0 || row >= a.in_rows) {
+                            for (int e = lane; e < a.vs; e += 32)
+                                *reinterpret_cast<double *>(cbase + (static_cast<size_t>(first + c) * a.vsp + e) * 8u) = 0.;
+                        } else {
+                            const double *p = a.in + row * a.ld_in + a.col0;
+                            if (in16) {
+                                if (2 * lane < a.mc)
+                                    cp_async16(dst + 16u * lane, p + 2 * lane);
+                            } else {
+                                for (int e = lane; e < a.mc; e += 32)
+                                    cp_async8(dst + 8u * e, p + e);
+                            }
+                        }
+                    } else { // a scratch vector (VS doubles, 16 B aligned)
+                        const double *p = a.mscratch + static_cast<size_t>(src) * a.vsp;
+                        if (2 * lane < a.vs)
+                            cp_async16(dst + 16u * lane, p + 2 * lane);
+                    }
+                }
+                j += n;
+            }
+            bpos += K;
+        }
+        // end of the stage: its last chunks go out now (the consumers must not wait for the next stage to see them)
+        cp_async_commit();
+        cp_async_wait<0>();
+        publish_upto(open);
+        if (lane == 0)
+            mbar_arrive(smem_u32(&empty[pos.slot])); // the column tables of this stage are no longer needed
+    }
 }
 
-template <bool CPLX>
-__global__ void __launch_bounds__((kApplyWarps + 1) * 32) apply_m_kernel(MSide ks, MArgs a) {
+template <bool CPLX, int MIN_CTAS>
+__global__ void __launch_bounds__((kApplyWarps + 2) * 32, MIN_CTAS) apply_m_kernel(MSide ks, MArgs a, int b_log2n) {
     constexpr int CS = CPLX ? 1 : 0;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const BlockDesc bd = ks.blocks[ks.order[blockIdx.x]];
@@ -283,16 +359,38 @@ __global__ void __launch_bounds__((kApplyWarps + 1) * 32) apply_m_kernel(MSide k
     const uint32_t n_my_stages = a.twice_only ? bd.n_twice_stages : bd.n_stages;
     const uint32_t slot_bytes  = ks.stage_bytes + ks.aux_bytes;
     unsigned char *ring = smem_raw;
-    uint64_t *full      = reinterpret_cast<uint64_t *>(smem_raw + static_cast<size_t>(ks.ring_stages) * slot_bytes);
-    uint64_t *empty     = full + ks.ring_stages;
+    BRing br;
+    br.log2n       = static_cast<uint32_t>(b_log2n);
+    br.mask        = (1u << b_log2n) - 1u;
+    br.chunk_bytes = static_cast<uint32_t>(kBChunk) * static_cast<uint32_t>(a.vsp) * 8u;
+    br.base        = smem_raw + static_cast<size_t>(ks.ring_stages) * slot_bytes;
+    uint64_t *full  = reinterpret_cast<uint64_t *>(br.base + (static_cast<size_t>(kBChunk) * 72u * 8u << b_log2n));
+    uint64_t *empty = full + ks.ring_stages;
+    br.full         = empty + ks.ring_stages;
+    br.empty        = br.full + (1u << b_log2n);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, tig = lane & 3;
 
-    init_barriers(ks.ring_stages, full, empty, kApplyWarps);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < ks.ring_stages; s++) {
+            mbar_init(smem_u32(&full[s]), 1);
+            mbar_init(smem_u32(&empty[s]), kApplyWarps + 1); // the consumers and the B producer
+        }
+        for (uint32_t s = 0; s <= br.mask; s++) {
+            mbar_init(smem_u32(&br.full[s]), 1);
+            mbar_init(smem_u32(&br.empty[s]), kApplyWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     __syncthreads();
     if (warp == kApplyWarps) {
         if (lane == 0)
             produce(ks, bd, ring, slot_bytes, full, empty, a.twice_only);
+        return;
+    }
+    if (warp == kApplyWarps + 1) {
+        produce_b<CPLX>(ks, bd, a, ring, slot_bytes, full, empty, br, n_my_stages, lane);
         return;
     }
     const int ct = warp & 7, par = warp >> 3;
@@ -300,8 +398,15 @@ __global__ void __launch_bounds__((kApplyWarps + 1) * 32) apply_m_kernel(MSide k
 #pragma unroll
     for (int j = 0; j < 8; j++)
         acc[j][0] = acc[j][1] = 0.;
+    // column of the B row this lane reads: c = 8 ct + g; complex, odd contraction index: the swapped partner with a sign
+    const int cB         = 8 * ct + g;
+    const bool c_valid   = cB < a.mc;
+    const int cB_odd     = cB ^ 1;
+    const double sgn_odd = ((cB & 1) != 0) == (a.conj == 0) ? 1. : -1.; // (i v)[c] = c even ? -im(v) : re(v); conjugated: opposite
 
     RingPos pos;
+    uint32_t cpos     = 0;  // position in the B stream (same walk as produce_b)
+    long long cur     = -1; // chunk the warp is reading
     for (uint32_t q = 0; q < n_my_stages; q++, pos.advance(ks.ring_stages)) {
         mbar_wait(smem_u32(&full[pos.slot]), pos.phase);
         const unsigned char *stage = ring + static_cast<size_t>(pos.slot) * slot_bytes;
@@ -310,28 +415,47 @@ __global__ void __launch_bounds__((kApplyWarps + 1) * 32) apply_m_kernel(MSide k
         const double *data         = reinterpret_cast<const double *>(stage + hdr.data_byte_off);
         const AuxHeader ah         = *reinterpret_cast<const AuxHeader *>(stage + ks.stage_bytes);
         const RunDesc *runs        = reinterpret_cast<const RunDesc *>(stage + ks.stage_bytes + sizeof(AuxHeader));
-        const uint32_t *cols       = reinterpret_cast<const uint32_t *>(runs + ah.n_runs);
+        cpos                       = (cpos + 31u) & ~31u;
         for (uint32_t r = 0; r < ah.n_runs; r++) {
             const RunDesc rd = runs[r];
             if (a.twice_only && !(rd.flags & 1u))
                 continue;
+            cpos = (cpos + 3u) & ~3u;
+            const uint32_t run_pos = cpos;
+            cpos += rd.K;
             const int row0 = rd.row0, h = static_cast<int>(rd.h_minus_1) + 1;
             // my row tiles 2 j + par that meet rows [row0, row0 + h)
             const int tlo = row0 >> 3, thi = (row0 + h - 1) >> 3;
             const int jlo = (tlo - par + 1) >> 1, jhi = (thi - par) >> 1; // ceil / floor of (t - par) / 2 (arithmetic shift)
-            if (jlo > jhi)
-                continue;
+            const bool mine = jlo <= jhi; // (a warp without rows in the run still walks its chunks: the B ring is released by all)
             const uint32_t Kr = static_cast<uint32_t>(rd.K) << CS; // contraction length
             const uint32_t ld = CPLX ? 2u * static_cast<uint32_t>(h) : unit_ld(static_cast<uint32_t>(h), sizeof(double));
             const double *P   = data + (static_cast<size_t>(rd.data_off) << CS);
-            // per-tile row offset of this lane inside the panel (clamped), and whether the row belongs to the run
-            double bcur = load_b<CPLX>(a, cols, rd.col0, Kr, tig, ct, g);
             for (uint32_t k0 = 0; k0 < Kr; k0 += 4) {
-                const uint32_t kk  = k0 + tig;
-                const double b     = bcur;
-                bcur               = load_b<CPLX>(a, cols, rd.col0, Kr, kk + 4u, ct, g); // next k-step, in flight during the DMMAs
-                const bool kv      = kk < Kr;
-                const double *Pk   = P + static_cast<size_t>((kv ? kk : Kr - 1u) >> CS) * ld + (CPLX ? (kk & 1u) : 0u);
+                const uint32_t kk = k0 + tig;
+                const uint32_t bp = run_pos + (kk >> CS); // stream position of this lane's B row
+                const long long chunk = static_cast<long long>((run_pos + (k0 >> CS)) >> 5);
+                if (chunk != cur) {
+                    if (cur >= 0) {
+                        __syncwarp();
+                        if (lane == 0)
+                            mbar_arrive(smem_u32(&br.empty[cur & br.mask]));
+                    }
+                    mbar_wait(smem_u32(&br.full[chunk & br.mask]), static_cast<uint32_t>((chunk >> br.log2n) & 1));
+                    cur = chunk;
+                }
+                if (!mine)
+                    continue;
+                const bool kv    = kk < Kr;
+                const double *Bs = reinterpret_cast<const double *>(br.base + static_cast<size_t>(chunk & br.mask) * br.chunk_bytes) + static_cast<size_t>(bp & 31u) * a.vsp;
+                double b         = 0.;
+                if (kv && c_valid) {
+                    if (CPLX && (kk & 1u))
+                        b = sgn_odd * Bs[cB_odd];
+                    else
+                        b = Bs[cB];
+                }
+                const double *Pk = P + static_cast<size_t>((kv ? kk : Kr - 1u) >> CS) * ld + (CPLX ? (kk & 1u) : 0u);
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     if (j >= jlo && j <= jhi) { // warp-uniform
@@ -442,7 +566,8 @@ size_t reduce_m_smem_bytes(const LaunchConfig &cfg, int vs, size_t esize) {
 }
 size_t apply_m_smem_bytes(const LaunchConfig &cfg) {
     const size_t slot = static_cast<size_t>(cfg.stage_bytes) + aux_slot_bytes(static_cast<uint32_t>(cfg.cseg_bytes));
-    return static_cast<size_t>(cfg.m_ring_stages) * slot + 16 * static_cast<size_t>(cfg.m_ring_stages);
+    const size_t nb   = size_t(1) << cfg.m_b_ring_log2;
+    return static_cast<size_t>(cfg.m_ring_stages) * slot + nb * kBChunk * 72 * 8 + 16 * static_cast<size_t>(cfg.m_ring_stages) + 16 * nb;
 }
 
 cudaError_t configure_mkernels(const LaunchConfig &cfg, size_t esize) {
@@ -453,10 +578,13 @@ cudaError_t configure_mkernels(const LaunchConfig &cfg, size_t esize) {
     };
     cudaError_t e;
     const void *red = esize == 16 ? reinterpret_cast<const void *>(reduce_m_kernel<true>) : reinterpret_cast<const void *>(reduce_m_kernel<false>);
-    const void *app = esize == 16 ? reinterpret_cast<const void *>(apply_m_kernel<true>) : reinterpret_cast<const void *>(apply_m_kernel<false>);
+    const void *app1 = esize == 16 ? reinterpret_cast<const void *>(apply_m_kernel<true, 1>) : reinterpret_cast<const void *>(apply_m_kernel<false, 1>);
+    const void *app2 = esize == 16 ? reinterpret_cast<const void *>(apply_m_kernel<true, 2>) : reinterpret_cast<const void *>(apply_m_kernel<false, 2>);
     if ((e = set(red, reduce_m_smem_bytes(cfg, 64, esize))) != cudaSuccess)
         return e;
-    return set(app, apply_m_smem_bytes(cfg));
+    if ((e = set(app1, apply_m_smem_bytes(cfg))) != cudaSuccess)
+        return e;
+    return set(app2, apply_m_smem_bytes(cfg));
 }
 
 cudaError_t launch_reduce_m(const SideDevice &side, const LaunchConfig &cfg, const MArgs &args, cudaStream_t stream) {
@@ -478,11 +606,18 @@ cudaError_t launch_apply_m(const SideDevice &side, const LaunchConfig &cfg, cons
     a.beta_is_zero     = (args.beta == 0. && args.beta_im == 0.) ? 1 : 0;
     const MSide ms     = make_mside(side, cfg, cfg.m_ring_stages, true);
     const size_t smem  = apply_m_smem_bytes(cfg);
-    const int threads  = (kApplyWarps + 1) * 32;
-    if (args.cplx)
-        apply_m_kernel<true><<<side.n_blocks, threads, smem, stream>>>(ms, a);
+    const int threads  = (kApplyWarps + 2) * 32;
+    const int bl       = cfg.m_b_ring_log2;
+    // m_apply_ctas = 2: register-capped variant (56 registers), two CTAs per SM when the ring is short enough to fit twice
+    if (cfg.m_apply_ctas >= 2) {
+        if (args.cplx)
+            apply_m_kernel<true, 2><<<side.n_blocks, threads, smem, stream>>>(ms, a, bl);
+        else
+            apply_m_kernel<false, 2><<<side.n_blocks, threads, smem, stream>>>(ms, a, bl);
+    } else if (args.cplx)
+        apply_m_kernel<true, 1><<<side.n_blocks, threads, smem, stream>>>(ms, a, bl);
     else
-        apply_m_kernel<false><<<side.n_blocks, threads, smem, stream>>>(ms, a);
+        apply_m_kernel<false, 1><<<side.n_blocks, threads, smem, stream>>>(ms, a, bl);
     return cudaGetLastError();
 }
 
