@@ -838,7 +838,7 @@ int htb_add_matrix_product_row_major(htb_handle h, char trans, const void *alpha
 }
 
 int htb_set_permutations(htb_handle h, const int32_t *target_permutation, const int32_t *source_permutation) {
-    if (!h || !target_permutation || !source_permutation)
+    if (!h || (!target_permutation && h->nb_rows > 0) || (!source_permutation && h->nb_cols > 0)) // (an empty side has nothing to permute)
         return fail(HTB_ERR_INVALID, "null argument");
     DeviceGuard guard(h->device);
     const int32_t *src[2] = {target_permutation, source_permutation};
@@ -851,7 +851,8 @@ int htb_set_permutations(htb_handle h, const int32_t *target_permutation, const 
             cudaFree(h->d_perm[s]);
         h->d_perm[s] = nullptr;
         HTB_CUDA(cudaMalloc(&h->d_perm[s], std::max<size_t>(1, n[s]) * sizeof(int32_t)));
-        HTB_CUDA(cudaMemcpy(h->d_perm[s], src[s], n[s] * sizeof(int32_t), cudaMemcpyHostToDevice));
+        if (n[s] > 0)
+            HTB_CUDA(cudaMemcpy(h->d_perm[s], src[s], n[s] * sizeof(int32_t), cudaMemcpyHostToDevice));
     }
     return HTB_OK;
 }

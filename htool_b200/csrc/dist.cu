@@ -110,7 +110,20 @@ struct DistState {
     // stream order as long as the caller keeps one stream, and this event when htb_set_stream switched streams in between
     cudaEvent_t product_done    = nullptr;
     cudaStream_t product_stream = nullptr;
+    // ---- small all-reduce over peer memory (inner products of the Krylov loop, gmres.cu) ------------------------------------
+    // every rank owns an inbox [2 parities][world][kRedMax doubles] and arrival flags [world]; a reduction = every rank
+    // stores its values into slot [parity][rank] of EVERY inbox, releases flag[rank] = epoch on every peer, waits for the
+    // world flags of its own inbox and sums the slots in rank order (same order on every rank: identical results)
+    double *red_inbox = nullptr;
+    unsigned long long *red_flags = nullptr;
+    std::vector<double *> peer_red_inbox;
+    std::vector<unsigned long long *> peer_red_flags;
+    double **d_peer_red_inbox             = nullptr;
+    unsigned long long **d_peer_red_flags = nullptr;
+    unsigned long long red_epoch          = 0;
+    bool red_p2p                          = false;
 };
+constexpr int kRedMax = 256; // doubles per reduction (restart 40, complex, two Gram-Schmidt passes: 2 * 2 * 42 = 168)
 
 static int nccl_fail(ncclResult_t r, const char *what) {
     return fail(HTB_ERR_NCCL, std::string(what) + ": " + nccl().GetErrorString(r));
@@ -127,11 +140,16 @@ static void close_peer_buffers(DistState *d) {
 
 int dist_world(const htb_operator *h) { return h->dist ? h->dist->world : 0; }
 
+int dist_allreduce_small(htb_operator *h, double *dev, int n, cudaStream_t st);
 // in-place sum over the ranks of n doubles on the device (inner products of the Krylov loop, gmres.cu)
 int dist_allreduce_sum(htb_operator *h, double *dev, size_t n, cudaStream_t st) {
     DistState *d = h->dist;
     if (!d || d->world <= 1 || n == 0)
         return HTB_OK;
+    if (d->red_p2p && n <= static_cast<size_t>(kRedMax)) {
+        // (defined below) no collective call, no NCCL kernel: one small CTA per rank over the peer mappings
+        return dist_allreduce_small(h, dev, static_cast<int>(n), st);
+    }
     ncclResult_t r = nccl().AllReduce(dev, dev, n, ncclDouble, ncclSum, d->comm, st);
     if (r != ncclSuccess)
         return fail(HTB_ERR_NCCL, std::string("ncclAllReduce: ") + nccl().GetErrorString(r));
@@ -158,6 +176,15 @@ void dist_destroy(htb_operator *h) {
         if (static_cast<int>(r) != d->rank && d->peer_flags[r])
             cudaIpcCloseMemHandle(d->peer_flags[r]);
     d->peer_flags.clear();
+    for (size_t r = 0; r < d->peer_red_inbox.size(); r++)
+        if (static_cast<int>(r) != d->rank && d->peer_red_inbox[r])
+            cudaIpcCloseMemHandle(d->peer_red_inbox[r]);
+    for (size_t r = 0; r < d->peer_red_flags.size(); r++)
+        if (static_cast<int>(r) != d->rank && d->peer_red_flags[r])
+            cudaIpcCloseMemHandle(d->peer_red_flags[r]);
+    for (void *p : {static_cast<void *>(d->red_inbox), static_cast<void *>(d->red_flags), static_cast<void *>(d->d_peer_red_inbox), static_cast<void *>(d->d_peer_red_flags)})
+        if (p)
+            cudaFree(p);
     for (void *p : {d->xg[0], d->xg[1], static_cast<void *>(d->flags), static_cast<void *>(d->arrive), static_cast<void *>(d->d_peer_xg[0]), static_cast<void *>(d->d_peer_xg[1]),
                     static_cast<void *>(d->d_peer_flags), static_cast<void *>(d->d_order_all), static_cast<void *>(d->d_owner), d->d_hbuf})
         if (p)
@@ -266,6 +293,34 @@ __global__ void push_x_kernel(const unsigned long long *src, size_t n8, void *co
     }
 }
 
+// In-place sum over the ranks of n <= kRedMax doubles, one CTA. WAR safety of the two inbox parities: a rank stores epoch e
+// into parity e & 1 only after it has seen every peer's flag e - 1 (inside its reduction e - 1), and a peer publishes e - 1
+// only after its reduction e - 2 — the last reader of that parity — has finished (stream order).
+__global__ void allreduce_small_kernel(double *vals, int n, double *const *peer_inbox, unsigned long long *const *peer_flags, const double *own_inbox, const unsigned long long *own_flags, int world,
+                                       int rank, unsigned long long epoch) {
+    const int t        = threadIdx.x;
+    const size_t slot  = (static_cast<size_t>(epoch & 1ull) * world + rank) * kRedMax;
+    if (t < n) {
+        const double v = vals[t];
+        for (int p = 0; p < world; p++)
+            peer_inbox[p][slot + t] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t < world)
+        st_release_sys_u64(peer_flags[t] + rank, epoch);
+    if (t < world)
+        while (ld_acquire_sys_u64(own_flags + t) < epoch)
+            __nanosleep(32);
+    __syncthreads();
+    if (t < n) {
+        double s = 0.;
+        for (int r = 0; r < world; r++)
+            s += own_inbox[(static_cast<size_t>(epoch & 1ull) * world + r) * kRedMax + t];
+        vals[t] = s;
+    }
+}
+
 static cudaError_t grow_device(void **p, size_t *cap, size_t need) {
     if (need <= *cap)
         return cudaSuccess;
@@ -277,6 +332,17 @@ static cudaError_t grow_device(void **p, size_t *cap, size_t need) {
     if (e == cudaSuccess)
         *cap = need;
     return e;
+}
+
+int dist_allreduce_small(htb_operator *h, double *dev, int n, cudaStream_t st) {
+    DistState *d = h->dist;
+    const unsigned long long epoch = ++d->red_epoch;
+    allreduce_small_kernel<<<1, kRedMax, 0, st>>>(dev, n, d->d_peer_red_inbox, d->d_peer_red_flags, d->red_inbox, d->red_flags, d->world, d->rank, epoch);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return cuda_fail(e, "allreduce_small_kernel");
+    h->launches++;
+    return HTB_OK;
 }
 
 } // namespace htb
@@ -378,6 +444,47 @@ static int p2p_init(htb_operator *h, DistState *d) {
     if ((rc = agree(d, ok, &all)) != HTB_OK)
         return rc;
     d->p2p = all;
+    if (d->p2p) {
+        // inbox + flags of the small all-reduce, mapped on every rank like the gather flags (collective sequence: every rank
+        // goes through the same exchanges whatever its local verdict)
+        bool rok = d->world <= kRedMax;
+        if (rok && cudaMalloc(reinterpret_cast<void **>(&d->red_inbox), sizeof(double) * 2 * d->world * kRedMax) != cudaSuccess) {
+            cudaGetLastError();
+            rok = false;
+        }
+        if (rok && cudaMalloc(reinterpret_cast<void **>(&d->red_flags), sizeof(unsigned long long) * d->world) != cudaSuccess) {
+            cudaGetLastError();
+            rok = false;
+        }
+        if (rok) {
+            HTB_CUDA(cudaMemset(d->red_inbox, 0, sizeof(double) * 2 * d->world * kRedMax));
+            HTB_CUDA(cudaMemset(d->red_flags, 0, sizeof(unsigned long long) * d->world));
+        }
+        std::vector<void *> m1, m2;
+        bool ok1 = rok, ok2 = rok;
+        if ((rc = exchange_and_map(d, rok ? static_cast<void *>(d->red_inbox) : static_cast<void *>(d->flags), m1, &ok1)) != HTB_OK)
+            return rc;
+        if ((rc = exchange_and_map(d, rok ? static_cast<void *>(d->red_flags) : static_cast<void *>(d->flags), m2, &ok2)) != HTB_OK)
+            return rc;
+        rok = rok && ok1 && ok2;
+        d->peer_red_inbox.resize(d->world);
+        d->peer_red_flags.resize(d->world);
+        for (int r = 0; r < d->world; r++) {
+            d->peer_red_inbox[r] = static_cast<double *>(m1[r]);
+            d->peer_red_flags[r] = static_cast<unsigned long long *>(m2[r]);
+        }
+        if (!rok) { // entries that point at the stand-in allocation must not be closed as if they were ours
+            d->peer_red_inbox[d->rank] = nullptr;
+            d->peer_red_flags[d->rank] = nullptr;
+        }
+        if (rok && (rc = upload_table(reinterpret_cast<void **>(&d->d_peer_red_inbox), d->peer_red_inbox.data(), sizeof(void *) * d->world)) != HTB_OK)
+            return rc;
+        if (rok && (rc = upload_table(reinterpret_cast<void **>(&d->d_peer_red_flags), d->peer_red_flags.data(), sizeof(void *) * d->world)) != HTB_OK)
+            return rc;
+        if ((rc = agree(d, rok, &all)) != HTB_OK)
+            return rc;
+        d->red_p2p = all;
+    }
     // launch order of the single REDUCE: own-partition blocks first; owners of every block's index range
     const std::vector<BlockDesc> &blocks = h->host_blocks[1];
     std::vector<uint32_t> owner(blocks.size(), 0xFFFFFFFFu), order_all;

@@ -265,22 +265,31 @@ struct BRing {
     uint32_t chunk_bytes, mask, log2n; // ring of 2^log2n chunks
 };
 
-// The B producer warp: see above. Mirrors the consumers' walk (stages, runs, the applied-twice filter, the 4-alignment of
-// run starts) so that both sides agree on the position of every column in the stream.
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+
+// The B producer warp: see above. Mirrors the consumers' walk (stages, runs, the applied-twice filter, the alignment of
+// run / stage starts) so that both sides agree on the position of every column in the stream. One LANE per column: a row
+// is one bulk copy (TMA, completion counted in bytes on the chunk's mbarrier), so the warp never waits for data; rows of
+// an input matrix whose row stride is not a multiple of 16 B (odd mu, double) go through 8-byte cp.async instead.
 template <bool CPLX>
 __device__ __forceinline__ void produce_b(const MSide &ks, const BlockDesc &bd, const MArgs &a, unsigned char *ring, uint32_t slot_bytes, uint64_t *full, uint64_t *empty, const BRing &br, uint32_t n_my_stages, int lane) {
-    const bool in16 = (a.ld_in % 2 == 0) && (a.col0 % 2 == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 15u) == 0); // rows of the input matrix are 16 B aligned
+    const bool in16 = (a.ld_in % 2 == 0) && (a.col0 % 2 == 0) && (a.mc % 2 == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 15u) == 0); // rows of the input matrix are 16 B aligned
     RingPos pos;
-    uint32_t bpos       = 0;  // position in the B stream
-    long long open      = -1; // chunk being filled
-    long long published = -1; // chunks <= published have been handed to the consumers
-    auto publish_upto   = [&](long long c) { // all copies of chunks <= c have landed (callers waited for the groups)
+    uint32_t bpos    = 0;  // position in the B stream
+    long long open   = -1; // chunk being filled
+    bool slow_copies = false; // the open chunk holds cp.async copies: wait for them before publishing
+    auto publish     = [&]() { // hand the open chunk to the consumers: its phase completes when the bulk copies have landed
+        if (open < 0)
+            return;
+        if (slow_copies) {
+            cp_async_commit();
+            cp_async_wait<0>();
+            slow_copies = false;
+        }
         __syncwarp();
         if (lane == 0)
-            for (long long q = published + 1; q <= c; q++)
-                mbar_arrive(smem_u32(&br.full[q & br.mask]));
-        if (c > published)
-            published = c;
+            mbar_arrive(smem_u32(&br.full[open & br.mask]));
+        open = -1;
     };
     for (uint32_t q = 0; q < n_my_stages; q++, pos.advance(ks.ring_stages)) {
         mbar_wait(smem_u32(&full[pos.slot]), pos.phase);
@@ -300,50 +309,58 @@ __device__ __forceinline__ void produce_b(const MSide &ks, const BlockDesc &bd, 
                 const uint32_t first  = (bpos + j) & 31u;
                 const uint32_t n      = (K - j) < (32u - first) ? (K - j) : (32u - first);
                 if (chunk != open) {
-                    if (open >= 0) {
-                        cp_async_commit();   // the group of chunk `open`
-                        cp_async_wait<1>();  // everything but that group has landed: chunks < open are complete
-                        publish_upto(open - 1);
-                    }
+                    publish();
                     if (lane == 0)
                         mbar_wait(smem_u32(&br.empty[chunk & br.mask]), static_cast<uint32_t>((chunk >> br.log2n) & 1) ^ 1u);
                     __syncwarp();
                     open = chunk;
                 }
                 unsigned char *cbase = br.base + static_cast<size_t>(chunk & br.mask) * br.chunk_bytes;
-                // column jj = j + c of the run goes to row first + c of the chunk; the 32 lanes copy one row together
-                for (uint32_t c = 0; c < n; c++) {
-                    const uint32_t src = cols[rd.col0 + j + c];
-                    const uint32_t dst = smem_u32(cbase + static_cast<size_t>(first + c) * a.vsp * 8u);
+                const uint32_t bar   = smem_u32(&br.full[chunk & br.mask]);
+                // lane c copies the row of column j + c of the run into row first + c of the chunk
+                const double *p = nullptr;
+                uint32_t bytes = 0, mode = 3; // 0 bulk copy, 1 cp.async 8 B pieces, 2 zero row, 3 nothing
+                if (static_cast<uint32_t>(lane) < n) {
+                    const uint32_t src = cols[rd.col0 + j + lane];
                     if (src & 0x80000000u) { // dense column: a row of the input matrix, mc doubles
                         const long long row = static_cast<long long>(src & 0x7fffffffu) + a.in_shift;
-                        if (row < 0 || row >= a.in_rows) {
-                            for (int e = lane; e < a.vs; e += 32)
-                                *reinterpret_cast<double *>(cbase + (static_cast<size_t>(first + c) * a.vsp + e) * 8u) = 0.;
-                        } else {
-                            const double *p = a.in + row * a.ld_in + a.col0;
-                            if (in16) {
-                                if (2 * lane < a.mc)
-                                    cp_async16(dst + 16u * lane, p + 2 * lane);
-                            } else {
-                                for (int e = lane; e < a.mc; e += 32)
-                                    cp_async8(dst + 8u * e, p + e);
-                            }
+                        if (row < 0 || row >= a.in_rows)
+                            mode = 2;
+                        else {
+                            p     = a.in + row * a.ld_in + a.col0;
+                            bytes = static_cast<uint32_t>(a.mc) * 8u;
+                            mode  = in16 ? 0u : 1u;
                         }
                     } else { // a scratch vector (VS doubles, 16 B aligned)
-                        const double *p = a.mscratch + static_cast<size_t>(src) * a.vsp;
-                        if (2 * lane < a.vs)
-                            cp_async16(dst + 16u * lane, p + 2 * lane);
+                        p     = a.mscratch + static_cast<size_t>(src) * a.vsp;
+                        bytes = static_cast<uint32_t>(a.vs) * 8u;
+                        mode  = 0;
                     }
                 }
+                uint32_t tx = mode == 0 ? bytes : 0u;
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1)
+                    tx += __shfl_xor_sync(0xffffffffu, tx, d);
+                if (lane == 0 && tx)
+                    mbar_expect_tx(bar, tx);
+                __syncwarp();
+                unsigned char *drow = cbase + static_cast<size_t>(first + lane) * a.vsp * 8u;
+                if (mode == 0)
+                    bulk_g2s_plain(smem_u32(drow), p, bytes, bar);
+                else if (mode == 1) {
+                    for (int e = 0; e < a.mc; e++)
+                        cp_async8(smem_u32(drow) + 8u * e, p + e);
+                } else if (mode == 2) {
+                    for (int e = 0; e < a.vs; e++)
+                        reinterpret_cast<double *>(drow)[e] = 0.;
+                }
+                if (__any_sync(0xffffffffu, mode == 1))
+                    slow_copies = true;
                 j += n;
             }
             bpos += K;
         }
-        // end of the stage: its last chunks go out now (the consumers must not wait for the next stage to see them)
-        cp_async_commit();
-        cp_async_wait<0>();
-        publish_upto(open);
+        publish(); // end of the stage: the consumers must not wait for the next stage to see its last chunk
         if (lane == 0)
             mbar_arrive(smem_u32(&empty[pos.slot])); // the column tables of this stage are no longer needed
     }
@@ -532,6 +549,8 @@ __global__ void __launch_bounds__((kApplyWarps + 2) * 32, MIN_CTAS) apply_m_kern
 }
 
 // One warp per (piece, vector of the piece): sums the per-chunk partial vectors in chunk order (fixed summation order).
+// A lane owns two adjacent columns (one 16 B load per partial); the loads of 8 partials are in flight together, the adds
+// keep their order.
 __global__ void combine_m_kernel(const CombineEntry *entries, int n, double *mscratch, int vs, int vsp, int twice_only) {
     const int warps_per_block = blockDim.x >> 5;
     const long long gw        = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
@@ -543,13 +562,28 @@ __global__ void combine_m_kernel(const CombineEntry *entries, int n, double *msc
     const uint32_t lane = threadIdx.x & 31, len = combine_len(ce.packed), n_sum = combine_n_sum(ce.packed);
     if (k >= len || (twice_only && !combine_twice(ce.packed)))
         return;
-    for (uint32_t c = lane; c < static_cast<uint32_t>(vs); c += 32) {
+    const size_t step = static_cast<size_t>(len) * vsp;
+    for (uint32_t c = 2 * lane; c < static_cast<uint32_t>(vs); c += 64) {
         const double *p = mscratch + (static_cast<size_t>(ce.src) + k) * vsp + c;
-        double v        = 0.;
-#pragma unroll 4
-        for (uint32_t j = 0; j < n_sum; j++)
-            v += p[static_cast<size_t>(j) * len * vsp];
-        mscratch[(static_cast<size_t>(ce.dst_first) + k) * vsp + c] = v;
+        double2 v       = make_double2(0., 0.);
+        uint32_t j      = 0;
+        for (; j + 8 <= n_sum; j += 8) {
+            double2 t[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                t[q] = *reinterpret_cast<const double2 *>(p + static_cast<size_t>(j + q) * step);
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                v.x += t[q].x;
+                v.y += t[q].y;
+            }
+        }
+        for (; j < n_sum; j++) {
+            const double2 t = *reinterpret_cast<const double2 *>(p + static_cast<size_t>(j) * step);
+            v.x += t.x;
+            v.y += t.y;
+        }
+        *reinterpret_cast<double2 *>(mscratch + (static_cast<size_t>(ce.dst_first) + k) * vsp + c) = v;
     }
 }
 
