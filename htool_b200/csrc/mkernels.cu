@@ -448,10 +448,10 @@ __global__ void __launch_bounds__((kApplyWarps + 2) * 32, MIN_CTAS) apply_m_kern
             const uint32_t Kr = static_cast<uint32_t>(rd.K) << CS; // contraction length
             const uint32_t ld = CPLX ? 2u * static_cast<uint32_t>(h) : unit_ld(static_cast<uint32_t>(h), sizeof(double));
             const double *P   = data + (static_cast<size_t>(rd.data_off) << CS);
-            for (uint32_t k0 = 0; k0 < Kr; k0 += 4) {
-                const uint32_t kk = k0 + tig;
-                const uint32_t bp = run_pos + (kk >> CS); // stream position of this lane's B row
-                const long long chunk = static_cast<long long>((run_pos + (k0 >> CS)) >> 5);
+            // the k-steps of the run, chunk by chunk of the B ring (a k-step never straddles two chunks)
+            for (uint32_t k0 = 0; k0 < Kr;) {
+                const uint32_t pos0   = run_pos + (k0 >> CS);
+                const long long chunk = static_cast<long long>(pos0 >> 5);
                 if (chunk != cur) {
                     if (cur >= 0) {
                         __syncwarp();
@@ -461,27 +461,66 @@ __global__ void __launch_bounds__((kApplyWarps + 2) * 32, MIN_CTAS) apply_m_kern
                     mbar_wait(smem_u32(&br.full[chunk & br.mask]), static_cast<uint32_t>((chunk >> br.log2n) & 1));
                     cur = chunk;
                 }
-                if (!mine)
-                    continue;
-                const bool kv    = kk < Kr;
-                const double *Bs = reinterpret_cast<const double *>(br.base + static_cast<size_t>(chunk & br.mask) * br.chunk_bytes) + static_cast<size_t>(bp & 31u) * a.vsp;
-                double b         = 0.;
-                if (kv && c_valid) {
-                    if (CPLX && (kk & 1u))
-                        b = sgn_odd * Bs[cB_odd];
-                    else
-                        b = Bs[cB];
-                }
-                const double *Pk = P + static_cast<size_t>((kv ? kk : Kr - 1u) >> CS) * ld + (CPLX ? (kk & 1u) : 0u);
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    if (j >= jlo && j <= jhi) { // warp-uniform
-                        const int row   = 8 * (2 * j + par) + g;
+                uint32_t kend = k0 + ((32u - (pos0 & 31u)) << CS); // first contraction index of the next chunk
+                if (kend > Kr)
+                    kend = Kr;
+                if (mine) {
+                    // this lane's B row (contraction index k0 + tig) and panel column; both advance by one k-step per iteration
+                    const double *Bl = reinterpret_cast<const double *>(br.base + static_cast<size_t>(chunk & br.mask) * br.chunk_bytes) + static_cast<size_t>((pos0 & 31u) + (static_cast<uint32_t>(tig) >> CS)) * a.vsp +
+                                       ((CPLX && (tig & 1)) ? cB_odd : cB);
+                    const double bs  = (CPLX && (tig & 1)) ? sgn_odd : 1.;
+                    const double *Pl = P + static_cast<size_t>((k0 + tig) >> CS) * ld + (CPLX ? (tig & 1) : 0);
+                    const size_t bstep = static_cast<size_t>(4 >> CS) * a.vsp, pstep = static_cast<size_t>(4 >> CS) * ld;
+                    if (jlo == jhi) {
+                        // ONE row tile (dense leaves, small clusters): two accumulation chains over alternating k-steps hide
+                        // the DMMA latency, folded into the tile's accumulator at the end of the segment
+                        const int row   = 8 * (2 * jlo + par) + g;
                         const bool rv   = row >= row0 && row < row0 + h;
-                        const double av = (rv && kv) ? Pk[static_cast<uint32_t>(rv ? row - row0 : 0) << CS] : 0.;
-                        dmma(acc[j], av, b);
+                        const uint32_t ao = static_cast<uint32_t>(rv ? row - row0 : 0) << CS;
+                        double t0[2] = {0., 0.}, t1[2] = {0., 0.};
+                        uint32_t k = k0;
+                        for (; k + 4 < kend; k += 8) {
+                            const bool kv1 = k + 4 + tig < Kr;
+                            const double b0 = c_valid ? bs * Bl[0] : 0., b1 = (c_valid && kv1) ? bs * Bl[bstep] : 0.;
+                            const double a0 = rv ? Pl[ao] : 0., a1 = (rv && kv1) ? Pl[pstep + ao] : 0.;
+                            dmma(t0, a0, b0);
+                            dmma(t1, a1, b1);
+                            Bl += 2 * bstep;
+                            Pl += 2 * pstep;
+                        }
+                        if (k < kend) {
+                            const bool kv  = k + tig < Kr;
+                            const double b = (c_valid && kv) ? bs * Bl[0] : 0.;
+                            const double av = (rv && kv) ? Pl[ao] : 0.;
+                            dmma(t0, av, b);
+                        }
+                        t0[0] += t1[0];
+                        t0[1] += t1[1];
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                            if (j == jlo) {
+                                acc[j][0] += t0[0];
+                                acc[j][1] += t0[1];
+                            }
+                    } else {
+                        for (uint32_t k = k0; k < kend; k += 4) {
+                            const bool kv  = k + tig < Kr;
+                            const double b = (c_valid && kv) ? bs * Bl[0] : 0.;
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                if (j >= jlo && j <= jhi) { // warp-uniform
+                                    const int row   = 8 * (2 * j + par) + g;
+                                    const bool rv   = row >= row0 && row < row0 + h;
+                                    const double av = (rv && kv) ? Pl[static_cast<uint32_t>(rv ? row - row0 : 0) << CS] : 0.;
+                                    dmma(acc[j], av, b);
+                                }
+                            }
+                            Bl += bstep;
+                            Pl += pstep;
+                        }
                     }
                 }
+                k0 = kend == Kr ? Kr : kend;
             }
         }
         // ADDVEC units (side 1, transposed direction): C rows += the TF vectors REDUCE_M produced for dense leaves
