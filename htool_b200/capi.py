@@ -115,6 +115,13 @@ class htb_packed_side(C.Structure):
     ]
 
 
+class htb_generator_desc(C.Structure):
+    _fields_ = [("kernel", C.c_int32), ("spatial_dimension", C.c_int32), ("wavenumber", C.c_double), ("target_points", C.c_void_p), ("source_points", C.c_void_p)]
+
+
+HTB_KERNELS = {"laplace": 0, "laplace_reg": 1, "complex_reg": 2, "hermitian_reg": 3, "helmholtz": 4, "complex": 5}
+
+
 class htb_gmres_options(C.Structure):
     _fields_ = [("restart", C.c_int32), ("max_iterations", C.c_int32), ("tolerance", C.c_double), ("orthogonalization", C.c_int32), ("verbosity", C.c_int32),
                 ("compute_true_residual", C.c_int32), ("reserved", C.c_int32)]
@@ -130,6 +137,8 @@ HTB_GMRES_CGS, HTB_GMRES_CGS2 = 0, 1
 # name -> (restype, argtypes): every symbol include/htool_b200.h declares
 SYMBOLS = {
     "htb_create": (C.c_int, [C.POINTER(htb_hmatrix_desc), C.POINTER(C.c_void_p)]),
+    "htb_create_generated": (C.c_int, [C.POINTER(htb_hmatrix_desc), C.c_void_p, C.POINTER(C.c_void_p)]),
+    "htb_download_store": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
     "htb_destroy": (C.c_int, [C.c_void_p]),
     "htb_get_info": (C.c_int, [C.c_void_p, C.POINTER(htb_info)]),
     "htb_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -206,14 +215,28 @@ def _ptr(a):
 class Operator:
     """Thin RAII wrapper over an htb_handle (what htool_b200::GpuHMatrix is on the C++ side)."""
 
-    def __init__(self, desc: htb_hmatrix_desc, keepalive=None):
+    def __init__(self, desc: htb_hmatrix_desc, keepalive=None, generator=None):
+        """generator = (kernel name, target points (n x 3, cluster numbering), source points, wavenumber): dense leaves
+        whose data0 is NULL are generated on the device (htb_create_generated)."""
         self.lib = load()
         self.handle = C.c_void_p()
         self.dtype_code = desc.dtype
         self.dtype = np_dtype(desc.dtype)
         self.nb_rows, self.nb_cols = desc.nb_rows, desc.nb_cols
         self._keepalive = keepalive
-        check(self.lib, self.lib.htb_create(C.byref(desc), C.byref(self.handle)))
+        if generator is None:
+            check(self.lib, self.lib.htb_create(C.byref(desc), C.byref(self.handle)))
+        else:
+            kernel, tp, sp, k = generator
+            tp, sp = np.ascontiguousarray(tp, dtype=np.float64), np.ascontiguousarray(sp, dtype=np.float64)
+            assert tp.shape == (desc.nb_rows, 3) and sp.shape == (desc.nb_cols, 3)
+            g = htb_generator_desc(HTB_KERNELS[kernel], 3, float(k), tp.ctypes.data, sp.ctypes.data)
+            check(self.lib, self.lib.htb_create_generated(C.byref(desc), C.byref(g), C.byref(self.handle)))
+
+    def download_store(self, side: int, nbytes: int) -> np.ndarray:
+        out = np.zeros(nbytes, dtype=np.uint8)
+        check(self.lib, self.lib.htb_download_store(self.handle, side, _ptr(out), nbytes))
+        return out
 
     def close(self):
         if self.handle:

@@ -4,6 +4,7 @@
 // the t / z vectors, a CUDA stream, pinned staging buffers for the host-pointer entry points and,
 // optionally, an NCCL communicator (dist.cu). There is no CPU path: every compute entry point needs a
 // CUDA device and fails with HTB_ERR_CUDA otherwise.
+#include "generate.cuh"
 #include "handle.hpp"
 
 #include <algorithm>
@@ -28,7 +29,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 namespace {
 std::mutex g_option_mutex;
 std::map<std::string, int64_t> g_options = {
-    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 2048}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 4}, {"m_b_ring_log2", 2}, {"m_reduce_ring_stages", 5}, {"mrhs_min", 2}, {"m_apply_ctas", 1}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}};
+    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 2048}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 4}, {"m_b_ring_log2", 2}, {"m_reduce_ring_stages", 5}, {"mrhs_min", 2}, {"m_apply_ctas", 1}, {"m_reduce_warps", 24}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}};
 
 int64_t option(const char *key) {
     std::lock_guard<std::mutex> lock(g_option_mutex);
@@ -143,6 +144,7 @@ static int upload_store(htb_operator *h, const Packer &pk) {
         h->owned.push_back(dstream);
         sd.stream = static_cast<const unsigned char *>(dstream);
         h->store_bytes += sl.stream_bytes;
+        h->side_stream_bytes[s] = sl.stream_bytes;
         // batches of consecutive blocks whose streams fit one pinned buffer
         const int nb = sd.n_blocks;
         int b0 = 0, turn = 0;
@@ -617,7 +619,73 @@ int htb_get_option(const char *key, int64_t *value) {
     return HTB_OK;
 }
 
-int htb_create(const htb_hmatrix_desc *desc, htb_handle *out) {
+static int create_impl(const htb_hmatrix_desc *desc, const htb_generator_desc *gen, htb_handle *out);
+
+int htb_create(const htb_hmatrix_desc *desc, htb_handle *out) { return create_impl(desc, nullptr, out); }
+
+int htb_create_generated(const htb_hmatrix_desc *desc, const htb_generator_desc *gen, htb_handle *out) {
+    if (!gen)
+        return fail(HTB_ERR_INVALID, "null generator description");
+    if (gen->spatial_dimension != 3)
+        return fail(HTB_ERR_INVALID, "the built-in kernel functions are defined for points in R^3");
+    if (gen->kernel < HTB_KERNEL_LAPLACE || gen->kernel > HTB_KERNEL_COMPLEX)
+        return fail(HTB_ERR_INVALID, "unknown built-in kernel function");
+    if (desc && kernel_is_complex(gen->kernel) != (desc->dtype == HTB_COMPLEX_DOUBLE))
+        return fail(HTB_ERR_INVALID, "the kernel function does not produce the coefficient type of the H-matrix");
+    if (desc && ((desc->nb_rows > 0 && !gen->target_points) || (desc->nb_cols > 0 && !gen->source_points)))
+        return fail(HTB_ERR_INVALID, "null point array");
+    return create_impl(desc, gen, out);
+}
+
+int htb_download_store(htb_handle h, int side, void *dst, int64_t bytes) {
+    if (!h || (side != 0 && side != 1) || !dst || bytes < 0)
+        return fail(HTB_ERR_INVALID, "invalid argument");
+    DeviceGuard guard(h->device);
+    const int64_t have = static_cast<int64_t>(h->side_stream_bytes[side]);
+    if (bytes > have)
+        return fail(HTB_ERR_INVALID, "more bytes requested than the side's stream holds");
+    if (bytes)
+        HTB_CUDA(cudaMemcpy(dst, h->side[side].stream, static_cast<size_t>(bytes), cudaMemcpyDeviceToHost));
+    return HTB_OK;
+}
+
+// dense units of leaves that came without host data: generated on the device straight into the uploaded stream
+static int generate_dense(htb_operator *h, const Packer &pk, const htb_generator_desc *gen) {
+    const std::vector<DenseTask> &tasks = pk.side[0].dense_tasks;
+    if (tasks.empty())
+        return HTB_OK;
+    void *d_tasks = nullptr, *d_tp = nullptr, *d_sp = nullptr;
+    auto cleanup = [&]() {
+        for (void *p : {d_tasks, d_tp, d_sp})
+            if (p)
+                cudaFree(p);
+    };
+    const size_t tb = tasks.size() * sizeof(DenseTask), tpb = size_t(3) * h->nb_rows * sizeof(double), spb = size_t(3) * h->nb_cols * sizeof(double);
+    cudaError_t e = cudaMalloc(&d_tasks, tb);
+    if (e == cudaSuccess)
+        e = cudaMalloc(&d_tp, std::max<size_t>(8, tpb));
+    if (e == cudaSuccess)
+        e = cudaMalloc(&d_sp, std::max<size_t>(8, spb));
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(d_tasks, tasks.data(), tb, cudaMemcpyHostToDevice, h->own_stream);
+    if (e == cudaSuccess && tpb)
+        e = cudaMemcpyAsync(d_tp, gen->target_points, tpb, cudaMemcpyHostToDevice, h->own_stream);
+    if (e == cudaSuccess && spb)
+        e = cudaMemcpyAsync(d_sp, gen->source_points, spb, cudaMemcpyHostToDevice, h->own_stream);
+    if (e == cudaSuccess)
+        e = launch_generate_dense(gen->kernel, static_cast<const DenseTask *>(d_tasks), static_cast<long long>(tasks.size()), const_cast<unsigned char *>(h->side[0].stream), static_cast<const double *>(d_tp),
+                                  static_cast<const double *>(d_sp), gen->wavenumber, h->own_stream);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(h->own_stream);
+    cleanup();
+    if (e != cudaSuccess)
+        return cuda_fail(e, "dense leaf generation");
+    h->launches++;
+    h->generated_dense_units = static_cast<int64_t>(tasks.size());
+    return HTB_OK;
+}
+
+static int create_impl(const htb_hmatrix_desc *desc, const htb_generator_desc *gen, htb_handle *out) {
     if (!desc || !out)
         return fail(HTB_ERR_INVALID, "null argument");
     *out = nullptr;
@@ -632,6 +700,7 @@ int htb_create(const htb_hmatrix_desc *desc, htb_handle *out) {
         return fail(HTB_ERR_INVALID, "device ordinal out of range");
 
     PackOptions popt;
+    popt.generate_dense = gen != nullptr;
     popt.block_rows  = static_cast<int>(option("block_rows"));
     popt.piece_cols  = static_cast<int>(option("piece_cols"));
     popt.stage_bytes = static_cast<int>(option("stage_bytes"));
@@ -683,6 +752,7 @@ int htb_create(const htb_hmatrix_desc *desc, htb_handle *out) {
     h->launch_cfg.m_reduce_ring_stages = static_cast<int>(option("m_reduce_ring_stages"));
     h->launch_cfg.m_apply_ctas         = static_cast<int>(option("m_apply_ctas"));
     h->launch_cfg.m_b_ring_log2        = static_cast<int>(option("m_b_ring_log2"));
+    h->launch_cfg.m_reduce_warps       = static_cast<int>(option("m_reduce_warps"));
     if (h->launch_cfg.m_b_ring_log2 < 1 || h->launch_cfg.m_b_ring_log2 > 3)
         return fail(HTB_ERR_INVALID, "m_b_ring_log2 must be in [1, 3]");
     if (h->launch_cfg.m_ring_stages < 2 || h->launch_cfg.m_ring_stages > 8 || h->launch_cfg.m_reduce_ring_stages < 2 || h->launch_cfg.m_reduce_ring_stages > 8)
@@ -698,6 +768,8 @@ int htb_create(const htb_hmatrix_desc *desc, htb_handle *out) {
     h->stream = h->own_stream;
 
     int rc = upload_store(h.get(), *pk);
+    if (rc == HTB_OK && gen)
+        rc = generate_dense(h.get(), *pk, gen);
     if (rc != HTB_OK) {
         htb_destroy(h.release());
         return rc;

@@ -1,0 +1,125 @@
+// htool_b200/csrc/generate.cu — leaf assembly on the device, first step: the dense near-field
+// leaves are generated on the GPU straight into the side-0 stream of the leaf store.
+//
+// What it replaces in the reference: HMatrix::compute_dense_data (include/htool/hmatrix/hmatrix.hpp:222-226), one
+// generator.copy_submatrix per dense leaf, called from HMatrixTreeBuilder::openmp_compute_blocks
+// (hmatrix/tree_builder/tree_builder.hpp:629-633) or, in one batch, through the hook
+// VirtualDenseBlocksGenerator::copy_dense_blocks (hmatrix/interfaces/virtual_dense_blocks_generator.hpp:12, called at
+// tree_builder.hpp:650-665) — the shape of this entry point: a list of (rows, cols, row offset, col offset) blocks.
+// At N = 1e6 that is 2.29 M leaves / 178.7 M coefficients which never exist on the host here.
+//
+// Built-in kernel functions = the analytic generators of the reference's test-suite
+// (include/htool/testing/generator_test.hpp:155-205) plus the Helmholtz kernel of SURVEY.md 8d. Every operation is an
+// explicitly rounded IEEE operation in the order the host generator performs it (no FMA contraction), so the real
+// kernels are BIT-IDENTICAL to compute_dense_data; the Helmholtz kernel differs by the last ulps of sin / cos.
+#include "generate.cuh"
+
+namespace htb {
+
+namespace {
+
+struct Value {
+    double re, im;
+};
+
+template <int KERNEL>
+__device__ __forceinline__ Value kernel_value(const double *a, const double *b, double wavenumber) {
+    const double dx = __dsub_rn(a[0], b[0]), dy = __dsub_rn(a[1], b[1]), dz = __dsub_rn(a[2], b[2]);
+    const double r  = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+    const double four_pi = 4 * 3.14159265358979323846; // 4 * M_PI, folded at compile time on the host as well
+    const double fpr     = __dmul_rn(four_pi, r);
+    if (KERNEL == HTB_KERNEL_LAPLACE) // 1 / (4 pi r), generator_test.hpp:155-161
+        return Value{__ddiv_rn(1., fpr), 0.};
+    if (KERNEL == HTB_KERNEL_LAPLACE_REG) // 1 / (1e-5 + 4 pi r), :180-187
+        return Value{__ddiv_rn(1., __dadd_rn(1e-5, fpr)), 0.};
+    if (KERNEL == HTB_KERNEL_COMPLEX) { // (1 + i) / (4 pi r), :163-170
+        const double v = __ddiv_rn(1., fpr);
+        return Value{v, v};
+    }
+    if (KERNEL == HTB_KERNEL_COMPLEX_REG) { // (1 + i) / (1e-5 + 4 pi r), :189-196
+        const double v = __ddiv_rn(1., __dadd_rn(1e-5, fpr));
+        return Value{v, v};
+    }
+    if (KERNEL == HTB_KERNEL_HERMITIAN_REG) { // (1 + sign(x_t - x_s) i) / (1e-5 + 4 pi r), :198-205
+        const double d = __dadd_rn(1e-5, fpr);
+        const double s = dx > 0 ? 1. : (dx < 0 ? -1. : 0.);
+        return Value{__ddiv_rn(1., d), __ddiv_rn(s, d)};
+    }
+    // HTB_KERNEL_HELMHOLTZ: exp(i k r) / (4 pi r), finite diagonal
+    if (r < 1e-12)
+        return Value{__ddiv_rn(1., __dmul_rn(four_pi, 1e-3)), __ddiv_rn(wavenumber, four_pi)};
+    double sn, cs;
+    sincos(__dmul_rn(wavenumber, r), &sn, &cs);
+    return Value{__ddiv_rn(cs, fpr), __ddiv_rn(sn, fpr)};
+}
+
+// One warp per dense unit.
+template <bool CPLX, int KERNEL>
+__global__ void generate_dense_kernel(const DenseTask *tasks, long long n_tasks, unsigned char *stream, const double *target_points, const double *source_points, double wavenumber) {
+    const long long t = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (t >= n_tasks)
+        return;
+    const DenseTask task = tasks[t];
+    const int lane       = threadIdx.x & 31;
+    double *out          = reinterpret_cast<double *>(stream + task.byte_off);
+    const bool diag      = (task.flags & (HTB_LEAF_DIAG_SYMMETRIC | HTB_LEAF_DIAG_HERMITIAN)) != 0;
+    const bool upper     = (task.flags & HTB_LEAF_UPLO_UPPER) != 0;
+    const bool herm      = (task.flags & HTB_LEAF_DIAG_HERMITIAN) != 0;
+    const int total      = static_cast<int>(task.h) * task.w;
+    for (int e = lane; e < total; e += 32) {
+        const int k = e / task.h, i = e - k * task.h;
+        int gi = task.p0 + i, gj = task.k0 + k;
+        bool mirrored = false;
+        if (diag && gi != gj && !(upper ? gi <= gj : gi >= gj)) { // symv / hemv read only the UPLO triangle: entry (j, i), conjugated for hemv
+            const int tmp = gi;
+            gi            = gj;
+            gj            = tmp;
+            mirrored      = true;
+        }
+        Value v = kernel_value<KERNEL>(target_points + 3ll * (task.lrow + gi), source_points + 3ll * (task.lcol + gj), wavenumber);
+        if (herm && (mirrored || gi == gj))
+            v.im = gi == gj ? 0. : -v.im; // hemv ignores the imaginary part of the diagonal
+        const size_t at = static_cast<size_t>(k) * task.ld + i;
+        if (CPLX) {
+            out[2 * at]     = v.re;
+            out[2 * at + 1] = v.im;
+        } else
+            out[at] = v.re;
+    }
+}
+
+} // namespace
+
+bool kernel_is_complex(int kernel) { return kernel == HTB_KERNEL_COMPLEX_REG || kernel == HTB_KERNEL_HERMITIAN_REG || kernel == HTB_KERNEL_HELMHOLTZ || kernel == HTB_KERNEL_COMPLEX; }
+
+cudaError_t launch_generate_dense(int kernel, const DenseTask *tasks, long long n_tasks, unsigned char *stream, const double *target_points, const double *source_points, double wavenumber, cudaStream_t st) {
+    if (n_tasks == 0)
+        return cudaSuccess;
+    const int threads   = 256;
+    const unsigned grid = static_cast<unsigned>((n_tasks * 32 + threads - 1) / threads);
+    switch (kernel) {
+    case HTB_KERNEL_LAPLACE:
+        generate_dense_kernel<false, HTB_KERNEL_LAPLACE><<<grid, threads, 0, st>>>(tasks, n_tasks, stream, target_points, source_points, wavenumber);
+        break;
+    case HTB_KERNEL_LAPLACE_REG:
+        generate_dense_kernel<false, HTB_KERNEL_LAPLACE_REG><<<grid, threads, 0, st>>>(tasks, n_tasks, stream, target_points, source_points, wavenumber);
+        break;
+    case HTB_KERNEL_COMPLEX_REG:
+        generate_dense_kernel<true, HTB_KERNEL_COMPLEX_REG><<<grid, threads, 0, st>>>(tasks, n_tasks, stream, target_points, source_points, wavenumber);
+        break;
+    case HTB_KERNEL_HERMITIAN_REG:
+        generate_dense_kernel<true, HTB_KERNEL_HERMITIAN_REG><<<grid, threads, 0, st>>>(tasks, n_tasks, stream, target_points, source_points, wavenumber);
+        break;
+    case HTB_KERNEL_HELMHOLTZ:
+        generate_dense_kernel<true, HTB_KERNEL_HELMHOLTZ><<<grid, threads, 0, st>>>(tasks, n_tasks, stream, target_points, source_points, wavenumber);
+        break;
+    case HTB_KERNEL_COMPLEX:
+        generate_dense_kernel<true, HTB_KERNEL_COMPLEX><<<grid, threads, 0, st>>>(tasks, n_tasks, stream, target_points, source_points, wavenumber);
+        break;
+    default:
+        return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+} // namespace htb

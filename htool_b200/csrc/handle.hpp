@@ -68,6 +68,8 @@ struct htb_operator {
     };
     std::vector<TimedLaunch> timed;
     size_t store_bytes = 0, descriptor_bytes = 0, workspace_bytes = 0;
+    uint64_t side_stream_bytes[2] = {0, 0};
+    int64_t generated_dense_units = 0; // dense units generated on the device (htb_create_generated)
     htb_info info{};
     htb::DistState *dist = nullptr;
     // Krylov workspace (gmres.cu), grown on demand and kept between solves

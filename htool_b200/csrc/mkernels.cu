@@ -32,6 +32,7 @@
 // flops = 2 * mu * C per product, x 4 for complex.
 #include "mkernels.cuh"
 
+#include <algorithm>
 #include <cstdint>
 
 namespace htb {
@@ -39,7 +40,7 @@ namespace htb {
 namespace {
 
 constexpr int kApplyWarps  = 16; // APPLY_M: 8 column tiles x 2 row-tile parities
-constexpr int kReduceWarps = 24; // REDUCE_M: jobs (8 columns of a run) dealt round-robin
+constexpr int kReduceWarpsMax = 24; // REDUCE_M: jobs (8 columns of a run) dealt round-robin over the consumer warps (option m_reduce_warps)
 
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
@@ -133,7 +134,7 @@ __device__ __forceinline__ void init_barriers(int ring, uint64_t *full, uint64_t
 // ---- REDUCE_M -------------------------------------------------------------------------------------------------------
 // smem: [ring: slot = stage | aux] [Xs ((real rows of a block + 4) x VSP)] [barriers]
 template <bool CPLX>
-__global__ void __launch_bounds__((kReduceWarps + 1) * 32) reduce_m_kernel(MSide ks, MArgs a) {
+__global__ void __launch_bounds__((kReduceWarpsMax + 1) * 32) reduce_m_kernel(MSide ks, MArgs a) {
     constexpr int CS = CPLX ? 1 : 0; // a complex row is two real rows
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const BlockDesc bd         = ks.blocks[ks.order[blockIdx.x]];
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__((kReduceWarps + 1) * 32) reduce_m_kernel(MSide
     uint64_t *empty           = full + ks.ring_stages;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, tig = lane & 3;
+    const int kReduceWarps = static_cast<int>(blockDim.x >> 5) - 1; // consumer warps; the last warp is the producer
 
     init_barriers(ks.ring_stages, full, empty, kReduceWarps);
     __syncthreads();
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__((kReduceWarps + 1) * 32) reduce_m_kernel(MSide
         }
         Xs[r * XS + c] = v;
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(kReduceWarps * 32) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"r"(kReduceWarps * 32) : "memory");
 
     const int MT = a.vs >> 3; // column tiles of the right-hand sides
     RingPos pos;
@@ -199,10 +201,10 @@ __global__ void __launch_bounds__((kReduceWarps + 1) * 32) reduce_m_kernel(MSide
             const double *P   = data + (static_cast<size_t>(rd.data_off) << CS);
             const double *xrow = Xs + ((static_cast<uint32_t>(rd.row0) << CS) + tig) * XS + g;
             // my tiles of this run: t = t0, t0 + W, ...
-            uint32_t t0 = static_cast<uint32_t>(warp) + kReduceWarps - jmod;
-            if (t0 >= kReduceWarps)
+            uint32_t t0 = static_cast<uint32_t>(warp + kReduceWarps) - jmod;
+            if (t0 >= static_cast<uint32_t>(kReduceWarps))
                 t0 -= kReduceWarps;
-            jmod = (jmod + ntiles) % kReduceWarps;
+            jmod = (jmod + ntiles) % static_cast<uint32_t>(kReduceWarps);
             for (uint32_t t = t0; t < ntiles; t += kReduceWarps) {
                 double acc[8][2];
 #pragma unroll
@@ -411,9 +413,10 @@ __global__ void __launch_bounds__((kApplyWarps + 2) * 32, MIN_CTAS) apply_m_kern
         return;
     }
     const int ct = warp & 7, par = warp >> 3;
-    double acc[8][2];
+    constexpr int NJ = CPLX ? 4 : 8; // row tiles of a warp: block_rows / 16 (a complex block has 64 rows)
+    double acc[NJ][2];
 #pragma unroll
-    for (int j = 0; j < 8; j++)
+    for (int j = 0; j < NJ; j++)
         acc[j][0] = acc[j][1] = 0.;
     // column of the B row this lane reads: c = 8 ct + g; complex, odd contraction index: the swapped partner with a sign
     const int cB         = 8 * ct + g;
@@ -497,17 +500,41 @@ __global__ void __launch_bounds__((kApplyWarps + 2) * 32, MIN_CTAS) apply_m_kern
                         t0[0] += t1[0];
                         t0[1] += t1[1];
 #pragma unroll
-                        for (int j = 0; j < 8; j++)
+                        for (int j = 0; j < NJ; j++)
                             if (j == jlo) {
                                 acc[j][0] += t0[0];
                                 acc[j][1] += t0[1];
                             }
+                    } else if (row0 == 0 && h == bd.nrows && jlo == 0 && jhi == NJ - 1) {
+                        // A run over ALL the rows of the block (the panels of the tall leaves: most of the coefficients): no
+                        // row predicates. A lane whose row lies past the block reads the coefficient of a neighbouring
+                        // column instead of a zero: it only pollutes accumulators of rows >= nrows, which are never stored.
+                        const double *Pa = Pl + (static_cast<size_t>(8 * par + g) << CS);
+                        uint32_t k = k0;
+                        const uint32_t kfull = (kend == Kr) ? (Kr & ~3u) : kend; // k-steps below kfull have four valid contraction indices
+                        for (; k < kfull; k += 4) {
+                            const double b = c_valid ? bs * Bl[0] : 0.;
+#pragma unroll
+                            for (int j = 0; j < NJ; j++)
+                                dmma(acc[j], Pa[static_cast<size_t>(16 * j) << CS], b);
+                            Bl += bstep;
+                            Pa += pstep;
+                        }
+                        if (k < kend) { // last, partial k-step of the run: contraction indices >= Kr meet zeros on both sides
+                            const bool kv  = k + tig < Kr;
+                            const double b = (c_valid && kv) ? bs * Bl[0] : 0.;
+#pragma unroll
+                            for (int j = 0; j < NJ; j++) {
+                                const bool rv = 16 * j + 8 * par + g < h;
+                                dmma(acc[j], (kv && rv) ? Pa[static_cast<size_t>(16 * j) << CS] : 0., b);
+                            }
+                        }
                     } else {
                         for (uint32_t k = k0; k < kend; k += 4) {
                             const bool kv  = k + tig < Kr;
                             const double b = (c_valid && kv) ? bs * Bl[0] : 0.;
 #pragma unroll
-                            for (int j = 0; j < 8; j++) {
+                            for (int j = 0; j < NJ; j++) {
                                 if (j >= jlo && j <= jhi) { // warp-uniform
                                     const int row   = 8 * (2 * j + par) + g;
                                     const bool rv   = row >= row0 && row < row0 + h;
@@ -538,7 +565,7 @@ __global__ void __launch_bounds__((kApplyWarps + 2) * 32, MIN_CTAS) apply_m_kern
                 const uint32_t src = mun[u].src;
                 const int c        = 8 * ct + 2 * tig;
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
+                for (int j = 0; j < NJ; j++) {
                     if (j >= jlo && j <= jhi) {
                         const int row = 8 * (2 * j + par) + g;
                         if (row >= row0 && row < row0 + h && c < a.vs) {
@@ -557,7 +584,7 @@ __global__ void __launch_bounds__((kApplyWarps + 2) * 32, MIN_CTAS) apply_m_kern
     // epilogue: alpha / beta, one write per C entry (complex: a lane holds re and im of one entry)
     const int c = 8 * ct + 2 * tig;
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
+    for (int j = 0; j < NJ; j++) {
         const int i = 8 * (2 * j + par) + g;
         if (i < bd.nrows && c < a.mc) {
             const long long gr = static_cast<long long>(bd.row_start) + i + a.out_shift;
@@ -664,7 +691,7 @@ cudaError_t launch_reduce_m(const SideDevice &side, const LaunchConfig &cfg, con
     if (side.n_blocks == 0)
         return cudaSuccess;
     const MSide ms    = make_mside(side, cfg, cfg.m_reduce_ring_stages, false);
-    const int threads = (kReduceWarps + 1) * 32;
+    const int threads = (std::min(std::max(cfg.m_reduce_warps, 4), kReduceWarpsMax) + 1) * 32;
     if (args.cplx)
         reduce_m_kernel<true><<<side.n_blocks, threads, reduce_m_smem_bytes(cfg, args.vs, 16), stream>>>(ms, args);
     else

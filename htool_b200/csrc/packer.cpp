@@ -93,7 +93,7 @@ Packer::Packer(const htb_hmatrix_desc &desc, const PackOptions &o) : dtype(desc.
         bool empty = l.nb_rows == 0 || l.nb_cols == 0;
         if (l.rank < 0) {
             n_dense++;
-            if (!empty && !l.data0)
+            if (!empty && !l.data0 && !opt.generate_dense)
                 throw std::runtime_error("dense leaf without data");
             if ((l.flags & (HTB_LEAF_DIAG_SYMMETRIC | HTB_LEAF_DIAG_HERMITIAN)) && l.nb_rows != l.nb_cols)
                 throw std::runtime_error("symmetric dense leaf is not square");
@@ -487,6 +487,7 @@ void Packer::make_mtables() {
         // aux records (runs + column tables, store.hpp) of every block, concatenated below
         std::vector<std::vector<unsigned char>> aux_r(nb), aux_a(nb);
         std::vector<std::vector<uint32_t>> aux_len(nb); // per stage of the block, bytes
+        std::vector<std::vector<DenseTask>> tasks(nb);
         bool aux_overflow = false;
 #pragma omp parallel for schedule(dynamic, 64)
         for (int b = 0; b < nb; b++) {
@@ -517,6 +518,12 @@ void Packer::make_mtables() {
                         if (!(l.rank < 0 && s == 1)) { // (dense leaves hold no panel on side 1)
                             const uint32_t po = m_partm_off[1 - s][gp];
                             out               = po == kDirect ? m_tf_off[gp] : po + static_cast<uint32_t>(u.chunk) * static_cast<uint32_t>(piece_len(l, u.piece));
+                        }
+                        if (u.kind == UNIT_DENSE && !l.data0) {
+                            const StageDesc &sd = side[s].stages[side[s].blocks[b].first_stage + aux_len[b].size()];
+                            tasks[b].push_back(DenseTask{sd.byte_off + cut.header_bytes() + static_cast<uint64_t>(eoff) * esize, l.row_offset, l.col_offset, static_cast<int32_t>(u.p0), static_cast<int32_t>(u.k0),
+                                                         static_cast<uint16_t>(u.h), static_cast<uint16_t>(u.w), static_cast<uint16_t>(u.ld),
+                                                         static_cast<uint16_t>(l.flags & (HTB_LEAF_DIAG_SYMMETRIC | HTB_LEAF_DIAG_HERMITIAN | HTB_LEAF_UPLO_UPPER))});
                         }
                         for (uint32_t k = 0; k < u.w; k++) {
                             col_out.push_back(out + k);
@@ -616,6 +623,7 @@ void Packer::make_mtables() {
                 sd.flags      = static_cast<uint16_t>((sd.flags & 1u) | ((aux_len[b][q] / 16u) << 1));
                 off += aux_len[b][q];
             }
+            side[s].dense_tasks.insert(side[s].dense_tasks.end(), tasks[b].begin(), tasks[b].end());
             at += aux_r[b].size();
             std::vector<unsigned char>().swap(aux_r[b]);
             std::vector<unsigned char>().swap(aux_a[b]);
@@ -772,6 +780,10 @@ void Packer::fill_block(int s, int b, char *dst) const {
                 for (uint32_t k = 0; k < u.w; k++)
                     for (uint32_t i = 0; i < u.h; i++)
                         out[i + static_cast<size_t>(k) * u.ld] = V[(u.k0 + k) + (u.p0 + i) * r];
+            } else if (u.kind == UNIT_DENSE && !l.data0) {
+                // generated on the device after the upload (htb_create_generated): the panel travels as zeros
+                for (uint32_t k = 0; k < u.w; k++)
+                    std::memset(static_cast<void *>(out + static_cast<size_t>(k) * u.ld), 0, sizeof(T) * u.h);
             } else if (u.kind == UNIT_DENSE && (l.flags & (HTB_LEAF_DIAG_SYMMETRIC | HTB_LEAF_DIAG_HERMITIAN))) {
                 // symv / hemv read only the UPLO triangle (add_matrix_vector_product.hpp:26-52): rebuild the full
                 // block from that triangle so the kernels see an ordinary dense leaf

@@ -181,7 +181,20 @@ static_assert(sizeof(RunDesc) == 16, "RunDesc must be 16 bytes");
 // capacity of a stage's aux record: a stage holds <= cseg_bytes / esize columns (c-segment limit), one run per column at worst
 HTB_HD inline uint32_t aux_slot_bytes(uint32_t cseg_bytes) { return (16u + 20u * (cseg_bytes / 8u) + 127u) & ~127u; }
 
+// ---- leaf assembly on the device: one task per dense unit whose leaf came without host data ------------
+// The generate kernel (generate.cu) evaluates the built-in kernel function at the unit's points straight into the
+// uploaded stream: coefficient (i, k) of the unit is entry (p0 + i, k0 + k) of the leaf whose first row / column are
+// lrow / lcol in the root block's cluster numbering. flags = the leaf's HTB_LEAF_DIAG_* / UPLO bits (symv / hemv leaves
+// are rebuilt from their UPLO triangle exactly as the packer does for host data).
+struct DenseTask {
+    uint64_t byte_off; // of the unit's panel inside side 0's stream
+    int32_t lrow, lcol, p0, k0;
+    uint16_t h, w, ld, flags;
+};
+static_assert(sizeof(DenseTask) == 32, "DenseTask must be 32 bytes");
+
 struct PackOptions {
+    bool generate_dense = false; // dense leaves with data0 == NULL are allowed: their panels are generated on the device
     int block_rows  = 0;     // 32, 64 or 128; 0 = automatic (128 for double, 64 for complex<double>)
     int piece_cols  = 16;    // columns of a unit (<= 32); lowered automatically so that a unit fits a stage
     int stage_bytes = 24576; // bulk-copy granule of the coefficient stream, multiple of 16
@@ -216,6 +229,7 @@ struct SideLayout {
     std::vector<CombineEntry> combine_m; // src = PARTM offset, dst_first = TF offset, n_dst unused
     uint64_t partm_base = 0, partm_elems = 0; // in vectors, inside the multi-RHS scratch [TF | PARTM[0] | PARTM[1]]
     std::vector<unsigned char> aux_reduce, aux_apply; // per-stage aux records (runs + column tables), same offsets in both
+    std::vector<DenseTask> dense_tasks;               // side 0 only: dense units to generate on the device
 };
 
 } // namespace htb

@@ -134,6 +134,36 @@ int htb_synchronize(htb_handle h);
 int htb_host_register(void *ptr, size_t bytes);
 int htb_host_unregister(void *ptr);
 
+/* ---- leaf assembly on the device (first step: the dense near-field leaves) ---------------------------- */
+
+/* Built-in kernel functions, evaluated on the device with the reference's own formulas
+ * (include/htool/testing/generator_test.hpp:155-205; Helmholtz exp(ikr)/(4 pi r) with a finite diagonal). */
+enum { HTB_KERNEL_LAPLACE = 0,       /* 1 / (4 pi r)                          double          */
+       HTB_KERNEL_LAPLACE_REG = 1,   /* 1 / (1e-5 + 4 pi r)                   double          */
+       HTB_KERNEL_COMPLEX_REG = 2,   /* (1 + i) / (1e-5 + 4 pi r)             complex<double> */
+       HTB_KERNEL_HERMITIAN_REG = 3, /* (1 + sign(x_t - x_s) i) / (1e-5 + 4 pi r)             */
+       HTB_KERNEL_HELMHOLTZ = 4,     /* exp(i k r) / (4 pi r)                                 */
+       HTB_KERNEL_COMPLEX = 5        /* (1 + i) / (4 pi r)                                    */ };
+typedef struct htb_generator_desc {
+    int32_t kernel;            /* HTB_KERNEL_* */
+    int32_t spatial_dimension; /* 3 */
+    double wavenumber;         /* k of HTB_KERNEL_HELMHOLTZ */
+    const double *target_points; /* 3 doubles per row of the root block, in CLUSTER numbering (row i of the block <-> point of
+                                    user index permutation[row_offset + i]); host memory, read during the call */
+    const double *source_points; /* same for the columns */
+} htb_generator_desc;
+/* htb_create for an H-matrix whose dense leaves may come WITHOUT coefficients (htb_leaf.data0 == NULL, rank == -1): those
+ * leaves are generated on the device, straight into the leaf store, from the built-in kernel function and the points —
+ * what HMatrix::compute_dense_data (hmatrix.hpp:222-226) does per leaf on the host, in the batch shape of
+ * VirtualDenseBlocksGenerator::copy_dense_blocks (virtual_dense_blocks_generator.hpp:12, tree_builder.hpp:650-665): the
+ * list of blocks is the list of such leaves. Dense leaves that do carry data0 (e.g. admissible blocks whose compression
+ * failed) and all low-rank leaves are packed from the host as usual. Symmetric / Hermitian diagonal leaves are rebuilt
+ * from their UPLO triangle like host data. Real kernels reproduce compute_dense_data bit for bit. */
+int htb_create_generated(const htb_hmatrix_desc *desc, const htb_generator_desc *generator, htb_handle *out);
+/* Test / debug: copies the first `bytes` bytes of one side's packed stream (layout: htool_b200/csrc/store.hpp) back from
+ * the device, e.g. to compare device-generated leaves with htb_pack_host of the host-generated ones. */
+int htb_download_store(htb_handle h, int side, void *dst, int64_t bytes);
+
 /* ---- products ------------------------------------------------------------------------------------- */
 
 /* out <- beta*out + alpha*op(H)*in, op = N | T | C. Replaces openmp_internal_add_hmatrix_vector_product
