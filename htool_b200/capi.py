@@ -112,6 +112,8 @@ class htb_packed_side(C.Structure):
         ("aux_bytes", C.c_int64),
         ("aux_reduce", C.c_void_p),
         ("aux_apply", C.c_void_p),
+        ("n_dense_tasks", C.c_int64),
+        ("dense_tasks", C.c_void_p),
     ]
 
 

@@ -10,8 +10,10 @@
 #define HTOOL_B200_DEVICE_HMATRIX_HPP
 
 #include "flatten.hpp"
+#include <htool/hmatrix/interfaces/virtual_dense_blocks_generator.hpp>
 #include <htool/misc/logger.hpp>
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 namespace htool_b200 {
@@ -51,6 +53,32 @@ class PinnedHostBuffer {
     bool is_pinned() const { return m_ptr != nullptr; }
 };
 
+/// Leaf assembly on the device, first step. Plugged into the reference's builder with
+/// HMatrixTreeBuilder::set_dense_blocks_generator (hmatrix/tree_builder/tree_builder.hpp:258), it receives the ONE batch
+/// call the builder makes for all its dense leaves (copy_dense_blocks, tree_builder.hpp:650-665) and computes nothing: it
+/// only records which host blocks were left unfilled. A DeviceHMatrix built with it (constructor below) generates those
+/// leaves on the GPU, straight into the leaf store, from a built-in kernel function and the points.
+/// The host H-matrix then holds zeros in those blocks: use it for assembly only, not for CPU products.
+template <typename CoefficientPrecision>
+class DeviceDenseBlocks final : public htool::VirtualDenseBlocksGenerator<CoefficientPrecision> {
+    mutable std::unordered_set<const void *> m_blocks;
+
+  public:
+    void copy_dense_blocks(const std::vector<int> &, const std::vector<int> &, const std::vector<int> &, const std::vector<int> &, std::vector<CoefficientPrecision *> &ptr) const override {
+        m_blocks.insert(ptr.begin(), ptr.end());
+    }
+    const std::unordered_set<const void *> &deferred() const { return m_blocks; }
+    std::size_t size() const { return m_blocks.size(); }
+};
+
+/// A built-in kernel function (htb_generator_desc) with the geometry in USER numbering, as a VirtualGenerator sees it.
+struct BuiltinKernel {
+    int kernel        = HTB_KERNEL_LAPLACE_REG;
+    double wavenumber = 0.;
+    const double *target_points = nullptr; // 3 x number of target points
+    const double *source_points = nullptr;
+};
+
 /// The leaf store of `hmatrix` on one B200: flattened with flatten() and uploaded once, at construction
 /// (north_star item 1). The HMatrix can be destroyed afterwards: nothing on the host is referenced again.
 template <typename CoefficientPrecision, typename CoordinatePrecision = htool::underlying_type<CoefficientPrecision>>
@@ -85,6 +113,39 @@ class DeviceHMatrix {
         }
         if (local) { // a sub-block of a non-local partition has no block-local permutation: user-numbering products are then unavailable, as in the reference
             check(htb_set_permutations(m_handle, t.data(), s.data()), "htb_set_permutations");
+        }
+    }
+    /// Device-side assembly of the dense leaves: `hmatrix` was built with `deferred` as its dense-blocks generator, so its
+    /// dense leaves hold no coefficients; they are generated on the GPU from `kernel` (htb_create_generated). Low-rank
+    /// leaves (and admissible blocks whose compression failed) are packed from the host as usual.
+    DeviceHMatrix(const htool::HMatrix<CoefficientPrecision, CoordinatePrecision> &hmatrix, const DeviceDenseBlocks<CoefficientPrecision> &deferred, const BuiltinKernel &kernel, int device = -1) {
+        FlatHMatrix flat = flatten(hmatrix, device, &deferred.deferred());
+        m_nb_rows        = flat.desc.nb_rows;
+        m_nb_cols        = flat.desc.nb_cols;
+        m_target_offset  = flat.desc.row_offset;
+        m_source_offset  = flat.desc.col_offset;
+        // the points of the root block in cluster numbering: row i <-> user index permutation[offset + i]
+        const auto &tp = hmatrix.get_target_cluster().get_permutation();
+        const auto &sp = hmatrix.get_source_cluster().get_permutation();
+        std::vector<double> tpts(static_cast<std::size_t>(3) * m_nb_rows), spts(static_cast<std::size_t>(3) * m_nb_cols);
+        for (int i = 0; i < m_nb_rows; i++) {
+            for (int d = 0; d < 3; d++) {
+                tpts[3 * static_cast<std::size_t>(i) + d] = kernel.target_points[3 * static_cast<std::size_t>(tp[m_target_offset + i]) + d];
+            }
+        }
+        for (int i = 0; i < m_nb_cols; i++) {
+            for (int d = 0; d < 3; d++) {
+                spts[3 * static_cast<std::size_t>(i) + d] = kernel.source_points[3 * static_cast<std::size_t>(sp[m_source_offset + i]) + d];
+            }
+        }
+        htb_generator_desc gen{};
+        gen.kernel            = kernel.kernel;
+        gen.spatial_dimension = 3;
+        gen.wavenumber        = kernel.wavenumber;
+        gen.target_points     = tpts.data();
+        gen.source_points     = spts.data();
+        if (!check(htb_create_generated(&flat.desc, &gen, &m_handle), "htb_create_generated")) {
+            m_handle = nullptr;
         }
     }
     DeviceHMatrix(const DeviceHMatrix &)            = delete;

@@ -34,8 +34,10 @@ struct FlatHMatrix {
     htb_hmatrix_desc desc{};
 };
 
+/// `deferred_dense` (optional): dense blocks whose coefficients were NOT computed on the host (DeviceDenseBlocks below,
+/// device_hmatrix.hpp); their leaves get data0 = nullptr and are generated on the device by htb_create_generated.
 template <typename CoefficientPrecision, typename CoordinatePrecision = htool::underlying_type<CoefficientPrecision>>
-FlatHMatrix flatten(const htool::HMatrix<CoefficientPrecision, CoordinatePrecision> &hmatrix, int device = -1) {
+FlatHMatrix flatten(const htool::HMatrix<CoefficientPrecision, CoordinatePrecision> &hmatrix, int device = -1, const std::unordered_set<const void *> *deferred_dense = nullptr) {
     using HMatrixType = htool::HMatrix<CoefficientPrecision, CoordinatePrecision>;
     FlatHMatrix flat;
 
@@ -62,6 +64,9 @@ FlatHMatrix flatten(const htool::HMatrix<CoefficientPrecision, CoordinatePrecisi
             d.rank  = -1;
             d.data0 = leaf->get_dense_data()->data();
             d.data1 = nullptr;
+            if (deferred_dense != nullptr && deferred_dense->count(d.data0) != 0) {
+                d.data0 = nullptr; // the host block was allocated but never filled
+            }
             // Diagonal dense leaves go through symv/hemv (add_hmatrix_vector_product.hpp:22-24,41-45).
             if (leaf->get_symmetry() == 'S') {
                 d.flags |= HTB_LEAF_DIAG_SYMMETRIC;

@@ -29,7 +29,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 namespace {
 std::mutex g_option_mutex;
 std::map<std::string, int64_t> g_options = {
-    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 2048}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 4}, {"m_b_ring_log2", 2}, {"m_reduce_ring_stages", 5}, {"mrhs_min", 2}, {"m_apply_ctas", 1}, {"m_reduce_warps", 24}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}};
+    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 2048}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 4}, {"m_b_ring_log2", 2}, {"m_reduce_ring_stages", 5}, {"mrhs_min", 2}, {"m_apply_ctas", 1}, {"pack_generate_dense", 0}, {"m_reduce_warps", 24}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}};
 
 int64_t option(const char *key) {
     std::lock_guard<std::mutex> lock(g_option_mutex);
@@ -1009,6 +1009,7 @@ int htb_pack_host(const htb_hmatrix_desc *desc, int side, htb_packed_side *out) 
     popt.tail_split        = static_cast<int>(option("tail_split"));
     if (option("cta_slots") > 0)
         popt.cta_slots = static_cast<int>(option("cta_slots"));
+    popt.generate_dense = option("pack_generate_dense") != 0; // tests: what htb_create_generated would upload
     try {
         Packer pk(*desc, popt);
         auto *own   = new PackedOwner();
@@ -1044,6 +1045,8 @@ int htb_pack_host(const htb_hmatrix_desc *desc, int side, htb_packed_side *out) 
         out->aux_bytes     = static_cast<int64_t>(own->layout.aux_reduce.size());
         out->aux_reduce    = own->layout.aux_reduce.data();
         out->aux_apply     = own->layout.aux_apply.data();
+        out->n_dense_tasks = static_cast<int64_t>(own->layout.dense_tasks.size());
+        out->dense_tasks   = own->layout.dense_tasks.data();
     } catch (const std::exception &ex) {
         return fail(HTB_ERR_INVALID, ex.what());
     }

@@ -300,6 +300,8 @@ typedef struct htb_packed_side {
     int64_t aux_bytes;        /* multi-RHS aux records of the side's stages (store.hpp: AuxHeader | RunDesc[] | column table) */
     const void *aux_reduce;   /* column entry = scratch vector receiving the column's REDUCE_M result */
     const void *aux_apply;    /* column entry = scratch vector (or input row | bit 31) the column multiplies in APPLY_M */
+    int64_t n_dense_tasks;    /* side 0, option pack_generate_dense = 1: dense units of leaves without data0 (store.hpp: DenseTask, 32 B) */
+    const void *dense_tasks;
 } htb_packed_side;
 int htb_pack_host(const htb_hmatrix_desc *desc, int side, htb_packed_side *out);
 int htb_pack_free(htb_packed_side *packed);

@@ -77,6 +77,7 @@ enum { G2L_VECTOR = 0,
        FREE_MATRIX_USER,
        LOGGED_UNSUPPORTED,
        DEVICE_DIST,
+       GENERATED_DENSE,
        N_GROUPS };
 
 struct CountingWriter : htool::IObjectWriter {
@@ -318,6 +319,45 @@ int run(htb_ref::Case<T> &c, double *results, int n_results) {
             htool::add_hmatrix_matrix_product(exec_compat::par, trans, 'N', alpha, H, B, beta, Cr);
             htool_b200::add_hmatrix_matrix_product(exec_compat::par, trans, 'N', alpha, DH, xv.data(), beta, cg.data(), mu);
             upd(FREE_MATRIX_USER, rel_err(cg, std::vector<T>(Cr.data(), Cr.data() + no * mu)));
+        }
+    }
+
+    // ---- leaf assembly on the device: the SAME builder call with htool_b200::DeviceDenseBlocks as its dense-blocks generator
+    // (HMatrixTreeBuilder::set_dense_blocks_generator, tree_builder.hpp:258): the dense leaves are never computed on the
+    // host, the GPU generates them from the built-in kernel function; products must agree with the reference's on H -------
+    if (c.spec.compressor == 0 && (c.spec.kernel >= 0 && c.spec.kernel <= 5)) {
+        HMatrixTreeBuilder<T, double> builder(c.spec.epsilon, c.spec.eta, static_cast<char>(c.spec.symmetry), static_cast<char>(c.spec.uplo));
+        if (c.spec.min_depth > 0) {
+            builder.set_minimal_target_depth(c.spec.min_depth);
+            builder.set_minimal_source_depth(c.spec.min_depth);
+        }
+        auto deferred = std::make_shared<htool_b200::DeviceDenseBlocks<T>>();
+        builder.set_dense_blocks_generator(deferred);
+        std::unique_ptr<HMatrix<T, double>> H2;
+        if (c.spec.partition_rank >= 0 && c.spec.local_block)
+            H2 = std::make_unique<HMatrix<T, double>>(builder.build(exec_compat::par, *c.internal_generator, c.target_cluster->get_cluster_on_partition(c.spec.partition_rank), c.source_cluster->get_cluster_on_partition(c.spec.partition_rank)));
+        else if (c.spec.partition_rank >= 0)
+            H2 = std::make_unique<HMatrix<T, double>>(builder.build(exec_compat::par, *c.internal_generator, *c.target_cluster, *c.source_cluster, c.spec.partition_rank, c.spec.partition_rank));
+        else
+            H2 = std::make_unique<HMatrix<T, double>>(builder.build(exec_compat::par, *c.internal_generator, *c.target_cluster, *c.source_cluster));
+        htool_b200::BuiltinKernel bk;
+        bk.kernel        = c.spec.kernel;
+        bk.wavenumber    = c.spec.wavenumber;
+        bk.target_points = c.target_points.data();
+        bk.source_points = c.source_points->data();
+        htool_b200::DeviceHMatrix<T, double> DG(*H2, *deferred, bk);
+        if (!DG.is_valid() || deferred->size() == 0) {
+            upd(GENERATED_DENSE, 1.);
+        } else {
+            for (char trans : valid_trans(sym, is_complex)) {
+                const size_t ni = trans == 'N' ? nc : nr, no = trans == 'N' ? nr : nc;
+                T alpha = rnd_scalar<T>(gen), beta = rnd_scalar<T>(gen);
+                auto x = rnd_vector<T>(gen, ni), y0 = rnd_vector<T>(gen, no);
+                auto yr = y0, yg = y0;
+                openmp_internal_add_hmatrix_vector_product(trans, alpha, H, x.data(), beta, yr.data());
+                DG.internal_add_vector_product(trans, alpha, x.data(), beta, yg.data());
+                upd(GENERATED_DENSE, rel_err(yg, yr));
+            }
         }
     }
 

@@ -19,6 +19,7 @@ void ref_case_destroy(void *h) { delete static_cast<CaseBase *>(h); }
 const htb_hmatrix_desc *ref_case_desc(void *h) { return static_cast<CaseBase *>(h)->desc(); }
 void ref_case_info(void *h, double *out, int n) { static_cast<CaseBase *>(h)->info(out, n); }
 void ref_case_permutation(void *h, int side, int32_t *out) { static_cast<CaseBase *>(h)->permutation(side, out); }
+void ref_case_points(void *h, int side, double *out) { static_cast<CaseBase *>(h)->points(side, out); }
 
 // variant: 0 openmp_internal_*, 1 sequential_internal_*, 2 user-numbering add_hmatrix_vector_product(par),
 //          3 through htool::LocalToLocalHMatrix, 4 through htool::RestrictedGlobalToLocalHMatrix

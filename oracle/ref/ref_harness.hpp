@@ -142,6 +142,7 @@ struct CaseBase {
     virtual const htb_hmatrix_desc *desc()                                                                                             = 0;
     virtual void info(double *out, int n)                                                                                              = 0;
     virtual void permutation(int side, int32_t *out)                                                                                   = 0;
+    virtual void points(int side, double *out)                                                                                         = 0;
     virtual void vector_product(int variant, char trans, const void *alpha, const void *in, const void *beta, void *out)               = 0;
     virtual void matrix_product_row_major(int variant, char trans, const void *alpha, const void *in, const void *beta, void *out, int mu) = 0;
     virtual void matrix_product_user(char trans, const void *alpha, const void *in, const void *beta, void *out, int mu)               = 0;
@@ -272,6 +273,17 @@ struct Case final : CaseBase {
         const auto &prm = c.get_permutation();
         for (int i = 0; i < c.get_size(); i++)
             out[i] = prm[c.get_offset() + i] - c.get_offset();
+    }
+
+    // the points of the root block's rows (side 0) / columns (side 1) in CLUSTER numbering, 3 doubles each: what
+    // htb_generator_desc wants (row i of the block <-> user index permutation[offset + i])
+    void points(int side, double *out) override {
+        const auto &c       = side == 0 ? hmatrix->get_target_cluster() : hmatrix->get_source_cluster();
+        const auto &prm     = c.get_permutation();
+        const double *pts   = side == 0 ? target_points.data() : source_points->data();
+        for (int i = 0; i < c.get_size(); i++)
+            for (int d = 0; d < 3; d++)
+                out[3 * static_cast<size_t>(i) + d] = pts[3 * static_cast<size_t>(prm[c.get_offset() + i]) + d];
     }
 
     void vector_product(int variant, char trans, const void *alpha, const void *in, const void *beta, void *out) override {

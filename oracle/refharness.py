@@ -13,7 +13,7 @@ import os
 
 import numpy as np
 
-from htool_b200.capi import LEAF_NP_DTYPE, htb_hmatrix_desc
+from htool_b200.capi import LEAF_NP_DTYPE, htb_hmatrix_desc, htb_leaf
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_LIB = os.path.join(HERE, "_ref", "libhtool_ref.so")
@@ -74,6 +74,7 @@ def load():
         lib.ref_case_desc.argtypes = [C.c_void_p]
         lib.ref_case_info.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         lib.ref_case_permutation.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        lib.ref_case_points.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         lib.ref_case_vector_product.argtypes = [C.c_void_p, C.c_int, C.c_char, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.ref_case_matrix_product_row_major.argtypes = [C.c_void_p, C.c_int, C.c_char, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.ref_case_matrix_product_user.argtypes = [C.c_void_p, C.c_char, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -159,6 +160,23 @@ class RefCase:
         out = np.zeros(self.nb_rows if side == 0 else self.nb_cols, dtype=np.int32)
         self.lib.ref_case_permutation(self.handle, side, out.ctypes.data)
         return out
+
+    def points(self, side: int) -> np.ndarray:
+        """(n, 3) points of the root block's rows (side 0) / columns (side 1) in cluster numbering."""
+        out = np.zeros((self.nb_rows if side == 0 else self.nb_cols, 3))
+        self.lib.ref_case_points(self.handle, side, out.ctypes.data)
+        return out
+
+    def desc_without_dense_data(self):
+        """A copy of the descriptor whose dense leaves carry no coefficients (data0 = NULL): the input of
+        htb_create_generated. Returns (desc, keepalive)."""
+        lv = self.leaves().copy()
+        lv["data0"][lv["rank"] < 0] = 0
+        arr = (htb_leaf * max(1, len(lv))).from_buffer_copy(lv.tobytes() if len(lv) else bytes(C.sizeof(htb_leaf)))
+        d = htb_hmatrix_desc()
+        C.memmove(C.byref(d), C.byref(self.desc), C.sizeof(htb_hmatrix_desc))
+        d.leaves = C.cast(arr, C.POINTER(htb_leaf))
+        return d, arr
 
     def _sc(self, v):
         return np.array([v], dtype=self.np_dtype)
