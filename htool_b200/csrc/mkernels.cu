@@ -243,23 +243,28 @@ __global__ void __launch_bounds__((kReduceWarpsMax + 1) * 32) reduce_m_kernel(MS
 }
 
 // ---- APPLY_M --------------------------------------------------------------------------------------------------------
-// Warp w < 16: column tile ct = w & 7 (real columns 8 ct .. 8 ct + 7 of the group), parity par = w >> 3: it owns the 8-row
-// tiles 2 j + par, j < 8, of the block for those columns: acc[j] = C[8 (2 j + par) + g][8 ct + 2 tig + {0, 1}].
+// 16 consumer warps = CT column tiles x PAR = 16 / CT row-tile classes (CT = 8 for a full group of 64 real columns, fewer for
+// small mu so that no warp multiplies zero columns). Warp w: column tile ct = w % CT (real columns 8 ct .. 8 ct + 7), class
+// par = w / CT: it owns the 8-row tiles j PAR + par of the block for those columns,
+// acc[j] = C[8 (j PAR + par) + g][8 ct + 2 tig + {0, 1}].
 //   D[i][c] += A[i][k] B[k][c]:  A = panel fragment P[row][k0 + tig] read from the ring slot, one per row tile the run
 //   meets; B = row (k0 + tig) of what the run's columns multiply, columns 8 ct + g.
 // The B rows (T vectors REDUCE_M / COMBINE_M just wrote, rows of the input matrix for dense columns) form a STREAM in the
 // order of the block's columns. Warp 17, the B producer, walks the column tables of the stages as they arrive and copies
-// the rows with cp.async into a ring of chunks of 32 rows (row stride VSP: conflict-free B fragments), 1 - 2 chunks ahead of
-// the consumers, so that the DRAM latency of the B rows never meets a DMMA. Every run starts at a multiple of 4 in the
-// stream: a k-step never straddles two chunks.
+// the rows with cp.async (LDGSTS: one warp instruction moves one 512 B row; a per-row bulk copy is ~6 x slower to issue)
+// into a ring of chunks of 32 rows (row stride VSP: conflict-free B fragments), completion signalled on the chunk's
+// mbarrier by cp.async.mbarrier.arrive — the producer never waits for data and stays 2 - 3 chunks ahead of the consumers, so
+// the DRAM latency of the B rows never meets a DMMA. Every run starts at a multiple of 4 in the stream and every stage at
+// a multiple of 32: a k-step never straddles two chunks, a chunk never two stages.
 // smem: [stage ring: slot = stage | aux] [B ring: chunk = 32 x VSP doubles] [barriers]
 constexpr int kBChunk = 32;
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
+// 16 B of zeros (src-size 0: nothing is read from src, which only has to be a valid address)
+__device__ __forceinline__ void cp_async16_zero(uint32_t dst, const void *src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16, 0;" ::"r"(dst), "l"(src) : "memory"); }
 __device__ __forceinline__ void cp_async8(uint32_t dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory"); }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// arrive on the mbarrier (one of its expected arrivals) once all the cp.async of this thread issued so far have landed
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) { asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory"); }
 
 struct BRing {
     unsigned char *base;
@@ -267,30 +272,20 @@ struct BRing {
     uint32_t chunk_bytes, mask, log2n; // ring of 2^log2n chunks
 };
 
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
-
 // The B producer warp: see above. Mirrors the consumers' walk (stages, runs, the applied-twice filter, the alignment of
-// run / stage starts) so that both sides agree on the position of every column in the stream. One LANE per column: a row
-// is one bulk copy (TMA, completion counted in bytes on the chunk's mbarrier), so the warp never waits for data; rows of
-// an input matrix whose row stride is not a multiple of 16 B (odd mu, double) go through 8-byte cp.async instead.
+// run / stage starts) so that both sides agree on the position of every column in the stream. Lane c first works out where
+// the row of column c of the batch comes from; then the warp copies the rows one after the other, 16 B per lane.
 template <bool CPLX>
 __device__ __forceinline__ void produce_b(const MSide &ks, const BlockDesc &bd, const MArgs &a, unsigned char *ring, uint32_t slot_bytes, uint64_t *full, uint64_t *empty, const BRing &br, uint32_t n_my_stages, int lane) {
     const bool in16 = (a.ld_in % 2 == 0) && (a.col0 % 2 == 0) && (a.mc % 2 == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 15u) == 0); // rows of the input matrix are 16 B aligned
+    const uint32_t row_bytes = static_cast<uint32_t>(a.vsp) * 8u;
     RingPos pos;
-    uint32_t bpos    = 0;  // position in the B stream
-    long long open   = -1; // chunk being filled
-    bool slow_copies = false; // the open chunk holds cp.async copies: wait for them before publishing
-    auto publish     = [&]() { // hand the open chunk to the consumers: its phase completes when the bulk copies have landed
+    uint32_t bpos  = 0;  // position in the B stream
+    long long open = -1; // chunk being filled
+    auto publish   = [&]() { // hand the open chunk to the consumers: its phase completes when every lane's copies have landed
         if (open < 0)
             return;
-        if (slow_copies) {
-            cp_async_commit();
-            cp_async_wait<0>();
-            slow_copies = false;
-        }
-        __syncwarp();
-        if (lane == 0)
-            mbar_arrive(smem_u32(&br.full[open & br.mask]));
+        cp_async_arrive(smem_u32(&br.full[open & br.mask]));
         open = -1;
     };
     for (uint32_t q = 0; q < n_my_stages; q++, pos.advance(ks.ring_stages)) {
@@ -299,7 +294,7 @@ __device__ __forceinline__ void produce_b(const MSide &ks, const BlockDesc &bd, 
         const AuxHeader ah         = *reinterpret_cast<const AuxHeader *>(stage + ks.stage_bytes);
         const RunDesc *runs        = reinterpret_cast<const RunDesc *>(stage + ks.stage_bytes + sizeof(AuxHeader));
         const uint32_t *cols       = reinterpret_cast<const uint32_t *>(runs + ah.n_runs);
-        bpos                       = (bpos + 31u) & ~31u; // a chunk never spans two stages: everything is published when the stage ends
+        bpos                       = (bpos + 31u) & ~31u;
         for (uint32_t r = 0; r < ah.n_runs; r++) {
             const RunDesc rd = runs[r];
             if (a.twice_only && !(rd.flags & 1u))
@@ -317,60 +312,53 @@ __device__ __forceinline__ void produce_b(const MSide &ks, const BlockDesc &bd, 
                     __syncwarp();
                     open = chunk;
                 }
-                unsigned char *cbase = br.base + static_cast<size_t>(chunk & br.mask) * br.chunk_bytes;
-                const uint32_t bar   = smem_u32(&br.full[chunk & br.mask]);
-                // lane c copies the row of column j + c of the run into row first + c of the chunk
-                const double *p = nullptr;
-                uint32_t bytes = 0, mode = 3; // 0 bulk copy, 1 cp.async 8 B pieces, 2 zero row, 3 nothing
+                const uint32_t dst0 = smem_u32(br.base + static_cast<size_t>(chunk & br.mask) * br.chunk_bytes) + first * row_bytes;
+                // lane c: source of the row of column j + c
+                const double *p = nullptr; // nullptr: a row of zeros (dense column outside the input matrix)
+                bool dense      = false;
                 if (static_cast<uint32_t>(lane) < n) {
                     const uint32_t src = cols[rd.col0 + j + lane];
                     if (src & 0x80000000u) { // dense column: a row of the input matrix, mc doubles
                         const long long row = static_cast<long long>(src & 0x7fffffffu) + a.in_shift;
-                        if (row < 0 || row >= a.in_rows)
-                            mode = 2;
-                        else {
-                            p     = a.in + row * a.ld_in + a.col0;
-                            bytes = static_cast<uint32_t>(a.mc) * 8u;
-                            mode  = in16 ? 0u : 1u;
-                        }
-                    } else { // a scratch vector (VS doubles, 16 B aligned)
-                        p     = a.mscratch + static_cast<size_t>(src) * a.vsp;
-                        bytes = static_cast<uint32_t>(a.vs) * 8u;
-                        mode  = 0;
+                        dense               = true;
+                        if (row >= 0 && row < a.in_rows)
+                            p = a.in + row * a.ld_in + a.col0;
+                    } else // a scratch vector (VS doubles, 16 B aligned)
+                        p = a.mscratch + static_cast<size_t>(src) * a.vsp;
+                }
+                const unsigned dense_mask = __ballot_sync(0xffffffffu, dense);
+                for (uint32_t c = 0; c < n; c++) {
+                    const unsigned long long pc = __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(p), static_cast<int>(c));
+                    const double *row           = reinterpret_cast<const double *>(pc);
+                    const uint32_t dst          = dst0 + c * row_bytes;
+                    const bool is_dense         = (dense_mask >> c) & 1u;
+                    if (row == nullptr) {
+                        if (2 * lane < a.vs)
+                            cp_async16_zero(dst + 16u * lane, a.mscratch);
+                    } else if (!is_dense || in16) {
+                        if (2 * lane < (is_dense ? a.mc : a.vs))
+                            cp_async16(dst + 16u * lane, row + 2 * lane);
+                    } else {
+                        for (int e = lane; e < a.mc; e += 32)
+                            cp_async8(dst + 8u * e, row + e);
                     }
                 }
-                uint32_t tx = mode == 0 ? bytes : 0u;
-#pragma unroll
-                for (int d = 16; d >= 1; d >>= 1)
-                    tx += __shfl_xor_sync(0xffffffffu, tx, d);
-                if (lane == 0 && tx)
-                    mbar_expect_tx(bar, tx);
-                __syncwarp();
-                unsigned char *drow = cbase + static_cast<size_t>(first + lane) * a.vsp * 8u;
-                if (mode == 0)
-                    bulk_g2s_plain(smem_u32(drow), p, bytes, bar);
-                else if (mode == 1) {
-                    for (int e = 0; e < a.mc; e++)
-                        cp_async8(smem_u32(drow) + 8u * e, p + e);
-                } else if (mode == 2) {
-                    for (int e = 0; e < a.vs; e++)
-                        reinterpret_cast<double *>(drow)[e] = 0.;
-                }
-                if (__any_sync(0xffffffffu, mode == 1))
-                    slow_copies = true;
                 j += n;
             }
             bpos += K;
         }
         publish(); // end of the stage: the consumers must not wait for the next stage to see its last chunk
+        __syncwarp();
         if (lane == 0)
             mbar_arrive(smem_u32(&empty[pos.slot])); // the column tables of this stage are no longer needed
     }
 }
 
-template <bool CPLX, int MIN_CTAS>
-__global__ void __launch_bounds__((kApplyWarps + 2) * 32, MIN_CTAS) apply_m_kernel(MSide ks, MArgs a, int b_log2n) {
-    constexpr int CS = CPLX ? 1 : 0;
+template <bool CPLX, int CT>
+__global__ void __launch_bounds__((kApplyWarps + 2) * 32, 1) apply_m_kernel(MSide ks, MArgs a, int b_log2n) {
+    constexpr int CS  = CPLX ? 1 : 0;
+    constexpr int PAR = kApplyWarps / CT;                            // row-tile classes
+    constexpr int NJ  = (CPLX ? 8 : 16) / PAR > 0 ? (CPLX ? 8 : 16) / PAR : 1; // row tiles of a warp (a complex block has 64 rows = 8 tiles)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const BlockDesc bd = ks.blocks[ks.order[blockIdx.x]];
     if (a.twice_only && !(bd.flags & 1u))
@@ -396,7 +384,7 @@ __global__ void __launch_bounds__((kApplyWarps + 2) * 32, MIN_CTAS) apply_m_kern
             mbar_init(smem_u32(&empty[s]), kApplyWarps + 1); // the consumers and the B producer
         }
         for (uint32_t s = 0; s <= br.mask; s++) {
-            mbar_init(smem_u32(&br.full[s]), 1);
+            mbar_init(smem_u32(&br.full[s]), 32); // one cp.async.mbarrier.arrive per lane of the B producer
             mbar_init(smem_u32(&br.empty[s]), kApplyWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -412,21 +400,22 @@ __global__ void __launch_bounds__((kApplyWarps + 2) * 32, MIN_CTAS) apply_m_kern
         produce_b<CPLX>(ks, bd, a, ring, slot_bytes, full, empty, br, n_my_stages, lane);
         return;
     }
-    const int ct = warp & 7, par = warp >> 3;
-    constexpr int NJ = CPLX ? 4 : 8; // row tiles of a warp: block_rows / 16 (a complex block has 64 rows)
+    const int ct = warp % CT, par = warp / CT;
     double acc[NJ][2];
 #pragma unroll
     for (int j = 0; j < NJ; j++)
         acc[j][0] = acc[j][1] = 0.;
     // column of the B row this lane reads: c = 8 ct + g; complex, odd contraction index: the swapped partner with a sign
-    const int cB         = 8 * ct + g;
-    const bool c_valid   = cB < a.mc;
-    const int cB_odd     = cB ^ 1;
-    const double sgn_odd = ((cB & 1) != 0) == (a.conj == 0) ? 1. : -1.; // (i v)[c] = c even ? -im(v) : re(v); conjugated: opposite
+    const int cB       = 8 * ct + g;
+    const bool c_valid = cB < a.mc;
+    const int cBl      = (CPLX && (tig & 1)) ? (cB ^ 1) : cB; // (i v)[c] = c even ? -im(v) : re(v); conjugated panel: the opposite sign
+    const double bs    = (CPLX && (tig & 1)) ? ((((cB & 1) != 0) == (a.conj == 0)) ? 1. : -1.) : 1.;
+    const size_t bstep = static_cast<size_t>(4 >> CS) * a.vsp; // B rows per k-step
+    const int my_row0  = 8 * par + g;                          // my row in tile j is my_row0 + 8 PAR j
 
     RingPos pos;
-    uint32_t cpos     = 0;  // position in the B stream (same walk as produce_b)
-    long long cur     = -1; // chunk the warp is reading
+    uint32_t cpos = 0;  // position in the B stream (same walk as produce_b)
+    long long cur = -1; // chunk the warp is reading
     for (uint32_t q = 0; q < n_my_stages; q++, pos.advance(ks.ring_stages)) {
         mbar_wait(smem_u32(&full[pos.slot]), pos.phase);
         const unsigned char *stage = ring + static_cast<size_t>(pos.slot) * slot_bytes;
@@ -444,14 +433,17 @@ __global__ void __launch_bounds__((kApplyWarps + 2) * 32, MIN_CTAS) apply_m_kern
             const uint32_t run_pos = cpos;
             cpos += rd.K;
             const int row0 = rd.row0, h = static_cast<int>(rd.h_minus_1) + 1;
-            // my row tiles 2 j + par that meet rows [row0, row0 + h)
+            // my row tiles j PAR + par that meet rows [row0, row0 + h): j in [jlo, jhi]
             const int tlo = row0 >> 3, thi = (row0 + h - 1) >> 3;
-            const int jlo = (tlo - par + 1) >> 1, jhi = (thi - par) >> 1; // ceil / floor of (t - par) / 2 (arithmetic shift)
-            const bool mine = jlo <= jhi; // (a warp without rows in the run still walks its chunks: the B ring is released by all)
+            const int jlo = tlo <= par ? 0 : (tlo - par + PAR - 1) / PAR, jhi = thi >= par ? (thi - par) / PAR : -1;
+            const bool mine = jlo <= jhi && jlo < NJ; // (a warp without rows in the run still walks its chunks: the B ring is released by all)
             const uint32_t Kr = static_cast<uint32_t>(rd.K) << CS; // contraction length
             const uint32_t ld = CPLX ? 2u * static_cast<uint32_t>(h) : unit_ld(static_cast<uint32_t>(h), sizeof(double));
-            const double *P   = data + (static_cast<size_t>(rd.data_off) << CS);
-            // the k-steps of the run, chunk by chunk of the B ring (a k-step never straddles two chunks)
+            const size_t pstep = static_cast<size_t>(4 >> CS) * ld;
+            // this lane's panel column (contraction index tig) at my row of tile 0 — dereferenced only where the row exists
+            const double *Prun = data + (static_cast<size_t>(rd.data_off) << CS) + static_cast<size_t>(tig >> CS) * ld + (CPLX ? (tig & 1) : 0);
+            const int path     = !mine ? 0 : (jlo == jhi ? 1 : ((row0 == 0 && h == bd.nrows && jlo == 0 && jhi == NJ - 1) ? 2 : 3));
+            // the k-steps of the run, chunk by chunk of the B ring
             for (uint32_t k0 = 0; k0 < Kr;) {
                 const uint32_t pos0   = run_pos + (k0 >> CS);
                 const long long chunk = static_cast<long long>(pos0 >> 5);
@@ -467,35 +459,36 @@ __global__ void __launch_bounds__((kApplyWarps + 2) * 32, MIN_CTAS) apply_m_kern
                 uint32_t kend = k0 + ((32u - (pos0 & 31u)) << CS); // first contraction index of the next chunk
                 if (kend > Kr)
                     kend = Kr;
-                if (mine) {
-                    // this lane's B row (contraction index k0 + tig) and panel column; both advance by one k-step per iteration
-                    const double *Bl = reinterpret_cast<const double *>(br.base + static_cast<size_t>(chunk & br.mask) * br.chunk_bytes) + static_cast<size_t>((pos0 & 31u) + (static_cast<uint32_t>(tig) >> CS)) * a.vsp +
-                                       ((CPLX && (tig & 1)) ? cB_odd : cB);
-                    const double bs  = (CPLX && (tig & 1)) ? sgn_odd : 1.;
-                    const double *Pl = P + static_cast<size_t>((k0 + tig) >> CS) * ld + (CPLX ? (tig & 1) : 0);
-                    const size_t bstep = static_cast<size_t>(4 >> CS) * a.vsp, pstep = static_cast<size_t>(4 >> CS) * ld;
-                    if (jlo == jhi) {
+                const uint32_t kfull = (kend == Kr) ? (Kr & ~3u) : kend; // k-steps starting below kfull have four valid contraction indices
+                if (path != 0) {
+                    const double *Bl = reinterpret_cast<const double *>(br.base + static_cast<size_t>(chunk & br.mask) * br.chunk_bytes) + static_cast<size_t>((pos0 & 31u) + (static_cast<uint32_t>(tig) >> CS)) * a.vsp + cBl;
+                    const double *Pl = Prun + static_cast<size_t>(k0 >> 2) * pstep;
+                    uint32_t k       = k0;
+                    if (path == 1) {
                         // ONE row tile (dense leaves, small clusters): two accumulation chains over alternating k-steps hide
-                        // the DMMA latency, folded into the tile's accumulator at the end of the segment
-                        const int row   = 8 * (2 * jlo + par) + g;
-                        const bool rv   = row >= row0 && row < row0 + h;
-                        const uint32_t ao = static_cast<uint32_t>(rv ? row - row0 : 0) << CS;
+                        // the DMMA latency; folded into the tile's accumulator at the end of the segment
+                        const int rr   = my_row0 + 8 * PAR * jlo - row0;
+                        const bool rv  = rr >= 0 && rr < h;
+                        const double *Pa = Pl + (static_cast<size_t>(rv ? rr : 0) << CS);
                         double t0[2] = {0., 0.}, t1[2] = {0., 0.};
-                        uint32_t k = k0;
-                        for (; k + 4 < kend; k += 8) {
-                            const bool kv1 = k + 4 + tig < Kr;
-                            const double b0 = c_valid ? bs * Bl[0] : 0., b1 = (c_valid && kv1) ? bs * Bl[bstep] : 0.;
-                            const double a0 = rv ? Pl[ao] : 0., a1 = (rv && kv1) ? Pl[pstep + ao] : 0.;
-                            dmma(t0, a0, b0);
-                            dmma(t1, a1, b1);
+                        // (mma.sync is warp-wide: every lane runs the same DMMAs; a lane without a row or a column in the run
+                        // feeds zeros)
+                        const bool lv = rv && c_valid;
+                        for (; k + 8 <= kfull; k += 8) {
+                            dmma(t0, lv ? Pa[0] : 0., lv ? bs * Bl[0] : 0.);
+                            dmma(t1, lv ? Pa[pstep] : 0., lv ? bs * Bl[bstep] : 0.);
                             Bl += 2 * bstep;
-                            Pl += 2 * pstep;
+                            Pa += 2 * pstep;
                         }
-                        if (k < kend) {
-                            const bool kv  = k + tig < Kr;
-                            const double b = (c_valid && kv) ? bs * Bl[0] : 0.;
-                            const double av = (rv && kv) ? Pl[ao] : 0.;
-                            dmma(t0, av, b);
+                        if (k < kfull) {
+                            dmma(t0, lv ? Pa[0] : 0., lv ? bs * Bl[0] : 0.);
+                            Bl += bstep;
+                            Pa += pstep;
+                            k += 4;
+                        }
+                        if (k < kend) { // last, partial k-step of the run
+                            const bool kv = lv && k + tig < Kr;
+                            dmma(t1, kv ? Pa[0] : 0., kv ? bs * Bl[0] : 0.);
                         }
                         t0[0] += t1[0];
                         t0[1] += t1[1];
@@ -505,18 +498,16 @@ __global__ void __launch_bounds__((kApplyWarps + 2) * 32, MIN_CTAS) apply_m_kern
                                 acc[j][0] += t0[0];
                                 acc[j][1] += t0[1];
                             }
-                    } else if (row0 == 0 && h == bd.nrows && jlo == 0 && jhi == NJ - 1) {
+                    } else if (path == 2) {
                         // A run over ALL the rows of the block (the panels of the tall leaves: most of the coefficients): no
                         // row predicates. A lane whose row lies past the block reads the coefficient of a neighbouring
                         // column instead of a zero: it only pollutes accumulators of rows >= nrows, which are never stored.
-                        const double *Pa = Pl + (static_cast<size_t>(8 * par + g) << CS);
-                        uint32_t k = k0;
-                        const uint32_t kfull = (kend == Kr) ? (Kr & ~3u) : kend; // k-steps below kfull have four valid contraction indices
+                        const double *Pa = Pl + (static_cast<size_t>(my_row0) << CS);
                         for (; k < kfull; k += 4) {
                             const double b = c_valid ? bs * Bl[0] : 0.;
 #pragma unroll
                             for (int j = 0; j < NJ; j++)
-                                dmma(acc[j], Pa[static_cast<size_t>(16 * j) << CS], b);
+                                dmma(acc[j], Pa[static_cast<size_t>(8 * PAR * j) << CS], b);
                             Bl += bstep;
                             Pa += pstep;
                         }
@@ -525,20 +516,20 @@ __global__ void __launch_bounds__((kApplyWarps + 2) * 32, MIN_CTAS) apply_m_kern
                             const double b = (c_valid && kv) ? bs * Bl[0] : 0.;
 #pragma unroll
                             for (int j = 0; j < NJ; j++) {
-                                const bool rv = 16 * j + 8 * par + g < h;
-                                dmma(acc[j], (kv && rv) ? Pa[static_cast<size_t>(16 * j) << CS] : 0., b);
+                                const bool rv = 8 * PAR * j + my_row0 < h;
+                                dmma(acc[j], (kv && rv) ? Pa[static_cast<size_t>(8 * PAR * j) << CS] : 0., b);
                             }
                         }
                     } else {
-                        for (uint32_t k = k0; k < kend; k += 4) {
+                        for (; k < kend; k += 4) {
                             const bool kv  = k + tig < Kr;
                             const double b = (c_valid && kv) ? bs * Bl[0] : 0.;
 #pragma unroll
                             for (int j = 0; j < NJ; j++) {
                                 if (j >= jlo && j <= jhi) { // warp-uniform
-                                    const int row   = 8 * (2 * j + par) + g;
-                                    const bool rv   = row >= row0 && row < row0 + h;
-                                    const double av = (rv && kv) ? Pl[static_cast<uint32_t>(rv ? row - row0 : 0) << CS] : 0.;
+                                    const int rr    = my_row0 + 8 * PAR * j - row0;
+                                    const bool rv   = rr >= 0 && rr < h;
+                                    const double av = (rv && kv) ? Pl[static_cast<size_t>(rv ? rr : 0) << CS] : 0.;
                                     dmma(acc[j], av, b);
                                 }
                             }
@@ -547,7 +538,7 @@ __global__ void __launch_bounds__((kApplyWarps + 2) * 32, MIN_CTAS) apply_m_kern
                         }
                     }
                 }
-                k0 = kend == Kr ? Kr : kend;
+                k0 = kend;
             }
         }
         // ADDVEC units (side 1, transposed direction): C rows += the TF vectors REDUCE_M produced for dense leaves
@@ -558,21 +549,15 @@ __global__ void __launch_bounds__((kApplyWarps + 2) * 32, MIN_CTAS) apply_m_kern
                 if (a.twice_only && !unit_twice(un.geom))
                     continue;
                 const int row0 = static_cast<int>(unit_row0(un.geom)), h = static_cast<int>(unit_h(un.geom));
-                const int tlo = row0 >> 3, thi = (row0 + h - 1) >> 3;
-                const int jlo = (tlo - par + 1) >> 1, jhi = (thi - par) >> 1;
-                if (jlo > jhi)
-                    continue;
                 const uint32_t src = mun[u].src;
                 const int c        = 8 * ct + 2 * tig;
 #pragma unroll
                 for (int j = 0; j < NJ; j++) {
-                    if (j >= jlo && j <= jhi) {
-                        const int row = 8 * (2 * j + par) + g;
-                        if (row >= row0 && row < row0 + h && c < a.vs) {
-                            const double2 v = *reinterpret_cast<const double2 *>(a.mscratch + static_cast<size_t>(src + row - row0) * a.vsp + c);
-                            acc[j][0] += v.x;
-                            acc[j][1] += v.y;
-                        }
+                    const int rr = my_row0 + 8 * PAR * j - row0;
+                    if (rr >= 0 && rr < h && c < a.vs) {
+                        const double2 v = *reinterpret_cast<const double2 *>(a.mscratch + static_cast<size_t>(src + rr) * a.vsp + c);
+                        acc[j][0] += v.x;
+                        acc[j][1] += v.y;
                     }
                 }
             }
@@ -585,7 +570,7 @@ __global__ void __launch_bounds__((kApplyWarps + 2) * 32, MIN_CTAS) apply_m_kern
     const int c = 8 * ct + 2 * tig;
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
-        const int i = 8 * (2 * j + par) + g;
+        const int i = my_row0 + 8 * PAR * j;
         if (i < bd.nrows && c < a.mc) {
             const long long gr = static_cast<long long>(bd.row_start) + i + a.out_shift;
             if (gr >= 0 && gr < a.out_rows) {
@@ -678,13 +663,20 @@ cudaError_t configure_mkernels(const LaunchConfig &cfg, size_t esize) {
     };
     cudaError_t e;
     const void *red = esize == 16 ? reinterpret_cast<const void *>(reduce_m_kernel<true>) : reinterpret_cast<const void *>(reduce_m_kernel<false>);
-    const void *app1 = esize == 16 ? reinterpret_cast<const void *>(apply_m_kernel<true, 1>) : reinterpret_cast<const void *>(apply_m_kernel<false, 1>);
-    const void *app2 = esize == 16 ? reinterpret_cast<const void *>(apply_m_kernel<true, 2>) : reinterpret_cast<const void *>(apply_m_kernel<false, 2>);
     if ((e = set(red, reduce_m_smem_bytes(cfg, 64, esize))) != cudaSuccess)
         return e;
-    if ((e = set(app1, apply_m_smem_bytes(cfg))) != cudaSuccess)
-        return e;
-    return set(app2, apply_m_smem_bytes(cfg));
+    const void *app[4];
+    if (esize == 16) {
+        app[0] = reinterpret_cast<const void *>(apply_m_kernel<true, 1>), app[1] = reinterpret_cast<const void *>(apply_m_kernel<true, 2>);
+        app[2] = reinterpret_cast<const void *>(apply_m_kernel<true, 4>), app[3] = reinterpret_cast<const void *>(apply_m_kernel<true, 8>);
+    } else {
+        app[0] = reinterpret_cast<const void *>(apply_m_kernel<false, 1>), app[1] = reinterpret_cast<const void *>(apply_m_kernel<false, 2>);
+        app[2] = reinterpret_cast<const void *>(apply_m_kernel<false, 4>), app[3] = reinterpret_cast<const void *>(apply_m_kernel<false, 8>);
+    }
+    for (const void *f : app)
+        if ((e = set(f, apply_m_smem_bytes(cfg))) != cudaSuccess)
+            return e;
+    return cudaSuccess;
 }
 
 cudaError_t launch_reduce_m(const SideDevice &side, const LaunchConfig &cfg, const MArgs &args, cudaStream_t stream) {
@@ -708,16 +700,29 @@ cudaError_t launch_apply_m(const SideDevice &side, const LaunchConfig &cfg, cons
     const size_t smem  = apply_m_smem_bytes(cfg);
     const int threads  = (kApplyWarps + 2) * 32;
     const int bl       = cfg.m_b_ring_log2;
-    // m_apply_ctas = 2: register-capped variant (56 registers), two CTAs per SM when the ring is short enough to fit twice
-    if (cfg.m_apply_ctas >= 2) {
-        if (args.cplx)
-            apply_m_kernel<true, 2><<<side.n_blocks, threads, smem, stream>>>(ms, a, bl);
+    // column tiles of the group: no warp is given zero columns to multiply
+    const int ct = args.vs > 32 ? 8 : (args.vs > 16 ? 4 : (args.vs > 8 ? 2 : 1));
+#define HTB_APPLY_M(C, T) apply_m_kernel<C, T><<<side.n_blocks, threads, smem, stream>>>(ms, a, bl)
+    if (args.cplx) {
+        if (ct == 8)
+            HTB_APPLY_M(true, 8);
+        else if (ct == 4)
+            HTB_APPLY_M(true, 4);
+        else if (ct == 2)
+            HTB_APPLY_M(true, 2);
         else
-            apply_m_kernel<false, 2><<<side.n_blocks, threads, smem, stream>>>(ms, a, bl);
-    } else if (args.cplx)
-        apply_m_kernel<true, 1><<<side.n_blocks, threads, smem, stream>>>(ms, a, bl);
-    else
-        apply_m_kernel<false, 1><<<side.n_blocks, threads, smem, stream>>>(ms, a, bl);
+            HTB_APPLY_M(true, 1);
+    } else {
+        if (ct == 8)
+            HTB_APPLY_M(false, 8);
+        else if (ct == 4)
+            HTB_APPLY_M(false, 4);
+        else if (ct == 2)
+            HTB_APPLY_M(false, 2);
+        else
+            HTB_APPLY_M(false, 1);
+    }
+#undef HTB_APPLY_M
     return cudaGetLastError();
 }
 
