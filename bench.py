@@ -72,7 +72,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gmres-iterations", type=int, default=200, help="BASELINE.json configs[4]: repeated matvecs inside a device-resident GMRES solve (0: skip)")
     ap.add_argument("--sections", default=os.environ.get("HTB_BENCH_SECTIONS", "all"),
-                    help="comma-separated extra sections (all | none | mu64,mu5,symmetric,helmholtz,gmres,dist_parity,config3,config4)")
+                    help="comma-separated extra sections (all | none | mu64,mu5,symmetric,helmholtz,gmres,generated_dense,dist_parity,config3_helmholtz_S_N2e6,config4_laplace_N8e6_gmres)")
     ap.add_argument("--extra-points", type=int, default=0, help="override the point count of the extra sections (tests)")
     return ap.parse_args()
 
@@ -544,6 +544,33 @@ def section_single(w: Workload, steps, warmup, label):
             "store_bytes_this_rank": w.oinfo["store_bytes"]}
 
 
+def section_generated_dense(w: Workload, y_host_packed, x_global):
+    """SURVEY.md 8f rank 1, first step: the dense near-field leaves generated on the GPU straight into the leaf store
+    (htb_create_generated) instead of HMatrix::compute_dense_data on the host. Same descriptors; the product of the
+    device-generated operator must equal the host-packed one bit for bit (real kernel) and the reference's to 1e-12."""
+    from htool_b200 import capi
+
+    case = w.case
+    desc0, keep = case.desc_without_dense_data()
+    desc0.device = w.ctx.local_rank
+    kernel = "laplace_reg" if w.dtype == np.float64 else "helmholtz"
+    t0 = time.perf_counter()
+    op = capi.Operator(desc0, generator=(kernel, case.points(0), case.points(1), 5.0))
+    t_create = time.perf_counter() - t0
+    y = np.zeros(w.n_local, w.dtype)
+    op.add_vector_product("N", 1.0, x_global, 0.0, y)
+    lv = case.leaves()
+    dense = lv["rank"] < 0
+    out = {"dense_leaves_generated_on_device": int(dense.sum()), "dense_coefficients": int((lv["nb_rows"][dense].astype(np.int64) * lv["nb_cols"][dense]).sum()),
+           "create_seconds_with_device_generation": t_create, "create_seconds_host_packed": w.t_upload,
+           "product_bit_identical_to_host_packed_operator": bool(np.array_equal(y, y_host_packed)),
+           "rel_l2_vs_host_packed_operator": float(np.linalg.norm(y - y_host_packed) / np.linalg.norm(y_host_packed))}
+    op.close()
+    if not out["rel_l2_vs_host_packed_operator"] <= 1e-12:
+        raise SystemExit(f"PARITY FAILURE (device-generated dense leaves): {out}")
+    return out
+
+
 def section_gmres(w: Workload, n_products, bare_value, restart=40):
     """BASELINE.json configs[4]: products INSIDE a device-resident restarted GMRES (htb_gmres; with N > 1 the product is the
     distributed one and the inner products are summed over the ranks). Call sequence per iteration = what
@@ -769,6 +796,7 @@ def run_ours(args):
     }
     RESULT["line"] = line
     log(f"headline: {value:.1f} matvec/s, e2e {1.0 / m['e2e_s']:.1f}, parity {gate['parity']:.1e}")
+    y_headline, x_headline = gate["y_gpu"], gate["x_global"]
     del gate
 
     npts = args.extra_points
@@ -779,6 +807,8 @@ def run_ours(args):
         run_section("mu5", lambda: section_multi_rhs(w, 5, steps=10), 30)  # HPDDM block methods, the reference tests mu = 5
     if mu == 1 and args.gmres_iterations > 0 and world == 1:
         run_section("gmres", lambda: section_gmres(w, args.gmres_iterations, value), 20)
+    if base_double and world == 1:
+        run_section("generated_dense", lambda: section_generated_dense(w, y_headline, x_headline), 20)
     line["gmres"] = extras.get("gmres")
     w.close()
     del w

@@ -471,24 +471,22 @@ __global__ void __launch_bounds__((kApplyWarps + 2) * 32, 1) apply_m_kernel(MSid
                         const bool rv  = rr >= 0 && rr < h;
                         const double *Pa = Pl + (static_cast<size_t>(rv ? rr : 0) << CS);
                         double t0[2] = {0., 0.}, t1[2] = {0., 0.};
-                        // (mma.sync is warp-wide: every lane runs the same DMMAs; a lane without a row or a column in the run
-                        // feeds zeros)
-                        const bool lv = rv && c_valid;
+                        // (a lane supplies A[row g][k tig] and B[k tig][column g]: the two are valid independently)
                         for (; k + 8 <= kfull; k += 8) {
-                            dmma(t0, lv ? Pa[0] : 0., lv ? bs * Bl[0] : 0.);
-                            dmma(t1, lv ? Pa[pstep] : 0., lv ? bs * Bl[bstep] : 0.);
+                            dmma(t0, rv ? Pa[0] : 0., c_valid ? bs * Bl[0] : 0.);
+                            dmma(t1, rv ? Pa[pstep] : 0., c_valid ? bs * Bl[bstep] : 0.);
                             Bl += 2 * bstep;
                             Pa += 2 * pstep;
                         }
                         if (k < kfull) {
-                            dmma(t0, lv ? Pa[0] : 0., lv ? bs * Bl[0] : 0.);
+                            dmma(t0, rv ? Pa[0] : 0., c_valid ? bs * Bl[0] : 0.);
                             Bl += bstep;
                             Pa += pstep;
                             k += 4;
                         }
                         if (k < kend) { // last, partial k-step of the run
-                            const bool kv = lv && k + tig < Kr;
-                            dmma(t1, kv ? Pa[0] : 0., kv ? bs * Bl[0] : 0.);
+                            const bool kv = k + tig < Kr;
+                            dmma(t1, (rv && kv) ? Pa[0] : 0., (c_valid && kv) ? bs * Bl[0] : 0.);
                         }
                         t0[0] += t1[0];
                         t0[1] += t1[1];
