@@ -361,9 +361,9 @@ static int run_product_m(htb_operator *h, char trans, const double *alpha, const
         if ((rc = ensure_mscratch(h, (std::min(group, mu) * W + 7) & ~7)) != HTB_OK)
             return rc;
         double *M1 = static_cast<double *>(h->d_mscratch);
-        double *M2 = M1 + h->mscratch_elems * static_cast<size_t>(h->mscratch_vs + 8);
+        double *M2 = M1 + h->mscratch_elems * static_cast<size_t>(h->mscratch_vs + 8); // (allocated with the padded stride: any vsp <= vs + 8 fits)
         MArgs base;
-        base.ld_in = mu * W, base.ld_out = mu * W, base.col0 = col0 * W, base.mc = mc, base.vs = vs, base.vsp = vs + 8, base.cplx = cplx ? 1 : 0;
+        base.ld_in = mu * W, base.ld_out = mu * W, base.col0 = col0 * W, base.mc = mc, base.vs = vs, base.vsp = vs, base.cplx = cplx ? 1 : 0; // vsp: vector stride of the scratch = row stride of APPLY_M's B ring
         base.alpha = alpha[0], base.alpha_im = cplx ? alpha[1] : 0.;
         // ps: side streamed by REDUCE_M (producers), cs: side streamed by APPLY_M (consumers)
         auto direction = [&](int cs, double *M, int in_shift, long long in_rows, int out_shift, long long out_rows, double b_re, double b_im, int twice_only, int conj) -> int {
@@ -373,7 +373,7 @@ static int run_product_m(htb_operator *h, char trans, const double *alpha, const
             int rc2;
             if (h->side[ps].stream && (rc2 = timed(HTB_PASS_REDUCE, [&]() { return launch_reduce_m(h->side[ps], h->launch_cfg, r, st); }, "reduce_m")) != HTB_OK)
                 return rc2;
-            if (h->side[cs].n_combine_m && (rc2 = timed(HTB_PASS_COMBINE, [&]() { return launch_combine_m(h->side[cs], M, vs, twice_only, st); }, "combine_m")) != HTB_OK)
+            if (h->side[cs].n_combine_m && (rc2 = timed(HTB_PASS_COMBINE, [&]() { return launch_combine_m(h->side[cs], M, vs, base.vsp, twice_only, st); }, "combine_m")) != HTB_OK)
                 return rc2;
             MArgs ap = r;
             ap.out = out, ap.out_rows = out_rows, ap.out_shift = out_shift, ap.beta = b_re, ap.beta_im = b_im;

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__((kReduceWarpsMax + 1) * 32) reduce_m_kernel(MS
     if (n_my_stages == 0)
         return;
     const uint32_t slot_bytes = ks.stage_bytes + ks.aux_bytes;
-    const int XS              = a.vsp;
+    const int XS              = a.vs + 8; // row stride of the X block in shared memory: conflict-free A fragments
     const int RB              = ks.block_rows << CS; // real rows of a block
     unsigned char *ring       = smem_raw;
     double *Xs                = reinterpret_cast<double *>(smem_raw + static_cast<size_t>(ks.ring_stages) * slot_bytes);
@@ -213,6 +213,7 @@ __global__ void __launch_bounds__((kReduceWarpsMax + 1) * 32) reduce_m_kernel(MS
                 const uint32_t col  = 8u * t + g;
                 const bool cv       = col < K;
                 const double *Pc    = P + static_cast<size_t>(cv ? col : K - 1u) * ld;
+#pragma unroll 2
                 for (uint32_t i0 = 0; i0 < h; i0 += 4) {
                     const uint32_t i = i0 + tig;
                     const double b   = (cv && i < h) ? Pc[i < h ? i : h - 1u] : 0.; // P[i][col], zero outside the run
@@ -251,10 +252,9 @@ __global__ void __launch_bounds__((kReduceWarpsMax + 1) * 32) reduce_m_kernel(MS
 //   meets; B = row (k0 + tig) of what the run's columns multiply, columns 8 ct + g.
 // The B rows (T vectors REDUCE_M / COMBINE_M just wrote, rows of the input matrix for dense columns) form a STREAM in the
 // order of the block's columns. Warp 17, the B producer, walks the column tables of the stages as they arrive and copies
-// the rows with cp.async (LDGSTS: one warp instruction moves one 512 B row; a per-row bulk copy is ~6 x slower to issue)
-// into a ring of chunks of 32 rows (row stride VSP: conflict-free B fragments), completion signalled on the chunk's
-// mbarrier by cp.async.mbarrier.arrive — the producer never waits for data and stays 2 - 3 chunks ahead of the consumers, so
-// the DRAM latency of the B rows never meets a DMMA. Every run starts at a multiple of 4 in the stream and every stage at
+// the rows with bulk copies (TMA; consecutive rows in ONE copy, see produce_b) into a ring of chunks of 32 rows whose row
+// stride is the scratch's vector stride, completion counted in bytes on the chunk's mbarrier — the producer never waits
+// for data and stays 2 - 3 chunks ahead of the consumers, so the DRAM latency of the B rows never meets a DMMA. Every run starts at a multiple of 4 in the stream and every stage at
 // a multiple of 32: a k-step never straddles two chunks, a chunk never two stages.
 // smem: [stage ring: slot = stage | aux] [B ring: chunk = 32 x VSP doubles] [barriers]
 constexpr int kBChunk = 32;
@@ -272,20 +272,35 @@ struct BRing {
     uint32_t chunk_bytes, mask, log2n; // ring of 2^log2n chunks
 };
 
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+
 // The B producer warp: see above. Mirrors the consumers' walk (stages, runs, the applied-twice filter, the alignment of
-// run / stage starts) so that both sides agree on the position of every column in the stream. Lane c first works out where
-// the row of column c of the batch comes from; then the warp copies the rows one after the other, 16 B per lane.
+// run / stage starts) so that both sides agree on the position of every column in the stream. One LANE per column works
+// out where the column's row comes from; consecutive columns whose rows are consecutive in memory too — the columns of one
+// low-rank piece (its T vectors are adjacent in the scratch, whose vector stride IS the row stride of the chunk), the
+// columns of one dense leaf when the rows of the input matrix are VS doubles apart — are then copied by ONE bulk copy
+// (TMA, completion counted in bytes on the chunk's mbarrier): ~4 copies per chunk of 32 rows instead of 32, and the warp
+// never waits for data.
 template <bool CPLX>
 __device__ __forceinline__ void produce_b(const MSide &ks, const BlockDesc &bd, const MArgs &a, unsigned char *ring, uint32_t slot_bytes, uint64_t *full, uint64_t *empty, const BRing &br, uint32_t n_my_stages, int lane) {
-    const bool in16 = (a.ld_in % 2 == 0) && (a.col0 % 2 == 0) && (a.mc % 2 == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 15u) == 0); // rows of the input matrix are 16 B aligned
+    const bool in16   = (a.ld_in % 2 == 0) && (a.col0 % 2 == 0) && (a.mc % 2 == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 15u) == 0); // rows of the input matrix are 16 B aligned
+    const bool in_seq = in16 && a.ld_in == a.vsp && a.mc == a.vs && a.vs == a.vsp;                                                        // ... and consecutive rows are one row of the chunk apart
     const uint32_t row_bytes = static_cast<uint32_t>(a.vsp) * 8u;
     RingPos pos;
-    uint32_t bpos  = 0;  // position in the B stream
-    long long open = -1; // chunk being filled
-    auto publish   = [&]() { // hand the open chunk to the consumers: its phase completes when every lane's copies have landed
+    uint32_t bpos    = 0;  // position in the B stream
+    long long open   = -1; // chunk being filled
+    bool slow_copies = false; // the open chunk holds cp.async copies: wait for them before publishing
+    auto publish     = [&]() { // hand the open chunk to the consumers: its phase completes when the bulk copies have landed
         if (open < 0)
             return;
-        cp_async_arrive(smem_u32(&br.full[open & br.mask]));
+        if (slow_copies) {
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            slow_copies = false;
+        }
+        __syncwarp();
+        if (lane == 0)
+            mbar_arrive(smem_u32(&br.full[open & br.mask]));
         open = -1;
     };
     for (uint32_t q = 0; q < n_my_stages; q++, pos.advance(ks.ring_stages)) {
@@ -312,43 +327,65 @@ __device__ __forceinline__ void produce_b(const MSide &ks, const BlockDesc &bd, 
                     __syncwarp();
                     open = chunk;
                 }
-                const uint32_t dst0 = smem_u32(br.base + static_cast<size_t>(chunk & br.mask) * br.chunk_bytes) + first * row_bytes;
-                // lane c: source of the row of column j + c
-                const double *p = nullptr; // nullptr: a row of zeros (dense column outside the input matrix)
-                bool dense      = false;
+                const uint32_t bar  = smem_u32(&br.full[chunk & br.mask]);
+                const uint32_t dst  = smem_u32(br.base + static_cast<size_t>(chunk & br.mask) * br.chunk_bytes) + (first + lane) * row_bytes;
+                // lane c: where the row of column j + c comes from. key: rows with consecutive keys are consecutive in memory
+                const double *p = nullptr;
+                uint32_t mode = 3, key = 0xffffffffu; // 0 bulk copy, 1 cp.async 8 B pieces, 2 zero row, 3 nothing
                 if (static_cast<uint32_t>(lane) < n) {
                     const uint32_t src = cols[rd.col0 + j + lane];
                     if (src & 0x80000000u) { // dense column: a row of the input matrix, mc doubles
                         const long long row = static_cast<long long>(src & 0x7fffffffu) + a.in_shift;
-                        dense               = true;
-                        if (row >= 0 && row < a.in_rows)
-                            p = a.in + row * a.ld_in + a.col0;
-                    } else // a scratch vector (VS doubles, 16 B aligned)
-                        p = a.mscratch + static_cast<size_t>(src) * a.vsp;
-                }
-                const unsigned dense_mask = __ballot_sync(0xffffffffu, dense);
-                for (uint32_t c = 0; c < n; c++) {
-                    const unsigned long long pc = __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(p), static_cast<int>(c));
-                    const double *row           = reinterpret_cast<const double *>(pc);
-                    const uint32_t dst          = dst0 + c * row_bytes;
-                    const bool is_dense         = (dense_mask >> c) & 1u;
-                    if (row == nullptr) {
-                        if (2 * lane < a.vs)
-                            cp_async16_zero(dst + 16u * lane, a.mscratch);
-                    } else if (!is_dense || in16) {
-                        if (2 * lane < (is_dense ? a.mc : a.vs))
-                            cp_async16(dst + 16u * lane, row + 2 * lane);
-                    } else {
-                        for (int e = lane; e < a.mc; e += 32)
-                            cp_async8(dst + 8u * e, row + e);
+                        if (row < 0 || row >= a.in_rows)
+                            mode = 2;
+                        else {
+                            p    = a.in + row * a.ld_in + a.col0;
+                            mode = in16 ? 0u : 1u;
+                            key  = in_seq ? src : 0xffffffffu;
+                        }
+                    } else { // a scratch vector (VS doubles, 16 B aligned), the next column of the piece is the next vector
+                        p    = a.mscratch + static_cast<size_t>(src) * a.vsp;
+                        mode = 0;
+                        key  = src;
                     }
                 }
+                // heads of the sequences of consecutive rows; a head copies its whole sequence
+                const uint32_t prev_key = __shfl_up_sync(0xffffffffu, key, 1);
+                const bool cont         = lane > 0 && mode == 0 && key != 0xffffffffu && prev_key != 0xffffffffu && key == prev_key + 1u;
+                const unsigned heads    = __ballot_sync(0xffffffffu, mode == 0 && !cont);
+                const unsigned bulk     = __ballot_sync(0xffffffffu, mode == 0);
+                const uint32_t one_row  = (mode == 0 && key == 0xffffffffu) ? static_cast<uint32_t>(a.mc) * 8u : row_bytes; // (a lone row of the input matrix: mc doubles)
+                const uint32_t tx       = static_cast<uint32_t>(__popc(bulk)) * row_bytes; // counted below with the exact sizes
+                (void)tx;
+                uint32_t my_bytes = 0;
+                if (mode == 0 && !cont) {
+                    const unsigned above = (lane == 31) ? 0u : ((heads | ~bulk) >> (lane + 1)); // next head, or the first lane that does not bulk-copy
+                    const uint32_t len   = above ? static_cast<uint32_t>(__ffs(static_cast<int>(above))) : (32u - static_cast<uint32_t>(lane));
+                    my_bytes             = len == 1 ? one_row : len * row_bytes;
+                }
+                uint32_t total = my_bytes;
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1)
+                    total += __shfl_xor_sync(0xffffffffu, total, d);
+                if (lane == 0 && total)
+                    mbar_expect_tx(bar, total);
+                __syncwarp();
+                if (my_bytes)
+                    bulk_g2s_plain(dst, p, my_bytes, bar);
+                else if (mode == 1) {
+                    for (int e = 0; e < a.mc; e++)
+                        cp_async8(dst + 8u * e, p + e);
+                } else if (mode == 2) {
+                    for (int e = 0; e < a.vs; e++)
+                        asm volatile("st.shared.f64 [%0], %1;" ::"r"(dst + 8u * e), "d"(0.) : "memory");
+                }
+                if (__any_sync(0xffffffffu, mode == 1))
+                    slow_copies = true;
                 j += n;
             }
             bpos += K;
         }
         publish(); // end of the stage: the consumers must not wait for the next stage to see its last chunk
-        __syncwarp();
         if (lane == 0)
             mbar_arrive(smem_u32(&empty[pos.slot])); // the column tables of this stage are no longer needed
     }
@@ -384,7 +421,7 @@ __global__ void __launch_bounds__((kApplyWarps + 2) * 32, 1) apply_m_kernel(MSid
             mbar_init(smem_u32(&empty[s]), kApplyWarps + 1); // the consumers and the B producer
         }
         for (uint32_t s = 0; s <= br.mask; s++) {
-            mbar_init(smem_u32(&br.full[s]), 32); // one cp.async.mbarrier.arrive per lane of the B producer
+            mbar_init(smem_u32(&br.full[s]), 1); // the B producer's arrive; the rows are counted in bytes (expect_tx)
             mbar_init(smem_u32(&br.empty[s]), kApplyWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -501,6 +538,7 @@ __global__ void __launch_bounds__((kApplyWarps + 2) * 32, 1) apply_m_kernel(MSid
                         // row predicates. A lane whose row lies past the block reads the coefficient of a neighbouring
                         // column instead of a zero: it only pollutes accumulators of rows >= nrows, which are never stored.
                         const double *Pa = Pl + (static_cast<size_t>(my_row0) << CS);
+#pragma unroll 2
                         for (; k < kfull; k += 4) {
                             const double b = c_valid ? bs * Bl[0] : 0.;
 #pragma unroll
@@ -724,11 +762,11 @@ cudaError_t launch_apply_m(const SideDevice &side, const LaunchConfig &cfg, cons
     return cudaGetLastError();
 }
 
-cudaError_t launch_combine_m(const SideDevice &side, double *mscratch, int vs, int twice_only, cudaStream_t stream) {
+cudaError_t launch_combine_m(const SideDevice &side, double *mscratch, int vs, int vsp, int twice_only, cudaStream_t stream) {
     if (side.n_combine_m == 0)
         return cudaSuccess;
     const int warps = 8; // 32 warps (one per vector of the piece, pieces hold <= 32 vectors) per entry
-    combine_m_kernel<<<static_cast<unsigned>((static_cast<long long>(side.n_combine_m) * 32 + warps - 1) / warps), warps * 32, 0, stream>>>(side.combine_m, side.n_combine_m, mscratch, vs, vs + 8, twice_only);
+    combine_m_kernel<<<static_cast<unsigned>((static_cast<long long>(side.n_combine_m) * 32 + warps - 1) / warps), warps * 32, 0, stream>>>(side.combine_m, side.n_combine_m, mscratch, vs, vsp, twice_only);
     return cudaGetLastError();
 }
 

@@ -20,7 +20,7 @@ struct MArgs {
     int ld_out        = 0;
     int col0 = 0, mc = 0; // column group
     int vs            = 0; // mc rounded up to a multiple of 8
-    int vsp           = 0; // vector stride of the scratch = vs + 8 (padded: conflict-free fragments once staged in shared memory)
+    int vsp           = 0; // vector stride of the scratch (= vs) and row stride of the B ring of APPLY_M: consecutive vectors of a piece are consecutive rows
     double *mscratch  = nullptr; // one multi-RHS scratch copy: [TF | PARTM[0] | PARTM[1]] x vsp
     double alpha = 0., beta = 0.;
     double alpha_im = 0., beta_im = 0.; // complex<double> only
@@ -33,7 +33,7 @@ struct MArgs {
 cudaError_t launch_reduce_m(const SideDevice &side, const LaunchConfig &cfg, const MArgs &args, cudaStream_t stream);
 cudaError_t launch_apply_m(const SideDevice &side, const LaunchConfig &cfg, const MArgs &args, cudaStream_t stream);
 // Sums the partials of the direction whose consumer is `side` into TF.
-cudaError_t launch_combine_m(const SideDevice &side, double *mscratch, int vs, int twice_only, cudaStream_t stream);
+cudaError_t launch_combine_m(const SideDevice &side, double *mscratch, int vs, int vsp, int twice_only, cudaStream_t stream);
 size_t reduce_m_smem_bytes(const LaunchConfig &cfg, int vs, size_t esize);
 size_t apply_m_smem_bytes(const LaunchConfig &cfg);
 cudaError_t configure_mkernels(const LaunchConfig &cfg, size_t esize);
