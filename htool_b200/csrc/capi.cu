@@ -29,7 +29,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 namespace {
 std::mutex g_option_mutex;
 std::map<std::string, int64_t> g_options = {
-    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 2048}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 4}, {"m_b_ring_log2", 2}, {"m_reduce_ring_stages", 5}, {"mrhs_min", 2}, {"m_apply_ctas", 1}, {"pack_generate_dense", 0}, {"m_reduce_warps", 24}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}};
+    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 2048}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 4}, {"m_b_ring_log2", 2}, {"m_reduce_ring_stages", 5}, {"mrhs_min", 0}, {"m_apply_ctas", 1}, {"pack_generate_dense", 0}, {"m_reduce_warps", 24}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}};
 
 int64_t option(const char *key) {
     std::lock_guard<std::mutex> lock(g_option_mutex);
@@ -411,7 +411,11 @@ int product_device(htb_operator *h, char trans, const void *alpha, const void *i
     int rc = check_trans(h, trans);
     if (rc != HTB_OK)
         return rc;
-    if (h->m_path_ok && mu >= static_cast<int>(option("mrhs_min"))) {
+    // From how many right-hand sides the tensor-core path wins over a loop of single-RHS products (measured, N = 1e6: the
+    // multi-RHS passes cost ~5 single-RHS products whatever mu <= 64 is): option mrhs_min, 0 = automatic
+    const int mrhs_auto = h->dtype == HTB_COMPLEX_DOUBLE ? 4 : 5;
+    const int mrhs_min  = option("mrhs_min") > 0 ? static_cast<int>(option("mrhs_min")) : mrhs_auto;
+    if (h->m_path_ok && mu >= mrhs_min) {
         // tensor-core path: one pass over all columns, so a distributed product first waits for the gather of x
         if (split && split->flags)
             HTB_CUDA(launch_wait_flags(split->flags, split->world, split->epoch, h->stream));

@@ -213,7 +213,6 @@ __global__ void __launch_bounds__((kReduceWarpsMax + 1) * 32) reduce_m_kernel(MS
                 const uint32_t col  = 8u * t + g;
                 const bool cv       = col < K;
                 const double *Pc    = P + static_cast<size_t>(cv ? col : K - 1u) * ld;
-#pragma unroll 2
                 for (uint32_t i0 = 0; i0 < h; i0 += 4) {
                     const uint32_t i = i0 + tig;
                     const double b   = (cv && i < h) ? Pc[i < h ? i : h - 1u] : 0.; // P[i][col], zero outside the run
@@ -355,18 +354,15 @@ __device__ __forceinline__ void produce_b(const MSide &ks, const BlockDesc &bd, 
                 const unsigned heads    = __ballot_sync(0xffffffffu, mode == 0 && !cont);
                 const unsigned bulk     = __ballot_sync(0xffffffffu, mode == 0);
                 const uint32_t one_row  = (mode == 0 && key == 0xffffffffu) ? static_cast<uint32_t>(a.mc) * 8u : row_bytes; // (a lone row of the input matrix: mc doubles)
-                const uint32_t tx       = static_cast<uint32_t>(__popc(bulk)) * row_bytes; // counted below with the exact sizes
-                (void)tx;
                 uint32_t my_bytes = 0;
                 if (mode == 0 && !cont) {
                     const unsigned above = (lane == 31) ? 0u : ((heads | ~bulk) >> (lane + 1)); // next head, or the first lane that does not bulk-copy
                     const uint32_t len   = above ? static_cast<uint32_t>(__ffs(static_cast<int>(above))) : (32u - static_cast<uint32_t>(lane));
                     my_bytes             = len == 1 ? one_row : len * row_bytes;
                 }
-                uint32_t total = my_bytes;
-#pragma unroll
-                for (int d = 16; d >= 1; d >>= 1)
-                    total += __shfl_xor_sync(0xffffffffu, total, d);
+                // bytes of the batch: every bulk-copied row brings row_bytes, except lone rows of an input matrix narrower than VS
+                const unsigned narrow = __ballot_sync(0xffffffffu, my_bytes != 0 && my_bytes < row_bytes);
+                const uint32_t total  = static_cast<uint32_t>(__popc(bulk)) * row_bytes - static_cast<uint32_t>(__popc(narrow)) * (row_bytes - static_cast<uint32_t>(a.mc) * 8u);
                 if (lane == 0 && total)
                     mbar_expect_tx(bar, total);
                 __syncwarp();

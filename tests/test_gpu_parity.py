@@ -82,7 +82,7 @@ def test_random_leaf_lists_vs_oracle(capi, seed, dtype_code, symmetric):
             assert rel_err(yg, yo) < TOL, (trans, alpha, beta, rel_err(yg, yo))
         # mu >= 2: FP64 tensor-core kernels on RUNS (mkernels.cu), column groups of 64 real / 32 complex right-hand sides
         am, bm = (0.5, 2.0) if flat.np_dtype == np.float64 else (0.5 - 0.3j, 2.0 + 0.25j)
-        for mu in (2, 5, 8, 13, 33, 64, 70):
+        for mu in (2, 5, 8, 13, 24, 33, 64, 70):
             X, Y0 = rnd(rng, ni * mu, flat.np_dtype), rnd(rng, no * mu, flat.np_dtype)
             Yo, Yg = Y0.copy(), Y0.copy()
             flat.oracle_matrix_product_row_major(trans, am, X, bm, Yo, mu)
@@ -95,6 +95,30 @@ def test_random_leaf_lists_vs_oracle(capi, seed, dtype_code, symmetric):
                 op.add_matrix_product_row_major(trans, am, X, 0.0, Yg, mu)
                 assert rel_err(Yg, Yo) < TOL
     op.close()
+
+
+@pytest.mark.parametrize("dtype_code", [0, 1])
+def test_tensor_core_path_from_two_right_hand_sides(capi, dtype_code):
+    """mrhs_min = 2 forces the DMMA kernels for mu = 2, 3, 4 (by default a loop of single-RHS products is faster there)."""
+    from oracle.flatcase import random_flatcase
+
+    flat = random_flatcase(seed=11, dtype_code=dtype_code, symmetric="S", nb_rows=500, nb_cols=500, n_leaves=120, max_dim=200, max_rank=30)
+    capi.set_option("mrhs_min", 2)
+    try:
+        op = capi.Operator(flat.desc)
+        rng = np.random.default_rng(2)
+        for trans in valid_trans(flat.symmetry):
+            for mu in (2, 3, 4):
+                X, Y0 = rnd(rng, flat.nb_cols * mu, flat.np_dtype), rnd(rng, flat.nb_rows * mu, flat.np_dtype)
+                Yo, Yg = Y0.copy(), Y0.copy()
+                l0 = op.launch_count()
+                flat.oracle_matrix_product_row_major(trans, 0.5, X, -1.5, Yo, mu)
+                op.add_matrix_product_row_major(trans, 0.5, X, -1.5, Yg, mu)
+                assert rel_err(Yg, Yo) < TOL, (trans, mu)
+                assert op.launch_count() - l0 <= 6  # one multi-RHS pass sequence (twice under symmetry), not mu products
+        op.close()
+    finally:
+        capi.set_option("mrhs_min", 0)
 
 
 def test_beta_zero_ignores_nan_in_out(capi):
