@@ -29,7 +29,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 namespace {
 std::mutex g_option_mutex;
 std::map<std::string, int64_t> g_options = {
-    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 2048}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 4}, {"m_b_ring_log2", 2}, {"m_reduce_ring_stages", 5}, {"mrhs_min", 0}, {"m_apply_ctas", 1}, {"pack_generate_dense", 0}, {"m_reduce_warps", 24}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}};
+    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 4096}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 4}, {"m_b_ring_log2", 2}, {"m_reduce_ring_stages", 4}, {"mrhs_min", 0}, {"pack_generate_dense", 0}, {"sort_units", 1}, {"m_reduce_warps", 24}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}};
 
 int64_t option(const char *key) {
     std::lock_guard<std::mutex> lock(g_option_mutex);
@@ -705,6 +705,7 @@ static int create_impl(const htb_hmatrix_desc *desc, const htb_generator_desc *g
 
     PackOptions popt;
     popt.generate_dense = gen != nullptr;
+    popt.sort_units     = static_cast<int>(option("sort_units"));
     popt.block_rows  = static_cast<int>(option("block_rows"));
     popt.piece_cols  = static_cast<int>(option("piece_cols"));
     popt.stage_bytes = static_cast<int>(option("stage_bytes"));
@@ -754,7 +755,6 @@ static int create_impl(const htb_hmatrix_desc *desc, const htb_generator_desc *g
         return fail(HTB_ERR_INVALID, "the shared-memory ring (ring_stages x stage_bytes) exceeds the shared memory of an SM");
     h->launch_cfg.m_ring_stages        = static_cast<int>(option("m_ring_stages"));
     h->launch_cfg.m_reduce_ring_stages = static_cast<int>(option("m_reduce_ring_stages"));
-    h->launch_cfg.m_apply_ctas         = static_cast<int>(option("m_apply_ctas"));
     h->launch_cfg.m_b_ring_log2        = static_cast<int>(option("m_b_ring_log2"));
     h->launch_cfg.m_reduce_warps       = static_cast<int>(option("m_reduce_warps"));
     if (h->launch_cfg.m_b_ring_log2 < 1 || h->launch_cfg.m_b_ring_log2 > 3)
@@ -1014,6 +1014,7 @@ int htb_pack_host(const htb_hmatrix_desc *desc, int side, htb_packed_side *out) 
     if (option("cta_slots") > 0)
         popt.cta_slots = static_cast<int>(option("cta_slots"));
     popt.generate_dense = option("pack_generate_dense") != 0; // tests: what htb_create_generated would upload
+    popt.sort_units     = static_cast<int>(option("sort_units"));
     try {
         Packer pk(*desc, popt);
         auto *own   = new PackedOwner();

@@ -34,14 +34,13 @@ struct SideDevice {
 struct LaunchConfig {
     int block_rows  = 128;
     int stage_bytes = 24576;
-    int cseg_bytes  = 2048;
+    int cseg_bytes  = 4096;
     int ring_stages = 2;        // APPLY ring depth (slot = stage + c segment)
     int reduce_ring_stages = 3; // REDUCE ring depth (slot = stage)
     int m_ring_stages        = 4; // APPLY_M ring depth (slot = stage + aux record)
-    int m_reduce_ring_stages = 5; // REDUCE_M ring depth (1 CTA / SM: the X block takes 76 KiB)
+    int m_reduce_ring_stages = 4; // REDUCE_M ring depth (1 CTA / SM: the X block takes 76 KiB)
     int m_reduce_warps       = 24; // REDUCE_M consumer warps (4 .. 24)
     int m_b_ring_log2        = 2; // APPLY_M: the ring of B-row chunks (32 rows each) holds 2^this chunks
-    int m_apply_ctas         = 1; // APPLY_M: 2 = register-capped variant for two CTAs per SM (needs m_ring_stages <= 3)
     int evict_first = 1; // L2 evict_first hint on the coefficient stream
 };
 

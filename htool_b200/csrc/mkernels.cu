@@ -258,12 +258,7 @@ __global__ void __launch_bounds__((kReduceWarpsMax + 1) * 32) reduce_m_kernel(MS
 // smem: [stage ring: slot = stage | aux] [B ring: chunk = 32 x VSP doubles] [barriers]
 constexpr int kBChunk = 32;
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
-// 16 B of zeros (src-size 0: nothing is read from src, which only has to be a valid address)
-__device__ __forceinline__ void cp_async16_zero(uint32_t dst, const void *src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16, 0;" ::"r"(dst), "l"(src) : "memory"); }
 __device__ __forceinline__ void cp_async8(uint32_t dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory"); }
-// arrive on the mbarrier (one of its expected arrivals) once all the cp.async of this thread issued so far have landed
-__device__ __forceinline__ void cp_async_arrive(uint32_t bar) { asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory"); }
 
 struct BRing {
     unsigned char *base;

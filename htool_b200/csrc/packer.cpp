@@ -332,7 +332,7 @@ void Packer::make_incidence(int s) {
     // the block become consecutive in the stream and form RUNS (store.hpp) for the multi-RHS kernels. The sort is stable,
     // so leaf order — hence the summation order — stays fixed inside a run.
 #pragma omp parallel for schedule(dynamic, 64)
-    for (int b = 0; b < nb; b++) {
+    for (int b = 0; b < (opt.sort_units ? nb : 0); b++) {
         const uint64_t e0 = m_csr_ptr[s][b], e1 = m_csr_ptr[s][b + 1];
         auto key = [&](uint32_t li) {
             int lo, hi;

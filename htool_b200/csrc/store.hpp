@@ -194,11 +194,12 @@ struct DenseTask {
 static_assert(sizeof(DenseTask) == 32, "DenseTask must be 32 bytes");
 
 struct PackOptions {
+    int sort_units      = 1;     // order the units of a block by the rows they act on (RUNS of the multi-RHS kernels); 0: leaf order
     bool generate_dense = false; // dense leaves with data0 == NULL are allowed: their panels are generated on the device
     int block_rows  = 0;     // 32, 64 or 128; 0 = automatic (128 for double, 64 for complex<double>)
     int piece_cols  = 16;    // columns of a unit (<= 32); lowered automatically so that a unit fits a stage
     int stage_bytes = 24576; // bulk-copy granule of the coefficient stream, multiple of 16
-    int cseg_bytes  = 2048;  // capacity of a stage's c segment, multiple of 16
+    int cseg_bytes  = 4096;  // capacity of a stage's c segment, multiple of 16 (512 columns: stages of small-cluster runs still fill up)
     // Side 0 (target rows) may use smaller blocks than side 1 (0 = same as block_rows). Tried for the row strips of a
     // distributed operator (few target rows, all the source columns: 1024 APPLY blocks = 2.3 waves at 8 GPUs): halving
     // the target blocks speeds APPLY up by 8 % but the extra chunks cost the same in COMBINE (gpurun_out/t32), so the
