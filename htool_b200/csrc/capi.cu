@@ -29,7 +29,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 namespace {
 std::mutex g_option_mutex;
 std::map<std::string, int64_t> g_options = {
-    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 4096}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 4}, {"m_b_ring_log2", 2}, {"m_reduce_ring_stages", 4}, {"mrhs_min", 0}, {"pack_generate_dense", 0}, {"sort_units", 1}, {"m_reduce_warps", 24}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}};
+    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 4096}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 4}, {"m_b_ring_log2", 2}, {"m_reduce_ring_stages", 4}, {"mrhs_min", 0}, {"pack_generate_dense", 0}, {"sort_units", 1}, {"reduce_blocks_per_cta", 0}, {"m_reduce_warps", 24}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}};
 
 int64_t option(const char *key) {
     std::lock_guard<std::mutex> lock(g_option_mutex);
@@ -142,7 +142,8 @@ static int upload_store(htb_operator *h, const Packer &pk) {
             break;
         }
         h->owned.push_back(dstream);
-        sd.stream = static_cast<const unsigned char *>(dstream);
+        sd.stream       = static_cast<const unsigned char *>(dstream);
+        sd.stream_bytes = sl.stream_bytes;
         h->store_bytes += sl.stream_bytes;
         h->side_stream_bytes[s] = sl.stream_bytes;
         // batches of consecutive blocks whose streams fit one pinned buffer
@@ -746,6 +747,7 @@ static int create_impl(const htb_hmatrix_desc *desc, const htb_generator_desc *g
     h->launch_cfg.ring_stages        = static_cast<int>(option("ring_stages"));
     h->launch_cfg.reduce_ring_stages = static_cast<int>(option("reduce_ring_stages"));
     h->launch_cfg.evict_first = static_cast<int>(option("evict_first"));
+    h->launch_cfg.reduce_blocks_per_cta = static_cast<int>(option("reduce_blocks_per_cta"));
     if (h->launch_cfg.ring_stages < 2 || h->launch_cfg.ring_stages > 32 || h->launch_cfg.reduce_ring_stages < 2 || h->launch_cfg.reduce_ring_stages > 32)
         return fail(HTB_ERR_INVALID, "ring_stages / reduce_ring_stages must be in [2, 32]");
     cudaDeviceProp prop{};

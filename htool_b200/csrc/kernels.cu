@@ -426,13 +426,15 @@ __device__ __forceinline__ void fused_unit(const Unit &un, const T *data, const 
 }
 
 // ---- REDUCE -------------------------------------------------------------------------------------------
+// A CTA handles `bpc` blocks one after the other (bpc = 1 for big blocks; 2 for the small source blocks of a row strip of a
+// distributed operator, ~150 KB each at 8 GPUs): the producer lane streams their stages back to back through the same
+// ring, so the bulk-copy pipeline is filled once per CTA and never drains at a block boundary; only the consumers meet
+// there (the x sub-vector is re-staged). Blocks are paired heaviest with lightest (order[c], order[n - 1 - c]).
+__device__ __forceinline__ int reduce_block_of(int cta, int bi, int n_blocks) { return bi == 0 ? cta : n_blocks - 1 - cta; }
+
 template <typename T, bool CONJ>
-__global__ void __launch_bounds__(kThreads, sizeof(T) == 16 ? 3 : 0) reduce_kernel(KernelSide ks, PassArgs<T> a) {
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 16 ? 3 : 0) reduce_kernel(KernelSide ks, PassArgs<T> a, int n_blocks, int bpc) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const BlockDesc bd = ks.blocks[ks.order[blockIdx.x]];
-    const uint32_t n_my_stages = a.twice_only ? bd.n_twice_stages : bd.n_stages;
-    if (n_my_stages == 0)
-        return;
     const SmemLayout sm = carve(smem_raw, ks, ks.stage_bytes, sizeof(T) * ks.block_rows);
     T *xin              = reinterpret_cast<T *>(sm.vec);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -444,59 +446,94 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 16 ? 3 : 0) reduce_kern
     // the producer starts streaming coefficients at once: the first bulk copies are in flight while the consumers
     // wait for / stage the block's x sub-vector (a consumer-only named barrier orders that hand-off)
     if (warp == kConsumerWarps) {
-        if (lane == 0)
-            produce<T, false>(ks, bd, sm, a.twice_only, nullptr);
+        if (lane == 0) {
+            const uint64_t policy = ks.evict_first ? l2_evict_first_policy() : 0;
+            RingPos pos;
+            for (int bi = 0; bi < bpc; bi++) {
+                const int slot_id = reduce_block_of(blockIdx.x, bi, n_blocks);
+                if (bi > 0 && slot_id <= static_cast<int>(blockIdx.x))
+                    break; // odd block count: the middle block belongs to its CTA once
+                const BlockDesc bd = ks.blocks[ks.order[slot_id]];
+                if (bd.n_stages == 0)
+                    continue;
+                StageDesc next = ks.stages[bd.first_stage];
+                for (uint32_t st = 0; st < bd.n_stages; st++) {
+                    const StageDesc sd = next;
+                    if (st + 1 < bd.n_stages)
+                        next = ks.stages[bd.first_stage + st + 1]; // in flight while this stage waits for its slot
+                    if (a.twice_only && !(sd.flags & 1u))
+                        continue;
+                    const uint32_t full = smem_u32(&sm.full[pos.slot]);
+                    mbar_wait(smem_u32(&sm.empty[pos.slot]), pos.phase ^ 1u);
+                    mbar_arrive_expect_tx(full, sd.nbytes);
+                    bulk_g2s(smem_u32(sm.ring + static_cast<size_t>(pos.slot) * sm.slot_bytes), ks.stream + sd.byte_off, sd.nbytes, full, policy, ks.evict_first != 0);
+                    pos.advance(ks.ring_stages);
+                }
+            }
+        }
         return;
     }
-    if (a.wait_flags) { // distributed: the slice of x this block reads is written by its owner's push kernel (dist.cu)
-        if (threadIdx.x == 0) {
-            const uint32_t ow = a.wait_owner[ks.order[blockIdx.x]];
-            if (ow != 0xFFFFFFFFu)
-                for (uint32_t q = ow & 0xFFFFu; q <= (ow >> 16); q++)
-                    while (ld_acquire_sys(a.wait_flags + q) < a.wait_epoch)
-                        __nanosleep(64);
-        }
-        consumer_barrier();
-    }
-    // stage the block's x sub-vector in shared memory (every unit of the block multiplies a slice of it)
-    for (int i = threadIdx.x; i < ks.block_rows; i += kConsumerWarps * 32) {
-        const long long g = static_cast<long long>(bd.row_start) + i + a.in_shift;
-        xin[i]            = (i < bd.nrows && g >= 0 && g < a.in_len) ? a.in[g * a.stride] : zero_of(T{});
-    }
-    consumer_barrier();
-
-    // Every warp walks every stage (in the producer's order); the units are dealt round-robin over the warps ACROSS
-    // stages (ubase), so that a stage with few units does not always land on the same warps.
     RingPos pos;
     uint32_t ubase = warp;
-    for (uint32_t q = 0; q < n_my_stages; q++, pos.advance(ks.ring_stages)) {
-        const uint32_t slot = pos.slot;
-        mbar_wait(smem_u32(&sm.full[slot]), pos.phase);
-        const unsigned char *stage = sm.ring + static_cast<size_t>(slot) * sm.slot_bytes;
-        const StageHeader hdr      = *reinterpret_cast<const StageHeader *>(stage);
-        const Unit *units          = reinterpret_cast<const Unit *>(stage + sizeof(StageHeader));
-        const T *data              = reinterpret_cast<const T *>(stage + hdr.data_byte_off);
-        // ADDVEC units (dense leaves, direction 0): hand their x slices to the APPLY pass through the c-stream. They
-        // hold no coefficients: one unit per LANE, over all the consumer lanes of the CTA.
-        for (uint32_t u = hdr.n_panel + warp * 32 + lane; u < hdr.n_units; u += kConsumerWarps * 32) {
-            const Unit un = units[u];
-            if (a.twice_only && !unit_twice(un.geom))
-                continue;
-            const uint32_t row0 = unit_row0(un.geom), h = unit_h(un.geom);
-            T *out = a.scratch + un.out;
-            for (uint32_t i = 0; i < h; i++)
-                out[i] = xin[row0 + i];
+    for (int bi = 0; bi < bpc; bi++) {
+        const int slot_id = reduce_block_of(blockIdx.x, bi, n_blocks);
+        if (bi > 0 && slot_id <= static_cast<int>(blockIdx.x))
+            break;
+        const uint32_t block_id    = ks.order[slot_id];
+        const BlockDesc bd         = ks.blocks[block_id];
+        const uint32_t n_my_stages = a.twice_only ? bd.n_twice_stages : bd.n_stages;
+        if (n_my_stages == 0)
+            continue;
+        if (bi > 0)
+            consumer_barrier(); // every consumer has finished the units of the previous block: xin may be overwritten
+        if (a.wait_flags) { // distributed: the slice of x this block reads is written by its owner's push kernel (dist.cu)
+            if (threadIdx.x == 0) {
+                const uint32_t ow = a.wait_owner[block_id];
+                if (ow != 0xFFFFFFFFu)
+                    for (uint32_t q = ow & 0xFFFFu; q <= (ow >> 16); q++)
+                        while (ld_acquire_sys(a.wait_flags + q) < a.wait_epoch)
+                            __nanosleep(64);
+            }
+            consumer_barrier();
         }
-        for (uint32_t u = ubase; u < hdr.n_panel; u += kConsumerWarps) {
-            const Unit un = units[u];
-            if (a.twice_only && !unit_twice(un.geom))
-                continue;
-            reduce_unit<T, CONJ>(un, data, xin, a.scratch, lane);
+        // stage the block's x sub-vector in shared memory (every unit of the block multiplies a slice of it)
+        for (int i = threadIdx.x; i < ks.block_rows; i += kConsumerWarps * 32) {
+            const long long g = static_cast<long long>(bd.row_start) + i + a.in_shift;
+            xin[i]            = (i < bd.nrows && g >= 0 && g < a.in_len) ? a.in[g * a.stride] : zero_of(T{});
         }
-        ubase = (ubase - hdr.n_panel) & (kConsumerWarps - 1); // == (warp - units dealt so far) mod 8
-        __syncwarp();
-        if (lane == 0)
-            mbar_arrive(smem_u32(&sm.empty[slot]));
+        consumer_barrier();
+
+        // Every warp walks every stage (in the producer's order); the units are dealt round-robin over the warps ACROSS
+        // stages (ubase), so that a stage with few units does not always land on the same warps.
+        for (uint32_t q = 0; q < n_my_stages; q++, pos.advance(ks.ring_stages)) {
+            const uint32_t slot = pos.slot;
+            mbar_wait(smem_u32(&sm.full[slot]), pos.phase);
+            const unsigned char *stage = sm.ring + static_cast<size_t>(slot) * sm.slot_bytes;
+            const StageHeader hdr      = *reinterpret_cast<const StageHeader *>(stage);
+            const Unit *units          = reinterpret_cast<const Unit *>(stage + sizeof(StageHeader));
+            const T *data              = reinterpret_cast<const T *>(stage + hdr.data_byte_off);
+            // ADDVEC units (dense leaves, direction 0): hand their x slices to the APPLY pass through the c-stream. They
+            // hold no coefficients: one unit per LANE, over all the consumer lanes of the CTA.
+            for (uint32_t u = hdr.n_panel + warp * 32 + lane; u < hdr.n_units; u += kConsumerWarps * 32) {
+                const Unit un = units[u];
+                if (a.twice_only && !unit_twice(un.geom))
+                    continue;
+                const uint32_t row0 = unit_row0(un.geom), h = unit_h(un.geom);
+                T *out = a.scratch + un.out;
+                for (uint32_t i = 0; i < h; i++)
+                    out[i] = xin[row0 + i];
+            }
+            for (uint32_t u = ubase; u < hdr.n_panel; u += kConsumerWarps) {
+                const Unit un = units[u];
+                if (a.twice_only && !unit_twice(un.geom))
+                    continue;
+                reduce_unit<T, CONJ>(un, data, xin, a.scratch, lane);
+            }
+            ubase = (ubase - hdr.n_panel) & (kConsumerWarps - 1); // == (warp - units dealt so far) mod 8
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(smem_u32(&sm.empty[slot]));
+        }
     }
 }
 
@@ -776,7 +813,9 @@ template <typename T>
 struct Kernels;
 template <>
 struct Kernels<double> {
-    static void reduce(const KernelSide &ks, const PassArgs<double> &a, int grid, size_t smem, cudaStream_t st) { launch_pdl(reduce_kernel<double, false>, grid, kThreads, smem, st, ks, a); }
+    static void reduce(const KernelSide &ks, const PassArgs<double> &a, int n_blocks, int bpc, size_t smem, cudaStream_t st) {
+        launch_pdl(reduce_kernel<double, false>, (n_blocks + bpc - 1) / bpc, kThreads, smem, st, ks, a, n_blocks, bpc);
+    }
     static void apply(const KernelSide &ks, const PassArgs<double> &a, int grid, size_t smem, cudaStream_t st) {
         if (a.fused)
             launch_pdl(apply_kernel<double, false, true, false>, grid, kThreads, smem, st, ks, a);
@@ -794,11 +833,12 @@ struct Kernels<double> {
 };
 template <>
 struct Kernels<cplx> {
-    static void reduce(const KernelSide &ks, const PassArgs<cplx> &a, int grid, size_t smem, cudaStream_t st) {
+    static void reduce(const KernelSide &ks, const PassArgs<cplx> &a, int n_blocks, int bpc, size_t smem, cudaStream_t st) {
+        const int grid = (n_blocks + bpc - 1) / bpc;
         if (a.conj)
-            launch_pdl(reduce_kernel<cplx, true>, grid, kThreads, smem, st, ks, a);
+            launch_pdl(reduce_kernel<cplx, true>, grid, kThreads, smem, st, ks, a, n_blocks, bpc);
         else
-            launch_pdl(reduce_kernel<cplx, false>, grid, kThreads, smem, st, ks, a);
+            launch_pdl(reduce_kernel<cplx, false>, grid, kThreads, smem, st, ks, a, n_blocks, bpc);
     }
     static void apply(const KernelSide &ks, const PassArgs<cplx> &a, int grid, size_t smem, cudaStream_t st) {
         if (a.fused) { // (conj, conj2): (0,0) symmetric, (0,1) Hermitian 'N', (1,0) Hermitian 'C'
@@ -861,7 +901,13 @@ template <typename T>
 cudaError_t launch_reduce(const SideDevice &side, const LaunchConfig &cfg, const PassArgs<T> &args, cudaStream_t stream) {
     if (side.n_blocks == 0)
         return cudaSuccess;
-    Kernels<T>::reduce(make_kernel_side(side, cfg, cfg.reduce_ring_stages), args, side.n_blocks, reduce_smem_bytes(cfg, sizeof(T)), stream);
+    // blocks per CTA: 2 when the side's blocks are small (a row strip of a distributed operator), else 1; option reduce_blocks_per_cta
+    int bpc = cfg.reduce_blocks_per_cta;
+    if (bpc <= 0)
+        bpc = (side.n_blocks >= 2 && side.stream_bytes / static_cast<uint64_t>(side.n_blocks) < (uint64_t(400) << 10)) ? 2 : 1;
+    if (bpc > 2)
+        bpc = 2;
+    Kernels<T>::reduce(make_kernel_side(side, cfg, cfg.reduce_ring_stages), args, side.n_blocks, bpc, reduce_smem_bytes(cfg, sizeof(T)), stream);
     return cudaGetLastError();
 }
 

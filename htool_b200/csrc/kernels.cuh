@@ -25,6 +25,7 @@ struct SideDevice {
     const CombineEntry *combine_m   = nullptr; // multi-RHS partial sums of the direction whose consumer is this side
     int n_combine_m                 = 0;
     int n_blocks                    = 0;
+    uint64_t stream_bytes           = 0; // bytes of the side's stream (average block size decides how REDUCE groups blocks)
     int n_combine                   = 0;
     int n                           = 0;
     uint64_t cs_base                = 0; // element offset of CS[side] inside a scratch copy
@@ -41,6 +42,7 @@ struct LaunchConfig {
     int m_reduce_ring_stages = 4; // REDUCE_M ring depth (1 CTA / SM: the X block takes 76 KiB)
     int m_reduce_warps       = 24; // REDUCE_M consumer warps (4 .. 24)
     int m_b_ring_log2        = 2; // APPLY_M: the ring of B-row chunks (32 rows each) holds 2^this chunks
+    int reduce_blocks_per_cta = 0; // REDUCE: blocks handled by one CTA through one ring (0 = automatic: 2 for small blocks, else 1)
     int evict_first = 1; // L2 evict_first hint on the coefficient stream
 };
 

@@ -41,9 +41,8 @@ def main():
     from oracle import refharness as R
 
     R.set_num_threads(os.cpu_count() or 1)
-    bargs = argparse.Namespace(n=args.n, dtype=args.dtype, symmetry=args.symmetry, mu=1, gpus=1)
     t0 = time.perf_counter()
-    case = R.RefCase(**(bench.case_kwargs(bargs, args.partitions, args.rank) if args.partitions > 1 else bench.case_kwargs(bargs)))
+    case = R.RefCase(**(bench.case_kwargs(args.n, args.dtype, args.symmetry, args.partitions, args.rank) if args.partitions > 1 else bench.case_kwargs(args.n, args.dtype, args.symmetry)))
     print(json.dumps({"assembly_s": time.perf_counter() - t0, **{k: v for k, v in case.info().items() if k in ("nb_leaves", "coefficients", "coefficients_twice")}}), flush=True)
     dtype = case.np_dtype
     esize = np.dtype(dtype).itemsize
@@ -55,7 +54,7 @@ def main():
         case.vector_product(args.trans, 1.0, x, 0.0, y_ref, variant="openmp")
     else:
         case.matrix_product_row_major(args.trans, 1.0, x, 0.0, y_ref, mu, variant="openmp")
-    defaults = {k: capi.get_option(k) for k in ("block_rows", "piece_cols", "stage_bytes", "cseg_bytes", "ring_stages", "reduce_ring_stages", "evict_first", "m_ring_stages", "m_reduce_ring_stages", "mrhs_min", "fused_symmetric", "target_block_rows", "tail_split", "pdl")}
+    defaults = {k: capi.get_option(k) for k in ("block_rows", "piece_cols", "stage_bytes", "cseg_bytes", "ring_stages", "reduce_ring_stages", "evict_first", "m_ring_stages", "m_reduce_ring_stages", "mrhs_min", "fused_symmetric", "target_block_rows", "tail_split", "pdl", "reduce_blocks_per_cta", "sort_units", "m_b_ring_log2", "m_reduce_warps")}
     stream = torch.cuda.Stream()
     x_d = torch.from_numpy(x).cuda()
     tdt = torch.float64 if dtype == np.float64 else torch.complex128
