@@ -426,11 +426,11 @@ __device__ __forceinline__ void fused_unit(const Unit &un, const T *data, const 
 }
 
 // ---- REDUCE -------------------------------------------------------------------------------------------
-// A CTA handles `bpc` blocks one after the other (bpc = 1 for big blocks; 2 for the small source blocks of a row strip of a
-// distributed operator, ~150 KB each at 8 GPUs): the producer lane streams their stages back to back through the same
-// ring, so the bulk-copy pipeline is filled once per CTA and never drains at a block boundary; only the consumers meet
-// there (the x sub-vector is re-staged). Blocks are paired heaviest with lightest (order[c], order[n - 1 - c]).
-__device__ __forceinline__ int reduce_block_of(int cta, int bi, int n_blocks) { return bi == 0 ? cta : n_blocks - 1 - cta; }
+// A CTA handles `bpc` blocks one after the other (bpc = 1 for big blocks; several for the small source blocks of a row
+// strip of a distributed operator, ~150 KB each at 8 GPUs): the producer lane streams their stages back to back through
+// the same ring, so the bulk-copy pipeline is filled once per CTA and never drains at a block boundary; only the
+// consumers meet there (the x sub-vector is re-staged). CTA c takes order[c], order[c + G], order[c + 2 G], ... (G = grid):
+// the order is heaviest first, so every CTA gets a similar mix.
 
 template <typename T, bool CONJ>
 __global__ void __launch_bounds__(kThreads, sizeof(T) == 16 ? 3 : 0) reduce_kernel(KernelSide ks, PassArgs<T> a, int n_blocks, int bpc) {
@@ -450,9 +450,9 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 16 ? 3 : 0) reduce_kern
             const uint64_t policy = ks.evict_first ? l2_evict_first_policy() : 0;
             RingPos pos;
             for (int bi = 0; bi < bpc; bi++) {
-                const int slot_id = reduce_block_of(blockIdx.x, bi, n_blocks);
-                if (bi > 0 && slot_id <= static_cast<int>(blockIdx.x))
-                    break; // odd block count: the middle block belongs to its CTA once
+                const int slot_id = static_cast<int>(blockIdx.x + bi * gridDim.x);
+                if (slot_id >= n_blocks)
+                    break;
                 const BlockDesc bd = ks.blocks[ks.order[slot_id]];
                 if (bd.n_stages == 0)
                     continue;
@@ -476,8 +476,8 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 16 ? 3 : 0) reduce_kern
     RingPos pos;
     uint32_t ubase = warp;
     for (int bi = 0; bi < bpc; bi++) {
-        const int slot_id = reduce_block_of(blockIdx.x, bi, n_blocks);
-        if (bi > 0 && slot_id <= static_cast<int>(blockIdx.x))
+        const int slot_id = static_cast<int>(blockIdx.x + bi * gridDim.x);
+        if (slot_id >= n_blocks)
             break;
         const uint32_t block_id    = ks.order[slot_id];
         const BlockDesc bd         = ks.blocks[block_id];
@@ -904,9 +904,9 @@ cudaError_t launch_reduce(const SideDevice &side, const LaunchConfig &cfg, const
     // blocks per CTA: 2 when the side's blocks are small (a row strip of a distributed operator), else 1; option reduce_blocks_per_cta
     int bpc = cfg.reduce_blocks_per_cta;
     if (bpc <= 0)
-        bpc = (side.n_blocks >= 2 && side.stream_bytes / static_cast<uint64_t>(side.n_blocks) < (uint64_t(400) << 10)) ? 2 : 1;
-    if (bpc > 2)
-        bpc = 2;
+        bpc = (side.n_blocks >= 2 && side.stream_bytes / static_cast<uint64_t>(side.n_blocks) < (uint64_t(800) << 10)) ? 2 : 1;
+    if (bpc > 8)
+        bpc = 8;
     Kernels<T>::reduce(make_kernel_side(side, cfg, cfg.reduce_ring_stages), args, side.n_blocks, bpc, reduce_smem_bytes(cfg, sizeof(T)), stream);
     return cudaGetLastError();
 }
