@@ -901,10 +901,13 @@ template <typename T>
 cudaError_t launch_reduce(const SideDevice &side, const LaunchConfig &cfg, const PassArgs<T> &args, cudaStream_t stream) {
     if (side.n_blocks == 0)
         return cudaSuccess;
-    // blocks per CTA: 2 when the side's blocks are small (a row strip of a distributed operator), else 1; option reduce_blocks_per_cta
+    // blocks per CTA: several when the side's blocks are small (a row strip of a distributed operator), else 1; option
+    // reduce_blocks_per_cta. Measured on a 1/8 strip of N = 1e6 (142 KB per block): 1 -> 0.220 ms, 2 -> 0.208, 4 -> 0.204.
     int bpc = cfg.reduce_blocks_per_cta;
-    if (bpc <= 0)
-        bpc = (side.n_blocks >= 2 && side.stream_bytes / static_cast<uint64_t>(side.n_blocks) < (uint64_t(800) << 10)) ? 2 : 1;
+    if (bpc <= 0) {
+        const uint64_t avg = side.n_blocks > 0 ? side.stream_bytes / static_cast<uint64_t>(side.n_blocks) : 0;
+        bpc                = side.n_blocks < 2 ? 1 : (avg < (uint64_t(256) << 10) ? 4 : (avg < (uint64_t(800) << 10) ? 2 : 1));
+    }
     if (bpc > 8)
         bpc = 8;
     Kernels<T>::reduce(make_kernel_side(side, cfg, cfg.reduce_ring_stages), args, side.n_blocks, bpc, reduce_smem_bytes(cfg, sizeof(T)), stream);
