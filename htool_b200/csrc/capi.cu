@@ -29,7 +29,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 namespace {
 std::mutex g_option_mutex;
 std::map<std::string, int64_t> g_options = {
-    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 4096}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 4}, {"m_b_ring_log2", 2}, {"m_reduce_ring_stages", 4}, {"mrhs_min", 0}, {"pack_generate_dense", 0}, {"sort_units", 1}, {"reduce_blocks_per_cta", 0}, {"m_reduce_warps", 24}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}};
+    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 4096}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 0}, {"m_b_ring_log2", 2}, {"m_reduce_ring_stages", 0}, {"mrhs_min", 0}, {"pack_generate_dense", 0}, {"sort_units", 1}, {"reduce_blocks_per_cta", 0}, {"m_reduce_warps", 24}, {"m_pad", 4}, {"m_stage_input", 1}, {"m_small_runs", 1}, {"m_reduce_split", 1}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}};
 
 int64_t option(const char *key) {
     std::lock_guard<std::mutex> lock(g_option_mutex);
@@ -364,13 +364,36 @@ static int run_product_m(htb_operator *h, char trans, const double *alpha, const
         double *M1 = static_cast<double *>(h->d_mscratch);
         double *M2 = M1 + h->mscratch_elems * static_cast<size_t>(h->mscratch_vs + 8); // (allocated with the padded stride: any vsp <= vs + 8 fits)
         MArgs base;
-        base.ld_in = mu * W, base.ld_out = mu * W, base.col0 = col0 * W, base.mc = mc, base.vs = vs, base.vsp = vs, base.cplx = cplx ? 1 : 0; // vsp: vector stride of the scratch = row stride of APPLY_M's B ring
+        // vsp: vector stride of the scratch = row stride of APPLY_M's B ring and of REDUCE_M's X block; vs + 4 keeps the DMMA
+        // fragment loads free of bank conflicts (mkernels.cuh)
+        const int pad = h->launch_cfg.m_pad;
+        base.ld_in = mu * W, base.ld_out = mu * W, base.col0 = col0 * W, base.col0_in = col0 * W, base.mc = mc, base.vs = vs, base.vsp = vs + pad, base.cplx = cplx ? 1 : 0;
+        base.small_runs = option("m_small_runs") != 0, base.reduce_split = static_cast<int>(std::min<int64_t>(8, std::max<int64_t>(1, option("m_reduce_split"))));
+        // the group's columns of the input, copied once into rows one B-ring row apart (zero padded): the input rows of a dense
+        // leaf then reach the B ring with one bulk copy whatever mu is, and every row is 16 B aligned
+        const long long in_rows_all = trans == 'N' ? h->nb_cols : h->nb_rows;
+        const double *in_g          = in;
+        if (option("m_stage_input") != 0 && (base.ld_in != base.vsp || col0 != 0)) {
+            const size_t need = static_cast<size_t>(std::max<long long>(1, in_rows_all)) * base.vsp * sizeof(double);
+            if (need > h->mstage_cap) {
+                if (h->d_mstage)
+                    cudaFree(h->d_mstage);
+                h->d_mstage = nullptr, h->mstage_cap = 0;
+                cudaError_t e = cudaMalloc(&h->d_mstage, need);
+                if (e != cudaSuccess)
+                    return cuda_fail(e, "cudaMalloc(multi-RHS input staging)");
+                h->mstage_cap = need;
+            }
+            if ((rc = timed(HTB_PASS_OTHER, [&]() { return launch_stage_group(in, in_rows_all, base.ld_in, base.col0_in, mc, static_cast<double *>(h->d_mstage), base.vsp, st); }, "stage_group")) != HTB_OK)
+                return rc;
+            in_g = static_cast<const double *>(h->d_mstage), base.ld_in = base.vsp, base.col0_in = 0;
+        }
         base.alpha = alpha[0], base.alpha_im = cplx ? alpha[1] : 0.;
         // ps: side streamed by REDUCE_M (producers), cs: side streamed by APPLY_M (consumers)
         auto direction = [&](int cs, double *M, int in_shift, long long in_rows, int out_shift, long long out_rows, double b_re, double b_im, int twice_only, int conj) -> int {
             const int ps = 1 - cs;
             MArgs r      = base;
-            r.in = in, r.in_rows = in_rows, r.in_shift = in_shift, r.mscratch = M, r.twice_only = twice_only, r.conj = conj;
+            r.in = in_g, r.in_rows = in_rows, r.in_shift = in_shift, r.mscratch = M, r.twice_only = twice_only, r.conj = conj;
             int rc2;
             if (h->side[ps].stream && (rc2 = timed(HTB_PASS_REDUCE, [&]() { return launch_reduce_m(h->side[ps], h->launch_cfg, r, st); }, "reduce_m")) != HTB_OK)
                 return rc2;
@@ -761,8 +784,23 @@ static int create_impl(const htb_hmatrix_desc *desc, const htb_generator_desc *g
     h->launch_cfg.m_reduce_warps       = static_cast<int>(option("m_reduce_warps"));
     if (h->launch_cfg.m_b_ring_log2 < 1 || h->launch_cfg.m_b_ring_log2 > 3)
         return fail(HTB_ERR_INVALID, "m_b_ring_log2 must be in [1, 3]");
-    if (h->launch_cfg.m_ring_stages < 2 || h->launch_cfg.m_ring_stages > 8 || h->launch_cfg.m_reduce_ring_stages < 2 || h->launch_cfg.m_reduce_ring_stages > 8)
-        return fail(HTB_ERR_INVALID, "m_ring_stages / m_reduce_ring_stages must be in [2, 8]");
+    // a ring slot of the multi-RHS kernels = stage + the largest aux record of THIS store; ring depths 0 = as deep as the
+    // shared memory of an SM allows (a slot is idle while it is refilled: bytes in flight are what keeps the DMMAs fed)
+    h->launch_cfg.m_aux_bytes = static_cast<int>((std::max<uint32_t>(16u, std::max(pk->side[0].aux_max_bytes, pk->side[1].aux_max_bytes)) + 127u) & ~127u);
+    h->launch_cfg.m_pad = static_cast<int>(std::min<int64_t>(8, std::max<int64_t>(0, option("m_pad")))) & ~1;
+    for (int sd = 0; sd < 2; sd++)
+        for (const BlockDesc &bd : pk->side[sd].blocks)
+            h->launch_cfg.m_x_rows = std::max(h->launch_cfg.m_x_rows, static_cast<int>(bd.nrows));
+    for (int *depth : {&h->launch_cfg.m_ring_stages, &h->launch_cfg.m_reduce_ring_stages}) {
+        if (*depth != 0 && (*depth < 2 || *depth > 8))
+            return fail(HTB_ERR_INVALID, "m_ring_stages / m_reduce_ring_stages must be 0 (automatic) or in [2, 8]");
+        if (*depth == 0) {
+            const bool red = depth == &h->launch_cfg.m_reduce_ring_stages;
+            for (*depth = 8; *depth > 2; --*depth)
+                if ((red ? reduce_m_smem_bytes(h->launch_cfg, 64, h->esize) : apply_m_smem_bytes(h->launch_cfg)) <= static_cast<size_t>(prop.sharedMemPerBlockOptin))
+                    break;
+        }
+    }
     HTB_CUDA(configure_kernels(h->launch_cfg));
     h->m_path_ok = std::max(reduce_m_smem_bytes(h->launch_cfg, 64, h->esize), apply_m_smem_bytes(h->launch_cfg)) <= static_cast<size_t>(prop.sharedMemPerBlockOptin);
     if (h->m_path_ok)
@@ -822,7 +860,7 @@ int htb_destroy(htb_handle h) {
         cudaStreamSynchronize(h->own_stream);
     for (void *p : h->owned)
         cudaFree(p);
-    for (void *p : {h->d_mscratch, h->d_scratch, h->d_in, h->d_out, h->d_perm[0], h->d_perm[1], h->d_work_in, h->d_work_out, h->d_krylov})
+    for (void *p : {h->d_mscratch, h->d_mstage, h->d_scratch, h->d_in, h->d_out, h->d_perm[0], h->d_perm[1], h->d_work_in, h->d_work_out, h->d_krylov})
         if (p)
             cudaFree(p);
     for (void *p : {h->h_in, h->h_out, h->h_krylov})

@@ -45,6 +45,8 @@ struct htb_operator {
     uint64_t scratch_elems = 0;
     // multi-RHS scratch ([TF | PARTM[0] | PARTM[1]] x vector stride), allocated at the first multi-RHS product
     void *d_mscratch        = nullptr;
+    void *d_mstage          = nullptr; // multi-RHS: the current column group of the input, rows padded to the B-ring stride
+    size_t mstage_cap       = 0;
     uint64_t mscratch_elems = 0; // vectors per copy
     int mscratch_vs         = 0; // vector stride it was allocated for
     bool needs_second_copy  = false;

@@ -41,6 +41,10 @@ struct LaunchConfig {
     int m_ring_stages        = 4; // APPLY_M ring depth (slot = stage + aux record)
     int m_reduce_ring_stages = 4; // REDUCE_M ring depth (1 CTA / SM: the X block takes 76 KiB)
     int m_reduce_warps       = 24; // REDUCE_M consumer warps (4 .. 24)
+    int m_aux_bytes          = 0; // aux part of a ring slot of the multi-RHS kernels: the largest aux record of the store, rounded up to 128
+                                  // (0: the worst case a stage can hold, aux_slot_bytes(cseg_bytes))
+    int m_pad                = 4; // vector stride of the multi-RHS scratch / B ring / X block = vs + m_pad (mkernels.cuh)
+    int m_x_rows             = 0; // tallest block of the store: rows of REDUCE_M's X block in shared memory
     int m_b_ring_log2        = 2; // APPLY_M: the ring of B-row chunks (32 rows each) holds 2^this chunks
     int reduce_blocks_per_cta = 0; // REDUCE: blocks handled by one CTA through one ring (0 = automatic: 2 for small blocks, else 1)
     int evict_first = 1; // L2 evict_first hint on the coefficient stream

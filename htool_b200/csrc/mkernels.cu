@@ -43,7 +43,7 @@ constexpr int kApplyWarps  = 16; // APPLY_M: 8 column tiles x 2 row-tile paritie
 constexpr int kReduceWarpsMax = 24; // REDUCE_M: jobs (8 columns of a run) dealt round-robin over the consumer warps (option m_reduce_warps)
 
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
 // ---- mbarrier / bulk copy (same protocol as kernels.cu) --------------------------------------------------------------
@@ -131,6 +131,24 @@ __device__ __forceinline__ void init_barriers(int ring, uint64_t *full, uint64_t
     }
 }
 
+// One REDUCE_M job: acc[mt] += X-fragment(mt) x P-fragment over the k-steps (4 rows each) of a run, column tiles
+// mt < mn of the right-hand sides (FULL: all 8, no predicates). b = P[i][col], zero outside the run: rows past the run meet
+// b == 0. Plain loop on purpose: two resident warps per scheduler already keep the DMMA pipe full with the loads in front
+// of each DMMA, and a software-pipelined variant (fragments of the next k-step in their own registers) measured SLOWER
+// once the pipe is shared (tools/dmma_probe.cu: 27 vs 35 TFLOP/s at 8+ warps per SM: the register moves cost issue slots).
+template <bool FULL>
+__device__ __forceinline__ void reduce_job(double (&acc)[8][2], const double *Pc, const double *xj, int XS, uint32_t h, int tig, bool cv, int mn) {
+    for (uint32_t i0 = 0; i0 < h; i0 += 4) {
+        const uint32_t i = i0 + tig;
+        const double b   = (cv && i < h) ? Pc[i < h ? i : h - 1u] : 0.;
+        const double *xr = xj + i0 * XS;
+#pragma unroll
+        for (int mt = 0; mt < 8; mt++)
+            if (FULL || mt < mn)
+                dmma(acc[mt], xr[8 * mt], b); // X[row0 + i0 + tig][8 (m0 + mt) + g]
+    }
+}
+
 // ---- REDUCE_M -------------------------------------------------------------------------------------------------------
 // smem: [ring: slot = stage | aux] [Xs ((real rows of a block + 4) x VSP)] [barriers]
 template <bool CPLX>
@@ -142,7 +160,8 @@ __global__ void __launch_bounds__((kReduceWarpsMax + 1) * 32) reduce_m_kernel(MS
     if (n_my_stages == 0)
         return;
     const uint32_t slot_bytes = ks.stage_bytes + ks.aux_bytes;
-    const int XS              = a.vs + 8; // row stride of the X block in shared memory: conflict-free A fragments
+    const int XS              = a.vsp; // row stride of the X block in shared memory = 4 (mod 8): conflict-free A fragments (64-bit
+                                       // loads are served per half warp: tig * XS + g, g < 4, must hit 16 different bank pairs)
     const int RB              = ks.block_rows << CS; // real rows of a block
     unsigned char *ring       = smem_raw;
     double *Xs                = reinterpret_cast<double *>(smem_raw + static_cast<size_t>(ks.ring_stages) * slot_bytes);
@@ -167,7 +186,7 @@ __global__ void __launch_bounds__((kReduceWarpsMax + 1) * 32) reduce_m_kernel(MS
         const long long gr = static_cast<long long>(bd.row_start) + i + a.in_shift;
         double v           = 0.;
         if (i < bd.nrows && c < a.mc && gr >= 0 && gr < a.in_rows) {
-            const double *row = a.in + gr * a.ld_in + a.col0;
+            const double *row = a.in + gr * a.ld_in + a.col0_in;
             if (!CPLX || !(r & 1))
                 v = row[c];
             else { // row 2i+1 of the embedding: i * X[i][.] = (-im, re); conjugated panel: -i * X[i][.] = (im, -re)
@@ -200,12 +219,21 @@ __global__ void __launch_bounds__((kReduceWarpsMax + 1) * 32) reduce_m_kernel(MS
             const uint32_t ld = CPLX ? 2u * hc : unit_ld(hc, sizeof(double)); // real leading dimension
             const double *P   = data + (static_cast<size_t>(rd.data_off) << CS);
             const double *xrow = Xs + ((static_cast<uint32_t>(rd.row0) << CS) + tig) * XS + g;
-            // my tiles of this run: t = t0, t0 + W, ...
-            uint32_t t0 = static_cast<uint32_t>(warp + kReduceWarps) - jmod;
-            if (t0 >= static_cast<uint32_t>(kReduceWarps))
-                t0 -= kReduceWarps;
-            jmod = (jmod + ntiles) % static_cast<uint32_t>(kReduceWarps);
-            for (uint32_t t = t0; t < ntiles; t += kReduceWarps) {
+            // jobs of this run: (tile of 8 columns) x (one of S groups of column tiles of the right-hand sides). S > 1 for tall
+            // runs: a stage of a 122-row panel holds ~25 columns = 3 tiles, so with one job per tile a 4-stage ring feeds 12 of
+            // the 24 warps; splitting the right-hand sides keeps every warp busy (the panel fragment is re-read from shared
+            // memory by the S jobs, the DMMAs are the same). My jobs: jb = jb0, jb0 + W, ...; jb = S t + part.
+            const uint32_t S     = (h >= 64u && a.reduce_split > 1 && MT >= a.reduce_split) ? static_cast<uint32_t>(a.reduce_split) : 1u;
+            const uint32_t njobs = ntiles * S;
+            const int mper       = (MT + static_cast<int>(S) - 1) / static_cast<int>(S); // column tiles per job
+            uint32_t jb0 = static_cast<uint32_t>(warp + kReduceWarps) - jmod;
+            if (jb0 >= static_cast<uint32_t>(kReduceWarps))
+                jb0 -= kReduceWarps;
+            jmod = (jmod + njobs) % static_cast<uint32_t>(kReduceWarps);
+            for (uint32_t jb = jb0; jb < njobs; jb += kReduceWarps) {
+                const uint32_t t = jb / S;
+                const int m0     = static_cast<int>(jb - t * S) * mper;
+                const int mn     = MT - m0 < mper ? MT - m0 : mper; // column tiles m0 .. m0 + mn - 1
                 double acc[8][2];
 #pragma unroll
                 for (int mt = 0; mt < 8; mt++)
@@ -213,24 +241,20 @@ __global__ void __launch_bounds__((kReduceWarpsMax + 1) * 32) reduce_m_kernel(MS
                 const uint32_t col  = 8u * t + g;
                 const bool cv       = col < K;
                 const double *Pc    = P + static_cast<size_t>(cv ? col : K - 1u) * ld;
-                for (uint32_t i0 = 0; i0 < h; i0 += 4) {
-                    const uint32_t i = i0 + tig;
-                    const double b   = (cv && i < h) ? Pc[i < h ? i : h - 1u] : 0.; // P[i][col], zero outside the run
-                    const double *xr = xrow + i0 * XS;
-#pragma unroll
-                    for (int mt = 0; mt < 8; mt++)
-                        if (mt < MT)
-                            dmma(acc[mt], xr[8 * mt], b); // X[row0 + i0 + tig][8 mt + g]; rows past the run meet b == 0
-                }
-                // D[c = 8 mt + g][k = 8 t + 2 tig + j] -> scratch vector named by the column table
+                const double *xj    = xrow + 8 * m0;
+                if (mn == 8)
+                    reduce_job<true>(acc, Pc, xj, XS, h, tig, cv, 8);
+                else
+                    reduce_job<false>(acc, Pc, xj, XS, h, tig, cv, mn);
+                // D[c = 8 (m0 + mt) + g][k = 8 t + 2 tig + j] -> scratch vector named by the column table
 #pragma unroll
                 for (int j = 0; j < 2; j++) {
                     const uint32_t k = 8u * t + 2u * tig + j;
                     if (k < K) {
-                        double *T = a.mscratch + static_cast<size_t>(cols[rd.col0 + k]) * a.vsp + g;
+                        double *T = a.mscratch + static_cast<size_t>(cols[rd.col0 + k]) * a.vsp + g + 8 * m0;
 #pragma unroll
                         for (int mt = 0; mt < 8; mt++)
-                            if (mt < MT)
+                            if (mt < mn)
                                 T[8 * mt] = acc[mt][j];
                     }
                 }
@@ -277,8 +301,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { a
 // never waits for data.
 template <bool CPLX>
 __device__ __forceinline__ void produce_b(const MSide &ks, const BlockDesc &bd, const MArgs &a, unsigned char *ring, uint32_t slot_bytes, uint64_t *full, uint64_t *empty, const BRing &br, uint32_t n_my_stages, int lane) {
-    const bool in16   = (a.ld_in % 2 == 0) && (a.col0 % 2 == 0) && (a.mc % 2 == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 15u) == 0); // rows of the input matrix are 16 B aligned
-    const bool in_seq = in16 && a.ld_in == a.vsp && a.mc == a.vs && a.vs == a.vsp;                                                        // ... and consecutive rows are one row of the chunk apart
+    const bool in16   = (a.ld_in % 2 == 0) && (a.col0_in % 2 == 0) && (a.mc % 2 == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 15u) == 0); // rows of the input matrix are 16 B aligned
+    const bool in_seq = in16 && a.ld_in == a.vsp && a.col0_in == 0;                                                                        // ... and consecutive rows are one row of the chunk apart (the staged group)
     const uint32_t row_bytes = static_cast<uint32_t>(a.vsp) * 8u;
     RingPos pos;
     uint32_t bpos    = 0;  // position in the B stream
@@ -333,7 +357,7 @@ __device__ __forceinline__ void produce_b(const MSide &ks, const BlockDesc &bd, 
                         if (row < 0 || row >= a.in_rows)
                             mode = 2;
                         else {
-                            p    = a.in + row * a.ld_in + a.col0;
+                            p    = a.in + row * a.ld_in + a.col0_in;
                             mode = in16 ? 0u : 1u;
                             key  = in_seq ? src : 0xffffffffu;
                         }
@@ -379,6 +403,127 @@ __device__ __forceinline__ void produce_b(const MSide &ks, const BlockDesc &bd, 
         publish(); // end of the stage: the consumers must not wait for the next stage to see its last chunk
         if (lane == 0)
             mbar_arrive(smem_u32(&empty[pos.slot])); // the column tables of this stage are no longer needed
+    }
+}
+
+// A consumer warp enters chunk `chunk` of the B ring (releasing the one it was reading).
+__device__ __forceinline__ void enter_chunk(const BRing &br, long long &cur, long long chunk, int lane) {
+    if (chunk != cur) {
+        if (cur >= 0) {
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(smem_u32(&br.empty[cur & br.mask]));
+        }
+        mbar_wait(smem_u32(&br.full[chunk & br.mask]), static_cast<uint32_t>((chunk >> br.log2n) & 1));
+        cur = chunk;
+    }
+}
+
+template <int NT, int NJ, int J0>
+__device__ __forceinline__ void fold_tiles(double (&acc)[NJ][2], const double (&t)[NT][2]) {
+#pragma unroll
+    for (int jj = 0; jj < NT; jj++)
+        if (J0 + jj < NJ) {
+            acc[J0 + jj][0] += t[jj][0];
+            acc[J0 + jj][1] += t[jj][1];
+        }
+}
+
+// A run that meets NT <= 5 consecutive row tiles jlo .. jlo + NT - 1 of the warp's class (every run but the tall panels: the
+// near field and the low-rank panels of the small clusters). The run is contracted into NT private accumulators with NO
+// row predicates: a DMMA output row depends on the same row of A only, so a lane whose row lies outside the run
+// may read whatever follows / precedes its panel in the ring slot (tile 0: clamped to row 0) — it pollutes rows of t that
+// the fold below drops. The fold into the block accumulators (compile-time indices) happens once per run instead of a
+// predicated walk over all NJ tiles at every k-step (legacy path 3: 20 - 35 instructions per DMMA; here 3 - 6). Columns
+// >= mc of the B rows are not masked either: they only reach columns of C that the epilogue never stores.
+template <bool CPLX, int NT, int PAR, int NJ>
+__device__ __forceinline__ void run_tiles(const BRing &br, long long &cur, int lane, int tig, uint32_t run_pos, uint32_t Kr, const double *Prun, size_t pstep, size_t bstep,
+                                          int vsp, int cBl, double bs, int rr0, int h, int jlo, double (&acc)[NJ][2]) {
+    constexpr int CS = CPLX ? 1 : 0;
+    constexpr int TS = (8 * PAR) << CS; // doubles between my rows of consecutive tiles of my class
+    double t[NT][2], u[2] = {0., 0.};
+#pragma unroll
+    for (int jj = 0; jj < NT; jj++)
+        t[jj][0] = t[jj][1] = 0.;
+    const double *P0 = Prun + (static_cast<size_t>(rr0 > 0 ? rr0 : 0) << CS); // tile 0 (clamped)
+    const double *PN = Prun + (static_cast<ptrdiff_t>(rr0) * (1 << CS));       // tiles >= 1 at PN[TS jj]: rr0 + 8 PAR jj > 0
+    for (uint32_t k0 = 0; k0 < Kr;) {
+        const uint32_t pos0 = run_pos + (k0 >> CS);
+        const long long chunk = static_cast<long long>(pos0 >> 5);
+        enter_chunk(br, cur, chunk, lane);
+        uint32_t kend = k0 + ((32u - (pos0 & 31u)) << CS); // first contraction index of the next chunk
+        if (kend > Kr)
+            kend = Kr;
+        const uint32_t kfull = (kend == Kr) ? (Kr & ~3u) : kend; // k-steps starting below kfull have four valid contraction indices
+        const double *Bl = reinterpret_cast<const double *>(br.base + static_cast<size_t>(chunk & br.mask) * br.chunk_bytes) + static_cast<size_t>((pos0 & 31u) + (static_cast<uint32_t>(tig) >> CS)) * vsp + cBl;
+        const double *A0 = P0 + static_cast<size_t>(k0 >> 2) * pstep;
+        const double *AN = PN + static_cast<ptrdiff_t>(k0 >> 2) * static_cast<ptrdiff_t>(pstep);
+        uint32_t k = k0;
+        if (NT == 1) { // one tile: two accumulation chains over alternating k-steps hide the DMMA latency
+            for (; k + 8 <= kfull; k += 8) {
+                dmma(t[0], A0[0], CPLX ? bs * Bl[0] : Bl[0]);
+                dmma(u, A0[pstep], CPLX ? bs * Bl[bstep] : Bl[bstep]);
+                Bl += 2 * bstep;
+                A0 += 2 * pstep;
+            }
+            if (k < kfull) {
+                dmma(t[0], A0[0], CPLX ? bs * Bl[0] : Bl[0]);
+                Bl += bstep;
+                A0 += pstep;
+                k += 4;
+            }
+            if (k < kend) { // last, partial k-step of the run: contraction indices >= Kr meet zeros on both sides
+                const bool kv = k + tig < Kr;
+                dmma(u, kv ? A0[0] : 0., kv ? bs * Bl[0] : 0.);
+            }
+        } else {
+#pragma unroll 2
+            for (; k < kfull; k += 4) {
+                const double b = CPLX ? bs * Bl[0] : Bl[0];
+                double av[NT]; // all the fragments of the k-step are in flight before its first DMMA
+                av[0] = A0[0];
+#pragma unroll
+                for (int jj = 1; jj < NT; jj++)
+                    av[jj] = AN[TS * jj];
+#pragma unroll
+                for (int jj = 0; jj < NT; jj++)
+                    dmma(t[jj], av[jj], b);
+                Bl += bstep;
+                A0 += pstep;
+                AN += pstep;
+            }
+            if (k < kend) {
+                const bool kv  = k + tig < Kr;
+                const double b = kv ? bs * Bl[0] : 0.;
+                dmma(t[0], kv ? A0[0] : 0., b);
+#pragma unroll
+                for (int jj = 1; jj < NT; jj++)
+                    dmma(t[jj], kv ? AN[TS * jj] : 0., b);
+            }
+        }
+        k0 = kend;
+    }
+    if (NT == 1) {
+        t[0][0] += u[0];
+        t[0][1] += u[1];
+    }
+#pragma unroll
+    for (int jj = 0; jj < NT; jj++) {
+        const int rr  = rr0 + 8 * PAR * jj;
+        const bool rv = rr >= 0 && rr < h;
+        t[jj][0] = rv ? t[jj][0] : 0.;
+        t[jj][1] = rv ? t[jj][1] : 0.;
+    }
+    // acc[jlo + jj] += t[jj] with compile-time indices (one case per jlo; a data-dependent index would push acc to local memory)
+    switch (jlo) {
+#define HTB_FOLD(J0)                                                                                                                                                 \
+    case J0:                                                                                                                                                         \
+        if constexpr (J0 < NJ)                                                                                                                                       \
+            fold_tiles<NT, NJ, J0>(acc, t);                                                                                                                         \
+        break;
+        HTB_FOLD(0) HTB_FOLD(1) HTB_FOLD(2) HTB_FOLD(3) HTB_FOLD(4) HTB_FOLD(5) HTB_FOLD(6) HTB_FOLD(7)
+#undef HTB_FOLD
+    default: break;
     }
 }
 
@@ -470,7 +615,23 @@ __global__ void __launch_bounds__((kApplyWarps + 2) * 32, 1) apply_m_kernel(MSid
             const size_t pstep = static_cast<size_t>(4 >> CS) * ld;
             // this lane's panel column (contraction index tig) at my row of tile 0 — dereferenced only where the row exists
             const double *Prun = data + (static_cast<size_t>(rd.data_off) << CS) + static_cast<size_t>(tig >> CS) * ld + (CPLX ? (tig & 1) : 0);
-            const int path     = !mine ? 0 : (jlo == jhi ? 1 : ((row0 == 0 && h == bd.nrows && jlo == 0 && jhi == NJ - 1) ? 2 : 3));
+            const bool tall    = row0 == 0 && h == bd.nrows && jlo == 0 && jhi == NJ - 1;
+            if (mine && !tall && a.small_runs && jhi - jlo < 5) {
+                const int rr0 = my_row0 + 8 * PAR * jlo - row0;
+#define HTB_RUN_TILES(N)                                                                                                                                              \
+    if constexpr (N <= NJ)                                                                                                                                           \
+        run_tiles<CPLX, N, PAR, NJ>(br, cur, lane, tig, run_pos, Kr, Prun, pstep, bstep, a.vsp, cBl, bs, rr0, h, jlo, acc);
+                switch (jhi - jlo) {
+                case 0: HTB_RUN_TILES(1) break;
+                case 1: HTB_RUN_TILES(2) break;
+                case 2: HTB_RUN_TILES(3) break;
+                case 3: HTB_RUN_TILES(4) break;
+                default: HTB_RUN_TILES(5) break;
+                }
+#undef HTB_RUN_TILES
+                continue;
+            }
+            const int path     = !mine ? 0 : (jlo == jhi ? 1 : (tall ? 2 : 3));
             // the k-steps of the run, chunk by chunk of the B ring
             for (uint32_t k0 = 0; k0 < Kr;) {
                 const uint32_t pos0   = run_pos + (k0 >> CS);
@@ -531,10 +692,14 @@ __global__ void __launch_bounds__((kApplyWarps + 2) * 32, 1) apply_m_kernel(MSid
                         const double *Pa = Pl + (static_cast<size_t>(my_row0) << CS);
 #pragma unroll 2
                         for (; k < kfull; k += 4) {
-                            const double b = c_valid ? bs * Bl[0] : 0.;
+                            const double b = CPLX ? bs * Bl[0] : Bl[0]; // (columns >= mc: garbage that only reaches columns of C never stored)
+                            double av[NJ]; // all the fragments of the k-step are in flight before its first DMMA
 #pragma unroll
                             for (int j = 0; j < NJ; j++)
-                                dmma(acc[j], Pa[static_cast<size_t>(8 * PAR * j) << CS], b);
+                                av[j] = Pa[static_cast<size_t>(8 * PAR * j) << CS];
+#pragma unroll
+                            for (int j = 0; j < NJ; j++)
+                                dmma(acc[j], av[j], b);
                             Bl += bstep;
                             Pa += pstep;
                         }
@@ -665,19 +830,30 @@ __global__ void combine_m_kernel(const CombineEntry *entries, int n, double *msc
     }
 }
 
+__global__ void stage_group_kernel(const double *__restrict__ in, long long rows, int ld_in, int col0, int mc, double *__restrict__ dst, int vsp) {
+    const long long total = rows * vsp;
+    for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = idx / vsp;
+        const int c       = static_cast<int>(idx - r * vsp);
+        dst[idx]          = c < mc ? in[r * ld_in + col0 + c] : 0.;
+    }
+}
+
+inline size_t aux_part(const LaunchConfig &cfg) { return cfg.m_aux_bytes > 0 ? static_cast<size_t>(cfg.m_aux_bytes) : aux_slot_bytes(static_cast<uint32_t>(cfg.cseg_bytes)); }
+
 inline MSide make_mside(const SideDevice &s, const LaunchConfig &cfg, int ring, bool apply_role) {
-    return MSide{s.blocks, s.stages, s.order, s.stream, apply_role ? s.aux_apply : s.aux_reduce, s.munits, cfg.block_rows, cfg.stage_bytes, static_cast<int>(aux_slot_bytes(static_cast<uint32_t>(cfg.cseg_bytes))), ring};
+    return MSide{s.blocks, s.stages, s.order, s.stream, apply_role ? s.aux_apply : s.aux_reduce, s.munits, cfg.m_x_rows > 0 ? cfg.m_x_rows : cfg.block_rows, cfg.stage_bytes, static_cast<int>(aux_part(cfg)), ring};
 }
 
 } // namespace
 
 size_t reduce_m_smem_bytes(const LaunchConfig &cfg, int vs, size_t esize) {
-    const size_t slot = static_cast<size_t>(cfg.stage_bytes) + aux_slot_bytes(static_cast<uint32_t>(cfg.cseg_bytes));
-    const size_t rb   = static_cast<size_t>(cfg.block_rows) * (esize / 8);
-    return static_cast<size_t>(cfg.m_reduce_ring_stages) * slot + sizeof(double) * (rb + 4) * (vs + 8) + 16 * static_cast<size_t>(cfg.m_reduce_ring_stages);
+    const size_t slot = static_cast<size_t>(cfg.stage_bytes) + aux_part(cfg);
+    const size_t rb   = static_cast<size_t>(cfg.m_x_rows > 0 ? cfg.m_x_rows : cfg.block_rows) * (esize / 8);
+    return static_cast<size_t>(cfg.m_reduce_ring_stages) * slot + sizeof(double) * (rb + 4) * (vs + cfg.m_pad) + 16 * static_cast<size_t>(cfg.m_reduce_ring_stages);
 }
 size_t apply_m_smem_bytes(const LaunchConfig &cfg) {
-    const size_t slot = static_cast<size_t>(cfg.stage_bytes) + aux_slot_bytes(static_cast<uint32_t>(cfg.cseg_bytes));
+    const size_t slot = static_cast<size_t>(cfg.stage_bytes) + aux_part(cfg);
     const size_t nb   = size_t(1) << cfg.m_b_ring_log2;
     return static_cast<size_t>(cfg.m_ring_stages) * slot + nb * kBChunk * 72 * 8 + 16 * static_cast<size_t>(cfg.m_ring_stages) + 16 * nb;
 }
@@ -750,6 +926,15 @@ cudaError_t launch_apply_m(const SideDevice &side, const LaunchConfig &cfg, cons
             HTB_APPLY_M(false, 1);
     }
 #undef HTB_APPLY_M
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stage_group(const double *in, long long rows, int ld_in, int col0, int mc, double *dst, int vsp, cudaStream_t stream) {
+    if (rows <= 0)
+        return cudaSuccess;
+    const long long total = rows * vsp;
+    const unsigned grid   = static_cast<unsigned>(std::min<long long>((total + 255) / 256, 148LL * 32));
+    stage_group_kernel<<<grid, 256, 0, stream>>>(in, rows, ld_in, col0, mc, dst, vsp);
     return cudaGetLastError();
 }
 

@@ -18,9 +18,12 @@ struct MArgs {
     long long out_rows = 0;
     int out_shift     = 0;
     int ld_out        = 0;
-    int col0 = 0, mc = 0; // column group
+    int col0 = 0, mc = 0; // column group (col0: first real column of the group in `out`)
+    int col0_in       = 0; // first real column of the group in `in` (0 when `in` is the padded staging copy of the group)
     int vs            = 0; // mc rounded up to a multiple of 8
-    int vsp           = 0; // vector stride of the scratch (= vs) and row stride of the B ring of APPLY_M: consecutive vectors of a piece are consecutive rows
+    int vsp           = 0; // vector stride of the scratch, row stride of the B ring of APPLY_M and of the X block of REDUCE_M: vs + 4, i.e.
+                           // = 4 (mod 8) doubles: the four rows k0 + tig of a DMMA fragment fall into four different groups of banks
+                           // (a stride = 0 (mod 16) doubles puts them on the SAME banks: 4-way conflicts on every fragment load)
     double *mscratch  = nullptr; // one multi-RHS scratch copy: [TF | PARTM[0] | PARTM[1]] x vsp
     double alpha = 0., beta = 0.;
     double alpha_im = 0., beta_im = 0.; // complex<double> only
@@ -28,12 +31,17 @@ struct MArgs {
     int twice_only   = 0;
     int cplx         = 0; // coefficients are complex<double>
     int conj         = 0; // conjugate the coefficients (trans == 'C', Hermitian second application)
+    int small_runs   = 1; // APPLY_M: run-private accumulators for runs of <= 5 row tiles per warp (0: the predicated per-tile walk)
+    int reduce_split = 1; // REDUCE_M: jobs per 8-column tile of a tall run (groups of column tiles of the right-hand sides)
 };
 
 cudaError_t launch_reduce_m(const SideDevice &side, const LaunchConfig &cfg, const MArgs &args, cudaStream_t stream);
 cudaError_t launch_apply_m(const SideDevice &side, const LaunchConfig &cfg, const MArgs &args, cudaStream_t stream);
 // Sums the partials of the direction whose consumer is `side` into TF.
 cudaError_t launch_combine_m(const SideDevice &side, double *mscratch, int vs, int vsp, int twice_only, cudaStream_t stream);
+// Copies real columns [col0, col0 + mc) of the row-major matrix `in` (rows x ld_in) into dst (rows x vsp), zero padded: the
+// staged group. Rows of the staged copy are one B-ring row apart, so the input rows of a dense leaf land with ONE bulk copy.
+cudaError_t launch_stage_group(const double *in, long long rows, int ld_in, int col0, int mc, double *dst, int vsp, cudaStream_t stream);
 size_t reduce_m_smem_bytes(const LaunchConfig &cfg, int vs, size_t esize);
 size_t apply_m_smem_bytes(const LaunchConfig &cfg);
 cudaError_t configure_mkernels(const LaunchConfig &cfg, size_t esize);

@@ -622,6 +622,7 @@ void Packer::make_mtables() {
                 sd.aux_off16  = static_cast<uint32_t>(off / 16u);
                 sd.flags      = static_cast<uint16_t>((sd.flags & 1u) | ((aux_len[b][q] / 16u) << 1));
                 off += aux_len[b][q];
+                side[s].aux_max_bytes = std::max(side[s].aux_max_bytes, aux_len[b][q]);
             }
             side[s].dense_tasks.insert(side[s].dense_tasks.end(), tasks[b].begin(), tasks[b].end());
             at += aux_r[b].size();

@@ -230,6 +230,7 @@ struct SideLayout {
     std::vector<CombineEntry> combine_m; // src = PARTM offset, dst_first = TF offset, n_dst unused
     uint64_t partm_base = 0, partm_elems = 0; // in vectors, inside the multi-RHS scratch [TF | PARTM[0] | PARTM[1]]
     std::vector<unsigned char> aux_reduce, aux_apply; // per-stage aux records (runs + column tables), same offsets in both
+    uint32_t aux_max_bytes = 0;                        // largest aux record of the side: sizes the aux part of a ring slot
     std::vector<DenseTask> dense_tasks;               // side 0 only: dense units to generate on the device
 };
 
