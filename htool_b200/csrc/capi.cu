@@ -29,7 +29,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 namespace {
 std::mutex g_option_mutex;
 std::map<std::string, int64_t> g_options = {
-    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 4096}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 0}, {"m_b_ring_log2", 2}, {"m_reduce_ring_stages", 0}, {"mrhs_min", 0}, {"pack_generate_dense", 0}, {"sort_units", 1}, {"reduce_blocks_per_cta", 0}, {"m_reduce_warps", 24}, {"m_pad", 4}, {"m_stage_input", 1}, {"m_small_runs", 1}, {"m_reduce_split", 1}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}};
+    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 4096}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 0}, {"m_b_ring_log2", 3}, {"m_reduce_ring_stages", 0}, {"mrhs_min", 0}, {"pack_generate_dense", 0}, {"sort_units", 1}, {"reduce_blocks_per_cta", 0}, {"m_reduce_warps", 24}, {"m_pad", 4}, {"m_b_producers", 3}, {"m_stage_input", 1}, {"m_small_runs", 1}, {"m_reduce_split", 1}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}};
 
 int64_t option(const char *key) {
     std::lock_guard<std::mutex> lock(g_option_mutex);
@@ -782,6 +782,7 @@ static int create_impl(const htb_hmatrix_desc *desc, const htb_generator_desc *g
     h->launch_cfg.m_reduce_ring_stages = static_cast<int>(option("m_reduce_ring_stages"));
     h->launch_cfg.m_b_ring_log2        = static_cast<int>(option("m_b_ring_log2"));
     h->launch_cfg.m_reduce_warps       = static_cast<int>(option("m_reduce_warps"));
+    h->launch_cfg.m_b_producers        = static_cast<int>(option("m_b_producers"));
     if (h->launch_cfg.m_b_ring_log2 < 1 || h->launch_cfg.m_b_ring_log2 > 3)
         return fail(HTB_ERR_INVALID, "m_b_ring_log2 must be in [1, 3]");
     // a ring slot of the multi-RHS kernels = stage + the largest aux record of THIS store; ring depths 0 = as deep as the

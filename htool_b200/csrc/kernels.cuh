@@ -45,7 +45,8 @@ struct LaunchConfig {
                                   // (0: the worst case a stage can hold, aux_slot_bytes(cseg_bytes))
     int m_pad                = 4; // vector stride of the multi-RHS scratch / B ring / X block = vs + m_pad (mkernels.cuh)
     int m_x_rows             = 0; // tallest block of the store: rows of REDUCE_M's X block in shared memory
-    int m_b_ring_log2        = 2; // APPLY_M: the ring of B-row chunks (32 rows each) holds 2^this chunks
+    int m_b_producers        = 3; // APPLY_M: B producer warps (1 .. 3)
+    int m_b_ring_log2        = 3; // APPLY_M: the ring of B-row chunks (32 rows each) holds 2^this chunks
     int reduce_blocks_per_cta = 0; // REDUCE: blocks handled by one CTA through one ring (0 = automatic: 2 for small blocks, else 1)
     int evict_first = 1; // L2 evict_first hint on the coefficient stream
 };

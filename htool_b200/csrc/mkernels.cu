@@ -171,32 +171,64 @@ __global__ void __launch_bounds__((kReduceWarpsMax + 1) * 32) reduce_m_kernel(MS
     const int g = lane >> 2, tig = lane & 3;
     const int kReduceWarps = static_cast<int>(blockDim.x >> 5) - 1; // consumer warps; the last warp is the producer
 
+    uint64_t *xbar = empty + ks.ring_stages; // completion of the bulk copy of the X block
+    // The staged group (capi.cu: rows one X-block row apart, 16 B aligned, zero padded) is ONE contiguous piece of memory
+    // with the layout of the X block: the producer lane brings the block's rows with a single bulk copy that overlaps the
+    // first stages, instead of ~11 dependent global loads per consumer thread in front of the first DMMA.
+    const bool x_bulk       = !CPLX && a.ld_in == XS && a.col0_in == 0 && ((reinterpret_cast<uintptr_t>(a.in) & 15u) == 0);
+    const long long gr0     = static_cast<long long>(bd.row_start) + a.in_shift; // input row of the block's first row
+    const int x_lo          = gr0 < 0 ? static_cast<int>(gr0 < -bd.nrows ? bd.nrows : -gr0) : 0;
+    const long long x_avail = a.in_rows - gr0;
+    const int x_hi          = x_avail < x_lo ? x_lo : (x_avail < bd.nrows ? static_cast<int>(x_avail) : bd.nrows); // rows [x_lo, x_hi) of the block exist in the input
+
     init_barriers(ks.ring_stages, full, empty, kReduceWarps);
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(xbar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     if (warp == kReduceWarps) {
-        if (lane == 0)
+        if (lane == 0) {
+            if (x_bulk && x_hi > x_lo) {
+                const uint32_t bytes = static_cast<uint32_t>(x_hi - x_lo) * static_cast<uint32_t>(XS) * 8u;
+                mbar_arrive_expect_tx(smem_u32(xbar), bytes);
+                bulk_g2s_plain(smem_u32(Xs + static_cast<size_t>(x_lo) * XS), a.in + (gr0 + x_lo) * a.ld_in, bytes, smem_u32(xbar));
+            } else
+                mbar_arrive(smem_u32(xbar));
             produce(ks, bd, ring, slot_bytes, full, empty, a.twice_only);
+        }
         return;
     }
     // (the producer is already streaming) the block's rows of the input matrix, real columns [col0, col0 + mc), zero padded
     // to VS columns; 4 zero rows follow the block (the last k-step of a run that ends the block reads up to 3 rows past it)
-    for (int idx = threadIdx.x; idx < (RB + 4) * a.vs; idx += kReduceWarps * 32) {
-        const int r = idx / a.vs, c = idx - r * a.vs;
-        const int i = r >> CS;
-        const long long gr = static_cast<long long>(bd.row_start) + i + a.in_shift;
-        double v           = 0.;
-        if (i < bd.nrows && c < a.mc && gr >= 0 && gr < a.in_rows) {
-            const double *row = a.in + gr * a.ld_in + a.col0_in;
-            if (!CPLX || !(r & 1))
-                v = row[c];
-            else { // row 2i+1 of the embedding: i * X[i][.] = (-im, re); conjugated panel: -i * X[i][.] = (im, -re)
-                const double o = row[c ^ 1];
-                v              = ((c & 1) != 0) == (a.conj == 0) ? o : -o;
-            }
+    if (x_bulk) {
+        const int nz = (RB + 4) - (x_hi - x_lo); // rows that the bulk copy does not bring: zeros
+        for (int idx = threadIdx.x; idx < nz * a.vs; idx += kReduceWarps * 32) {
+            int r       = idx / a.vs;
+            const int c = idx - r * a.vs;
+            r           = r < x_lo ? r : r + (x_hi - x_lo);
+            Xs[r * XS + c] = 0.;
         }
-        Xs[r * XS + c] = v;
+    } else {
+        for (int idx = threadIdx.x; idx < (RB + 4) * a.vs; idx += kReduceWarps * 32) {
+            const int r = idx / a.vs, c = idx - r * a.vs;
+            const int i = r >> CS;
+            const long long gr = static_cast<long long>(bd.row_start) + i + a.in_shift;
+            double v           = 0.;
+            if (i < bd.nrows && c < a.mc && gr >= 0 && gr < a.in_rows) {
+                const double *row = a.in + gr * a.ld_in + a.col0_in;
+                if (!CPLX || !(r & 1))
+                    v = row[c];
+                else { // row 2i+1 of the embedding: i * X[i][.] = (-im, re); conjugated panel: -i * X[i][.] = (im, -re)
+                    const double o = row[c ^ 1];
+                    v              = ((c & 1) != 0) == (a.conj == 0) ? o : -o;
+                }
+            }
+            Xs[r * XS + c] = v;
+        }
     }
     asm volatile("bar.sync 1, %0;" ::"r"(kReduceWarps * 32) : "memory");
+    mbar_wait(smem_u32(xbar), 0);
 
     const int MT = a.vs >> 3; // column tiles of the right-hand sides
     RingPos pos;
@@ -281,6 +313,8 @@ __global__ void __launch_bounds__((kReduceWarpsMax + 1) * 32) reduce_m_kernel(MS
 // a multiple of 32: a k-step never straddles two chunks, a chunk never two stages.
 // smem: [stage ring: slot = stage | aux] [B ring: chunk = 32 x VSP doubles] [barriers]
 constexpr int kBChunk = 32;
+constexpr int kBProducersMax = 3; // B producer warps: chunk c is filled by producer c % np (one warp cannot keep up with the near field, whose
+                                  // 9-row panels turn a chunk of 32 B rows into a handful of DMMAs per consumer warp)
 
 __device__ __forceinline__ void cp_async8(uint32_t dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory"); }
 
@@ -300,7 +334,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { a
 // (TMA, completion counted in bytes on the chunk's mbarrier): ~4 copies per chunk of 32 rows instead of 32, and the warp
 // never waits for data.
 template <bool CPLX>
-__device__ __forceinline__ void produce_b(const MSide &ks, const BlockDesc &bd, const MArgs &a, unsigned char *ring, uint32_t slot_bytes, uint64_t *full, uint64_t *empty, const BRing &br, uint32_t n_my_stages, int lane) {
+__device__ __forceinline__ void produce_b(const MSide &ks, const BlockDesc &bd, const MArgs &a, unsigned char *ring, uint32_t slot_bytes, uint64_t *full, uint64_t *empty, const BRing &br, uint32_t n_my_stages, int lane, uint32_t pid, uint32_t np) {
     const bool in16   = (a.ld_in % 2 == 0) && (a.col0_in % 2 == 0) && (a.mc % 2 == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 15u) == 0); // rows of the input matrix are 16 B aligned
     const bool in_seq = in16 && a.ld_in == a.vsp && a.col0_in == 0;                                                                        // ... and consecutive rows are one row of the chunk apart (the staged group)
     const uint32_t row_bytes = static_cast<uint32_t>(a.vsp) * 8u;
@@ -338,6 +372,10 @@ __device__ __forceinline__ void produce_b(const MSide &ks, const BlockDesc &bd, 
                 const long long chunk = static_cast<long long>((bpos + j) >> 5);
                 const uint32_t first  = (bpos + j) & 31u;
                 const uint32_t n      = (K - j) < (32u - first) ? (K - j) : (32u - first);
+                if (static_cast<uint32_t>(chunk % np) != pid) { // another B producer's chunk
+                    j += n;
+                    continue;
+                }
                 if (chunk != open) {
                     publish();
                     if (lane == 0)
@@ -528,7 +566,7 @@ __device__ __forceinline__ void run_tiles(const BRing &br, long long &cur, int l
 }
 
 template <bool CPLX, int CT>
-__global__ void __launch_bounds__((kApplyWarps + 2) * 32, 1) apply_m_kernel(MSide ks, MArgs a, int b_log2n) {
+__global__ void __launch_bounds__((kApplyWarps + 1 + kBProducersMax) * 32, 1) apply_m_kernel(MSide ks, MArgs a, int b_log2n) {
     constexpr int CS  = CPLX ? 1 : 0;
     constexpr int PAR = kApplyWarps / CT;                            // row-tile classes
     constexpr int NJ  = (CPLX ? 8 : 16) / PAR > 0 ? (CPLX ? 8 : 16) / PAR : 1; // row tiles of a warp (a complex block has 64 rows = 8 tiles)
@@ -550,11 +588,12 @@ __global__ void __launch_bounds__((kApplyWarps + 2) * 32, 1) apply_m_kernel(MSid
     br.empty        = br.full + (1u << b_log2n);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, tig = lane & 3;
+    const uint32_t np = (blockDim.x >> 5) - kApplyWarps - 1; // B producer warps
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < ks.ring_stages; s++) {
             mbar_init(smem_u32(&full[s]), 1);
-            mbar_init(smem_u32(&empty[s]), kApplyWarps + 1); // the consumers and the B producer
+            mbar_init(smem_u32(&empty[s]), kApplyWarps + np); // the consumers and the B producers
         }
         for (uint32_t s = 0; s <= br.mask; s++) {
             mbar_init(smem_u32(&br.full[s]), 1); // the B producer's arrive; the rows are counted in bytes (expect_tx)
@@ -569,8 +608,8 @@ __global__ void __launch_bounds__((kApplyWarps + 2) * 32, 1) apply_m_kernel(MSid
             produce(ks, bd, ring, slot_bytes, full, empty, a.twice_only);
         return;
     }
-    if (warp == kApplyWarps + 1) {
-        produce_b<CPLX>(ks, bd, a, ring, slot_bytes, full, empty, br, n_my_stages, lane);
+    if (warp > kApplyWarps) {
+        produce_b<CPLX>(ks, bd, a, ring, slot_bytes, full, empty, br, n_my_stages, lane, static_cast<uint32_t>(warp - kApplyWarps - 1), np);
         return;
     }
     const int ct = warp % CT, par = warp / CT;
@@ -850,7 +889,7 @@ inline MSide make_mside(const SideDevice &s, const LaunchConfig &cfg, int ring, 
 size_t reduce_m_smem_bytes(const LaunchConfig &cfg, int vs, size_t esize) {
     const size_t slot = static_cast<size_t>(cfg.stage_bytes) + aux_part(cfg);
     const size_t rb   = static_cast<size_t>(cfg.m_x_rows > 0 ? cfg.m_x_rows : cfg.block_rows) * (esize / 8);
-    return static_cast<size_t>(cfg.m_reduce_ring_stages) * slot + sizeof(double) * (rb + 4) * (vs + cfg.m_pad) + 16 * static_cast<size_t>(cfg.m_reduce_ring_stages);
+    return static_cast<size_t>(cfg.m_reduce_ring_stages) * slot + sizeof(double) * (rb + 4) * (vs + cfg.m_pad) + 16 * static_cast<size_t>(cfg.m_reduce_ring_stages) + 16;
 }
 size_t apply_m_smem_bytes(const LaunchConfig &cfg) {
     const size_t slot = static_cast<size_t>(cfg.stage_bytes) + aux_part(cfg);
@@ -859,8 +898,18 @@ size_t apply_m_smem_bytes(const LaunchConfig &cfg) {
 }
 
 cudaError_t configure_mkernels(const LaunchConfig &cfg, size_t esize) {
-    auto set = [](const void *f, size_t smem) -> cudaError_t {
-        cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    // The attribute belongs to the kernel, not to the handle, and ring slots are sized per store (largest aux record): two
+    // operators of one process need different amounts. Allow whatever the device offers; each launch passes its own size.
+    int dev = 0, optin = 0;
+    cudaError_t e0 = cudaGetDevice(&dev);
+    if (e0 == cudaSuccess)
+        e0 = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e0 != cudaSuccess)
+        return e0;
+    auto set = [optin](const void *f, size_t smem) -> cudaError_t {
+        if (smem > static_cast<size_t>(optin))
+            return cudaErrorInvalidValue;
+        cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
         // several CTAs per SM: ask for the largest shared-memory carve-out, the default only guarantees one block
         return e != cudaSuccess ? e : cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     };
@@ -901,7 +950,7 @@ cudaError_t launch_apply_m(const SideDevice &side, const LaunchConfig &cfg, cons
     a.beta_is_zero     = (args.beta == 0. && args.beta_im == 0.) ? 1 : 0;
     const MSide ms     = make_mside(side, cfg, cfg.m_ring_stages, true);
     const size_t smem  = apply_m_smem_bytes(cfg);
-    const int threads  = (kApplyWarps + 2) * 32;
+    const int threads  = (kApplyWarps + 1 + std::min(std::max(cfg.m_b_producers, 1), kBProducersMax)) * 32;
     const int bl       = cfg.m_b_ring_log2;
     // column tiles of the group: no warp is given zero columns to multiply
     const int ct = args.vs > 32 ? 8 : (args.vs > 16 ? 4 : (args.vs > 8 ? 2 : 1));
