@@ -72,7 +72,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gmres-iterations", type=int, default=200, help="BASELINE.json configs[4]: repeated matvecs inside a device-resident GMRES solve (0: skip)")
     ap.add_argument("--sections", default=os.environ.get("HTB_BENCH_SECTIONS", "all"),
-                    help="comma-separated extra sections (all | none | mu64,mu5,symmetric,helmholtz,gmres,generated_dense,dist_parity,config3_helmholtz_S_N2e6,config4_laplace_N8e6_gmres)")
+                    help="comma-separated extra sections (all | none | mu64,mu5,symmetric,helmholtz,gmres,generated_dense,device_assembly,dist_parity,config3_helmholtz_S_N2e6,config4_laplace_N8e6_gmres)")
     ap.add_argument("--extra-points", type=int, default=0, help="override the point count of the extra sections (tests)")
     return ap.parse_args()
 
@@ -571,6 +571,46 @@ def section_generated_dense(w: Workload, y_host_packed, x_global):
     return out
 
 
+def section_device_assembly(w: Workload, y_host_packed, x_global):
+    """SURVEY.md 8f rank 1, second step: the WHOLE leaf assembly on the GPU (htb_create_compressed) — the admissible blocks
+    compressed by a batched sympartialACA, the dense leaves generated — from the block cluster tree, the points and epsilon
+    alone, instead of HMatrixTreeBuilder::openmp_compute_blocks on the host cores (tree_builder.hpp:604-666). Gate: the
+    same rank as the reference for every block; reported: whether the product equals the host-assembled operator's bit
+    for bit (it does when the host BLAS computes axpy without FMA, as the fixtures' did) and its relative l2 distance."""
+    import ctypes as C
+
+    from htool_b200 import capi
+
+    case = w.case
+    lv = case.leaves().copy()
+    ref_rank = lv["rank"].copy()
+    lv["rank"] = np.where(ref_rank >= 0, capi.HTB_RANK_COMPRESS, -1)
+    lv["data0"], lv["data1"] = 0, 0
+    arr = (capi.htb_leaf * max(1, len(lv))).from_buffer_copy(lv.tobytes())
+    d = capi.htb_hmatrix_desc()
+    C.memmove(C.byref(d), C.byref(case.desc), C.sizeof(capi.htb_hmatrix_desc))
+    d.leaves = C.cast(arr, C.POINTER(capi.htb_leaf))
+    d.device = w.ctx.local_rank
+    t0 = time.perf_counter()
+    op = capi.Operator(d, generator=("laplace_reg", case.points(0), case.points(1), 0.0), compress_epsilon=1e-4)
+    t_create = time.perf_counter() - t0
+    ci = op.compression_info()
+    ranks = op.leaf_ranks()
+    y = np.zeros(w.n_local, w.dtype)
+    op.add_vector_product("N", 1.0, x_global, 0.0, y)
+    op.close()
+    info = case.info()
+    out = {"admissible_blocks_compressed_on_device": ci["nb_blocks"], "compression_failures": ci["nb_failed"], "coefficients_of_the_factors": ci["coefficients"],
+           "rank_min": ci["rank_min"], "rank_max": ci["rank_max"], "aca_kernel_seconds": ci["seconds_aca"], "factor_pool_bytes": ci["pool_bytes"],
+           "create_seconds_device_assembly": t_create, "reference_host_assembly_seconds": info["build_seconds"], "reference_host_threads": info["omp_threads"],
+           "create_seconds_host_packed": w.t_upload, "leaves_with_the_reference_rank": int((ranks == ref_rank).sum()), "leaves": int(len(ranks)),
+           "product_bit_identical_to_host_assembled_operator": bool(np.array_equal(y, y_host_packed)),
+           "rel_l2_vs_host_assembled_operator": float(np.linalg.norm(y - y_host_packed) / np.linalg.norm(y_host_packed))}
+    if not out["rel_l2_vs_host_assembled_operator"] <= 1e-3:  # two epsilon-accurate compressions of the same operator
+        raise SystemExit(f"PARITY FAILURE (device assembly): {out}")
+    return out
+
+
 def section_gmres(w: Workload, n_products, bare_value, restart=40):
     """BASELINE.json configs[4]: products INSIDE a device-resident restarted GMRES (htb_gmres; with N > 1 the product is the
     distributed one and the inner products are summed over the ranks). Call sequence per iteration = what
@@ -809,6 +849,7 @@ def run_ours(args):
         run_section("gmres", lambda: section_gmres(w, args.gmres_iterations, value), 20)
     if base_double and world == 1:
         run_section("generated_dense", lambda: section_generated_dense(w, y_headline, x_headline), 20)
+        run_section("device_assembly", lambda: section_device_assembly(w, y_headline, x_headline), 40)
     line["gmres"] = extras.get("gmres")
     w.close()
     del w

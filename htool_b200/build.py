@@ -20,8 +20,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-fopenmp,-Wall,-Wno-unknown-pragmas",
           "-I", os.path.join(REPO, "include"), "-I", CSRC]
-SOURCES = ["packer.cpp", "kernels.cu", "mkernels.cu", "generate.cu", "capi.cu", "dist.cu", "gmres.cu"]
-HEADERS = ["store.hpp", "packer.hpp", "kernels.cuh", "mkernels.cuh", "generate.cuh", "handle.hpp", os.path.join(REPO, "include", "htool_b200.h")]
+SOURCES = ["packer.cpp", "kernels.cu", "mkernels.cu", "generate.cu", "aca.cu", "capi.cu", "dist.cu", "gmres.cu"]
+HEADERS = ["store.hpp", "packer.hpp", "kernels.cuh", "mkernels.cuh", "generate.cuh", "aca.cuh", "kernel_functions.cuh", "handle.hpp", os.path.join(REPO, "include", "htool_b200.h")]
 
 
 def _newer(target: str, deps: list[str]) -> bool:

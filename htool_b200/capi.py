@@ -114,6 +114,8 @@ class htb_packed_side(C.Structure):
         ("aux_apply", C.c_void_p),
         ("n_dense_tasks", C.c_int64),
         ("dense_tasks", C.c_void_p),
+        ("n_lowrank_tasks", C.c_int64),
+        ("lowrank_tasks", C.c_void_p),
     ]
 
 
@@ -121,6 +123,15 @@ class htb_generator_desc(C.Structure):
     _fields_ = [("kernel", C.c_int32), ("spatial_dimension", C.c_int32), ("wavenumber", C.c_double), ("target_points", C.c_void_p), ("source_points", C.c_void_p)]
 
 
+class htb_compression_info(C.Structure):
+    _fields_ = [("nb_blocks", C.c_int64), ("nb_failed", C.c_int64), ("coefficients", C.c_int64), ("pool_bytes", C.c_int64), ("rank_min", C.c_int32), ("rank_max", C.c_int32),
+                ("seconds_aca", C.c_double), ("seconds_total", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+HTB_RANK_COMPRESS = -2
 HTB_KERNELS = {"laplace": 0, "laplace_reg": 1, "complex_reg": 2, "hermitian_reg": 3, "helmholtz": 4, "complex": 5}
 
 
@@ -140,6 +151,9 @@ HTB_GMRES_CGS, HTB_GMRES_CGS2 = 0, 1
 SYMBOLS = {
     "htb_create": (C.c_int, [C.POINTER(htb_hmatrix_desc), C.POINTER(C.c_void_p)]),
     "htb_create_generated": (C.c_int, [C.POINTER(htb_hmatrix_desc), C.c_void_p, C.POINTER(C.c_void_p)]),
+    "htb_create_compressed": (C.c_int, [C.POINTER(htb_hmatrix_desc), C.c_void_p, C.c_double, C.POINTER(C.c_void_p)]),
+    "htb_get_leaf_ranks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "htb_get_compression_info": (C.c_int, [C.c_void_p, C.POINTER(htb_compression_info)]),
     "htb_download_store": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
     "htb_destroy": (C.c_int, [C.c_void_p]),
     "htb_get_info": (C.c_int, [C.c_void_p, C.POINTER(htb_info)]),
@@ -217,9 +231,10 @@ def _ptr(a):
 class Operator:
     """Thin RAII wrapper over an htb_handle (what htool_b200::GpuHMatrix is on the C++ side)."""
 
-    def __init__(self, desc: htb_hmatrix_desc, keepalive=None, generator=None):
+    def __init__(self, desc: htb_hmatrix_desc, keepalive=None, generator=None, compress_epsilon=None):
         """generator = (kernel name, target points (n x 3, cluster numbering), source points, wavenumber): dense leaves
-        whose data0 is NULL are generated on the device (htb_create_generated)."""
+        whose data0 is NULL are generated on the device (htb_create_generated). compress_epsilon: leaves of rank
+        HTB_RANK_COMPRESS are compressed on the device as well (htb_create_compressed)."""
         self.lib = load()
         self.handle = C.c_void_p()
         self.dtype_code = desc.dtype
@@ -233,7 +248,21 @@ class Operator:
             tp, sp = np.ascontiguousarray(tp, dtype=np.float64), np.ascontiguousarray(sp, dtype=np.float64)
             assert tp.shape == (desc.nb_rows, 3) and sp.shape == (desc.nb_cols, 3)
             g = htb_generator_desc(HTB_KERNELS[kernel], 3, float(k), tp.ctypes.data, sp.ctypes.data)
-            check(self.lib, self.lib.htb_create_generated(C.byref(desc), C.byref(g), C.byref(self.handle)))
+            if compress_epsilon is None:
+                check(self.lib, self.lib.htb_create_generated(C.byref(desc), C.byref(g), C.byref(self.handle)))
+            else:
+                check(self.lib, self.lib.htb_create_compressed(C.byref(desc), C.byref(g), float(compress_epsilon), C.byref(self.handle)))
+        self.nb_leaves = desc.nb_leaves
+
+    def leaf_ranks(self) -> np.ndarray:
+        out = np.zeros(self.nb_leaves, dtype=np.int32)
+        check(self.lib, self.lib.htb_get_leaf_ranks(self.handle, _ptr(out), self.nb_leaves))
+        return out
+
+    def compression_info(self) -> dict:
+        i = htb_compression_info()
+        check(self.lib, self.lib.htb_get_compression_info(self.handle, C.byref(i)))
+        return i.as_dict()
 
     def download_store(self, side: int, nbytes: int) -> np.ndarray:
         out = np.zeros(nbytes, dtype=np.uint8)

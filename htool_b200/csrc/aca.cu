@@ -1,0 +1,307 @@
+// htool_b200/csrc/aca.cu — batched adaptive cross approximation on the device: the admissible blocks of the block cluster tree
+// are compressed on the GPU, straight from the kernel function and the points, and their factors go into the leaf store
+// without ever existing on the host (second step; the dense leaves are generate.cu).
+//
+// What it replaces in the reference: sympartialACA::copy_low_rank_approximation
+// (include/htool/hmatrix/lrmat/sympartialACA.hpp:41-216), called per admissible block from HMatrix::compute_low_rank_data
+// (hmatrix/hmatrix.hpp:228-237) inside HMatrixTreeBuilder::openmp_compute_blocks (hmatrix/tree_builder/tree_builder.hpp:604-626):
+// 1.0 M blocks / 2.32 G coefficients / 11 s on 16 host cores at N = 1e6.
+//
+// The arithmetic is the reference's, operation for operation, so that a real kernel function produces the SAME pivots, the
+// same ranks and bit-identical factors:
+//   * the generator values are those of kernel_functions.cuh (bit-identical to the host generators);
+//   * the residual updates are the reference's axpy chain in term order (u -= uu_j[I1] vv_j for j = 0, 1, ...: :107-110,
+//     :138-141), one rounded product + one rounded sum per term (fma_axpy = 1: one fused operation, for FMA BLAS builds);
+//   * the pivot searches take the LAST maximum among the unvisited entries (the reference's `if (tmp < pivot) continue`,
+//     :114-122, :144-152): a team-wide arg-max with "larger index wins ties";
+//   * the dot products of the stopping criterion (:158-166) are the reference's own scalar loop
+//     (wrapper_blas.hpp:152-157: sum += x[i] * y[i], in index order): one THREAD per dot product walks its vectors in order —
+//     the 2 q dot products of an iteration are independent and run side by side;
+//   * q (n1 + n2) > n1 n2 is evaluated in 64 bits (the reference's int product overflows from 46341 x 46341 on).
+// One CTA ("team") per block; blocks are sorted by size and launched in three classes (512 / 128 / 32 threads). Every new
+// term takes a chunk [uu (n1) | vv (n2)] from a bump-allocated pool; the block's chunk offsets are its term table.
+#include "aca.cuh"
+#include "kernel_functions.cuh"
+
+namespace htb {
+
+namespace {
+
+template <int KERNEL>
+__device__ __forceinline__ double entry(bool swapped, const double *p1, const double *p2, int a, int b, double wavenumber) {
+    // a: index along dimension 1, b: along dimension 2; the kernel function takes (target point, source point)
+    return swapped ? kernel_value<KERNEL>(p2 + 3ll * b, p1 + 3ll * a, wavenumber).re : kernel_value<KERNEL>(p1 + 3ll * a, p2 + 3ll * b, wavenumber).re;
+}
+
+template <bool FMA>
+__device__ __forceinline__ double axpy1(double coef, double x, double y) {
+    return FMA ? fma(coef, x, y) : __dadd_rn(y, __dmul_rn(coef, x));
+}
+
+// sum += x[i] * y[i] in index order, every operation rounded (wrapper_blas.hpp:152-157)
+__device__ __forceinline__ double dot_in_order(const double *x, const double *y, int len) {
+    double s = 0.;
+    int i    = 0;
+    for (; i + 4 <= len; i += 4) {
+        const double x0 = x[i], x1 = x[i + 1], x2 = x[i + 2], x3 = x[i + 3];
+        const double y0 = y[i], y1 = y[i + 1], y2 = y[i + 2], y3 = y[i + 3];
+        s = __dadd_rn(s, __dmul_rn(x0, y0));
+        s = __dadd_rn(s, __dmul_rn(x1, y1));
+        s = __dadd_rn(s, __dmul_rn(x2, y2));
+        s = __dadd_rn(s, __dmul_rn(x3, y3));
+    }
+    for (; i < len; i++)
+        s = __dadd_rn(s, __dmul_rn(x[i], y[i]));
+    return s;
+}
+
+// Team-wide arg-max of (value, index): the larger value wins, equal values: the larger index (the reference's scan keeps the
+// LAST maximum). index -1 = no candidate. Every thread returns the result.
+template <int TS>
+__device__ __forceinline__ int team_argmax(double best, int idx, double *s_rv, int *s_ri) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, d);
+        const int oi    = __shfl_xor_sync(0xffffffffu, idx, d);
+        if (ob > best || (ob == best && oi > idx)) {
+            best = ob;
+            idx  = oi;
+        }
+    }
+    if (TS == 32)
+        return idx;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads(); // (the scratch may still be read by the previous call)
+    if (lane == 0) {
+        s_rv[warp] = best;
+        s_ri[warp] = idx;
+    }
+    __syncthreads();
+    best = s_rv[0], idx = s_ri[0];
+#pragma unroll
+    for (int w = 1; w < TS / 32; w++) {
+        const double ob = s_rv[w];
+        const int oi    = s_ri[w];
+        if (ob > best || (ob == best && oi > idx)) {
+            best = ob;
+            idx  = oi;
+        }
+    }
+    return idx;
+}
+
+template <int TS>
+__device__ __forceinline__ void team_sync() {
+    if (TS == 32)
+        __syncwarp();
+    else
+        __syncthreads();
+}
+
+template <int TS, int KERNEL, bool FMA>
+__global__ void __launch_bounds__(TS) aca_kernel(const AcaBlock *__restrict__ blocks, long long first, const double *__restrict__ tp, const double *__restrict__ sp, double wavenumber, double epsilon, AcaPool pool,
+                                                 int32_t *__restrict__ rank_out) {
+    __shared__ uint32_t s_off[kAcaMaxRank];
+    __shared__ int s_piv1[kAcaMaxRank], s_piv2[kAcaMaxRank];
+    __shared__ double s_dot[2 * kAcaMaxRank + 2];
+    __shared__ double s_rv[TS / 32];
+    __shared__ int s_ri[TS / 32];
+    __shared__ unsigned long long s_chunk;
+
+    const long long bi = first + blockIdx.x;
+    const AcaBlock blk = blocks[bi];
+    const int tid      = threadIdx.x;
+    const bool swapped = blk.swapped != 0;
+    const int n1 = swapped ? blk.n : blk.m, n2 = swapped ? blk.m : blk.n;
+    const double *p1 = swapped ? sp + 3ll * blk.lcol : tp + 3ll * blk.lrow; // points of dimension 1
+    const double *p2 = swapped ? tp + 3ll * blk.lrow : sp + 3ll * blk.lcol;
+
+    // (sympartialACA.hpp:69-92) every thread carries the same copy of the scalar state
+    int q = 0, I1 = 0, I2 = 0, nv1 = 0, nv2 = 0;
+    double frob = 0., aux = 0.;
+    while (q == 0 || __dsqrt_rn(__ddiv_rn(aux, frob)) > epsilon) { // :97
+        q += 1;
+        if (static_cast<long long>(q) * (static_cast<long long>(n1) + n2) > static_cast<long long>(n1) * n2) { // :102: the next rank would not be advantageous
+            q = kAcaFailed;
+            break;
+        }
+        if (q > static_cast<int>(blk.term_cap)) {
+            q = kAcaRankCap;
+            break;
+        }
+        // a chunk [uu_q | vv_q] for the new term
+        const unsigned long long len = (static_cast<unsigned long long>(n1) + n2 + 1ull) & ~1ull;
+        team_sync<TS>();
+        if (tid == 0) {
+            const unsigned long long off = atomicAdd(pool.cursor, len);
+            s_chunk                      = off + len <= pool.capacity ? off : ~0ull;
+            if (off + len <= pool.capacity)
+                s_off[q - 1] = static_cast<uint32_t>(off >> 1);
+        }
+        team_sync<TS>();
+        const unsigned long long off = s_chunk;
+        if (off == ~0ull) {
+            q = kAcaPoolOverflow;
+            break;
+        }
+        double *uq = pool.pool + off, *vq = uq + n1;
+
+        // row I1 of the residual (:105-110), pivot among the unvisited columns (:112-122)
+        double best = 0.;
+        int idx     = -1;
+        for (int b = tid; b < n2; b += TS) {
+            double v = entry<KERNEL>(swapped, p1, p2, I1, b, wavenumber);
+            for (int j = 0; j < q - 1; j++) {
+                const double *ch = pool.pool + 2ull * s_off[j];
+                v                = axpy1<FMA>(-ch[I1], ch[n1 + b], v);
+            }
+            vq[b]     = v;
+            bool seen = false;
+            for (int t = 0; t < nv2; t++)
+                seen |= s_piv2[t] == b;
+            if (!seen) {
+                const double tmp = fabs(v);
+                if (tmp >= best) {
+                    best = tmp;
+                    idx  = b;
+                }
+            }
+        }
+        idx = team_argmax<TS>(best, idx, s_rv, s_ri);
+        if (idx >= 0)
+            I2 = idx;
+        if (tid == 0)
+            s_piv1[nv1] = I1; // :123
+        nv1++;
+        team_sync<TS>(); // vq written by the team is visible to every thread
+        const double pivot = vq[I2];
+        if (!(fabs(pivot) > 1e-15)) { // :128 / :185-193: a zero row
+            q -= 1;
+            if (q == 0)
+                q = kAcaFailed;
+            break;
+        }
+        const double gamma = __ddiv_rn(1., pivot); // :124
+
+        // column I2 of the residual, scaled (:130-142), pivot among the unvisited rows (:143-152)
+        best = 0.;
+        idx  = -1;
+        for (int a = tid; a < n1; a += TS) {
+            double v = entry<KERNEL>(swapped, p1, p2, a, I2, wavenumber);
+            for (int j = 0; j < q - 1; j++) {
+                const double *ch = pool.pool + 2ull * s_off[j];
+                v                = axpy1<FMA>(-ch[n1 + I2], ch[a], v);
+            }
+            v         = __dmul_rn(v, gamma);
+            uq[a]     = v;
+            bool seen = false;
+            for (int t = 0; t < nv1; t++)
+                seen |= s_piv1[t] == a;
+            if (!seen) {
+                const double tmp = fabs(v);
+                if (tmp >= best) {
+                    best = tmp;
+                    idx  = a;
+                }
+            }
+        }
+        idx = team_argmax<TS>(best, idx, s_rv, s_ri);
+        if (idx >= 0)
+            I1 = idx;
+        if (tid == 0)
+            s_piv2[nv2] = I2; // :153
+        nv2++;
+        team_sync<TS>();
+
+        // error estimator (:156-168): 2 q dot products, one thread each, every one in index order
+        const int ndots = 2 * q;
+        for (int t = tid; t < ndots; t += TS) {
+            double d;
+            if (t == 0)
+                d = dot_in_order(uq, uq, n1);
+            else if (t == 1)
+                d = dot_in_order(vq, vq, n2);
+            else {
+                const double *ch = pool.pool + 2ull * s_off[(t - 2) >> 1];
+                d                = (t & 1) ? dot_in_order(uq, ch, n1) : dot_in_order(vq, ch + n1, n2);
+            }
+            s_dot[t] = d;
+        }
+        team_sync<TS>();
+        aux             = __dmul_rn(fabs(s_dot[0]), fabs(s_dot[1]));
+        double frob_aux = 0.;
+        for (int j = 0; j < q - 1; j++)
+            frob_aux = __dadd_rn(frob_aux, __dmul_rn(s_dot[2 + 2 * j], s_dot[3 + 2 * j]));
+        frob = __dadd_rn(frob, __dadd_rn(aux, __dmul_rn(2., frob_aux)));
+    }
+    team_sync<TS>();
+    for (int j = tid; j < q; j += TS) // (q <= 0: nothing)
+        pool.term_off[blk.term_base + j] = s_off[j];
+    if (tid == 0)
+        rank_out[bi] = q;
+}
+
+// One warp per unit of a low-rank leaf whose factors live in the pool: panel(i, k) = term (k0 + k), entry (p0 + i) of the
+// side's vector — U column k = uu_k (vv_k if the block's dimensions were swapped), V row k = the other one.
+__global__ void scatter_lowrank_kernel(const DenseTask *tasks, long long n_tasks, int side, unsigned char *stream, const AcaLeaf *leaves, const double *pool, const uint32_t *term_off) {
+    const long long t = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (t >= n_tasks)
+        return;
+    const DenseTask task = tasks[t];
+    const AcaLeaf lf     = leaves[task.lrow];
+    const int lane       = threadIdx.x & 31;
+    double *out          = reinterpret_cast<double *>(stream + task.byte_off);
+    const bool second    = (side == 0) == (lf.swapped != 0); // the vv half of the chunk
+    const size_t delta   = (second ? lf.n1 : 0u) + static_cast<size_t>(task.p0);
+    const int total      = static_cast<int>(task.h) * task.w;
+    for (int e = lane; e < total; e += 32) {
+        const int k = e / task.h, i = e - k * task.h;
+        out[static_cast<size_t>(k) * task.ld + i] = pool[2ull * term_off[lf.term_base + task.k0 + k] + delta + i];
+    }
+}
+
+template <int TS, int KERNEL>
+cudaError_t launch_team(const AcaBlock *blocks, long long first, long long count, const double *tp, const double *sp, double wavenumber, double epsilon, int fma_axpy, AcaPool pool, int32_t *rank, cudaStream_t st) {
+    const unsigned grid = static_cast<unsigned>(count);
+    if (fma_axpy)
+        aca_kernel<TS, KERNEL, true><<<grid, TS, 0, st>>>(blocks, first, tp, sp, wavenumber, epsilon, pool, rank);
+    else
+        aca_kernel<TS, KERNEL, false><<<grid, TS, 0, st>>>(blocks, first, tp, sp, wavenumber, epsilon, pool, rank);
+    return cudaGetLastError();
+}
+
+template <int KERNEL>
+cudaError_t launch_kernel(int team, const AcaBlock *blocks, long long first, long long count, const double *tp, const double *sp, double wavenumber, double epsilon, int fma_axpy, AcaPool pool, int32_t *rank, cudaStream_t st) {
+    switch (team) {
+    case 32: return launch_team<32, KERNEL>(blocks, first, count, tp, sp, wavenumber, epsilon, fma_axpy, pool, rank, st);
+    case 128: return launch_team<128, KERNEL>(blocks, first, count, tp, sp, wavenumber, epsilon, fma_axpy, pool, rank, st);
+    case 512: return launch_team<512, KERNEL>(blocks, first, count, tp, sp, wavenumber, epsilon, fma_axpy, pool, rank, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+} // namespace
+
+cudaError_t launch_aca(int kernel, int team, const AcaBlock *blocks, long long first, long long count, const double *target_points, const double *source_points, double wavenumber, double epsilon, int fma_axpy, AcaPool pool,
+                       int32_t *rank, cudaStream_t st) {
+    if (count <= 0)
+        return cudaSuccess;
+    if (count > 0x7fffffffll)
+        return cudaErrorInvalidValue;
+    switch (kernel) { // (real kernel functions; the complex ones keep the host compressor)
+    case HTB_KERNEL_LAPLACE: return launch_kernel<HTB_KERNEL_LAPLACE>(team, blocks, first, count, target_points, source_points, wavenumber, epsilon, fma_axpy, pool, rank, st);
+    case HTB_KERNEL_LAPLACE_REG: return launch_kernel<HTB_KERNEL_LAPLACE_REG>(team, blocks, first, count, target_points, source_points, wavenumber, epsilon, fma_axpy, pool, rank, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_scatter_lowrank(const DenseTask *tasks, long long n_tasks, int side, unsigned char *stream, const AcaLeaf *leaves, const double *pool, const uint32_t *term_off, cudaStream_t st) {
+    if (n_tasks == 0)
+        return cudaSuccess;
+    const int threads   = 256;
+    const unsigned grid = static_cast<unsigned>((n_tasks * 32 + threads - 1) / threads);
+    scatter_lowrank_kernel<<<grid, threads, 0, st>>>(tasks, n_tasks, side, stream, leaves, pool, term_off);
+    return cudaGetLastError();
+}
+
+} // namespace htb

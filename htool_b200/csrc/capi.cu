@@ -4,10 +4,13 @@
 // the t / z vectors, a CUDA stream, pinned staging buffers for the host-pointer entry points and,
 // optionally, an NCCL communicator (dist.cu). There is no CPU path: every compute entry point needs a
 // CUDA device and fails with HTB_ERR_CUDA otherwise.
+#include "aca.cuh"
 #include "generate.cuh"
 #include "handle.hpp"
 
 #include <algorithm>
+#include <chrono>
+#include <climits>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -29,7 +32,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 namespace {
 std::mutex g_option_mutex;
 std::map<std::string, int64_t> g_options = {
-    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 4096}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 0}, {"m_b_ring_log2", 3}, {"m_reduce_ring_stages", 0}, {"mrhs_min", 0}, {"pack_generate_dense", 0}, {"sort_units", 1}, {"reduce_blocks_per_cta", 0}, {"m_reduce_warps", 24}, {"m_pad", 4}, {"m_b_producers", 3}, {"m_stage_input", 1}, {"m_small_runs", 1}, {"m_reduce_split", 1}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}};
+    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 4096}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 0}, {"m_b_ring_log2", 3}, {"m_reduce_ring_stages", 0}, {"mrhs_min", 0}, {"pack_generate_dense", 0}, {"sort_units", 1}, {"reduce_blocks_per_cta", 0}, {"m_reduce_warps", 24}, {"m_pad", 4}, {"m_b_producers", 3}, {"m_stage_input", 1}, {"m_small_runs", 1}, {"m_reduce_split", 1}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}, {"aca_fma_axpy", 0}, {"aca_rank_guess", 16}};
 
 int64_t option(const char *key) {
     std::lock_guard<std::mutex> lock(g_option_mutex);
@@ -647,9 +650,15 @@ int htb_get_option(const char *key, int64_t *value) {
     return HTB_OK;
 }
 
-static int create_impl(const htb_hmatrix_desc *desc, const htb_generator_desc *gen, htb_handle *out);
+// factors of the leaves compressed on the device (htb_create_compressed): where the packer's low-rank tasks find them
+struct CompressedFactors {
+    std::vector<AcaLeaf> leaves; // per leaf of the descriptor
+    AcaPool pool;
+};
 
-int htb_create(const htb_hmatrix_desc *desc, htb_handle *out) { return create_impl(desc, nullptr, out); }
+static int create_impl(const htb_hmatrix_desc *desc, const htb_generator_desc *gen, const CompressedFactors *factors, htb_handle *out);
+
+int htb_create(const htb_hmatrix_desc *desc, htb_handle *out) { return create_impl(desc, nullptr, nullptr, out); }
 
 int htb_create_generated(const htb_hmatrix_desc *desc, const htb_generator_desc *gen, htb_handle *out) {
     if (!gen)
@@ -662,7 +671,7 @@ int htb_create_generated(const htb_hmatrix_desc *desc, const htb_generator_desc 
         return fail(HTB_ERR_INVALID, "the kernel function does not produce the coefficient type of the H-matrix");
     if (desc && ((desc->nb_rows > 0 && !gen->target_points) || (desc->nb_cols > 0 && !gen->source_points)))
         return fail(HTB_ERR_INVALID, "null point array");
-    return create_impl(desc, gen, out);
+    return create_impl(desc, gen, nullptr, out);
 }
 
 int htb_download_store(htb_handle h, int side, void *dst, int64_t bytes) {
@@ -713,7 +722,38 @@ static int generate_dense(htb_operator *h, const Packer &pk, const htb_generator
     return HTB_OK;
 }
 
-static int create_impl(const htb_hmatrix_desc *desc, const htb_generator_desc *gen, htb_handle *out) {
+// panels of the leaves compressed on the device: copied out of the factor pool into the uploaded streams of both sides
+static int scatter_lowrank(htb_operator *h, const Packer &pk, const CompressedFactors &cf) {
+    void *d_leaves = nullptr, *d_tasks = nullptr;
+    cudaError_t e  = cudaMalloc(&d_leaves, std::max<size_t>(16, cf.leaves.size() * sizeof(AcaLeaf)));
+    if (e == cudaSuccess && !cf.leaves.empty())
+        e = cudaMemcpyAsync(d_leaves, cf.leaves.data(), cf.leaves.size() * sizeof(AcaLeaf), cudaMemcpyHostToDevice, h->own_stream);
+    for (int s = 0; s < 2 && e == cudaSuccess; s++) {
+        const std::vector<DenseTask> &tasks = pk.side[s].lr_tasks;
+        if (tasks.empty())
+            continue;
+        e = cudaMalloc(&d_tasks, tasks.size() * sizeof(DenseTask));
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(d_tasks, tasks.data(), tasks.size() * sizeof(DenseTask), cudaMemcpyHostToDevice, h->own_stream);
+        if (e == cudaSuccess)
+            e = launch_scatter_lowrank(static_cast<const DenseTask *>(d_tasks), static_cast<long long>(tasks.size()), s, const_cast<unsigned char *>(h->side[s].stream), static_cast<const AcaLeaf *>(d_leaves), cf.pool.pool,
+                                       cf.pool.term_off, h->own_stream);
+        if (e == cudaSuccess)
+            e = cudaStreamSynchronize(h->own_stream);
+        if (e == cudaSuccess)
+            h->launches++;
+        cudaFree(d_tasks);
+        d_tasks = nullptr;
+    }
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(h->own_stream);
+    cudaFree(d_leaves);
+    if (e != cudaSuccess)
+        return cuda_fail(e, "copy of the device-compressed factors into the leaf store");
+    return HTB_OK;
+}
+
+static int create_impl(const htb_hmatrix_desc *desc, const htb_generator_desc *gen, const CompressedFactors *factors, htb_handle *out) {
     if (!desc || !out)
         return fail(HTB_ERR_INVALID, "null argument");
     *out = nullptr;
@@ -815,6 +855,8 @@ static int create_impl(const htb_hmatrix_desc *desc, const htb_generator_desc *g
     int rc = upload_store(h.get(), *pk);
     if (rc == HTB_OK && gen)
         rc = generate_dense(h.get(), *pk, gen);
+    if (rc == HTB_OK && factors)
+        rc = scatter_lowrank(h.get(), *pk, *factors);
     if (rc != HTB_OK) {
         htb_destroy(h.release());
         return rc;
@@ -849,6 +891,239 @@ static int create_impl(const htb_hmatrix_desc *desc, const htb_generator_desc *g
     i.nb_source_blocks      = h->side[1].n_blocks;
     i.sm_count              = h->sm_count;
     *out                    = h.release();
+    return HTB_OK;
+}
+
+// Leaf assembly on the device, second step: the admissible blocks are compressed by the batched ACA (aca.cu), the ranks come
+// back to the host (they decide the layout of the store), the packer lays the store out with empty low-rank panels and the
+// factors are copied from the pool into the uploaded streams. The factors never exist on the host.
+int htb_create_compressed(const htb_hmatrix_desc *desc, const htb_generator_desc *gen, double epsilon, htb_handle *out) {
+    const auto t_begin = std::chrono::steady_clock::now();
+    if (!desc || !gen || !out)
+        return fail(HTB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (gen->spatial_dimension != 3)
+        return fail(HTB_ERR_INVALID, "the built-in kernel functions are defined for points in R^3");
+    if (gen->kernel < HTB_KERNEL_LAPLACE || gen->kernel > HTB_KERNEL_COMPLEX)
+        return fail(HTB_ERR_INVALID, "unknown built-in kernel function");
+    if (kernel_is_complex(gen->kernel) != (desc->dtype == HTB_COMPLEX_DOUBLE))
+        return fail(HTB_ERR_INVALID, "the kernel function does not produce the coefficient type of the H-matrix");
+    if (desc->dtype != HTB_DOUBLE || (gen->kernel != HTB_KERNEL_LAPLACE && gen->kernel != HTB_KERNEL_LAPLACE_REG))
+        return fail(HTB_ERR_UNSUPPORTED, "device compression is implemented for the real kernel functions (complex kernels: compress on the host, htb_create_generated)");
+    if (!(epsilon > 0.))
+        return fail(HTB_ERR_INVALID, "epsilon must be positive (a required rank is not supported on the device)");
+    if ((desc->nb_rows > 0 && !gen->target_points) || (desc->nb_cols > 0 && !gen->source_points))
+        return fail(HTB_ERR_INVALID, "null point array");
+    if (desc->nb_leaves < 0 || (desc->nb_leaves > 0 && !desc->leaves))
+        return fail(HTB_ERR_INVALID, "null leaf array");
+
+    // the blocks to compress, one size class after the other (teams of 512 / 128 / 32 threads), large blocks first
+    std::vector<AcaBlock> blocks;
+    std::vector<htb_leaf> leaves(desc->leaves, desc->leaves + desc->nb_leaves);
+    uint64_t term_slots = 0;
+    for (int64_t i = 0; i < desc->nb_leaves; i++) {
+        const htb_leaf &l = leaves[i];
+        if (l.rank != HTB_RANK_COMPRESS)
+            continue;
+        if (l.data0 || l.data1)
+            return fail(HTB_ERR_INVALID, "a leaf to compress carries data");
+        if (l.nb_rows < 0 || l.nb_cols < 0 || l.row_offset < 0 || l.col_offset < 0 || int64_t(l.row_offset) + l.nb_rows > desc->nb_rows || int64_t(l.col_offset) + l.nb_cols > desc->nb_cols)
+            return fail(HTB_ERR_INVALID, "leaf outside the root block");
+        if (l.nb_rows == 0 || l.nb_cols == 0) {
+            leaves[i].rank = 0;
+            continue;
+        }
+        AcaBlock b{};
+        b.lrow = l.row_offset, b.lcol = l.col_offset, b.m = l.nb_rows, b.n = l.nb_cols;
+        b.swapped  = (int64_t(desc->row_offset) + l.row_offset >= int64_t(desc->col_offset) + l.col_offset) ? 0 : 1; // sympartialACA.hpp:46
+        b.term_cap = static_cast<uint16_t>(std::min<int64_t>(kAcaMaxRank, (int64_t(b.m) * b.n) / (int64_t(b.m) + b.n)));
+        b.leaf     = static_cast<uint32_t>(i);
+        blocks.push_back(b);
+    }
+    if (blocks.empty()) {
+        htb_hmatrix_desc d2 = *desc; // nothing to compress
+        d2.leaves           = leaves.data();
+        int rc = create_impl(&d2, gen, nullptr, out);
+        if (rc == HTB_OK) {
+            (*out)->leaf_ranks.resize(leaves.size());
+            for (size_t i = 0; i < leaves.size(); i++)
+                (*out)->leaf_ranks[i] = leaves[i].rank;
+            (*out)->compression.seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+        }
+        return rc;
+    }
+    auto team_of = [](const AcaBlock &b) { const int mx = std::max(b.m, b.n); return mx > 512 ? 512 : (mx > 64 ? 128 : 32); };
+    std::stable_sort(blocks.begin(), blocks.end(), [&](const AcaBlock &a, const AcaBlock &b) {
+        const int ta = team_of(a), tb = team_of(b);
+        return ta != tb ? ta > tb : int64_t(a.m) + a.n > int64_t(b.m) + b.n;
+    });
+    for (AcaBlock &b : blocks) {
+        b.term_base = static_cast<uint32_t>(term_slots);
+        term_slots += b.term_cap;
+    }
+    if (term_slots >= (uint64_t(1) << 32))
+        return fail(HTB_ERR_UNSUPPORTED, "term table of the device compression exceeds 2^32 slots");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(HTB_ERR_CUDA, std::string("no CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") + "): htool_b200 has no CPU fallback");
+    int device = desc->device;
+    if (device < 0)
+        HTB_CUDA(cudaGetDevice(&device));
+    if (device >= ndev)
+        return fail(HTB_ERR_INVALID, "device ordinal out of range");
+    DeviceGuard guard(device);
+    if (!guard.ok)
+        return fail(HTB_ERR_CUDA, "cudaSetDevice failed");
+
+    CompressedFactors cf;
+    void *d_blocks = nullptr, *d_tp = nullptr, *d_sp = nullptr, *d_rank = nullptr;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    auto cleanup = [&]() {
+        for (void *p : {d_blocks, d_tp, d_sp, d_rank, static_cast<void *>(cf.pool.pool), static_cast<void *>(cf.pool.cursor), static_cast<void *>(cf.pool.term_off)})
+            if (p)
+                cudaFree(p);
+        if (ev0)
+            cudaEventDestroy(ev0);
+        if (ev1)
+            cudaEventDestroy(ev1);
+        if (st)
+            cudaStreamDestroy(st);
+    };
+#define HTB_CC(call)                          \
+    do {                                      \
+        cudaError_t e__ = (call);             \
+        if (e__ != cudaSuccess) {             \
+            cleanup();                        \
+            return cuda_fail(e__, #call);     \
+        }                                     \
+    } while (0)
+    const size_t tpb = size_t(3) * desc->nb_rows * sizeof(double), spb = size_t(3) * desc->nb_cols * sizeof(double);
+    HTB_CC(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    HTB_CC(cudaEventCreate(&ev0));
+    HTB_CC(cudaEventCreate(&ev1));
+    HTB_CC(cudaMalloc(&d_blocks, blocks.size() * sizeof(AcaBlock)));
+    HTB_CC(cudaMalloc(&d_rank, blocks.size() * sizeof(int32_t)));
+    HTB_CC(cudaMalloc(&d_tp, std::max<size_t>(8, tpb)));
+    HTB_CC(cudaMalloc(&d_sp, std::max<size_t>(8, spb)));
+    HTB_CC(cudaMalloc(reinterpret_cast<void **>(&cf.pool.cursor), sizeof(unsigned long long)));
+    HTB_CC(cudaMalloc(reinterpret_cast<void **>(&cf.pool.term_off), std::max<uint64_t>(1, term_slots) * sizeof(uint32_t)));
+    HTB_CC(cudaMemcpyAsync(d_blocks, blocks.data(), blocks.size() * sizeof(AcaBlock), cudaMemcpyHostToDevice, st));
+    HTB_CC(cudaMemcpyAsync(d_tp, gen->target_points, tpb, cudaMemcpyHostToDevice, st));
+    HTB_CC(cudaMemcpyAsync(d_sp, gen->source_points, spb, cudaMemcpyHostToDevice, st));
+
+    // The factor pool. The ranks are unknown before the compression: the pool is sized for `guess` terms per block (never
+    // more than a block can hold) and the whole batch is repeated with twice the guess when it overflows.
+    size_t free_bytes = 0, total_bytes = 0;
+    HTB_CC(cudaMemGetInfo(&free_bytes, &total_bytes));
+    const uint64_t pool_limit = std::min<uint64_t>(uint64_t(1) << 33, static_cast<uint64_t>(free_bytes * 0.45) / sizeof(double)); // (term offsets are stored in 16-byte units, 32 bits)
+    std::vector<int32_t> rank(blocks.size());
+    double seconds_aca = 0.;
+    const int fma_axpy = option("aca_fma_axpy") != 0;
+    for (int64_t guess = std::max<int64_t>(1, option("aca_rank_guess"));; guess *= 2) {
+        uint64_t want = 0, full = 0;
+        for (const AcaBlock &b : blocks) {
+            const uint64_t len = (uint64_t(b.m) + b.n + 1u) & ~uint64_t(1);
+            want += len * std::min<uint64_t>(b.term_cap, static_cast<uint64_t>(guess));
+            full += len * b.term_cap;
+        }
+        const uint64_t capacity = std::max<uint64_t>(2, std::min(want, pool_limit));
+        if (cf.pool.pool)
+            cudaFree(cf.pool.pool);
+        cf.pool.pool = nullptr;
+        HTB_CC(cudaMalloc(reinterpret_cast<void **>(&cf.pool.pool), capacity * sizeof(double)));
+        cf.pool.capacity = capacity;
+        HTB_CC(cudaMemsetAsync(cf.pool.cursor, 0, sizeof(unsigned long long), st));
+        HTB_CC(cudaEventRecord(ev0, st));
+        for (size_t first = 0; first < blocks.size();) { // one launch per size class
+            size_t last = first;
+            while (last < blocks.size() && team_of(blocks[last]) == team_of(blocks[first]))
+                last++;
+            HTB_CC(launch_aca(gen->kernel, team_of(blocks[first]), static_cast<const AcaBlock *>(d_blocks), static_cast<long long>(first), static_cast<long long>(last - first), static_cast<const double *>(d_tp),
+                              static_cast<const double *>(d_sp), gen->wavenumber, epsilon, fma_axpy, cf.pool, static_cast<int32_t *>(d_rank), st));
+            first = last;
+        }
+        HTB_CC(cudaEventRecord(ev1, st));
+        HTB_CC(cudaMemcpyAsync(rank.data(), d_rank, rank.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        HTB_CC(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        seconds_aca += ms * 1e-3;
+        bool overflow = false;
+        for (int32_t q : rank)
+            overflow = overflow || q == kAcaPoolOverflow;
+        if (!overflow)
+            break;
+        if (capacity >= std::min(full, pool_limit)) {
+            cleanup();
+            return fail(HTB_ERR_CUDA, "the factor pool of the device compression does not fit the device memory");
+        }
+    }
+
+    htb_compression_info ci{};
+    ci.nb_blocks  = static_cast<int64_t>(blocks.size());
+    ci.rank_min   = INT32_MAX;
+    ci.pool_bytes = static_cast<int64_t>(cf.pool.capacity * sizeof(double));
+    cf.leaves.assign(leaves.size(), AcaLeaf{0u, 0u, 0u, 0u});
+    for (size_t i = 0; i < blocks.size(); i++) {
+        const AcaBlock &b = blocks[i];
+        const int32_t q   = rank[i];
+        if (q == kAcaRankCap) {
+            cleanup();
+            return fail(HTB_ERR_UNSUPPORTED, "an admissible block needs more than " + std::to_string(kAcaMaxRank) + " terms at this epsilon: compress on the host");
+        }
+        if (q > 0) {
+            leaves[b.leaf].rank = q;
+            cf.leaves[b.leaf]   = AcaLeaf{b.term_base, static_cast<uint32_t>(b.swapped ? b.n : b.m), b.swapped, 0u};
+            ci.coefficients += int64_t(q) * (int64_t(b.m) + b.n);
+            ci.rank_min = std::min(ci.rank_min, q);
+            ci.rank_max = std::max(ci.rank_max, q);
+        } else { // the compression failed: a dense leaf, generated like the others (tree_builder.hpp:619-625)
+            leaves[b.leaf].rank = -1;
+            ci.nb_failed++;
+        }
+    }
+    if (ci.rank_min == INT32_MAX)
+        ci.rank_min = 0;
+    ci.seconds_aca = seconds_aca;
+    for (void **p : {&d_blocks, &d_tp, &d_sp, &d_rank}) { // (the store needs the room)
+        cudaFree(*p);
+        *p = nullptr;
+    }
+
+    htb_hmatrix_desc d2 = *desc;
+    d2.leaves           = leaves.data();
+    d2.device           = device;
+    int rc              = create_impl(&d2, gen, &cf, out);
+    cleanup();
+#undef HTB_CC
+    if (rc != HTB_OK)
+        return rc;
+    (*out)->leaf_ranks.resize(leaves.size());
+    for (size_t i = 0; i < leaves.size(); i++)
+        (*out)->leaf_ranks[i] = leaves[i].rank;
+    ci.seconds_total      = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+    (*out)->compression   = ci;
+    return HTB_OK;
+}
+
+int htb_get_leaf_ranks(htb_handle h, int32_t *ranks, int64_t nb_leaves) {
+    if (!h || !ranks)
+        return fail(HTB_ERR_INVALID, "null argument");
+    if (h->leaf_ranks.empty() && nb_leaves != 0)
+        return fail(HTB_ERR_INVALID, "the operator was not created by htb_create_compressed");
+    if (nb_leaves != static_cast<int64_t>(h->leaf_ranks.size()))
+        return fail(HTB_ERR_INVALID, "leaf count differs from the descriptor's");
+    std::copy(h->leaf_ranks.begin(), h->leaf_ranks.end(), ranks);
+    return HTB_OK;
+}
+
+int htb_get_compression_info(htb_handle h, htb_compression_info *info) {
+    if (!h || !info)
+        return fail(HTB_ERR_INVALID, "null argument");
+    *info = h->compression;
     return HTB_OK;
 }
 
@@ -1093,6 +1368,8 @@ int htb_pack_host(const htb_hmatrix_desc *desc, int side, htb_packed_side *out) 
         out->aux_apply     = own->layout.aux_apply.data();
         out->n_dense_tasks = static_cast<int64_t>(own->layout.dense_tasks.size());
         out->dense_tasks   = own->layout.dense_tasks.data();
+        out->n_lowrank_tasks = static_cast<int64_t>(own->layout.lr_tasks.size());
+        out->lowrank_tasks   = own->layout.lr_tasks.data();
     } catch (const std::exception &ex) {
         return fail(HTB_ERR_INVALID, ex.what());
     }

@@ -44,6 +44,8 @@ struct htb_operator {
     void *d_scratch      = nullptr;
     uint64_t scratch_elems = 0;
     // multi-RHS scratch ([TF | PARTM[0] | PARTM[1]] x vector stride), allocated at the first multi-RHS product
+    std::vector<int32_t> leaf_ranks;      // htb_create_compressed: ranks per leaf of the descriptor
+    htb_compression_info compression{};
     void *d_mscratch        = nullptr;
     void *d_mstage          = nullptr; // multi-RHS: the current column group of the input, rows padded to the B-ring stride
     size_t mstage_cap       = 0;

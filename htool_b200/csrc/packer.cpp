@@ -91,6 +91,8 @@ Packer::Packer(const htb_hmatrix_desc &desc, const PackOptions &o) : dtype(desc.
         if (l.nb_rows < 0 || l.nb_cols < 0 || l.row_offset < 0 || l.col_offset < 0 || l.row_offset + l.nb_rows > nb_rows || l.col_offset + l.nb_cols > nb_cols)
             throw std::runtime_error("leaf " + std::to_string(i) + " lies outside the root block");
         bool empty = l.nb_rows == 0 || l.nb_cols == 0;
+        if (l.rank < -1)
+            throw std::runtime_error("leaf " + std::to_string(i) + " is an admissible block still to be compressed (rank HTB_RANK_COMPRESS): use htb_create_compressed");
         if (l.rank < 0) {
             n_dense++;
             if (!empty && !l.data0 && !opt.generate_dense)
@@ -100,8 +102,8 @@ Packer::Packer(const htb_hmatrix_desc &desc, const PackOptions &o) : dtype(desc.
             coefficients += int64_t(l.nb_rows) * l.nb_cols;
         } else {
             n_lowrank++;
-            if (!empty && l.rank > 0 && (!l.data0 || !l.data1))
-                throw std::runtime_error("low-rank leaf without data");
+            if (!empty && l.rank > 0 && (!l.data0 || !l.data1) && !(opt.generate_dense && !l.data0 && !l.data1))
+                throw std::runtime_error("low-rank leaf without data"); // (both pointers null + a generator: factors in the device pool, aca.cu)
             rank_min = std::min(rank_min, l.rank);
             rank_max = std::max(rank_max, l.rank);
             coefficients += int64_t(l.rank) * (l.nb_rows + l.nb_cols);
@@ -487,7 +489,7 @@ void Packer::make_mtables() {
         // aux records (runs + column tables, store.hpp) of every block, concatenated below
         std::vector<std::vector<unsigned char>> aux_r(nb), aux_a(nb);
         std::vector<std::vector<uint32_t>> aux_len(nb); // per stage of the block, bytes
-        std::vector<std::vector<DenseTask>> tasks(nb);
+        std::vector<std::vector<DenseTask>> tasks(nb), lr_tasks(nb);
         bool aux_overflow = false;
 #pragma omp parallel for schedule(dynamic, 64)
         for (int b = 0; b < nb; b++) {
@@ -524,6 +526,11 @@ void Packer::make_mtables() {
                             tasks[b].push_back(DenseTask{sd.byte_off + cut.header_bytes() + static_cast<uint64_t>(eoff) * esize, l.row_offset, l.col_offset, static_cast<int32_t>(u.p0), static_cast<int32_t>(u.k0),
                                                          static_cast<uint16_t>(u.h), static_cast<uint16_t>(u.w), static_cast<uint16_t>(u.ld),
                                                          static_cast<uint16_t>(l.flags & (HTB_LEAF_DIAG_SYMMETRIC | HTB_LEAF_DIAG_HERMITIAN | HTB_LEAF_UPLO_UPPER))});
+                        }
+                        if (u.kind == UNIT_LOWRANK && !l.data0) { // factors in the device pool: the panel is copied on the device (aca.cu)
+                            const StageDesc &sd = side[s].stages[side[s].blocks[b].first_stage + aux_len[b].size()];
+                            lr_tasks[b].push_back(DenseTask{sd.byte_off + cut.header_bytes() + static_cast<uint64_t>(eoff) * esize, static_cast<int32_t>(u.leaf), s, static_cast<int32_t>(u.p0), static_cast<int32_t>(u.k0),
+                                                            static_cast<uint16_t>(u.h), static_cast<uint16_t>(u.w), static_cast<uint16_t>(u.ld), 0});
                         }
                         for (uint32_t k = 0; k < u.w; k++) {
                             col_out.push_back(out + k);
@@ -625,6 +632,7 @@ void Packer::make_mtables() {
                 side[s].aux_max_bytes = std::max(side[s].aux_max_bytes, aux_len[b][q]);
             }
             side[s].dense_tasks.insert(side[s].dense_tasks.end(), tasks[b].begin(), tasks[b].end());
+            side[s].lr_tasks.insert(side[s].lr_tasks.end(), lr_tasks[b].begin(), lr_tasks[b].end());
             at += aux_r[b].size();
             std::vector<unsigned char>().swap(aux_r[b]);
             std::vector<unsigned char>().swap(aux_a[b]);
@@ -774,7 +782,11 @@ void Packer::fill_block(int s, int b, char *dst) const {
                 continue;
             const htb_leaf &l = m_leaves[u.leaf];
             T *out            = data + eoff;
-            if (u.kind == UNIT_LOWRANK && s == 1) {
+            if (u.kind == UNIT_LOWRANK && !l.data0) {
+                // factors in the device pool (htb_create_compressed): the panel travels as zeros and is copied on the device
+                for (uint32_t k = 0; k < u.w; k++)
+                    std::memset(static_cast<void *>(out + static_cast<size_t>(k) * u.ld), 0, sizeof(T) * u.h);
+            } else if (u.kind == UNIT_LOWRANK && s == 1) {
                 // Vt panel: element (i, k) = V[k + (p0+i) * r], V is r x n column-major
                 const T *V     = static_cast<const T *>(l.data1);
                 const size_t r = static_cast<size_t>(l.rank);

@@ -232,6 +232,7 @@ struct SideLayout {
     std::vector<unsigned char> aux_reduce, aux_apply; // per-stage aux records (runs + column tables), same offsets in both
     uint32_t aux_max_bytes = 0;                        // largest aux record of the side: sizes the aux part of a ring slot
     std::vector<DenseTask> dense_tasks;               // side 0 only: dense units to generate on the device
+    std::vector<DenseTask> lr_tasks;                  // units of low-rank leaves whose factors live in the device pool (lrow = leaf index, lcol = side)
 };
 
 } // namespace htb

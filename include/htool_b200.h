@@ -160,6 +160,36 @@ typedef struct htb_generator_desc {
  * failed) and all low-rank leaves are packed from the host as usual. Symmetric / Hermitian diagonal leaves are rebuilt
  * from their UPLO triangle like host data. Real kernels reproduce compute_dense_data bit for bit. */
 int htb_create_generated(const htb_hmatrix_desc *desc, const htb_generator_desc *generator, htb_handle *out);
+/* ---- leaf assembly on the device (second step: the admissible blocks) -------------------------------- */
+
+/* rank of a leaf that is an ADMISSIBLE block still to be compressed (data0 == data1 == NULL): htb_create_compressed runs the
+ * reference's adaptive cross approximation on the device for all such leaves at once. */
+#define HTB_RANK_COMPRESS (-2)
+typedef struct htb_compression_info {
+    int64_t nb_blocks;          /* admissible blocks handed to the device                                             */
+    int64_t nb_failed;          /* of which stored as dense leaves ("false positives", tree_builder.hpp:619-625)      */
+    int64_t coefficients;       /* sum r (m + n) over the compressed blocks                                           */
+    int64_t pool_bytes;         /* device bytes of the factor pool while the store was built                          */
+    int32_t rank_min, rank_max; /* over the compressed blocks                                                         */
+    double seconds_aca;         /* the ACA kernels                                                                    */
+    double seconds_total;       /* the whole call (ACA + packing + upload + generation of the dense leaves + copies)  */
+} htb_compression_info;
+/* htb_create for an H-matrix whose block cluster tree is known but whose leaves hold NO coefficients: dense leaves
+ * (rank == -1, data0 == NULL) are generated as in htb_create_generated, admissible leaves (rank == HTB_RANK_COMPRESS) are
+ * compressed on the device by sympartialACA (include/htool/hmatrix/lrmat/sympartialACA.hpp:41-216, the reference's default
+ * compressor, tree_builder.hpp:385) with the reference's stopping criterion at `epsilon` — what
+ * HMatrixTreeBuilder::openmp_compute_blocks (tree_builder.hpp:604-666) does on the host: HMatrix::compute_low_rank_data
+ * (hmatrix.hpp:228-237) per admissible block, a dense leaf instead when the compression fails (:619-625). Pivots, ranks and
+ * factors are those of the reference (bit for bit for the real kernel functions when the host BLAS computes axpy with a
+ * rounded product and a rounded sum, as the OpenBLAS of this image does; option aca_fma_axpy = 1 for FMA builds). Leaves
+ * that carry data are packed from the host as usual. Real kernel functions (HTB_KERNEL_LAPLACE, HTB_KERNEL_LAPLACE_REG);
+ * HTB_ERR_UNSUPPORTED for the complex ones. */
+int htb_create_compressed(const htb_hmatrix_desc *desc, const htb_generator_desc *generator, double epsilon, htb_handle *out);
+/* Ranks the device found, in the order of the descriptor's leaves: the rank for compressed leaves, -1 for dense leaves
+ * (including admissible blocks whose compression failed), the descriptor's rank for leaves that carried data. */
+int htb_get_leaf_ranks(htb_handle h, int32_t *ranks, int64_t nb_leaves);
+int htb_get_compression_info(htb_handle h, htb_compression_info *info);
+
 /* Test / debug: copies the first `bytes` bytes of one side's packed stream (layout: htool_b200/csrc/store.hpp) back from
  * the device, e.g. to compare device-generated leaves with htb_pack_host of the host-generated ones. */
 int htb_download_store(htb_handle h, int side, void *dst, int64_t bytes);
@@ -302,6 +332,10 @@ typedef struct htb_packed_side {
     const void *aux_apply;    /* column entry = scratch vector (or input row | bit 31) the column multiplies in APPLY_M */
     int64_t n_dense_tasks;    /* side 0, option pack_generate_dense = 1: dense units of leaves without data0 (store.hpp: DenseTask, 32 B) */
     const void *dense_tasks;
+    int64_t n_lowrank_tasks;  /* either side, same option: units of low-rank leaves without data0 / data1 (their factors are in the
+                               * device pool of htb_create_compressed); DenseTask with lrow = leaf index, lcol = side, p0 = first row of
+                               * the panel inside the leaf's factor, k0 = first term */
+    const void *lowrank_tasks;
 } htb_packed_side;
 int htb_pack_host(const htb_hmatrix_desc *desc, int side, htb_packed_side *out);
 int htb_pack_free(htb_packed_side *packed);
