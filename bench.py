@@ -601,7 +601,9 @@ def section_device_assembly(w: Workload, y_host_packed, x_global):
     op.close()
     info = case.info()
     out = {"admissible_blocks_compressed_on_device": ci["nb_blocks"], "compression_failures": ci["nb_failed"], "coefficients_of_the_factors": ci["coefficients"],
-           "rank_min": ci["rank_min"], "rank_max": ci["rank_max"], "aca_kernel_seconds": ci["seconds_aca"], "factor_pool_bytes": ci["pool_bytes"],
+           "rank_min": ci["rank_min"], "rank_max": ci["rank_max"], "aca_kernel_seconds": ci["seconds_aca"], "aca_kernel_seconds_by_team_512_128_32": ci["seconds_aca_team"], "blocks_by_team_512_128_32": ci["nb_blocks_team"],
+           "prepare_seconds_host": ci["seconds_prepare"], "compress_seconds": ci["seconds_compress"], "store_seconds": ci["seconds_store"], "c_call_seconds": ci["seconds_total"],
+           "layout_seconds_host": ci["seconds_layout"], "upload_seconds": ci["seconds_upload"], "device_fill_seconds": ci["seconds_fill"], "factor_pool_bytes": ci["pool_bytes"],
            "create_seconds_device_assembly": t_create, "reference_host_assembly_seconds": info["build_seconds"], "reference_host_threads": info["omp_threads"],
            "create_seconds_host_packed": w.t_upload, "leaves_with_the_reference_rank": int((ranks == ref_rank).sum()), "leaves": int(len(ranks)),
            "product_bit_identical_to_host_assembled_operator": bool(np.array_equal(y, y_host_packed)),

@@ -116,6 +116,8 @@ class htb_packed_side(C.Structure):
         ("dense_tasks", C.c_void_p),
         ("n_lowrank_tasks", C.c_int64),
         ("lowrank_tasks", C.c_void_p),
+        ("ld_pad_rows", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -125,10 +127,12 @@ class htb_generator_desc(C.Structure):
 
 class htb_compression_info(C.Structure):
     _fields_ = [("nb_blocks", C.c_int64), ("nb_failed", C.c_int64), ("coefficients", C.c_int64), ("pool_bytes", C.c_int64), ("rank_min", C.c_int32), ("rank_max", C.c_int32),
-                ("seconds_aca", C.c_double), ("seconds_total", C.c_double)]
+                ("seconds_aca", C.c_double), ("seconds_total", C.c_double), ("seconds_aca_team", C.c_double * 3), ("nb_blocks_team", C.c_int64 * 3),
+                ("seconds_layout", C.c_double), ("seconds_upload", C.c_double), ("seconds_fill", C.c_double), ("seconds_prepare", C.c_double),
+                ("seconds_compress", C.c_double), ("seconds_store", C.c_double)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        return {k: (list(getattr(self, k)) if hasattr(getattr(self, k), "__len__") else getattr(self, k)) for k, _ in self._fields_}
 
 
 HTB_RANK_COMPRESS = -2

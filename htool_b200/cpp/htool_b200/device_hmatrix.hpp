@@ -11,6 +11,7 @@
 
 #include "flatten.hpp"
 #include <htool/hmatrix/interfaces/virtual_dense_blocks_generator.hpp>
+#include <htool/hmatrix/interfaces/virtual_lrmat_generator.hpp>
 #include <htool/misc/logger.hpp>
 #include <string>
 #include <unordered_set>
@@ -71,6 +72,25 @@ class DeviceDenseBlocks final : public htool::VirtualDenseBlocksGenerator<Coeffi
     std::size_t size() const { return m_blocks.size(); }
 };
 
+/// Leaf assembly on the device, second step. Plugged into the reference's builder with
+/// HMatrixTreeBuilder::set_low_rank_generator (hmatrix/tree_builder/tree_builder.hpp:251) in place of the default
+/// sympartialACA (tree_builder.hpp:385), it receives the builder's call for every admissible block
+/// (HMatrix::compute_low_rank_data, hmatrix.hpp:228-237) and computes nothing: it reports success and leaves the factors
+/// empty. A DeviceHMatrix built with it (constructor below) compresses those blocks on the GPU with the reference's own
+/// algorithm and stopping criterion (htb_create_compressed); blocks whose compression fails become dense leaves of the
+/// device store, as in tree_builder.hpp:619-625. The host H-matrix then holds rank-0 leaves: use it for assembly only.
+/// A required rank (reqrank > 0) is not supported on the device: the call reports a failure and the builder computes the
+/// block as a dense leaf on the host, which is what the reference does with any failed compression.
+template <typename CoefficientPrecision>
+class DeviceLowRankBlocks final : public htool::VirtualInternalLowRankGenerator<CoefficientPrecision> {
+  public:
+    bool copy_low_rank_approximation(int, int, int, int, htool::LowRankMatrix<CoefficientPrecision> &) const override { return true; }
+    bool copy_low_rank_approximation(int, int, int, int, int, htool::LowRankMatrix<CoefficientPrecision> &) const override {
+        htool::Logger::get_instance().log(htool::LogLevel::WARNING, "[htool_b200] a required rank is not supported by the device compression: dense block instead"); // LCOV_EXCL_LINE
+        return false;
+    }
+};
+
 /// A built-in kernel function (htb_generator_desc) with the geometry in USER numbering, as a VirtualGenerator sees it.
 struct BuiltinKernel {
     int kernel        = HTB_KERNEL_LAPLACE_REG;
@@ -85,6 +105,7 @@ template <typename CoefficientPrecision, typename CoordinatePrecision = htool::u
 class DeviceHMatrix {
     htb_handle m_handle = nullptr;
     int m_nb_rows = 0, m_nb_cols = 0, m_target_offset = 0, m_source_offset = 0;
+    int64_t m_nb_leaves = 0;
 
   public:
     explicit DeviceHMatrix(const htool::HMatrix<CoefficientPrecision, CoordinatePrecision> &hmatrix, int device = -1) {
@@ -119,7 +140,29 @@ class DeviceHMatrix {
     /// dense leaves hold no coefficients; they are generated on the GPU from `kernel` (htb_create_generated). Low-rank
     /// leaves (and admissible blocks whose compression failed) are packed from the host as usual.
     DeviceHMatrix(const htool::HMatrix<CoefficientPrecision, CoordinatePrecision> &hmatrix, const DeviceDenseBlocks<CoefficientPrecision> &deferred, const BuiltinKernel &kernel, int device = -1) {
-        FlatHMatrix flat = flatten(hmatrix, device, &deferred.deferred());
+        assemble_on_device(hmatrix, deferred, kernel, false, device);
+    }
+    /// Device-side assembly of ALL the leaves: `hmatrix` was built with `deferred` as its dense-blocks generator and a
+    /// DeviceLowRankBlocks as its low-rank generator, so it is a block cluster tree without coefficients. The admissible
+    /// blocks are compressed on the GPU by the reference's sympartialACA at the builder's epsilon, the dense leaves are
+    /// generated (htb_create_compressed). Real built-in kernel functions.
+    DeviceHMatrix(const htool::HMatrix<CoefficientPrecision, CoordinatePrecision> &hmatrix, const DeviceDenseBlocks<CoefficientPrecision> &deferred, const DeviceLowRankBlocks<CoefficientPrecision> &, const BuiltinKernel &kernel, int device = -1) {
+        assemble_on_device(hmatrix, deferred, kernel, true, device);
+    }
+    /// Ranks found by the device compression, in the order of htool::get_leaves_from (-1: dense leaf).
+    std::vector<int32_t> leaf_ranks() const {
+        std::vector<int32_t> r(static_cast<std::size_t>(m_nb_leaves));
+        if (!m_handle || !check(htb_get_leaf_ranks(m_handle, r.data(), m_nb_leaves), "htb_get_leaf_ranks")) {
+            r.clear();
+        }
+        return r;
+    }
+
+  private:
+    void assemble_on_device(const htool::HMatrix<CoefficientPrecision, CoordinatePrecision> &hmatrix, const DeviceDenseBlocks<CoefficientPrecision> &deferred, const BuiltinKernel &kernel, bool compress, int device) {
+        double epsilon   = -1.;
+        FlatHMatrix flat = flatten(hmatrix, device, &deferred.deferred(), compress, &epsilon);
+        m_nb_leaves      = flat.desc.nb_leaves;
         m_nb_rows        = flat.desc.nb_rows;
         m_nb_cols        = flat.desc.nb_cols;
         m_target_offset  = flat.desc.row_offset;
@@ -144,13 +187,16 @@ class DeviceHMatrix {
         gen.wavenumber        = kernel.wavenumber;
         gen.target_points     = tpts.data();
         gen.source_points     = spts.data();
-        if (!check(htb_create_generated(&flat.desc, &gen, &m_handle), "htb_create_generated")) {
+        const bool ok = compress && epsilon > 0. ? check(htb_create_compressed(&flat.desc, &gen, epsilon, &m_handle), "htb_create_compressed") : check(htb_create_generated(&flat.desc, &gen, &m_handle), "htb_create_generated");
+        if (!ok) {
             m_handle = nullptr;
         }
     }
+
+  public:
     DeviceHMatrix(const DeviceHMatrix &)            = delete;
     DeviceHMatrix &operator=(const DeviceHMatrix &) = delete;
-    DeviceHMatrix(DeviceHMatrix &&o) noexcept : m_handle(o.m_handle), m_nb_rows(o.m_nb_rows), m_nb_cols(o.m_nb_cols), m_target_offset(o.m_target_offset), m_source_offset(o.m_source_offset) { o.m_handle = nullptr; }
+    DeviceHMatrix(DeviceHMatrix &&o) noexcept : m_handle(o.m_handle), m_nb_rows(o.m_nb_rows), m_nb_cols(o.m_nb_cols), m_target_offset(o.m_target_offset), m_source_offset(o.m_source_offset), m_nb_leaves(o.m_nb_leaves) { o.m_handle = nullptr; }
     DeviceHMatrix &operator=(DeviceHMatrix &&o) noexcept {
         if (this != &o) {
             if (m_handle) {
@@ -161,6 +207,7 @@ class DeviceHMatrix {
             m_nb_cols       = o.m_nb_cols;
             m_target_offset = o.m_target_offset;
             m_source_offset = o.m_source_offset;
+            m_nb_leaves     = o.m_nb_leaves;
             o.m_handle      = nullptr;
         }
         return *this;

@@ -36,8 +36,11 @@ struct FlatHMatrix {
 
 /// `deferred_dense` (optional): dense blocks whose coefficients were NOT computed on the host (DeviceDenseBlocks below,
 /// device_hmatrix.hpp); their leaves get data0 = nullptr and are generated on the device by htb_create_generated.
+/// `compress_on_device`: the low-rank leaves were "computed" by DeviceLowRankBlocks (device_hmatrix.hpp), i.e. not at all: they
+/// get rank = HTB_RANK_COMPRESS and no data, and are compressed on the device by htb_create_compressed; `epsilon_out` receives
+/// the tolerance the builder gave them (LowRankMatrix::get_epsilon, what sympartialACA reads, sympartialACA.hpp:32).
 template <typename CoefficientPrecision, typename CoordinatePrecision = htool::underlying_type<CoefficientPrecision>>
-FlatHMatrix flatten(const htool::HMatrix<CoefficientPrecision, CoordinatePrecision> &hmatrix, int device = -1, const std::unordered_set<const void *> *deferred_dense = nullptr) {
+FlatHMatrix flatten(const htool::HMatrix<CoefficientPrecision, CoordinatePrecision> &hmatrix, int device = -1, const std::unordered_set<const void *> *deferred_dense = nullptr, bool compress_on_device = false, double *epsilon_out = nullptr) {
     using HMatrixType = htool::HMatrix<CoefficientPrecision, CoordinatePrecision>;
     FlatHMatrix flat;
 
@@ -81,6 +84,14 @@ FlatHMatrix flatten(const htool::HMatrix<CoefficientPrecision, CoordinatePrecisi
             d.rank            = lrmat->rank_of();
             d.data0           = lrmat->get_U().data();
             d.data1           = lrmat->get_V().data();
+            if (compress_on_device && d.rank == 0) {
+                d.rank  = HTB_RANK_COMPRESS;
+                d.data0 = nullptr;
+                d.data1 = nullptr;
+                if (epsilon_out != nullptr) {
+                    *epsilon_out = static_cast<double>(lrmat->get_epsilon());
+                }
+            }
         } else {
             continue; // a childless hierarchical node holds no data and contributes nothing
         }

@@ -98,9 +98,35 @@ __device__ __forceinline__ void team_sync() {
         __syncthreads();
 }
 
+// The reference's error estimator for the term (uq, vq) that follows q - 1 accepted terms (sympartialACA.hpp:156-168): 2 q dot
+// products in index order, one THREAD each (they are independent), then aux = |<u,u>| |<v,v>| and
+// frob += aux + 2 sum_j <v, vv_j> <u, uu_j> accumulated in term order. Every thread returns the same values.
+template <int TS>
+__device__ __forceinline__ void in_order_estimator(int q, const double *uq, const double *vq, int n1, int n2, const double *pool, const uint32_t *s_off, double *s_dot, int tid, double &aux, double &frob) {
+    const int ndots = 2 * q;
+    for (int t = tid; t < ndots; t += TS) {
+        double d;
+        if (t == 0)
+            d = dot_in_order(uq, uq, n1);
+        else if (t == 1)
+            d = dot_in_order(vq, vq, n2);
+        else {
+            const double *ch = pool + 2ull * s_off[(t - 2) >> 1];
+            d                = (t & 1) ? dot_in_order(uq, ch, n1) : dot_in_order(vq, ch + n1, n2);
+        }
+        s_dot[t] = d;
+    }
+    team_sync<TS>();
+    aux             = __dmul_rn(fabs(s_dot[0]), fabs(s_dot[1]));
+    double frob_aux = 0.;
+    for (int j = 0; j < q - 1; j++)
+        frob_aux = __dadd_rn(frob_aux, __dmul_rn(s_dot[2 + 2 * j], s_dot[3 + 2 * j]));
+    frob = __dadd_rn(frob, __dadd_rn(aux, __dmul_rn(2., frob_aux)));
+}
+
 template <int TS, int KERNEL, bool FMA>
-__global__ void __launch_bounds__(TS) aca_kernel(const AcaBlock *__restrict__ blocks, long long first, const double *__restrict__ tp, const double *__restrict__ sp, double wavenumber, double epsilon, AcaPool pool,
-                                                 int32_t *__restrict__ rank_out) {
+__global__ void __launch_bounds__(TS, TS == 512 ? 2 : (TS == 128 ? 8 : 28)) aca_kernel(const AcaBlock *__restrict__ blocks, long long first, const double *__restrict__ tp, const double *__restrict__ sp, double wavenumber, double epsilon, AcaPool pool,
+                                                 int32_t *__restrict__ rank_out, int dots_mode) {
     __shared__ uint32_t s_off[kAcaMaxRank];
     __shared__ int s_piv1[kAcaMaxRank], s_piv2[kAcaMaxRank];
     __shared__ double s_dot[2 * kAcaMaxRank + 2];
@@ -119,7 +145,9 @@ __global__ void __launch_bounds__(TS) aca_kernel(const AcaBlock *__restrict__ bl
     // (sympartialACA.hpp:69-92) every thread carries the same copy of the scalar state
     int q = 0, I1 = 0, I2 = 0, nv1 = 0, nv2 = 0;
     double frob = 0., aux = 0.;
-    while (q == 0 || __dsqrt_rn(__ddiv_rn(aux, frob)) > epsilon) { // :97
+    double frob_fast = 0.;   // running Frobenius estimate of the guarded fast path (below)
+    bool go_on       = true; // the reference's loop condition (:97), decided at the end of the iteration
+    while (go_on) {
         q += 1;
         if (static_cast<long long>(q) * (static_cast<long long>(n1) + n2) > static_cast<long long>(n1) * n2) { // :102: the next rank would not be advantageous
             q = kAcaFailed;
@@ -213,26 +241,68 @@ __global__ void __launch_bounds__(TS) aca_kernel(const AcaBlock *__restrict__ bl
         nv2++;
         team_sync<TS>();
 
-        // error estimator (:156-168): 2 q dot products, one thread each, every one in index order
-        const int ndots = 2 * q;
-        for (int t = tid; t < ndots; t += TS) {
-            double d;
-            if (t == 0)
-                d = dot_in_order(uq, uq, n1);
-            else if (t == 1)
-                d = dot_in_order(vq, vq, n2);
-            else {
-                const double *ch = pool.pool + 2ull * s_off[(t - 2) >> 1];
-                d                = (t & 1) ? dot_in_order(uq, ch, n1) : dot_in_order(vq, ch + n1, n2);
+        // error estimator (:156-168)
+        if (TS == 32 || dots_mode == 1) {
+            // the reference's arithmetic: 2 q dot products, one thread each, every one in index order
+            in_order_estimator<TS>(q, uq, vq, n1, n2, pool.pool, s_off, s_dot, tid, aux, frob);
+            go_on = __dsqrt_rn(__ddiv_rn(aux, frob)) > epsilon;
+        } else {
+            // Large blocks: an in-order dot product is ONE serial chain of n additions and the rest of the team waits for
+            // it at the barrier (ncu: 5 % issue-active, 134 barrier stalls per issue). The dot products only feed the
+            // STOPPING DECISION sqrt(aux / frob) > epsilon — the factors do not depend on them — so the decision is taken
+            // from dot products computed by whole warps (lane-strided FMA partial sums + shuffle reduction): they differ
+            // from the in-order sums by <= (n / 32 + 5) u |x|.|y|, i.e. the ratio by well under 1e-8 relative for
+            // any block the kernel accepts (q <= 128, n <= 2^31). Whenever the fast ratio lies within kGuard (1e-6,
+            // relative) of epsilon, or is not finite, the decision is taken instead from the reference's own arithmetic,
+            // replayed in order from the first term (rare: the ratio falls by ~10x per iteration). Same ranks as the
+            // reference, provably; dots_mode 2 (tests) forces the replay at every iteration.
+            constexpr int W = TS / 32;
+            const int w = tid >> 5, ln = tid & 31;
+            const int ndots = 2 * q;
+            for (int t = w; t < ndots; t += W) {
+                const double *x, *y;
+                int len;
+                if (t == 0)
+                    x = uq, y = uq, len = n1;
+                else if (t == 1)
+                    x = vq, y = vq, len = n2;
+                else {
+                    const double *ch = pool.pool + 2ull * s_off[(t - 2) >> 1];
+                    if (t & 1)
+                        x = uq, y = ch, len = n1;
+                    else
+                        x = vq, y = ch + n1, len = n2;
+                }
+                double sum = 0.;
+                for (int i = ln; i < len; i += 32)
+                    sum = fma(x[i], y[i], sum);
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1)
+                    sum += __shfl_xor_sync(0xffffffffu, sum, d);
+                if (ln == 0)
+                    s_dot[t] = sum;
             }
-            s_dot[t] = d;
+            team_sync<TS>();
+            const double aux_fast = fabs(s_dot[0]) * fabs(s_dot[1]);
+            double cross          = 0.;
+            for (int j = 0; j < q - 1; j++)
+                cross += s_dot[2 + 2 * j] * s_dot[3 + 2 * j];
+            frob_fast += aux_fast + 2. * cross;
+            const double ratio = sqrt(aux_fast / frob_fast);
+            constexpr double kGuard = 1e-6;
+            const bool sure = dots_mode != 2 && isfinite(ratio) && fabs(ratio - epsilon) > kGuard * epsilon; // (uniform: every thread reads the same s_dot)
+            if (sure)
+                go_on = ratio > epsilon;
+            else {
+                aux = frob = 0.;
+                for (int t1 = 1; t1 <= q; t1++) {
+                    const double *ut = pool.pool + 2ull * s_off[t1 - 1];
+                    team_sync<TS>();
+                    in_order_estimator<TS>(t1, ut, ut + n1, n1, n2, pool.pool, s_off, s_dot, tid, aux, frob);
+                }
+                go_on = __dsqrt_rn(__ddiv_rn(aux, frob)) > epsilon;
+            }
         }
-        team_sync<TS>();
-        aux             = __dmul_rn(fabs(s_dot[0]), fabs(s_dot[1]));
-        double frob_aux = 0.;
-        for (int j = 0; j < q - 1; j++)
-            frob_aux = __dadd_rn(frob_aux, __dmul_rn(s_dot[2 + 2 * j], s_dot[3 + 2 * j]));
-        frob = __dadd_rn(frob, __dadd_rn(aux, __dmul_rn(2., frob_aux)));
     }
     team_sync<TS>();
     for (int j = tid; j < q; j += TS) // (q <= 0: nothing)
@@ -261,21 +331,21 @@ __global__ void scatter_lowrank_kernel(const DenseTask *tasks, long long n_tasks
 }
 
 template <int TS, int KERNEL>
-cudaError_t launch_team(const AcaBlock *blocks, long long first, long long count, const double *tp, const double *sp, double wavenumber, double epsilon, int fma_axpy, AcaPool pool, int32_t *rank, cudaStream_t st) {
+cudaError_t launch_team(const AcaBlock *blocks, long long first, long long count, const double *tp, const double *sp, double wavenumber, double epsilon, int fma_axpy, AcaPool pool, int32_t *rank, int dots_mode, cudaStream_t st) {
     const unsigned grid = static_cast<unsigned>(count);
     if (fma_axpy)
-        aca_kernel<TS, KERNEL, true><<<grid, TS, 0, st>>>(blocks, first, tp, sp, wavenumber, epsilon, pool, rank);
+        aca_kernel<TS, KERNEL, true><<<grid, TS, 0, st>>>(blocks, first, tp, sp, wavenumber, epsilon, pool, rank, dots_mode);
     else
-        aca_kernel<TS, KERNEL, false><<<grid, TS, 0, st>>>(blocks, first, tp, sp, wavenumber, epsilon, pool, rank);
+        aca_kernel<TS, KERNEL, false><<<grid, TS, 0, st>>>(blocks, first, tp, sp, wavenumber, epsilon, pool, rank, dots_mode);
     return cudaGetLastError();
 }
 
 template <int KERNEL>
-cudaError_t launch_kernel(int team, const AcaBlock *blocks, long long first, long long count, const double *tp, const double *sp, double wavenumber, double epsilon, int fma_axpy, AcaPool pool, int32_t *rank, cudaStream_t st) {
+cudaError_t launch_kernel(int team, const AcaBlock *blocks, long long first, long long count, const double *tp, const double *sp, double wavenumber, double epsilon, int fma_axpy, AcaPool pool, int32_t *rank, int dots_mode, cudaStream_t st) {
     switch (team) {
-    case 32: return launch_team<32, KERNEL>(blocks, first, count, tp, sp, wavenumber, epsilon, fma_axpy, pool, rank, st);
-    case 128: return launch_team<128, KERNEL>(blocks, first, count, tp, sp, wavenumber, epsilon, fma_axpy, pool, rank, st);
-    case 512: return launch_team<512, KERNEL>(blocks, first, count, tp, sp, wavenumber, epsilon, fma_axpy, pool, rank, st);
+    case 32: return launch_team<32, KERNEL>(blocks, first, count, tp, sp, wavenumber, epsilon, fma_axpy, pool, rank, dots_mode, st);
+    case 128: return launch_team<128, KERNEL>(blocks, first, count, tp, sp, wavenumber, epsilon, fma_axpy, pool, rank, dots_mode, st);
+    case 512: return launch_team<512, KERNEL>(blocks, first, count, tp, sp, wavenumber, epsilon, fma_axpy, pool, rank, dots_mode, st);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -283,14 +353,14 @@ cudaError_t launch_kernel(int team, const AcaBlock *blocks, long long first, lon
 } // namespace
 
 cudaError_t launch_aca(int kernel, int team, const AcaBlock *blocks, long long first, long long count, const double *target_points, const double *source_points, double wavenumber, double epsilon, int fma_axpy, AcaPool pool,
-                       int32_t *rank, cudaStream_t st) {
+                       int32_t *rank, int dots_mode, cudaStream_t st) {
     if (count <= 0)
         return cudaSuccess;
     if (count > 0x7fffffffll)
         return cudaErrorInvalidValue;
     switch (kernel) { // (real kernel functions; the complex ones keep the host compressor)
-    case HTB_KERNEL_LAPLACE: return launch_kernel<HTB_KERNEL_LAPLACE>(team, blocks, first, count, target_points, source_points, wavenumber, epsilon, fma_axpy, pool, rank, st);
-    case HTB_KERNEL_LAPLACE_REG: return launch_kernel<HTB_KERNEL_LAPLACE_REG>(team, blocks, first, count, target_points, source_points, wavenumber, epsilon, fma_axpy, pool, rank, st);
+    case HTB_KERNEL_LAPLACE: return launch_kernel<HTB_KERNEL_LAPLACE>(team, blocks, first, count, target_points, source_points, wavenumber, epsilon, fma_axpy, pool, rank, dots_mode, st);
+    case HTB_KERNEL_LAPLACE_REG: return launch_kernel<HTB_KERNEL_LAPLACE_REG>(team, blocks, first, count, target_points, source_points, wavenumber, epsilon, fma_axpy, pool, rank, dots_mode, st);
     default: return cudaErrorInvalidValue;
     }
 }

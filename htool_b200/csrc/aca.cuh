@@ -40,8 +40,11 @@ struct AcaPool {
 // Compresses blocks [first, first + count) with teams of `team` threads (32, 128 or 512) — one CTA per block.
 // fma_axpy: the residual updates u -= c * v use one fused multiply-add (an FMA BLAS on the host) instead of a rounded
 // product followed by a rounded sum (the SSE2 daxpy of the OpenBLAS this image carries).
+// dots_mode: how the stopping criterion's dot products are computed by the teams of 128 / 512 threads — 0: by whole warps, with the
+// in-order replay whenever the decision is close (aca.cu), 1: always in order (the reference's arithmetic, one thread per dot
+// product), 2: warps + the replay at every iteration (tests). Teams of 32 threads always work in order.
 cudaError_t launch_aca(int kernel, int team, const AcaBlock *blocks, long long first, long long count, const double *target_points, const double *source_points, double wavenumber, double epsilon, int fma_axpy, AcaPool pool,
-                       int32_t *rank, cudaStream_t st);
+                       int32_t *rank, int dots_mode, cudaStream_t st);
 
 // Per leaf of the descriptor: where its factors are (LowRankTask.leaf indexes this table).
 struct AcaLeaf {

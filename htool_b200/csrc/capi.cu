@@ -32,7 +32,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 namespace {
 std::mutex g_option_mutex;
 std::map<std::string, int64_t> g_options = {
-    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 4096}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 0}, {"m_b_ring_log2", 3}, {"m_reduce_ring_stages", 0}, {"mrhs_min", 0}, {"pack_generate_dense", 0}, {"sort_units", 1}, {"reduce_blocks_per_cta", 0}, {"m_reduce_warps", 24}, {"m_pad", 4}, {"m_b_producers", 3}, {"m_stage_input", 1}, {"m_small_runs", 1}, {"m_reduce_split", 1}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}, {"aca_fma_axpy", 0}, {"aca_rank_guess", 16}};
+    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 4096}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 0}, {"m_b_ring_log2", 3}, {"m_reduce_ring_stages", 0}, {"mrhs_min", 0}, {"pack_generate_dense", 0}, {"sort_units", 1}, {"reduce_blocks_per_cta", 0}, {"m_reduce_warps", 24}, {"m_pad", 4}, {"m_b_producers", 3}, {"m_stage_input", 1}, {"m_small_runs", 1}, {"m_reduce_split", 1}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}, {"aca_fma_axpy", 0}, {"aca_rank_guess", 16}, {"aca_dots", 0}, {"ld_pad_rows", 0}};
 
 int64_t option(const char *key) {
     std::lock_guard<std::mutex> lock(g_option_mutex);
@@ -771,6 +771,7 @@ static int create_impl(const htb_hmatrix_desc *desc, const htb_generator_desc *g
     popt.generate_dense = gen != nullptr;
     popt.sort_units     = static_cast<int>(option("sort_units"));
     popt.block_rows  = static_cast<int>(option("block_rows"));
+    popt.ld_pad_rows = static_cast<int>(option("ld_pad_rows"));
     popt.piece_cols  = static_cast<int>(option("piece_cols"));
     popt.stage_bytes = static_cast<int>(option("stage_bytes"));
     popt.cseg_bytes  = static_cast<int>(option("cseg_bytes"));
@@ -784,11 +785,13 @@ static int create_impl(const htb_hmatrix_desc *desc, const htb_generator_desc *g
             popt.cta_slots = static_cast<int>(option("cta_slots"));
     }
     std::unique_ptr<Packer> pk;
+    const auto t_layout = std::chrono::steady_clock::now();
     try {
         pk = std::make_unique<Packer>(*desc, popt);
     } catch (const std::exception &ex) {
         return fail(HTB_ERR_INVALID, ex.what());
     }
+    const double seconds_layout = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_layout).count();
 
     DeviceGuard guard(device);
     if (!guard.ok)
@@ -805,6 +808,7 @@ static int create_impl(const htb_hmatrix_desc *desc, const htb_generator_desc *g
     h->uplo           = desc->uplo_for_leaves ? desc->uplo_for_leaves : 'N';
     h->scratch_elems  = pk->scratch_elems;
     h->launch_cfg.block_rows  = pk->opt.block_rows; // resolved (0 = automatic)
+    h->launch_cfg.ld_pad_rows = pk->opt.ld_pad_rows;
     h->launch_cfg.stage_bytes = popt.stage_bytes;
     h->launch_cfg.cseg_bytes  = popt.cseg_bytes;
     h->launch_cfg.ring_stages        = static_cast<int>(option("ring_stages"));
@@ -852,11 +856,16 @@ static int create_impl(const htb_hmatrix_desc *desc, const htb_generator_desc *g
     HTB_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
 
-    int rc = upload_store(h.get(), *pk);
+    const auto t_upload = std::chrono::steady_clock::now();
+    int rc              = upload_store(h.get(), *pk);
+    const auto t_fill   = std::chrono::steady_clock::now();
     if (rc == HTB_OK && gen)
         rc = generate_dense(h.get(), *pk, gen);
     if (rc == HTB_OK && factors)
         rc = scatter_lowrank(h.get(), *pk, *factors);
+    h->create_seconds[0] = seconds_layout;
+    h->create_seconds[1] = std::chrono::duration<double>(t_fill - t_upload).count();
+    h->create_seconds[2] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_fill).count();
     if (rc != HTB_OK) {
         htb_destroy(h.release());
         return rc;
@@ -980,7 +989,10 @@ int htb_create_compressed(const htb_hmatrix_desc *desc, const htb_generator_desc
     CompressedFactors cf;
     void *d_blocks = nullptr, *d_tp = nullptr, *d_sp = nullptr, *d_rank = nullptr;
     cudaStream_t st = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_class[3] = {nullptr, nullptr, nullptr};
+    int class_slot[3]       = {0, 0, 0};
+    double seconds_team[3]  = {0., 0., 0.};
+    int64_t blocks_team[3]  = {0, 0, 0};
     auto cleanup = [&]() {
         for (void *p : {d_blocks, d_tp, d_sp, d_rank, static_cast<void *>(cf.pool.pool), static_cast<void *>(cf.pool.cursor), static_cast<void *>(cf.pool.term_off)})
             if (p)
@@ -989,6 +1001,9 @@ int htb_create_compressed(const htb_hmatrix_desc *desc, const htb_generator_desc
             cudaEventDestroy(ev0);
         if (ev1)
             cudaEventDestroy(ev1);
+        for (cudaEvent_t ev : ev_class)
+            if (ev)
+                cudaEventDestroy(ev);
         if (st)
             cudaStreamDestroy(st);
     };
@@ -1004,6 +1019,8 @@ int htb_create_compressed(const htb_hmatrix_desc *desc, const htb_generator_desc
     HTB_CC(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     HTB_CC(cudaEventCreate(&ev0));
     HTB_CC(cudaEventCreate(&ev1));
+    for (cudaEvent_t &ev : ev_class)
+        HTB_CC(cudaEventCreate(&ev));
     HTB_CC(cudaMalloc(&d_blocks, blocks.size() * sizeof(AcaBlock)));
     HTB_CC(cudaMalloc(&d_rank, blocks.size() * sizeof(int32_t)));
     HTB_CC(cudaMalloc(&d_tp, std::max<size_t>(8, tpb)));
@@ -1014,6 +1031,7 @@ int htb_create_compressed(const htb_hmatrix_desc *desc, const htb_generator_desc
     HTB_CC(cudaMemcpyAsync(d_tp, gen->target_points, tpb, cudaMemcpyHostToDevice, st));
     HTB_CC(cudaMemcpyAsync(d_sp, gen->source_points, spb, cudaMemcpyHostToDevice, st));
 
+    const auto t_prepared = std::chrono::steady_clock::now();
     // The factor pool. The ranks are unknown before the compression: the pool is sized for `guess` terms per block (never
     // more than a block can hold) and the whole batch is repeated with twice the guess when it overflows.
     size_t free_bytes = 0, total_bytes = 0;
@@ -1021,7 +1039,8 @@ int htb_create_compressed(const htb_hmatrix_desc *desc, const htb_generator_desc
     const uint64_t pool_limit = std::min<uint64_t>(uint64_t(1) << 33, static_cast<uint64_t>(free_bytes * 0.45) / sizeof(double)); // (term offsets are stored in 16-byte units, 32 bits)
     std::vector<int32_t> rank(blocks.size());
     double seconds_aca = 0.;
-    const int fma_axpy = option("aca_fma_axpy") != 0;
+    const int fma_axpy  = option("aca_fma_axpy") != 0;
+    const int dots_mode = static_cast<int>(option("aca_dots"));
     for (int64_t guess = std::max<int64_t>(1, option("aca_rank_guess"));; guess *= 2) {
         uint64_t want = 0, full = 0;
         for (const AcaBlock &b : blocks) {
@@ -1037,12 +1056,17 @@ int htb_create_compressed(const htb_hmatrix_desc *desc, const htb_generator_desc
         cf.pool.capacity = capacity;
         HTB_CC(cudaMemsetAsync(cf.pool.cursor, 0, sizeof(unsigned long long), st));
         HTB_CC(cudaEventRecord(ev0, st));
+        int n_class = 0;
         for (size_t first = 0; first < blocks.size();) { // one launch per size class
             size_t last = first;
             while (last < blocks.size() && team_of(blocks[last]) == team_of(blocks[first]))
                 last++;
             HTB_CC(launch_aca(gen->kernel, team_of(blocks[first]), static_cast<const AcaBlock *>(d_blocks), static_cast<long long>(first), static_cast<long long>(last - first), static_cast<const double *>(d_tp),
-                              static_cast<const double *>(d_sp), gen->wavenumber, epsilon, fma_axpy, cf.pool, static_cast<int32_t *>(d_rank), st));
+                              static_cast<const double *>(d_sp), gen->wavenumber, epsilon, fma_axpy, cf.pool, static_cast<int32_t *>(d_rank), dots_mode, st));
+            const int slot = team_of(blocks[first]) == 512 ? 0 : (team_of(blocks[first]) == 128 ? 1 : 2);
+            HTB_CC(cudaEventRecord(ev_class[n_class], st));
+            class_slot[n_class++] = slot;
+            blocks_team[slot]     = static_cast<int64_t>(last - first);
             first = last;
         }
         HTB_CC(cudaEventRecord(ev1, st));
@@ -1051,6 +1075,10 @@ int htb_create_compressed(const htb_hmatrix_desc *desc, const htb_generator_desc
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ev0, ev1);
         seconds_aca += ms * 1e-3;
+        for (int c = 0; c < n_class; c++) {
+            cudaEventElapsedTime(&ms, c == 0 ? ev0 : ev_class[c - 1], ev_class[c]);
+            seconds_team[class_slot[c]] = ms * 1e-3; // (of the last attempt)
+        }
         bool overflow = false;
         for (int32_t q : rank)
             overflow = overflow || q == kAcaPoolOverflow;
@@ -1062,7 +1090,10 @@ int htb_create_compressed(const htb_hmatrix_desc *desc, const htb_generator_desc
         }
     }
 
+    const auto t_compressed = std::chrono::steady_clock::now();
     htb_compression_info ci{};
+    ci.seconds_prepare  = std::chrono::duration<double>(t_prepared - t_begin).count();
+    ci.seconds_compress = std::chrono::duration<double>(t_compressed - t_prepared).count();
     ci.nb_blocks  = static_cast<int64_t>(blocks.size());
     ci.rank_min   = INT32_MAX;
     ci.pool_bytes = static_cast<int64_t>(cf.pool.capacity * sizeof(double));
@@ -1096,7 +1127,9 @@ int htb_create_compressed(const htb_hmatrix_desc *desc, const htb_generator_desc
     htb_hmatrix_desc d2 = *desc;
     d2.leaves           = leaves.data();
     d2.device           = device;
+    const auto t_store  = std::chrono::steady_clock::now();
     int rc              = create_impl(&d2, gen, &cf, out);
+    ci.seconds_store    = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_store).count();
     cleanup();
 #undef HTB_CC
     if (rc != HTB_OK)
@@ -1105,6 +1138,10 @@ int htb_create_compressed(const htb_hmatrix_desc *desc, const htb_generator_desc
     for (size_t i = 0; i < leaves.size(); i++)
         (*out)->leaf_ranks[i] = leaves[i].rank;
     ci.seconds_total      = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+    for (int c = 0; c < 3; c++) {
+        ci.seconds_aca_team[c] = seconds_team[c];
+        ci.nb_blocks_team[c]   = blocks_team[c];
+    }
     (*out)->compression   = ci;
     return HTB_OK;
 }
@@ -1123,7 +1160,10 @@ int htb_get_leaf_ranks(htb_handle h, int32_t *ranks, int64_t nb_leaves) {
 int htb_get_compression_info(htb_handle h, htb_compression_info *info) {
     if (!h || !info)
         return fail(HTB_ERR_INVALID, "null argument");
-    *info = h->compression;
+    *info                = h->compression;
+    info->seconds_layout = h->create_seconds[0];
+    info->seconds_upload = h->create_seconds[1];
+    info->seconds_fill   = h->create_seconds[2];
     return HTB_OK;
 }
 
@@ -1322,6 +1362,7 @@ int htb_pack_host(const htb_hmatrix_desc *desc, int side, htb_packed_side *out) 
         return fail(HTB_ERR_INVALID, "invalid argument");
     PackOptions popt;
     popt.block_rows  = static_cast<int>(option("block_rows"));
+    popt.ld_pad_rows = static_cast<int>(option("ld_pad_rows"));
     popt.piece_cols  = static_cast<int>(option("piece_cols"));
     popt.stage_bytes = static_cast<int>(option("stage_bytes"));
     popt.cseg_bytes  = static_cast<int>(option("cseg_bytes"));
@@ -1370,6 +1411,7 @@ int htb_pack_host(const htb_hmatrix_desc *desc, int side, htb_packed_side *out) 
         out->dense_tasks   = own->layout.dense_tasks.data();
         out->n_lowrank_tasks = static_cast<int64_t>(own->layout.lr_tasks.size());
         out->lowrank_tasks   = own->layout.lr_tasks.data();
+        out->ld_pad_rows     = pk.opt.ld_pad_rows;
     } catch (const std::exception &ex) {
         return fail(HTB_ERR_INVALID, ex.what());
     }

@@ -46,6 +46,7 @@ struct htb_operator {
     // multi-RHS scratch ([TF | PARTM[0] | PARTM[1]] x vector stride), allocated at the first multi-RHS product
     std::vector<int32_t> leaf_ranks;      // htb_create_compressed: ranks per leaf of the descriptor
     htb_compression_info compression{};
+    double create_seconds[3] = {0., 0., 0.}; // layout (host), upload, device fill (generation + factor copies)
     void *d_mscratch        = nullptr;
     void *d_mstage          = nullptr; // multi-RHS: the current column group of the input, rows padded to the B-ring stride
     size_t mstage_cap       = 0;

@@ -71,9 +71,12 @@ Packer::Packer(const htb_hmatrix_desc &desc, const PackOptions &o) : dtype(desc.
         throw std::runtime_error("invalid piece_cols / stage_bytes / cseg_bytes");
     // a unit (block_rows x piece) and its descriptor must fit one stage; its c vector one c segment
     piece = 1;
-    while (piece * 2 <= opt.piece_cols && 32u + static_cast<size_t>(opt.block_rows) * (piece * 2) * esize <= static_cast<size_t>(opt.stage_bytes))
+    if (opt.ld_pad_rows < 0 || opt.ld_pad_rows > 65535)
+        throw std::runtime_error("ld_pad_rows must be in [0, 65535]");
+    const size_t max_ld = unit_ld(static_cast<uint32_t>(opt.block_rows), esize, static_cast<uint32_t>(opt.ld_pad_rows)); // (the tallest unit has the largest leading dimension)
+    while (piece * 2 <= opt.piece_cols && 32u + max_ld * (piece * 2) * esize <= static_cast<size_t>(opt.stage_bytes))
         piece *= 2;
-    if (32u + static_cast<size_t>(opt.block_rows) * piece * esize > static_cast<size_t>(opt.stage_bytes))
+    if (32u + max_ld * piece * esize > static_cast<size_t>(opt.stage_bytes))
         throw std::runtime_error("stage_bytes too small for one unit");
     if (static_cast<size_t>(std::max(opt.block_rows, piece)) * esize > static_cast<size_t>(opt.cseg_bytes) || opt.cseg_bytes / esize > 65535)
         throw std::runtime_error("cseg_bytes too small for one unit (or too large)");
@@ -698,7 +701,7 @@ void Packer::walk_block(int s, int b, Emit &&emit) const {
         u.row0 = static_cast<uint32_t>(a + lo - bs);
         u.h    = static_cast<uint32_t>(hi - lo);
         u.p0   = static_cast<uint32_t>(lo);
-        u.ld   = unit_ld(u.h, esize);
+        u.ld   = unit_ld(u.h, esize, static_cast<uint32_t>(opt.ld_pad_rows));
         for (int p = 0; p < n_pieces(l); p++) {
             u.ui    = ui++;
             u.piece = p;
@@ -824,9 +827,10 @@ void Packer::fill_block(int s, int b, char *dst) const {
                 for (uint32_t k = 0; k < u.w; k++)
                     std::memcpy(out + static_cast<size_t>(k) * u.ld, A + u.p0 + (u.k0 + k) * m, sizeof(T) * u.h);
             }
-            if (u.ld != u.h) // zero pad row
+            if (u.ld != u.h) // zero pad rows
                 for (uint32_t k = 0; k < u.w; k++)
-                    out[u.h + static_cast<size_t>(k) * u.ld] = T(0);
+                    for (uint32_t i = u.h; i < u.ld; i++)
+                        out[i + static_cast<size_t>(k) * u.ld] = T(0);
             eoff += u.elems();
         }
         const size_t used = cut.header_bytes() + static_cast<size_t>(cut.data_elems) * esize;

@@ -73,8 +73,16 @@ HTB_HD inline uint32_t unit_h(uint32_t g) { return ((g >> 8) & 0xffu) + 1u; }
 HTB_HD inline uint32_t unit_w(uint32_t g) { return (g >> 16) & 0xffu; }
 HTB_HD inline uint32_t unit_kind(uint32_t g) { return (g >> 24) & 0x3u; }
 HTB_HD inline uint32_t unit_twice(uint32_t g) { return (g >> 26) & 0x1u; }
-// leading dimension of a unit of height h
-HTB_HD inline uint32_t unit_ld(uint32_t h, size_t esize) { return esize == 8 ? (h + 1u) & ~1u : h; }
+// Leading dimension of a unit of height h. double: even (16-byte panel columns). Tall panels (h >= pad_rows real rows,
+// pad_rows > 0: packer option ld_pad_rows) get the smallest leading dimension >= h that is = 4 (mod 8) REAL doubles
+// (complex: = 2 (mod 4) elements): the DMMA fragment loads of the multi-RHS kernels — lane (g, tig) reads
+// P[row g][column tig] = address tig * ld + g — are then free of shared-memory bank conflicts (the four columns of a
+// half warp fall on four different groups of 4 bank pairs), where ld = 122 costs two wavefronts per load and ld = 128 four.
+HTB_HD inline uint32_t unit_ld(uint32_t h, size_t esize, uint32_t pad_rows) {
+    if (esize == 8)
+        return (pad_rows && h >= pad_rows) ? ((h + 3u) & ~7u) + 4u : (h + 1u) & ~1u;
+    return (pad_rows && 2u * h >= pad_rows) ? ((h + 1u) & ~3u) + 2u : h;
+}
 inline uint32_t make_geom(uint32_t row0, uint32_t h, uint32_t w, uint32_t kind, uint32_t twice) {
     return (row0 & 0xffu) | (((h - 1u) & 0xffu) << 8) | ((w & 0xffu) << 16) | ((kind & 3u) << 24) | ((twice & 1u) << 26);
 }
@@ -197,6 +205,9 @@ struct PackOptions {
     int sort_units      = 1;     // order the units of a block by the rows they act on (RUNS of the multi-RHS kernels); 0: leaf order
     bool generate_dense = false; // dense leaves with data0 == NULL are allowed: their panels are generated on the device
     int block_rows  = 0;     // 32, 64 or 128; 0 = automatic (128 for double, 64 for complex<double>)
+    int ld_pad_rows = 0;     // panels of >= this many real rows get a bank-conflict-free leading dimension (unit_ld); 0 = never (default:
+                             // measured at N = 1e6, 96 vs 0: mu = 64 18.07 vs 18.28 ms, mu = 1 3.36 vs 3.30 ms — the fragment loads are not
+                             // what limits the multi-RHS kernels, and the 1.2 % of extra bytes cost the single-RHS product more)
     int piece_cols  = 16;    // columns of a unit (<= 32); lowered automatically so that a unit fits a stage
     int stage_bytes = 24576; // bulk-copy granule of the coefficient stream, multiple of 16
     int cseg_bytes  = 4096;  // capacity of a stage's c segment, multiple of 16 (512 columns: stages of small-cluster runs still fill up)

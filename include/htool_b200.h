@@ -173,6 +173,14 @@ typedef struct htb_compression_info {
     int32_t rank_min, rank_max; /* over the compressed blocks                                                         */
     double seconds_aca;         /* the ACA kernels                                                                    */
     double seconds_total;       /* the whole call (ACA + packing + upload + generation of the dense leaves + copies)  */
+    double seconds_aca_team[3]; /* the ACA kernels by team size: 512, 128, 32 threads per block                       */
+    int64_t nb_blocks_team[3];  /* admissible blocks of each team size                                                */
+    double seconds_layout;      /* host: layout of the store (ranks known)                                            */
+    double seconds_upload;      /* descriptors + streams to the device (the panels travel as zeros)                   */
+    double seconds_fill;        /* device: generation of the dense leaves + copy of the factors into the streams      */
+    double seconds_prepare;     /* host: list of the blocks, device allocations, points to the device                 */
+    double seconds_compress;    /* pool allocation + the ACA kernels + ranks back to the host                         */
+    double seconds_store;       /* layout + upload + fill + scratch allocations (the htb_create part)                 */
 } htb_compression_info;
 /* htb_create for an H-matrix whose block cluster tree is known but whose leaves hold NO coefficients: dense leaves
  * (rank == -1, data0 == NULL) are generated as in htb_create_generated, admissible leaves (rank == HTB_RANK_COMPRESS) are
@@ -336,6 +344,8 @@ typedef struct htb_packed_side {
                                * device pool of htb_create_compressed); DenseTask with lrow = leaf index, lcol = side, p0 = first row of
                                * the panel inside the leaf's factor, k0 = first term */
     const void *lowrank_tasks;
+    int32_t ld_pad_rows;      /* store.hpp unit_ld: panels of >= this many real rows have a leading dimension = 4 (mod 8) doubles */
+    int32_t reserved;
 } htb_packed_side;
 int htb_pack_host(const htb_hmatrix_desc *desc, int side, htb_packed_side *out);
 int htb_pack_free(htb_packed_side *packed);

@@ -78,6 +78,7 @@ enum { G2L_VECTOR = 0,
        LOGGED_UNSUPPORTED,
        DEVICE_DIST,
        GENERATED_DENSE,
+       DEVICE_ASSEMBLY,
        N_GROUPS };
 
 struct CountingWriter : htool::IObjectWriter {
@@ -357,6 +358,61 @@ int run(htb_ref::Case<T> &c, double *results, int n_results) {
                 openmp_internal_add_hmatrix_vector_product(trans, alpha, H, x.data(), beta, yr.data());
                 DG.internal_add_vector_product(trans, alpha, x.data(), beta, yg.data());
                 upd(GENERATED_DENSE, rel_err(yg, yr));
+            }
+        }
+    }
+
+    // ---- the WHOLE leaf assembly on the device: the same builder call with DeviceDenseBlocks AND DeviceLowRankBlocks
+    // (HMatrixTreeBuilder::set_low_rank_generator, tree_builder.hpp:251): the host builds the block cluster tree only, the
+    // GPU compresses the admissible blocks with the reference's sympartialACA and generates the dense leaves. Same ranks as
+    // the reference's leaves, products equal to the reference's on H (real kernel functions) ------------------------------
+    if (c.spec.compressor == 0 && !is_complex && (c.spec.kernel == 0 || c.spec.kernel == 1)) {
+        HMatrixTreeBuilder<T, double> builder(c.spec.epsilon, c.spec.eta, static_cast<char>(c.spec.symmetry), static_cast<char>(c.spec.uplo));
+        if (c.spec.min_depth > 0) {
+            builder.set_minimal_target_depth(c.spec.min_depth);
+            builder.set_minimal_source_depth(c.spec.min_depth);
+        }
+        auto deferred = std::make_shared<htool_b200::DeviceDenseBlocks<T>>();
+        auto lowrank  = std::make_shared<htool_b200::DeviceLowRankBlocks<T>>();
+        builder.set_dense_blocks_generator(deferred);
+        builder.set_low_rank_generator(std::static_pointer_cast<VirtualInternalLowRankGenerator<T>>(lowrank));
+        std::unique_ptr<HMatrix<T, double>> H2;
+        if (c.spec.partition_rank >= 0 && c.spec.local_block)
+            H2 = std::make_unique<HMatrix<T, double>>(builder.build(exec_compat::par, *c.internal_generator, c.target_cluster->get_cluster_on_partition(c.spec.partition_rank), c.source_cluster->get_cluster_on_partition(c.spec.partition_rank)));
+        else if (c.spec.partition_rank >= 0)
+            H2 = std::make_unique<HMatrix<T, double>>(builder.build(exec_compat::par, *c.internal_generator, *c.target_cluster, *c.source_cluster, c.spec.partition_rank, c.spec.partition_rank));
+        else
+            H2 = std::make_unique<HMatrix<T, double>>(builder.build(exec_compat::par, *c.internal_generator, *c.target_cluster, *c.source_cluster));
+        htool_b200::BuiltinKernel bk;
+        bk.kernel        = c.spec.kernel;
+        bk.wavenumber    = c.spec.wavenumber;
+        bk.target_points = c.target_points.data();
+        bk.source_points = c.source_points->data();
+        htool_b200::DeviceHMatrix<T, double> DA(*H2, *deferred, *lowrank, bk);
+        if (!DA.is_valid()) {
+            upd(DEVICE_ASSEMBLY, 1.);
+        } else {
+            // ranks: leaf by leaf against the H-matrix the reference assembled (same tree, same order of get_leaves_from)
+            auto ranks       = DA.leaf_ranks();
+            auto ref_leaves  = htool::get_leaves_from(H).first;
+            std::size_t k    = 0;
+            bool ranks_equal = true;
+            for (const auto *leaf : ref_leaves) {
+                if (!leaf->is_dense() && !leaf->is_low_rank())
+                    continue;
+                const int r = leaf->is_dense() ? -1 : leaf->get_low_rank_data()->rank_of();
+                ranks_equal = ranks_equal && k < ranks.size() && ranks[k] == r;
+                k++;
+            }
+            upd(DEVICE_ASSEMBLY, ranks_equal && k == ranks.size() ? 0. : 1.);
+            for (char trans : valid_trans(sym, is_complex)) {
+                const size_t ni = trans == 'N' ? nc : nr, no = trans == 'N' ? nr : nc;
+                T alpha = rnd_scalar<T>(gen), beta = rnd_scalar<T>(gen);
+                auto x = rnd_vector<T>(gen, ni), y0 = rnd_vector<T>(gen, no);
+                auto yr = y0, yg = y0;
+                openmp_internal_add_hmatrix_vector_product(trans, alpha, H, x.data(), beta, yr.data());
+                DA.internal_add_vector_product(trans, alpha, x.data(), beta, yg.data());
+                upd(DEVICE_ASSEMBLY, rel_err(yg, yr));
             }
         }
     }

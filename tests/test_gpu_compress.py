@@ -15,15 +15,18 @@ from conftest import rel_err
 from htool_b200 import capi
 
 
-def assemble_and_compare(case, mask=None, expected=None, fma_axpy=False):
-    """Device assembly of `case` with the leaves of `mask` as admissible blocks; `expected` = the FlatCase the store must equal."""
+def assemble_and_compare(case, mask=None, expected=None, fma_axpy=False, dots=0):
+    """Device assembly of `case` with the leaves of `mask` as admissible blocks; `expected` = the FlatCase the store must equal.
+    dots: how the teams of 128 / 512 threads compute the stopping criterion (option aca_dots, aca.cuh)."""
     expected = expected or case.flat
     desc0, keep = case.stripped_desc(mask)
     capi.set_option("aca_fma_axpy", 1 if fma_axpy else 0)
+    capi.set_option("aca_dots", dots)
     try:
         op = capi.Operator(desc0, generator=(case.kernel, case.tp, case.sp, 0.0), compress_epsilon=case.epsilon)
     finally:
         capi.set_option("aca_fma_axpy", 0)
+        capi.set_option("aca_dots", 0)
     ranks = op.leaf_ranks()
     assert np.array_equal(ranks, expected.table[:, 4]), f"{int((ranks != expected.table[:, 4]).sum())} leaves got another rank than the reference"
     ci = op.compression_info()
@@ -59,9 +62,10 @@ def assemble_and_compare(case, mask=None, expected=None, fma_axpy=False):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ACA_GOLDEN)
-def test_device_assembly_rebuilds_the_reference_hmatrix(name):
+@pytest.mark.parametrize("dots", [0, 1, 2], ids=["warp_dots_guarded", "in_order_dots", "replay_always"])
+def test_device_assembly_rebuilds_the_reference_hmatrix(name, dots):
     case = AcaCase.golden(name)
-    op = assemble_and_compare(case)
+    op = assemble_and_compare(case, dots=dots)
     y = np.zeros(case.flat.nb_rows)
     op.add_vector_product("N", 1.0, case.x, 0.0, y)
     assert rel_err(y, case.y) < 1e-12  # the reference's own product on its own H-matrix
@@ -97,7 +101,8 @@ def test_device_assembly_against_the_live_reference(kw, have_ref):
     if not have_ref:
         pytest.skip("oracle/_ref is not built")
     case = AcaCase.live(**kw)
-    assemble_and_compare(case).close()
+    for dots in (0, 1, 2):  # (the guarded warp-level dot products, the reference's in-order ones, the in-order replay at every iteration)
+        assemble_and_compare(case, dots=dots).close()
 
 
 @pytest.mark.gpu

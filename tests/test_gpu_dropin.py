@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 DROPIN_LIB = os.path.join(REPO, "oracle", "_ref", "libhtool_dropin.so")
 GROUPS = ["g2l_vector", "g2l_row_major", "g2l_sub_product", "l2l_vector", "l2l_row_major", "l2l_sub_product", "dist_vector_g2g",
           "dist_vector_l2l", "dist_matrix_g2g", "dist_matrix_l2l", "dist_row_major_l2l", "dist_sub_product", "free_vector_user",
-          "free_matrix_user", "logged_unsupported", "device_dist", "generated_dense"]
+          "free_matrix_user", "logged_unsupported", "device_dist", "generated_dense", "device_assembly"]
 
 CASES = [
     dict(n=6000),
@@ -57,7 +57,8 @@ def test_reference_code_runs_unchanged_on_the_gpu_operators(kw):
     for name, err in zip(GROUPS, out):
         if err < 0:  # group not run for this case: distributed / free-function groups need the whole operator
             assert (name.startswith(("dist_", "free_", "device_dist")) and not whole) or (name == "logged_unsupported" and kw.get("symmetry", "N") == "N") \
-                or (name == "device_dist" and not kw.get("same_cluster", True)) or (name == "generated_dense" and kw.get("compressor", "sympartialACA") != "sympartialACA"), name
+                or (name == "device_dist" and not kw.get("same_cluster", True)) or (name == "generated_dense" and kw.get("compressor", "sympartialACA") != "sympartialACA") \
+                or (name == "device_assembly" and (kw.get("dtype", "double") != "double" or kw.get("compressor", "sympartialACA") != "sympartialACA")), name
             continue
         assert err < 1e-12, (kw, name, err)
     # the operator-level groups always run
