@@ -7,7 +7,8 @@
 //       CustomApproximationBuilder (distributed_operator/utility.hpp:22-35): every reference entry point keeps working,
 //       HPDDM included (use_distributed_operator.cpp:108);
 //   (3) one process per GPU with the exchange on NVLink: htool_b200::DeviceDistributedOperator, and the device-resident
-//       GMRES that stands for DDM::solve with -hpddm_schwarz_method none.
+//       GMRES that stands for DDM::solve with -hpddm_schwarz_method none;
+//   (4) the leaf assembly itself on the GPU (batched sympartialACA + dense generation): the host keeps the block tree only.
 //
 // Build:
 //   g++ -std=c++17 -fopenmp examples/use_b200_operator.cpp -I<htool>/include -Iinclude -Ihtool_b200/cpp \
@@ -24,6 +25,7 @@
 #include <htool_b200/operators.hpp>
 
 #include <cmath>
+#include <memory>
 #include <iostream>
 #include <vector>
 
@@ -111,6 +113,26 @@ int main(int argc, char *argv[]) {
         htool_b200::add_hmatrix_vector_product(exec_compat::par, 'N', 1., device_hmatrix, x.data(), 0., y_user.data());
         htool::add_hmatrix_vector_product(exec_compat::par, 'N', 1., strip, x.data(), 0., y_ref.data());
         std::cout << "add_hmatrix_vector_product (user numbering):         " << relative_error(y_user, y_ref) << "\n";
+    }
+
+    // (4) the WHOLE leaf assembly on the GPU: the same builder call, with generators that compute nothing plugged into the
+    // builder's own hooks (tree_builder.hpp:251,258) — the host builds the block cluster tree, the device compresses the
+    // admissible blocks with the reference's sympartialACA at the builder's epsilon and generates the dense leaves.
+    {
+        htool::HMatrixTreeBuilder<double, double> tree_builder(1e-4, 10., 'N', 'N');
+        auto dense   = std::make_shared<htool_b200::DeviceDenseBlocks<double>>();
+        auto lowrank = std::make_shared<htool_b200::DeviceLowRankBlocks<double>>();
+        tree_builder.set_dense_blocks_generator(dense);
+        tree_builder.set_low_rank_generator(std::static_pointer_cast<htool::VirtualInternalLowRankGenerator<double>>(lowrank));
+        htool::HMatrix<double, double> tree = tree_builder.build(kernel, cluster, cluster, rank, rank); // no coefficient is computed
+        htool_b200::BuiltinKernel builtin{HTB_KERNEL_LAPLACE_REG, 0., points.data(), points.data()};     // 1 / (1e-5 + 4 pi r), user numbering
+        htool_b200::DeviceHMatrix<double, double> assembled(tree, *dense, *lowrank, builtin, device);
+        const int n_rows = strip.get_target_cluster().get_size();
+        std::vector<double> xc(n, 1.), y_dev_asm(n_rows, 0.), y_host_asm(n_rows, 0.);
+        assembled.internal_add_vector_product('N', 1., xc.data(), 0., y_dev_asm.data());
+        htool::openmp_internal_add_hmatrix_vector_product('N', 1., strip, xc.data(), 0., y_host_asm.data());
+        if (rank == 0)
+            std::cout << "device-assembled H-matrix vs host-assembled (strip product): " << relative_error(y_dev_asm, y_host_asm) << "\n";
     }
     MPI_Finalize();
     return 0;
