@@ -12,6 +12,7 @@
 #include <chrono>
 #include <climits>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -32,7 +33,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 namespace {
 std::mutex g_option_mutex;
 std::map<std::string, int64_t> g_options = {
-    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 4096}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 0}, {"m_b_ring_log2", 3}, {"m_reduce_ring_stages", 0}, {"mrhs_min", 0}, {"pack_generate_dense", 0}, {"sort_units", 1}, {"reduce_blocks_per_cta", 0}, {"m_reduce_warps", 24}, {"m_pad", 4}, {"m_b_producers", 3}, {"m_stage_input", 1}, {"m_small_runs", 1}, {"m_reduce_split", 1}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}, {"aca_fma_axpy", 0}, {"aca_rank_guess", 16}, {"aca_dots", 0}, {"ld_pad_rows", 0}};
+    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 4096}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 0}, {"m_b_ring_log2", 3}, {"m_reduce_ring_stages", 0}, {"mrhs_min", 0}, {"pack_generate_dense", 0}, {"sort_units", 1}, {"reduce_blocks_per_cta", 0}, {"m_reduce_warps", 24}, {"m_pad", 4}, {"m_b_producers", 3}, {"m_stage_input", 1}, {"m_small_runs", 1}, {"m_reduce_split", 1}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}, {"aca_fma_axpy", 0}, {"aca_rank_guess", 16}, {"aca_dots", 0}, {"upload_headers_only", 1}, {"ld_pad_rows", 0}};
 
 int64_t option(const char *key) {
     std::lock_guard<std::mutex> lock(g_option_mutex);
@@ -76,12 +77,28 @@ static int upload_vector(const std::vector<V> &v, const V **dptr, std::vector<vo
 }
 
 static int upload_store(htb_operator *h, const Packer &pk) {
+    const bool timing = std::getenv("HTB_PACK_TIMING") != nullptr; // development aid: seconds of every phase on stderr
+    auto t_last       = std::chrono::steady_clock::now();
+    auto lap          = [&](const char *what) {
+        if (!timing)
+            return;
+        cudaDeviceSynchronize();
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[htb upload] %-22s %.3f s\n", what, std::chrono::duration<double>(now - t_last).count());
+        t_last = now;
+    };
     const size_t chunk = static_cast<size_t>(std::max<int64_t>(1, option("upload_chunk_mb"))) << 20;
     // two pinned buffers: the CPU packs block streams into one while the other is in flight to the device
-    size_t need = 0;
-    for (int s = 0; s < 2; s++)
-        need = std::max<size_t>(need, pk.side[s].stream_bytes);
-    const size_t buf_bytes = std::min(need, chunk);
+    const bool headers_only = pk.all_on_device && option("upload_headers_only") != 0;
+    size_t need = 0, largest_block = 0;
+    for (int s = 0; s < 2; s++) {
+        need = std::max<size_t>(need, headers_only ? pk.header_offset(s, pk.side[s].stages.size()) : pk.side[s].stream_bytes);
+        if (headers_only)
+            for (const BlockDesc &bd : pk.side[s].blocks)
+                largest_block = std::max<size_t>(largest_block, pk.header_offset(s, bd.first_stage + bd.n_stages) - pk.header_offset(s, bd.first_stage));
+    }
+    // (page-locking costs ~0.4 s per GB: the headers of a device-assembled store travel through 2 x 32 MB)
+    const size_t buf_bytes = std::min(need, headers_only ? std::max<size_t>(largest_block, size_t(32) << 20) : chunk);
     char *pinned[2]        = {nullptr, nullptr};
     cudaEvent_t done[2]    = {nullptr, nullptr};
     int status             = HTB_OK;
@@ -104,6 +121,7 @@ static int upload_store(htb_operator *h, const Packer &pk) {
             }
         }
     }
+    lap("pinned buffers");
     for (int s = 0; s < 2 && status == HTB_OK; s++) {
         const SideLayout &sl = pk.side[s];
         SideDevice &sd       = h->side[s];
@@ -136,6 +154,7 @@ static int upload_store(htb_operator *h, const Packer &pk) {
         sd.n_combine_m = static_cast<int>(sl.combine_m.size());
         h->descriptor_bytes += sl.munits.size() * sizeof(MUnit) + sl.combine_m.size() * sizeof(CombineEntry);
         h->descriptor_bytes += sl.blocks.size() * sizeof(BlockDesc) + sl.stages.size() * sizeof(StageDesc) + sl.order.size() * 4 + sl.combine.size() * sizeof(CombineEntry) + sl.combine_dst.size() * sizeof(CombineDst);
+        lap("descriptor tables");
         if (sl.stream_bytes == 0)
             continue;
         void *dstream = nullptr;
@@ -149,8 +168,57 @@ static int upload_store(htb_operator *h, const Packer &pk) {
         sd.stream_bytes = sl.stream_bytes;
         h->store_bytes += sl.stream_bytes;
         h->side_stream_bytes[s] = sl.stream_bytes;
-        // batches of consecutive blocks whose streams fit one pinned buffer
         const int nb = sd.n_blocks;
+        if (headers_only) {
+            // Device assembly: every panel is generated / copied on the device, the stream is zeros + the stage headers. Only the
+            // headers travel (16 + 16 n_units bytes per stage, ~2 % of the stream), packed back to back, and a kernel puts them in place.
+            const uint64_t total_hdr = pk.header_offset(s, sl.stages.size());
+            void *d_compact = nullptr, *d_off = nullptr;
+            e = cudaMemsetAsync(dstream, 0, sl.stream_bytes, h->own_stream);
+            if (e == cudaSuccess)
+                e = cudaMalloc(&d_compact, std::max<uint64_t>(16, total_hdr));
+            if (e == cudaSuccess)
+                e = cudaMalloc(&d_off, (sl.stages.size() + 1) * sizeof(uint64_t));
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(d_off, pk.header_offsets(s).data(), (sl.stages.size() + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, h->own_stream);
+            int b0 = 0, turn = 0;
+            while (e == cudaSuccess && b0 < nb) {
+                auto hoff = [&](int b) { return b < nb ? pk.header_offset(s, sl.blocks[b].first_stage) : total_hdr; };
+                int b1 = b0 + 1;
+                while (b1 < nb && hoff(b1 + 1) - hoff(b0) <= buf_bytes)
+                    b1++;
+                const uint64_t off = hoff(b0), bytes = hoff(b1) - off;
+                if (bytes > buf_bytes) {
+                    status = fail(HTB_ERR_ALLOC, "block headers larger than the upload buffer");
+                    break;
+                }
+                if (bytes) {
+                    cudaEventSynchronize(done[turn]);
+                    pk.fill_headers(s, b0, b1, pinned[turn]);
+                    e = cudaMemcpyAsync(static_cast<char *>(d_compact) + off, pinned[turn], bytes, cudaMemcpyHostToDevice, h->own_stream);
+                    if (e == cudaSuccess)
+                        e = cudaEventRecord(done[turn], h->own_stream);
+                    turn ^= 1;
+                }
+                b0 = b1;
+            }
+            if (e == cudaSuccess && status == HTB_OK)
+                e = launch_scatter_headers(sd.stages, static_cast<const unsigned long long *>(d_off), static_cast<long long>(sl.stages.size()), static_cast<const unsigned char *>(d_compact), static_cast<unsigned char *>(dstream), h->own_stream);
+            if (e == cudaSuccess)
+                e = cudaStreamSynchronize(h->own_stream);
+            if (d_compact)
+                cudaFree(d_compact);
+            if (d_off)
+                cudaFree(d_off);
+            if (e != cudaSuccess && status == HTB_OK)
+                status = cuda_fail(e, "upload of the stage headers");
+            if (status != HTB_OK)
+                break;
+            h->launches++;
+            lap("stream (headers only)");
+            continue;
+        }
+        // batches of consecutive blocks whose streams fit one pinned buffer
         int b0 = 0, turn = 0;
         while (b0 < nb) {
             int b1 = b0 + 1;
@@ -175,9 +243,11 @@ static int upload_store(htb_operator *h, const Packer &pk) {
             }
             b0 = b1;
         }
+        lap("stream");
     }
     cudaError_t e = cudaStreamSynchronize(h->own_stream);
     cleanup();
+    lap("cleanup");
     if (status == HTB_OK && e != cudaSuccess)
         status = cuda_fail(e, "upload of the leaf store");
     return status;

@@ -54,7 +54,28 @@ __global__ void generate_dense_kernel(const DenseTask *tasks, long long n_tasks,
     }
 }
 
+__global__ void scatter_headers_kernel(const StageDesc *stages, const unsigned long long *hdr_off, long long n_stages, const unsigned char *compact, unsigned char *stream) {
+    const long long st = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (st >= n_stages)
+        return;
+    const int lane    = threadIdx.x & 31;
+    const uint4 *src  = reinterpret_cast<const uint4 *>(compact + hdr_off[st]);
+    uint4 *dst        = reinterpret_cast<uint4 *>(stream + stages[st].byte_off);
+    const int n16     = static_cast<int>((hdr_off[st + 1] - hdr_off[st]) >> 4);
+    for (int i = lane; i < n16; i += 32)
+        dst[i] = src[i];
+}
+
 } // namespace
+
+cudaError_t launch_scatter_headers(const StageDesc *stages, const unsigned long long *hdr_off, long long n_stages, const unsigned char *compact, unsigned char *stream, cudaStream_t st) {
+    if (n_stages <= 0)
+        return cudaSuccess;
+    const int threads   = 256;
+    const unsigned grid = static_cast<unsigned>((n_stages * 32 + threads - 1) / threads);
+    scatter_headers_kernel<<<grid, threads, 0, st>>>(stages, hdr_off, n_stages, compact, stream);
+    return cudaGetLastError();
+}
 
 bool kernel_is_complex(int kernel) { return kernel == HTB_KERNEL_COMPLEX_REG || kernel == HTB_KERNEL_HERMITIAN_REG || kernel == HTB_KERNEL_HELMHOLTZ || kernel == HTB_KERNEL_COMPLEX; }
 

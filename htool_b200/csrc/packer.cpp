@@ -2,6 +2,9 @@
 #include "packer.hpp"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <complex>
 #include <cstring>
 #include <numeric>
@@ -119,6 +122,17 @@ Packer::Packer(const htb_hmatrix_desc &desc, const PackOptions &o) : dtype(desc.
     if (n_lowrank == 0)
         rank_min = 0;
 
+    // HTB_PACK_TIMING=1: seconds of every phase of the layout on stderr (development aid)
+    const bool timing = std::getenv("HTB_PACK_TIMING") != nullptr;
+    auto t_last       = std::chrono::steady_clock::now();
+    auto lap          = [&](const char *what) {
+        if (!timing)
+            return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[htb pack] %-14s %.3f s\n", what, std::chrono::duration<double>(now - t_last).count());
+        t_last = now;
+    };
+    lap("validation");
     m_piece_ptr.assign(n_leaves + 1, 0);
     for (int64_t i = 0; i < n_leaves; i++)
         m_piece_ptr[i + 1] = m_piece_ptr[i] + (active(m_leaves[i]) ? n_pieces(m_leaves[i]) : 0);
@@ -127,9 +141,12 @@ Packer::Packer(const htb_hmatrix_desc &desc, const PackOptions &o) : dtype(desc.
     side[1].n = nb_cols;
     for (int s = 0; s < 2; s++)
         make_blocks(s);
+    lap("make_blocks");
     for (int s = 0; s < 2; s++)
         make_incidence(s);
+    lap("make_incidence");
     make_partials();
+    lap("make_partials");
 
     // per-block stage layout
     std::vector<uint32_t> unit_stage[2];
@@ -186,6 +203,7 @@ Packer::Packer(const htb_hmatrix_desc &desc, const PackOptions &o) : dtype(desc.
         });
     }
 
+    lap("layout_blocks");
     // scratch copy: [PART[0] | PART[1] | CS[0] | CS[1]], c-stream bases 16 B aligned
     side[0].part_base = 0;
     side[1].part_base = side[0].part_elems;
@@ -206,9 +224,21 @@ Packer::Packer(const htb_hmatrix_desc &desc, const PackOptions &o) : dtype(desc.
                 m_unit_slot[s][ui] = static_cast<uint32_t>(side[s].cs_base + side[s].stages[side[s].blocks[b].first_stage + unit_stage[s][ui]].c_off + m_unit_cslot[s][ui]);
         }
     }
+    all_on_device = n_leaves > 0;
+    for (int64_t i = 0; i < n_leaves; i++)
+        if (active(m_leaves[i]) && m_leaves[i].data0)
+            all_on_device = false;
+    for (int s = 0; s < 2; s++) {
+        m_hdr_off[s].assign(side[s].stages.size() + 1, 0);
+        for (size_t st = 0; st < side[s].stages.size(); st++)
+            m_hdr_off[s][st + 1] = m_hdr_off[s][st] + 16u + 16u * side[s].stages[st].n_units;
+    }
+    lap("unit_slots");
     for (int s = 0; s < 2; s++)
         make_combine(s);
+    lap("make_combine");
     make_mtables();
+    lap("make_mtables");
 }
 
 // Cut [0, n) into blocks of <= block_rows indices. Cut points are taken where no small leaf (<= block_rows
@@ -760,7 +790,7 @@ inline std::complex<double> real_of(std::complex<double> v) { return std::comple
 } // namespace
 
 template <typename T>
-void Packer::fill_block(int s, int b, char *dst) const {
+void Packer::fill_block(int s, int b, char *dst, bool headers_only) const {
     StageCutter cut{esize, static_cast<uint32_t>(opt.stage_bytes), static_cast<uint32_t>(opt.cseg_bytes)};
     std::vector<UnitSpec> pending;
     char *cursor        = dst;
@@ -783,6 +813,10 @@ void Packer::fill_block(int s, int b, char *dst) const {
             units[i]          = Unit{eoff, make_geom(u.row0, u.h, u.w, u.kind, u.twice), producer_out(s, u), m_unit_cslot[s][u.ui], 0};
             if (u.kind == UNIT_ADDVEC)
                 continue;
+            if (headers_only) { // (the panels are filled on the device)
+                eoff += u.elems();
+                continue;
+            }
             const htb_leaf &l = m_leaves[u.leaf];
             T *out            = data + eoff;
             if (u.kind == UNIT_LOWRANK && !l.data0) {
@@ -834,9 +868,13 @@ void Packer::fill_block(int s, int b, char *dst) const {
             eoff += u.elems();
         }
         const size_t used = cut.header_bytes() + static_cast<size_t>(cut.data_elems) * esize;
-        if (used < nbytes)
-            std::memset(cursor + used, 0, nbytes - used);
-        cursor += nbytes;
+        if (headers_only)
+            cursor += cut.header_bytes();
+        else {
+            if (used < nbytes)
+                std::memset(cursor + used, 0, nbytes - used);
+            cursor += nbytes;
+        }
         cut.reset();
         pending.clear();
     };
@@ -847,6 +885,18 @@ void Packer::fill_block(int s, int b, char *dst) const {
         pending.push_back(u);
     });
     close();
+}
+
+void Packer::fill_headers(int s, int b0, int b1, char *dst) const {
+    const uint64_t base = m_hdr_off[s][side[s].blocks[b0].first_stage];
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int b = b0; b < b1; b++) {
+        char *p = dst + (m_hdr_off[s][side[s].blocks[b].first_stage] - base);
+        if (dtype == HTB_DOUBLE)
+            fill_block<double>(s, b, p, true);
+        else
+            fill_block<std::complex<double>>(s, b, p, true);
+    }
 }
 
 void Packer::fill(int s, int b0, int b1, char *dst) const {

@@ -21,6 +21,13 @@ class Packer {
     // Writes the stream bytes of blocks [b0, b1) of side s to dst, dst[0] being the first byte of block
     // b0's stream (blocks are contiguous in the side's stream, in block order).
     void fill(int s, int b0, int b1, char *dst) const;
+    // Device assembly: no leaf carries host coefficients (all_on_device), so a stream is zeros except for the headers of its
+    // stages (StageHeader + Unit table, 16 + 16 n_units bytes each). fill_headers writes those of blocks [b0, b1) back to
+    // back: the header of stage st starts at header_offset(s, st) - header_offset(s, first stage of b0).
+    bool all_on_device = false;
+    void fill_headers(int s, int b0, int b1, char *dst) const;
+    uint64_t header_offset(int s, size_t st) const { return m_hdr_off[s][st]; } // st in [0, n_stages]
+    const std::vector<uint64_t> &header_offsets(int s) const { return m_hdr_off[s]; }
 
     uint64_t block_offset(int s, int b) const { return m_block_off[s][b]; } // byte offset of block b's stream, b in [0, nblocks]
 
@@ -55,6 +62,7 @@ class Packer {
     std::vector<uint16_t> m_unit_cslot[2]; // per unit: offset of its c slot inside its stage's c segment
     std::vector<uint32_t> m_part_off[2];   // [consumer side] per global piece: scratch offset of the partials, or kDirect
     std::vector<uint64_t> m_block_off[2];
+    std::vector<uint64_t> m_hdr_off[2];    // prefix sums of the stages' header bytes (n_stages + 1)
 
     bool active(const htb_leaf &l) const { return l.nb_rows > 0 && l.nb_cols > 0 && l.rank != 0; }
     int vec_len(const htb_leaf &l) const { return l.rank < 0 ? l.nb_cols : l.rank; }
@@ -81,7 +89,7 @@ class Packer {
     void walk_block(int s, int b, Emit &&emit) const;
     void layout_block(int s, int b, std::vector<StageDesc> &stages, std::vector<uint32_t> &unit_stage, uint64_t &n_units, bool &any_twice);
     template <typename T>
-    void fill_block(int s, int b, char *dst) const;
+    void fill_block(int s, int b, char *dst, bool headers_only = false) const;
 };
 
 } // namespace htb
