@@ -133,6 +133,12 @@ int main(int argc, char *argv[]) {
         htool::openmp_internal_add_hmatrix_vector_product('N', 1., strip, xc.data(), 0., y_host_asm.data());
         if (rank == 0)
             std::cout << "device-assembled H-matrix vs host-assembled (strip product): " << relative_error(y_dev_asm, y_host_asm) << "\n";
+        // ... and the distributed operator over the device-assembled strips (every rank compressed its own block row)
+        htool_b200::DeviceDistributedOperator<double> assembled_operator(std::move(assembled), partition, MPI_COMM_WORLD);
+        std::vector<double> y_asm(n, 0.);
+        htool_b200::add_distributed_operator_vector_product_global_to_global('N', 1., assembled_operator, x.data(), 0., y_asm.data());
+        if (rank == 0)
+            std::cout << "DeviceDistributedOperator over device-assembled strips: " << relative_error(y_asm, y_cpu) << "\n";
     }
     MPI_Finalize();
     return 0;

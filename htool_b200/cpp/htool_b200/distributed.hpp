@@ -21,6 +21,7 @@
 #include "device_hmatrix.hpp"
 #include <htool/distributed_operator/interfaces/virtual_partition.hpp>
 #include <mpi.h>
+#include <utility>
 #include <vector>
 
 namespace htool_b200 {
@@ -73,6 +74,14 @@ class DeviceDistributedOperator {
     /// cluster tree (square operator, as in DefaultApproximationBuilder's symmetric constructor, utility.hpp:61).
     DeviceDistributedOperator(const htool::HMatrix<CoefficientPrecision, CoordinatePrecision> &strip, const htool::VirtualPartition<CoefficientPrecision> &partition, MPI_Comm comm, int device = -1)
         : m_data(strip, device), m_partition(partition), m_comm(comm) {
+        MPI_Comm_rank(comm, &m_rank);
+        MPI_Comm_size(comm, &m_size);
+        m_ready = bootstrap();
+    }
+    /// Same, for a strip whose leaf store already exists — e.g. one ASSEMBLED ON THE DEVICE from the block cluster tree
+    /// (DeviceHMatrix(tree, dense, lowrank, kernel), device_hmatrix.hpp): every rank compresses its own block row on its own GPU.
+    DeviceDistributedOperator(DeviceHMatrix<CoefficientPrecision, CoordinatePrecision> &&strip, const htool::VirtualPartition<CoefficientPrecision> &partition, MPI_Comm comm)
+        : m_data(std::move(strip)), m_partition(partition), m_comm(comm) {
         MPI_Comm_rank(comm, &m_rank);
         MPI_Comm_size(comm, &m_size);
         m_ready = bootstrap();
