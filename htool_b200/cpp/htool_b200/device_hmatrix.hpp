@@ -79,6 +79,7 @@ class DeviceDenseBlocks final : public htool::VirtualDenseBlocksGenerator<Coeffi
 /// empty. A DeviceHMatrix built with it (constructor below) compresses those blocks on the GPU with the reference's own
 /// algorithm and stopping criterion (htb_create_compressed); blocks whose compression fails become dense leaves of the
 /// device store, as in tree_builder.hpp:619-625. The host H-matrix then holds rank-0 leaves: use it for assembly only.
+/// double and complex<double> (the reference's std::complex instantiation of sympartialACA).
 /// A required rank (reqrank > 0) is not supported on the device: the call reports a failure and the builder computes the
 /// block as a dense leaf on the host, which is what the reference does with any failed compression.
 template <typename CoefficientPrecision>
@@ -145,7 +146,7 @@ class DeviceHMatrix {
     /// Device-side assembly of ALL the leaves: `hmatrix` was built with `deferred` as its dense-blocks generator and a
     /// DeviceLowRankBlocks as its low-rank generator, so it is a block cluster tree without coefficients. The admissible
     /// blocks are compressed on the GPU by the reference's sympartialACA at the builder's epsilon, the dense leaves are
-    /// generated (htb_create_compressed). Real built-in kernel functions.
+    /// generated (htb_create_compressed). Any built-in kernel function, double or complex<double>.
     DeviceHMatrix(const htool::HMatrix<CoefficientPrecision, CoordinatePrecision> &hmatrix, const DeviceDenseBlocks<CoefficientPrecision> &deferred, const DeviceLowRankBlocks<CoefficientPrecision> &, const BuiltinKernel &kernel, int device = -1) {
         assemble_on_device(hmatrix, deferred, kernel, true, device);
     }

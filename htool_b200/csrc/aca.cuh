@@ -8,7 +8,11 @@
 
 namespace htb {
 
-constexpr int kAcaMaxRank = 128; // terms a block can hold (slots of its term table are min(this, floor(m n / (m + n))))
+// Terms a block can hold, by team size: a block never needs more than floor(m n / (m + n)) terms (sympartialACA.hpp:102), i.e. 32 for the
+// teams of 32 threads (max(m, n) <= 64) and 256 for the teams of 128 (max(m, n) <= 512): only blocks of the largest class can
+// hit the limit (kAcaRankCap), when the reference itself would go past 512 terms.
+HTB_HD constexpr int aca_max_rank(int team) { return team == 32 ? 32 : (team == 128 ? 256 : 512); }
+HTB_HD constexpr int aca_team(int m, int n) { return (m > n ? m : n) > 512 ? 512 : ((m > n ? m : n) > 64 ? 128 : 32); }
 
 // One admissible block of the block cluster tree (a leaf with rank == HTB_RANK_COMPRESS), in the root block's cluster
 // numbering. "Dimension 1" is the rows when row_offset >= col_offset (GLOBAL offsets) and the columns otherwise
@@ -27,9 +31,10 @@ static_assert(sizeof(AcaBlock) == 32, "AcaBlock must be 32 bytes");
 // status of a block after the kernel (rank[] entry): q > 0 = rank; the others:
 constexpr int kAcaFailed       = -1; // not advantageous / zero first row: the leaf becomes a dense leaf (tree_builder.hpp:617-626)
 constexpr int kAcaPoolOverflow = -3; // the factor pool is full: the caller retries with a larger pool
-constexpr int kAcaRankCap      = -4; // more than kAcaMaxRank terms
+constexpr int kAcaRankCap      = -4; // more than aca_max_rank(team) terms
 
-// The factor pool: term j of a block is the chunk [uu_j (n1 doubles) | vv_j (n2 doubles)] at pool + 2 * term_off[term_base + j].
+// The factor pool: term j of a block is the chunk [uu_j (n1 coefficients) | vv_j (n2 coefficients)] at pool + 2 * term_off[term_base + j]
+// (complex coefficients: re / im interleaved).
 struct AcaPool {
     double *pool                = nullptr;
     unsigned long long capacity = 0; // doubles
@@ -51,7 +56,7 @@ struct AcaLeaf {
     uint32_t term_base, n1, swapped, reserved;
 };
 // One warp per unit: copies the unit's panel out of the pool into the uploaded stream of side `side` (0: U panels, 1: V^T panels).
-cudaError_t launch_scatter_lowrank(const DenseTask *tasks, long long n_tasks, int side, unsigned char *stream, const AcaLeaf *leaves, const double *pool, const uint32_t *term_off, cudaStream_t st);
+cudaError_t launch_scatter_lowrank(bool complex_coefficients, const DenseTask *tasks, long long n_tasks, int side, unsigned char *stream, const AcaLeaf *leaves, const double *pool, const uint32_t *term_off, cudaStream_t st);
 
 } // namespace htb
 #endif

@@ -806,7 +806,7 @@ static int scatter_lowrank(htb_operator *h, const Packer &pk, const CompressedFa
         if (e == cudaSuccess)
             e = cudaMemcpyAsync(d_tasks, tasks.data(), tasks.size() * sizeof(DenseTask), cudaMemcpyHostToDevice, h->own_stream);
         if (e == cudaSuccess)
-            e = launch_scatter_lowrank(static_cast<const DenseTask *>(d_tasks), static_cast<long long>(tasks.size()), s, const_cast<unsigned char *>(h->side[s].stream), static_cast<const AcaLeaf *>(d_leaves), cf.pool.pool,
+            e = launch_scatter_lowrank(h->dtype == HTB_COMPLEX_DOUBLE, static_cast<const DenseTask *>(d_tasks), static_cast<long long>(tasks.size()), s, const_cast<unsigned char *>(h->side[s].stream), static_cast<const AcaLeaf *>(d_leaves), cf.pool.pool,
                                        cf.pool.term_off, h->own_stream);
         if (e == cudaSuccess)
             e = cudaStreamSynchronize(h->own_stream);
@@ -987,8 +987,6 @@ int htb_create_compressed(const htb_hmatrix_desc *desc, const htb_generator_desc
         return fail(HTB_ERR_INVALID, "unknown built-in kernel function");
     if (kernel_is_complex(gen->kernel) != (desc->dtype == HTB_COMPLEX_DOUBLE))
         return fail(HTB_ERR_INVALID, "the kernel function does not produce the coefficient type of the H-matrix");
-    if (desc->dtype != HTB_DOUBLE || (gen->kernel != HTB_KERNEL_LAPLACE && gen->kernel != HTB_KERNEL_LAPLACE_REG))
-        return fail(HTB_ERR_UNSUPPORTED, "device compression is implemented for the real kernel functions (complex kernels: compress on the host, htb_create_generated)");
     if (!(epsilon > 0.))
         return fail(HTB_ERR_INVALID, "epsilon must be positive (a required rank is not supported on the device)");
     if ((desc->nb_rows > 0 && !gen->target_points) || (desc->nb_cols > 0 && !gen->source_points))
@@ -1015,7 +1013,7 @@ int htb_create_compressed(const htb_hmatrix_desc *desc, const htb_generator_desc
         AcaBlock b{};
         b.lrow = l.row_offset, b.lcol = l.col_offset, b.m = l.nb_rows, b.n = l.nb_cols;
         b.swapped  = (int64_t(desc->row_offset) + l.row_offset >= int64_t(desc->col_offset) + l.col_offset) ? 0 : 1; // sympartialACA.hpp:46
-        b.term_cap = static_cast<uint16_t>(std::min<int64_t>(kAcaMaxRank, (int64_t(b.m) * b.n) / (int64_t(b.m) + b.n)));
+        b.term_cap = static_cast<uint16_t>(std::min<int64_t>(aca_max_rank(aca_team(b.m, b.n)), (int64_t(b.m) * b.n) / (int64_t(b.m) + b.n)));
         b.leaf     = static_cast<uint32_t>(i);
         blocks.push_back(b);
     }
@@ -1031,7 +1029,7 @@ int htb_create_compressed(const htb_hmatrix_desc *desc, const htb_generator_desc
         }
         return rc;
     }
-    auto team_of = [](const AcaBlock &b) { const int mx = std::max(b.m, b.n); return mx > 512 ? 512 : (mx > 64 ? 128 : 32); };
+    auto team_of = [](const AcaBlock &b) { return aca_team(b.m, b.n); };
     std::stable_sort(blocks.begin(), blocks.end(), [&](const AcaBlock &a, const AcaBlock &b) {
         const int ta = team_of(a), tb = team_of(b);
         return ta != tb ? ta > tb : int64_t(a.m) + a.n > int64_t(b.m) + b.n;
@@ -1114,7 +1112,7 @@ int htb_create_compressed(const htb_hmatrix_desc *desc, const htb_generator_desc
     for (int64_t guess = std::max<int64_t>(1, option("aca_rank_guess"));; guess *= 2) {
         uint64_t want = 0, full = 0;
         for (const AcaBlock &b : blocks) {
-            const uint64_t len = (uint64_t(b.m) + b.n + 1u) & ~uint64_t(1);
+            const uint64_t len = desc->dtype == HTB_COMPLEX_DOUBLE ? 2u * (uint64_t(b.m) + b.n) : (uint64_t(b.m) + b.n + 1u) & ~uint64_t(1); // doubles per term
             want += len * std::min<uint64_t>(b.term_cap, static_cast<uint64_t>(guess));
             full += len * b.term_cap;
         }
@@ -1173,7 +1171,7 @@ int htb_create_compressed(const htb_hmatrix_desc *desc, const htb_generator_desc
         const int32_t q   = rank[i];
         if (q == kAcaRankCap) {
             cleanup();
-            return fail(HTB_ERR_UNSUPPORTED, "an admissible block needs more than " + std::to_string(kAcaMaxRank) + " terms at this epsilon: compress on the host");
+            return fail(HTB_ERR_UNSUPPORTED, "an admissible block needs more than " + std::to_string(aca_max_rank(512)) + " terms at this epsilon: compress on the host");
         }
         if (q > 0) {
             leaves[b.leaf].rank = q;

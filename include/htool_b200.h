@@ -190,8 +190,9 @@ typedef struct htb_compression_info {
  * (hmatrix.hpp:228-237) per admissible block, a dense leaf instead when the compression fails (:619-625). Pivots, ranks and
  * factors are those of the reference (bit for bit for the real kernel functions when the host BLAS computes axpy with a
  * rounded product and a rounded sum, as the OpenBLAS of this image does; option aca_fma_axpy = 1 for FMA builds). Leaves
- * that carry data are packed from the host as usual. Real kernel functions (HTB_KERNEL_LAPLACE, HTB_KERNEL_LAPLACE_REG);
- * HTB_ERR_UNSUPPORTED for the complex ones. */
+ * that carry data are packed from the host as usual. All the built-in kernel functions: the complex ones follow the reference's
+ * std::complex<double> instantiation (std::abs, the compiler's complex division and product, zaxpy as y += ar x, y += ai (i x));
+ * those without transcendental calls reproduce the reference's factors bit for bit, Helmholtz to the last ulps of sincos. */
 int htb_create_compressed(const htb_hmatrix_desc *desc, const htb_generator_desc *generator, double epsilon, htb_handle *out);
 /* Ranks the device found, in the order of the descriptor's leaves: the rank for compressed leaves, -1 for dense leaves
  * (including admissible blocks whose compression failed), the descriptor's rank for leaves that carried data. */

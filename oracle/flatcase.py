@@ -30,19 +30,27 @@ def load_oracle():
         lib.oracle_add_matrix_product_row_major.argtypes = [C.POINTER(htb_hmatrix_desc), C.c_char, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.oracle_sympartial_aca.restype = C.c_int
         lib.oracle_sympartial_aca.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.oracle_sympartial_aca_z.restype = C.c_int
+        lib.oracle_sympartial_aca_z.argtypes = [C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = lib
     return _lib
 
 
-def oracle_sympartial_aca(kernel, target_points, source_points, m, n, row_offset, col_offset, lrow, lcol, epsilon, fma_axpy=False, max_rank=None):
+def oracle_sympartial_aca(kernel, target_points, source_points, m, n, row_offset, col_offset, lrow, lcol, epsilon, fma_axpy=False, max_rank=None, wavenumber=0.0):
     """oracle/aca_oracle.c on one block. kernel: 'laplace' | 'laplace_reg'. Returns (rank, U (m x rank, Fortran order),
     V (rank x n, Fortran order), pivots (rank x 2)); rank = -1: the reference reports a failure (dense leaf)."""
     lib = load_oracle()
     cap = max_rank or max(1, (m * n) // (m + n))
     tp, sp = np.ascontiguousarray(target_points, dtype=np.float64), np.ascontiguousarray(source_points, dtype=np.float64)
-    U, V, piv = np.zeros(m * cap), np.zeros(cap * n), np.zeros(2 * cap, dtype=np.int32)
-    q = lib.oracle_sympartial_aca({"laplace": 0, "laplace_reg": 1}[kernel], tp.ctypes.data, sp.ctypes.data, m, n, row_offset, col_offset, lrow, lcol, float(epsilon), int(bool(fma_axpy)), cap,
-                                  U.ctypes.data, V.ctypes.data, piv.ctypes.data)
+    piv = np.zeros(2 * cap, dtype=np.int32)
+    if kernel in ("laplace", "laplace_reg"):
+        U, V = np.zeros(m * cap), np.zeros(cap * n)
+        q = lib.oracle_sympartial_aca({"laplace": 0, "laplace_reg": 1}[kernel], tp.ctypes.data, sp.ctypes.data, m, n, row_offset, col_offset, lrow, lcol, float(epsilon), int(bool(fma_axpy)), cap,
+                                      U.ctypes.data, V.ctypes.data, piv.ctypes.data)
+    else:  # complex kernel functions (ids of oracle/ref/ref_harness.hpp)
+        U, V = np.zeros(m * cap, np.complex128), np.zeros(cap * n, np.complex128)
+        q = lib.oracle_sympartial_aca_z({"complex_reg": 2, "hermitian_reg": 3, "helmholtz": 4, "complex": 5}[kernel], float(wavenumber), tp.ctypes.data, sp.ctypes.data, m, n, row_offset, col_offset, lrow, lcol,
+                                        float(epsilon), int(bool(fma_axpy)), cap, U.ctypes.data, V.ctypes.data, piv.ctypes.data)
     if q == -2:
         raise RuntimeError("max_rank too small")
     if q <= 0:

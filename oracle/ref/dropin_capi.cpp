@@ -365,8 +365,8 @@ int run(htb_ref::Case<T> &c, double *results, int n_results) {
     // ---- the WHOLE leaf assembly on the device: the same builder call with DeviceDenseBlocks AND DeviceLowRankBlocks
     // (HMatrixTreeBuilder::set_low_rank_generator, tree_builder.hpp:251): the host builds the block cluster tree only, the
     // GPU compresses the admissible blocks with the reference's sympartialACA and generates the dense leaves. Same ranks as
-    // the reference's leaves, products equal to the reference's on H (real kernel functions) ------------------------------
-    if (c.spec.compressor == 0 && !is_complex && (c.spec.kernel == 0 || c.spec.kernel == 1)) {
+    // the reference's leaves, products equal to the reference's on H (all the built-in kernel functions) ------------------
+    if (c.spec.compressor == 0 && (c.spec.kernel >= 0 && c.spec.kernel <= 5)) {
         HMatrixTreeBuilder<T, double> builder(c.spec.epsilon, c.spec.eta, static_cast<char>(c.spec.symmetry), static_cast<char>(c.spec.uplo));
         if (c.spec.min_depth > 0) {
             builder.set_minimal_target_depth(c.spec.min_depth);

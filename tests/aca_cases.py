@@ -19,13 +19,16 @@ DIAG_FLAGS = capi.HTB_LEAF_DIAG_SYMMETRIC | capi.HTB_LEAF_DIAG_HERMITIAN
 
 
 class AcaCase:
-    def __init__(self, flat, tp, sp, kernel, epsilon, x=None, y=None):
+    def __init__(self, flat, tp, sp, kernel, epsilon, x=None, y=None, wavenumber=0.0):
         self.flat, self.tp, self.sp, self.kernel, self.epsilon, self.x, self.y = flat, np.ascontiguousarray(tp), np.ascontiguousarray(sp), kernel, float(epsilon), x, y
+        self.wavenumber = float(wavenumber)
+        self.dtype = flat.np_dtype
 
     @classmethod
     def golden(cls, name):
         z = np.load(os.path.join(ACA_DIR, name + ".npz"))
-        return cls(FlatCase.from_arrays(z), z["points_target"], z["points_source"], KERNEL_NAMES[int(z["aca_meta"][0])], z["aca_meta"][1], z["x"], z["y"])
+        meta = z["aca_meta"]
+        return cls(FlatCase.from_arrays(z), z["points_target"], z["points_source"], KERNEL_NAMES[int(meta[0])], meta[1], z["x"], z["y"], meta[2] if len(meta) > 2 else 0.0)
 
     @classmethod
     def live(cls, **kw):
@@ -33,7 +36,7 @@ class AcaCase:
         from oracle import refharness as R
 
         case = R.RefCase(**kw)
-        return cls(FlatCase.from_desc(case.desc), case.points(0), case.points(1), kw.get("kernel", "laplace_reg"), kw.get("epsilon", 1e-4))
+        return cls(FlatCase.from_desc(case.desc), case.points(0), case.points(1), kw.get("kernel", "laplace_reg"), kw.get("epsilon", 1e-4), wavenumber=kw.get("wavenumber", 5.0 if kw.get("kernel") == "helmholtz" else 0.0))
 
     def factors(self, i):
         """U (m x r) and V (r x n) of low-rank leaf i as the reference stored them."""
@@ -45,7 +48,7 @@ class AcaCase:
     def oracle_block(self, i, fma_axpy=False):
         f = self.flat
         lr, lc, m, n = (int(v) for v in f.table[i, 0:4])
-        return oracle_sympartial_aca(self.kernel, self.tp, self.sp, m, n, f.row_offset + lr, f.col_offset + lc, lr, lc, self.epsilon, fma_axpy)
+        return oracle_sympartial_aca(self.kernel, self.tp, self.sp, m, n, f.row_offset + lr, f.col_offset + lc, lr, lc, self.epsilon, fma_axpy, wavenumber=self.wavenumber)
 
     def stripped_desc(self, compress_mask=None):
         """The descriptor htb_create_compressed is given: no coefficients anywhere; leaves of `compress_mask` (default: the
@@ -88,8 +91,8 @@ class AcaCase:
                     parts.append(f.coeffs[s: s + m * n])
                 else:
                     gi, gj = np.meshgrid(np.arange(m), np.arange(n), indexing="ij")
-                    parts.append(kernel_values(self.kernel, self.tp[lr + gi], self.sp[lc + gj], 0.0).ravel(order="F"))
-        coeffs = np.concatenate(parts) if parts else np.zeros(0)
+                    parts.append(kernel_values(self.kernel, self.tp[lr + gi], self.sp[lc + gj], self.wavenumber).astype(self.dtype).ravel(order="F"))
+        coeffs = np.concatenate(parts) if parts else np.zeros(0, self.dtype)
         return FlatCase(f.dtype_code, f.nb_rows, f.nb_cols, f.row_offset, f.col_offset, f.symmetry, f.uplo, table, coeffs)
 
 

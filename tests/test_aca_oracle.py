@@ -30,11 +30,14 @@ def test_oracle_reproduces_the_reference_factors(name):
 
 
 def test_fixtures_exist():
-    assert len(ACA_GOLDEN) >= 5
+    assert len(ACA_GOLDEN) >= 8
 
 
 @pytest.mark.parametrize("kw", [dict(n=2500, kernel="laplace_reg", epsilon=1e-4), dict(n=1800, kernel="laplace_reg", epsilon=1e-5, symmetry="S", uplo="L"),
-                                dict(n=1500, n_source=1100, same_cluster=False, z_source=1.5, kernel="laplace", epsilon=1e-3)], ids=["N", "SL", "rect"])
+                                dict(n=1500, n_source=1100, same_cluster=False, z_source=1.5, kernel="laplace", epsilon=1e-3),
+                                dict(n=1800, dtype="complex", kernel="complex_reg", epsilon=1e-4, symmetry="S", uplo="L"),
+                                dict(n=1600, dtype="complex", kernel="hermitian_reg", epsilon=1e-5, symmetry="H", uplo="U"),
+                                dict(n=2000, dtype="complex", kernel="helmholtz", epsilon=1e-4, wavenumber=5.0)], ids=["N", "SL", "rect", "z_SL", "z_HU", "z_helmholtz"])
 def test_oracle_against_the_live_reference(kw, have_ref):
     if not have_ref:
         pytest.skip("oracle/_ref is not built")
@@ -78,6 +81,7 @@ def test_lowrank_task_table_rebuilds_the_host_streams(name):
     case = AcaCase.golden(name)
     f = case.flat
     lr = f.table[:, 4] >= 0
+    esz = np.dtype(case.dtype).itemsize
     desc0, keep = case.stripped_desc()
     lv = np.frombuffer(keep, dtype=LEAF_NP_DTYPE)
     lv["rank"][: f.table.shape[0]] = f.table[:, 4]  # the ranks are known (after the device ACA), the factors are not on the host
@@ -95,16 +99,16 @@ def test_lowrank_task_table_rebuilds_the_host_streams(name):
             U, V = case.factors(i)
             h, w, ld, p0, k0 = int(t["h"]), int(t["w"]), int(t["ld"]), int(t["p0"]), int(t["k0"])
             src = U[p0: p0 + h, k0: k0 + w] if side == 0 else V[k0: k0 + w, p0: p0 + h].T
-            panel = np.zeros((w, ld))
+            panel = np.zeros((w, ld), case.dtype)
             panel[:, :h] = src.T
             off = int(t["byte_off"])
-            stream[off: off + w * ld * 8] = np.frombuffer(panel.tobytes(), dtype=np.uint8)
+            stream[off: off + w * ld * esz] = np.frombuffer(panel.tobytes(), dtype=np.uint8)
             covered[i] += h * w
         m, n, r = f.table[:, 2].astype(np.int64), f.table[:, 3].astype(np.int64), f.table[:, 4].astype(np.int64)
         assert np.array_equal(covered[lr], ((m if side == 0 else n) * r)[lr]), "every factor entry is copied exactly once"
         if side == 0:  # the dense panels are the business of tests/test_generated_dense.py: take them from the host stream
             for t in dense:
-                off, nbytes = int(t["byte_off"]), int(t["w"]) * int(t["ld"]) * 8
+                off, nbytes = int(t["byte_off"]), int(t["w"]) * int(t["ld"]) * esz
                 stream[off: off + nbytes] = ref_stream[off: off + nbytes]
         assert np.array_equal(stream, ref_stream)
 

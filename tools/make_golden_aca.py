@@ -4,7 +4,7 @@ needs to redo the work: the kernel function, epsilon and the points of the root 
 
 Run in the build container (needs /root/reference to have built oracle/_ref):  python tools/make_golden_aca.py
 Each file holds the flattened leaves (oracle/flatcase.py format: the reference's ranks and U / V factors, and the dense
-leaves), `points_target`, `points_source` (n x 3), `aca_meta` = [kernel id (capi.HTB_KERNELS), epsilon] and one reference
+leaves), `points_target`, `points_source` (n x 3), `aca_meta` = [kernel id (capi.HTB_KERNELS), epsilon, wavenumber] and one reference
 product (x, y = H x by openmp_internal_add_hmatrix_vector_product).
 The blocks of a fixture were compressed with the BLAS of this image (OpenBLAS: daxpy = rounded product + rounded sum); the
 oracle (oracle/aca_oracle.c, fma_axpy = 0) and the device kernels (option aca_fma_axpy = 0) reproduce them bit for bit.
@@ -26,6 +26,10 @@ CASES = {
     "d_SU_eps6": dict(n=520, kernel="laplace_reg", epsilon=1e-6, symmetry="S", uplo="U"),
     "d_rect": dict(n=600, n_source=450, same_cluster=False, z_source=1.5, kernel="laplace", epsilon=1e-4),
     "d_strip": dict(n=900, n_partitions=3, partition_rank=1, kernel="laplace_reg", epsilon=1e-3),
+    # complex kernel functions (the reference's template instantiated for std::complex<double>)
+    "z_SL": dict(n=420, dtype="complex", kernel="complex_reg", epsilon=1e-4, symmetry="S", uplo="L"),
+    "z_HU": dict(n=400, dtype="complex", kernel="hermitian_reg", epsilon=1e-4, symmetry="H", uplo="U"),
+    "z_helmholtz": dict(n=360, dtype="complex", kernel="helmholtz", epsilon=1e-4, wavenumber=5.0),
 }
 
 
@@ -38,10 +42,12 @@ def main():
         info = case.info()
         arrays = flat.save_arrays()
         arrays["points_target"], arrays["points_source"] = case.points(0), case.points(1)
-        arrays["aca_meta"] = np.array([HTB_KERNELS[kw["kernel"]], kw["epsilon"]], dtype=np.float64)
+        arrays["aca_meta"] = np.array([HTB_KERNELS[kw["kernel"]], kw["epsilon"], kw.get("wavenumber", 0.0)], dtype=np.float64)
         rng = np.random.default_rng(sum(map(ord, name)))
-        x = rng.random(case.nb_cols) - 0.5
-        y = np.zeros(case.nb_rows)
+        x = (rng.random(case.nb_cols) - 0.5).astype(case.np_dtype)
+        if case.np_dtype == np.complex128:
+            x = x + 1j * (rng.random(case.nb_cols) - 0.5)
+        y = np.zeros(case.nb_rows, case.np_dtype)
         case.vector_product("N", 1.0, x, 0.0, y, variant="openmp")
         arrays["x"], arrays["y"] = x, y
         path = os.path.join(out_dir, name + ".npz")
