@@ -33,7 +33,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 namespace {
 std::mutex g_option_mutex;
 std::map<std::string, int64_t> g_options = {
-    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 4096}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 0}, {"m_b_ring_log2", 3}, {"m_reduce_ring_stages", 0}, {"mrhs_min", 0}, {"pack_generate_dense", 0}, {"sort_units", 1}, {"reduce_blocks_per_cta", 0}, {"m_reduce_warps", 24}, {"m_pad", 4}, {"m_b_producers", 3}, {"m_stage_input", 1}, {"m_small_runs", 1}, {"m_reduce_split", 1}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}, {"aca_fma_axpy", 0}, {"aca_rank_guess", 16}, {"aca_dots", 0}, {"upload_headers_only", 1}, {"ld_pad_rows", 0}};
+    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 4096}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 0}, {"m_b_ring_log2", 3}, {"m_reduce_ring_stages", 0}, {"mrhs_min", 0}, {"pack_generate_dense", 0}, {"sort_units", 1}, {"reduce_blocks_per_cta", 0}, {"m_reduce_warps", 24}, {"m_pad", 4}, {"m_b_producers", 3}, {"m_stage_input", 1}, {"m_small_runs", 1}, {"m_reduce_split", 1}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}, {"aca_fma_axpy", 0}, {"aca_rank_guess", 16}, {"aca_dots", 0}, {"upload_headers_only", 1}, {"ld_pad_rows", 0}, {"m_near_field", 0}, {"m_nf_rows", 0}};
 
 int64_t option(const char *key) {
     std::lock_guard<std::mutex> lock(g_option_mutex);
@@ -404,6 +404,76 @@ static int ensure_mscratch(htb_operator *h, int vs) {
     return HTB_OK;
 }
 
+// Device copy of the multi-RHS near field, built from the main stream of side 0 the first time a multi-RHS product 'N' runs.
+// A failure (e.g. out of memory for the second copy of the dense coefficients) is not an error: the product keeps the dense
+// columns in the runs of the main stream.
+static void ensure_near_field(htb_operator *h) {
+    if (h->nf_ready || h->nf_failed || !h->nf_host)
+        return;
+    const NearFieldLayout &nf = *h->nf_host;
+    std::vector<void *> mine;
+    void *d_tasks = nullptr, *d_hdr = nullptr, *d_off = nullptr, *d_stream = nullptr;
+    auto up = [&](const void *src, size_t bytes, void **dst) -> cudaError_t {
+        cudaError_t e = cudaMalloc(dst, std::max<size_t>(16, bytes));
+        if (e == cudaSuccess && bytes)
+            e = cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, h->own_stream);
+        return e;
+    };
+    void *d_blocks = nullptr, *d_stages = nullptr, *d_order = nullptr, *d_aux = nullptr;
+    cudaError_t e = up(nf.blocks.data(), nf.blocks.size() * sizeof(BlockDesc), &d_blocks);
+    if (e == cudaSuccess)
+        e = up(nf.stages.data(), nf.stages.size() * sizeof(StageDesc), &d_stages);
+    if (e == cudaSuccess)
+        e = up(nf.order.data(), nf.order.size() * sizeof(uint32_t), &d_order);
+    if (e == cudaSuccess)
+        e = up(nf.aux_apply.data(), nf.aux_apply.size(), &d_aux);
+    if (e == cudaSuccess)
+        e = up(nf.tasks.data(), nf.tasks.size() * sizeof(NfTask), &d_tasks);
+    if (e == cudaSuccess)
+        e = up(nf.headers.data(), nf.headers.size(), &d_hdr);
+    if (e == cudaSuccess)
+        e = up(nf.hdr_off.data(), nf.hdr_off.size() * sizeof(uint64_t), &d_off);
+    if (e == cudaSuccess)
+        e = cudaMalloc(&d_stream, std::max<uint64_t>(16, nf.stream_bytes));
+    if (e == cudaSuccess)
+        e = cudaMemsetAsync(d_stream, 0, nf.stream_bytes, h->own_stream);
+    if (e == cudaSuccess)
+        e = launch_scatter_headers(static_cast<const StageDesc *>(d_stages), static_cast<const unsigned long long *>(d_off), static_cast<long long>(nf.stages.size()), static_cast<const unsigned char *>(d_hdr),
+                                   static_cast<unsigned char *>(d_stream), h->own_stream);
+    if (e == cudaSuccess)
+        e = launch_nf_copy(static_cast<const NfTask *>(d_tasks), static_cast<long long>(nf.tasks.size()), h->side[0].stream, static_cast<unsigned char *>(d_stream), static_cast<int>(h->esize), h->own_stream);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(h->own_stream);
+    for (void *p : {d_tasks, d_hdr, d_off})
+        if (p)
+            cudaFree(p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        for (void *p : {d_blocks, d_stages, d_order, d_aux, d_stream})
+            if (p)
+                cudaFree(p);
+        h->nf_failed = true;
+        h->nf_host.reset();
+        return;
+    }
+    for (void *p : {d_blocks, d_stages, d_order, d_aux, d_stream})
+        h->owned.push_back(p);
+    h->nf.blocks    = static_cast<const BlockDesc *>(d_blocks);
+    h->nf.stages    = static_cast<const StageDesc *>(d_stages);
+    h->nf.order     = static_cast<const uint32_t *>(d_order);
+    h->nf.stream    = static_cast<const unsigned char *>(d_stream);
+    h->nf.aux_apply = static_cast<const unsigned char *>(d_aux);
+    h->nf.n_blocks  = static_cast<int>(nf.blocks.size());
+    h->nf.stream_bytes = nf.stream_bytes;
+    h->nf.n            = h->side[0].n;
+    h->nf_bytes        = nf.stream_bytes + nf.aux_apply.size();
+    h->store_bytes += nf.stream_bytes;
+    h->descriptor_bytes += nf.aux_apply.size() + nf.blocks.size() * sizeof(BlockDesc) + nf.stages.size() * sizeof(StageDesc);
+    h->launches += 2;
+    h->nf_ready = true;
+    h->nf_host.reset();
+}
+
 static int run_product_m(htb_operator *h, char trans, const double *alpha, const double *in, const double *beta, double *out, int mu) {
     const char sym   = h->symmetry;
     const bool twice = sym != 'N' && (h->side[0].any_twice || h->side[1].any_twice);
@@ -430,6 +500,8 @@ static int run_product_m(htb_operator *h, char trans, const double *alpha, const
         h->launches++;
         return HTB_OK;
     };
+    if (trans == 'N' && option("m_near_field") != 0)
+        ensure_near_field(h);
     for (int col0 = 0; col0 < mu; col0 += group) {
         const int mc = std::min(group, mu - col0) * W, vs = (mc + 7) & ~7;
         if ((rc = ensure_mscratch(h, (std::min(group, mu) * W + 7) & ~7)) != HTB_OK)
@@ -474,7 +546,14 @@ static int run_product_m(htb_operator *h, char trans, const double *alpha, const
                 return rc2;
             MArgs ap = r;
             ap.out = out, ap.out_rows = out_rows, ap.out_shift = out_shift, ap.beta = b_re, ap.beta_im = b_im;
-            return timed(HTB_PASS_APPLY, [&]() { return launch_apply_m(h->side[cs], h->launch_cfg, ap, st); }, "apply_m");
+            // first application of 'N': the dense leaves come from the near-field panels (one full-height panel per target block)
+            const bool near_field = cs == 0 && !twice_only && !conj && h->nf_ready && option("m_near_field") != 0;
+            ap.skip_dense         = near_field ? 1 : 0;
+            if ((rc2 = timed(HTB_PASS_APPLY, [&]() { return launch_apply_m(h->side[cs], h->launch_cfg, ap, st); }, "apply_m")) != HTB_OK || !near_field)
+                return rc2;
+            MArgs nfa      = ap;
+            nfa.skip_dense = 0, nfa.beta = 1., nfa.beta_im = 0.;
+            return timed(std::getenv("HTB_NF_AS_OTHER") ? HTB_PASS_OTHER : HTB_PASS_APPLY, [&]() { return launch_apply_m(h->nf, h->launch_cfg, nfa, st); }, "apply_m(near field)");
         };
         const double b_re = beta[0], b_im = cplx ? beta[1] : 0.;
         const int herm = (sym == 'H' && cplx) ? 1 : 0; // second application of a Hermitian leaf stored once: conjugate-transposed
@@ -842,6 +921,8 @@ static int create_impl(const htb_hmatrix_desc *desc, const htb_generator_desc *g
     popt.sort_units     = static_cast<int>(option("sort_units"));
     popt.block_rows  = static_cast<int>(option("block_rows"));
     popt.ld_pad_rows = static_cast<int>(option("ld_pad_rows"));
+    popt.near_field  = option("m_near_field") != 0;
+    popt.nf_rows     = static_cast<int>(std::max<int64_t>(0, std::min<int64_t>(128, option("m_nf_rows"))));
     popt.piece_cols  = static_cast<int>(option("piece_cols"));
     popt.stage_bytes = static_cast<int>(option("stage_bytes"));
     popt.cseg_bytes  = static_cast<int>(option("cseg_bytes"));
@@ -933,6 +1014,8 @@ static int create_impl(const htb_hmatrix_desc *desc, const htb_generator_desc *g
         rc = generate_dense(h.get(), *pk, gen);
     if (rc == HTB_OK && factors)
         rc = scatter_lowrank(h.get(), *pk, *factors);
+    if (rc == HTB_OK && h->m_path_ok && !pk->nf.empty())
+        h->nf_host = std::make_unique<NearFieldLayout>(std::move(pk->nf));
     h->create_seconds[0] = seconds_layout;
     h->create_seconds[1] = std::chrono::duration<double>(t_fill - t_upload).count();
     h->create_seconds[2] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_fill).count();
@@ -1431,6 +1514,8 @@ int htb_pack_host(const htb_hmatrix_desc *desc, int side, htb_packed_side *out) 
     PackOptions popt;
     popt.block_rows  = static_cast<int>(option("block_rows"));
     popt.ld_pad_rows = static_cast<int>(option("ld_pad_rows"));
+    popt.near_field  = option("m_near_field") != 0;
+    popt.nf_rows     = static_cast<int>(std::max<int64_t>(0, std::min<int64_t>(128, option("m_nf_rows"))));
     popt.piece_cols  = static_cast<int>(option("piece_cols"));
     popt.stage_bytes = static_cast<int>(option("stage_bytes"));
     popt.cseg_bytes  = static_cast<int>(option("cseg_bytes"));

@@ -47,6 +47,11 @@ struct htb_operator {
     std::vector<int32_t> leaf_ranks;      // htb_create_compressed: ranks per leaf of the descriptor
     htb_compression_info compression{};
     double create_seconds[3] = {0., 0., 0.}; // layout (host), upload, device fill (generation + factor copies)
+    // multi-RHS near field (store.hpp, NearFieldLayout): host layout kept until the first multi-RHS product 'N' builds the device copy
+    std::unique_ptr<htb::NearFieldLayout> nf_host;
+    htb::SideDevice nf{};
+    bool nf_ready = false, nf_failed = false;
+    uint64_t nf_bytes = 0;
     void *d_mscratch        = nullptr;
     void *d_mstage          = nullptr; // multi-RHS: the current column group of the input, rows padded to the B-ring stride
     size_t mstage_cap       = 0;

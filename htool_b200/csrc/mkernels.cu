@@ -368,7 +368,7 @@ __device__ __forceinline__ void produce_b(const MSide &ks, const BlockDesc &bd, 
             if (a.twice_only && !(rd.flags & 1u))
                 continue;
             bpos             = (bpos + 3u) & ~3u;
-            const uint32_t K = rd.K;
+            const uint32_t K = a.skip_dense ? rd.K_lr : rd.K; // (near field applied from its own panels: the dense tail of the run is skipped)
             for (uint32_t j = 0; j < K;) {
                 const long long chunk = static_cast<long long>((bpos + j) >> 5);
                 const uint32_t first  = (bpos + j) & 31u;
@@ -644,13 +644,16 @@ __global__ void __launch_bounds__((kApplyWarps + 1 + kBProducersMax) * 32, 1) ap
                 continue;
             cpos = (cpos + 3u) & ~3u;
             const uint32_t run_pos = cpos;
-            cpos += rd.K;
+            const uint32_t Krun    = a.skip_dense ? rd.K_lr : rd.K;
+            if (Krun == 0)
+                continue;
+            cpos += Krun;
             const int row0 = rd.row0, h = static_cast<int>(rd.h_minus_1) + 1;
             // my row tiles j PAR + par that meet rows [row0, row0 + h): j in [jlo, jhi]
             const int tlo = row0 >> 3, thi = (row0 + h - 1) >> 3;
             const int jlo = tlo <= par ? 0 : (tlo - par + PAR - 1) / PAR, jhi = thi >= par ? (thi - par) / PAR : -1;
             const bool mine = jlo <= jhi && jlo < NJ; // (a warp without rows in the run still walks its chunks: the B ring is released by all)
-            const uint32_t Kr = static_cast<uint32_t>(rd.K) << CS; // contraction length
+            const uint32_t Kr = Krun << CS; // contraction length
             const uint32_t ld = CPLX ? 2u * unit_ld(static_cast<uint32_t>(h), 16, ks.ld_pad) : unit_ld(static_cast<uint32_t>(h), sizeof(double), ks.ld_pad);
             const size_t pstep = static_cast<size_t>(4 >> CS) * ld;
             // this lane's panel column (contraction index tig) at my row of tile 0 — dereferenced only where the row exists
@@ -879,6 +882,23 @@ __global__ void stage_group_kernel(const double *__restrict__ in, long long rows
     }
 }
 
+// One warp per task: an h x w panel of doubles (complex: 2 h real rows) from the main stream into a near-field panel.
+__global__ void nf_copy_kernel(const NfTask *tasks, long long n_tasks, const unsigned char *src, unsigned char *dst, int real_per_elem) {
+    const long long t = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (t >= n_tasks)
+        return;
+    const NfTask task = tasks[t];
+    const int lane    = threadIdx.x & 31;
+    const double *s   = reinterpret_cast<const double *>(src + task.src_off);
+    double *d         = reinterpret_cast<double *>(dst + task.dst_off);
+    const int h = task.h * real_per_elem, sld = task.src_ld * real_per_elem, dld = task.dst_ld * real_per_elem;
+    const int total = h * task.w;
+    for (int e = lane; e < total; e += 32) {
+        const int k = e / h, i = e - k * h;
+        atomicAdd(&d[static_cast<size_t>(k) * dld + i], s[static_cast<size_t>(k) * sld + i]); // (leaves of a block tree never overlap: 0 + x, exact; overlapping leaf lists add up)
+    }
+}
+
 inline size_t aux_part(const LaunchConfig &cfg) { return cfg.m_aux_bytes > 0 ? static_cast<size_t>(cfg.m_aux_bytes) : aux_slot_bytes(static_cast<uint32_t>(cfg.cseg_bytes)); }
 
 inline MSide make_mside(const SideDevice &s, const LaunchConfig &cfg, int ring, bool apply_role) {
@@ -976,6 +996,15 @@ cudaError_t launch_apply_m(const SideDevice &side, const LaunchConfig &cfg, cons
             HTB_APPLY_M(false, 1);
     }
 #undef HTB_APPLY_M
+    return cudaGetLastError();
+}
+
+cudaError_t launch_nf_copy(const NfTask *tasks, long long n_tasks, const unsigned char *src, unsigned char *dst, int esize, cudaStream_t stream) {
+    if (n_tasks <= 0)
+        return cudaSuccess;
+    const int threads   = 256;
+    const unsigned grid = static_cast<unsigned>((n_tasks * 32 + threads - 1) / threads);
+    nf_copy_kernel<<<grid, threads, 0, stream>>>(tasks, n_tasks, src, dst, esize / 8);
     return cudaGetLastError();
 }
 

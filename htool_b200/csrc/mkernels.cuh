@@ -33,6 +33,7 @@ struct MArgs {
     int conj         = 0; // conjugate the coefficients (trans == 'C', Hermitian second application)
     int small_runs   = 1; // APPLY_M: run-private accumulators for runs of <= 5 row tiles per warp (0: the predicated per-tile walk)
     int reduce_split = 1; // REDUCE_M: jobs per 8-column tile of a tall run (groups of column tiles of the right-hand sides)
+    int skip_dense   = 0; // APPLY_M: the dense columns of the runs (their tail, RunDesc::K_lr) are applied from the near-field panels instead
 };
 
 cudaError_t launch_reduce_m(const SideDevice &side, const LaunchConfig &cfg, const MArgs &args, cudaStream_t stream);
@@ -42,6 +43,8 @@ cudaError_t launch_combine_m(const SideDevice &side, double *mscratch, int vs, i
 // Copies real columns [col0, col0 + mc) of the row-major matrix `in` (rows x ld_in) into dst (rows x vsp), zero padded: the
 // staged group. Rows of the staged copy are one B-ring row apart, so the input rows of a dense leaf land with ONE bulk copy.
 cudaError_t launch_stage_group(const double *in, long long rows, int ld_in, int col0, int mc, double *dst, int vsp, cudaStream_t stream);
+// Fills the near-field panels (store.hpp, NearFieldLayout) from the dense units of the main stream of side 0.
+cudaError_t launch_nf_copy(const NfTask *tasks, long long n_tasks, const unsigned char *src, unsigned char *dst, int esize, cudaStream_t stream);
 size_t reduce_m_smem_bytes(const LaunchConfig &cfg, int vs, size_t esize);
 size_t apply_m_smem_bytes(const LaunchConfig &cfg);
 cudaError_t configure_mkernels(const LaunchConfig &cfg, size_t esize);

@@ -36,6 +36,7 @@ class Packer {
     PackOptions opt;
     int piece = 16; // effective piece_cols
     SideLayout side[2];
+    NearFieldLayout nf; // multi-RHS near field of side 0 (store.hpp)
     uint64_t scratch_elems = 0; // elements of one scratch copy: PART[0] | PART[1] | CS[0] | CS[1]
     uint64_t tf_elems = 0, mscratch_elems = 0; // multi-RHS scratch copy, in vectors: TF | PARTM[0] | PARTM[1]
 
@@ -90,6 +91,12 @@ class Packer {
     void layout_block(int s, int b, std::vector<StageDesc> &stages, std::vector<uint32_t> &unit_stage, uint64_t &n_units, bool &any_twice);
     template <typename T>
     void fill_block(int s, int b, char *dst, bool headers_only = false) const;
+    struct NfSrc { // a dense unit of side 0 in the main stream
+        uint64_t src_off;
+        uint32_t col; // first column (root numbering)
+        uint16_t row0, h, w, ld;
+    };
+    void make_near_field(const std::vector<std::vector<NfSrc>> &per_block);
 };
 
 } // namespace htb

@@ -183,7 +183,9 @@ struct RunDesc {
     uint8_t h_minus_1;
     uint8_t flags;     // bit 0: applied-twice units (runs are homogeneous)
     uint8_t reserved8;
-    uint32_t reserved;
+    uint16_t K_lr;     // the first K_lr columns of the run belong to low-rank units, the dense ones follow (sorted so by the packer)
+    uint16_t tiles;    // bit t set = the run has coefficients in rows [8 t, 8 t + 8) of the block (0xffff for the runs of the main streams;
+                       // near-field panels are block-sparse. Skipping the empty tiles in APPLY_M was measured: no gain)
 };
 static_assert(sizeof(RunDesc) == 16, "RunDesc must be 16 bytes");
 // capacity of a stage's aux record: a stage holds <= cseg_bytes / esize columns (c-segment limit), one run per column at worst
@@ -205,6 +207,8 @@ struct PackOptions {
     int sort_units      = 1;     // order the units of a block by the rows they act on (RUNS of the multi-RHS kernels); 0: leaf order
     bool generate_dense = false; // dense leaves with data0 == NULL are allowed: their panels are generated on the device
     int block_rows  = 0;     // 32, 64 or 128; 0 = automatic (128 for double, 64 for complex<double>)
+    bool near_field = false; // build the multi-RHS near-field layout (NearFieldLayout; needs sort_units). Off by default: measured, DESIGN.md 6
+    int nf_rows     = 0;     // rows of a near-field panel (rounded up to a multiple of 8; 0: one panel over all the rows of a block)
     int ld_pad_rows = 0;     // panels of >= this many real rows get a bank-conflict-free leading dimension (unit_ld); 0 = never (default:
                              // measured at N = 1e6, 96 vs 0: mu = 64 18.07 vs 18.28 ms, mu = 1 3.36 vs 3.30 ms — the fragment loads are not
                              // what limits the multi-RHS kernels, and the 1.2 % of extra bytes cost the single-RHS product more)
@@ -220,6 +224,34 @@ struct PackOptions {
     // APPLY CTAs when the side has between 1 and 6 rounds of blocks. cta_slots = resident APPLY CTAs of the device.
     int tail_split = 1;
     int cta_slots  = 148 * 3;
+};
+
+// ---- multi-RHS near field (mkernels.cu, APPLY_M) ------------------------------------------------------------------------------
+// The dense leaves of a target block (the near field: ~16 leaf clusters of 7 - 8 rows, each against ~27 source clusters that
+// are mostly the SAME for the whole block) cost the multi-RHS APPLY pass far more than their 7 % of the coefficients: 8-row
+// runs that straddle two row tiles, B rows (rows of the input matrix) fetched again by every leaf cluster. For the multi-RHS
+// product 'N' they are therefore ALSO kept as ONE block-sparse panel per target block: all the rows of the block x the union
+// of the columns its dense leaves touch (zeros where there is no leaf), in stages of the usual size — the full-height run path of
+// APPLY_M, every B row fetched once per block. It is a second copy of the dense coefficients (x ~2.5 with the zeros), built
+// on the device from the main stream the first time it is needed; the single-RHS kernels never see it.
+struct NfTask { // one dense unit (or the part of it that falls into one near-field stage): h x w panel, main stream -> near-field stream
+    uint64_t src_off, dst_off; // bytes
+    uint16_t h, w, src_ld, dst_ld;
+    uint32_t reserved[2];
+};
+static_assert(sizeof(NfTask) == 32, "NfTask must be 32 bytes");
+struct NearFieldLayout {
+    std::vector<BlockDesc> blocks; // only the target blocks that hold dense units
+    std::vector<StageDesc> stages;
+    std::vector<uint32_t> order;
+    std::vector<unsigned char> aux_apply; // one run per stage: all the rows, K columns = rows of the input matrix
+    std::vector<unsigned char> headers;   // 16 bytes per stage (StageHeader with no unit)
+    std::vector<uint64_t> hdr_off;        // n_stages + 1 (= 16 st)
+    std::vector<NfTask> tasks;
+    uint64_t stream_bytes  = 0;
+    uint32_t aux_max_bytes = 0;
+    uint64_t coefficients  = 0; // panel entries, zeros included
+    bool empty() const { return blocks.empty(); }
 };
 
 // Host description of one side, produced by the packer. Device copies are owned by the handle.

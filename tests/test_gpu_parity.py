@@ -115,7 +115,9 @@ def test_tensor_core_path_from_two_right_hand_sides(capi, dtype_code):
                 flat.oracle_matrix_product_row_major(trans, 0.5, X, -1.5, Yo, mu)
                 op.add_matrix_product_row_major(trans, 0.5, X, -1.5, Yg, mu)
                 assert rel_err(Yg, Yo) < TOL, (trans, mu)
-                assert op.launch_count() - l0 <= 7  # one multi-RHS pass sequence (staging of the group + twice under symmetry), not mu products
+                # one multi-RHS pass sequence (staging of the group + twice under symmetry + the near-field pass and, the first time, the
+                # two launches that build the near-field panels), not mu products of three passes each
+                assert op.launch_count() - l0 <= 10
         op.close()
     finally:
         capi.set_option("mrhs_min", 0)
@@ -331,3 +333,36 @@ def test_page_locked_host_vectors_zero_copy(capi, name):
             capi.host_unregister(y_pin)
         assert rel_err(y_page, e["y_seq"]) < TOL
     op.close()
+
+
+@pytest.mark.parametrize("nf_rows", [0, 64, 24])
+@pytest.mark.parametrize("dtype_code,symmetric", [(0, None), (1, None), (0, "S"), (1, "H")])
+def test_near_field_panels_of_the_multi_rhs_product(capi, dtype_code, symmetric, nf_rows):
+    """Option m_near_field = 1: for the multi-RHS product 'N' the dense leaves of a target block are applied from ONE
+    block-sparse panel per block (or per group of m_nf_rows rows), built on the device from the main stream, and skipped in
+    the runs of the main stream (RunDesc::K_lr). Same results — on a block tree, and on overlapping leaf lists where the
+    panels must add up."""
+    from oracle.flatcase import random_flatcase
+
+    capi.set_option("m_near_field", 1)
+    capi.set_option("m_nf_rows", nf_rows)
+    try:
+        cases = [random_flatcase(seed=3, dtype_code=dtype_code, symmetric=symmetric, nb_rows=700, nb_cols=530, n_leaves=150, max_dim=300, max_rank=40)]
+        if symmetric is None:
+            cases.append(load_golden("d_N" if dtype_code == 0 else "z_N_helmholtz")[0])
+        for flat in cases:
+            op = capi.Operator(flat.desc)
+            rng = np.random.default_rng(5)
+            for trans in valid_trans(flat.symmetry):
+                ni, no = (flat.nb_cols, flat.nb_rows) if trans == "N" else (flat.nb_rows, flat.nb_cols)
+                for mu in (8, 33, 70):
+                    am, bm = (0.5, 2.0) if flat.np_dtype == np.float64 else (0.5 - 0.3j, 2.0 + 0.25j)
+                    X, Y0 = rnd(rng, ni * mu, flat.np_dtype), rnd(rng, no * mu, flat.np_dtype)
+                    Yo, Yg = Y0.copy(), Y0.copy()
+                    flat.oracle_matrix_product_row_major(trans, am, X, bm, Yo, mu)
+                    op.add_matrix_product_row_major(trans, am, X, bm, Yg, mu)
+                    assert rel_err(Yg, Yo) < TOL, (trans, mu, rel_err(Yg, Yo))
+            op.close()
+    finally:
+        capi.set_option("m_near_field", 0)
+        capi.set_option("m_nf_rows", 0)
