@@ -116,8 +116,6 @@ class htb_packed_side(C.Structure):
         ("dense_tasks", C.c_void_p),
         ("n_lowrank_tasks", C.c_int64),
         ("lowrank_tasks", C.c_void_p),
-        ("ld_pad_rows", C.c_int32),
-        ("reserved", C.c_int32),
     ]
 
 

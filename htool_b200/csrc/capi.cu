@@ -33,7 +33,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 namespace {
 std::mutex g_option_mutex;
 std::map<std::string, int64_t> g_options = {
-    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 4096}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 0}, {"m_b_ring_log2", 3}, {"m_reduce_ring_stages", 0}, {"mrhs_min", 0}, {"pack_generate_dense", 0}, {"sort_units", 1}, {"reduce_blocks_per_cta", 0}, {"m_reduce_warps", 24}, {"m_pad", 4}, {"m_b_producers", 3}, {"m_stage_input", 1}, {"m_small_runs", 1}, {"m_reduce_split", 1}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}, {"aca_fma_axpy", 0}, {"aca_rank_guess", 16}, {"aca_dots", 0}, {"upload_headers_only", 1}, {"ld_pad_rows", 0}, {"m_near_field", 0}, {"m_nf_rows", 0}};
+    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 4096}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 0}, {"m_b_ring_log2", 3}, {"m_reduce_ring_stages", 0}, {"mrhs_min", 0}, {"pack_generate_dense", 0}, {"sort_units", 1}, {"reduce_blocks_per_cta", 0}, {"m_reduce_warps", 24}, {"m_pad", 4}, {"m_b_producers", 3}, {"m_stage_input", 1}, {"m_small_runs", 1}, {"m_reduce_split", 1}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}, {"aca_fma_axpy", 0}, {"aca_rank_guess", 16}, {"aca_dots", 0}, {"upload_headers_only", 1}, {"m_near_field", 0}, {"m_nf_rows", 0}};
 
 int64_t option(const char *key) {
     std::lock_guard<std::mutex> lock(g_option_mutex);
@@ -920,7 +920,6 @@ static int create_impl(const htb_hmatrix_desc *desc, const htb_generator_desc *g
     popt.generate_dense = gen != nullptr;
     popt.sort_units     = static_cast<int>(option("sort_units"));
     popt.block_rows  = static_cast<int>(option("block_rows"));
-    popt.ld_pad_rows = static_cast<int>(option("ld_pad_rows"));
     popt.near_field  = option("m_near_field") != 0;
     popt.nf_rows     = static_cast<int>(std::max<int64_t>(0, std::min<int64_t>(128, option("m_nf_rows"))));
     popt.piece_cols  = static_cast<int>(option("piece_cols"));
@@ -959,7 +958,6 @@ static int create_impl(const htb_hmatrix_desc *desc, const htb_generator_desc *g
     h->uplo           = desc->uplo_for_leaves ? desc->uplo_for_leaves : 'N';
     h->scratch_elems  = pk->scratch_elems;
     h->launch_cfg.block_rows  = pk->opt.block_rows; // resolved (0 = automatic)
-    h->launch_cfg.ld_pad_rows = pk->opt.ld_pad_rows;
     h->launch_cfg.stage_bytes = popt.stage_bytes;
     h->launch_cfg.cseg_bytes  = popt.cseg_bytes;
     h->launch_cfg.ring_stages        = static_cast<int>(option("ring_stages"));
@@ -1513,7 +1511,6 @@ int htb_pack_host(const htb_hmatrix_desc *desc, int side, htb_packed_side *out) 
         return fail(HTB_ERR_INVALID, "invalid argument");
     PackOptions popt;
     popt.block_rows  = static_cast<int>(option("block_rows"));
-    popt.ld_pad_rows = static_cast<int>(option("ld_pad_rows"));
     popt.near_field  = option("m_near_field") != 0;
     popt.nf_rows     = static_cast<int>(std::max<int64_t>(0, std::min<int64_t>(128, option("m_nf_rows"))));
     popt.piece_cols  = static_cast<int>(option("piece_cols"));
@@ -1564,7 +1561,6 @@ int htb_pack_host(const htb_hmatrix_desc *desc, int side, htb_packed_side *out) 
         out->dense_tasks   = own->layout.dense_tasks.data();
         out->n_lowrank_tasks = static_cast<int64_t>(own->layout.lr_tasks.size());
         out->lowrank_tasks   = own->layout.lr_tasks.data();
-        out->ld_pad_rows     = pk.opt.ld_pad_rows;
     } catch (const std::exception &ex) {
         return fail(HTB_ERR_INVALID, ex.what());
     }

@@ -128,7 +128,6 @@ struct KernelSide {
     const unsigned char *stream;
     unsigned long long cs_base;
     int block_rows, stage_bytes, cseg_bytes, ring_stages, evict_first;
-    uint32_t ld_pad; // unit_ld's pad_rows of the store
 };
 
 // Shared-memory carve-up common to both kernels: [ring (slot = stage [+ c segment]) | vec | barriers]
@@ -291,12 +290,12 @@ __device__ __forceinline__ void reduce_batch(const T *P, uint32_t ld, uint32_t w
 
 // REDUCE of one coefficient-carrying unit: out[k] = sum_i op(P[i,k]) xin[row0 + i], k < w
 template <typename T, bool CONJ>
-__device__ __forceinline__ void reduce_unit(const Unit &un, const T *data, const T *xin, T *scratch, int lane, uint32_t ld_pad) {
+__device__ __forceinline__ void reduce_unit(const Unit &un, const T *data, const T *xin, T *scratch, int lane) {
     constexpr int R = Rows<T>::R;
     const uint32_t row0 = unit_row0(un.geom), h = unit_h(un.geom), w = unit_w(un.geom);
     T *out            = scratch + un.out;
     const T *P        = data + un.data_off;
-    const uint32_t ld = unit_ld(h, sizeof(T), ld_pad);
+    const uint32_t ld = unit_ld(h, sizeof(T));
     const LaneMap m   = lane_map<R>(h, lane);
     uint32_t off[kMaxQ];
     T xv[kMaxQ][R];
@@ -377,12 +376,12 @@ __device__ __forceinline__ void fused_batch(const T *P, uint32_t ld, uint32_t w,
 }
 
 template <typename T, bool CONJ, bool CONJ2>
-__device__ __forceinline__ void fused_unit(const Unit &un, const T *data, const T *c, const T *xin, T *yacc, T *scratch2, int lane, uint32_t ld_pad) {
+__device__ __forceinline__ void fused_unit(const Unit &un, const T *data, const T *c, const T *xin, T *yacc, T *scratch2, int lane) {
     constexpr int R = Rows<T>::R;
     const uint32_t row0 = unit_row0(un.geom), h = unit_h(un.geom), w = unit_w(un.geom);
     T *out            = scratch2 + un.out;
     const T *P        = data + un.data_off;
-    const uint32_t ld = unit_ld(h, sizeof(T), ld_pad);
+    const uint32_t ld = unit_ld(h, sizeof(T));
     const LaneMap m   = lane_map<R>(h, lane);
     uint32_t off[kMaxQ];
     T xv[kMaxQ][R], acc[kMaxQ][R];
@@ -528,7 +527,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 16 ? 3 : 0) reduce_kern
                 const Unit un = units[u];
                 if (a.twice_only && !unit_twice(un.geom))
                     continue;
-                reduce_unit<T, CONJ>(un, data, xin, a.scratch, lane, ks.ld_pad);
+                reduce_unit<T, CONJ>(un, data, xin, a.scratch, lane);
             }
             ubase = (ubase - hdr.n_panel) & (kConsumerWarps - 1); // == (warp - units dealt so far) mod 8
             __syncwarp();
@@ -609,13 +608,13 @@ __global__ void __launch_bounds__(kThreads, FUSED ? (sizeof(T) == 16 ? 2 : 3) : 
                 if (a.twice_only && !unit_twice(un.geom))
                     continue;
                 if (FUSED && unit_twice(un.geom)) { // both applications from one walk over the panel
-                    fused_unit<T, CONJ, CONJ2>(un, data, cseg + un.cslot, xin, yacc, a.scratch2, lane, ks.ld_pad);
+                    fused_unit<T, CONJ, CONJ2>(un, data, cseg + un.cslot, xin, yacc, a.scratch2, lane);
                     continue;
                 }
                 const uint32_t row0 = unit_row0(un.geom), h = unit_h(un.geom), w = unit_w(un.geom);
                 const T *c = cseg + un.cslot;
                 const T *P        = data + un.data_off;
-                const uint32_t ld = unit_ld(h, sizeof(T), ks.ld_pad);
+                const uint32_t ld = unit_ld(h, sizeof(T));
                 const LaneMap m   = lane_map<R>(h, lane);
                 T acc[kMaxQ][R];
 #pragma unroll
@@ -804,7 +803,7 @@ inline void launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t sme
 }
 
 inline KernelSide make_kernel_side(const SideDevice &s, const LaunchConfig &cfg, int ring) {
-    return KernelSide{s.blocks, s.stages, s.order, s.stream, s.cs_base, cfg.block_rows, cfg.stage_bytes, cfg.cseg_bytes, ring, cfg.evict_first, static_cast<uint32_t>(cfg.ld_pad_rows)};
+    return KernelSide{s.blocks, s.stages, s.order, s.stream, s.cs_base, cfg.block_rows, cfg.stage_bytes, cfg.cseg_bytes, ring, cfg.evict_first};
 }
 
 inline bool is_zero(double v) { return v == 0.; }

@@ -34,7 +34,6 @@ struct SideDevice {
 
 struct LaunchConfig {
     int block_rows  = 128;
-    int ld_pad_rows = 0;    // unit_ld's pad_rows of the store (packer option ld_pad_rows)
     int stage_bytes = 24576;
     int cseg_bytes  = 4096;
     int ring_stages = 2;        // APPLY ring depth (slot = stage + c segment)

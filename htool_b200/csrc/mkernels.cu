@@ -82,7 +82,6 @@ struct MSide {
     const unsigned char *aux; // aux_reduce or aux_apply of the side, by kernel
     const MUnit *munits;
     int block_rows, stage_bytes, aux_bytes, ring_stages;
-    uint32_t ld_pad; // unit_ld's pad_rows of the store
 };
 
 struct RingPos {
@@ -249,7 +248,7 @@ __global__ void __launch_bounds__((kReduceWarpsMax + 1) * 32) reduce_m_kernel(MS
             const uint32_t K = rd.K, ntiles = (K + 7u) >> 3;
             const uint32_t hc = static_cast<uint32_t>(rd.h_minus_1) + 1u;
             const uint32_t h  = hc << CS;                                      // real rows
-            const uint32_t ld = CPLX ? 2u * unit_ld(hc, 16, ks.ld_pad) : unit_ld(hc, sizeof(double), ks.ld_pad); // real leading dimension
+            const uint32_t ld = CPLX ? 2u * hc : unit_ld(hc, sizeof(double)); // real leading dimension
             const double *P   = data + (static_cast<size_t>(rd.data_off) << CS);
             const double *xrow = Xs + ((static_cast<uint32_t>(rd.row0) << CS) + tig) * XS + g;
             // jobs of this run: (tile of 8 columns) x (one of S groups of column tiles of the right-hand sides). S > 1 for tall
@@ -654,7 +653,7 @@ __global__ void __launch_bounds__((kApplyWarps + 1 + kBProducersMax) * 32, 1) ap
             const int jlo = tlo <= par ? 0 : (tlo - par + PAR - 1) / PAR, jhi = thi >= par ? (thi - par) / PAR : -1;
             const bool mine = jlo <= jhi && jlo < NJ; // (a warp without rows in the run still walks its chunks: the B ring is released by all)
             const uint32_t Kr = Krun << CS; // contraction length
-            const uint32_t ld = CPLX ? 2u * unit_ld(static_cast<uint32_t>(h), 16, ks.ld_pad) : unit_ld(static_cast<uint32_t>(h), sizeof(double), ks.ld_pad);
+            const uint32_t ld = CPLX ? 2u * static_cast<uint32_t>(h) : unit_ld(static_cast<uint32_t>(h), sizeof(double));
             const size_t pstep = static_cast<size_t>(4 >> CS) * ld;
             // this lane's panel column (contraction index tig) at my row of tile 0 — dereferenced only where the row exists
             const double *Prun = data + (static_cast<size_t>(rd.data_off) << CS) + static_cast<size_t>(tig >> CS) * ld + (CPLX ? (tig & 1) : 0);
@@ -902,7 +901,7 @@ __global__ void nf_copy_kernel(const NfTask *tasks, long long n_tasks, const uns
 inline size_t aux_part(const LaunchConfig &cfg) { return cfg.m_aux_bytes > 0 ? static_cast<size_t>(cfg.m_aux_bytes) : aux_slot_bytes(static_cast<uint32_t>(cfg.cseg_bytes)); }
 
 inline MSide make_mside(const SideDevice &s, const LaunchConfig &cfg, int ring, bool apply_role) {
-    return MSide{s.blocks, s.stages, s.order, s.stream, apply_role ? s.aux_apply : s.aux_reduce, s.munits, cfg.m_x_rows > 0 ? cfg.m_x_rows : cfg.block_rows, cfg.stage_bytes, static_cast<int>(aux_part(cfg)), ring, static_cast<uint32_t>(cfg.ld_pad_rows)};
+    return MSide{s.blocks, s.stages, s.order, s.stream, apply_role ? s.aux_apply : s.aux_reduce, s.munits, cfg.m_x_rows > 0 ? cfg.m_x_rows : cfg.block_rows, cfg.stage_bytes, static_cast<int>(aux_part(cfg)), ring};
 }
 
 } // namespace

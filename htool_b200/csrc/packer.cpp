@@ -74,9 +74,7 @@ Packer::Packer(const htb_hmatrix_desc &desc, const PackOptions &o) : dtype(desc.
         throw std::runtime_error("invalid piece_cols / stage_bytes / cseg_bytes");
     // a unit (block_rows x piece) and its descriptor must fit one stage; its c vector one c segment
     piece = 1;
-    if (opt.ld_pad_rows < 0 || opt.ld_pad_rows > 65535)
-        throw std::runtime_error("ld_pad_rows must be in [0, 65535]");
-    const size_t max_ld = unit_ld(static_cast<uint32_t>(opt.block_rows), esize, static_cast<uint32_t>(opt.ld_pad_rows)); // (the tallest unit has the largest leading dimension)
+    const size_t max_ld = unit_ld(static_cast<uint32_t>(opt.block_rows), esize); // (the tallest unit has the largest leading dimension)
     while (piece * 2 <= opt.piece_cols && 32u + max_ld * (piece * 2) * esize <= static_cast<size_t>(opt.stage_bytes))
         piece *= 2;
     if (32u + max_ld * piece * esize > static_cast<size_t>(opt.stage_bytes))
@@ -723,7 +721,7 @@ void Packer::make_near_field(const std::vector<std::vector<NfSrc>> &per_block) {
                 continue;
             std::sort(cols.begin(), cols.end());
             cols.erase(std::unique(cols.begin(), cols.end()), cols.end());
-            const uint32_t ld  = unit_ld(hsub, esize, static_cast<uint32_t>(opt.ld_pad_rows));
+            const uint32_t ld  = unit_ld(hsub, esize);
             const uint32_t kst = std::max<uint32_t>(1u, std::min<uint32_t>(k_cap, static_cast<uint32_t>((static_cast<size_t>(opt.stage_bytes) - 16u) / (static_cast<size_t>(ld) * esize))));
             std::vector<uint64_t> stage_off;
             std::vector<size_t> run_at; // where the stage's RunDesc sits in out.aux
@@ -877,7 +875,7 @@ void Packer::walk_block(int s, int b, Emit &&emit) const {
         u.row0 = static_cast<uint32_t>(a + lo - bs);
         u.h    = static_cast<uint32_t>(hi - lo);
         u.p0   = static_cast<uint32_t>(lo);
-        u.ld   = unit_ld(u.h, esize, static_cast<uint32_t>(opt.ld_pad_rows));
+        u.ld   = unit_ld(u.h, esize);
         for (int p = 0; p < n_pieces(l); p++) {
             u.ui    = ui++;
             u.piece = p;

@@ -73,16 +73,11 @@ HTB_HD inline uint32_t unit_h(uint32_t g) { return ((g >> 8) & 0xffu) + 1u; }
 HTB_HD inline uint32_t unit_w(uint32_t g) { return (g >> 16) & 0xffu; }
 HTB_HD inline uint32_t unit_kind(uint32_t g) { return (g >> 24) & 0x3u; }
 HTB_HD inline uint32_t unit_twice(uint32_t g) { return (g >> 26) & 0x1u; }
-// Leading dimension of a unit of height h. double: even (16-byte panel columns). Tall panels (h >= pad_rows real rows,
-// pad_rows > 0: packer option ld_pad_rows) get the smallest leading dimension >= h that is = 4 (mod 8) REAL doubles
-// (complex: = 2 (mod 4) elements): the DMMA fragment loads of the multi-RHS kernels — lane (g, tig) reads
-// P[row g][column tig] = address tig * ld + g — are then free of shared-memory bank conflicts (the four columns of a
-// half warp fall on four different groups of 4 bank pairs), where ld = 122 costs two wavefronts per load and ld = 128 four.
-HTB_HD inline uint32_t unit_ld(uint32_t h, size_t esize, uint32_t pad_rows) {
-    if (esize == 8)
-        return (pad_rows && h >= pad_rows) ? ((h + 3u) & ~7u) + 4u : (h + 1u) & ~1u;
-    return (pad_rows && 2u * h >= pad_rows) ? ((h + 1u) & ~3u) + 2u : h;
-}
+// leading dimension of a unit of height h (double: even, so that panel columns are 16-byte aligned). A leading dimension = 4 (mod 8)
+// doubles for the tall panels (conflict-free DMMA fragment loads: ld = 122 costs two shared-memory wavefronts per load) was measured
+// at N = 1e6: mu = 64 18.07 vs 18.28 ms, mu = 1 3.36 vs 3.30 ms — the fragment loads are not what limits the multi-RHS kernels, and the
+// 1.2 % of extra bytes cost the single-RHS product more. Not kept.
+HTB_HD inline uint32_t unit_ld(uint32_t h, size_t esize) { return esize == 8 ? (h + 1u) & ~1u : h; }
 inline uint32_t make_geom(uint32_t row0, uint32_t h, uint32_t w, uint32_t kind, uint32_t twice) {
     return (row0 & 0xffu) | (((h - 1u) & 0xffu) << 8) | ((w & 0xffu) << 16) | ((kind & 3u) << 24) | ((twice & 1u) << 26);
 }
@@ -209,9 +204,6 @@ struct PackOptions {
     int block_rows  = 0;     // 32, 64 or 128; 0 = automatic (128 for double, 64 for complex<double>)
     bool near_field = false; // build the multi-RHS near-field layout (NearFieldLayout; needs sort_units). Off by default: measured, DESIGN.md 6
     int nf_rows     = 0;     // rows of a near-field panel (rounded up to a multiple of 8; 0: one panel over all the rows of a block)
-    int ld_pad_rows = 0;     // panels of >= this many real rows get a bank-conflict-free leading dimension (unit_ld); 0 = never (default:
-                             // measured at N = 1e6, 96 vs 0: mu = 64 18.07 vs 18.28 ms, mu = 1 3.36 vs 3.30 ms — the fragment loads are not
-                             // what limits the multi-RHS kernels, and the 1.2 % of extra bytes cost the single-RHS product more)
     int piece_cols  = 16;    // columns of a unit (<= 32); lowered automatically so that a unit fits a stage
     int stage_bytes = 24576; // bulk-copy granule of the coefficient stream, multiple of 16
     int cseg_bytes  = 4096;  // capacity of a stage's c segment, multiple of 16 (512 columns: stages of small-cluster runs still fill up)

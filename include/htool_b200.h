@@ -345,8 +345,6 @@ typedef struct htb_packed_side {
                                * device pool of htb_create_compressed); DenseTask with lrow = leaf index, lcol = side, p0 = first row of
                                * the panel inside the leaf's factor, k0 = first term */
     const void *lowrank_tasks;
-    int32_t ld_pad_rows;      /* store.hpp unit_ld: panels of >= this many real rows have a leading dimension = 4 (mod 8) doubles */
-    int32_t reserved;
 } htb_packed_side;
 int htb_pack_host(const htb_hmatrix_desc *desc, int side, htb_packed_side *out);
 int htb_pack_free(htb_packed_side *packed);

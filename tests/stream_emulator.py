@@ -27,11 +27,9 @@ PANEL_BUFFER_ELEMS = 4608
 assert BLOCK_DT.itemsize == 32 and STAGE_DT.itemsize == 32 and COMBINE_DT.itemsize == 16 and COMBINE_DST_DT.itemsize == 8 and UNIT_DT.itemsize == 16
 
 
-def unit_ld(h, isz, pad_rows):
-    """store.hpp unit_ld: leading dimension of a panel of h rows."""
-    if isz == 8:
-        return ((h + 3) & ~7) + 4 if pad_rows and h >= pad_rows else (h + 1) & ~1
-    return ((h + 1) & ~3) + 2 if pad_rows and 2 * h >= pad_rows else h
+def unit_ld(h, isz):
+    """store.hpp unit_ld: leading dimension of a panel of h rows (double: even)."""
+    return (h + 1) & ~1 if isz == 8 else h
 
 
 def _view(addr, count, dt):
@@ -57,7 +55,6 @@ class PackedSide:
         self.munits = _view(p.munits, p.n_munits, MUNIT_DT)
         self.combine_m = _view(p.combine_m, p.n_combine_m, COMBINE_DT)
         self.mscratch_elems, self.block_rows = p.mscratch_elems, p.block_rows
-        self.ld_pad_rows = p.ld_pad_rows
         self.stream = _view(p.stream, p.stream_bytes, np.dtype("u1"))
         self.stream_bytes = p.stream_bytes
         self.aux = {"reduce": _view(p.aux_reduce, p.aux_bytes, np.dtype("u1")), "apply": _view(p.aux_apply, p.aux_bytes, np.dtype("u1"))}
@@ -81,7 +78,7 @@ class PackedSide:
         covered = 0
         for rd in runs:
             h, K = int(rd["h_minus_1"]) + 1, int(rd["K"])
-            ld = unit_ld(h, isz, self.ld_pad_rows)
+            ld = unit_ld(h, isz)
             panel = data[int(rd["data_off"]): int(rd["data_off"]) + ld * K].reshape(K, ld).T[:h, :]
             covered += K
             yield int(rd["row0"]), h, int(rd["flags"]) & 1, panel, cols[int(rd["col0"]): int(rd["col0"]) + K]
@@ -104,7 +101,7 @@ class PackedSide:
             row0, h, w, kind, twice = g & 0xFF, ((g >> 8) & 0xFF) + 1, (g >> 16) & 0xFF, (g >> 24) & 3, (g >> 26) & 1
             panel = None
             if kind != UNIT_ADDVEC:
-                ld = unit_ld(h, isz, self.ld_pad_rows)
+                ld = unit_ld(h, isz)
                 full = data[int(u["data_off"]): int(u["data_off"]) + ld * w].reshape(w, ld).T  # column-major
                 assert not full[h:, :].any()  # pad rows are zero
                 panel = full[:h, :]
