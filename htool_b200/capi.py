@@ -116,6 +116,9 @@ class htb_packed_side(C.Structure):
         ("dense_tasks", C.c_void_p),
         ("n_lowrank_tasks", C.c_int64),
         ("lowrank_tasks", C.c_void_p),
+        ("header_bytes", C.c_int64),
+        ("headers", C.c_void_p),
+        ("header_offsets", C.c_void_p),
     ]
 
 

@@ -1503,7 +1503,8 @@ static int product_user(htb_handle h, char trans, const void *alpha, const void 
 
 struct PackedOwner {
     SideLayout layout;
-    std::vector<char> stream;
+    std::vector<char> stream, headers;
+    std::vector<uint64_t> header_offsets;
 };
 
 int htb_pack_host(const htb_hmatrix_desc *desc, int side, htb_packed_side *out) {
@@ -1561,6 +1562,15 @@ int htb_pack_host(const htb_hmatrix_desc *desc, int side, htb_packed_side *out) 
         out->dense_tasks   = own->layout.dense_tasks.data();
         out->n_lowrank_tasks = static_cast<int64_t>(own->layout.lr_tasks.size());
         out->lowrank_tasks   = own->layout.lr_tasks.data();
+        out->header_bytes = 0, out->headers = nullptr, out->header_offsets = nullptr;
+        if (pk.all_on_device && !own->layout.blocks.empty()) { // what upload_store sends instead of the stream (upload_headers_only)
+            own->header_offsets = pk.header_offsets(side);
+            own->headers.resize(own->header_offsets.back());
+            pk.fill_headers(side, 0, static_cast<int>(own->layout.blocks.size()), own->headers.data());
+            out->header_bytes   = static_cast<int64_t>(own->headers.size());
+            out->headers        = own->headers.data();
+            out->header_offsets = own->header_offsets.data();
+        }
     } catch (const std::exception &ex) {
         return fail(HTB_ERR_INVALID, ex.what());
     }

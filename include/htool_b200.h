@@ -345,6 +345,9 @@ typedef struct htb_packed_side {
                                * device pool of htb_create_compressed); DenseTask with lrow = leaf index, lcol = side, p0 = first row of
                                * the panel inside the leaf's factor, k0 = first term */
     const void *lowrank_tasks;
+    int64_t header_bytes;     /* when NO leaf carries data (device assembly): the stage headers packed back to back, what travels instead of */
+    const void *headers;      /* the stream (header of stage st = headers[header_offsets[st] .. header_offsets[st + 1]) -> stream + stage byte_off); */
+    const void *header_offsets; /* (n_stages + 1) x uint64; NULL / 0 when some leaf carries host data                                      */
 } htb_packed_side;
 int htb_pack_host(const htb_hmatrix_desc *desc, int side, htb_packed_side *out);
 int htb_pack_free(htb_packed_side *packed);

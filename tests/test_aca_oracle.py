@@ -115,3 +115,45 @@ def test_lowrank_task_table_rebuilds_the_host_streams(name):
 
 def test_diag_flags_constant():
     assert DIAG_FLAGS == 0x6
+
+
+@pytest.mark.parametrize("name", ["d_SL", "d_rect", "z_HU"])
+def test_headers_only_upload_rebuilds_the_stream(name):
+    """Device assembly (no leaf carries host data): only the stage headers travel (htb_pack_host: headers + header_offsets) and a
+    kernel puts them into the zeroed stream. Zeros + the scattered headers must equal the stream the packer fills on the host."""
+    import ctypes as C
+
+    from aca_cases import TASK_DT  # noqa: F401  (same module: keeps the struct layouts in one place)
+    from htool_b200 import capi
+
+    case = AcaCase.golden(name)
+    f = case.flat
+    desc0, keep = case.stripped_desc()
+    lv = np.frombuffer(keep, dtype=LEAF_NP_DTYPE)
+    lv["rank"][: f.table.shape[0]] = f.table[:, 4]  # (ranks known, no data anywhere)
+    lib = capi.load()
+    capi.set_option("pack_generate_dense", 1)
+    try:
+        for side in (0, 1):
+            p = capi.htb_packed_side()
+            capi.check(lib, lib.htb_pack_host(C.byref(desc0), side, C.byref(p)))
+            assert p.header_bytes > 0 and p.headers and p.header_offsets
+            stream = np.frombuffer((C.c_char * p.stream_bytes).from_address(p.stream), dtype=np.uint8).copy()
+            headers = np.frombuffer((C.c_char * p.header_bytes).from_address(p.headers), dtype=np.uint8)
+            offs = np.frombuffer((C.c_char * (8 * (p.n_stages + 1))).from_address(p.header_offsets), dtype=np.uint64).astype(np.int64)
+            stages = np.frombuffer((C.c_char * (32 * p.n_stages)).from_address(p.stages), dtype=np.dtype([("byte_off", "<u8"), ("rest", "V24")]))
+            rebuilt = np.zeros_like(stream)
+            for st in range(p.n_stages):
+                n = int(offs[st + 1] - offs[st])
+                o = int(stages["byte_off"][st])
+                rebuilt[o: o + n] = headers[int(offs[st]): int(offs[st]) + n]
+            assert int(offs[-1]) == p.header_bytes and p.header_bytes < 0.25 * p.stream_bytes
+            assert np.array_equal(rebuilt, stream)
+            lib.htb_pack_free(C.byref(p))
+        # a descriptor whose leaves carry data has no header-only form
+        p = capi.htb_packed_side()
+        capi.check(lib, lib.htb_pack_host(C.byref(f.desc), 0, C.byref(p)))
+        assert p.header_bytes == 0 and not p.headers
+        lib.htb_pack_free(C.byref(p))
+    finally:
+        capi.set_option("pack_generate_dense", 0)
