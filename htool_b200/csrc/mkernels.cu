@@ -355,13 +355,24 @@ __device__ __forceinline__ void produce_b(const MSide &ks, const BlockDesc &bd, 
             mbar_arrive(smem_u32(&br.full[open & br.mask]));
         open = -1;
     };
+    // b_global: the column tables are read from GLOBAL memory (the side's aux array) instead of the stage ring, so that the B rows
+    // are fetched as far ahead as the B ring allows (8 chunks) and not only as far as the stage ring does (its 3 - 4 slots)
+    uint32_t st_next = 0; // b_global: next stage of the block to look at
     for (uint32_t q = 0; q < n_my_stages; q++, pos.advance(ks.ring_stages)) {
-        mbar_wait(smem_u32(&full[pos.slot]), pos.phase);
-        const unsigned char *stage = ring + static_cast<size_t>(pos.slot) * slot_bytes;
-        const AuxHeader ah         = *reinterpret_cast<const AuxHeader *>(stage + ks.stage_bytes);
-        const RunDesc *runs        = reinterpret_cast<const RunDesc *>(stage + ks.stage_bytes + sizeof(AuxHeader));
-        const uint32_t *cols       = reinterpret_cast<const uint32_t *>(runs + ah.n_runs);
-        bpos                       = (bpos + 31u) & ~31u;
+        const unsigned char *auxrec;
+        if (a.b_global) {
+            StageDesc sd = ks.stages[bd.first_stage + st_next++];
+            while (a.twice_only && !(sd.flags & 1u))
+                sd = ks.stages[bd.first_stage + st_next++];
+            auxrec = ks.aux + static_cast<size_t>(sd.aux_off16) * 16u;
+        } else {
+            mbar_wait(smem_u32(&full[pos.slot]), pos.phase);
+            auxrec = ring + static_cast<size_t>(pos.slot) * slot_bytes + ks.stage_bytes;
+        }
+        const AuxHeader ah   = *reinterpret_cast<const AuxHeader *>(auxrec);
+        const RunDesc *runs  = reinterpret_cast<const RunDesc *>(auxrec + sizeof(AuxHeader));
+        const uint32_t *cols = reinterpret_cast<const uint32_t *>(runs + ah.n_runs);
+        bpos                 = (bpos + 31u) & ~31u;
         for (uint32_t r = 0; r < ah.n_runs; r++) {
             const RunDesc rd = runs[r];
             if (a.twice_only && !(rd.flags & 1u))
@@ -439,7 +450,7 @@ __device__ __forceinline__ void produce_b(const MSide &ks, const BlockDesc &bd, 
             bpos += K;
         }
         publish(); // end of the stage: the consumers must not wait for the next stage to see its last chunk
-        if (lane == 0)
+        if (lane == 0 && !a.b_global)
             mbar_arrive(smem_u32(&empty[pos.slot])); // the column tables of this stage are no longer needed
     }
 }
@@ -593,7 +604,7 @@ __global__ void __launch_bounds__((kApplyWarps + 1 + kBProducersMax) * 32, 1) ap
     if (threadIdx.x == 0) {
         for (int s = 0; s < ks.ring_stages; s++) {
             mbar_init(smem_u32(&full[s]), 1);
-            mbar_init(smem_u32(&empty[s]), kApplyWarps + np); // the consumers and the B producers
+            mbar_init(smem_u32(&empty[s]), kApplyWarps + (a.b_global ? 0u : np)); // the consumers and (unless they read the tables from global memory) the B producers
         }
         for (uint32_t s = 0; s <= br.mask; s++) {
             mbar_init(smem_u32(&br.full[s]), 1); // the B producer's arrive; the rows are counted in bytes (expect_tx)
