@@ -33,7 +33,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 namespace {
 std::mutex g_option_mutex;
 std::map<std::string, int64_t> g_options = {
-    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 4096}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 0}, {"m_b_ring_log2", 3}, {"m_reduce_ring_stages", 0}, {"mrhs_min", 0}, {"pack_generate_dense", 0}, {"sort_units", 1}, {"reduce_blocks_per_cta", 0}, {"m_reduce_warps", 24}, {"m_pad", 4}, {"m_b_producers", 3}, {"m_stage_input", 1}, {"m_small_runs", 1}, {"m_reduce_split", 1}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}, {"aca_fma_axpy", 0}, {"aca_rank_guess", 16}, {"aca_dots", 0}, {"upload_headers_only", 1}, {"m_near_field", 0}, {"m_b_global", 0}, {"m_nf_rows", 0}};
+    {"block_rows", 0}, {"piece_cols", 16}, {"stage_bytes", 24576}, {"cseg_bytes", 4096}, {"ring_stages", 2}, {"reduce_ring_stages", 3}, {"evict_first", 1}, {"upload_chunk_mb", 256}, {"m_ring_stages", 0}, {"m_b_ring_log2", 3}, {"m_reduce_ring_stages", 0}, {"mrhs_min", 0}, {"pack_generate_dense", 0}, {"sort_units", 1}, {"reduce_blocks_per_cta", 0}, {"m_reduce_warps", 24}, {"m_pad", 4}, {"m_b_producers", 3}, {"m_stage_input", 1}, {"m_small_runs", 1}, {"m_reduce_split", 1}, {"fused_symmetric", 1}, {"dist_p2p", 1}, {"target_block_rows", 0}, {"zero_copy", 1}, {"tail_split", 1}, {"cta_slots", 0}, {"pdl", 1}, {"aca_fma_axpy", 0}, {"aca_rank_guess", 16}, {"aca_dots", 0}, {"upload_headers_only", 1}, {"m_near_field", 0}, {"m_b_global", 1}, {"m_fast_tall", 1}, {"m_nf_rows", 0}};
 
 int64_t option(const char *key) {
     std::lock_guard<std::mutex> lock(g_option_mutex);
@@ -514,6 +514,7 @@ static int run_product_m(htb_operator *h, char trans, const double *alpha, const
         const int pad = h->launch_cfg.m_pad;
         base.ld_in = mu * W, base.ld_out = mu * W, base.col0 = col0 * W, base.col0_in = col0 * W, base.mc = mc, base.vs = vs, base.vsp = vs + pad, base.cplx = cplx ? 1 : 0;
         base.b_global   = option("m_b_global") != 0;
+        base.fast_tall  = option("m_fast_tall") != 0;
         base.small_runs = option("m_small_runs") != 0, base.reduce_split = static_cast<int>(std::min<int64_t>(8, std::max<int64_t>(1, option("m_reduce_split"))));
         // the group's columns of the input, copied once into rows one B-ring row apart (zero padded): the input rows of a dense
         // leaf then reach the B ring with one bulk copy whatever mu is, and every row is 16 B aligned

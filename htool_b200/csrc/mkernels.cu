@@ -636,6 +636,13 @@ __global__ void __launch_bounds__((kApplyWarps + 1 + kBProducersMax) * 32, 1) ap
     const size_t bstep = static_cast<size_t>(4 >> CS) * a.vsp; // B rows per k-step
     const int my_row0  = 8 * par + g;                          // my row in tile j is my_row0 + 8 PAR j
 
+    // Block constants of the FULL-HEIGHT fast path (below): most of the coefficients sit in stages made of ONE run over all the
+    // rows of the block with <= 32 columns (a 24 KiB stage of a 122-row panel holds 25) — one chunk of the B ring, no row predicate.
+    const uint32_t ld_blk    = CPLX ? 2u * static_cast<uint32_t>(bd.nrows) : unit_ld(static_cast<uint32_t>(bd.nrows), sizeof(double));
+    const size_t pstep_blk   = static_cast<size_t>(4 >> CS) * ld_blk;
+    const size_t poff_blk    = static_cast<size_t>(tig >> CS) * ld_blk + (CPLX ? (tig & 1) : 0) + (static_cast<size_t>(my_row0) << CS);
+    const bool full_height   = a.fast_tall && ((bd.nrows - 1) >> 3) >= par + PAR * (NJ - 1); // my last tile meets rows of the block
+
     RingPos pos;
     uint32_t cpos = 0;  // position in the B stream (same walk as produce_b)
     long long cur = -1; // chunk the warp is reading
@@ -648,6 +655,45 @@ __global__ void __launch_bounds__((kApplyWarps + 1 + kBProducersMax) * 32, 1) ap
         const AuxHeader ah         = *reinterpret_cast<const AuxHeader *>(stage + ks.stage_bytes);
         const RunDesc *runs        = reinterpret_cast<const RunDesc *>(stage + ks.stage_bytes + sizeof(AuxHeader));
         cpos                       = (cpos + 31u) & ~31u;
+        if (full_height && ah.n_runs == 1u && hdr.n_units == hdr.n_panel) {
+            const RunDesc rd    = runs[0];
+            const uint32_t Krun = a.skip_dense ? rd.K_lr : rd.K;
+            if (rd.row0 == 0 && static_cast<int>(rd.h_minus_1) + 1 == bd.nrows && Krun != 0u && Krun <= 32u && !(a.twice_only && !(rd.flags & 1u))) {
+                const long long chunk = static_cast<long long>(cpos >> 5);
+                cpos += Krun;
+                enter_chunk(br, cur, chunk, lane);
+                const uint32_t Kr = Krun << CS, kfull = Kr & ~3u;
+                const double *Bl  = reinterpret_cast<const double *>(br.base + static_cast<size_t>(chunk & br.mask) * br.chunk_bytes) + static_cast<size_t>(static_cast<uint32_t>(tig) >> CS) * a.vsp + cBl;
+                const double *Pa  = data + (static_cast<size_t>(rd.data_off) << CS) + poff_blk;
+                uint32_t k        = 0;
+#pragma unroll 2
+                for (; k < kfull; k += 4) {
+                    const double b = CPLX ? bs * Bl[0] : Bl[0];
+                    double av[NJ];
+#pragma unroll
+                    for (int j = 0; j < NJ; j++)
+                        av[j] = Pa[static_cast<size_t>(8 * PAR * j) << CS];
+#pragma unroll
+                    for (int j = 0; j < NJ; j++)
+                        dmma(acc[j], av[j], b);
+                    Bl += bstep;
+                    Pa += pstep_blk;
+                }
+                if (k < Kr) { // last, partial k-step: contraction indices >= Kr meet zeros on both sides
+                    const bool kv  = k + tig < Kr;
+                    const double b = (c_valid && kv) ? bs * Bl[0] : 0.;
+#pragma unroll
+                    for (int j = 0; j < NJ; j++) {
+                        const bool rv = 8 * PAR * j + my_row0 < bd.nrows;
+                        dmma(acc[j], (kv && rv) ? Pa[static_cast<size_t>(8 * PAR * j) << CS] : 0., b);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0)
+                    mbar_arrive(smem_u32(&empty[pos.slot]));
+                continue;
+            }
+        }
         for (uint32_t r = 0; r < ah.n_runs; r++) {
             const RunDesc rd = runs[r];
             if (a.twice_only && !(rd.flags & 1u))

@@ -33,7 +33,8 @@ struct MArgs {
     int conj         = 0; // conjugate the coefficients (trans == 'C', Hermitian second application)
     int small_runs   = 1; // APPLY_M: run-private accumulators for runs of <= 5 row tiles per warp (0: the predicated per-tile walk)
     int reduce_split = 1; // REDUCE_M: jobs per 8-column tile of a tall run (groups of column tiles of the right-hand sides)
-    int b_global     = 0; // APPLY_M: the B producers read the column tables from global memory (run ahead of the stage ring)
+    int fast_tall    = 1; // APPLY_M: stage-level fast path for stages made of one full-height run of <= 32 columns
+    int b_global     = 1; // APPLY_M: the B producers read the column tables from global memory (run ahead of the stage ring)
     int skip_dense   = 0; // APPLY_M: the dense columns of the runs (their tail, RunDesc::K_lr) are applied from the near-field panels instead
 };
 

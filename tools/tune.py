@@ -54,7 +54,7 @@ def main():
         case.vector_product(args.trans, 1.0, x, 0.0, y_ref, variant="openmp")
     else:
         case.matrix_product_row_major(args.trans, 1.0, x, 0.0, y_ref, mu, variant="openmp")
-    defaults = {k: capi.get_option(k) for k in ("block_rows", "piece_cols", "stage_bytes", "cseg_bytes", "ring_stages", "reduce_ring_stages", "evict_first", "m_ring_stages", "m_reduce_ring_stages", "mrhs_min", "fused_symmetric", "target_block_rows", "tail_split", "pdl", "reduce_blocks_per_cta", "sort_units", "m_b_ring_log2", "m_reduce_warps", "m_pad", "m_stage_input", "m_small_runs", "m_reduce_split", "m_b_producers", "m_near_field", "m_nf_rows", "m_b_global")}
+    defaults = {k: capi.get_option(k) for k in ("block_rows", "piece_cols", "stage_bytes", "cseg_bytes", "ring_stages", "reduce_ring_stages", "evict_first", "m_ring_stages", "m_reduce_ring_stages", "mrhs_min", "fused_symmetric", "target_block_rows", "tail_split", "pdl", "reduce_blocks_per_cta", "sort_units", "m_b_ring_log2", "m_reduce_warps", "m_pad", "m_stage_input", "m_small_runs", "m_reduce_split", "m_b_producers", "m_near_field", "m_nf_rows", "m_b_global", "m_fast_tall")}
     stream = torch.cuda.Stream()
     x_d = torch.from_numpy(x).cuda()
     tdt = torch.float64 if dtype == np.float64 else torch.complex128
