@@ -63,8 +63,8 @@ struct DeviceGuard {
     }
 };
 
-template <typename V>
-static int upload_vector(const std::vector<V> &v, const V **dptr, std::vector<void *> &owned) {
+template <typename V, typename A>
+static int upload_vector(const std::vector<V, A> &v, const V **dptr, std::vector<void *> &owned) {
     *dptr = nullptr;
     if (v.empty())
         return HTB_OK;
@@ -839,7 +839,7 @@ int htb_download_store(htb_handle h, int side, void *dst, int64_t bytes) {
 
 // dense units of leaves that came without host data: generated on the device straight into the uploaded stream
 static int generate_dense(htb_operator *h, const Packer &pk, const htb_generator_desc *gen) {
-    const std::vector<DenseTask> &tasks = pk.side[0].dense_tasks;
+    const auto &tasks = pk.side[0].dense_tasks;
     if (tasks.empty())
         return HTB_OK;
     void *d_tasks = nullptr, *d_tp = nullptr, *d_sp = nullptr;
@@ -880,7 +880,7 @@ static int scatter_lowrank(htb_operator *h, const Packer &pk, const CompressedFa
     if (e == cudaSuccess && !cf.leaves.empty())
         e = cudaMemcpyAsync(d_leaves, cf.leaves.data(), cf.leaves.size() * sizeof(AcaLeaf), cudaMemcpyHostToDevice, h->own_stream);
     for (int s = 0; s < 2 && e == cudaSuccess; s++) {
-        const std::vector<DenseTask> &tasks = pk.side[s].lr_tasks;
+        const auto &tasks = pk.side[s].lr_tasks;
         if (tasks.empty())
             continue;
         e = cudaMalloc(&d_tasks, tasks.size() * sizeof(DenseTask));

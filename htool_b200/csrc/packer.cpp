@@ -333,6 +333,9 @@ int Packer::units_in_incidence(int s, uint32_t li, int c) const {
 
 void Packer::make_incidence(int s) {
     const int nb = static_cast<int>(side[s].blocks.size());
+    const bool tm = std::getenv("HTB_PACK_TIMING") != nullptr;
+    auto t0       = std::chrono::steady_clock::now();
+    auto lapi     = [&](const char *w) { if (tm) { auto n = std::chrono::steady_clock::now(); std::fprintf(stderr, "[htb pack]   incidence(%d) %-10s %.3f s\n", s, w, std::chrono::duration<double>(n - t0).count()); t0 = n; } };
     m_first_blk[s].assign(n_leaves, 0);
     m_nchunks[s].assign(n_leaves, 0);
     m_chunk_ptr[s].assign(n_leaves + 1, 0);
@@ -351,6 +354,7 @@ void Packer::make_incidence(int s) {
     }
     for (int b = 0; b < nb; b++)
         m_csr_ptr[s][b + 1] += m_csr_ptr[s][b];
+    lapi("count");
     const uint64_t n_inc = m_csr_ptr[s][nb];
     m_csr_leaf[s].assign(n_inc, 0);
     m_inc_index[s].assign(n_inc, 0);
@@ -361,6 +365,7 @@ void Packer::make_incidence(int s) {
             m_csr_leaf[s][e]                      = static_cast<uint32_t>(i);
             m_inc_index[s][m_chunk_ptr[s][i] + c] = e;
         }
+    lapi("scatter");
     // Inside a block, order the incidences by (first row, height, applied-twice): the panels acting on the same rows of
     // the block become consecutive in the stream and form RUNS (store.hpp) for the multi-RHS kernels. The sort is stable,
     // so leaf order — hence the summation order — stays fixed inside a run.
@@ -383,7 +388,9 @@ void Packer::make_incidence(int s) {
             m_inc_index[s][m_chunk_ptr[s][li] + (b - m_first_blk[s][li])] = e;
         }
     }
+    lapi("sort");
     m_unit_ptr[s].assign(n_inc + 1, 0);
+#pragma omp parallel for schedule(dynamic, 64)
     for (int b = 0; b < nb; b++)
         for (uint64_t e = m_csr_ptr[s][b]; e < m_csr_ptr[s][b + 1]; e++) {
             const uint32_t li    = m_csr_leaf[s][e];
@@ -391,6 +398,7 @@ void Packer::make_incidence(int s) {
         }
     for (uint64_t e = 0; e < n_inc; e++)
         m_unit_ptr[s][e + 1] += m_unit_ptr[s][e];
+    lapi("units");
 }
 
 // For every piece and direction (= consumer side cs): can its single producer write straight into its single
@@ -513,6 +521,16 @@ void Packer::make_mtables() {
         side[cs].partm_elems = off;
         base += off;
     }
+    const bool mt_timing = std::getenv("HTB_PACK_TIMING") != nullptr;
+    auto mt_last         = std::chrono::steady_clock::now();
+    auto mt_lap          = [&](const char *what) {
+        if (!mt_timing)
+            return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[htb pack]   mtables %-18s %.3f s\n", what, std::chrono::duration<double>(now - mt_last).count());
+        mt_last = now;
+    };
+    mt_lap("tf / partm (+ before)");
     mscratch_elems = base;
     if (mscratch_elems >= (uint64_t(1) << 31))
         throw std::runtime_error("multi-RHS scratch exceeds 2^31 vectors");
@@ -648,21 +666,31 @@ void Packer::make_mtables() {
             });
             close();
         }
+        mt_lap(s == 0 ? "walk side 0" : "walk side 1");
         if (aux_overflow)
             throw std::runtime_error("multi-RHS aux record exceeds its slot");
-        // concatenate the per-block aux records; every stage learns where its record is
-        uint64_t total = 0;
-        for (int b = 0; b < nb; b++)
-            total += aux_r[b].size();
+        // concatenate the per-block aux records and task lists (offsets by prefix sums, copies in parallel); every stage learns
+        // where its record is
+        std::vector<uint64_t> aux_at(static_cast<size_t>(nb) + 1, 0), dt_at(static_cast<size_t>(nb) + 1, 0), lt_at(static_cast<size_t>(nb) + 1, 0);
+        for (int b = 0; b < nb; b++) {
+            aux_at[b + 1] = aux_at[b] + aux_r[b].size();
+            dt_at[b + 1]  = dt_at[b] + tasks[b].size();
+            lt_at[b + 1]  = lt_at[b] + lr_tasks[b].size();
+            if (aux_len[b].size() != side[s].blocks[b].n_stages)
+                throw std::runtime_error("internal: aux records do not match the stages");
+        }
+        const uint64_t total = aux_at[nb];
         if (total / 16u >= (uint64_t(1) << 32))
             throw std::runtime_error("multi-RHS aux tables too large");
         side[s].aux_reduce.resize(total);
         side[s].aux_apply.resize(total);
-        uint64_t at = 0;
+        side[s].dense_tasks.resize(dt_at[nb]);
+        side[s].lr_tasks.resize(lt_at[nb]);
+        uint32_t aux_max = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(max : aux_max)
         for (int b = 0; b < nb; b++) {
             const BlockDesc &bd = side[s].blocks[b];
-            if (aux_len[b].size() != bd.n_stages)
-                throw std::runtime_error("internal: aux records do not match the stages");
+            const uint64_t at   = aux_at[b];
             if (!aux_r[b].empty()) {
                 std::memcpy(side[s].aux_reduce.data() + at, aux_r[b].data(), aux_r[b].size());
                 std::memcpy(side[s].aux_apply.data() + at, aux_a[b].data(), aux_a[b].size());
@@ -673,14 +701,17 @@ void Packer::make_mtables() {
                 sd.aux_off16  = static_cast<uint32_t>(off / 16u);
                 sd.flags      = static_cast<uint16_t>((sd.flags & 1u) | ((aux_len[b][q] / 16u) << 1));
                 off += aux_len[b][q];
-                side[s].aux_max_bytes = std::max(side[s].aux_max_bytes, aux_len[b][q]);
+                aux_max = std::max(aux_max, aux_len[b][q]);
             }
-            side[s].dense_tasks.insert(side[s].dense_tasks.end(), tasks[b].begin(), tasks[b].end());
-            side[s].lr_tasks.insert(side[s].lr_tasks.end(), lr_tasks[b].begin(), lr_tasks[b].end());
-            at += aux_r[b].size();
+            if (!tasks[b].empty())
+                std::memcpy(static_cast<void *>(side[s].dense_tasks.data() + dt_at[b]), tasks[b].data(), tasks[b].size() * sizeof(DenseTask));
+            if (!lr_tasks[b].empty())
+                std::memcpy(static_cast<void *>(side[s].lr_tasks.data() + lt_at[b]), lr_tasks[b].data(), lr_tasks[b].size() * sizeof(DenseTask));
             std::vector<unsigned char>().swap(aux_r[b]);
             std::vector<unsigned char>().swap(aux_a[b]);
         }
+        side[s].aux_max_bytes = std::max(side[s].aux_max_bytes, aux_max);
+        mt_lap(s == 0 ? "concat side 0" : "concat side 1");
     }
     if (!nf_src_side[0].empty())
         make_near_field(nf_src_side[0]); // (after both sides: the aux slot size is known)

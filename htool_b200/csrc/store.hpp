@@ -42,6 +42,10 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <memory>
+#include <new>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #ifdef __CUDACC__
@@ -246,6 +250,29 @@ struct NearFieldLayout {
     bool empty() const { return blocks.empty(); }
 };
 
+// std::vector that does not zero its elements on resize: the big side tables (hundreds of MB) are sized once and then filled by
+// all the threads of the packer — the first touch of a page happens in the parallel copy, not in a serial memset.
+template <typename T>
+struct DefaultInitAllocator : std::allocator<T> {
+    template <typename U>
+    struct rebind {
+        using other = DefaultInitAllocator<U>;
+    };
+    DefaultInitAllocator() = default;
+    template <typename U>
+    DefaultInitAllocator(const DefaultInitAllocator<U> &) {}
+    template <typename U>
+    void construct(U *ptr) noexcept(std::is_nothrow_default_constructible<U>::value) {
+        ::new (static_cast<void *>(ptr)) U;
+    }
+    template <typename U, typename... Args>
+    void construct(U *ptr, Args &&...args) {
+        ::new (static_cast<void *>(ptr)) U(std::forward<Args>(args)...);
+    }
+};
+template <typename T>
+using RawVector = std::vector<T, DefaultInitAllocator<T>>;
+
 // Host description of one side, produced by the packer. Device copies are owned by the handle.
 struct SideLayout {
     int n = 0; // length of the index space
@@ -264,10 +291,10 @@ struct SideLayout {
     std::vector<MUnit> munits;
     std::vector<CombineEntry> combine_m; // src = PARTM offset, dst_first = TF offset, n_dst unused
     uint64_t partm_base = 0, partm_elems = 0; // in vectors, inside the multi-RHS scratch [TF | PARTM[0] | PARTM[1]]
-    std::vector<unsigned char> aux_reduce, aux_apply; // per-stage aux records (runs + column tables), same offsets in both
+    RawVector<unsigned char> aux_reduce, aux_apply; // per-stage aux records (runs + column tables), same offsets in both
     uint32_t aux_max_bytes = 0;                        // largest aux record of the side: sizes the aux part of a ring slot
-    std::vector<DenseTask> dense_tasks;               // side 0 only: dense units to generate on the device
-    std::vector<DenseTask> lr_tasks;                  // units of low-rank leaves whose factors live in the device pool (lrow = leaf index, lcol = side)
+    RawVector<DenseTask> dense_tasks;                 // side 0 only: dense units to generate on the device
+    RawVector<DenseTask> lr_tasks;                    // units of low-rank leaves whose factors live in the device pool (lrow = leaf index, lcol = side)
 };
 
 } // namespace htb
