@@ -301,9 +301,14 @@ enum { HTB_PASS_REDUCE = 0, /* t = V x / op(U)^T x / op(A)^T x, streams one side
        HTB_PASS_KINDS = 4 };
 int htb_profile_passes(htb_handle h, int enable);
 int htb_get_pass_times(htb_handle h, double ms[HTB_PASS_KINDS], int64_t launches[HTB_PASS_KINDS]);
-/* Tunables for experiments: block_rows, piece_cols, stage_bytes, cseg_bytes, ring_stages, reduce_ring_stages, evict_first,
- * upload_chunk_mb; unknown keys return HTB_ERR_INVALID. Must be set before htb_create, they are read when the
- * store is packed. */
+/* Tunables for experiments; unknown keys return HTB_ERR_INVALID. Read when the store is packed (set them before htb_create):
+ * block_rows, piece_cols, stage_bytes, cseg_bytes, ring_stages, reduce_ring_stages, evict_first, upload_chunk_mb, sort_units,
+ * upload_headers_only (device assembly: only the stage headers travel), m_near_field / m_nf_rows (second, block-sparse copy of the
+ * dense leaves for the multi-RHS product 'N'; off: measured, no gain). Read by htb_create_compressed: aca_fma_axpy (the BLAS the
+ * reference was linked with fuses its axpy), aca_dots (0: guarded warp-level dot products, 1: in order, 2: replay always),
+ * aca_rank_guess (terms per block the factor pool is first sized for). Read at product time: mrhs_min (right-hand sides from which
+ * the tensor-core path is used; 0 = automatic), m_fast_tall, m_b_global, m_small_runs, m_reduce_split, m_stage_input (multi-RHS
+ * kernel variants), zero_copy, fused_symmetric, pdl, dist_p2p. */
 int htb_set_option(const char *key, int64_t value);
 int htb_get_option(const char *key, int64_t *value);
 
