@@ -551,6 +551,8 @@ void Packer::make_mtables() {
             // same walk and the same cuts as layout_block / fill_block; inside a stage panel units come first
             StageCutter cut{esize, static_cast<uint32_t>(opt.stage_bytes), static_cast<uint32_t>(opt.cseg_bytes)};
             std::vector<UnitSpec> pending;
+            std::vector<RunDesc> runs;
+            std::vector<uint32_t> col_out, col_src;
             uint64_t pos = m_unit_ptr[s][m_csr_ptr[s][b]];
             auto close   = [&]() {
                 if (cut.nu == 0)
@@ -558,8 +560,7 @@ void Packer::make_mtables() {
                 std::stable_partition(pending.begin(), pending.end(), [](const UnitSpec &u) { return u.kind != UNIT_ADDVEC; });
                 // runs: consecutive panel units on the same rows (and the same applied-twice flag) are one h x K panel
                 {
-                    std::vector<RunDesc> runs;
-                    std::vector<uint32_t> col_out, col_src;
+                    runs.clear(), col_out.clear(), col_src.clear(); // (per-block buffers: a stage must not cost three allocations)
                     uint32_t eoff = 0;
                     for (const UnitSpec &u : pending) {
                         if (u.kind == UNIT_ADDVEC)
