@@ -7,8 +7,12 @@
 #include <cstdlib>
 #include <complex>
 #include <cstring>
+#include <exception>
 #include <numeric>
 #include <stdexcept>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 namespace htb {
 
@@ -56,6 +60,40 @@ struct StageCutter {
         c_elems    = 0;
     }
 };
+
+// The serial passes over the leaf list are independent for the two sides (or the two directions): one thread each, inside
+// a team of the usual size (a team of two would make libgomp drop and re-create its other threads around every call). f
+// must not open a parallel region of its own (it would be serialised); exceptions leave through the calling thread.
+template <typename F>
+void both_sides(F &&f) {
+    std::exception_ptr err[2];
+    auto run = [&](int s) {
+        try {
+            f(s);
+        } catch (...) {
+            err[s] = std::current_exception();
+        }
+    };
+#ifdef _OPENMP
+#pragma omp parallel
+    {
+        const int t = omp_get_thread_num();
+        if (omp_get_num_threads() >= 2) {
+            if (t < 2)
+                run(t);
+        } else {
+            run(0);
+            run(1);
+        }
+    }
+#else
+    run(0);
+    run(1);
+#endif
+    for (const std::exception_ptr &e : err)
+        if (e)
+            std::rethrow_exception(e);
+}
 
 } // namespace
 
@@ -137,9 +175,10 @@ Packer::Packer(const htb_hmatrix_desc &desc, const PackOptions &o) : dtype(desc.
 
     side[0].n = nb_rows;
     side[1].n = nb_cols;
-    for (int s = 0; s < 2; s++)
-        make_blocks(s);
+    both_sides([&](int s) { make_blocks(s); });
     lap("make_blocks");
+    both_sides([&](int s) { make_incidence_lists(s); });
+    lap("incidence lists");
     for (int s = 0; s < 2; s++)
         make_incidence(s);
     lap("make_incidence");
@@ -232,8 +271,7 @@ Packer::Packer(const htb_hmatrix_desc &desc, const PackOptions &o) : dtype(desc.
             m_hdr_off[s][st + 1] = m_hdr_off[s][st] + 16u + 16u * side[s].stages[st].n_units;
     }
     lap("unit_slots");
-    for (int s = 0; s < 2; s++)
-        make_combine(s);
+    both_sides([&](int s) { make_combine(s); });
     lap("make_combine");
     make_mtables();
     lap("make_mtables");
@@ -331,11 +369,10 @@ int Packer::units_in_incidence(int s, uint32_t li, int c) const {
     return n_pieces(l);
 }
 
-void Packer::make_incidence(int s) {
+// Serial part of the incidence structure of side s (which leaf meets which block, block-major, leaf order kept inside a
+// block): independent for the two sides, run concurrently (both_sides).
+void Packer::make_incidence_lists(int s) {
     const int nb = static_cast<int>(side[s].blocks.size());
-    const bool tm = std::getenv("HTB_PACK_TIMING") != nullptr;
-    auto t0       = std::chrono::steady_clock::now();
-    auto lapi     = [&](const char *w) { if (tm) { auto n = std::chrono::steady_clock::now(); std::fprintf(stderr, "[htb pack]   incidence(%d) %-10s %.3f s\n", s, w, std::chrono::duration<double>(n - t0).count()); t0 = n; } };
     m_first_blk[s].assign(n_leaves, 0);
     m_nchunks[s].assign(n_leaves, 0);
     m_chunk_ptr[s].assign(n_leaves + 1, 0);
@@ -354,7 +391,6 @@ void Packer::make_incidence(int s) {
     }
     for (int b = 0; b < nb; b++)
         m_csr_ptr[s][b + 1] += m_csr_ptr[s][b];
-    lapi("count");
     const uint64_t n_inc = m_csr_ptr[s][nb];
     m_csr_leaf[s].assign(n_inc, 0);
     m_inc_index[s].assign(n_inc, 0);
@@ -365,7 +401,15 @@ void Packer::make_incidence(int s) {
             m_csr_leaf[s][e]                      = static_cast<uint32_t>(i);
             m_inc_index[s][m_chunk_ptr[s][i] + c] = e;
         }
-    lapi("scatter");
+}
+
+// Parallel part: order of the incidences inside every block, unit counts.
+void Packer::make_incidence(int s) {
+    const int nb         = static_cast<int>(side[s].blocks.size());
+    const uint64_t n_inc = m_csr_ptr[s][nb];
+    const bool tm = std::getenv("HTB_PACK_TIMING") != nullptr;
+    auto t0       = std::chrono::steady_clock::now();
+    auto lapi     = [&](const char *w) { if (tm) { auto n = std::chrono::steady_clock::now(); std::fprintf(stderr, "[htb pack]   incidence(%d) %-10s %.3f s\n", s, w, std::chrono::duration<double>(n - t0).count()); t0 = n; } };
     // Inside a block, order the incidences by (first row, height, applied-twice): the panels acting on the same rows of
     // the block become consecutive in the stream and form RUNS (store.hpp) for the multi-RHS kernels. The sort is stable,
     // so leaf order — hence the summation order — stays fixed inside a run.
@@ -382,9 +426,14 @@ void Packer::make_incidence(int s) {
             // 2 % faster with the dense columns interleaved with the low-rank ones than with all of them at the end of a run)
             return (r0 << 32) | (static_cast<uint64_t>(hi - lo) << 2) | ((l.flags & HTB_LEAF_APPLY_TRANSPOSED_TOO) ? 2u : 0u) | ((opt.near_field && l.rank < 0) ? 1u : 0u);
         };
-        std::stable_sort(m_csr_leaf[s].begin() + e0, m_csr_leaf[s].begin() + e1, [&](uint32_t a, uint32_t c) { return key(a) < key(c); });
+        // (keys computed once per incidence: a key reads the leaf record, a cache miss in a list of millions of leaves)
+        std::vector<std::pair<uint64_t, uint32_t>> keyed(e1 - e0);
+        for (uint64_t e = e0; e < e1; e++)
+            keyed[e - e0] = {key(m_csr_leaf[s][e]), m_csr_leaf[s][e]};
+        std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<uint64_t, uint32_t> &a, const std::pair<uint64_t, uint32_t> &c) { return a.first < c.first; });
         for (uint64_t e = e0; e < e1; e++) {
-            const uint32_t li                                              = m_csr_leaf[s][e];
+            const uint32_t li                                              = keyed[e - e0].second;
+            m_csr_leaf[s][e]                                               = li;
             m_inc_index[s][m_chunk_ptr[s][li] + (b - m_first_blk[s][li])] = e;
         }
     }
@@ -404,7 +453,7 @@ void Packer::make_incidence(int s) {
 // For every piece and direction (= consumer side cs): can its single producer write straight into its single
 // consumer slot, or does it go through partials + COMBINE? Offsets are relative to PART[cs] here.
 void Packer::make_partials() {
-    for (int cs = 0; cs < 2; cs++) {
+    both_sides([&](int cs) {
         const int ps = 1 - cs;
         m_part_off[cs].assign(m_piece_ptr[n_leaves], kDirect);
         uint64_t off = 0;
@@ -438,7 +487,7 @@ void Packer::make_partials() {
             }
         }
         side[cs].part_elems = off;
-    }
+    });
 }
 
 void Packer::make_combine(int cs) {
@@ -484,6 +533,8 @@ void Packer::make_combine(int cs) {
 // Side tables of the multi-RHS path (store.hpp, MUnit): TF offsets per piece, partial areas for pieces with several
 // producer chunks, one MUnit per unit in stage order, and the panel-buffer batches of every stage.
 void Packer::make_mtables() {
+    const bool mt_timing = std::getenv("HTB_PACK_TIMING") != nullptr;
+    auto mt_last         = std::chrono::steady_clock::now();
     const uint64_t n_pieces_total = m_piece_ptr[n_leaves];
     m_tf_off.assign(n_pieces_total, 0);
     uint64_t tf = 0;
@@ -497,9 +548,21 @@ void Packer::make_mtables() {
         }
     }
     tf_elems = tf;
-    uint64_t base = tf;
+    // sizes of the two partial areas first (a parallel sum), so that both directions are laid out concurrently
+    uint64_t partm_total[2] = {0, 0};
     for (int cs = 0; cs < 2; cs++) {
-        const int ps = 1 - cs;
+        uint64_t sum = 0;
+#pragma omp parallel for schedule(static) reduction(+ : sum)
+        for (int64_t i = 0; i < n_leaves; i++) {
+            const htb_leaf &l = m_leaves[i];
+            if (active(l) && !(l.rank < 0 && cs == 0) && m_nchunks[1 - cs][i] > 1)
+                sum += static_cast<uint64_t>(m_nchunks[1 - cs][i]) * static_cast<uint64_t>(vec_len(l));
+        }
+        partm_total[cs] = sum;
+    }
+    both_sides([&](int cs) {
+        const int ps        = 1 - cs;
+        const uint64_t base = tf + (cs == 1 ? partm_total[0] : 0u);
         m_partm_off[cs].assign(n_pieces_total, kDirect);
         side[cs].partm_base = base;
         uint64_t off        = 0;
@@ -519,10 +582,10 @@ void Packer::make_mtables() {
             }
         }
         side[cs].partm_elems = off;
-        base += off;
-    }
-    const bool mt_timing = std::getenv("HTB_PACK_TIMING") != nullptr;
-    auto mt_last         = std::chrono::steady_clock::now();
+        if (off != partm_total[cs])
+            throw std::runtime_error("internal: size of a multi-RHS partial area");
+    });
+    const uint64_t base = tf + partm_total[0] + partm_total[1];
     auto mt_lap          = [&](const char *what) {
         if (!mt_timing)
             return;
@@ -530,7 +593,7 @@ void Packer::make_mtables() {
         std::fprintf(stderr, "[htb pack]   mtables %-18s %.3f s\n", what, std::chrono::duration<double>(now - mt_last).count());
         mt_last = now;
     };
-    mt_lap("tf / partm (+ before)");
+    mt_lap("tf / partm");
     mscratch_elems = base;
     if (mscratch_elems >= (uint64_t(1) << 31))
         throw std::runtime_error("multi-RHS scratch exceeds 2^31 vectors");

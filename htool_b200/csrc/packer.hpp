@@ -80,6 +80,7 @@ class Packer {
     uint32_t producer_out(int ps, const UnitSpec &u) const;
 
     void make_blocks(int s);
+    void make_incidence_lists(int s);
     void make_incidence(int s);
     void make_partials();
     void make_combine(int cs);
