@@ -186,13 +186,13 @@ Packer::Packer(const htb_hmatrix_desc &desc, const PackOptions &o) : dtype(desc.
     lap("make_partials");
 
     // per-block stage layout
-    std::vector<uint32_t> unit_stage[2];
+    RawVector<uint32_t> unit_stage[2]; // (every entry is written by the walks: no serial zero fill of tens of MB)
     for (int s = 0; s < 2; s++) {
         const int nb = static_cast<int>(side[s].blocks.size());
         const uint64_t nu = m_unit_ptr[s].back();
-        unit_stage[s].assign(nu, 0);
-        m_unit_cslot[s].assign(nu, 0);
-        m_unit_slot[s].assign(nu, 0);
+        unit_stage[s].resize(nu);
+        m_unit_cslot[s].resize(nu);
+        m_unit_slot[s].resize(nu);
         std::vector<std::vector<StageDesc>> per_block(nb);
         std::vector<uint64_t> units(nb, 0);
         std::vector<char> twice(nb, 0);
@@ -202,34 +202,63 @@ Packer::Packer(const htb_hmatrix_desc &desc, const PackOptions &o) : dtype(desc.
             layout_block(s, b, per_block[b], unit_stage[s], units[b], t);
             twice[b] = t;
         }
+        lap(s == 0 ? "  layout walk 0" : "  layout walk 1");
+        // where every block's stages, stream bytes, c segments and aux records start (prefix sums over the blocks), then the
+        // side-wide stage table in parallel
+        std::vector<uint64_t> stage_at(static_cast<size_t>(nb) + 1, 0), c_at(static_cast<size_t>(nb) + 1, 0), aux_at(static_cast<size_t>(nb) + 1, 0);
         m_block_off[s].assign(nb + 1, 0);
-        uint64_t stream = 0, c_off = 0;
-        size_t nstages  = 0;
-        for (int b = 0; b < nb; b++)
-            nstages += per_block[b].size();
-        side[s].stages.reserve(nstages);
         for (int b = 0; b < nb; b++) {
-            m_block_off[s][b] = stream;
+            uint64_t bytes = 0, c_len = 0, aux = 0;
+            for (const StageDesc &sd : per_block[b]) {
+                bytes += sd.nbytes;
+                c_len += sd.c_len;
+                aux += sd.aux_off16; // (layout_block left the size of the stage's aux record here)
+            }
+            stage_at[b + 1]       = stage_at[b] + per_block[b].size();
+            m_block_off[s][b + 1] = m_block_off[s][b] + bytes;
+            c_at[b + 1]           = c_at[b] + c_len;
+            aux_at[b + 1]         = aux_at[b] + aux;
+            side[s].any_twice     = side[s].any_twice || twice[b];
+            side[s].n_units += units[b];
+        }
+        const uint64_t stream = m_block_off[s][nb], c_off = c_at[nb], aux_off = aux_at[nb];
+        if (aux_off / 16u >= (uint64_t(1) << 32))
+            throw std::runtime_error("multi-RHS aux tables too large");
+        side[s].stages.resize(stage_at[nb]);
+        uint32_t aux_max  = 0;
+        bool aux_overflow = false;
+#pragma omp parallel for schedule(static) reduction(max : aux_max) reduction(|| : aux_overflow)
+        for (int b = 0; b < nb; b++) {
             BlockDesc &bd     = side[s].blocks[b];
-            bd.first_stage    = static_cast<uint32_t>(side[s].stages.size());
+            bd.first_stage    = static_cast<uint32_t>(stage_at[b]);
             bd.n_stages       = static_cast<uint32_t>(per_block[b].size());
             bd.flags          = twice[b] ? 1u : 0u;
             bd.n_twice_stages = 0;
-            for (const StageDesc &sd : per_block[b])
-                bd.n_twice_stages += sd.flags & 1u;
-            side[s].any_twice = side[s].any_twice || twice[b];
-            side[s].n_units += units[b];
+            uint64_t c = c_at[b], aux = aux_at[b];
+            size_t at  = stage_at[b];
             for (StageDesc sd : per_block[b]) {
-                sd.byte_off += stream;
+                bd.n_twice_stages += sd.flags & 1u;
+                sd.byte_off += m_block_off[s][b];
                 sd.first_unit += static_cast<uint32_t>(m_unit_ptr[s][m_csr_ptr[s][b]]); // block-local -> side-wide
-                sd.c_off = static_cast<uint32_t>(c_off);
-                c_off += sd.c_len;
-                side[s].stages.push_back(sd);
+                sd.c_off = static_cast<uint32_t>(c);
+                c += sd.c_len;
+                const uint32_t aux_bytes = sd.aux_off16;
+                // (cannot happen: a stage holds <= cseg_bytes / esize columns)
+                aux_overflow = aux_overflow || aux_bytes > aux_slot_bytes(static_cast<uint32_t>(opt.cseg_bytes)) || aux_bytes / 16u > 0x7fffu;
+                sd.aux_off16 = static_cast<uint32_t>(aux / 16u);
+                sd.flags     = static_cast<uint16_t>((sd.flags & 1u) | ((aux_bytes / 16u) << 1));
+                aux += aux_bytes;
+                aux_max               = std::max(aux_max, aux_bytes);
+                side[s].stages[at++] = sd;
             }
-            if (!per_block[b].empty())
-                stream = side[s].stages.back().byte_off + side[s].stages.back().nbytes;
+            std::vector<StageDesc>().swap(per_block[b]);
         }
-        m_block_off[s][nb]   = stream;
+        if (aux_overflow)
+            throw std::runtime_error("multi-RHS aux record exceeds its slot");
+        side[s].aux_max_bytes = std::max(side[s].aux_max_bytes, aux_max);
+        lap(s == 0 ? "  layout stages 0" : "  layout stages 1");
+        side[s].aux_reduce.resize(aux_off); // written by make_mtables
+        side[s].aux_apply.resize(aux_off);
         side[s].stream_bytes = stream;
         side[s].cs_elems     = c_off;
         // heaviest blocks first: the hardware block scheduler then balances the tail
@@ -428,8 +457,11 @@ void Packer::make_incidence(int s) {
         };
         // (keys computed once per incidence: a key reads the leaf record, a cache miss in a list of millions of leaves)
         std::vector<std::pair<uint64_t, uint32_t>> keyed(e1 - e0);
-        for (uint64_t e = e0; e < e1; e++)
+        for (uint64_t e = e0; e < e1; e++) {
+            if (e + 8 < e1)
+                prefetch_leaf(s, m_csr_leaf[s][e + 8]);
             keyed[e - e0] = {key(m_csr_leaf[s][e]), m_csr_leaf[s][e]};
+        }
         std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<uint64_t, uint32_t> &a, const std::pair<uint64_t, uint32_t> &c) { return a.first < c.first; });
         for (uint64_t e = e0; e < e1; e++) {
             const uint32_t li                                              = keyed[e - e0].second;
@@ -442,6 +474,8 @@ void Packer::make_incidence(int s) {
 #pragma omp parallel for schedule(dynamic, 64)
     for (int b = 0; b < nb; b++)
         for (uint64_t e = m_csr_ptr[s][b]; e < m_csr_ptr[s][b + 1]; e++) {
+            if (e + 8 < m_csr_ptr[s][b + 1])
+                prefetch_leaf(s, m_csr_leaf[s][e + 8]);
             const uint32_t li    = m_csr_leaf[s][e];
             m_unit_ptr[s][e + 1] = static_cast<uint64_t>(units_in_incidence(s, li, b - m_first_blk[s][li]));
         }
@@ -601,16 +635,15 @@ void Packer::make_mtables() {
     std::vector<std::vector<NfSrc>> nf_src_side[2];
     for (int s = 0; s < 2; s++) {
         const int nb = static_cast<int>(side[s].blocks.size());
-        side[s].munits.assign(m_unit_ptr[s].back(), MUnit{0, 0, 0, 0});
-        // aux records (runs + column tables, store.hpp) of every block, concatenated below
-        std::vector<std::vector<unsigned char>> aux_r(nb), aux_a(nb);
-        std::vector<std::vector<uint32_t>> aux_len(nb); // per stage of the block, bytes
+        side[s].munits.resize(m_unit_ptr[s].back()); // (RawVector: every entry is written by the walk below)
+        // the aux records (runs + column tables, store.hpp) go straight to their place: layout_block sized them
         std::vector<std::vector<DenseTask>> tasks(nb), lr_tasks(nb);
         std::vector<std::vector<NfSrc>> &nf_src = nf_src_side[s];
         nf_src.assign(s == 0 && opt.near_field && opt.sort_units ? nb : 0, {});
-        bool aux_overflow = false;
+        bool aux_mismatch = false;
 #pragma omp parallel for schedule(dynamic, 64)
         for (int b = 0; b < nb; b++) {
+            uint32_t q = 0; // stage of the block being closed
             // same walk and the same cuts as layout_block / fill_block; inside a stage panel units come first
             StageCutter cut{esize, static_cast<uint32_t>(opt.stage_bytes), static_cast<uint32_t>(opt.cseg_bytes)};
             std::vector<UnitSpec> pending;
@@ -637,7 +670,7 @@ void Packer::make_mtables() {
                         if (u.kind == UNIT_LOWRANK)
                             runs.back().K_lr = runs.back().K; // (low-rank units come first: a prefix)
                         if (u.kind == UNIT_DENSE && !nf_src.empty()) {
-                            const StageDesc &sd = side[s].stages[side[s].blocks[b].first_stage + aux_len[b].size()];
+                            const StageDesc &sd = side[s].stages[side[s].blocks[b].first_stage + q];
                             nf_src[b].push_back(NfSrc{sd.byte_off + cut.header_bytes() + static_cast<uint64_t>(eoff) * esize, static_cast<uint32_t>(l.col_offset) + u.k0, static_cast<uint16_t>(u.row0), static_cast<uint16_t>(u.h),
                                                       static_cast<uint16_t>(u.w), static_cast<uint16_t>(u.ld)});
                         }
@@ -648,13 +681,13 @@ void Packer::make_mtables() {
                             out               = po == kDirect ? m_tf_off[gp] : po + static_cast<uint32_t>(u.chunk) * static_cast<uint32_t>(piece_len(l, u.piece));
                         }
                         if (u.kind == UNIT_DENSE && !l.data0) {
-                            const StageDesc &sd = side[s].stages[side[s].blocks[b].first_stage + aux_len[b].size()];
+                            const StageDesc &sd = side[s].stages[side[s].blocks[b].first_stage + q];
                             tasks[b].push_back(DenseTask{sd.byte_off + cut.header_bytes() + static_cast<uint64_t>(eoff) * esize, l.row_offset, l.col_offset, static_cast<int32_t>(u.p0), static_cast<int32_t>(u.k0),
                                                          static_cast<uint16_t>(u.h), static_cast<uint16_t>(u.w), static_cast<uint16_t>(u.ld),
                                                          static_cast<uint16_t>(l.flags & (HTB_LEAF_DIAG_SYMMETRIC | HTB_LEAF_DIAG_HERMITIAN | HTB_LEAF_UPLO_UPPER))});
                         }
                         if (u.kind == UNIT_LOWRANK && !l.data0) { // factors in the device pool: the panel is copied on the device (aca.cu)
-                            const StageDesc &sd = side[s].stages[side[s].blocks[b].first_stage + aux_len[b].size()];
+                            const StageDesc &sd = side[s].stages[side[s].blocks[b].first_stage + q];
                             lr_tasks[b].push_back(DenseTask{sd.byte_off + cut.header_bytes() + static_cast<uint64_t>(eoff) * esize, static_cast<int32_t>(u.leaf), s, static_cast<int32_t>(u.p0), static_cast<int32_t>(u.k0),
                                                             static_cast<uint16_t>(u.h), static_cast<uint16_t>(u.w), static_cast<uint16_t>(u.ld), 0});
                         }
@@ -666,22 +699,27 @@ void Packer::make_mtables() {
                     }
                     const size_t ncols4 = (col_out.size() + 3u) & ~size_t(3);
                     const size_t bytes  = sizeof(AuxHeader) + runs.size() * sizeof(RunDesc) + ncols4 * 4u;
-                    if (bytes > aux_slot_bytes(static_cast<uint32_t>(opt.cseg_bytes)) || bytes / 16u > 0x7fffu)
-                        aux_overflow = true; // (cannot happen: a stage holds <= cseg_bytes / esize columns; reported after the parallel loop)
+                    if (q >= side[s].blocks[b].n_stages) {
+                        aux_mismatch = true; // (reported after the parallel loop)
+                        return;
+                    }
+                    const StageDesc &sd_q = side[s].stages[side[s].blocks[b].first_stage + q];
+                    if (bytes != static_cast<size_t>(sd_q.flags >> 1) * 16u) {
+                        aux_mismatch = true; // (nothing is written past a record)
+                        return;
+                    }
                     col_out.resize(ncols4, 0u);
                     col_src.resize(ncols4, 0u);
                     const AuxHeader ah{static_cast<uint32_t>(runs.size()), static_cast<uint32_t>(col_out.size()), {0u, 0u}};
                     for (int role = 0; role < 2; role++) {
-                        std::vector<unsigned char> &dst = role == 0 ? aux_r[b] : aux_a[b];
-                        const size_t at                 = dst.size();
-                        dst.resize(at + bytes);
-                        std::memcpy(dst.data() + at, &ah, sizeof(ah));
+                        unsigned char *dst = (role == 0 ? side[s].aux_reduce : side[s].aux_apply).data() + static_cast<size_t>(sd_q.aux_off16) * 16u;
+                        std::memcpy(dst, &ah, sizeof(ah));
                         if (!runs.empty())
-                            std::memcpy(dst.data() + at + sizeof(ah), runs.data(), runs.size() * sizeof(RunDesc));
+                            std::memcpy(dst + sizeof(ah), runs.data(), runs.size() * sizeof(RunDesc));
                         if (ncols4)
-                            std::memcpy(dst.data() + at + sizeof(ah) + runs.size() * sizeof(RunDesc), (role == 0 ? col_out : col_src).data(), ncols4 * 4u);
+                            std::memcpy(dst + sizeof(ah) + runs.size() * sizeof(RunDesc), (role == 0 ? col_out : col_src).data(), ncols4 * 4u);
                     }
-                    aux_len[b].push_back(static_cast<uint32_t>(bytes));
+                    q++;
                 }
                 uint32_t poff = 0, in_batch = 0;
                 bool first    = true;
@@ -729,52 +767,27 @@ void Packer::make_mtables() {
                 pending.push_back(u);
             });
             close();
+            if (q != side[s].blocks[b].n_stages)
+                aux_mismatch = true;
         }
         mt_lap(s == 0 ? "walk side 0" : "walk side 1");
-        if (aux_overflow)
-            throw std::runtime_error("multi-RHS aux record exceeds its slot");
-        // concatenate the per-block aux records and task lists (offsets by prefix sums, copies in parallel); every stage learns
-        // where its record is
-        std::vector<uint64_t> aux_at(static_cast<size_t>(nb) + 1, 0), dt_at(static_cast<size_t>(nb) + 1, 0), lt_at(static_cast<size_t>(nb) + 1, 0);
+        if (aux_mismatch)
+            throw std::runtime_error("internal: aux records do not match the stages");
+        // concatenate the per-block task lists (offsets by prefix sums, copies in parallel)
+        std::vector<uint64_t> dt_at(static_cast<size_t>(nb) + 1, 0), lt_at(static_cast<size_t>(nb) + 1, 0);
         for (int b = 0; b < nb; b++) {
-            aux_at[b + 1] = aux_at[b] + aux_r[b].size();
-            dt_at[b + 1]  = dt_at[b] + tasks[b].size();
-            lt_at[b + 1]  = lt_at[b] + lr_tasks[b].size();
-            if (aux_len[b].size() != side[s].blocks[b].n_stages)
-                throw std::runtime_error("internal: aux records do not match the stages");
+            dt_at[b + 1] = dt_at[b] + tasks[b].size();
+            lt_at[b + 1] = lt_at[b] + lr_tasks[b].size();
         }
-        const uint64_t total = aux_at[nb];
-        if (total / 16u >= (uint64_t(1) << 32))
-            throw std::runtime_error("multi-RHS aux tables too large");
-        side[s].aux_reduce.resize(total);
-        side[s].aux_apply.resize(total);
         side[s].dense_tasks.resize(dt_at[nb]);
         side[s].lr_tasks.resize(lt_at[nb]);
-        uint32_t aux_max = 0;
-#pragma omp parallel for schedule(dynamic, 64) reduction(max : aux_max)
+#pragma omp parallel for schedule(dynamic, 64)
         for (int b = 0; b < nb; b++) {
-            const BlockDesc &bd = side[s].blocks[b];
-            const uint64_t at   = aux_at[b];
-            if (!aux_r[b].empty()) {
-                std::memcpy(side[s].aux_reduce.data() + at, aux_r[b].data(), aux_r[b].size());
-                std::memcpy(side[s].aux_apply.data() + at, aux_a[b].data(), aux_a[b].size());
-            }
-            uint64_t off = at;
-            for (uint32_t q = 0; q < bd.n_stages; q++) {
-                StageDesc &sd = side[s].stages[bd.first_stage + q];
-                sd.aux_off16  = static_cast<uint32_t>(off / 16u);
-                sd.flags      = static_cast<uint16_t>((sd.flags & 1u) | ((aux_len[b][q] / 16u) << 1));
-                off += aux_len[b][q];
-                aux_max = std::max(aux_max, aux_len[b][q]);
-            }
             if (!tasks[b].empty())
                 std::memcpy(static_cast<void *>(side[s].dense_tasks.data() + dt_at[b]), tasks[b].data(), tasks[b].size() * sizeof(DenseTask));
             if (!lr_tasks[b].empty())
                 std::memcpy(static_cast<void *>(side[s].lr_tasks.data() + lt_at[b]), lr_tasks[b].data(), lr_tasks[b].size() * sizeof(DenseTask));
-            std::vector<unsigned char>().swap(aux_r[b]);
-            std::vector<unsigned char>().swap(aux_a[b]);
         }
-        side[s].aux_max_bytes = std::max(side[s].aux_max_bytes, aux_max);
         mt_lap(s == 0 ? "concat side 0" : "concat side 1");
     }
     if (!nf_src_side[0].empty())
@@ -935,7 +948,10 @@ uint32_t Packer::producer_out(int ps, const UnitSpec &u) const {
 template <typename Emit>
 void Packer::walk_block(int s, int b, Emit &&emit) const {
     const int bs = m_block_start[s][b];
-    for (uint64_t e = m_csr_ptr[s][b]; e < m_csr_ptr[s][b + 1]; e++) {
+    const uint64_t e_end = m_csr_ptr[s][b + 1];
+    for (uint64_t e = m_csr_ptr[s][b]; e < e_end; e++) {
+        if (e + 8 < e_end)
+            prefetch_leaf(s, m_csr_leaf[s][e + 8]); // (the leaves of a block are scattered over a list of millions)
         const uint32_t li = m_csr_leaf[s][e];
         const htb_leaf &l = m_leaves[li];
         const int a       = start_of(s, l);
@@ -981,17 +997,22 @@ void Packer::walk_block(int s, int b, Emit &&emit) const {
     }
 }
 
-void Packer::layout_block(int s, int b, std::vector<StageDesc> &stages, std::vector<uint32_t> &unit_stage, uint64_t &n_units, bool &any_twice) {
+void Packer::layout_block(int s, int b, std::vector<StageDesc> &stages, RawVector<uint32_t> &unit_stage, uint64_t &n_units, bool &any_twice) {
     StageCutter cut{esize, static_cast<uint32_t>(opt.stage_bytes), static_cast<uint32_t>(opt.cseg_bytes)};
     uint64_t off     = 0;
     uint16_t stflags = 0;
     uint32_t first   = 0; // units of the block before the current stage
     uint32_t n_panel = 0; // coefficient-carrying units of the current stage
+    // size of the stage's multi-RHS aux record (make_mtables writes it: same run detection): it travels in aux_off16 until the
+    // constructor turns the sizes into offsets
+    uint32_t n_runs = 0, n_cols = 0, run_row0 = 0, run_h = 0, run_twice = 0, run_K = 0;
     auto close       = [&]() {
         if (cut.nu == 0)
             return;
-        stages.push_back(StageDesc{off, cut.nbytes(), 0u, static_cast<uint16_t>(cut.c_len_padded()), stflags, first, static_cast<uint16_t>(cut.nu), static_cast<uint16_t>(n_panel), 0u});
+        const uint32_t aux_bytes = static_cast<uint32_t>(sizeof(AuxHeader) + n_runs * sizeof(RunDesc) + ((n_cols + 3u) & ~3u) * 4u);
+        stages.push_back(StageDesc{off, cut.nbytes(), 0u, static_cast<uint16_t>(cut.c_len_padded()), stflags, first, static_cast<uint16_t>(cut.nu), static_cast<uint16_t>(n_panel), aux_bytes});
         n_panel = 0;
+        n_runs = n_cols = 0;
         off += cut.nbytes();
         first += cut.nu;
         cut.reset();
@@ -1004,6 +1025,14 @@ void Packer::layout_block(int s, int b, std::vector<StageDesc> &stages, std::vec
         m_unit_cslot[s][u.ui] = static_cast<uint16_t>(cut.c_elems);
         cut.add(u.elems(), u.celems());
         n_panel += u.kind != UNIT_ADDVEC ? 1u : 0u;
+        if (u.kind != UNIT_ADDVEC) {
+            if (n_runs == 0 || run_row0 != u.row0 || run_h != u.h || run_twice != u.twice || run_K + u.w > 0xffffu) {
+                n_runs++;
+                run_row0 = u.row0, run_h = u.h, run_twice = u.twice, run_K = 0;
+            }
+            run_K += u.w;
+            n_cols += u.w;
+        }
         n_units++;
         if (u.twice) {
             stflags |= 1u;

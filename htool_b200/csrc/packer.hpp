@@ -59,12 +59,17 @@ class Packer {
     std::vector<uint64_t> m_csr_ptr[2];    // nblocks + 1
     std::vector<uint32_t> m_csr_leaf[2];   // incidences (leaf ids), block-major, leaf order inside a block
     std::vector<uint64_t> m_unit_ptr[2];   // per incidence: first unit index (n_incidences + 1)
-    std::vector<uint32_t> m_unit_slot[2];  // per unit: scratch offset of its c slot
-    std::vector<uint16_t> m_unit_cslot[2]; // per unit: offset of its c slot inside its stage's c segment
+    RawVector<uint32_t> m_unit_slot[2];    // per unit: scratch offset of its c slot
+    RawVector<uint16_t> m_unit_cslot[2];   // per unit: offset of its c slot inside its stage's c segment
     std::vector<uint32_t> m_part_off[2];   // [consumer side] per global piece: scratch offset of the partials, or kDirect
     std::vector<uint64_t> m_block_off[2];
     std::vector<uint64_t> m_hdr_off[2];    // prefix sums of the stages' header bytes (n_stages + 1)
 
+    void prefetch_leaf(int s, uint32_t li) const { // what a walk over a block's incidences reads per leaf
+        __builtin_prefetch(&m_leaves[li]);
+        __builtin_prefetch(&m_first_blk[s][li]);
+        __builtin_prefetch(&m_piece_ptr[li]);
+    }
     bool active(const htb_leaf &l) const { return l.nb_rows > 0 && l.nb_cols > 0 && l.rank != 0; }
     int vec_len(const htb_leaf &l) const { return l.rank < 0 ? l.nb_cols : l.rank; }
     int n_pieces(const htb_leaf &l) const { return (vec_len(l) + piece - 1) / piece; }
@@ -89,7 +94,7 @@ class Packer {
     std::vector<uint32_t> m_tf_off;       // per global piece: TF offset (vectors)
     template <typename Emit>
     void walk_block(int s, int b, Emit &&emit) const;
-    void layout_block(int s, int b, std::vector<StageDesc> &stages, std::vector<uint32_t> &unit_stage, uint64_t &n_units, bool &any_twice);
+    void layout_block(int s, int b, std::vector<StageDesc> &stages, RawVector<uint32_t> &unit_stage, uint64_t &n_units, bool &any_twice);
     template <typename T>
     void fill_block(int s, int b, char *dst, bool headers_only = false) const;
     struct NfSrc { // a dense unit of side 0 in the main stream

@@ -288,7 +288,7 @@ struct SideLayout {
     uint64_t cs_base = 0, cs_elems = 0;     // CS[this side]
     bool any_twice = false;
     // multi-RHS tables (this side as CONSUMER for combine_m / partm)
-    std::vector<MUnit> munits;
+    RawVector<MUnit> munits;
     std::vector<CombineEntry> combine_m; // src = PARTM offset, dst_first = TF offset, n_dst unused
     uint64_t partm_base = 0, partm_elems = 0; // in vectors, inside the multi-RHS scratch [TF | PARTM[0] | PARTM[1]]
     RawVector<unsigned char> aux_reduce, aux_apply; // per-stage aux records (runs + column tables), same offsets in both
