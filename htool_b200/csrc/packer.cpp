@@ -279,9 +279,11 @@ Packer::Packer(const htb_hmatrix_desc &desc, const PackOptions &o) : dtype(desc.
     if (scratch_elems >= (uint64_t(1) << 32))
         throw std::runtime_error("scratch exceeds 2^32 elements");
     for (int s = 0; s < 2; s++) {
-        for (auto &p : m_part_off[s])
-            if (p != kDirect)
-                p += static_cast<uint32_t>(side[s].part_base);
+        const int64_t n_part = static_cast<int64_t>(m_part_off[s].size());
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n_part; i++)
+            if (m_part_off[s][i] != kDirect)
+                m_part_off[s][i] += static_cast<uint32_t>(side[s].part_base);
         const int nb = static_cast<int>(side[s].blocks.size());
 #pragma omp parallel for schedule(dynamic, 64)
         for (int b = 0; b < nb; b++) {
@@ -290,10 +292,11 @@ Packer::Packer(const htb_hmatrix_desc &desc, const PackOptions &o) : dtype(desc.
                 m_unit_slot[s][ui] = static_cast<uint32_t>(side[s].cs_base + side[s].stages[side[s].blocks[b].first_stage + unit_stage[s][ui]].c_off + m_unit_cslot[s][ui]);
         }
     }
-    all_on_device = n_leaves > 0;
+    bool some_host_data = false;
+#pragma omp parallel for schedule(static) reduction(|| : some_host_data)
     for (int64_t i = 0; i < n_leaves; i++)
-        if (active(m_leaves[i]) && m_leaves[i].data0)
-            all_on_device = false;
+        some_host_data = some_host_data || (active(m_leaves[i]) && m_leaves[i].data0);
+    all_on_device = n_leaves > 0 && !some_host_data;
     for (int s = 0; s < 2; s++) {
         m_hdr_off[s].assign(side[s].stages.size() + 1, 0);
         for (size_t st = 0; st < side[s].stages.size(); st++)
