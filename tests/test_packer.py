@@ -236,3 +236,19 @@ def test_multi_rhs_side_tables_golden():
             y = e["y_in"].copy()
             assert em.matrix_product_row_major(e["trans"], e["alpha"], e["x"], e["beta"], y, e["mu"]) == 0
             assert rel_err(y, e["y_seq"]) < TOL, (name, e["trans"])
+
+
+@pytest.mark.parametrize("dtype_code,symmetric", [(0, "-"), (1, "H")])
+def test_layout_does_not_depend_on_the_thread_count(dtype_code, symmetric):
+    """The packer's serial passes run one side per thread and its block loops are dynamically scheduled: streams and tables must
+    be the same bytes whatever OMP_NUM_THREADS is (1 = the serial fallback of both_sides, packer.cpp)."""
+    import subprocess
+    import sys
+
+    digests = set()
+    for threads in ("1", "2", "7"):
+        r = subprocess.run([sys.executable, os.path.join(REPO, "tests", "pack_digest.py"), str(dtype_code), symmetric], capture_output=True, text=True, timeout=300,
+                           env=dict(os.environ, OMP_NUM_THREADS=threads))
+        assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-2000:]
+        digests.add([l for l in r.stdout.splitlines() if l.startswith("digest ")][-1])
+    assert len(digests) == 1, digests
