@@ -1530,8 +1530,12 @@ int htb_pack_host(const htb_hmatrix_desc *desc, int side, htb_packed_side *out) 
         auto *own   = new PackedOwner();
         own->layout = pk.side[side];
         own->stream.resize(pk.side[side].stream_bytes);
-        if (!own->layout.blocks.empty())
+        if (!own->layout.blocks.empty()) {
+            const auto t0 = std::chrono::steady_clock::now();
             pk.fill(side, 0, static_cast<int>(own->layout.blocks.size()), own->stream.data());
+            if (std::getenv("HTB_PACK_TIMING")) // development aid (tools/pack_time.py --with-data)
+                std::fprintf(stderr, "[htb pack] fill side %d: %.3f s for %.2f GB\n", side, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), pk.side[side].stream_bytes / 1e9);
+        }
         out->n             = own->layout.n;
         out->n_blocks      = static_cast<int32_t>(own->layout.blocks.size());
         out->n_stages      = static_cast<int64_t>(own->layout.stages.size());

@@ -50,6 +50,7 @@ def main():
     ap.add_argument("--symmetry", default="N", choices=["N", "S"])
     ap.add_argument("--reps", type=int, default=1)
     ap.add_argument("--set", action="append", default=[], help="packer option key=value")
+    ap.add_argument("--with-data", action="store_true", help="keep the reference's coefficients (no cache): times the fill pass of the host-packed path too")
     ap.add_argument("--lib", default=None, help="another build of libhtool_b200.so (A/B of a packer change)")
     args = ap.parse_args()
     from htool_b200 import capi
@@ -57,9 +58,18 @@ def main():
     if args.lib:
         capi.LIB_PATH = os.path.abspath(args.lib)
     lib = capi.load()
-    lv, desc_bytes = leaf_list(args.n, args.dtype, args.symmetry)
-    lv = lv.copy()
-    lv["data0"], lv["data1"] = 0, 0
+    case = None
+    if args.with_data:
+        import bench
+        from oracle import refharness as R
+
+        R.set_num_threads(os.cpu_count() or 1)
+        case = R.RefCase(**bench.case_kwargs(args.n, args.dtype, args.symmetry))  # (kept alive: the leaves point into it)
+        lv, desc_bytes = case.leaves().copy(), bytes(case.desc)
+    else:
+        lv, desc_bytes = leaf_list(args.n, args.dtype, args.symmetry)
+        lv = lv.copy()
+        lv["data0"], lv["data1"] = 0, 0
     for kv in args.set:
         k, v = kv.split("=")
         capi.set_option(k, int(v))
