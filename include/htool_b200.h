@@ -308,7 +308,8 @@ int htb_get_pass_times(htb_handle h, double ms[HTB_PASS_KINDS], int64_t launches
  * reference was linked with fuses its axpy), aca_dots (0: guarded warp-level dot products, 1: in order, 2: replay always),
  * aca_rank_guess (terms per block the factor pool is first sized for). Read at product time: mrhs_min (right-hand sides from which
  * the tensor-core path is used; 0 = automatic), m_fast_tall, m_b_global, m_small_runs, m_reduce_split, m_stage_input (multi-RHS
- * kernel variants), zero_copy, fused_symmetric, pdl, dist_p2p. */
+ * kernel variants), zero_copy, fused_symmetric, pdl, dist_p2p. The table is PROCESS-WIDE (one per loaded library, not per handle): a
+ * value read at product time applies to every live handle; pdl is latched by the most recent htb_create. */
 int htb_set_option(const char *key, int64_t value);
 int htb_get_option(const char *key, int64_t *value);
 
