@@ -45,6 +45,7 @@
 #include <memory>
 #include <new>
 #include <type_traits>
+#include <cstring>
 #include <utility>
 #include <vector>
 
@@ -263,7 +264,11 @@ struct DefaultInitAllocator : std::allocator<T> {
     DefaultInitAllocator(const DefaultInitAllocator<U> &) {}
     template <typename U>
     void construct(U *ptr) noexcept(std::is_nothrow_default_constructible<U>::value) {
+#ifdef HTB_POISON_RAW_VECTORS /* debug builds: an entry the packer forgets to write shows up in the digests of tools/pack_time.py */
+        std::memset(static_cast<void *>(ptr), 0xAB, sizeof(U));
+#else
         ::new (static_cast<void *>(ptr)) U;
+#endif
     }
     template <typename U, typename... Args>
     void construct(U *ptr, Args &&...args) {
