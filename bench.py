@@ -892,6 +892,14 @@ def run_ours(args):
         # BASELINE.json configs[4]: Laplace N = 8e6 row-sharded, 200 repeated matvecs inside a GMRES solve (does not fit fewer GPUs)
         def cfg4(w2):
             out = section_single(w2, 20, 3, "configs[4]")
+            # the N = 8e6 operator (~300 GB) does not fit one GPU, so the 1-GPU point of the 1 -> N factor is DEFINED as
+            # one GPU streaming the same coefficients at its measured HBM copy peak (an upper bound of any real single-GPU rate:
+            # the factor reported is a LOWER bound of the speed-up over one GPU with enough memory).
+            peak_gbs, peak_src = peaks()
+            t_one = out["algorithmic_bytes_per_step"] / (peak_gbs * 1e9)
+            out["scaling_1_to_n"] = {"n_gpus": world, "single_gpu_bound_matvec_per_s": 1.0 / t_one, "factor_lower_bound": out["value"] * t_one,
+                                     "definition": f"value / (one GPU streaming the operator's {out['algorithmic_bytes_per_step'] / 1e9:.0f} GB per product at the HBM peak, {peak_gbs:.0f} GB/s {peak_src}); "
+                                                   "the operator does not fit one GPU's 180 GB"}
             out["gmres"] = section_gmres(w2, args.gmres_iterations or 200, out["value"])
             return out
 
