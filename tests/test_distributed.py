@@ -45,6 +45,13 @@ def test_four_gloo_ranks_host_logic(have_ref):
     _run("gloo", 4, ["--points", "3500", "--sym", "S"])
 
 
+def test_eight_gloo_ranks_host_logic(have_ref):
+    """Eight row strips, the partitioning of the 8-GPU scaling run (complex, symmetric storage inside the diagonal blocks)."""
+    if not have_ref:
+        pytest.skip("oracle/_ref is not built")
+    _run("gloo", 8, ["--points", "6000", "--scalar", "complex", "--sym", "S"])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("extra", [["--points", "20000"], ["--points", "16000", "--sym", "S"], ["--points", "12000", "--scalar", "complex", "--sym", "S"], ["--points", "8000", "--rhs", "3"],
                                    ["--points", "8000", "--rhs", "16"], ["--points", "16000", "--sym", "S", "--p2p", "0"], ["--points", "8000", "--rhs", "3", "--p2p", "0"]],
