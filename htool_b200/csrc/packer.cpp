@@ -61,38 +61,37 @@ struct StageCutter {
     }
 };
 
-// The serial passes over the leaf list are independent for the two sides (or the two directions): one thread each, inside
-// a team of the usual size (a team of two would make libgomp drop and re-create its other threads around every call). f
-// must not open a parallel region of its own (it would be serialised); exceptions leave through the calling thread.
+// The serial passes over the leaf list are independent of each other (per side, per direction, per table): job j of n runs on
+// thread j of a team of the usual size (a team of n would make libgomp drop and re-create its other threads around every
+// call). f must not open a parallel region of its own (it would be serialised); exceptions leave through the calling thread.
 template <typename F>
-void both_sides(F &&f) {
-    std::exception_ptr err[2];
-    auto run = [&](int s) {
+void concurrently(int n, F &&f) {
+    std::vector<std::exception_ptr> err(n);
+    auto run = [&](int j) {
         try {
-            f(s);
+            f(j);
         } catch (...) {
-            err[s] = std::current_exception();
+            err[j] = std::current_exception();
         }
     };
 #ifdef _OPENMP
 #pragma omp parallel
     {
-        const int t = omp_get_thread_num();
-        if (omp_get_num_threads() >= 2) {
-            if (t < 2)
-                run(t);
-        } else {
-            run(0);
-            run(1);
-        }
+        const int t = omp_get_thread_num(), nt = omp_get_num_threads();
+        for (int j = t; j < n; j += nt)
+            run(j);
     }
 #else
-    run(0);
-    run(1);
+    for (int j = 0; j < n; j++)
+        run(j);
 #endif
     for (const std::exception_ptr &e : err)
         if (e)
             std::rethrow_exception(e);
+}
+template <typename F>
+void both_sides(F &&f) {
+    concurrently(2, f);
 }
 
 } // namespace
@@ -182,7 +181,13 @@ Packer::Packer(const htb_hmatrix_desc &desc, const PackOptions &o) : dtype(desc.
     for (int s = 0; s < 2; s++)
         make_incidence(s);
     lap("make_incidence");
-    make_partials();
+    // three serial passes over the leaf list at once: the partial areas of the two directions and the TF offsets of the multi-RHS path
+    concurrently(3, [&](int j) {
+        if (j < 2)
+            make_partials(j);
+        else
+            make_tf();
+    });
     lap("make_partials");
 
     // per-block stage layout
@@ -303,7 +308,14 @@ Packer::Packer(const htb_hmatrix_desc &desc, const PackOptions &o) : dtype(desc.
             m_hdr_off[s][st + 1] = m_hdr_off[s][st] + 16u + 16u * side[s].stages[st].n_units;
     }
     lap("unit_slots");
-    both_sides([&](int s) { make_combine(s); });
+    // four more: the combine tables of the two directions, the multi-RHS partial areas of the two directions
+    make_partm_sizes();
+    concurrently(4, [&](int j) {
+        if (j < 2)
+            make_combine(j);
+        else
+            make_partm(j - 2);
+    });
     lap("make_combine");
     make_mtables();
     lap("make_mtables");
@@ -489,8 +501,8 @@ void Packer::make_incidence(int s) {
 
 // For every piece and direction (= consumer side cs): can its single producer write straight into its single
 // consumer slot, or does it go through partials + COMBINE? Offsets are relative to PART[cs] here.
-void Packer::make_partials() {
-    both_sides([&](int cs) {
+void Packer::make_partials(int cs) {
+    {
         const int ps = 1 - cs;
         m_part_off[cs].assign(m_piece_ptr[n_leaves], kDirect);
         uint64_t off = 0;
@@ -524,7 +536,7 @@ void Packer::make_partials() {
             }
         }
         side[cs].part_elems = off;
-    });
+    }
 }
 
 void Packer::make_combine(int cs) {
@@ -569,9 +581,7 @@ void Packer::make_combine(int cs) {
 
 // Side tables of the multi-RHS path (store.hpp, MUnit): TF offsets per piece, partial areas for pieces with several
 // producer chunks, one MUnit per unit in stage order, and the panel-buffer batches of every stage.
-void Packer::make_mtables() {
-    const bool mt_timing = std::getenv("HTB_PACK_TIMING") != nullptr;
-    auto mt_last         = std::chrono::steady_clock::now();
+void Packer::make_tf() {
     const uint64_t n_pieces_total = m_piece_ptr[n_leaves];
     m_tf_off.assign(n_pieces_total, 0);
     uint64_t tf = 0;
@@ -585,8 +595,10 @@ void Packer::make_mtables() {
         }
     }
     tf_elems = tf;
-    // sizes of the two partial areas first (a parallel sum), so that both directions are laid out concurrently
-    uint64_t partm_total[2] = {0, 0};
+}
+
+// Sizes of the two multi-RHS partial areas (a parallel sum), so that both directions can be laid out concurrently (make_partm).
+void Packer::make_partm_sizes() {
     for (int cs = 0; cs < 2; cs++) {
         uint64_t sum = 0;
 #pragma omp parallel for schedule(static) reduction(+ : sum)
@@ -595,34 +607,41 @@ void Packer::make_mtables() {
             if (active(l) && !(l.rank < 0 && cs == 0) && m_nchunks[1 - cs][i] > 1)
                 sum += static_cast<uint64_t>(m_nchunks[1 - cs][i]) * static_cast<uint64_t>(vec_len(l));
         }
-        partm_total[cs] = sum;
+        m_partm_total[cs] = sum;
     }
-    both_sides([&](int cs) {
-        const int ps        = 1 - cs;
-        const uint64_t base = tf + (cs == 1 ? partm_total[0] : 0u);
-        m_partm_off[cs].assign(n_pieces_total, kDirect);
-        side[cs].partm_base = base;
-        uint64_t off        = 0;
-        for (int64_t i = 0; i < n_leaves; i++) {
-            const htb_leaf &l = m_leaves[i];
-            if (!active(l) || (l.rank < 0 && cs == 0)) // dense leaves, direction 0: x rows are read from the input directly
-                continue;
-            const int n_prod = m_nchunks[ps][i];
-            if (n_prod <= 1)
-                continue;
-            for (int p = 0; p < n_pieces(l); p++) {
-                const int len                       = piece_len(l, p);
-                m_partm_off[cs][m_piece_ptr[i] + p] = static_cast<uint32_t>(base + off);
-                side[cs].combine_m.push_back(CombineEntry{static_cast<uint32_t>(base + off), m_tf_off[m_piece_ptr[i] + p], 0u,
-                                                          static_cast<uint32_t>(n_prod) | (static_cast<uint32_t>(len) << 24) | ((l.flags & HTB_LEAF_APPLY_TRANSPOSED_TOO) ? 0x80000000u : 0u)});
-                off += static_cast<uint64_t>(n_prod) * len;
-            }
+}
+
+// Partial area of direction cs (consumer side cs) of the multi-RHS path, after make_tf.
+void Packer::make_partm(int cs) {
+    const uint64_t n_pieces_total = m_piece_ptr[n_leaves];
+    const int ps                  = 1 - cs;
+    const uint64_t base           = tf_elems + (cs == 1 ? m_partm_total[0] : 0u);
+    m_partm_off[cs].assign(n_pieces_total, kDirect);
+    side[cs].partm_base = base;
+    uint64_t off        = 0;
+    for (int64_t i = 0; i < n_leaves; i++) {
+        const htb_leaf &l = m_leaves[i];
+        if (!active(l) || (l.rank < 0 && cs == 0)) // dense leaves, direction 0: x rows are read from the input directly
+            continue;
+        const int n_prod = m_nchunks[ps][i];
+        if (n_prod <= 1)
+            continue;
+        for (int p = 0; p < n_pieces(l); p++) {
+            const int len                       = piece_len(l, p);
+            m_partm_off[cs][m_piece_ptr[i] + p] = static_cast<uint32_t>(base + off);
+            side[cs].combine_m.push_back(CombineEntry{static_cast<uint32_t>(base + off), m_tf_off[m_piece_ptr[i] + p], 0u,
+                                                      static_cast<uint32_t>(n_prod) | (static_cast<uint32_t>(len) << 24) | ((l.flags & HTB_LEAF_APPLY_TRANSPOSED_TOO) ? 0x80000000u : 0u)});
+            off += static_cast<uint64_t>(n_prod) * len;
         }
-        side[cs].partm_elems = off;
-        if (off != partm_total[cs])
-            throw std::runtime_error("internal: size of a multi-RHS partial area");
-    });
-    const uint64_t base = tf + partm_total[0] + partm_total[1];
+    }
+    side[cs].partm_elems = off;
+    if (off != m_partm_total[cs])
+        throw std::runtime_error("internal: size of a multi-RHS partial area");
+}
+
+void Packer::make_mtables() {
+    const bool mt_timing = std::getenv("HTB_PACK_TIMING") != nullptr;
+    auto mt_last         = std::chrono::steady_clock::now();
     auto mt_lap          = [&](const char *what) {
         if (!mt_timing)
             return;
@@ -630,7 +649,7 @@ void Packer::make_mtables() {
         std::fprintf(stderr, "[htb pack]   mtables %-18s %.3f s\n", what, std::chrono::duration<double>(now - mt_last).count());
         mt_last = now;
     };
-    mt_lap("tf / partm");
+    const uint64_t base = tf_elems + m_partm_total[0] + m_partm_total[1]; // (make_tf, make_partm: run by the constructor beside the other serial passes)
     mscratch_elems = base;
     if (mscratch_elems >= (uint64_t(1) << 31))
         throw std::runtime_error("multi-RHS scratch exceeds 2^31 vectors");

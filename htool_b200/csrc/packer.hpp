@@ -87,7 +87,11 @@ class Packer {
     void make_blocks(int s);
     void make_incidence_lists(int s);
     void make_incidence(int s);
-    void make_partials();
+    void make_partials(int cs);
+    void make_tf();
+    void make_partm_sizes();
+    void make_partm(int cs);
+    uint64_t m_partm_total[2] = {0, 0};
     void make_combine(int cs);
     void make_mtables();
     std::vector<uint32_t> m_partm_off[2]; // [consumer side] per global piece: PARTM offset (vectors) or kDirect
