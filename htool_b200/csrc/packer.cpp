@@ -176,7 +176,8 @@ Packer::Packer(const htb_hmatrix_desc &desc, const PackOptions &o) : dtype(desc.
     side[1].n = nb_cols;
     both_sides([&](int s) { make_blocks(s); });
     lap("make_blocks");
-    both_sides([&](int s) { make_incidence_lists(s); });
+    for (int s = 0; s < 2; s++)
+        make_incidence_lists(s);
     lap("incidence lists");
     for (int s = 0; s < 2; s++)
         make_incidence(s);
@@ -413,38 +414,78 @@ int Packer::units_in_incidence(int s, uint32_t li, int c) const {
     return n_pieces(l);
 }
 
-// Serial part of the incidence structure of side s (which leaf meets which block, block-major, leaf order kept inside a
-// block): independent for the two sides, run concurrently (both_sides).
+// The incidence structure of side s: which leaf meets which block, block-major, leaf order kept inside a block.
 void Packer::make_incidence_lists(int s) {
     const int nb = static_cast<int>(side[s].blocks.size());
     m_first_blk[s].assign(n_leaves, 0);
     m_nchunks[s].assign(n_leaves, 0);
     m_chunk_ptr[s].assign(n_leaves + 1, 0);
     m_csr_ptr[s].assign(static_cast<size_t>(nb) + 1, 0);
-    for (int64_t i = 0; i < n_leaves; i++) {
-        const htb_leaf &l = m_leaves[i];
-        if (active(l)) {
-            int a = start_of(s, l), len = extent_of(s, l);
-            int b0 = m_blk_of[s][a], b1 = m_blk_of[s][a + len - 1];
+    // A counting sort of the (leaf, block) incidences by block, in parallel over contiguous ranges of the leaf list: thread t
+    // counts its range per block, the counts are scanned block-major then thread-major, and every thread scatters its range
+    // from its own cursors — inside a block the leaves of thread t follow those of thread t - 1, i.e. leaf order is kept
+    // exactly as a serial pass would keep it (fixed summation order, whatever the number of threads).
+#ifdef _OPENMP
+    const int max_threads = std::max(1, omp_get_max_threads());
+#else
+    const int max_threads = 1;
+#endif
+    std::vector<std::vector<uint64_t>> cursor(max_threads);
+    std::vector<uint64_t> chunks_before(static_cast<size_t>(max_threads) + 1, 0);
+#pragma omp parallel num_threads(max_threads)
+    {
+#ifdef _OPENMP
+        const int t = omp_get_thread_num(), nt = omp_get_num_threads();
+#else
+        const int t = 0, nt = 1;
+#endif
+        const int64_t lo = n_leaves * t / nt, hi = n_leaves * (t + 1) / nt;
+        std::vector<uint64_t> &cnt = cursor[t];
+        cnt.assign(nb, 0);
+        uint64_t my_chunks = 0;
+        for (int64_t i = lo; i < hi; i++) {
+            const htb_leaf &l = m_leaves[i];
+            if (!active(l))
+                continue;
+            const int a = start_of(s, l), len = extent_of(s, l);
+            const int b0 = m_blk_of[s][a], b1 = m_blk_of[s][a + len - 1];
             m_first_blk[s][i] = b0;
             m_nchunks[s][i]   = b1 - b0 + 1;
+            my_chunks += static_cast<uint64_t>(b1 - b0 + 1);
             for (int b = b0; b <= b1; b++)
-                m_csr_ptr[s][b + 1]++;
+                cnt[b]++;
         }
-        m_chunk_ptr[s][i + 1] = m_chunk_ptr[s][i] + m_nchunks[s][i];
+        chunks_before[t + 1] = my_chunks;
+#pragma omp barrier
+#pragma omp single
+        {
+            for (int u = 0; u < nt; u++)
+                chunks_before[u + 1] += chunks_before[u];
+            m_chunk_ptr[s][n_leaves] = chunks_before[nt];
+            uint64_t at = 0;
+            for (int b = 0; b < nb; b++) {
+                m_csr_ptr[s][b] = at;
+                for (int u = 0; u < nt; u++) { // count -> first position of thread u's leaves inside block b
+                    const uint64_t c = cursor[u][b];
+                    cursor[u][b]     = at;
+                    at += c;
+                }
+            }
+            m_csr_ptr[s][nb] = at;
+            m_csr_leaf[s].resize(at); // (default-initialised: every incidence is written exactly once below)
+            m_inc_index[s].resize(at);
+        } // (implicit barrier)
+        uint64_t run = chunks_before[t];
+        for (int64_t i = lo; i < hi; i++) {
+            m_chunk_ptr[s][i] = run;
+            for (int c = 0; c < m_nchunks[s][i]; c++) {
+                const uint64_t e         = cnt[m_first_blk[s][i] + c]++;
+                m_csr_leaf[s][e]         = static_cast<uint32_t>(i);
+                m_inc_index[s][run + c] = e;
+            }
+            run += static_cast<uint64_t>(m_nchunks[s][i]);
+        }
     }
-    for (int b = 0; b < nb; b++)
-        m_csr_ptr[s][b + 1] += m_csr_ptr[s][b];
-    const uint64_t n_inc = m_csr_ptr[s][nb];
-    m_csr_leaf[s].assign(n_inc, 0);
-    m_inc_index[s].assign(n_inc, 0);
-    std::vector<uint64_t> cursor(m_csr_ptr[s].begin(), m_csr_ptr[s].end() - 1);
-    for (int64_t i = 0; i < n_leaves; i++) // leaf order is kept inside every block: fixed summation order
-        for (int c = 0; c < m_nchunks[s][i]; c++) {
-            const uint64_t e                      = cursor[m_first_blk[s][i] + c]++;
-            m_csr_leaf[s][e]                      = static_cast<uint32_t>(i);
-            m_inc_index[s][m_chunk_ptr[s][i] + c] = e;
-        }
 }
 
 // Parallel part: order of the incidences inside every block, unit counts.

@@ -55,9 +55,9 @@ class Packer {
     std::vector<int32_t> m_first_blk[2];   // per leaf: first block it touches on side s
     std::vector<int32_t> m_nchunks[2];     // per leaf: number of blocks it touches on side s (0: leaf holds nothing)
     std::vector<uint64_t> m_chunk_ptr[2];  // per leaf: prefix sum of m_nchunks (n_leaves + 1)
-    std::vector<uint64_t> m_inc_index[2];  // per (leaf, chunk): position of the incidence in m_csr_leaf
+    RawVector<uint64_t> m_inc_index[2];    // per (leaf, chunk): position of the incidence in m_csr_leaf
     std::vector<uint64_t> m_csr_ptr[2];    // nblocks + 1
-    std::vector<uint32_t> m_csr_leaf[2];   // incidences (leaf ids), block-major, leaf order inside a block
+    RawVector<uint32_t> m_csr_leaf[2];     // incidences (leaf ids), block-major, leaf order inside a block
     std::vector<uint64_t> m_unit_ptr[2];   // per incidence: first unit index (n_incidences + 1)
     RawVector<uint32_t> m_unit_slot[2];    // per unit: scratch offset of its c slot
     RawVector<uint16_t> m_unit_cslot[2];   // per unit: offset of its c slot inside its stage's c segment
